@@ -1,0 +1,661 @@
+"""Minimal pure-Python HDF5 reader/writer for the two on-disk layouts of the
+matrix-correction path: HiCExplorer ``.h5`` (PyTables CArrays, Blosc/blosclz)
+and ``.cool`` (h5py, deflate+shuffle).
+
+Why this exists: the reference reads and writes its matrices through the
+third-party ``hicmatrix`` package (PyTables / cooler / h5py; call sites
+``hicexplorer/hicCorrectMatrix.py:603-609, 779``), none of which is available
+on the build or GPU boxes.  The layout contract is
+``docs/content/file-formats.rst:9-147`` of the reference.  Only the subset of
+HDF5 those files use is implemented:
+
+* superblock v0, object header v1 (+continuation blocks), old-style groups
+  (symbol-table B-tree v1 + local heap),
+* dataspace v1/v2, datatypes fixed-point / IEEE float / fixed string / enum,
+* layout v3 contiguous / chunked (B-tree v1) / compact,
+* filters: deflate (1), shuffle (2), Blosc (32001, blosclz/zlib codecs,
+  byte-shuffle), fletcher32 (3, checksum ignored),
+* attributes v1/v2/v3 with fixed-size types (variable-length strings are
+  returned as ``None``).
+
+The writer emits uncompressed contiguous datasets with PyTables-compatible
+cosmetic attributes so that generic HDF5 libraries (h5py, PyTables, cooler)
+can open the result.
+
+This is host-side I/O, not part of the device hot path.
+"""
+import struct
+import zlib
+
+import numpy as np
+
+_SIG = b"\x89HDF\r\n\x1a\n"
+_UNDEF = 0xFFFFFFFFFFFFFFFF
+
+
+# --------------------------------------------------------------------------
+# Blosc-1 container / blosclz codec (decode only)
+# --------------------------------------------------------------------------
+def _blosclz_decompress(src, maxout):
+    """FastLZ-style decoder used by Blosc's ``blosclz`` codec."""
+    out = bytearray(maxout)
+    ip = 0
+    n = len(src)
+    op = 0
+    ctrl = src[ip] & 31
+    ip += 1
+    while True:
+        if ctrl >= 32:
+            length = (ctrl >> 5) - 1
+            ofs = (ctrl & 31) << 8
+            if length == 6:
+                while True:
+                    code = src[ip]
+                    ip += 1
+                    length += code
+                    if code != 255:
+                        break
+            code = src[ip]
+            ip += 1
+            ref = op - ofs - code
+            if code == 255 and ofs == (31 << 8):
+                ofs = (src[ip] << 8) + src[ip + 1]
+                ip += 2
+                ref = op - ofs - 8191
+            more = ip < n
+            if more:
+                ctrl = src[ip]
+                ip += 1
+            length += 3
+            ref -= 1
+            if ref < 0:
+                raise ValueError("blosclz: bad back-reference")
+            dist = op - ref
+            if dist >= length:
+                out[op:op + length] = out[ref:ref + length]
+            else:
+                # overlapping copy == periodic repetition of the last `dist` bytes
+                pat = bytes(out[ref:op])
+                reps = (length + dist - 1) // dist
+                out[op:op + length] = (pat * reps)[:length]
+            op += length
+            if not more:
+                break
+        else:
+            ctrl += 1
+            out[op:op + ctrl] = src[ip:ip + ctrl]
+            op += ctrl
+            ip += ctrl
+            if ip >= n:
+                break
+            ctrl = src[ip]
+            ip += 1
+    return bytes(out[:op])
+
+
+def _unshuffle(buf, typesize):
+    n = len(buf)
+    if typesize <= 1 or n < typesize:
+        return bytes(buf)
+    nelem = n // typesize
+    body = np.frombuffer(buf, dtype=np.uint8, count=nelem * typesize)
+    body = body.reshape(typesize, nelem).T.tobytes()
+    return body + bytes(buf[nelem * typesize:])
+
+
+def _blosc_decompress(chunk):
+    version, versionlz, flags, typesize = struct.unpack_from("<BBBB", chunk, 0)
+    nbytes, blocksize, cbytes = struct.unpack_from("<III", chunk, 4)
+    if flags & 0x2:  # memcpyed
+        return bytes(chunk[16:16 + nbytes])
+    codec = flags >> 5
+    doshuffle = bool(flags & 0x1)
+    if flags & 0x4:
+        raise NotImplementedError("blosc bit-shuffle")
+    dont_split = bool(flags & 0x10)
+    nblocks = (nbytes + blocksize - 1) // blocksize if blocksize else 0
+    bstarts = struct.unpack_from("<%di" % nblocks, chunk, 16)
+    out = bytearray()
+    for b in range(nblocks):
+        bsize = min(blocksize, nbytes - b * blocksize)
+        leftover = bsize != blocksize
+        split = (not dont_split and not leftover and typesize <= 16
+                 and blocksize // typesize >= 128)
+        nsplits = typesize if split else 1
+        neblock = bsize // nsplits
+        pos = bstarts[b]
+        blk = bytearray()
+        for _ in range(nsplits):
+            (csize,) = struct.unpack_from("<i", chunk, pos)
+            pos += 4
+            raw = chunk[pos:pos + csize]
+            pos += csize
+            if csize == neblock:
+                blk += raw
+            elif codec == 0:
+                blk += _blosclz_decompress(raw, neblock)
+            elif codec == 3:
+                blk += zlib.decompress(raw)
+            else:
+                raise NotImplementedError("blosc codec %d" % codec)
+        if doshuffle:
+            blk = _unshuffle(blk, typesize)
+        out += blk
+    return bytes(out[:nbytes])
+
+
+# --------------------------------------------------------------------------
+# Reader
+# --------------------------------------------------------------------------
+class _Dataset(object):
+    def __init__(self, f, msgs):
+        self._f = f
+        self.attrs = {}
+        self.shape = ()
+        self.dtype = None
+        self._layout = None
+        self._filters = []
+        self._enum = None
+        for mtype, body in msgs:
+            if mtype == 0x01:
+                self.shape = _parse_dataspace(body)
+            elif mtype == 0x03:
+                self.dtype, self._enum, _ = _parse_datatype(body, 0)
+            elif mtype == 0x08:
+                self._layout = body
+            elif mtype == 0x0B:
+                self._filters = _parse_filters(body)
+            elif mtype == 0x0C:
+                k, v = _parse_attribute(body)
+                self.attrs[k] = v
+
+    @property
+    def enum(self):
+        """dict name -> value for enum datasets (cooler ``bins/chrom``)."""
+        return self._enum
+
+    def read(self):
+        buf = self._f._buf
+        lay = self._layout
+        ver = lay[0]
+        if ver != 3:
+            raise NotImplementedError("layout version %d" % ver)
+        cls = lay[1]
+        count = int(np.prod(self.shape, dtype=np.int64)) if len(self.shape) else 1
+        itemsize = self.dtype.itemsize
+        if cls == 0:  # compact
+            (size,) = struct.unpack_from("<H", lay, 2)
+            raw = lay[4:4 + size]
+            return np.frombuffer(raw, dtype=self.dtype, count=count).reshape(self.shape).copy()
+        if cls == 1:  # contiguous
+            addr, size = struct.unpack_from("<QQ", lay, 2)
+            if addr == _UNDEF:
+                return np.zeros(self.shape, dtype=self.dtype)
+            return np.frombuffer(buf, dtype=self.dtype, count=count, offset=addr).reshape(self.shape).copy()
+        if cls != 2:
+            raise NotImplementedError("layout class %d" % cls)
+        ndims = lay[2]
+        (btree,) = struct.unpack_from("<Q", lay, 3)
+        cdims = struct.unpack_from("<%dI" % ndims, lay, 11)
+        chunk_shape = cdims[:-1]
+        out = np.zeros(self.shape, dtype=self.dtype)
+        if btree == _UNDEF or count == 0:
+            return out
+        chunk_bytes = int(np.prod(chunk_shape, dtype=np.int64)) * itemsize
+        for size, fmask, offs, addr in self._f._iter_chunks(btree, ndims):
+            raw = buf[addr:addr + size]
+            for i in range(len(self._filters) - 1, -1, -1):
+                if fmask & (1 << i):
+                    continue
+                fid, cd = self._filters[i]
+                if fid == 1:
+                    raw = zlib.decompress(raw)
+                elif fid == 2:
+                    raw = _unshuffle(raw, cd[0] if cd else itemsize)
+                elif fid == 3:
+                    raw = raw[:-4]
+                elif fid == 32001:
+                    raw = _blosc_decompress(raw)
+                else:
+                    raise NotImplementedError("HDF5 filter %d" % fid)
+            if len(raw) < chunk_bytes:
+                raise ValueError("short chunk")
+            arr = np.frombuffer(raw, dtype=self.dtype, count=chunk_bytes // itemsize).reshape(chunk_shape)
+            sl_out = []
+            sl_in = []
+            for d in range(len(chunk_shape)):
+                lo = offs[d]
+                hi = min(lo + chunk_shape[d], self.shape[d])
+                sl_out.append(slice(lo, hi))
+                sl_in.append(slice(0, hi - lo))
+            out[tuple(sl_out)] = arr[tuple(sl_in)]
+        return out
+
+    def __getitem__(self, key):
+        return self.read()[key]
+
+
+class _Group(object):
+    def __init__(self, f, msgs):
+        self._f = f
+        self.attrs = {}
+        self._links = {}
+        for mtype, body in msgs:
+            if mtype == 0x11:
+                btree, heap = struct.unpack_from("<QQ", body, 0)
+                self._links = f._read_symbol_table(btree, heap)
+            elif mtype == 0x0C:
+                k, v = _parse_attribute(body)
+                self.attrs[k] = v
+
+    def keys(self):
+        return list(self._links)
+
+    def __contains__(self, name):
+        try:
+            self[name]
+            return True
+        except KeyError:
+            return False
+
+    def __getitem__(self, path):
+        node = self
+        for part in [p for p in path.split("/") if p]:
+            if not isinstance(node, _Group) or part not in node._links:
+                raise KeyError(path)
+            node = node._f._open(node._links[part])
+        return node
+
+
+class File(_Group):
+    """Read-only view of an HDF5 file: ``File(path)['matrix/data'].read()``."""
+
+    def __init__(self, path):
+        with open(path, "rb") as fh:
+            self._buf = fh.read()
+        buf = self._buf
+        if buf[:8] != _SIG:
+            raise ValueError("%s is not an HDF5 file" % path)
+        if buf[8] != 0 or buf[13] != 8 or buf[14] != 8:
+            raise NotImplementedError("only HDF5 superblock v0 with 8-byte offsets is supported")
+        (root_hdr,) = struct.unpack_from("<Q", buf, 56 + 8)
+        self._cache = {}
+        _Group.__init__(self, self, self._read_object_header(root_hdr))
+
+    # -- low level ----------------------------------------------------------
+    def _read_object_header(self, addr):
+        buf = self._buf
+        version = buf[addr]
+        if version != 1:
+            raise NotImplementedError("object header version %d" % version)
+        (nmsgs,) = struct.unpack_from("<H", buf, addr + 2)
+        (hsize,) = struct.unpack_from("<I", buf, addr + 8)
+        blocks = [(addr + 16, hsize)]
+        msgs = []
+        while blocks and len(msgs) < nmsgs:
+            pos, size = blocks.pop(0)
+            end = pos + size
+            while pos + 8 <= end and len(msgs) < nmsgs:
+                mtype, msize, _flags = struct.unpack_from("<HHB", buf, pos)
+                body = buf[pos + 8:pos + 8 + msize]
+                pos += 8 + msize
+                if mtype == 0x10:
+                    off, length = struct.unpack_from("<QQ", body, 0)
+                    blocks.append((off, length))
+                msgs.append((mtype, body))
+        return msgs
+
+    def _open(self, addr):
+        if addr not in self._cache:
+            msgs = self._read_object_header(addr)
+            types = set(m[0] for m in msgs)
+            if 0x11 in types:
+                self._cache[addr] = _Group(self, msgs)
+            elif 0x08 in types:
+                self._cache[addr] = _Dataset(self, msgs)
+            else:
+                raise NotImplementedError("unsupported HDF5 object (new-style group?)")
+        return self._cache[addr]
+
+    def _read_symbol_table(self, btree, heap):
+        buf = self._buf
+        if buf[heap:heap + 4] != b"HEAP":
+            raise ValueError("bad local heap")
+        (data_seg,) = struct.unpack_from("<Q", buf, heap + 24)
+        links = {}
+
+        def walk(node):
+            if buf[node:node + 4] == b"TREE":
+                level = buf[node + 5]
+                (nent,) = struct.unpack_from("<H", buf, node + 6)
+                pos = node + 24
+                for _ in range(nent):
+                    (child,) = struct.unpack_from("<Q", buf, pos + 8)
+                    pos += 16
+                    walk(child)
+                del level
+            elif buf[node:node + 4] == b"SNOD":
+                (nsym,) = struct.unpack_from("<H", buf, node + 6)
+                pos = node + 8
+                for _ in range(nsym):
+                    name_off, hdr = struct.unpack_from("<QQ", buf, pos)
+                    pos += 40
+                    s = data_seg + name_off
+                    e = buf.index(b"\x00", s)
+                    links[buf[s:e].decode("utf-8")] = hdr
+            else:
+                raise ValueError("bad group node")
+
+        walk(btree)
+        return links
+
+    def _iter_chunks(self, node, ndims):
+        buf = self._buf
+        if buf[node:node + 4] != b"TREE":
+            raise ValueError("bad chunk B-tree node")
+        level = buf[node + 5]
+        (nent,) = struct.unpack_from("<H", buf, node + 6)
+        pos = node + 24
+        keysize = 8 + 8 * ndims
+        for _ in range(nent):
+            size, fmask = struct.unpack_from("<II", buf, pos)
+            offs = struct.unpack_from("<%dQ" % ndims, buf, pos + 8)
+            (child,) = struct.unpack_from("<Q", buf, pos + keysize)
+            pos += keysize + 8
+            if level == 0:
+                yield size, fmask, offs, child
+            else:
+                for item in self._iter_chunks(child, ndims):
+                    yield item
+
+
+def _parse_dataspace(body):
+    version, rank, flags = body[0], body[1], body[2]
+    if version == 1:
+        pos = 8
+    elif version == 2:
+        pos = 4
+        if body[3] == 2:  # null dataspace
+            return (0,)
+    else:
+        raise NotImplementedError("dataspace version %d" % version)
+    return tuple(struct.unpack_from("<%dQ" % rank, body, pos))
+
+
+def _parse_datatype(body, pos):
+    """Returns (numpy dtype, enum-dict-or-None, bytes consumed)."""
+    cv = body[pos]
+    cls, version = cv & 0x0F, cv >> 4
+    bits0 = body[pos + 1]
+    bits = bits0 | (body[pos + 2] << 8) | (body[pos + 3] << 16)
+    (size,) = struct.unpack_from("<I", body, pos + 4)
+    p = pos + 8
+    if cls == 0:
+        order = ">" if bits0 & 1 else "<"
+        kind = "i" if bits0 & 8 else "u"
+        return np.dtype("%s%s%d" % (order, kind, size)), None, p + 4 - pos
+    if cls == 1:
+        order = ">" if bits0 & 1 else "<"
+        return np.dtype("%sf%d" % (order, size)), None, p + 12 - pos
+    if cls == 3:
+        return np.dtype("S%d" % size), None, p - pos
+    if cls == 8:
+        nmemb = bits & 0xFFFF
+        base, _, used = _parse_datatype(body, p)
+        p += used
+        names = []
+        for _ in range(nmemb):
+            e = body.index(b"\x00", p)
+            names.append(body[p:e].decode("utf-8"))
+            ln = e - p + 1
+            if version < 3:
+                ln = (ln + 7) // 8 * 8
+            p += ln
+        vals = np.frombuffer(body, dtype=base, count=nmemb, offset=p)
+        p += nmemb * base.itemsize
+        return base, dict(zip(names, [int(v) for v in vals])), p - pos
+    if cls == 9:
+        return np.dtype("V%d" % size), None, None
+    if cls == 6:
+        return np.dtype("V%d" % size), None, None
+    raise NotImplementedError("datatype class %d" % cls)
+
+
+def _parse_filters(body):
+    version, nfilt = body[0], body[1]
+    pos = 8 if version == 1 else 2
+    out = []
+    for _ in range(nfilt):
+        (fid,) = struct.unpack_from("<H", body, pos)
+        pos += 2
+        if version == 1 or fid >= 256:
+            (nlen,) = struct.unpack_from("<H", body, pos)
+            pos += 2
+        else:
+            nlen = 0
+        _flags, ncd = struct.unpack_from("<HH", body, pos)
+        pos += 4
+        if version == 1:
+            nlen = (nlen + 7) // 8 * 8
+        pos += nlen
+        cd = struct.unpack_from("<%dI" % ncd, body, pos)
+        pos += 4 * ncd
+        if version == 1 and ncd % 2:
+            pos += 4
+        out.append((fid, cd))
+    return out
+
+
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+def _parse_attribute(body):
+    version = body[0]
+    nlen, tlen, slen = struct.unpack_from("<HHH", body, 2)
+    pos = 8
+    if version == 3:
+        pos += 1
+    name = body[pos:pos + nlen].split(b"\x00")[0].decode("utf-8", "replace")
+    if version == 1:
+        pos += _pad8(nlen)
+        tbody = body[pos:pos + tlen]
+        pos += _pad8(tlen)
+        sbody = body[pos:pos + slen]
+        pos += _pad8(slen)
+    else:
+        pos += nlen
+        tbody = body[pos:pos + tlen]
+        pos += tlen
+        sbody = body[pos:pos + slen]
+        pos += slen
+    try:
+        dt, _enum, used = _parse_datatype(tbody, 0)
+        if used is None:
+            return name, None
+        shape = _parse_dataspace(sbody)
+        count = int(np.prod(shape, dtype=np.int64)) if len(shape) else 1
+        arr = np.frombuffer(body, dtype=dt, count=count, offset=pos)
+        if dt.kind == "S":
+            vals = [v.split(b"\x00")[0].decode("utf-8", "replace") for v in arr.tolist()]
+            return name, (vals[0] if len(shape) == 0 else vals)
+        if len(shape) == 0:
+            return name, arr[0].item()
+        return name, arr.reshape(shape).copy()
+    except (NotImplementedError, ValueError, struct.error):
+        return name, None
+
+
+# --------------------------------------------------------------------------
+# Writer (superblock v0, old-style groups, contiguous datasets)
+# --------------------------------------------------------------------------
+def _dtype_message(dt):
+    dt = np.dtype(dt)
+    if dt.kind in "iu":
+        bits0 = 0x08 if dt.kind == "i" else 0x00
+        return struct.pack("<BBBBI", 0x10, bits0, 0, 0, dt.itemsize) + struct.pack("<HH", 0, dt.itemsize * 8)
+    if dt.kind == "f":
+        if dt.itemsize == 8:
+            return (struct.pack("<BBBBI", 0x11, 0x20, 63, 0, 8)
+                    + struct.pack("<HHBBBBI", 0, 64, 52, 11, 0, 52, 1023))
+        if dt.itemsize == 4:
+            return (struct.pack("<BBBBI", 0x11, 0x20, 31, 0, 4)
+                    + struct.pack("<HHBBBBI", 0, 32, 23, 8, 0, 23, 127))
+    if dt.kind == "S":
+        # null-padded ASCII fixed string
+        return struct.pack("<BBBBI", 0x13, 0x01, 0, 0, dt.itemsize)
+    if dt.kind == "b":
+        return _dtype_message(np.uint8)
+    raise NotImplementedError("cannot write dtype %r" % dt)
+
+
+def _dataspace_message(shape):
+    if shape is None:  # scalar
+        return struct.pack("<BBBB4x", 1, 0, 0, 0)
+    rank = len(shape)
+    return struct.pack("<BBBB4x", 1, rank, 0, 0) + struct.pack("<%dQ" % rank, *shape)
+
+
+def _message(mtype, body, flags=0):
+    body = body + b"\x00" * (_pad8(len(body)) - len(body))
+    return struct.pack("<HHB3x", mtype, len(body), flags) + body
+
+
+def _attr_message(name, value):
+    if isinstance(value, str):
+        value = value.encode("utf-8")
+    if isinstance(value, bytes):
+        arr = np.array(value + b"\x00", dtype="S%d" % (len(value) + 1))
+        shape = None
+    else:
+        arr = np.asarray(value)
+        shape = None if arr.ndim == 0 else arr.shape
+        if arr.dtype.kind == "U":
+            arr = arr.astype("S")
+        if arr.dtype == np.bool_:
+            arr = arr.astype(np.uint8)
+    nm = name.encode("utf-8") + b"\x00"
+    t = _dtype_message(arr.dtype)
+    s = _dataspace_message(shape)
+    body = struct.pack("<BxHHH", 1, len(nm), len(t), len(s))
+    body += nm + b"\x00" * (_pad8(len(nm)) - len(nm))
+    body += t + b"\x00" * (_pad8(len(t)) - len(t))
+    body += s + b"\x00" * (_pad8(len(s)) - len(s))
+    body += arr.tobytes()
+    return _message(0x0C, body)
+
+
+class Writer(object):
+    """Build an HDF5 file in memory: ``w = Writer(); w.group('/matrix', attrs);
+    w.dataset('/matrix/data', array, attrs); w.save(path)``."""
+
+    def __init__(self, root_attrs=None):
+        self._tree = {"attrs": dict(root_attrs or {}), "children": {}, "data": None}
+
+    def _node(self, path, create=True):
+        node = self._tree
+        for part in [p for p in path.split("/") if p]:
+            if part not in node["children"]:
+                if not create:
+                    raise KeyError(path)
+                node["children"][part] = {"attrs": {}, "children": {}, "data": None}
+            node = node["children"][part]
+        return node
+
+    def group(self, path, attrs=None):
+        node = self._node(path)
+        node["attrs"].update(attrs or {})
+
+    def dataset(self, path, array, attrs=None):
+        node = self._node(path)
+        arr = np.ascontiguousarray(array)
+        if arr.dtype.kind == "U":
+            arr = arr.astype("S")
+        if arr.dtype.byteorder == ">":
+            arr = arr.astype(arr.dtype.newbyteorder("<"))
+        node["data"] = arr
+        node["attrs"].update(attrs or {})
+
+    def save(self, path):
+        out = bytearray(b"\x00" * 96)  # superblock placeholder
+
+        def alloc(blob):
+            while len(out) % 8:
+                out.append(0)
+            addr = len(out)
+            out.extend(blob)
+            return addr
+
+        def write_object_header(msgs):
+            body = b"".join(msgs)
+            hdr = struct.pack("<BxHII4x", 1, len(msgs), 1, len(body))
+            return alloc(hdr + body)
+
+        def write_dataset(node):
+            arr = node["data"]
+            raw = arr.tobytes()
+            daddr = alloc(raw) if len(raw) else _UNDEF
+            shape = arr.shape if arr.ndim else None
+            msgs = [
+                _message(0x01, _dataspace_message(shape)),
+                _message(0x03, _dtype_message(arr.dtype), flags=1),
+                _message(0x05, struct.pack("<BBBB", 2, 2, 2, 0x02)),  # fill value: never written
+                _message(0x08, struct.pack("<BBQQ", 3, 1, daddr, len(raw))),
+            ]
+            for k, v in node["attrs"].items():
+                msgs.append(_attr_message(k, v))
+            return write_object_header(msgs)
+
+        def write_group(node):
+            names = sorted(node["children"], key=lambda s: s.encode("utf-8"))
+            child_addr = {}
+            for nm in names:
+                ch = node["children"][nm]
+                child_addr[nm] = write_dataset(ch) if ch["data"] is not None else write_group(ch)[0]
+            # local heap: offset 0 holds the empty string
+            heap_data = bytearray(b"\x00" * 8)
+            name_off = {}
+            for nm in names:
+                name_off[nm] = len(heap_data)
+                enc = nm.encode("utf-8") + b"\x00"
+                heap_data += enc + b"\x00" * (_pad8(len(enc)) - len(enc))
+            free_off = len(heap_data)
+            heap_data += struct.pack("<QQ", 1, 16)  # free block: next=1 (none), size 16
+            seg_addr = alloc(bytes(heap_data))
+            heap_addr = alloc(b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap_data), free_off, seg_addr))
+            # symbol nodes: at most 2K = 8 entries each with leaf K = 4
+            leaf_k = 4
+            per = 2 * leaf_k
+            snods = []
+            for i in range(0, max(len(names), 1), per):
+                part = names[i:i + per]
+                blob = bytearray(b"SNOD" + struct.pack("<BxH", 1, len(part)))
+                for nm in part:
+                    blob += struct.pack("<QQII16x", name_off[nm], child_addr[nm], 0, 0)
+                blob += b"\x00" * (8 + 40 * per - len(blob))
+                snods.append((alloc(bytes(blob)), name_off[part[-1]] if part else 0))
+            internal_k = 16
+            if len(snods) > 2 * internal_k:
+                raise NotImplementedError("too many links in one group")
+            blob = bytearray(b"TREE" + struct.pack("<BBHQQ", 0, 0, len(snods), _UNDEF, _UNDEF))
+            blob += struct.pack("<Q", 0)
+            for addr, last_off in snods:
+                blob += struct.pack("<QQ", addr, last_off)
+            blob += b"\x00" * (24 + 8 + 16 * 2 * internal_k - len(blob))
+            btree_addr = alloc(bytes(blob))
+            msgs = [_message(0x11, struct.pack("<QQ", btree_addr, heap_addr))]
+            for k, v in node["attrs"].items():
+                msgs.append(_attr_message(k, v))
+            return write_object_header(msgs), btree_addr, heap_addr
+
+        root_hdr, root_btree, root_heap = write_group(self._tree)
+        eof = len(out)
+        sb = bytearray()
+        sb += _SIG
+        sb += struct.pack("<BBBBBBBB", 0, 0, 0, 0, 0, 8, 8, 0)
+        sb += struct.pack("<HHI", 4, 16, 0)
+        sb += struct.pack("<QQQQ", 0, _UNDEF, eof, _UNDEF)
+        sb += struct.pack("<QQII", 0, root_hdr, 1, 0) + struct.pack("<QQ", root_btree, root_heap)
+        out[0:len(sb)] = sb
+        with open(path, "wb") as fh:
+            fh.write(bytes(out))

@@ -1,0 +1,131 @@
+"""Pin the CPU oracle (oracle/) against the reference's golden vectors and,
+where /root/reference is present, against the reference functions themselves."""
+import numpy as np
+import pytest
+from scipy import sparse
+
+from oracle import ice_oracle, kr_oracle, ref_import
+from tests.helpers import csr_from_npz, full_from_pixels, random_hic
+
+
+def test_ice_pipeline_reproduces_reference_golden_file_bit_exact(small_ice):
+    z = small_ice
+    full = csr_from_npz(z, "in")
+    res = ice_oracle.correct_ice_pipeline(full, -1.5, 5.0, max_iter=500)
+    assert np.array_equal(res["zero_bins"], z["zero_bins"])
+    assert np.array_equal(res["outliers_rel"], z["outliers_rel"])
+    assert len(res["outliers_rel"]) == 64  # filtered.bed has 64 lines
+    assert res["ice"]["iterations"] == 500  # 59 empty rows pin the deviation at 1
+    # the reference's golden output file, bit for bit
+    assert np.array_equal(res["upper"].data, z["golden_data"])
+    assert np.array_equal(res["upper"].indices, z["golden_indices"])
+    assert np.array_equal(res["upper"].indptr, z["golden_indptr"])
+    assert np.array_equal(res["nan_bins"], z["golden_nan_bins"])
+    np.testing.assert_array_equal(res["correction_factors"], z["golden_correction_factors"])  # NaN-aware
+
+
+def test_filtered_bed_lists_the_outlier_bins(small_ice):
+    z = small_ice
+    full = csr_from_npz(z, "in")
+    res = ice_oracle.correct_ice_pipeline(full, -1.5, 5.0, max_iter=1)
+    want = set()
+    for ln in str(z["filtered_bed"]).splitlines():
+        c, s, e = ln.split("\t")[:3]
+        want.add((c, int(s), int(e)))
+    got = set((z["chr"][i].decode(), int(z["start"][i]), int(z["end"][i])) for i in res["outliers_abs"])
+    assert got == want
+
+
+def test_mad_scores_match_reference_values(small_ice, gm12878):
+    z = small_ice
+    full = csr_from_npz(z, "in")
+    keep = np.setdiff1d(np.arange(full.shape[0]), z["zero_bins"])
+    st1 = ice_oracle.scrub(ice_oracle.select_bins(full, keep))
+    mad = ice_oracle.MadScores(ice_oracle.coverage_points(st1))
+    assert mad.median == float(z["mad_median"]) and mad.mad == float(z["mad_mad"])
+    np.testing.assert_array_equal(mad.z, z["zscore"])
+    g = gm12878
+    fullg = full_from_pixels(g)
+    keep = np.setdiff1d(np.arange(fullg.shape[0]), g["zero_bins"])
+    st1 = ice_oracle.scrub(ice_oracle.select_bins(fullg, keep))
+    np.testing.assert_array_equal(ice_oracle.MadScores(ice_oracle.coverage_points(st1)).z, g["zscore"])
+    ranges = list(zip(g["chr_lo"].tolist(), g["chr_hi"].tolist()))
+    assert np.array_equal(ice_oracle.outlier_bins(st1, -1.5, 5.0, ranges), g["outliers_rel_perchr"])
+
+
+def test_ice_gm12878_matches_reference_run(gm12878):
+    g = gm12878
+    res = ice_oracle.correct_ice_pipeline(full_from_pixels(g), -1.5, 5.0, max_iter=500)
+    assert np.array_equal(res["zero_bins"], g["zero_bins"])
+    assert np.array_equal(res["outliers_rel"], g["outliers_rel"])
+    assert res["ice"]["iterations"] == int(g["ice_iterations"]) == 35
+    np.testing.assert_array_equal(res["ice"]["bias"], g["ice_bias"])
+    w = res["ice"]["matrix"]
+    w.sort_indices()
+    np.testing.assert_array_equal(w.data[g["ice_sample_idx"]], g["ice_sample_val"])
+
+
+def test_ice_rejects_asymmetric_input():
+    m = random_hic(50, 0.2, 1).tolil()
+    m[3, 7] = m[3, 7] + 5
+    with pytest.raises(ValueError, match="symmetric"):
+        ice_oracle.ice(m.tocsr())
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.parametrize("seed,n,empty", [(0, 200, 0.0), (1, 333, 0.03), (2, 64, 0.0)])
+def test_oracle_equals_reference_functions_on_random_input(seed, n, empty):
+    iterativeCorrection, MAD, filter_by_zscore, _ = ref_import.load()
+    m = random_hic(n, 0.15, seed, empty_frac=empty, low_frac=0.05)
+    W, b = iterativeCorrection(m.copy(), M=40)
+    res = ice_oracle.ice(m.copy(), max_iter=40)
+    W.sort_indices()
+    mine = res["matrix"]
+    mine.sort_indices()
+    np.testing.assert_array_equal(W.data, mine.data)
+    np.testing.assert_array_equal(b, res["bias"])
+
+    class Ma(object):
+        matrix = m
+
+    np.testing.assert_array_equal(np.array(filter_by_zscore(Ma, -1.0, 3.0)), ice_oracle.outlier_bins(m, -1.0, 3.0))
+    pts = ice_oracle.coverage_points(m)
+    np.testing.assert_array_equal(MAD(pts).get_motified_zscores(), ice_oracle.MadScores(pts).z)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="/root/reference not present (GPU box)")
+def test_reference_cli_defaults_are_what_we_mirror():
+    parse_arguments = ref_import.load()[3]
+    a = parse_arguments().parse_args(["correct", "-m", "x.h5", "-o", "y.h5"])
+    assert a.correctionMethod == "KR" and a.iterNum == 500 and a.filterThreshold is None
+    assert a.perchr is False and a.skipDiagonal is False and a.chromosomes is None
+
+
+def test_kr_oracle_matches_reference_golden_file(small_ice, small_kr):
+    full = csr_from_npz(small_ice, "in")
+    res = kr_oracle.kr_pipeline(full, rescale=True)
+    up = res["upper"]
+    assert np.array_equal(up.indptr, small_kr["golden_indptr"])
+    assert np.array_equal(up.indices, small_kr["golden_indices"])
+    # the reference's own test pins 5 decimals (test_hicCorrectMatrix.py:52-69)
+    np.testing.assert_allclose(up.data, small_kr["golden_data"], rtol=0, atol=1e-7)
+    np.testing.assert_array_almost_equal(up.data, small_kr["golden_data"], decimal=5)
+    # golden correction_factors follow the older 1/x convention
+    np.testing.assert_allclose(1.0 / res["x_out"], small_kr["golden_correction_factors"].ravel(), rtol=2e-6)
+    assert res["outer"] == 33 and res["matvecs"] == 252
+
+
+def test_kr_oracle_matches_kr_partial_weights(kr_partial):
+    res = kr_oracle.kr_pipeline(full_from_pixels(kr_partial), rescale=True)
+    ratio = kr_partial["weight"] / res["x_out"]
+    assert np.ptp(ratio) < 1e-12  # same trajectory
+    assert abs(ratio.mean() - 1.0) < 5e-6  # marginally different rescale constant
+    assert res["outer"] == 15 and res["matvecs"] == 35
+
+
+def test_kr_balances_rows():
+    m = random_hic(300, 0.2, 5)
+    res = kr_oracle.kr_balance(m)
+    a = res["A"]
+    rows = res["x"] * (a @ res["x"])
+    np.testing.assert_allclose(rows, 1.0, atol=2e-6)
