@@ -1,0 +1,373 @@
+// Handle management of the device-resident CSR store (include/hicbalance.h).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "hb_internal.cuh"
+
+std::atomic<uint64_t> g_hb_launches{0};
+static thread_local char g_err[512] = "";
+
+void hb_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int hb_cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    hb_set_error("CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return HB_ERR_NO_DEVICE;
+    return HB_ERR_CUDA;
+}
+
+int hb_use_device(const hb_csr* h) {
+    HB_CUDA(cudaSetDevice(h->device));
+    return HB_OK;
+}
+
+int hb_spmv_grid(int64_t n_rows) {
+    // persistent grid: a multiple of the SM count; shrink for tiny matrices
+    int64_t warps_needed = (n_rows + HB_ROWS_PER_GRAB - 1) / HB_ROWS_PER_GRAB;
+    int64_t ctas_needed = (warps_needed + (HB_SPMV_THREADS / 32) - 1) / (HB_SPMV_THREADS / 32);
+    int64_t full = (int64_t)HB_NUM_SMS * HB_SPMV_CTAS_PER_SM;
+    if (ctas_needed >= full) return (int)full;
+    return (int)(ctas_needed < 1 ? 1 : ctas_needed);
+}
+
+extern "C" {
+
+int hb_abi_version(void) { return HB_ABI_VERSION; }
+const char* hb_last_error(void) { return g_err; }
+uint64_t hb_launch_count(void) { return g_hb_launches.load(); }
+
+int hb_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int hb_pinned_alloc(void** out, uint64_t bytes) {
+    HB_REQUIRE(out != nullptr, "null output pointer");
+    HB_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return HB_OK;
+}
+
+int hb_pinned_free(void* p) {
+    if (p) HB_CUDA(cudaFreeHost(p));
+    return HB_OK;
+}
+
+}  // extern "C"
+
+__global__ void hb_rebase_indptr_kernel(int64_t* indptr, int64_t n1, int64_t base) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n1) indptr[i] -= base;
+}
+
+__global__ void hb_narrow_indices_kernel(const int64_t* __restrict__ in, int32_t* __restrict__ out, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = (int32_t)in[i];
+}
+
+static int hb_new_handle(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t row0, int64_t nnz, int device) {
+    HB_REQUIRE(out != nullptr, "null output handle");
+    HB_REQUIRE(n_rows >= 0 && n_cols >= 0 && nnz >= 0 && row0 >= 0, "negative size");
+    HB_REQUIRE(row0 + n_rows <= n_cols, "row block exceeds the matrix");
+    HB_REQUIRE(n_cols < 2147483647LL, "bin count must fit int32 column ids");
+    int ndev = hb_device_count();
+    if (ndev <= 0) {
+        hb_set_error("no CUDA device visible: libhicbalance has no CPU fallback");
+        return HB_ERR_NO_DEVICE;
+    }
+    HB_REQUIRE(device >= 0 && device < ndev, "device index out of range");
+    HB_CUDA(cudaSetDevice(device));
+    hb_csr* h = new hb_csr();
+    h->device = device;
+    h->n_rows = n_rows;
+    h->n_cols = n_cols;
+    h->row0 = row0;
+    h->nnz = nnz;
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete h;
+        return hb_cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__);
+    }
+    h->nseg = 1;
+    h->seg_off = {0, n_cols};
+    *out = h;
+    return HB_OK;
+}
+
+extern "C" {
+
+int hb_csr_create(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t row0, int64_t nnz, const int64_t* indptr,
+                  const void* indices, int indices_i64, const double* data, int device) {
+    HB_REQUIRE(indptr != nullptr, "null indptr");
+    HB_REQUIRE(nnz == 0 || (indices != nullptr && data != nullptr), "null indices/data");
+    HB_REQUIRE(indptr[n_rows] - indptr[0] == nnz, "indptr does not span nnz entries");
+    int rc = hb_new_handle(out, n_rows, n_cols, row0, nnz, device);
+    if (rc != HB_OK) return rc;
+    hb_csr* h = *out;
+    h->owns_csr = true;
+    cudaStream_t s = h->stream;
+#define HB_CREATE_CUDA(expr)                                               \
+    do {                                                                   \
+        cudaError_t _e = (expr);                                           \
+        if (_e != cudaSuccess) {                                           \
+            hb_csr_destroy(h);                                             \
+            *out = nullptr;                                                \
+            return hb_cuda_fail(_e, #expr, __FILE__, __LINE__);            \
+        }                                                                  \
+    } while (0)
+    HB_CREATE_CUDA(cudaMalloc(&h->d_indptr, sizeof(int64_t) * (size_t)(n_rows + 1)));
+    HB_CREATE_CUDA(cudaMalloc(&h->d_indices, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1) + 16));
+    HB_CREATE_CUDA(cudaMalloc(&h->d_data, sizeof(double) * (size_t)(nnz > 0 ? nnz : 1) + 16));
+    HB_CREATE_CUDA(cudaMemcpyAsync(h->d_indptr, indptr, sizeof(int64_t) * (size_t)(n_rows + 1),
+                                   cudaMemcpyHostToDevice, s));
+    if (indptr[0] != 0) {
+        int64_t n1 = n_rows + 1;
+        hb_rebase_indptr_kernel<<<(unsigned)((n1 + 255) / 256), 256, 0, s>>>(h->d_indptr, n1, indptr[0]);
+        g_hb_launches.fetch_add(1);
+    }
+    if (nnz > 0) {
+        HB_CREATE_CUDA(cudaMemcpyAsync(h->d_data, data + indptr[0], sizeof(double) * (size_t)nnz,
+                                       cudaMemcpyHostToDevice, s));
+        if (indices_i64) {
+            // krbalancing's constructor takes int64 indices (hicCorrectMatrix.py:744-747): narrow on the device
+            const int64_t* src = (const int64_t*)indices + indptr[0];
+            const int64_t chunk = (int64_t)1 << 26;
+            int64_t* d_tmp = nullptr;
+            HB_CREATE_CUDA(cudaMalloc(&d_tmp, sizeof(int64_t) * (size_t)(nnz < chunk ? nnz : chunk)));
+            for (int64_t o = 0; o < nnz; o += chunk) {
+                int64_t m = nnz - o < chunk ? nnz - o : chunk;
+                HB_CREATE_CUDA(cudaMemcpyAsync(d_tmp, src + o, sizeof(int64_t) * (size_t)m, cudaMemcpyHostToDevice, s));
+                hb_narrow_indices_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(d_tmp, h->d_indices + o, m);
+                g_hb_launches.fetch_add(1);
+            }
+            HB_CREATE_CUDA(cudaStreamSynchronize(s));
+            cudaFree(d_tmp);
+        } else {
+            HB_CREATE_CUDA(cudaMemcpyAsync(h->d_indices, (const int32_t*)indices + indptr[0],
+                                           sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, s));
+        }
+    }
+    HB_CREATE_CUDA(cudaStreamSynchronize(s));
+#undef HB_CREATE_CUDA
+    rc = hb_build_tiles(h);
+    if (rc != HB_OK) {
+        hb_csr_destroy(h);
+        *out = nullptr;
+    }
+    return rc;
+}
+
+int hb_dev_csr_wrap(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t row0, int64_t nnz, const int64_t* d_indptr,
+                    const int32_t* d_indices, const double* d_data, int device) {
+    HB_REQUIRE(d_indptr != nullptr, "null indptr");
+    HB_REQUIRE(((uintptr_t)d_indices % 16) == 0 && ((uintptr_t)d_data % 16) == 0,
+               "indices/data must be 16-byte aligned");
+    int rc = hb_new_handle(out, n_rows, n_cols, row0, nnz, device);
+    if (rc != HB_OK) return rc;
+    hb_csr* h = *out;
+    h->owns_csr = false;
+    h->d_indptr = const_cast<int64_t*>(d_indptr);
+    h->d_indices = const_cast<int32_t*>(d_indices);
+    h->d_data = const_cast<double*>(d_data);
+    rc = hb_build_tiles(h);
+    if (rc != HB_OK) {
+        hb_csr_destroy(h);
+        *out = nullptr;
+    }
+    return rc;
+}
+
+int hb_csr_destroy(hb_csr* h) {
+    if (!h) return HB_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    hb_free_state(h);
+    if (h->owns_csr) {
+        cudaFree(h->d_indptr);
+        cudaFree(h->d_indices);
+        cudaFree(h->d_data);
+    }
+    cudaFree(h->d_seg_off);
+    cudaFree(h->d_tile_row0);
+    cudaFree(h->d_tile_len);
+    cudaFree(h->d_tile_seg);
+    cudaFree(h->d_seg_tile0);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return HB_OK;
+}
+
+int hb_csr_shape(const hb_csr* h, int64_t* n_rows, int64_t* n_cols, int64_t* row0, int64_t* nnz) {
+    HB_REQUIRE(h != nullptr, "null handle");
+    if (n_rows) *n_rows = h->n_rows;
+    if (n_cols) *n_cols = h->n_cols;
+    if (row0) *row0 = h->row0;
+    if (nnz) *nnz = h->nnz;
+    return HB_OK;
+}
+
+int hb_csr_download(hb_csr* h, int64_t* indptr, int32_t* indices, double* data) {
+    HB_REQUIRE(h != nullptr, "null handle");
+    int rc = hb_use_device(h);
+    if (rc) return rc;
+    HB_CUDA(cudaStreamSynchronize(h->stream));
+    if (indptr) HB_CUDA(cudaMemcpy(indptr, h->d_indptr, sizeof(int64_t) * (size_t)(h->n_rows + 1), cudaMemcpyDeviceToHost));
+    if (indices && h->nnz) HB_CUDA(cudaMemcpy(indices, h->d_indices, sizeof(int32_t) * (size_t)h->nnz, cudaMemcpyDeviceToHost));
+    if (data && h->nnz) HB_CUDA(cudaMemcpy(data, h->d_data, sizeof(double) * (size_t)h->nnz, cudaMemcpyDeviceToHost));
+    return HB_OK;
+}
+
+int hb_dev_csr_pointers(hb_csr* h, const int64_t** d_indptr, const int32_t** d_indices, const double** d_data) {
+    HB_REQUIRE(h != nullptr, "null handle");
+    if (d_indptr) *d_indptr = h->d_indptr;
+    if (d_indices) *d_indices = h->d_indices;
+    if (d_data) *d_data = h->d_data;
+    return HB_OK;
+}
+
+int hb_sync(hb_csr* h) {
+    HB_REQUIRE(h != nullptr, "null handle");
+    int rc = hb_use_device(h);
+    if (rc) return rc;
+    HB_CUDA(cudaStreamSynchronize(h->stream));
+    return HB_OK;
+}
+
+int hb_set_comm(hb_csr* h, int rank, int world, hb_allreduce_fn fn, void* ctx) {
+    HB_REQUIRE(h != nullptr, "null handle");
+    HB_REQUIRE(world >= 1 && world <= 64 && rank >= 0 && rank < world, "bad rank/world");
+    HB_REQUIRE(world == 1 || fn != nullptr, "a collective callback is required when world > 1");
+    h->rank = rank;
+    h->world = world;
+    h->allreduce = fn;
+    h->comm_ctx = ctx;
+    return HB_OK;
+}
+
+int hb_set_segments(hb_csr* h, int nseg, const int64_t* seg_offsets) {
+    HB_REQUIRE(h != nullptr, "null handle");
+    HB_REQUIRE(nseg >= 1 && nseg <= HB_MAX_SEG && seg_offsets != nullptr, "bad segment count");
+    HB_REQUIRE(seg_offsets[0] == 0 && seg_offsets[nseg] == h->n_cols, "segments must cover [0, n_cols)");
+    for (int s = 0; s < nseg; ++s) HB_REQUIRE(seg_offsets[s] <= seg_offsets[s + 1], "segment offsets must ascend");
+    int rc = hb_use_device(h);
+    if (rc) return rc;
+    HB_CUDA(cudaStreamSynchronize(h->stream));
+    hb_free_state(h);
+    h->nseg = nseg;
+    h->seg_off.assign(seg_offsets, seg_offsets + nseg + 1);
+    return hb_build_tiles(h);
+}
+
+}  // extern "C"
+
+// Fixed reduction tiles: HB_TILE_ROWS consecutive GLOBAL rows, never crossing a segment boundary.
+// Sums over rows are always formed tile by tile in this order, so the result does not depend on
+// how many GPUs share the matrix.
+int hb_build_tiles(hb_csr* h) {
+    int rc = hb_use_device(h);
+    if (rc) return rc;
+    std::vector<int64_t> row0;
+    std::vector<int32_t> len, seg, seg_tile0(h->nseg + 1, 0);
+    for (int s = 0; s < h->nseg; ++s) {
+        seg_tile0[s] = (int32_t)row0.size();
+        for (int64_t r = h->seg_off[s]; r < h->seg_off[s + 1]; r += HB_TILE_ROWS) {
+            int64_t e = r + HB_TILE_ROWS < h->seg_off[s + 1] ? r + HB_TILE_ROWS : h->seg_off[s + 1];
+            row0.push_back(r);
+            len.push_back((int32_t)(e - r));
+            seg.push_back(s);
+        }
+    }
+    seg_tile0[h->nseg] = (int32_t)row0.size();
+    h->n_tiles = (int)row0.size();
+    cudaFree(h->d_seg_off);
+    cudaFree(h->d_tile_row0);
+    cudaFree(h->d_tile_len);
+    cudaFree(h->d_tile_seg);
+    cudaFree(h->d_seg_tile0);
+    h->d_seg_off = nullptr;
+    h->d_tile_row0 = nullptr;
+    h->d_tile_len = nullptr;
+    h->d_tile_seg = nullptr;
+    h->d_seg_tile0 = nullptr;
+    size_t nt = h->n_tiles > 0 ? (size_t)h->n_tiles : 1;
+    HB_CUDA(cudaMalloc(&h->d_seg_off, sizeof(int64_t) * (h->nseg + 1)));
+    HB_CUDA(cudaMalloc(&h->d_tile_row0, sizeof(int64_t) * nt));
+    HB_CUDA(cudaMalloc(&h->d_tile_len, sizeof(int32_t) * nt));
+    HB_CUDA(cudaMalloc(&h->d_tile_seg, sizeof(int32_t) * nt));
+    HB_CUDA(cudaMalloc(&h->d_seg_tile0, sizeof(int32_t) * (h->nseg + 1)));
+    HB_CUDA(cudaMemcpy(h->d_seg_off, h->seg_off.data(), sizeof(int64_t) * (h->nseg + 1), cudaMemcpyHostToDevice));
+    if (h->n_tiles) {
+        HB_CUDA(cudaMemcpy(h->d_tile_row0, row0.data(), sizeof(int64_t) * nt, cudaMemcpyHostToDevice));
+        HB_CUDA(cudaMemcpy(h->d_tile_len, len.data(), sizeof(int32_t) * nt, cudaMemcpyHostToDevice));
+        HB_CUDA(cudaMemcpy(h->d_tile_seg, seg.data(), sizeof(int32_t) * nt, cudaMemcpyHostToDevice));
+    }
+    HB_CUDA(cudaMemcpy(h->d_seg_tile0, seg_tile0.data(), sizeof(int32_t) * (h->nseg + 1), cudaMemcpyHostToDevice));
+    return HB_OK;
+}
+
+void hb_free_state(hb_csr* h) {
+    cudaFree(h->d_bias);
+    cudaFree(h->d_r);
+    cudaFree(h->d_exch);
+    cudaFree(h->d_tile_sum);
+    cudaFree(h->d_tile_cnt);
+    cudaFree(h->d_seg_mean);
+    cudaFree(h->d_seg_corr);
+    cudaFree(h->d_seg_devbits);
+    cudaFree(h->d_seg_dev);
+    cudaFree(h->d_seg_done);
+    cudaFree(h->d_seg_iters);
+    cudaFree(h->d_status);
+    cudaFree(h->d_counters);
+    cudaFree(h->d_row_counter);
+    cudaFree(h->d_scalar_bits);
+    if (h->h_status) cudaFreeHost(h->h_status);
+    h->d_bias = h->d_r = h->d_exch = h->d_tile_sum = h->d_tile_cnt = h->d_seg_mean = h->d_seg_corr = h->d_seg_dev = nullptr;
+    h->d_seg_devbits = nullptr;
+    h->d_seg_done = h->d_seg_iters = h->d_status = nullptr;
+    h->d_counters = nullptr;
+    h->d_row_counter = nullptr;
+    h->d_scalar_bits = nullptr;
+    h->h_status = nullptr;
+    h->state_ready = false;
+}
+
+int hb_ensure_state(hb_csr* h) {
+    if (h->state_ready) return HB_OK;
+    int rc = hb_use_device(h);
+    if (rc) return rc;
+    size_t n = (size_t)(h->n_cols > 0 ? h->n_cols : 1);
+    size_t nt = (size_t)(h->n_tiles > 0 ? h->n_tiles : 1);
+    size_t ns = (size_t)h->nseg;
+    HB_CUDA(cudaMalloc(&h->d_bias, sizeof(double) * n));
+    HB_CUDA(cudaMalloc(&h->d_r, sizeof(double) * n));
+    HB_CUDA(cudaMalloc(&h->d_exch, sizeof(double) * (n + 64)));
+    HB_CUDA(cudaMalloc(&h->d_tile_sum, sizeof(double) * nt));
+    HB_CUDA(cudaMalloc(&h->d_tile_cnt, sizeof(double) * nt));
+    HB_CUDA(cudaMalloc(&h->d_seg_mean, sizeof(double) * ns));
+    HB_CUDA(cudaMalloc(&h->d_seg_corr, sizeof(double) * ns));
+    HB_CUDA(cudaMalloc(&h->d_seg_devbits, sizeof(unsigned long long) * ns));
+    HB_CUDA(cudaMalloc(&h->d_seg_dev, sizeof(double) * ns));
+    HB_CUDA(cudaMalloc(&h->d_seg_done, sizeof(int32_t) * ns));
+    HB_CUDA(cudaMalloc(&h->d_seg_iters, sizeof(int32_t) * ns));
+    HB_CUDA(cudaMalloc(&h->d_status, sizeof(int32_t) * HB_ST_WORDS));
+    HB_CUDA(cudaMalloc(&h->d_counters, sizeof(unsigned int) * 8));
+    HB_CUDA(cudaMalloc(&h->d_row_counter, sizeof(unsigned long long) * 2));
+    HB_CUDA(cudaMalloc(&h->d_scalar_bits, sizeof(unsigned long long) * 8));
+    HB_CUDA(cudaHostAlloc((void**)&h->h_status, sizeof(int32_t) * HB_ST_WORDS * 16, cudaHostAllocDefault));
+    HB_CUDA(cudaMemset(h->d_counters, 0, sizeof(unsigned int) * 8));
+    HB_CUDA(cudaMemset(h->d_row_counter, 0, sizeof(unsigned long long) * 2));
+    HB_CUDA(cudaMemset(h->d_scalar_bits, 0, sizeof(unsigned long long) * 8));
+    h->state_ready = true;
+    return HB_OK;
+}

@@ -1,0 +1,635 @@
+// Pre-filter stage on the device CSR store: NaN/Inf scrub, row statistics, the MAD outlier mask,
+// bin deletion (row + column compaction), cis-only restriction, diagonal removal, symmetry test.
+// Reference: hicexplorer/hicCorrectMatrix.py:349-391 (MAD), :548-592 (filter_by_zscore),
+// :612-626 (zero bins, scrub), :648-649 (skipDiagonal), :672 (maskBins);
+// hicexplorer/iterativeCorrection.py:35 (symmetry).  Contract: include/hicbalance.h.
+//
+// Bit-exactness of the mask: every floating-point step below is a single correctly rounded IEEE
+// operation issued in the reference's order (subtract, subtract, divide, multiply); medians are
+// exact order statistics (radix select) combined as (a+b)/2 like numpy.  Row sums are formed in a
+// different order than scipy's, which is exact -- hence bit-identical -- for integer counts below
+// 2^53 (the raw matrices this filter is applied to); see DESIGN.md.
+#include "hb_internal.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// scrub
+// ---------------------------------------------------------------------------------------------
+__global__ void hb_scrub_kernel(double* __restrict__ data, int64_t nnz, unsigned long long* counts) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned int nn = 0, ni = 0;
+    for (; i < nnz; i += stride) {
+        const double v = data[i];
+        if (isnan(v)) {
+            data[i] = 0.0;
+            ++nn;
+        } else if (isinf(v)) {
+            data[i] = 0.0;
+            ++ni;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        nn += __shfl_xor_sync(0xffffffffu, nn, o);
+        ni += __shfl_xor_sync(0xffffffffu, ni, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (nn) atomicAdd(counts + 0, (unsigned long long)nn);
+        if (ni) atomicAdd(counts + 1, (unsigned long long)ni);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// row statistics: warp per row; sum over the row (optionally only columns of the row's own
+// segment = the chromosome block of --perchr) and the diagonal entry
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int hb_find_seg(const int64_t* __restrict__ seg_off, int nseg, int64_t g) {
+    int lo = 0, hi = nseg;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (seg_off[mid] <= g) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256)
+hb_row_stats_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
+                    int64_t n_rows, int64_t row0, const int64_t* __restrict__ seg_off, int nseg, int cis_only,
+                    double* __restrict__ row_sum, double* __restrict__ diag) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = gwarp; row < n_rows; row += nwarps) {
+        const int64_t g = row0 + row;
+        int64_t clo = 0, chi = INT64_MAX;
+        if (cis_only && nseg > 1) {
+            const int s = hb_find_seg(seg_off, nseg, g);
+            clo = seg_off[s];
+            chi = seg_off[s + 1];
+        }
+        double acc = 0.0, dg = 0.0;
+        const int64_t s = indptr[row], e = indptr[row + 1];
+        for (int64_t k = s + lane; k < e; k += 32) {
+            const int c = idx[k];
+            const double v = val[k];
+            if (c >= clo && c < chi) acc += v;
+            if (c == g) dg += v;
+        }
+        acc = hb_warp_sum(acc);
+        dg = hb_warp_sum(dg);
+        if (lane == 0) {
+            if (row_sum) row_sum[row] = acc;
+            if (diag) diag[row] = dg;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact per-segment order statistics of non-negative doubles by 8-bit radix select
+// ---------------------------------------------------------------------------------------------
+struct HbSelState {          // one per segment, device resident
+    unsigned long long prefix;   // decided high bits of the key
+    unsigned long long mask;     // which bits are decided
+    long long rank;              // remaining 0-based rank inside the candidate set
+    long long count;             // number of candidates (set by the first pass)
+};
+
+// mode 0: candidates are keys > 0 (np.median(points[points > 0])); mode 1: all keys
+__device__ __forceinline__ bool hb_sel_candidate(double v, int mode) { return mode == 1 || v > 0.0; }
+
+__global__ void __launch_bounds__(256)
+hb_sel_hist_kernel(const double* __restrict__ keys, const int64_t* __restrict__ tile_row0,
+                   const int32_t* __restrict__ tile_len, const int32_t* __restrict__ tile_seg,
+                   const HbSelState* __restrict__ st, int shift, int mode, unsigned int* __restrict__ hist /*nseg*256*/) {
+    __shared__ unsigned int sh[256];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    const int t = blockIdx.x;
+    const int seg = tile_seg[t];
+    const unsigned long long prefix = st[seg].prefix, mask = st[seg].mask;
+    const int64_t r0 = tile_row0[t];
+    for (int i = threadIdx.x; i < tile_len[t]; i += blockDim.x) {
+        const double v = keys[r0 + i];
+        if (!hb_sel_candidate(v, mode)) continue;
+        const unsigned long long k = (unsigned long long)__double_as_longlong(v);
+        if ((k & mask) == prefix) atomicAdd(&sh[(k >> shift) & 0xffu], 1u);
+    }
+    __syncthreads();
+    if (sh[threadIdx.x]) atomicAdd(&hist[seg * 256 + threadIdx.x], sh[threadIdx.x]);
+}
+
+// one thread block per segment: pick the bucket holding the wanted rank, narrow the prefix
+__global__ void hb_sel_pick_kernel(HbSelState* st, unsigned int* hist, int shift, int first_pass, int which /*0 lower, 1 upper middle*/) {
+    const int seg = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    unsigned int* h = hist + seg * 256;
+    HbSelState s = st[seg];
+    if (first_pass) {
+        long long cnt = 0;
+        for (int b = 0; b < 256; ++b) cnt += h[b];
+        s.count = cnt;
+        // numpy: even count -> elements cnt/2-1 and cnt/2 ; odd -> cnt/2 twice
+        s.rank = (cnt % 2 == 0 && which == 0) ? cnt / 2 - 1 : cnt / 2;
+    }
+    if (s.count > 0) {
+        long long r = s.rank;
+        int b = 0;
+        for (; b < 255; ++b) {
+            if (r < (long long)h[b]) break;
+            r -= h[b];
+        }
+        s.rank = r;
+        s.prefix |= ((unsigned long long)b) << shift;
+        s.mask |= 0xffull << shift;
+    }
+    st[seg] = s;
+    for (int b = 0; b < 256; ++b) h[b] = 0;
+}
+
+__global__ void hb_sel_init_kernel(HbSelState* st, int nseg) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nseg) {
+        st[i].prefix = 0;
+        st[i].mask = 0;
+        st[i].rank = 0;
+        st[i].count = 0;
+    }
+}
+
+// median[seg] = (lower + upper) / 2, NaN for an empty candidate set (np.median of an empty array)
+__global__ void hb_sel_finish_kernel(const HbSelState* lo, const HbSelState* hi, double* median, int nseg) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nseg) {
+        if (lo[i].count <= 0) {
+            median[i] = __longlong_as_double(0x7ff8000000000000LL);
+        } else {
+            const double a = __longlong_as_double((long long)lo[i].prefix);
+            const double b = __longlong_as_double((long long)hi[i].prefix);
+            median[i] = (lo[i].count % 2 == 0) ? __ddiv_rn(__dadd_rn(a, b), 2.0) : b;
+        }
+    }
+}
+
+// points = row_sum - diag
+__global__ void hb_points_kernel(const double* __restrict__ row_sum, const double* __restrict__ diag, double* __restrict__ points, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) points[i] = __dsub_rn(row_sum[i], diag[i]);
+}
+
+// diff = points - median[seg] ; absdiff = |diff|
+__global__ void __launch_bounds__(256)
+hb_diff_kernel(const double* __restrict__ points, const int64_t* __restrict__ tile_row0, const int32_t* __restrict__ tile_len,
+               const int32_t* __restrict__ tile_seg, const double* __restrict__ median, double* __restrict__ diff,
+               double* __restrict__ absdiff) {
+    const int t = blockIdx.x;
+    const double med = median[tile_seg[t]];
+    const int64_t r0 = tile_row0[t];
+    for (int i = threadIdx.x; i < tile_len[t]; i += blockDim.x) {
+        const double d = __dsub_rn(points[r0 + i], med);
+        diff[r0 + i] = d;
+        absdiff[r0 + i] = fabs(d);
+    }
+}
+
+// z = 0.6745 * (diff / mad) ; mask = (z < lo) | (z > hi)
+__global__ void __launch_bounds__(256)
+hb_zscore_kernel(const double* __restrict__ diff, const int64_t* __restrict__ tile_row0, const int32_t* __restrict__ tile_len,
+                 const int32_t* __restrict__ tile_seg, const double* __restrict__ mad, double lo, double hi,
+                 double* __restrict__ z_out, uint8_t* __restrict__ mask) {
+    const int t = blockIdx.x;
+    const double m = mad[tile_seg[t]];
+    const int64_t r0 = tile_row0[t];
+    for (int i = threadIdx.x; i < tile_len[t]; i += blockDim.x) {
+        const double z = __dmul_rn(0.6745, __ddiv_rn(diff[r0 + i], m));
+        if (z_out) z_out[r0 + i] = z;
+        mask[r0 + i] = (z < lo || z > hi) ? 1 : 0;
+    }
+}
+
+static int hb_segment_median(hb_csr* h, const double* d_keys, int mode, HbSelState* d_st /*2*nseg*/, unsigned int* d_hist,
+                             double* d_median) {
+    cudaStream_t s = h->stream;
+    const int nseg = h->nseg;
+    for (int which = 0; which < 2; ++which) {
+        HbSelState* st = d_st + which * nseg;
+        hb_sel_init_kernel<<<(nseg + 255) / 256, 256, 0, s>>>(st, nseg);
+        HB_LAUNCH_CHECK();
+        for (int pass = 0; pass < 8; ++pass) {
+            const int shift = 56 - 8 * pass;
+            if (h->n_tiles > 0) {
+                hb_sel_hist_kernel<<<h->n_tiles, 256, 0, s>>>(d_keys, h->d_tile_row0, h->d_tile_len, h->d_tile_seg, st,
+                                                              shift, mode, d_hist);
+                HB_LAUNCH_CHECK();
+            }
+            hb_sel_pick_kernel<<<nseg, 32, 0, s>>>(st, d_hist, shift, pass == 0, which);
+            HB_LAUNCH_CHECK();
+        }
+    }
+    hb_sel_finish_kernel<<<(nseg + 255) / 256, 256, 0, s>>>(d_st, d_st + nseg, d_median, nseg);
+    HB_LAUNCH_CHECK();
+    return HB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// single-block exclusive scan (n up to a few million; runs once per compaction)
+// ---------------------------------------------------------------------------------------------
+template <typename TIn>
+__global__ void __launch_bounds__(1024) hb_scan_kernel(const TIn* __restrict__ in, int64_t* __restrict__ out, int64_t n) {
+    __shared__ long long part[1024];
+    const int t = threadIdx.x;
+    const int64_t chunk = (n + 1023) / 1024;
+    const int64_t b = t * chunk, e = (b + chunk < n) ? b + chunk : n;
+    long long s = 0;
+    for (int64_t i = b; i < e; ++i) s += (long long)in[i];
+    part[t] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan of the 1024 partials
+        long long v = (t >= o) ? part[t - o] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    long long run = part[t] - s;
+    for (int64_t i = b; i < e; ++i) {
+        const long long v = (long long)in[i];
+        out[i] = run;
+        run += v;
+    }
+    if (t == 1023) out[n] = part[1023];
+}
+
+// ---------------------------------------------------------------------------------------------
+// compaction: keep entry (row, col) iff  newid[row] >= 0 && newid[col] >= 0
+//                                    && (!cis || seg(row) == seg(col)) && (!drop_diag || row != col)
+// ---------------------------------------------------------------------------------------------
+struct HbKeepRule {
+    const int32_t* __restrict__ newid;   // n_cols, -1 = bin removed (may be NULL = identity)
+    const int64_t* __restrict__ seg_off;
+    int nseg;
+    int cis;
+    int drop_diag;
+    __device__ __forceinline__ bool keep(int64_t grow, int64_t clo, int64_t chi, int c) const {
+        if (newid != nullptr && newid[c] < 0) return false;
+        if (cis && (c < clo || c >= chi)) return false;
+        if (drop_diag && c == grow) return false;
+        return true;
+    }
+};
+
+__global__ void __launch_bounds__(256)
+hb_compact_count_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, int64_t n_rows, int64_t row0,
+                        HbKeepRule rule, int64_t* __restrict__ new_count /* indexed by NEW local row */) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = gwarp; row < n_rows; row += nwarps) {
+        const int64_t g = row0 + row;
+        const int64_t nr = rule.newid ? rule.newid[g] : g;
+        if (nr < 0) continue;
+        int64_t clo = 0, chi = INT64_MAX;
+        if (rule.cis) {
+            const int s = hb_find_seg(rule.seg_off, rule.nseg, g);
+            clo = rule.seg_off[s];
+            chi = rule.seg_off[s + 1];
+        }
+        long long cnt = 0;
+        for (int64_t k = indptr[row] + lane; k < indptr[row + 1]; k += 32) cnt += rule.keep(g, clo, chi, idx[k]) ? 1 : 0;
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0) new_count[nr] = cnt;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+hb_compact_fill_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
+                       int64_t n_rows, int64_t row0, HbKeepRule rule, int64_t new_row0,
+                       const int64_t* __restrict__ new_indptr, int32_t* __restrict__ new_idx, double* __restrict__ new_val) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = gwarp; row < n_rows; row += nwarps) {
+        const int64_t g = row0 + row;
+        const int64_t nr = rule.newid ? rule.newid[g] : g;
+        if (nr < 0) continue;
+        int64_t clo = 0, chi = INT64_MAX;
+        if (rule.cis) {
+            const int s = hb_find_seg(rule.seg_off, rule.nseg, g);
+            clo = rule.seg_off[s];
+            chi = rule.seg_off[s + 1];
+        }
+        int64_t w = new_indptr[nr - new_row0];
+        const int64_t s = indptr[row], e = indptr[row + 1];
+        for (int64_t base = s; base < e; base += 32) {
+            const int64_t k = base + lane;
+            int c = 0;
+            double v = 0.0;
+            bool kp = false;
+            if (k < e) {
+                c = idx[k];
+                v = val[k];
+                kp = rule.keep(g, clo, chi, c);
+            }
+            const unsigned int bal = __ballot_sync(0xffffffffu, kp);
+            if (kp) {
+                const int64_t pos = w + __popc(bal & ((1u << lane) - 1u));
+                new_idx[pos] = rule.newid ? rule.newid[c] : c;
+                new_val[pos] = v;
+            }
+            w += __popc(bal);
+        }
+    }
+}
+
+__global__ void hb_newid_kernel(const uint8_t* __restrict__ remove, const int64_t* __restrict__ scan, int32_t* __restrict__ newid, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) newid[i] = remove[i] ? -1 : (int32_t)scan[i];
+}
+
+__global__ void hb_keepflag_kernel(const uint8_t* __restrict__ remove, int32_t* __restrict__ keep, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) keep[i] = remove[i] ? 0 : 1;
+}
+
+// Rebuild the store with `rule`; d_newid may be NULL (no bin removal).  Full blocks only when bins are removed.
+static int hb_compact_impl(hb_csr* h, const int32_t* d_newid, int64_t new_n, int cis, int drop_diag) {
+    cudaStream_t s = h->stream;
+    HbKeepRule rule;
+    rule.newid = d_newid;
+    rule.seg_off = h->d_seg_off;
+    rule.nseg = h->nseg;
+    rule.cis = (cis && h->nseg > 1) ? 1 : 0;
+    rule.drop_diag = drop_diag;
+    const int64_t new_rows = d_newid ? new_n : h->n_rows;
+    const int64_t new_row0 = d_newid ? 0 : h->row0;
+    int64_t* d_cnt = nullptr;
+    int64_t* d_new_indptr = nullptr;
+    HB_CUDA(cudaMalloc(&d_cnt, sizeof(int64_t) * (size_t)(new_rows + 1)));
+    HB_CUDA(cudaMalloc(&d_new_indptr, sizeof(int64_t) * (size_t)(new_rows + 1)));
+    HB_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int64_t) * (size_t)(new_rows + 1), s));
+    const int grid = HB_NUM_SMS * 8;
+    if (h->n_rows > 0) {
+        // new_count is indexed by new LOCAL row: nr - new_row0
+        hb_compact_count_kernel<<<grid, 256, 0, s>>>(h->d_indptr, h->d_indices, h->n_rows, h->row0, rule,
+                                                     d_cnt - new_row0);
+        HB_LAUNCH_CHECK();
+    }
+    hb_scan_kernel<int64_t><<<1, 1024, 0, s>>>(d_cnt, d_new_indptr, new_rows);
+    HB_LAUNCH_CHECK();
+    int64_t new_nnz = 0;
+    HB_CUDA(cudaMemcpyAsync(&new_nnz, d_new_indptr + new_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    HB_CUDA(cudaStreamSynchronize(s));
+    int32_t* d_new_idx = nullptr;
+    double* d_new_val = nullptr;
+    HB_CUDA(cudaMalloc(&d_new_idx, sizeof(int32_t) * (size_t)(new_nnz > 0 ? new_nnz : 1) + 16));
+    HB_CUDA(cudaMalloc(&d_new_val, sizeof(double) * (size_t)(new_nnz > 0 ? new_nnz : 1) + 16));
+    if (h->n_rows > 0 && new_nnz > 0) {
+        hb_compact_fill_kernel<<<grid, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, h->n_rows, h->row0, rule,
+                                                    new_row0, d_new_indptr, d_new_idx, d_new_val);
+        HB_LAUNCH_CHECK();
+    }
+    HB_CUDA(cudaStreamSynchronize(s));
+    cudaFree(d_cnt);
+    if (h->owns_csr) {
+        cudaFree(h->d_indptr);
+        cudaFree(h->d_indices);
+        cudaFree(h->d_data);
+    }
+    h->owns_csr = true;
+    h->d_indptr = d_new_indptr;
+    h->d_indices = d_new_idx;
+    h->d_data = d_new_val;
+    h->nnz = new_nnz;
+    if (d_newid) {
+        h->n_rows = new_n;
+        h->n_cols = new_n;
+        h->row0 = 0;
+    }
+    return HB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// symmetry: sum |M - M^T| and sum M   (iterativeCorrection.py:35)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+hb_symmetry_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
+                   int64_t n_rows, double* sums /* [0] sum|M-M^T|, [1] sum M */) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    double sd = 0.0, sm = 0.0;
+    for (int64_t row = gwarp; row < n_rows; row += nwarps) {
+        for (int64_t k = indptr[row] + lane; k < indptr[row + 1]; k += 32) {
+            const int c = idx[k];
+            const double a = val[k];
+            sm += a;
+            // binary search for `row` among the (ascending) columns of row c
+            int64_t lo = indptr[c], hi = indptr[c + 1];
+            bool found = false;
+            double b = 0.0;
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                const int cm = idx[mid];
+                if (cm < row) lo = mid + 1;
+                else if (cm > row) hi = mid;
+                else {
+                    found = true;
+                    b = val[mid];
+                    break;
+                }
+            }
+            sd += found ? fabs(a - b) : 2.0 * fabs(a);
+        }
+    }
+    sd = hb_warp_sum(sd);
+    sm = hb_warp_sum(sm);
+    if (lane == 0) {
+        atomicAdd(sums + 0, sd);
+        atomicAdd(sums + 1, sm);
+    }
+}
+
+extern "C" {
+
+int hb_scrub(hb_csr* h, int64_t counts[2]) {
+    HB_REQUIRE(h != nullptr, "null handle");
+    int rc = hb_ensure_state(h);
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    HB_CUDA(cudaMemsetAsync(h->d_scalar_bits, 0, sizeof(unsigned long long) * 2, s));
+    if (h->nnz > 0) {
+        hb_scrub_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_data, h->nnz, h->d_scalar_bits);
+        HB_LAUNCH_CHECK();
+    }
+    unsigned long long c[2] = {0, 0};
+    HB_CUDA(cudaMemcpyAsync(c, h->d_scalar_bits, sizeof(c), cudaMemcpyDeviceToHost, s));
+    HB_CUDA(cudaStreamSynchronize(s));
+    if (counts) {
+        counts[0] = (int64_t)c[0];
+        counts[1] = (int64_t)c[1];
+    }
+    return HB_OK;
+}
+
+int hb_row_stats(hb_csr* h, double* row_sum, double* diag) {
+    HB_REQUIRE(h != nullptr, "null handle");
+    int rc = hb_use_device(h);
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    size_t n = (size_t)(h->n_rows > 0 ? h->n_rows : 1);
+    double *d_rs = nullptr, *d_dg = nullptr;
+    HB_CUDA(cudaMalloc(&d_rs, sizeof(double) * n));
+    HB_CUDA(cudaMalloc(&d_dg, sizeof(double) * n));
+    if (h->n_rows > 0) {
+        hb_row_stats_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, h->n_rows, h->row0,
+                                                           h->d_seg_off, h->nseg, 0, d_rs, d_dg);
+        HB_LAUNCH_CHECK();
+    }
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess && row_sum && h->n_rows) e = cudaMemcpy(row_sum, d_rs, sizeof(double) * n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && diag && h->n_rows) e = cudaMemcpy(diag, d_dg, sizeof(double) * n, cudaMemcpyDeviceToHost);
+    cudaFree(d_rs);
+    cudaFree(d_dg);
+    if (e != cudaSuccess) return hb_cuda_fail(e, "row stats", __FILE__, __LINE__);
+    return HB_OK;
+}
+
+int hb_mad_filter(hb_csr* h, double lo, double hi, uint8_t* mask_out, double* zscore_out, double* median_out,
+                  double* mad_out) {
+    HB_REQUIRE(h != nullptr && mask_out != nullptr, "bad arguments");
+    HB_REQUIRE(h->row0 == 0 && h->n_rows == h->n_cols, "hb_mad_filter needs the full matrix on one device");
+    int rc = hb_use_device(h);
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    const int64_t n = h->n_cols;
+    const int nseg = h->nseg;
+    if (n == 0) return HB_OK;
+    double *d_rs, *d_dg, *d_pts, *d_diff, *d_abs, *d_z = nullptr, *d_med, *d_mad;
+    uint8_t* d_mask;
+    HbSelState* d_st;
+    unsigned int* d_hist;
+    HB_CUDA(cudaMalloc(&d_rs, sizeof(double) * n));
+    HB_CUDA(cudaMalloc(&d_dg, sizeof(double) * n));
+    HB_CUDA(cudaMalloc(&d_pts, sizeof(double) * n));
+    HB_CUDA(cudaMalloc(&d_diff, sizeof(double) * n));
+    HB_CUDA(cudaMalloc(&d_abs, sizeof(double) * n));
+    if (zscore_out) HB_CUDA(cudaMalloc(&d_z, sizeof(double) * n));
+    HB_CUDA(cudaMalloc(&d_med, sizeof(double) * nseg));
+    HB_CUDA(cudaMalloc(&d_mad, sizeof(double) * nseg));
+    HB_CUDA(cudaMalloc(&d_mask, n));
+    HB_CUDA(cudaMalloc(&d_st, sizeof(HbSelState) * 2 * nseg));
+    HB_CUDA(cudaMalloc(&d_hist, sizeof(unsigned int) * 256 * nseg));
+    HB_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned int) * 256 * nseg, s));
+    // with segments set, the statistics are those of each chromosome's diagonal block (hicCorrectMatrix.py:557-568)
+    hb_row_stats_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, h->n_rows, h->row0,
+                                                       h->d_seg_off, nseg, 1, d_rs, d_dg);
+    HB_LAUNCH_CHECK();
+    hb_points_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_rs, d_dg, d_pts, n);
+    HB_LAUNCH_CHECK();
+    rc = hb_segment_median(h, d_pts, 0, d_st, d_hist, d_med);
+    if (rc == HB_OK) {
+        hb_diff_kernel<<<h->n_tiles, 256, 0, s>>>(d_pts, h->d_tile_row0, h->d_tile_len, h->d_tile_seg, d_med, d_diff, d_abs);
+        g_hb_launches.fetch_add(1);
+        rc = hb_segment_median(h, d_abs, 1, d_st, d_hist, d_mad);
+    }
+    if (rc == HB_OK) {
+        hb_zscore_kernel<<<h->n_tiles, 256, 0, s>>>(d_diff, h->d_tile_row0, h->d_tile_len, h->d_tile_seg, d_mad, lo, hi, d_z, d_mask);
+        g_hb_launches.fetch_add(1);
+    }
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (rc == HB_OK && e == cudaSuccess) {
+        e = cudaMemcpy(mask_out, d_mask, n, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && zscore_out) e = cudaMemcpy(zscore_out, d_z, sizeof(double) * n, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && median_out) e = cudaMemcpy(median_out, d_med, sizeof(double) * nseg, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && mad_out) e = cudaMemcpy(mad_out, d_mad, sizeof(double) * nseg, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_rs); cudaFree(d_dg); cudaFree(d_pts); cudaFree(d_diff); cudaFree(d_abs); cudaFree(d_z);
+    cudaFree(d_med); cudaFree(d_mad); cudaFree(d_mask); cudaFree(d_st); cudaFree(d_hist);
+    if (rc) return rc;
+    if (e != cudaSuccess) return hb_cuda_fail(e, "mad filter", __FILE__, __LINE__);
+    return HB_OK;
+}
+
+int hb_csr_compact(hb_csr* h, const uint8_t* remove_mask) {
+    HB_REQUIRE(h != nullptr && remove_mask != nullptr, "bad arguments");
+    HB_REQUIRE(h->row0 == 0 && h->n_rows == h->n_cols, "hb_csr_compact needs the full matrix on one device");
+    int rc = hb_use_device(h);
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    const int64_t n = h->n_cols;
+    if (n == 0) return HB_OK;
+    // new segment offsets + new size from the host mask
+    std::vector<int64_t> new_off(h->nseg + 1, 0);
+    int64_t kept = 0;
+    {
+        int sgi = 0;
+        for (int64_t i = 0; i <= n; ++i) {
+            while (sgi <= h->nseg && h->seg_off[sgi] == i) new_off[sgi++] = kept;
+            if (i < n && !remove_mask[i]) ++kept;
+        }
+    }
+    uint8_t* d_rm = nullptr;
+    int32_t *d_keep = nullptr, *d_newid = nullptr;
+    int64_t* d_scan = nullptr;
+    HB_CUDA(cudaMalloc(&d_rm, n));
+    HB_CUDA(cudaMalloc(&d_keep, sizeof(int32_t) * n));
+    HB_CUDA(cudaMalloc(&d_newid, sizeof(int32_t) * n));
+    HB_CUDA(cudaMalloc(&d_scan, sizeof(int64_t) * (n + 1)));
+    HB_CUDA(cudaMemcpyAsync(d_rm, remove_mask, n, cudaMemcpyHostToDevice, s));
+    const unsigned g = (unsigned)((n + 255) / 256);
+    hb_keepflag_kernel<<<g, 256, 0, s>>>(d_rm, d_keep, n);
+    HB_LAUNCH_CHECK();
+    hb_scan_kernel<int32_t><<<1, 1024, 0, s>>>(d_keep, d_scan, n);
+    HB_LAUNCH_CHECK();
+    hb_newid_kernel<<<g, 256, 0, s>>>(d_rm, d_scan, d_newid, n);
+    HB_LAUNCH_CHECK();
+    rc = hb_compact_impl(h, d_newid, kept, 0, 0);
+    cudaFree(d_rm);
+    cudaFree(d_keep);
+    cudaFree(d_newid);
+    cudaFree(d_scan);
+    if (rc) return rc;
+    hb_free_state(h);
+    h->seg_off = new_off;
+    return hb_build_tiles(h);
+}
+
+int hb_csr_keep_cis(hb_csr* h) {
+    HB_REQUIRE(h != nullptr, "null handle");
+    int rc = hb_use_device(h);
+    if (rc) return rc;
+    if (h->nseg <= 1) return HB_OK;
+    return hb_compact_impl(h, nullptr, 0, 1, 0);
+}
+
+int hb_diag_zero(hb_csr* h) {
+    HB_REQUIRE(h != nullptr, "null handle");
+    int rc = hb_use_device(h);
+    if (rc) return rc;
+    return hb_compact_impl(h, nullptr, 0, 0, 1);
+}
+
+int hb_symmetry(hb_csr* h, double* ratio_out) {
+    HB_REQUIRE(h != nullptr && ratio_out != nullptr, "bad arguments");
+    HB_REQUIRE(h->row0 == 0 && h->n_rows == h->n_cols, "hb_symmetry needs the full matrix on one device");
+    int rc = hb_use_device(h);
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    double* d_sums = nullptr;
+    HB_CUDA(cudaMalloc(&d_sums, sizeof(double) * 2));
+    HB_CUDA(cudaMemsetAsync(d_sums, 0, sizeof(double) * 2, s));
+    if (h->nnz > 0) {
+        hb_symmetry_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, h->n_rows, d_sums);
+        g_hb_launches.fetch_add(1);
+    }
+    double sums[2] = {0, 0};
+    cudaError_t e = cudaMemcpyAsync(sums, d_sums, sizeof(sums), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(d_sums);
+    if (e != cudaSuccess) return hb_cuda_fail(e, "symmetry", __FILE__, __LINE__);
+    const double cells = (double)h->n_cols * (double)h->n_cols;
+    const double num = sums[0] / cells;
+    double den = sums[1] / cells;
+    if (den < 0) den = -den;
+    *ratio_out = num / (1.0 * den);
+    return HB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,462 @@
+// ICE iterative correction on the device CSR store.
+// Replaces hicexplorer/iterativeCorrection.py:10-86 of the reference (see include/hicbalance.h).
+//
+// Formulation.  The reference rescales W in place every iteration (lines 56-57):
+//   W_k = A o (r_k r_k^T),  r_k = prod_{m<=k} 1/s_m .
+// Its next marginals (line 42) are therefore s_{k+1} = r_k o (A r_k): ONE SpMV with the original
+// matrix per iteration, 12 B per stored entry, nothing written back.  The rescaled values exist
+// only in registers, where their maximum is taken for the 1e100 guard (line 58).  The matrix is
+// materialised once, after convergence (hb_dev_ice_emit; lines 79-80).
+//
+// Per iteration: hb_spmv_kernel<IceEpi>  ->  hb_ice_reduce_kernel  ->  hb_ice_update_kernel.
+// Between the first and the second, a sharded run sum-allreduces the exchange vector (each rank
+// has written only its own rows, the rest is zero); the two O(n) kernels then run identically on
+// every rank.  Convergence lives on the device (per-segment flags), the host only polls.
+#include "hb_spmv.cuh"
+
+struct HbIceEpi {
+    const double* __restrict__ r;
+    double* __restrict__ exch;
+    unsigned long long* wmax_slot;  // bits of a non-negative double
+    const int64_t* __restrict__ seg_off;
+    const int32_t* __restrict__ seg_done;
+    int nseg;
+    double wmax;  // per-thread running maximum (lane 0)
+
+    __device__ __forceinline__ bool active(int64_t g) const {
+        if (nseg <= 1) return true;
+        int lo = 0, hi = nseg;  // largest s with seg_off[s] <= g
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (seg_off[mid] <= g) lo = mid; else hi = mid;
+        }
+        return seg_done[lo] == 0;
+    }
+    __device__ __forceinline__ void row(int64_t g, double t, double m) {
+        const double rg = r[g];
+        exch[g] = rg * t;
+        wmax = fmax(wmax, rg * m);  // NaN-ignoring, like np.any(W.data > 1e100)
+    }
+    __device__ __forceinline__ void warp_done() const {
+        if (wmax > 0.0) atomicMax(wmax_slot, (unsigned long long)__double_as_longlong(wmax));
+    }
+};
+
+// Block-wide fixed-order sum of two values; result valid in thread 0.
+__device__ __forceinline__ void hb_block_sum2(double& a, double& b, double* smem /* 2*32 */) {
+    a = hb_warp_sum(a);
+    b = hb_warp_sum(b);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (lane == 0) {
+        smem[w] = a;
+        smem[32 + w] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sa = 0.0, sb = 0.0;
+        for (int i = 0; i < nw; ++i) {
+            sa += smem[i];
+            sb += smem[32 + i];
+        }
+        a = sa;
+        b = sb;
+    }
+}
+
+// tile_sum/tile_cnt = sum / count of the non-zero entries of vec in each fixed tile; the last
+// block to finish combines the tiles of every segment (in tile order) into seg_out = sum / count.
+// Used for the marginal mean (iterativeCorrection.py:43-44) and the final bias mean (line 77).
+__global__ void __launch_bounds__(256)
+hb_ice_reduce_kernel(const double* __restrict__ vec, const int64_t* __restrict__ tile_row0,
+                     const int32_t* __restrict__ tile_len, const int32_t* __restrict__ tile_seg,
+                     const int32_t* __restrict__ seg_tile0, int nseg, const int32_t* __restrict__ seg_done,
+                     double* __restrict__ tile_sum, double* __restrict__ tile_cnt, double* __restrict__ seg_out,
+                     unsigned int* counter, int32_t* status, const double* __restrict__ wmax_slots, int world) {
+    __shared__ double smem[64];
+    __shared__ int s_last;
+    if (status != nullptr && status[HB_ST_ALL_DONE] != 0) return;
+    const int t = blockIdx.x;
+    const int seg = tile_seg[t];
+    double s = 0.0, c = 0.0;
+    if (seg_done == nullptr || seg_done[seg] == 0) {
+        const int64_t r0 = tile_row0[t];
+        const int len = tile_len[t];
+        for (int i = threadIdx.x; i < len; i += blockDim.x) {
+            const double v = vec[r0 + i];
+            if (v != 0.0) {
+                s += v;
+                c += 1.0;
+            }
+        }
+    }
+    hb_block_sum2(s, c, smem);
+    if (threadIdx.x == 0) {
+        tile_sum[t] = s;
+        tile_cnt[t] = c;
+        __threadfence();
+        s_last = (atomicAdd(counter, 1u) == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int sg = 0; sg < nseg; ++sg) {
+        double a = 0.0, b = 0.0;
+        for (int i = seg_tile0[sg] + threadIdx.x; i < seg_tile0[sg + 1]; i += blockDim.x) {
+            a += __ldcg(tile_sum + i);
+            b += __ldcg(tile_cnt + i);
+        }
+        hb_block_sum2(a, b, smem);
+        if (threadIdx.x == 0) seg_out[sg] = a / b;
+    }
+    if (threadIdx.x == 0) {
+        *counter = 0u;
+        if (wmax_slots != nullptr && status != nullptr) {
+            double wm = 0.0;
+            for (int w = 0; w < world; ++w) wm = fmax(wm, wmax_slots[w]);
+            if (wm > 1e100) {  // iterativeCorrection.py:58
+                status[HB_ST_OVERFLOW] = 1;
+                status[HB_ST_ALL_DONE] = 1;
+            }
+        }
+    }
+}
+
+// s = s_raw / mean ; bias *= s ; deviation = max|s - 1| ; r *= 1/s   (iterativeCorrection.py:44-57)
+__global__ void __launch_bounds__(256)
+hb_ice_update_kernel(const double* __restrict__ exch, const int64_t* __restrict__ tile_row0,
+                     const int32_t* __restrict__ tile_len, const int32_t* __restrict__ tile_seg, int nseg,
+                     const double* __restrict__ seg_mean, double* __restrict__ bias, double* __restrict__ r,
+                     unsigned long long* seg_devbits, double* seg_dev, int32_t* seg_done, int32_t* seg_iters,
+                     unsigned int* counter, int32_t* status, double tol) {
+    __shared__ unsigned long long smax[32];
+    __shared__ int s_last;
+    if (status[HB_ST_ALL_DONE] != 0) return;
+    const int t = blockIdx.x;
+    const int seg = tile_seg[t];
+    if (seg_done[seg] == 0) {
+        const double mean = seg_mean[seg];
+        const int64_t r0 = tile_row0[t];
+        const int len = tile_len[t];
+        unsigned long long dmax = 0ull;
+        for (int i = threadIdx.x; i < len; i += blockDim.x) {
+            const int64_t g = r0 + i;
+            const double sraw = exch[g];
+            const double s = sraw / mean;
+            bias[g] *= s;
+            const unsigned long long d = (unsigned long long)__double_as_longlong(fabs(s - 1.0));
+            dmax = d > dmax ? d : dmax;  // NaN bits sort above +inf: a NaN deviation never converges, like numpy
+            r[g] = (sraw == 0.0) ? 0.0 : r[g] * (1.0 / s);
+        }
+        dmax = hb_warp_max_u64(dmax);
+        if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = dmax;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int i = 1; i < (int)(blockDim.x >> 5); ++i) dmax = smax[i] > dmax ? smax[i] : dmax;
+            atomicMax(seg_devbits + seg, dmax);
+        }
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(counter, 1u) == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    __shared__ int s_active;
+    if (threadIdx.x == 0) s_active = 0;
+    __syncthreads();
+    int my_active = 0;
+    for (int sg = threadIdx.x; sg < nseg; sg += blockDim.x) {
+        if (seg_done[sg] == 0) {
+            const double dev = __longlong_as_double((long long)__ldcg(seg_devbits + sg));
+            seg_dev[sg] = dev;
+            seg_devbits[sg] = 0ull;
+            seg_iters[sg] += 1;
+            if (dev < tol) seg_done[sg] = 1;  // strict '<', tested after the rescale (line 72)
+            else my_active += 1;
+        }
+    }
+    if (my_active) atomicAdd(&s_active, my_active);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *counter = 0u;
+        status[HB_ST_ITER] += 1;
+        status[HB_ST_ACTIVE] = s_active;
+        if (s_active == 0) status[HB_ST_ALL_DONE] = 1;
+    }
+}
+
+__global__ void hb_ice_begin_kernel(double* bias, double* r, int64_t n, unsigned long long* seg_devbits, double* seg_dev,
+                                    int32_t* seg_done, int32_t* seg_iters, double* seg_corr, int nseg, int32_t* status,
+                                    unsigned int* counters, unsigned long long* row_counters) {
+    const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = i0; i < n; i += stride) {
+        bias[i] = 1.0;
+        r[i] = 1.0;
+    }
+    for (int64_t i = i0; i < nseg; i += stride) {
+        seg_devbits[i] = 0ull;
+        seg_dev[i] = __longlong_as_double(0x7ff8000000000000LL);
+        seg_done[i] = 0;
+        seg_iters[i] = 0;
+        seg_corr[i] = 1.0;
+    }
+    if (i0 == 0) {
+        for (int k = 0; k < HB_ST_WORDS; ++k) status[k] = 0;
+        status[HB_ST_ACTIVE] = nseg;
+        counters[0] = counters[1] = 0u;
+        row_counters[0] = row_counters[1] = 0ull;
+    }
+}
+
+// bias /= corr  (iterativeCorrection.py:78)
+__global__ void __launch_bounds__(256)
+hb_ice_scale_bias_kernel(double* __restrict__ bias, const int64_t* __restrict__ tile_row0,
+                         const int32_t* __restrict__ tile_len, const int32_t* __restrict__ tile_seg,
+                         const double* __restrict__ seg_corr) {
+    const int t = blockIdx.x;
+    const double corr = seg_corr[tile_seg[t]];
+    const int64_t r0 = tile_row0[t];
+    for (int i = threadIdx.x; i < tile_len[t]; i += blockDim.x) bias[r0 + i] = bias[r0 + i] / corr;
+}
+
+// W_ij = ((A_ij * r_i) * r_j) * corr * corr  (lines 56-57, 79); running maxima of the value before
+// and after the corr^2 factor for the two overflow guards (lines 58, 80).
+__global__ void __launch_bounds__(256)
+hb_ice_emit_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
+                   int64_t n_rows, int64_t row0, const double* __restrict__ r, const int64_t* __restrict__ seg_off,
+                   const double* __restrict__ seg_corr, int nseg, double* __restrict__ out,
+                   unsigned long long* max_bits /* [0] before corr, [1] after */) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    double m0 = 0.0, m1 = 0.0;
+    for (int64_t row = gwarp; row < n_rows; row += nwarps) {
+        const int64_t g = row0 + row;
+        int lo = 0, hi = nseg;
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (seg_off[mid] <= g) lo = mid; else hi = mid;
+        }
+        const double corr = seg_corr[lo];
+        const double ri = r[g];
+        const int64_t s = indptr[row], e = indptr[row + 1];
+        for (int64_t k = s + lane; k < e; k += 32) {
+            const double w = (hb_ldg_stream_d1(val + k) * ri) * __ldg(r + hb_ldg_stream_i1(idx + k));
+            const double f = w * corr * corr;
+            out[k] = f;
+            m0 = fmax(m0, w);
+            m1 = fmax(m1, f);
+        }
+    }
+    m0 = hb_warp_max(m0);
+    m1 = hb_warp_max(m1);
+    if (lane == 0) {
+        if (m0 > 0.0) atomicMax(max_bits + 0, (unsigned long long)__double_as_longlong(m0));
+        if (m1 > 0.0) atomicMax(max_bits + 1, (unsigned long long)__double_as_longlong(m1));
+    }
+}
+
+static cudaStream_t pick_stream(hb_csr* h, void* stream) { return stream ? (cudaStream_t)stream : h->stream; }
+
+extern "C" {
+
+int hb_dev_ice_begin(hb_csr* h, void* stream) {
+    HB_REQUIRE(h != nullptr, "null handle");
+    int rc = hb_ensure_state(h);
+    if (rc) return rc;
+    cudaStream_t s = pick_stream(h, stream);
+    int64_t n = h->n_cols;
+    int grid = (int)((n + 255) / 256);
+    if (grid < 1) grid = 1;
+    if (grid > HB_NUM_SMS * 8) grid = HB_NUM_SMS * 8;
+    hb_ice_begin_kernel<<<grid, 256, 0, s>>>(h->d_bias, h->d_r, n, h->d_seg_devbits, h->d_seg_dev, h->d_seg_done,
+                                             h->d_seg_iters, h->d_seg_corr, h->nseg, h->d_status, h->d_counters,
+                                             h->d_row_counter);
+    HB_LAUNCH_CHECK();
+    return HB_OK;
+}
+
+int hb_dev_ice_spmv(hb_csr* h, double* d_exch, int rank, int world, void* stream) {
+    HB_REQUIRE(h != nullptr && h->state_ready, "call hb_dev_ice_begin first");
+    HB_REQUIRE(world >= 1 && world <= 64 && rank >= 0 && rank < world, "bad rank/world");
+    cudaStream_t s = pick_stream(h, stream);
+    if (d_exch == nullptr) d_exch = h->d_exch;
+    if (world > 1)
+        HB_CUDA(cudaMemsetAsync(d_exch, 0, sizeof(double) * (size_t)(h->n_cols + world), s));
+    else
+        HB_CUDA(cudaMemsetAsync(d_exch + h->n_cols, 0, sizeof(double), s));
+    if (h->n_rows == 0) return HB_OK;
+    HbIceEpi epi;
+    epi.r = h->d_r;
+    epi.exch = d_exch;
+    epi.wmax_slot = reinterpret_cast<unsigned long long*>(d_exch + h->n_cols + rank);
+    epi.seg_off = h->d_seg_off;
+    epi.seg_done = h->d_seg_done;
+    epi.nseg = h->nseg;
+    epi.wmax = 0.0;
+    // the two row counters alternate between consecutive launches on this handle
+    int p = h->spmv_parity;
+    h->spmv_parity ^= 1;
+    hb_spmv_kernel<HbIceEpi, true><<<hb_spmv_grid(h->n_rows), HB_SPMV_THREADS, 0, s>>>(
+        h->d_indptr, h->d_indices, h->d_data, h->n_rows, h->row0, h->d_r, h->d_row_counter, p, h->d_status, epi);
+    HB_LAUNCH_CHECK();
+    return HB_OK;
+}
+
+int hb_dev_ice_update(hb_csr* h, const double* d_exch, int world, double tol, void* stream) {
+    HB_REQUIRE(h != nullptr && h->state_ready, "call hb_dev_ice_begin first");
+    cudaStream_t s = pick_stream(h, stream);
+    if (d_exch == nullptr) d_exch = h->d_exch;
+    if (h->n_tiles == 0) return HB_OK;
+    hb_ice_reduce_kernel<<<h->n_tiles, 256, 0, s>>>(d_exch, h->d_tile_row0, h->d_tile_len, h->d_tile_seg,
+                                                     h->d_seg_tile0, h->nseg, h->d_seg_done, h->d_tile_sum,
+                                                     h->d_tile_cnt, h->d_seg_mean, h->d_counters + 0, h->d_status,
+                                                     d_exch + h->n_cols, world);
+    HB_LAUNCH_CHECK();
+    hb_ice_update_kernel<<<h->n_tiles, 256, 0, s>>>(d_exch, h->d_tile_row0, h->d_tile_len, h->d_tile_seg, h->nseg,
+                                                     h->d_seg_mean, h->d_bias, h->d_r, h->d_seg_devbits, h->d_seg_dev,
+                                                     h->d_seg_done, h->d_seg_iters, h->d_counters + 1, h->d_status, tol);
+    HB_LAUNCH_CHECK();
+    return HB_OK;
+}
+
+int hb_dev_ice_status(hb_csr* h, int32_t* pinned_status4, void* stream) {
+    HB_REQUIRE(h != nullptr && h->state_ready && pinned_status4 != nullptr, "bad arguments");
+    HB_CUDA(cudaMemcpyAsync(pinned_status4, h->d_status, sizeof(int32_t) * HB_ST_WORDS, cudaMemcpyDeviceToHost,
+                            pick_stream(h, stream)));
+    return HB_OK;
+}
+
+int hb_dev_ice_finish(hb_csr* h, void* stream) {
+    HB_REQUIRE(h != nullptr && h->state_ready, "call hb_dev_ice_begin first");
+    cudaStream_t s = pick_stream(h, stream);
+    if (h->n_tiles == 0) return HB_OK;
+    hb_ice_reduce_kernel<<<h->n_tiles, 256, 0, s>>>(h->d_bias, h->d_tile_row0, h->d_tile_len, h->d_tile_seg,
+                                                     h->d_seg_tile0, h->nseg, nullptr, h->d_tile_sum, h->d_tile_cnt,
+                                                     h->d_seg_corr, h->d_counters + 0, nullptr, nullptr, 0);
+    HB_LAUNCH_CHECK();
+    hb_ice_scale_bias_kernel<<<h->n_tiles, 256, 0, s>>>(h->d_bias, h->d_tile_row0, h->d_tile_len, h->d_tile_seg,
+                                                         h->d_seg_corr);
+    HB_LAUNCH_CHECK();
+    return HB_OK;
+}
+
+int hb_dev_ice_emit(hb_csr* h, double* d_out, double* d_max, void* stream) {
+    HB_REQUIRE(h != nullptr && h->state_ready && d_out != nullptr, "bad arguments");
+    cudaStream_t s = pick_stream(h, stream);
+    HB_CUDA(cudaMemsetAsync(h->d_scalar_bits, 0, sizeof(unsigned long long) * 2, s));
+    if (h->n_rows > 0 && h->nnz > 0) {
+        hb_ice_emit_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, h->n_rows, h->row0,
+                                                          h->d_r, h->d_seg_off, h->d_seg_corr, h->nseg, d_out,
+                                                          h->d_scalar_bits);
+        HB_LAUNCH_CHECK();
+    }
+    if (d_max)
+        HB_CUDA(cudaMemcpyAsync(d_max, h->d_scalar_bits, sizeof(double) * 2, cudaMemcpyDeviceToDevice, s));
+    return HB_OK;
+}
+
+int hb_dev_ice_vectors(hb_csr* h, double** d_bias, double** d_r) {
+    HB_REQUIRE(h != nullptr, "null handle");
+    int rc = hb_ensure_state(h);
+    if (rc) return rc;
+    if (d_bias) *d_bias = h->d_bias;
+    if (d_r) *d_r = h->d_r;
+    return HB_OK;
+}
+
+int hb_ice_results(hb_csr* h, double* bias_out, int32_t* iters_out, double* dev_out) {
+    HB_REQUIRE(h != nullptr && h->state_ready, "no ICE state");
+    int rc = hb_use_device(h);
+    if (rc) return rc;
+    HB_CUDA(cudaStreamSynchronize(h->stream));
+    if (bias_out && h->n_cols)
+        HB_CUDA(cudaMemcpy(bias_out, h->d_bias, sizeof(double) * (size_t)h->n_cols, cudaMemcpyDeviceToHost));
+    if (iters_out) HB_CUDA(cudaMemcpy(iters_out, h->d_seg_iters, sizeof(int32_t) * h->nseg, cudaMemcpyDeviceToHost));
+    if (dev_out) HB_CUDA(cudaMemcpy(dev_out, h->d_seg_dev, sizeof(double) * h->nseg, cudaMemcpyDeviceToHost));
+    return HB_OK;
+}
+
+int hb_ice_run(hb_csr* h, int max_iter, double tol, double* bias_out, int32_t* iters_out, double* dev_out) {
+    HB_REQUIRE(h != nullptr, "null handle");
+    HB_REQUIRE(h->world > 1 || (h->row0 == 0 && h->n_rows == h->n_cols),
+               "hb_ice_run needs the full matrix on one device unless hb_set_comm was called");
+    HB_REQUIRE(max_iter >= 0, "negative iteration count");
+    int rc = hb_use_device(h);
+    if (rc) return rc;
+    rc = hb_dev_ice_begin(h, nullptr);
+    if (rc) return rc;
+    const int LAG = 4, SLOTS = 16;
+    cudaEvent_t ev[SLOTS];
+    for (int i = 0; i < SLOTS; ++i) HB_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    bool stop = false;
+    for (int k = 0; k < max_iter && !stop; ++k) {
+        rc = hb_dev_ice_spmv(h, nullptr, h->rank, h->world, nullptr);
+        if (rc == HB_OK && h->world > 1) {
+            // the one exchange of the iteration: marginals + per-rank maxima, summed over the ranks
+            if (h->allreduce(h->comm_ctx, h->d_exch, h->n_cols + h->world, (void*)h->stream) != 0) {
+                hb_set_error("collective callback failed");
+                rc = HB_ERR_CUDA;
+            }
+        }
+        if (rc == HB_OK) rc = hb_dev_ice_update(h, nullptr, h->world, tol, nullptr);
+        if (rc == HB_OK) rc = hb_dev_ice_status(h, h->h_status + (k % SLOTS) * HB_ST_WORDS, nullptr);
+        if (rc != HB_OK) break;
+        cudaEventRecord(ev[k % SLOTS], h->stream);
+        if (k >= LAG) {
+            // look at the status of iteration k-LAG: the device queue stays LAG iterations deep and
+            // iterations enqueued after convergence are no-ops (every kernel returns on ALL_DONE)
+            int j = (k - LAG) % SLOTS;
+            cudaEventSynchronize(ev[j]);
+            if (h->h_status[j * HB_ST_WORDS + HB_ST_ALL_DONE]) stop = true;
+        }
+    }
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    for (int i = 0; i < SLOTS; ++i) cudaEventDestroy(ev[i]);
+    if (rc != HB_OK) return rc;
+    if (e != cudaSuccess) return hb_cuda_fail(e, "ICE loop", __FILE__, __LINE__);
+    int32_t st[HB_ST_WORDS];
+    HB_CUDA(cudaMemcpy(st, h->d_status, sizeof(st), cudaMemcpyDeviceToHost));
+    if (st[HB_ST_OVERFLOW]) {
+        hb_set_error("matrix correction is producing extremely large values (> 1e100)");
+        return HB_ERR_OVERFLOW_ITER;
+    }
+    rc = hb_dev_ice_finish(h, nullptr);
+    if (rc) return rc;
+    return hb_ice_results(h, bias_out, iters_out, dev_out);
+}
+
+int hb_ice_scaled_values(hb_csr* h, double* data_out, double* max_out) {
+    HB_REQUIRE(h != nullptr && h->state_ready, "run ICE first");
+    HB_REQUIRE(data_out != nullptr || h->nnz == 0, "null output");
+    int rc = hb_use_device(h);
+    if (rc) return rc;
+    double* d_out = nullptr;
+    HB_CUDA(cudaMalloc(&d_out, sizeof(double) * (size_t)(h->nnz > 0 ? h->nnz : 1)));
+    rc = hb_dev_ice_emit(h, d_out, nullptr, nullptr);
+    double mx[2] = {0.0, 0.0};
+    cudaError_t e = cudaSuccess;
+    if (rc == HB_OK) {
+        e = cudaStreamSynchronize(h->stream);
+        if (e == cudaSuccess && h->nnz) e = cudaMemcpy(data_out, d_out, sizeof(double) * (size_t)h->nnz, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(mx, h->d_scalar_bits, sizeof(mx), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_out);
+    if (rc) return rc;
+    if (e != cudaSuccess) return hb_cuda_fail(e, "emit", __FILE__, __LINE__);
+    if (max_out) *max_out = mx[1];
+    if (mx[0] > 1e100) {
+        hb_set_error("matrix correction is producing extremely large values (> 1e100)");
+        return HB_ERR_OVERFLOW_ITER;
+    }
+    if (mx[1] > 1e10) {
+        hb_set_error("matrix correction produced extremely large values (> 1e10)");
+        return HB_ERR_OVERFLOW_FINAL;
+    }
+    return HB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,140 @@
+// Internal declarations shared by the libhicbalance translation units.
+// Public contract: include/hicbalance.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "hicbalance.h"
+
+#define HB_NUM_SMS 148          // B200: 2 dies x 74 SMs
+#define HB_SPMV_THREADS 256     // 8 warps per CTA
+#define HB_SPMV_CTAS_PER_SM 4   // 32 resident warps per SM, <= 64 regs/thread
+#define HB_ROWS_PER_GRAB 4      // rows a warp claims per atomic on the row counter
+#define HB_TILE_ROWS 1024       // fixed reduction tile (rows) -> rank-count independent sums
+#define HB_MAX_SEG 4096
+
+extern std::atomic<uint64_t> g_hb_launches;
+void hb_set_error(const char* fmt, ...);
+int hb_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define HB_CUDA(expr)                                                      \
+    do {                                                                   \
+        cudaError_t _e = (expr);                                           \
+        if (_e != cudaSuccess) return hb_cuda_fail(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+#define HB_LAUNCH_CHECK()                                                  \
+    do {                                                                   \
+        g_hb_launches.fetch_add(1, std::memory_order_relaxed);             \
+        cudaError_t _e = cudaGetLastError();                               \
+        if (_e != cudaSuccess) return hb_cuda_fail(_e, "kernel launch", __FILE__, __LINE__); \
+    } while (0)
+
+#define HB_REQUIRE(cond, msg)                                              \
+    do {                                                                   \
+        if (!(cond)) {                                                     \
+            hb_set_error("%s (%s)", msg, #cond);                           \
+            return HB_ERR_INVALID_ARG;                                     \
+        }                                                                  \
+    } while (0)
+
+// status words kept on the device (int32 each)
+enum { HB_ST_ALL_DONE = 0, HB_ST_OVERFLOW = 1, HB_ST_ITER = 2, HB_ST_ACTIVE = 3, HB_ST_WORDS = 4 };
+
+struct hb_csr {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_csr = true;
+    int64_t n_rows = 0, n_cols = 0, row0 = 0, nnz = 0;
+    int64_t* d_indptr = nullptr;
+    int32_t* d_indices = nullptr;
+    double* d_data = nullptr;
+
+    // sharded runs: the one collective of the path is delegated to the host (torch.distributed / NCCL)
+    int rank = 0, world = 1;
+    hb_allreduce_fn allreduce = nullptr;
+    void* comm_ctx = nullptr;
+
+    // segments (independent diagonal blocks) and fixed reduction tiles over GLOBAL rows
+    int nseg = 1;
+    std::vector<int64_t> seg_off;      // nseg+1
+    int64_t* d_seg_off = nullptr;      // nseg+1
+    int n_tiles = 0;
+    int64_t* d_tile_row0 = nullptr;    // n_tiles
+    int32_t* d_tile_len = nullptr;     // n_tiles
+    int32_t* d_tile_seg = nullptr;     // n_tiles
+    int32_t* d_seg_tile0 = nullptr;    // nseg+1
+
+    // replicated n_cols-vectors and per-segment scalars (lazily allocated)
+    bool state_ready = false;
+    double* d_bias = nullptr;          // n_cols
+    double* d_r = nullptr;             // n_cols
+    double* d_exch = nullptr;          // n_cols + 64 (single-GPU exchange buffer)
+    double* d_tile_sum = nullptr;      // n_tiles
+    double* d_tile_cnt = nullptr;      // n_tiles
+    double* d_seg_mean = nullptr;      // nseg
+    double* d_seg_corr = nullptr;      // nseg (final bias normalisation)
+    unsigned long long* d_seg_devbits = nullptr;  // nseg
+    double* d_seg_dev = nullptr;       // nseg (last deviation)
+    int32_t* d_seg_done = nullptr;     // nseg
+    int32_t* d_seg_iters = nullptr;    // nseg
+    int32_t* d_status = nullptr;       // HB_ST_WORDS
+    unsigned int* d_counters = nullptr;          // [0] reduce tiles done, [1] update tiles done
+    unsigned long long* d_row_counter = nullptr; // dynamic row scheduler (two counters, alternating)
+    int spmv_parity = 0;
+    unsigned long long* d_scalar_bits = nullptr; // 8 scratch words
+    int32_t* h_status = nullptr;       // pinned, 16 slots x HB_ST_WORDS
+};
+
+int hb_build_tiles(hb_csr* h);
+int hb_ensure_state(hb_csr* h);
+void hb_free_state(hb_csr* h);
+int hb_use_device(const hb_csr* h);
+int hb_spmv_grid(int64_t n_rows);
+
+// ---- device helpers ---------------------------------------------------------
+__device__ __forceinline__ int4 hb_ldg_stream_i4(const int32_t* p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ double2 hb_ldg_stream_d2(const double* p) {
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ int hb_ldg_stream_i1(const int32_t* p) {
+    int r;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ double hb_ldg_stream_d1(const double* p) {
+    double r;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ double hb_warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double hb_warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ unsigned long long hb_warp_max_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = t > v ? t : v;
+    }
+    return v;
+}

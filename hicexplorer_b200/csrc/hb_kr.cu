@@ -1,0 +1,736 @@
+// Knight-Ruiz balancing (Knight & Ruiz 2012, routine `bnewt`: inexact Newton iteration with a
+// conjugate-gradient inner solve and a cone-boundary step limiter) on the device CSR store.
+// Replaces the third-party C++/Eigen object `krbalancing.kr_balancing` that the reference calls at
+// hicexplorer/hicCorrectMatrix.py:718-732, 744-757 (constants, the A + 1e-5*I augmentation and the
+// rescale convention restated in oracle/kr_oracle.py).  Contract: include/hicbalance.h.
+//
+// Device mapping.  Every CG step is ONE hb_spmv_kernel launch with the Hadamard update fused into
+// its row epilogue:  w = x o ((A + eps I)(x o p)) + v o p   (12 B per stored entry, HBM-bound);
+// the remaining work is O(n) vector kernels whose dot products / min / max are reduced over fixed
+// row tiles (deterministic, rank-count independent) into device-resident scalars.  alpha, beta
+// and the step decisions are computed FROM those device scalars, so the host synchronises once
+// per mat-vec (to evaluate the loop conditions), not once per vector operation.
+#include <cmath>
+
+#include "hb_spmv.cuh"
+
+enum {
+    SC_RHO = 0,    // rho_km1
+    SC_RHO2 = 1,   // rho_km2
+    SC_PTW = 2,    // p^T w
+    SC_MIN = 3,    // min(y + alpha p)
+    SC_MAX = 4,    // max(y + alpha p)
+    SC_GAMMA = 5,  // boundary step length
+    SC_ROUT = 6,   // r^T r after the outer update
+    SC_XMIN = 7,   // min(x) (breakdown check)
+    SC_A = 8,      // rescale: sum of (A+eps I) o (x x^T)
+    SC_B = 9,      // rescale: sum of (A+eps I)
+    SC_WORDS = 16
+};
+
+struct HbKrVec {
+    double *x, *y, *p, *z, *rk, *v, *w, *u;
+};
+
+struct HbTiles {
+    const int64_t* __restrict__ row0;
+    const int32_t* __restrict__ len;
+    int n_tiles;
+};
+
+// Generic tiled vector kernel: F::elem runs per row and may contribute to a sum / min / max; the
+// last block to finish folds the per-tile partials in tile order and calls F::finalize (thread 0).
+template <class F>
+__global__ void __launch_bounds__(256)
+hb_kr_vec_kernel(HbTiles tiles, F f, double* __restrict__ part /* 3*n_tiles */, unsigned int* counter, double* sc) {
+    __shared__ double ssum[8], smin[8], smax[8];
+    __shared__ int s_last;
+    if (f.skip(sc)) return;
+    f.prepare(sc);
+    const int t = blockIdx.x;
+    const int64_t r0 = tiles.row0[t];
+    const int len = tiles.len[t];
+    double s = 0.0, mn = INFINITY, mx = -INFINITY;
+    for (int i = threadIdx.x; i < len; i += blockDim.x) f.elem(r0 + i, s, mn, mx);
+    if (!F::REDUCES) return;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    s = hb_warp_sum(s);
+    mx = hb_warp_max(mx);
+    mn = -hb_warp_max(-mn);
+    if (lane == 0) {
+        ssum[w] = s;
+        smin[w] = mn;
+        smax[w] = mx;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) {
+            s += ssum[i];
+            mn = fmin(mn, smin[i]);
+            mx = fmax(mx, smax[i]);
+        }
+        part[3 * t + 0] = s;
+        part[3 * t + 1] = mn;
+        part[3 * t + 2] = mx;
+        __threadfence();
+        s_last = (atomicAdd(counter, 1u) == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    s = 0.0;
+    mn = INFINITY;
+    mx = -INFINITY;
+    for (int i = threadIdx.x; i < tiles.n_tiles; i += blockDim.x) {
+        s += __ldcg(part + 3 * i + 0);
+        mn = fmin(mn, __ldcg(part + 3 * i + 1));
+        mx = fmax(mx, __ldcg(part + 3 * i + 2));
+    }
+    s = hb_warp_sum(s);
+    mx = hb_warp_max(mx);
+    mn = -hb_warp_max(-mn);
+    __syncthreads();
+    if (lane == 0) {
+        ssum[w] = s;
+        smin[w] = mn;
+        smax[w] = mx;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) {
+            s += ssum[i];
+            mn = fmin(mn, smin[i]);
+            mx = fmax(mx, smax[i]);
+        }
+        *counter = 0u;
+        f.finalize(s, mn, mx, sc);
+    }
+}
+
+struct FBase {
+    static constexpr bool REDUCES = true;
+    __device__ __forceinline__ bool skip(const double*) const { return false; }
+    __device__ __forceinline__ void prepare(const double*) {}
+};
+
+// x = 1, y = 1
+struct FInit : FBase {
+    static constexpr bool REDUCES = false;
+    HbKrVec q;
+    __device__ __forceinline__ void elem(int64_t g, double&, double&, double&) const {
+        q.x[g] = 1.0;
+        q.y[g] = 1.0;
+    }
+    __device__ __forceinline__ void finalize(double, double, double, double*) const {}
+};
+
+// rk = 1 - v ; ROUT = RHO = rk^T rk
+struct FResid : FBase {
+    HbKrVec q;
+    __device__ __forceinline__ void elem(int64_t g, double& s, double&, double&) const {
+        const double r = 1.0 - q.v[g];
+        q.rk[g] = r;
+        s += r * r;
+    }
+    __device__ __forceinline__ void finalize(double s, double, double, double* sc) const {
+        sc[SC_ROUT] = s;
+        sc[SC_RHO] = s;
+    }
+};
+
+// k == 1:  Z = rk / v ; p = Z ; u = x o p ; RHO = rk^T Z
+struct FFirst : FBase {
+    HbKrVec q;
+    __device__ __forceinline__ void elem(int64_t g, double& s, double&, double&) const {
+        const double r = q.rk[g];
+        const double z = r / q.v[g];
+        q.z[g] = z;
+        q.p[g] = z;
+        q.u[g] = q.x[g] * z;
+        s += r * z;
+    }
+    __device__ __forceinline__ void finalize(double s, double, double, double* sc) const { sc[SC_RHO] = s; }
+};
+
+// k > 1:  beta = RHO / RHO2 ; p = Z + beta p ; u = x o p
+struct FDir : FBase {
+    static constexpr bool REDUCES = false;
+    HbKrVec q;
+    double beta;
+    __device__ __forceinline__ void prepare(const double* sc) { beta = sc[SC_RHO] / sc[SC_RHO2]; }
+    __device__ __forceinline__ void elem(int64_t g, double&, double&, double&) const {
+        const double p = q.z[g] + __dmul_rn(beta, q.p[g]);
+        q.p[g] = p;
+        q.u[g] = q.x[g] * p;
+    }
+    __device__ __forceinline__ void finalize(double, double, double, double*) const {}
+};
+
+// PTW = p^T w
+struct FDot : FBase {
+    HbKrVec q;
+    __device__ __forceinline__ void elem(int64_t g, double& s, double&, double&) const { s += q.p[g] * q.w[g]; }
+    __device__ __forceinline__ void finalize(double s, double, double, double* sc) const { sc[SC_PTW] = s; }
+};
+
+// alpha = RHO / PTW ; MIN / MAX of ynew = y + alpha p
+struct FYnew : FBase {
+    HbKrVec q;
+    double alpha;
+    __device__ __forceinline__ void prepare(const double* sc) { alpha = sc[SC_RHO] / sc[SC_PTW]; }
+    __device__ __forceinline__ void elem(int64_t g, double&, double& mn, double& mx) const {
+        const double yn = q.y[g] + __dmul_rn(alpha, q.p[g]);
+        mn = fmin(mn, yn);
+        mx = fmax(mx, yn);
+    }
+    __device__ __forceinline__ void finalize(double, double mn, double mx, double* sc) const {
+        sc[SC_MIN] = mn;
+        sc[SC_MAX] = mx;
+    }
+};
+
+// regular CG step (only if no cone bound was hit): y = ynew ; rk -= alpha w ; Z = rk / v ;
+// RHO2 = RHO ; RHO = rk^T Z
+struct FStep : FBase {
+    HbKrVec q;
+    double delta, Delta, alpha;
+    __device__ __forceinline__ bool skip(const double* sc) const { return sc[SC_MIN] <= delta || sc[SC_MAX] >= Delta; }
+    __device__ __forceinline__ void prepare(const double* sc) { alpha = sc[SC_RHO] / sc[SC_PTW]; }
+    __device__ __forceinline__ void elem(int64_t g, double& s, double&, double&) const {
+        q.y[g] = q.y[g] + __dmul_rn(alpha, q.p[g]);
+        const double r = q.rk[g] - __dmul_rn(alpha, q.w[g]);
+        q.rk[g] = r;
+        const double z = r / q.v[g];
+        q.z[g] = z;
+        s += r * z;
+    }
+    __device__ __forceinline__ void finalize(double s, double, double, double* sc) const {
+        sc[SC_RHO2] = sc[SC_RHO];
+        sc[SC_RHO] = s;
+    }
+};
+
+// boundary step length: lower bound  gamma = min_{ap<0} (delta - y)/ap ; upper bound  min_{ynew>Delta} (Delta - y)/ap
+struct FGamma : FBase {
+    HbKrVec q;
+    double bound, alpha;
+    int upper;
+    __device__ __forceinline__ void prepare(const double* sc) { alpha = sc[SC_RHO] / sc[SC_PTW]; }
+    __device__ __forceinline__ void elem(int64_t g, double&, double& mn, double&) const {
+        const double ap = __dmul_rn(alpha, q.p[g]);
+        const double y = q.y[g];
+        const bool sel = upper ? (y + ap > bound) : (ap < 0.0);
+        if (sel) mn = fmin(mn, (bound - y) / ap);
+    }
+    __device__ __forceinline__ void finalize(double, double mn, double, double* sc) const { sc[SC_GAMMA] = mn; }
+};
+
+// y += gamma * (alpha p)
+struct FBoundStep : FBase {
+    static constexpr bool REDUCES = false;
+    HbKrVec q;
+    double alpha, gamma;
+    __device__ __forceinline__ void prepare(const double* sc) {
+        alpha = sc[SC_RHO] / sc[SC_PTW];
+        gamma = sc[SC_GAMMA];
+    }
+    __device__ __forceinline__ void elem(int64_t g, double&, double&, double&) const {
+        q.y[g] = q.y[g] + __dmul_rn(gamma, __dmul_rn(alpha, q.p[g]));
+    }
+    __device__ __forceinline__ void finalize(double, double, double, double*) const {}
+};
+
+// x = x o y ; y = 1 ; XMIN = min(x)
+struct FXUpdate : FBase {
+    HbKrVec q;
+    __device__ __forceinline__ void elem(int64_t g, double&, double& mn, double&) const {
+        const double x = q.x[g] * q.y[g];
+        q.x[g] = x;
+        q.y[g] = 1.0;
+        mn = fmin(mn, x);
+    }
+    __device__ __forceinline__ void finalize(double, double mn, double, double* sc) const { sc[SC_XMIN] = mn; }
+};
+
+// plain sums of two n-vectors (rescale factor)
+struct FSum2 : FBase {
+    const double* a;
+    const double* b;
+    int which;
+    __device__ __forceinline__ void elem(int64_t g, double& s, double&, double&) const { s += which ? b[g] : a[g]; }
+    __device__ __forceinline__ void finalize(double s, double, double, double* sc) const { sc[which ? SC_B : SC_A] = s; }
+};
+
+// per-row sums over the upper triangle of A + eps I, off-diagonals doubled (krbalancing rescale_norm_vector)
+__global__ void __launch_bounds__(256)
+hb_kr_rescale_rows_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
+                          int64_t n_rows, const double* __restrict__ x, double eps, double* __restrict__ scaled,
+                          double* __restrict__ orig) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = gwarp; row < n_rows; row += nwarps) {
+        const double xi = x[row];
+        double so = 0.0, ss = 0.0, dg = 0.0;
+        for (int64_t k = indptr[row] + lane; k < indptr[row + 1]; k += 32) {
+            const int c = idx[k];
+            const double a = val[k];
+            if (c == row) dg += a;
+            else if (c > row) {
+                so += a * 2;
+                ss += a * xi * x[c] * 2;
+            }
+        }
+        so = hb_warp_sum(so);
+        ss = hb_warp_sum(ss);
+        dg = hb_warp_sum(dg);
+        if (lane == 0) {
+            const double d = dg + eps;
+            orig[row] = so + d;
+            scaled[row] = ss + d * xi * xi;
+        }
+    }
+}
+
+// upper triangle (diagonal always stored) of (A + eps I) o (x x^T)
+__global__ void __launch_bounds__(256)
+hb_kr_upper_count_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, int64_t n_rows,
+                         int64_t* __restrict__ cnt) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = gwarp; row < n_rows; row += nwarps) {
+        long long c = 0;
+        for (int64_t k = indptr[row] + lane; k < indptr[row + 1]; k += 32) c += idx[k] > row ? 1 : 0;
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0) cnt[row] = c + 1;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+hb_kr_upper_fill_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
+                        int64_t n_rows, const double* __restrict__ x, double eps, const int64_t* __restrict__ out_ptr,
+                        int32_t* __restrict__ out_idx, double* __restrict__ out_val) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = gwarp; row < n_rows; row += nwarps) {
+        const double xi = x[row];
+        int64_t w = out_ptr[row] + 1;
+        double dg = 0.0;
+        const int64_t s = indptr[row], e = indptr[row + 1];
+        for (int64_t base = s; base < e; base += 32) {
+            const int64_t k = base + lane;
+            int c = -1;
+            double a = 0.0;
+            if (k < e) {
+                c = idx[k];
+                a = val[k];
+            }
+            if (c == row) dg += a;
+            const bool kp = c > row;
+            const unsigned int bal = __ballot_sync(0xffffffffu, kp);
+            if (kp) {
+                const int64_t pos = w + __popc(bal & ((1u << lane) - 1u));
+                out_idx[pos] = c;
+                out_val[pos] = a * xi * x[c];
+            }
+            w += __popc(bal);
+        }
+        dg = hb_warp_sum(dg);
+        if (lane == 0) {
+            out_idx[out_ptr[row]] = (int32_t)row;
+            out_val[out_ptr[row]] = (dg + eps) * xi * xi;
+        }
+    }
+}
+
+// local single-block exclusive scan (same scheme as hb_filter.cu)
+__global__ void __launch_bounds__(1024) hb_kr_scan_kernel(const int64_t* __restrict__ in, int64_t* __restrict__ out, int64_t n) {
+    __shared__ long long part[1024];
+    const int t = threadIdx.x;
+    const int64_t chunk = (n + 1023) / 1024;
+    const int64_t b = t * chunk, e = (b + chunk < n) ? b + chunk : n;
+    long long s = 0;
+    for (int64_t i = b; i < e; ++i) s += in[i];
+    part[t] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        long long v = (t >= o) ? part[t - o] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    long long run = part[t] - s;
+    for (int64_t i = b; i < e; ++i) {
+        const long long v = in[i];
+        out[i] = run;
+        run += v;
+    }
+    if (t == 1023) out[n] = part[1023];
+}
+
+namespace {
+
+struct KrCtx {
+    hb_csr* h;
+    cudaStream_t s;
+    HbKrVec q;
+    HbTiles tiles;
+    double* part;
+    unsigned int* counter;
+    double* sc;       // device scalars
+    double* h_sc;     // pinned mirror
+    double* buf = nullptr;
+};
+
+template <class F>
+int kr_launch(KrCtx& c, F f) {
+    if (c.tiles.n_tiles == 0) return HB_OK;
+    hb_kr_vec_kernel<F><<<c.tiles.n_tiles, 256, 0, c.s>>>(c.tiles, f, c.part, c.counter, c.sc);
+    HB_LAUNCH_CHECK();
+    return HB_OK;
+}
+
+// out = a o ((A + eps I) u) + b o c  over the block's rows, assembled over the ranks
+int kr_spmv(KrCtx& c, const double* u, const double* a, const double* b, const double* cc, double* out, double eps) {
+    hb_csr* h = c.h;
+    if (h->world > 1) HB_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * (size_t)h->n_cols, c.s));
+    if (h->n_rows > 0) {
+        HbAffineEpi epi;
+        epi.u = u;
+        epi.a = a;
+        epi.b = b;
+        epi.c = cc;
+        epi.out = out;
+        epi.eps = eps;
+        int p = h->spmv_parity;
+        h->spmv_parity ^= 1;
+        hb_spmv_kernel<HbAffineEpi, false><<<hb_spmv_grid(h->n_rows), HB_SPMV_THREADS, 0, c.s>>>(
+            h->d_indptr, h->d_indices, h->d_data, h->n_rows, h->row0, u, h->d_row_counter, p, nullptr, epi);
+        HB_LAUNCH_CHECK();
+    }
+    if (h->world > 1) {
+        if (h->allreduce(h->comm_ctx, out, h->n_cols, (void*)c.s) != 0) {
+            hb_set_error("collective callback failed");
+            return HB_ERR_CUDA;
+        }
+    }
+    return HB_OK;
+}
+
+int kr_read_scalars(KrCtx& c) {
+    HB_CUDA(cudaMemcpyAsync(c.h_sc, c.sc, sizeof(double) * SC_WORDS, cudaMemcpyDeviceToHost, c.s));
+    HB_CUDA(cudaStreamSynchronize(c.s));
+    return HB_OK;
+}
+
+}  // namespace
+
+#define KR_TRY(expr)            \
+    do {                        \
+        rc = (expr);            \
+        if (rc != HB_OK) goto done; \
+    } while (0)
+
+extern "C" {
+
+int hb_dev_spmv(hb_csr* h, const double* d_u, double eps, const double* d_a, const double* d_b, const double* d_c,
+                double* d_out, int zero_rest, void* stream) {
+    HB_REQUIRE(h != nullptr && d_u != nullptr && d_out != nullptr, "bad arguments");
+    int rc = hb_ensure_state(h);
+    if (rc) return rc;
+    cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+    if (zero_rest) HB_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * (size_t)h->n_cols, s));
+    if (h->n_rows == 0) return HB_OK;
+    HbAffineEpi epi;
+    epi.u = d_u;
+    epi.a = d_a;
+    epi.b = d_b;
+    epi.c = d_c;
+    epi.out = d_out;
+    epi.eps = eps;
+    int p = h->spmv_parity;
+    h->spmv_parity ^= 1;
+    hb_spmv_kernel<HbAffineEpi, false><<<hb_spmv_grid(h->n_rows), HB_SPMV_THREADS, 0, s>>>(
+        h->d_indptr, h->d_indices, h->d_data, h->n_rows, h->row0, d_u, h->d_row_counter, p, nullptr, epi);
+    HB_LAUNCH_CHECK();
+    return HB_OK;
+}
+
+int hb_kr_run(hb_csr* h, double tol, double delta, double Delta, double diag_eps, int max_outer, double* x_out,
+              int32_t* outer_out, int32_t* matvecs_out, double* residual_out) {
+    HB_REQUIRE(h != nullptr && x_out != nullptr, "bad arguments");
+    HB_REQUIRE(h->world > 1 || (h->row0 == 0 && h->n_rows == h->n_cols),
+               "hb_kr_run needs the full matrix on one device unless hb_set_comm was called");
+    int rc = hb_ensure_state(h);
+    if (rc) return rc;
+    rc = hb_use_device(h);
+    if (rc) return rc;
+    const int64_t n = h->n_cols;
+    if (n == 0) {
+        if (outer_out) *outer_out = 0;
+        if (matvecs_out) *matvecs_out = 0;
+        if (residual_out) *residual_out = 0.0;
+        return HB_OK;
+    }
+    // krbalancing treats the whole matrix as one problem; per-chromosome runs are separate objects
+    HB_REQUIRE(h->nseg == 1, "hb_kr_run works on a single segment (create one store per chromosome block)");
+    KrCtx c;
+    c.h = h;
+    c.s = h->stream;
+    c.tiles.row0 = h->d_tile_row0;
+    c.tiles.len = h->d_tile_len;
+    c.tiles.n_tiles = h->n_tiles;
+    c.counter = h->d_counters + 2;
+    c.h_sc = nullptr;
+    c.sc = nullptr;
+    c.part = nullptr;
+    const double g = 0.9, etamax = 0.1;
+    double eta = etamax, stop_tol = tol * 0.5, rt = tol * tol;
+    double rho_km1 = 0.0, rout = 0.0, rold = 0.0;
+    int outer = 0, mvp = 0;
+    bool breakdown = false;
+    {
+        cudaError_t e = cudaMalloc(&c.buf, sizeof(double) * (size_t)(8 * n + 3 * h->n_tiles + SC_WORDS));
+        if (e != cudaSuccess) return hb_cuda_fail(e, "cudaMalloc KR vectors", __FILE__, __LINE__);
+        e = cudaHostAlloc((void**)&c.h_sc, sizeof(double) * SC_WORDS, cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            cudaFree(c.buf);
+            return hb_cuda_fail(e, "cudaHostAlloc", __FILE__, __LINE__);
+        }
+    }
+    {
+        double* b = c.buf;
+        c.q.x = b; b += n;
+        c.q.y = b; b += n;
+        c.q.p = b; b += n;
+        c.q.z = b; b += n;
+        c.q.rk = b; b += n;
+        c.q.v = b; b += n;
+        c.q.w = b; b += n;
+        c.q.u = b; b += n;
+        c.part = b; b += 3 * h->n_tiles;
+        c.sc = b;
+    }
+    {
+        cudaError_t e = cudaMemsetAsync(c.sc, 0, sizeof(double) * SC_WORDS, c.s);
+        if (e == cudaSuccess) e = cudaMemsetAsync(c.counter, 0, sizeof(unsigned int), c.s);
+        if (e != cudaSuccess) {
+            rc = hb_cuda_fail(e, "memset", __FILE__, __LINE__);
+            goto done;
+        }
+    }
+    {
+        FInit f0;
+        f0.q = c.q;
+        KR_TRY(kr_launch(c, f0));
+        // v = x o ((A + eps I) x) ; rk = 1 - v ; rho = rk^T rk
+        KR_TRY(kr_spmv(c, c.q.x, c.q.x, nullptr, nullptr, c.q.v, diag_eps));
+        FResid fr;
+        fr.q = c.q;
+        KR_TRY(kr_launch(c, fr));
+        KR_TRY(kr_read_scalars(c));
+        rho_km1 = c.h_sc[SC_RHO];
+        rout = rold = rho_km1;
+    }
+    while (rout > rt && outer < max_outer) {
+        ++outer;
+        int k = 0;
+        const double innertol = fmax(eta * eta * rout, rt);
+        while (rho_km1 > innertol) {
+            ++k;
+            if (k == 1) {
+                FFirst f;
+                f.q = c.q;
+                KR_TRY(kr_launch(c, f));
+            } else {
+                FDir f;
+                f.q = c.q;
+                f.beta = 0.0;
+                KR_TRY(kr_launch(c, f));
+            }
+            // w = x o ((A + eps I)(x o p)) + v o p
+            KR_TRY(kr_spmv(c, c.q.u, c.q.x, c.q.v, c.q.p, c.q.w, diag_eps));
+            {
+                FDot fd;
+                fd.q = c.q;
+                KR_TRY(kr_launch(c, fd));
+                FYnew fy;
+                fy.q = c.q;
+                fy.alpha = 0.0;
+                KR_TRY(kr_launch(c, fy));
+                FStep fs;
+                fs.q = c.q;
+                fs.delta = delta;
+                fs.Delta = Delta;
+                fs.alpha = 0.0;
+                KR_TRY(kr_launch(c, fs));
+            }
+            KR_TRY(kr_read_scalars(c));
+            if (c.h_sc[SC_MIN] <= delta) {
+                if (delta == 0.0) break;
+                FGamma fg;
+                fg.q = c.q;
+                fg.bound = delta;
+                fg.upper = 0;
+                fg.alpha = 0.0;
+                KR_TRY(kr_launch(c, fg));
+                FBoundStep fb;
+                fb.q = c.q;
+                fb.alpha = fb.gamma = 0.0;
+                KR_TRY(kr_launch(c, fb));
+                break;
+            }
+            if (c.h_sc[SC_MAX] >= Delta) {
+                FGamma fg;
+                fg.q = c.q;
+                fg.bound = Delta;
+                fg.upper = 1;
+                fg.alpha = 0.0;
+                KR_TRY(kr_launch(c, fg));
+                FBoundStep fb;
+                fb.q = c.q;
+                fb.alpha = fb.gamma = 0.0;
+                KR_TRY(kr_launch(c, fb));
+                break;
+            }
+            rho_km1 = c.h_sc[SC_RHO];
+            if (!(rho_km1 == rho_km1)) {
+                breakdown = true;
+                break;
+            }
+        }
+        if (breakdown) break;
+        {
+            FXUpdate fx;
+            fx.q = c.q;
+            KR_TRY(kr_launch(c, fx));
+            KR_TRY(kr_spmv(c, c.q.x, c.q.x, nullptr, nullptr, c.q.v, diag_eps));
+            FResid fr;
+            fr.q = c.q;
+            KR_TRY(kr_launch(c, fr));
+            KR_TRY(kr_read_scalars(c));
+        }
+        rho_km1 = c.h_sc[SC_RHO];
+        rout = c.h_sc[SC_ROUT];
+        mvp += k + 1;
+        if (!(rout == rout) || !(c.h_sc[SC_XMIN] > 0.0)) {
+            breakdown = true;
+            break;
+        }
+        const double rat = rout / rold;
+        rold = rout;
+        const double res_norm = sqrt(rout);
+        const double eta_o = eta;
+        eta = g * rat;
+        if (g * eta_o * eta_o > 0.1) eta = fmax(eta, g * eta_o * eta_o);
+        eta = fmax(fmin(eta, etamax), stop_tol / res_norm);
+    }
+    {
+        cudaError_t e = cudaMemcpyAsync(x_out, c.q.x, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c.s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c.s);
+        if (e != cudaSuccess) rc = hb_cuda_fail(e, "KR result copy", __FILE__, __LINE__);
+    }
+    if (outer_out) *outer_out = outer;
+    if (matvecs_out) *matvecs_out = mvp;
+    if (residual_out) *residual_out = sqrt(rout);
+    if (rc == HB_OK && breakdown) {
+        hb_set_error("Knight-Ruiz breakdown (non-finite residual or non-positive scaling vector)");
+        rc = HB_ERR_KR_BREAKDOWN;
+    }
+done:
+    cudaStreamSynchronize(c.s);
+    cudaFree(c.buf);
+    if (c.h_sc) cudaFreeHost(c.h_sc);
+    return rc;
+}
+
+int hb_kr_rescale(hb_csr* h, double diag_eps, double* x_inout, double* factor_out) {
+    HB_REQUIRE(h != nullptr && x_inout != nullptr, "bad arguments");
+    HB_REQUIRE(h->row0 == 0 && h->n_rows == h->n_cols, "hb_kr_rescale needs the full matrix on one device");
+    int rc = hb_ensure_state(h);
+    if (rc) return rc;
+    rc = hb_use_device(h);
+    if (rc) return rc;
+    const int64_t n = h->n_cols;
+    if (n == 0) return HB_OK;
+    cudaStream_t s = h->stream;
+    double* buf = nullptr;
+    HB_CUDA(cudaMalloc(&buf, sizeof(double) * (size_t)(3 * n + 3 * h->n_tiles + SC_WORDS)));
+    double *d_x = buf, *d_scaled = buf + n, *d_orig = buf + 2 * n, *d_part = buf + 3 * n, *d_sc = d_part + 3 * h->n_tiles;
+    double sc[SC_WORDS];
+    cudaError_t e = cudaMemcpyAsync(d_x, x_inout, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(h->d_counters + 2, 0, sizeof(unsigned int), s);
+    if (e == cudaSuccess) {
+        hb_kr_rescale_rows_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, h->n_rows, d_x,
+                                                                 diag_eps, d_scaled, d_orig);
+        g_hb_launches.fetch_add(1);
+        HbTiles tiles{h->d_tile_row0, h->d_tile_len, h->n_tiles};
+        for (int which = 0; which < 2; ++which) {
+            FSum2 f;
+            f.a = d_scaled;
+            f.b = d_orig;
+            f.which = which;
+            hb_kr_vec_kernel<FSum2><<<h->n_tiles, 256, 0, s>>>(tiles, f, d_part, h->d_counters + 2, d_sc);
+            g_hb_launches.fetch_add(1);
+        }
+        e = cudaMemcpyAsync(sc, d_sc, sizeof(sc), cudaMemcpyDeviceToHost, s);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(buf);
+    if (e != cudaSuccess) return hb_cuda_fail(e, "KR rescale", __FILE__, __LINE__);
+    const double factor = sqrt(sc[SC_A] / sc[SC_B]);
+    for (int64_t i = 0; i < n; ++i) x_inout[i] /= factor;
+    if (factor_out) *factor_out = factor;
+    return HB_OK;
+}
+
+int hb_kr_scaled_upper(hb_csr* h, double diag_eps, const double* x, int64_t* nnz_out, int64_t* indptr, int32_t* indices,
+                       double* data) {
+    HB_REQUIRE(h != nullptr && x != nullptr && nnz_out != nullptr, "bad arguments");
+    HB_REQUIRE(h->row0 == 0 && h->n_rows == h->n_cols, "hb_kr_scaled_upper needs the full matrix on one device");
+    int rc = hb_use_device(h);
+    if (rc) return rc;
+    const int64_t n = h->n_cols;
+    cudaStream_t s = h->stream;
+    int64_t *d_cnt = nullptr, *d_ptr = nullptr;
+    HB_CUDA(cudaMalloc(&d_cnt, sizeof(int64_t) * (size_t)(n + 1)));
+    HB_CUDA(cudaMalloc(&d_ptr, sizeof(int64_t) * (size_t)(n + 1)));
+    if (n > 0) {
+        hb_kr_upper_count_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_indptr, h->d_indices, n, d_cnt);
+        g_hb_launches.fetch_add(1);
+    }
+    hb_kr_scan_kernel<<<1, 1024, 0, s>>>(d_cnt, d_ptr, n);
+    g_hb_launches.fetch_add(1);
+    int64_t total = 0;
+    cudaError_t e = cudaMemcpyAsync(&total, d_ptr + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    *nnz_out = total;
+    if (e == cudaSuccess && indptr != nullptr && indices != nullptr && data != nullptr && n > 0) {
+        double *d_x = nullptr, *d_val = nullptr;
+        int32_t* d_idx = nullptr;
+        e = cudaMalloc(&d_x, sizeof(double) * (size_t)n);
+        if (e == cudaSuccess) e = cudaMalloc(&d_val, sizeof(double) * (size_t)total);
+        if (e == cudaSuccess) e = cudaMalloc(&d_idx, sizeof(int32_t) * (size_t)total);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_x, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) {
+            hb_kr_upper_fill_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, n, d_x, diag_eps,
+                                                                   d_ptr, d_idx, d_val);
+            g_hb_launches.fetch_add(1);
+            e = cudaStreamSynchronize(s);
+        }
+        if (e == cudaSuccess) e = cudaMemcpy(indptr, d_ptr, sizeof(int64_t) * (size_t)(n + 1), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(indices, d_idx, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(data, d_val, sizeof(double) * (size_t)total, cudaMemcpyDeviceToHost);
+        cudaFree(d_x);
+        cudaFree(d_val);
+        cudaFree(d_idx);
+    }
+    cudaFree(d_cnt);
+    cudaFree(d_ptr);
+    if (e != cudaSuccess) return hb_cuda_fail(e, "KR scaled upper", __FILE__, __LINE__);
+    return HB_OK;
+}
+
+}  // extern "C"

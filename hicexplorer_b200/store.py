@@ -1,0 +1,240 @@
+"""Host-side owner of a device-resident CSR block (``hb_csr`` in
+include/hicbalance.h).  Everything numeric happens in libhicbalance.so; this
+class only moves buffers and translates status codes.
+
+The block is what the reference keeps as ``ma.matrix`` (a full symmetric scipy
+CSR, hicCorrectMatrix.py:603-626), living in HBM as int64 ``indptr`` / int32
+``indices`` / fp64 ``data``.
+"""
+import ctypes
+
+import numpy as np
+from scipy import sparse
+
+from . import _lib
+from ._lib import check, lib, ptr
+
+KR_TOL = 1e-6
+KR_DELTA = 0.1
+KR_DELTA_UPPER = 3.0
+KR_DIAG_EPS = 1e-5
+
+
+def canonical_csr(matrix, dtype=np.float64):
+    """float64 CSR with sorted, duplicate-free rows (a copy only when needed)."""
+    m = matrix if sparse.isspmatrix_csr(matrix) else sparse.csr_matrix(matrix)
+    if m.dtype != dtype:
+        m = m.astype(dtype)
+    if not m.has_canonical_format:
+        m = m.copy() if m is matrix else m
+        m.sum_duplicates()
+    return m
+
+
+class DeviceCSR(object):
+    def __init__(self, handle, device):
+        self._h = ctypes.c_void_p(handle) if not isinstance(handle, ctypes.c_void_p) else handle
+        self.device = device
+
+    # ---- construction -------------------------------------------------------
+    @classmethod
+    def from_scipy(cls, matrix, device=0, row_range=None):
+        """Upload ``matrix`` (square, symmetric, canonical CSR).  ``row_range`` =
+        (row0, row1) uploads only that block of rows (sharded runs)."""
+        _lib.require_device()
+        m = canonical_csr(matrix)
+        n = m.shape[0]
+        if m.shape[0] != m.shape[1]:
+            raise ValueError("matrix must be square")
+        row0, row1 = (0, n) if row_range is None else row_range
+        indptr = np.ascontiguousarray(m.indptr[row0:row1 + 1], dtype=np.int64)
+        nnz = int(indptr[-1] - indptr[0])
+        idx_i64 = 1 if m.indices.dtype == np.int64 else 0
+        indices = np.ascontiguousarray(m.indices, dtype=np.int64 if idx_i64 else np.int32)
+        data = np.ascontiguousarray(m.data, dtype=np.float64)
+        h = ctypes.c_void_p()
+        check(lib().hb_csr_create(ctypes.byref(h), row1 - row0, n, row0, nnz, ptr(indptr), ptr(indices), idx_i64,
+                                  ptr(data), device))
+        return cls(h, device)
+
+    @classmethod
+    def wrap_device(cls, n_rows, n_cols, row0, nnz, d_indptr, d_indices, d_data, device=0):
+        """Zero-copy view of arrays already in HBM (raw device pointers, e.g. ``tensor.data_ptr()``)."""
+        _lib.require_device()
+        h = ctypes.c_void_p()
+        check(lib().hb_dev_csr_wrap(ctypes.byref(h), n_rows, n_cols, row0, nnz, d_indptr, d_indices, d_data, device))
+        return cls(h, device)
+
+    @classmethod
+    def synthetic(cls, chrom_bins, seed=0, band=2000, d0=200.0, gamma=1.0, lambda0=40.0, n_trans=8,
+                  low_frac=0.02, empty_frac=0.005, row_range=None, device=0):
+        """Deterministic synthetic Hi-C matrix generated directly in HBM."""
+        _lib.require_device()
+        cb = np.ascontiguousarray(chrom_bins, dtype=np.int64)
+        n = int(cb.sum())
+        row0, row1 = (0, n) if row_range is None else row_range
+        p = _lib.SynthParams(seed=seed, nchrom=len(cb), band=band, n_trans=n_trans, reserved=0, d0=d0, gamma=gamma,
+                             lambda0=lambda0, low_frac=low_frac, empty_frac=empty_frac)
+        h = ctypes.c_void_p()
+        check(lib().hb_synth_create(ctypes.byref(h), ctypes.byref(p), ptr(cb), row0, row1 - row0, device))
+        return cls(h, device)
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            lib().hb_csr_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- introspection ------------------------------------------------------
+    @property
+    def handle(self):
+        return self._h
+
+    def dims(self):
+        a, b, c, d = (ctypes.c_int64() for _ in range(4))
+        check(lib().hb_csr_shape(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(d)))
+        return a.value, b.value, c.value, d.value
+
+    @property
+    def n_rows(self):
+        return self.dims()[0]
+
+    @property
+    def n(self):
+        return self.dims()[1]
+
+    @property
+    def row0(self):
+        return self.dims()[2]
+
+    @property
+    def nnz(self):
+        return self.dims()[3]
+
+    def device_pointers(self):
+        a, b, c = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        check(lib().hb_dev_csr_pointers(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return a.value, b.value, c.value
+
+    def sync(self):
+        check(lib().hb_sync(self._h))
+
+    def download(self, values_only=False):
+        """Host copy of the block as a scipy CSR (rows = block rows, columns = all bins)."""
+        n_rows, n_cols, _row0, nnz = self.dims()
+        data = np.empty(nnz, dtype=np.float64)
+        if values_only:
+            check(lib().hb_csr_download(self._h, None, None, ptr(data)))
+            return data
+        indptr = np.empty(n_rows + 1, dtype=np.int64)
+        indices = np.empty(nnz, dtype=np.int32)
+        check(lib().hb_csr_download(self._h, ptr(indptr), ptr(indices), ptr(data)))
+        return sparse.csr_matrix((data, indices, indptr), shape=(n_rows, n_cols))
+
+    # ---- pre-filter ---------------------------------------------------------
+    def set_segments(self, offsets):
+        off = np.ascontiguousarray(offsets, dtype=np.int64)
+        check(lib().hb_set_segments(self._h, len(off) - 1, ptr(off)))
+        self._segments = len(off) - 1
+
+    def keep_cis(self):
+        check(lib().hb_csr_keep_cis(self._h))
+
+    def scrub(self):
+        """NaN -> 0, Inf -> 0 on the device; returns (#nan, #inf)."""
+        counts = np.zeros(2, dtype=np.int64)
+        check(lib().hb_scrub(self._h, ptr(counts)))
+        return int(counts[0]), int(counts[1])
+
+    def row_stats(self):
+        n_rows = self.n_rows
+        rs = np.empty(n_rows, dtype=np.float64)
+        dg = np.empty(n_rows, dtype=np.float64)
+        check(lib().hb_row_stats(self._h, ptr(rs), ptr(dg)))
+        return rs, dg
+
+    def mad_filter(self, lo, hi, want_z=False):
+        """(mask uint8[n], zscore or None, median[nseg], mad[nseg])."""
+        n = self.n
+        mask = np.zeros(n, dtype=np.uint8)
+        z = np.empty(n, dtype=np.float64) if want_z else None
+        nseg = max(1, self._nseg())
+        med = np.empty(nseg, dtype=np.float64)
+        mad = np.empty(nseg, dtype=np.float64)
+        check(lib().hb_mad_filter(self._h, float(lo), float(hi), ptr(mask), ptr(z), ptr(med), ptr(mad)))
+        return mask, z, med, mad
+
+    _segments = 1
+
+    def _nseg(self):
+        return self._segments
+
+    def compact(self, remove_mask):
+        m = np.ascontiguousarray(remove_mask, dtype=np.uint8)
+        if len(m) != self.n:
+            raise ValueError("mask length must equal the bin count")
+        check(lib().hb_csr_compact(self._h, ptr(m)))
+
+    def diag_zero(self):
+        check(lib().hb_diag_zero(self._h))
+
+    def symmetry_ratio(self):
+        r = ctypes.c_double()
+        check(lib().hb_symmetry(self._h, ctypes.byref(r)))
+        return r.value
+
+    # ---- ICE ------------------------------------------------------------------
+    def ice(self, max_iter=50, tolerance=1e-5):
+        """Returns (bias[n], iterations[nseg], deviation[nseg]).  Raises OverflowIter."""
+        n = self.n
+        nseg = self._nseg()
+        bias = np.empty(n, dtype=np.float64)
+        iters = np.zeros(nseg, dtype=np.int32)
+        dev = np.zeros(nseg, dtype=np.float64)
+        check(lib().hb_ice_run(self._h, int(max_iter), float(tolerance), ptr(bias), ptr(iters), ptr(dev)))
+        return bias, iters, dev
+
+    def ice_scaled_values(self):
+        """A_ij / (b_i b_j) in the store's entry order.  Raises OverflowIter / OverflowFinal."""
+        out = np.empty(self.nnz, dtype=np.float64)
+        mx = ctypes.c_double()
+        check(lib().hb_ice_scaled_values(self._h, ptr(out), ctypes.byref(mx)))
+        return out
+
+    # ---- Knight-Ruiz ------------------------------------------------------------
+    def kr(self, tol=KR_TOL, delta=KR_DELTA, Delta=KR_DELTA_UPPER, diag_eps=KR_DIAG_EPS, max_outer=100000):
+        """Returns (x[n], outer iterations, mat-vecs, residual norm)."""
+        x = np.empty(self.n, dtype=np.float64)
+        outer, mv, res = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_double()
+        check(lib().hb_kr_run(self._h, tol, delta, Delta, diag_eps, int(max_outer), ptr(x), ctypes.byref(outer),
+                              ctypes.byref(mv), ctypes.byref(res)))
+        return x, outer.value, mv.value, res.value
+
+    def kr_rescale(self, x, diag_eps=KR_DIAG_EPS):
+        x = np.ascontiguousarray(x, dtype=np.float64).copy()
+        f = ctypes.c_double()
+        check(lib().hb_kr_rescale(self._h, diag_eps, ptr(x), ctypes.byref(f)))
+        return x, f.value
+
+    def kr_scaled_upper(self, x, diag_eps=KR_DIAG_EPS):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        n = self.n
+        nnz = ctypes.c_int64()
+        check(lib().hb_kr_scaled_upper(self._h, diag_eps, ptr(x), ctypes.byref(nnz), None, None, None))
+        indptr = np.empty(n + 1, dtype=np.int64)
+        indices = np.empty(nnz.value, dtype=np.int32)
+        data = np.empty(nnz.value, dtype=np.float64)
+        check(lib().hb_kr_scaled_upper(self._h, diag_eps, ptr(x), ctypes.byref(nnz), ptr(indptr), ptr(indices),
+                                       ptr(data)))
+        return sparse.csr_matrix((data, indices, indptr), shape=(n, n))

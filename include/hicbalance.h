@@ -1,0 +1,234 @@
+/*
+ * libhicbalance -- B200-native (sm_100a) Hi-C matrix balancing: ICE iterative
+ * correction, Knight-Ruiz balancing and the MAD bin filter on a device-resident
+ * symmetric CSR store.
+ *
+ * This header is the drop-in boundary of the hot path.  The reference
+ * (HiCExplorer 3.7.6) is pure Python and reaches native code for this path in
+ * exactly one place, the pybind11 object `krbalancing.kr_balancing`
+ * (hicexplorer/hicCorrectMatrix.py:17, 718-732, 744-757); its ICE is numpy
+ * (hicexplorer/iterativeCorrection.py:10-86).  Every entry point below cites
+ * the reference interface it replaces.  INTEGRATION.md shows the ctypes stubs
+ * a maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - plain C ABI: pointers + sizes, no C++/torch types.
+ *   - HOST API  (hb_*):      array arguments are caller-owned host buffers; the
+ *     call is synchronous (returns after the device work finished), like the
+ *     reference's single-threaded functions.
+ *   - DEVICE API (hb_dev_*): array arguments are device pointers owned by the
+ *     caller (e.g. torch tensors); work is enqueued on `stream` (a cudaStream_t
+ *     passed as void*, NULL = the handle's own stream) and is asynchronous.
+ *     This is what the multi-GPU driver and the HBM-resident benchmark use.
+ *   - a handle owns one CUDA stream and is not thread-safe.
+ *   - every function returns an hb_status; hb_last_error() gives the message of
+ *     the last failure on the calling thread.
+ *   - matrix layout in HBM: indptr int64[n_rows+1] (block-local offsets),
+ *     indices int32[nnz] (GLOBAL column ids, ascending inside a row),
+ *     data fp64[nnz]; FULL symmetric storage (both triangles), which is what
+ *     the reference holds in memory.
+ */
+#ifndef HICBALANCE_H
+#define HICBALANCE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define HB_API __attribute__((visibility("default")))
+#else
+#define HB_API
+#endif
+
+typedef enum hb_status {
+    HB_OK = 0,
+    /* iterativeCorrection.py:35-36  -> ValueError("Please provide symmetric matrix!") */
+    HB_ERR_NOT_SYMMETRIC = 1,
+    /* iterativeCorrection.py:58-62  -> log.error + exit(1): a scaled value exceeded 1e100 */
+    HB_ERR_OVERFLOW_ITER = 2,
+    /* iterativeCorrection.py:80-84  -> log.error + exit(1): a final value exceeded 1e10 */
+    HB_ERR_OVERFLOW_FINAL = 3,
+    /* krbalancing asserts (rho > 0, finite, min(x) > 0) */
+    HB_ERR_KR_BREAKDOWN = 4,
+    HB_ERR_INVALID_ARG = 5,
+    HB_ERR_NO_DEVICE = 6,
+    HB_ERR_CUDA = 100
+} hb_status;
+
+typedef struct hb_csr hb_csr; /* opaque: device CSR block + work vectors + stream */
+
+/* ---- library ------------------------------------------------------------ */
+HB_API int hb_abi_version(void);
+HB_API const char* hb_last_error(void);
+/* number of visible CUDA devices (0 if none / driver missing); never fails */
+HB_API int hb_device_count(void);
+/* pinned host memory for callers that want full-rate H2D/D2H */
+HB_API int hb_pinned_alloc(void** out, uint64_t bytes);
+HB_API int hb_pinned_free(void* p);
+/* number of kernel launches issued by this library in this process (bench.py: gpu_launches) */
+HB_API uint64_t hb_launch_count(void);
+
+/* ---- device CSR store ------------------------------------------------------
+ * Replaces: the scipy CSR the reference keeps in `ma.matrix`
+ * (hicCorrectMatrix.py:603-626) and krbalancing's constructor copy of
+ * (indptr, indices, data) (hicCorrectMatrix.py:744-747).
+ *
+ * hb_csr_create: copy a host CSR block to `device`.  The block holds rows
+ * [row0, row0 + n_rows) of an n_cols x n_cols symmetric matrix (single GPU:
+ * row0 = 0, n_rows = n_cols).  indptr may start at any offset; it is rebased.
+ * indices_i64 != 0 means `indices` points at int64 (krbalancing's ctor
+ * signature) instead of int32. */
+HB_API int hb_csr_create(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t row0, int64_t nnz,
+                  const int64_t* indptr, const void* indices, int indices_i64, const double* data,
+                  int device);
+/* wrap device arrays already in HBM (not copied, not owned). indptr must be block-local (indptr[0]==0). */
+HB_API int hb_dev_csr_wrap(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t row0, int64_t nnz,
+                    const int64_t* d_indptr, const int32_t* d_indices, const double* d_data, int device);
+HB_API int hb_csr_destroy(hb_csr* h);
+HB_API int hb_csr_shape(const hb_csr* h, int64_t* n_rows, int64_t* n_cols, int64_t* row0, int64_t* nnz);
+/* copy the (possibly compacted) block back to host buffers sized from hb_csr_shape; any pointer may be NULL */
+HB_API int hb_csr_download(hb_csr* h, int64_t* indptr, int32_t* indices, double* data);
+/* device pointers of the store (for zero-copy torch views) */
+HB_API int hb_dev_csr_pointers(hb_csr* h, const int64_t** d_indptr, const int32_t** d_indices, const double** d_data);
+HB_API int hb_sync(hb_csr* h);
+
+/* Independent diagonal blocks (`--perchr`, hicCorrectMatrix.py:703-734).
+ * seg_offsets[nseg+1] are ascending GLOBAL row offsets with seg_offsets[0]=0 and
+ * seg_offsets[nseg]=n_cols.  Every later ICE / KR / filter call treats each
+ * segment as its own matrix (own mean, own convergence, own medians).
+ * Entries whose row and column lie in different segments must be removed first
+ * with hb_csr_keep_cis (the reference drops them: hicCorrectMatrix.py:702,711). */
+HB_API int hb_set_segments(hb_csr* h, int nseg, const int64_t* seg_offsets);
+HB_API int hb_csr_keep_cis(hb_csr* h);
+
+/* Sharded runs (one process per GPU, nnz-balanced row blocks).  The path has exactly
+ * one exchange step per SpMV: every rank writes the rows it owns into a zeroed fp64 vector and the
+ * vectors are summed across ranks (x + 0 is exact, so the result is bit-identical to a gather).
+ * The library calls `fn` for it: fn must sum-allreduce d_buf[0..count) over the ranks, ordered after
+ * the work already enqueued on `stream` and complete (stream-ordered) when it returns.  The Python
+ * host passes a torch.distributed (NCCL) all_reduce here.  With comm set, hb_ice_run / hb_kr_run
+ * accept a row block instead of the full matrix; the O(n) vector work runs replicated on every rank. */
+typedef int (*hb_allreduce_fn)(void* ctx, void* d_buf, int64_t count, void* stream);
+HB_API int hb_set_comm(hb_csr* h, int rank, int world, hb_allreduce_fn fn, void* ctx);
+
+/* ---- pre-filter (device) ---------------------------------------------------
+ * hb_scrub: NaN -> 0 and +-Inf -> 0 in the stored values
+ *   (utilities.py:111-128 via hicCorrectMatrix.py:624-625; iterativeCorrection.py:28-30).
+ *   counts[0] = #NaN, counts[1] = #Inf replaced.
+ * hb_row_stats: row_sum[i] (diagonal included, hicCorrectMatrix.py:613) and
+ *   diag[i] (hicCorrectMatrix.py:568,588) for the block's rows; either may be NULL.
+ * hb_mad_filter: modified z-score of points = row_sum - diag and the outlier
+ *   mask (class MAD, hicCorrectMatrix.py:349-391; filter_by_zscore :548-592;
+ *   per segment when segments are set).  Requires a full (unsharded) block.
+ *   mask_out[i] = 1 if z < lo or z > hi; zscore_out optional (NULL).
+ * hb_csr_compact: delete the rows AND columns with remove_mask[i] != 0 and
+ *   renumber (hicmatrix maskBins as used at hicCorrectMatrix.py:616, 672).
+ *   Segment offsets are renumbered with it. Requires a full block.
+ * hb_diag_zero: --skipDiagonal (hicCorrectMatrix.py:648-649).
+ * hb_symmetry: the reference's criterion (iterativeCorrection.py:35):
+ *   ratio = mean|M - M^T| / |mean M|; the caller raises when ratio > 1e-10. */
+HB_API int hb_scrub(hb_csr* h, int64_t counts[2]);
+HB_API int hb_row_stats(hb_csr* h, double* row_sum, double* diag);
+HB_API int hb_mad_filter(hb_csr* h, double lo, double hi, uint8_t* mask_out, double* zscore_out,
+                  double* median_out /*nseg*/, double* mad_out /*nseg*/);
+HB_API int hb_csr_compact(hb_csr* h, const uint8_t* remove_mask);
+HB_API int hb_diag_zero(hb_csr* h);
+HB_API int hb_symmetry(hb_csr* h, double* ratio_out);
+
+/* ---- ICE -------------------------------------------------------------------
+ * Replaces iterativeCorrection(matrix, v, M, tolerance, verbose)
+ * (hicexplorer/iterativeCorrection.py:10-86).
+ *
+ * hb_ice_run: iterate until max|s-1| < tol (strict, tested after the rescale of
+ *   that iteration) or max_iter passes.  bias_out[n_cols] is the divisive bias,
+ *   already normalised to mean 1 over its non-zero entries (lines 77-78).
+ *   iters_out[nseg]: loop bodies executed per segment (the reference LOGS this
+ *   value + 1).  dev_out[nseg]: last deviation.  Returns HB_ERR_OVERFLOW_ITER
+ *   when a rescaled value exceeded 1e100 (line 58).
+ * hb_ice_scaled_values: data_out[nnz] = A_ij / (b_i b_j) in the store's entry
+ *   order (lines 56-57, 79); returns HB_ERR_OVERFLOW_ITER / _FINAL per lines
+ *   58 / 80 for the final matrix.  max_out optional.
+ * hb_ice_run needs the full matrix on one device unless hb_set_comm was called. */
+HB_API int hb_ice_run(hb_csr* h, int max_iter, double tol, double* bias_out, int32_t* iters_out,
+               double* dev_out);
+HB_API int hb_ice_scaled_values(hb_csr* h, double* data_out, double* max_out);
+
+/* Step-level device API (all vectors are device fp64[n_cols], replicated per rank).
+ *   hb_dev_ice_begin : bias = 1, r = 1, clear convergence state.
+ *   hb_dev_ice_spmv  : exch[row0+i] = r_i * sum_j A_ij r_j for the block's rows and
+ *                      exch[n_cols + rank] = max_ij A_ij r_i r_j over the block; every other
+ *                      element of exch[0 .. n_cols+world) is zeroed first, so that ONE
+ *                      sum-allreduce of exch over the ranks assembles the marginals.
+ *   hb_dev_ice_update: from the assembled exch: per segment mean over non-zero
+ *                      marginals, bias *= s, deviation, r /= s, convergence + overflow flags.
+ *                      Identical on every rank (deterministic fixed-tile reductions).
+ *   hb_dev_ice_status: async copy of {all_done, overflow, iteration} to a pinned int32[4].
+ *   hb_dev_ice_finish: bias normalisation (lines 77-78); r is rescaled so that
+ *                      A_ij r_i r_j is the final corrected value.
+ *   hb_dev_ice_emit  : d_out[k] = A_k r_i r_j for the block (+ max into d_max[0], may be NULL). */
+HB_API int hb_dev_ice_begin(hb_csr* h, void* stream);
+HB_API int hb_dev_ice_spmv(hb_csr* h, double* d_exch, int rank, int world, void* stream);
+HB_API int hb_dev_ice_update(hb_csr* h, const double* d_exch, int world, double tol, void* stream);
+HB_API int hb_dev_ice_status(hb_csr* h, int32_t* pinned_status4, void* stream);
+HB_API int hb_dev_ice_finish(hb_csr* h, void* stream);
+HB_API int hb_dev_ice_emit(hb_csr* h, double* d_out, double* d_max, void* stream);
+/* device pointers of the replicated state: bias[n_cols], r[n_cols] (1/bias, 0 for dead bins) */
+HB_API int hb_dev_ice_vectors(hb_csr* h, double** d_bias, double** d_r);
+/* host copy of per-segment results after the loop (sync) */
+HB_API int hb_ice_results(hb_csr* h, double* bias_out, int32_t* iters_out, double* dev_out);
+
+/* ---- Knight-Ruiz -------------------------------------------------------------
+ * Replaces the krbalancing object (call sites hicCorrectMatrix.py:718-732, 744-757):
+ *   kr_balancing(rows, cols, nnz, indptr, indices, data)  -> hb_csr_create(..., indices_i64=1)
+ *   .computeKR()                                           -> hb_kr_run
+ *   .get_normalisation_vector(rescale)                     -> x_out of hb_kr_run (+ hb_kr_rescale)
+ *   .get_normalised_matrix(rescale)                        -> hb_kr_scaled_upper
+ * The algorithm is Knight & Ruiz's `bnewt` on A + diag_eps*I with krbalancing's
+ * constants (tol 1e-6, delta 0.1, Delta 3, g 0.9, etamax 0.1, diag_eps 1e-5).
+ * x_out[n_cols]; outer_out / matvecs_out / residual_out optional. */
+HB_API int hb_kr_run(hb_csr* h, double tol, double delta, double Delta, double diag_eps, int max_outer,
+              double* x_out, int32_t* outer_out, int32_t* matvecs_out, double* residual_out);
+/* factor = sqrt(sum_ij (A+eps I)_ij x_i x_j / sum_ij (A+eps I)_ij); x_inout /= factor (krbalancing rescale_norm_vector) */
+HB_API int hb_kr_rescale(hb_csr* h, double diag_eps, double* x_inout, double* factor_out);
+/* upper triangle (diagonal always present) of (A + eps I) o (x x^T):
+ * call with all outputs NULL to get nnz_out, then with buffers indptr[n+1], indices[nnz], data[nnz]. */
+HB_API int hb_kr_scaled_upper(hb_csr* h, double diag_eps, const double* x, int64_t* nnz_out, int64_t* indptr,
+                       int32_t* indices, double* data);
+
+/* step-level device API for the sharded KR loop: d_out[row0+i] = a_i * (sum_j A_ij u_j + eps*u_i) + b_i*c_i
+ * for the block's rows (a, b, c optional device vectors indexed by GLOBAL row; NULL a -> 1, NULL b or c -> 0);
+ * elements of d_out outside the block are zeroed when zero_rest != 0 (sum-allreduce assembly). */
+HB_API int hb_dev_spmv(hb_csr* h, const double* d_u, double eps, const double* d_a, const double* d_b,
+                const double* d_c, double* d_out, int zero_rest, void* stream);
+
+/* ---- synthetic Hi-C matrices (benchmark inputs) --------------------
+ * Deterministic symmetric matrix generated directly in HBM, block by block:
+ * chromosome layout chrom_bins[nchrom]; cis entry (i,j) in the same chromosome with |i-j| <= band
+ * exists iff hash(seed,min,max) < min(1, (d0/(|i-j|+1))^gamma); n_trans far entries per row at
+ * j = (c_k - i) mod n; integer counts with planted per-bin biases, `low_frac` low-coverage
+ * bins and `empty_frac` empty bins.  The same generator in numpy (tests/synth_ref.py) reproduces
+ * it on the CPU for cross-checks.  Rows [row0, row0+n_rows). */
+typedef struct hb_synth_params {
+    uint64_t seed;
+    int32_t nchrom;
+    int32_t band;
+    int32_t n_trans;
+    int32_t reserved;
+    double d0;
+    double gamma;
+    double lambda0;
+    double low_frac;
+    double empty_frac;
+} hb_synth_params;
+HB_API int hb_synth_create(hb_csr** out, const hb_synth_params* p, const int64_t* chrom_bins, int64_t row0,
+                    int64_t n_rows, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HICBALANCE_H */

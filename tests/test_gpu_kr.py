@@ -1,0 +1,71 @@
+"""GPU parity tests for Knight-Ruiz: CUDA path vs the restated CPU oracle and the reference's golden KR file.
+Tolerance: x 1e-9 relative, matrix 1e-8 relative (north star); the reference's own test pins 5 decimals."""
+import numpy as np
+import pytest
+from scipy import sparse
+
+from oracle import kr_oracle
+from tests.helpers import csr_from_npz, full_from_pixels, random_hic
+
+pytestmark = pytest.mark.gpu
+
+
+def test_kr_small_matrix_matches_oracle_and_reference_golden(small_ice, small_kr):
+    from hicexplorer_b200.pipeline import kr_pipeline
+    full = csr_from_npz(small_ice, "in")
+    ref = kr_oracle.kr_pipeline(full, rescale=True)
+    got = kr_pipeline(full, rescale=True)
+    assert got["outer"] == ref["outer"] and got["matvecs"] == ref["matvecs"]
+    np.testing.assert_allclose(got["x"], ref["x_out"], rtol=1e-9)
+    up = got["upper"]
+    assert np.array_equal(up.indptr, small_kr["golden_indptr"]) and np.array_equal(up.indices, small_kr["golden_indices"])
+    np.testing.assert_allclose(up.data, ref["upper"].data, rtol=1e-8)
+    np.testing.assert_array_almost_equal(up.data, small_kr["golden_data"], decimal=5)   # the reference's own pin
+
+
+def test_kr_object_protocol_matches_reference_call_sites(kr_partial):
+    from hicexplorer_b200.krbalancing import kr_balancing
+    m = full_from_pixels(kr_partial)
+    ref = kr_oracle.kr_pipeline(m, rescale=True)
+    kr = kr_balancing(m.shape[0], m.shape[1], m.count_nonzero(), m.indptr.astype(np.int64, copy=False),
+                      m.indices.astype(np.int64, copy=False), m.data.astype(np.float64, copy=False))
+    kr.computeKR()
+    cf = kr.get_normalisation_vector(True).todense()        # hicCorrectMatrix.py:754
+    assert cf.shape == (m.shape[0], 1)
+    np.testing.assert_allclose(np.asarray(cf).ravel(), ref["x_out"], rtol=1e-9)
+    again = np.asarray(kr.get_normalisation_vector(False).todense()).ravel()     # stays rescaled (:727-732)
+    np.testing.assert_array_equal(again, np.asarray(cf).ravel())
+    nm = kr.get_normalised_matrix(True)
+    assert sparse.tril(nm, -1).nnz == 0
+    np.testing.assert_allclose(sparse.csr_matrix(nm).data, ref["upper"].data, rtol=1e-8)
+    lil = sparse.lil_matrix(m.shape)
+    lil[0:m.shape[0], 0:m.shape[0]] = nm                     # assignable like at :728
+    ratio = kr_partial["weight"] / np.asarray(cf).ravel()
+    assert np.ptp(ratio) < 1e-9 and abs(ratio.mean() - 1) < 5e-6
+    assert kr.outer_iterations == ref["outer"] == 15 and kr.matvecs == ref["matvecs"] == 35
+
+
+@pytest.mark.parametrize("seed,n,density,empty", [(0, 300, 0.2, 0.0), (1, 2000, 0.02, 0.03), (2, 50, 0.6, 0.0)])
+def test_kr_random_matrices(seed, n, density, empty):
+    from hicexplorer_b200.pipeline import kr_pipeline
+    m = random_hic(n, density, seed, empty_frac=empty)
+    ref = kr_oracle.kr_pipeline(m, rescale=True)
+    got = kr_pipeline(m, rescale=True)
+    assert abs(got["outer"] - ref["outer"]) <= 1
+    np.testing.assert_allclose(got["x"], ref["x_out"], rtol=1e-7 if got["outer"] != ref["outer"] else 1e-9)
+    a = ref["A"]
+    x_un = got["x"] * got["factor"]
+    np.testing.assert_allclose(x_un * (a @ x_un), 1.0, atol=5e-6)     # balanced: unit row sums
+
+
+def test_kr_gm12878_genome_wide(gm12878):
+    from hicexplorer_b200.pipeline import kr_pipeline
+    m = full_from_pixels(gm12878)
+    ref = kr_oracle.kr_pipeline(m, rescale=True)
+    got = kr_pipeline(m, rescale=True)
+    assert got["outer"] == ref["outer"] and got["matvecs"] == ref["matvecs"]
+    np.testing.assert_allclose(got["x"], ref["x_out"], rtol=1e-9)
+    np.testing.assert_allclose(got["upper"].data, ref["upper"].data, rtol=1e-8)
+    # the reference's own test for this file: 3e9 < sum // 2 < 3688003604 (test_hicCorrectMatrix.py:72-91)
+    full = got["upper"] + sparse.triu(got["upper"], 1).T
+    assert 3e9 < full.sum() // 2 < 3688003604
