@@ -1,0 +1,492 @@
+#!/usr/bin/env python
+"""Benchmark of the matrix-correction hot path (BASELINE.json metric: ICE/KR nnz/s and iters/s vs the HBM
+roofline at 1/2/4/8 B200; time-to-converge).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ice10k|kr25k|...] [--impl reference]
+
+Headline workload (all N): BASELINE.json configs[2] -- ICE on a synthetic genome-wide 10 kb human matrix
+(hg38 layout, ~309 k bins, ~1.5e9 stored entries), row-sharded in nnz-balanced blocks over the N ranks
+(strong scaling: the matrix is fixed).  A "step" is one ICE iteration over the whole matrix: one fused
+SpMV pass over the CSR (12 B per stored entry) + the O(n) update (+ one sum-allreduce of n doubles when
+N > 1).  `value` = stored entries processed per second with the CSR resident in HBM; `e2e` = the same
+through the host-buffer C-ABI (hb_csr_create from pinned host memory -> hb_ice_run(K) -> bias back),
+copies inside the timed region.  configs[1] (KR, 25 kb, ~3e8 entries) is measured too at N = 1 and reported
+under "kr".  `--impl reference` times the reference's CPU algorithm (numpy port in oracle/, single thread
+like the reference) on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HG38 = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636, 138394717,
+        133797422, 135086622, 133275309, 114364328, 107043718, 101991189, 90338345, 83257441, 80373285,
+        58617616, 64444167, 46709983, 50818468, 156040895, 57227415]
+
+WORKLOADS = {
+    # name: (method, resolution bp, target stored entries, band in bins)
+    "ice10k": ("ICE", 10000, 1.5e9, 16000),
+    "kr25k": ("KR", 25000, 3.0e8, 8000),
+    "ice25k": ("ICE", 25000, 3.0e8, 8000),
+    "ice100k": ("ICE", 100000, 4.0e7, 2000),   # small case for quick checks
+}
+
+
+def chrom_bins(res):
+    return [-(-length // res) for length in HG38]
+
+
+def expected_nnz(bins, band, d0):
+    tot = 0.0
+    for L in bins:
+        dmax = min(band, L - 1)
+        d = np.arange(1, dmax + 1, dtype=np.float64)
+        p = np.minimum(1.0, d0 / (d + 1.0))
+        tot += L + 2.0 * np.sum(p * (L - d))
+    return tot
+
+
+def solve_d0(bins, band, target):
+    lo, hi = 1.0, float(band)
+    for _ in range(60):
+        mid = 0.5 * (lo + hi)
+        if expected_nnz(bins, band, mid) < target:
+            lo = mid
+        else:
+            hi = mid
+    return round(0.5 * (lo + hi), 3)
+
+
+def synth_kwargs(workload, clean=True):
+    method, res, target, band = WORKLOADS[workload]
+    bins = chrom_bins(res)
+    d0 = solve_d0(bins, band, target)
+    kw = dict(seed=0, band=band, d0=d0, gamma=1.0, lambda0=40.0, n_trans=16,
+              low_frac=0.0 if clean else 0.02, empty_frac=0.0 if clean else 0.005)
+    return method, bins, kw
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md) through NVML
+    (the same counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints), every 10 ms."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, device):
+        self.samples = []
+        self.mark = 0
+        self.stop_flag = False
+        self.handle = None
+        self.nvml = None
+        self.thread = None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            try:
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(device).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(device)
+            self.nvml = pynvml
+        except Exception as exc:
+            self.error = repr(exc)
+
+    def start(self):
+        if self.nvml is None:
+            return
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                pw = nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                self.samples.append((sm, rs, pw))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def begin_region(self):
+        self.mark = len(self.samples)
+
+    def stop(self):
+        if self.nvml is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "error", "")]}
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        region = self.samples[self.mark:] or self.samples[-1:]
+        try:
+            mx = self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM)
+        except Exception:
+            mx = None
+        bits = 0
+        for _sm, rs, _pw in region:
+            bits |= int(rs)
+        reasons = sorted(name for bit, name in self.REASONS.items() if bits & bit)
+        return {"sm_mhz": float(np.median([r[0] for r in region])) if region else None, "sm_max_mhz": mx,
+                "power_w_max": max([r[2] for r in region]) if region else None, "samples": len(region),
+                "reasons": reasons}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_ice_baseline(workload, seconds_budget=25.0, use_gpu_generator=False):
+    """The reference's ICE loop (numpy port, oracle/ice_oracle.py == iterativeCorrection.py:40-74) on a bounded
+    sample: the same generator and parameters restricted to chromosome 1."""
+    from oracle import ice_oracle
+    method, bins, kw = synth_kwargs(workload, clean=True)
+    sample_bins = [bins[0]]
+    t0 = time.time()
+    if use_gpu_generator:
+        from hicexplorer_b200.store import DeviceCSR
+        with DeviceCSR.synthetic(sample_bins, **kw) as dev:
+            m = dev.download()
+    else:
+        from oracle import hic_cpu
+        m = hic_cpu.synth_matrix(sample_bins, **kw)
+    gen_s = time.time() - t0
+    nnz = m.nnz
+    t0 = time.time()
+    ice_oracle.ice(m.copy(), max_iter=1, tolerance=0.0)
+    t1 = time.time() - t0
+    k = int(max(2, min(20, (seconds_budget - t1) / max(t1 * 0.6, 1e-3))))
+    t0 = time.time()
+    ice_oracle.ice(m.copy(), max_iter=1 + k, tolerance=0.0)
+    t2 = time.time() - t0
+    per_iter = max((t2 - t1) / k, 1e-9)
+    return {"value": nnz / per_iter, "unit": "nnz/s", "cores": 1, "kind": "port",
+            "iters_per_s": 1.0 / per_iter, "host_cores_available": os.cpu_count(),
+            "sample": "chromosome 1 of the same synthetic layout (%d bins, %d stored entries, same band/d0); "
+                      "%d loop iterations of the reference's numpy ICE (oracle/ice_oracle.py), setup excluded; "
+                      "generated in %.1f s" % (m.shape[0], nnz, k, gen_s)}, m
+
+
+def cpu_kr_baseline(workload="kr25k", seconds_budget=20.0):
+    """Restated KR (oracle/kr_oracle.py, scipy CSR mat-vec, single thread; krbalancing is not installed)."""
+    from oracle import hic_cpu
+    method, bins, kw = synth_kwargs(workload, clean=True)
+    m = hic_cpu.synth_matrix([bins[0]], **kw)
+    x = np.ones(m.shape[0])
+    t0 = time.time()
+    reps = 0
+    while time.time() - t0 < min(seconds_budget, 8.0):
+        _ = x * (m @ x)
+        reps += 1
+    per = (time.time() - t0) / reps
+    return {"value": m.nnz / per, "unit": "nnz/s", "cores": 1, "kind": "port", "matvecs_per_s": 1.0 / per,
+            "sample": "chromosome 1 of the 25 kb layout (%d bins, %d entries): %d scipy CSR mat-vecs x o (A x), "
+                      "the operation inside the restated bnewt loop" % (m.shape[0], m.nnz, reps)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base, _ = cpu_ice_baseline(args.workload, seconds_budget=30.0, use_gpu_generator=False)
+    method, bins, kw = synth_kwargs(args.workload)
+    line = {"impl": "reference", "metric": "ICE stored entries processed per second (nnz x iterations / s)",
+            "value": base["value"], "unit": "nnz/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": None, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": workload_name(args.workload, bins, kw)},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_name(workload, bins, kw):
+    method, res, target, band = WORKLOADS[workload]
+    return ("%s synthetic genome-wide %d kb human (hg38 layout, %d bins, target %.2g stored entries, band %d, "
+            "d0 %.3f, seed 0), full symmetric CSR int64/int32/fp64" % (method, res // 1000, sum(bins), target, band,
+                                                                       kw["d0"]))
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="ice10k", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-kr", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from hicexplorer_b200 import _lib
+    from hicexplorer_b200.dist import attach_comm, nnz_balanced_partition
+    from hicexplorer_b200.store import DeviceCSR
+    L = _lib.lib()
+    check = _lib.check
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    _lib.require_device()
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # a real (non-default) stream: the C-ABI treats a NULL stream as "the handle's own stream"
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    sptr = ctypes.c_void_p(stream.cuda_stream)
+    assert stream.cuda_stream != 0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    method, bins, kw = synth_kwargs(args.workload, clean=True)
+    n = int(sum(bins))
+
+    # ---- generate this rank's nnz-balanced row block directly in HBM ---------------------------------
+    t_gen = time.time()
+    if world == 1:
+        dev = DeviceCSR.synthetic(bins, device=local, **kw)
+        bounds = np.array([0, n])
+    else:
+        eq = np.linspace(0, n, world + 1).astype(np.int64)
+        with DeviceCSR.synthetic(bins, row_range=(int(eq[rank]), int(eq[rank + 1])), device=local, **kw) as tmp:
+            ip = np.empty(tmp.n_rows + 1, dtype=np.int64)
+            check(L.hb_csr_download(tmp.handle, _lib.ptr(ip), None, None))
+        counts = torch.zeros(n, dtype=torch.int64, device="cuda")
+        counts[int(eq[rank]):int(eq[rank + 1])] = torch.from_numpy(np.diff(ip)).cuda()
+        dist.all_reduce(counts)
+        indptr_all = np.concatenate([[0], np.cumsum(counts.cpu().numpy())])
+        bounds = nnz_balanced_partition(indptr_all, world)
+        dev = DeviceCSR.synthetic(bins, row_range=(int(bounds[rank]), int(bounds[rank + 1])), device=local, **kw)
+    keep = attach_comm(dev, rank, world) if world > 1 else None
+    n_rows, n_cols, row0, nnz_local = dev.dims()
+    nnz_t = torch.tensor([float(nnz_local)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(nnz_t)
+    nnz_total = int(nnz_t.item())
+    torch.cuda.synchronize()
+    t_gen = time.time() - t_gen
+    h = dev.handle
+
+    exch = torch.zeros(n + 64, dtype=torch.float64, device="cuda")
+    eptr = ctypes.c_void_p(exch.data_ptr())
+
+    def ice_step(timed_events=None):
+        if timed_events is not None:
+            timed_events[0].record(stream)
+        check(L.hb_dev_ice_spmv(h, eptr, rank, world, sptr))
+        if timed_events is not None:
+            timed_events[1].record(stream)
+        if world > 1:
+            dist.all_reduce(exch[:n + world])
+        check(L.hb_dev_ice_update(h, eptr, world, 0.0, sptr))
+
+    # ---- device-resident timing -------------------------------------------------------------------------
+    check(L.hb_dev_ice_begin(h, sptr))
+    for _ in range(args.warmup):
+        ice_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for _ in range(max(args.warmup, 20)):     # let the sampler thread spin up under load (all ranks)
+        ice_step()
+    pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = L.hb_launch_count()
+    barrier()
+    sampler.begin_region()
+    ev0.record(stream)
+    for k in range(args.steps):
+        ice_step(pairs[k])
+    ev1.record(stream)
+    barrier()
+    launches = L.hb_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    spmv_ms = max_over_ranks(float(np.mean([a.elapsed_time(b) for a, b in pairs])))
+    ms_step = ms_total / args.steps
+    value = nnz_total * args.steps / (ms_total * 1e-3)
+
+    # ---- time to converge (tol 1e-5, the reference default), device resident ------------------------------
+    barrier()
+    check(L.hb_dev_ice_begin(h, sptr))
+    status = torch.zeros(4, dtype=torch.int32, pin_memory=True)
+    t0 = time.time()
+    conv_iters = 0
+    for k in range(1, 501):
+        check(L.hb_dev_ice_spmv(h, eptr, rank, world, sptr))
+        if world > 1:
+            dist.all_reduce(exch[:n + world])
+        check(L.hb_dev_ice_update(h, eptr, world, 1e-5, sptr))
+        if k % 4 == 0:
+            check(L.hb_dev_ice_status(h, ctypes.c_void_p(status.data_ptr()), sptr))
+            stream.synchronize()
+            if int(status[0]):
+                break
+    check(L.hb_dev_ice_status(h, ctypes.c_void_p(status.data_ptr()), sptr))
+    stream.synchronize()
+    conv_iters = int(status[2])
+    converge_ms = max_over_ranks((time.time() - t0) * 1e3)
+    converged = bool(int(status[0])) and not bool(int(status[1]))
+    check(L.hb_dev_ice_finish(h, sptr))
+    stream.synchronize()
+    # size-independent property at full size: the balanced matrix has unit row sums (mean-normalised)
+    dptr = ctypes.c_void_p()
+    rptr = ctypes.c_void_p()
+    check(L.hb_dev_ice_vectors(h, ctypes.byref(dptr), ctypes.byref(rptr)))
+
+    # ---- end to end through the host-buffer C-ABI ------------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        try:
+            ip_h = torch.empty(n_rows + 1, dtype=torch.int64, pin_memory=True)
+            ix_h = torch.empty(max(nnz_local, 1), dtype=torch.int32, pin_memory=True)
+            da_h = torch.empty(max(nnz_local, 1), dtype=torch.float64, pin_memory=True)
+            check(L.hb_csr_download(h, ctypes.c_void_p(ip_h.data_ptr()), ctypes.c_void_p(ix_h.data_ptr()),
+                                    ctypes.c_void_p(da_h.data_ptr())))
+            bias_h = torch.empty(n, dtype=torch.float64, pin_memory=True)
+            iters_h = np.zeros(1, dtype=np.int32)
+            devv = np.zeros(1, dtype=np.float64)
+            dev.close()
+            dev = None
+            barrier()
+            t0 = time.time()
+            h2 = ctypes.c_void_p()
+            check(L.hb_csr_create(ctypes.byref(h2), n_rows, n_cols, row0, nnz_local, ctypes.c_void_p(ip_h.data_ptr()),
+                                  ctypes.c_void_p(ix_h.data_ptr()), 0, ctypes.c_void_p(da_h.data_ptr()), local))
+            dev2 = DeviceCSR(h2, local)
+            keep2 = attach_comm(dev2, rank, world) if world > 1 else None
+            check(L.hb_ice_run(h2, args.steps, 0.0, ctypes.c_void_p(bias_h.data_ptr()), _lib.ptr(iters_h),
+                               _lib.ptr(devv)))
+            barrier()
+            e2e_s = max_over_ranks(time.time() - t0)
+            dev2.close()
+            del keep2
+            e2e = {"value": nnz_total * args.steps / e2e_s, "unit": "nnz/s",
+                   "h2d_bytes_per_step": (12.0 * nnz_total + 8.0 * (n + world)) / args.steps,
+                   "d2h_bytes_per_step": 8.0 * n * world / args.steps, "seconds": e2e_s, "iterations": int(iters_h[0]),
+                   "what": "hb_csr_create (pinned host CSR -> HBM) + hb_ice_run(max_iter=steps, tol=0) + bias to host; "
+                           "one call = `steps` iterations, so the one-off copy is amortised over them"}
+        except Exception as exc:  # keep the device-resident numbers if the host leg cannot run (e.g. host RAM)
+            e2e = {"value": None, "unit": "nnz/s", "error": repr(exc)}
+    if dev is not None:
+        dev.close()
+
+    # ---- KR (configs[1]) at N = 1 ------------------------------------------------------------------------------
+    kr = None
+    if world == 1 and not args.no_kr:
+        kr = bench_kr(torch, L, check, _lib, DeviceCSR, local, stream, sptr)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = measured_peak()
+    bytes_spmv = 12.0 * nnz_total + 24.0 * n
+    achieved = bytes_spmv / world / (spmv_ms * 1e-3) / 1e9   # per GPU: each rank streams its own share
+    line = {
+        "metric": "ICE stored entries processed per second (nnz x iterations / s)",
+        "value": value, "unit": "nnz/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "iters_per_s": 1e3 / ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload, bins, kw), "bins": n, "nnz": nnz_total,
+                   "parallelism": "%d nnz-balanced row block(s), 1 sum-allreduce of n fp64 per iteration" % world,
+                   "l2": "inputs larger than L2 (%.1f GB of CSR per GPU vs 126 MB)" % (12e-9 * nnz_total / world),
+                   "generated_in_s": round(t_gen, 2)},
+        "time_to_converge": {"ms": converge_ms, "iterations": conv_iters, "converged": converged, "tolerance": 1e-5},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "hb_spmv_kernel<HbIceEpi,true>", "peak_source": peak_src,
+                     "bytes_per_launch": bytes_spmv / world, "avg_launch_ms": spmv_ms,
+                     "frac_of_nominal_8TBps": achieved / 8000.0},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if kr is not None:
+        line["kr"] = kr
+    if not args.no_cpu and world == 1:
+        base, _ = cpu_ice_baseline(args.workload, seconds_budget=25.0, use_gpu_generator=True)
+        line["cpu_baseline"] = base
+        if kr is not None:
+            line["kr"]["cpu_baseline"] = cpu_kr_baseline()
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_kr(torch, L, check, _lib, DeviceCSR, local, stream, sptr):
+    """configs[1]: KR on the synthetic 25 kb matrix, 1 GPU: mat-vec throughput + time to converge."""
+    method, bins, kw = synth_kwargs("kr25k", clean=False)
+    n = int(sum(bins))
+    with DeviceCSR.synthetic(bins, device=local, **kw) as dev:
+        nnz = dev.nnz
+        h = dev.handle
+        x = torch.ones(n, dtype=torch.float64, device="cuda")
+        v = torch.ones(n, dtype=torch.float64, device="cuda")
+        p = torch.ones(n, dtype=torch.float64, device="cuda")
+        w = torch.zeros(n, dtype=torch.float64, device="cuda")
+        P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+
+        def mv():
+            check(L.hb_dev_spmv(h, P(x), 1e-5, P(x), P(v), P(p), P(w), 0, sptr))
+        for _ in range(5):
+            mv()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 30
+        e0.record(stream)
+        for _ in range(reps):
+            mv()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        mv_ms = e0.elapsed_time(e1) / reps
+        t0 = time.time()
+        xs, outer, matvecs, resid = dev.kr()
+        kr_s = time.time() - t0
+    peak, _src = measured_peak()
+    bytes_mv = 12.0 * nnz + 120.0 * n
+    return {"workload": workload_name("kr25k", bins, kw) + " incl. 2% low-coverage and 0.5% empty bins",
+            "bins": n, "nnz": nnz, "matvec_ms": mv_ms, "matvec_nnz_per_s": nnz / (mv_ms * 1e-3),
+            "matvec_GBps": bytes_mv / (mv_ms * 1e-3) / 1e9, "matvec_frac_of_peak": bytes_mv / (mv_ms * 1e-3) / 1e9 / peak,
+            "time_to_converge_ms": kr_s * 1e3, "outer_iterations": outer, "matvecs": matvecs, "residual": resid,
+            "nnz_per_s_converge": nnz * matvecs / kr_s}
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,234 @@
+/*
+ * Plain-C CPU restatement for the matrix-correction path.  TEST INFRASTRUCTURE ONLY: loaded by
+ * tests/ and by bench.py's cpu_baseline / --impl reference legs through oracle/hic_cpu.py, never by
+ * the product.
+ *
+ *   ice_loop_coo()   the hot loop of the reference, hicexplorer/iterativeCorrection.py:40-74, in the
+ *                    reference's own formulation (COO triplets, row sums, two in-place rescaling
+ *                    passes, overflow scan), one OpenMP thread team.  threads=1 reproduces the
+ *                    reference's single-threaded numpy arithmetic order exactly for the row sums
+ *                    (sequential accumulation in stored order, like scipy's coo_matvec).
+ *   kr_matvec()      y = x o ((A + eps I) u) + v o p : the mat-vec inside krbalancing's CG loop
+ *                    (restated in oracle/kr_oracle.py), CSR, OpenMP over rows.
+ *   synth_*()        the benchmark's synthetic matrix, same function as
+ *                    hicexplorer_b200/csrc/hb_synth.cu and oracle/synth_ref.py.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* returns iterations done; *deviation_out = last max|s-1|; -1 on overflow (> 1e100) */
+int ice_loop_coo(int64_t n, int64_t nnz, const int32_t* row, const int32_t* col, double* data, double* bias,
+                 int max_iter, double tol, int threads, double* deviation_out) {
+    double* s = (double*)malloc(sizeof(double) * (size_t)n);
+    int done = 0;
+    double dev = NAN;
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#endif
+    for (int it = 0; it < max_iter; ++it) {
+        done++;
+        memset(s, 0, sizeof(double) * (size_t)n);
+        if (threads == 1) {
+            for (int64_t k = 0; k < nnz; ++k) s[row[k]] += data[k]; /* W.sum(axis=1), line 42 */
+        } else {
+#pragma omp parallel for schedule(static)
+            for (int64_t k = 0; k < nnz; ++k) {
+#pragma omp atomic
+                s[row[k]] += data[k];
+            }
+        }
+        double tot = 0.0;
+        int64_t cnt = 0;
+        for (int64_t i = 0; i < n; ++i)
+            if (s[i] != 0.0) {
+                tot += s[i];
+                cnt++;
+            }
+        const double mean = tot / (double)cnt; /* line 44 */
+        dev = 0.0;
+        for (int64_t i = 0; i < n; ++i) {
+            s[i] = s[i] / mean;
+            bias[i] *= s[i];
+            const double d = fabs(s[i] - 1.0);
+            if (d > dev || d != d) dev = d;
+            s[i] = 1.0 / s[i];
+        }
+        int overflow = 0;
+#pragma omp parallel for schedule(static) reduction(| : overflow)
+        for (int64_t k = 0; k < nnz; ++k) {
+            double v = data[k];
+            v *= s[row[k]]; /* line 56 */
+            v *= s[col[k]]; /* line 57 */
+            data[k] = v;
+            if (v > 1e100) overflow |= 1; /* line 58 */
+        }
+        if (overflow) {
+            free(s);
+            return -1;
+        }
+        if (dev < tol) break; /* line 72 */
+    }
+    free(s);
+    if (deviation_out) *deviation_out = dev;
+    return done;
+}
+
+void kr_matvec(int64_t n, const int64_t* indptr, const int32_t* idx, const double* val, const double* u,
+               const double* x, const double* v, const double* p, double eps, double* out, int threads) {
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t i = 0; i < n; ++i) {
+        double acc = 0.0;
+        for (int64_t k = indptr[i]; k < indptr[i + 1]; ++k) acc += val[k] * u[idx[k]];
+        double r = x[i] * (acc + eps * u[i]);
+        if (v && p) r += v[i] * p[i];
+        out[i] = r;
+    }
+}
+
+/* ---------------- synthetic matrix (same function as hb_synth.cu) ---------------- */
+static inline uint64_t mix64(uint64_t z) {
+    z ^= z >> 30;
+    z *= 0xbf58476d1ce4e5b9ull;
+    z ^= z >> 27;
+    z *= 0x94d049bb133111ebull;
+    z ^= z >> 31;
+    return z;
+}
+static inline uint64_t hash3(uint64_t seed, uint64_t a, uint64_t b) {
+    uint64_t z = mix64(seed + 0x9E3779B97F4A7C15ull * (a + 1));
+    return mix64(z ^ (0xD1B54A32D192ED03ull * (b + 1)));
+}
+static inline double u01(uint64_t h) { return (double)(h >> 11) * (1.0 / 9007199254740992.0); }
+#define TAG_BASE (1ull << 40)
+
+typedef struct {
+    uint64_t seed;
+    int32_t nchrom, band, n_trans, reserved;
+    double d0, gamma, lambda0, low_frac, empty_frac;
+} synth_params;
+
+static double count_of(uint64_t hp, double lam, double ga, double gb) {
+    const double u2 = u01(mix64(hp + 0x9E3779B97F4A7C15ull));
+    volatile double t = lam * ga; /* volatile: forbid FMA contraction, one rounding per operation */
+    t = t * gb;
+    t = t * u2;
+    return 1.0 + floor(t);
+}
+
+static int cmp_i64(const void* a, const void* b) {
+    const int64_t x = *(const int64_t*)a, y = *(const int64_t*)b;
+    return (x > y) - (x < y);
+}
+
+/* pass 1 (idx == NULL): fills indptr[n+1]; pass 2: fills idx/val.  Returns nnz. */
+int64_t synth_generate(const synth_params* p, const int64_t* chrom_bins, int64_t* indptr, int32_t* idx, double* val) {
+    int64_t n = 0;
+    int64_t* off = (int64_t*)malloc(sizeof(int64_t) * (size_t)(p->nchrom + 1));
+    off[0] = 0;
+    for (int c = 0; c < p->nchrom; ++c) off[c + 1] = off[c] + chrom_bins[c];
+    n = off[p->nchrom];
+    double* g = (double*)malloc(sizeof(double) * (size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        if (u01(hash3(p->seed, (uint64_t)i, TAG_BASE + 0)) < p->empty_frac) g[i] = 0.0;
+        else if (u01(hash3(p->seed, (uint64_t)i, TAG_BASE + 1)) < p->low_frac) g[i] = 0.02;
+        else {
+            const double u = u01(hash3(p->seed, (uint64_t)i, TAG_BASE + 2));
+            volatile double t = u * u;
+            t = t * u;
+            t = 4.8 * t;
+            g[i] = 0.2 + t;
+        }
+    }
+    int64_t cs[64];
+    int ncs = 0;
+    for (int k = 0; k < p->n_trans && k < 32; ++k) cs[ncs++] = (int64_t)(hash3(p->seed, (uint64_t)k, TAG_BASE + 3) % (uint64_t)n);
+    qsort(cs, (size_t)ncs, sizeof(int64_t), cmp_i64);
+    {
+        int m = 0;
+        for (int k = 0; k < ncs; ++k)
+            if (m == 0 || cs[k] != cs[m - 1]) cs[m++] = cs[k];
+        ncs = m;
+    }
+    const int fill = idx != NULL;
+    int64_t* chrom_of = (int64_t*)malloc(sizeof(int64_t) * (size_t)n);
+    for (int c = 0; c < p->nchrom; ++c)
+        for (int64_t i = off[c]; i < off[c + 1]; ++i) chrom_of[i] = c;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t i = 0; i < n; ++i) {
+        int64_t w = fill ? indptr[i] : 0;
+        int64_t c_n = 0;
+        if (g[i] != 0.0) {
+            const int64_t clo = off[chrom_of[i]], chi = off[chrom_of[i] + 1];
+            const int64_t blo = i - p->band > clo ? i - p->band : clo;
+            const int64_t bhi = i + p->band < chi - 1 ? i + p->band : chi - 1;
+            int64_t tj[64];
+            int nt = 0;
+            for (int k = 0; k < ncs; ++k) {
+                int64_t j = (cs[k] - i) % n;
+                if (j < 0) j += n;
+                if ((j < blo || j > bhi) && g[j] != 0.0) tj[nt++] = j;
+            }
+            qsort(tj, (size_t)nt, sizeof(int64_t), cmp_i64);
+            int t = 0;
+            for (; t < nt && tj[t] < blo; ++t) {
+                if (fill) {
+                    const int64_t a = i < tj[t] ? i : tj[t], b = i < tj[t] ? tj[t] : i;
+                    idx[w] = (int32_t)tj[t];
+                    val[w] = count_of(hash3(p->seed, (uint64_t)a, (uint64_t)b), 2.0, g[a], g[b]);
+                    w++;
+                }
+                c_n++;
+            }
+            for (int64_t j = blo; j <= bhi; ++j) {
+                if (g[j] == 0.0) continue;
+                const int64_t a = i < j ? i : j, b = i < j ? j : i;
+                const uint64_t hp = hash3(p->seed, (uint64_t)a, (uint64_t)b);
+                const double d1 = (double)(b - a + 1);
+                const double u = u01(hp);
+                int ex;
+                if (p->gamma == 1.0) {
+                    volatile double t2 = u * d1;
+                    ex = t2 < p->d0;
+                } else ex = u < pow(p->d0 / d1, p->gamma);
+                if (!ex) continue;
+                if (fill) {
+                    volatile double q = (double)(b - a) / p->d0;
+                    q = 1.0 + q;
+                    q = p->lambda0 / q;
+                    idx[w] = (int32_t)j;
+                    val[w] = count_of(hp, q, g[a], g[b]);
+                    w++;
+                }
+                c_n++;
+            }
+            for (; t < nt; ++t) {
+                if (fill) {
+                    const int64_t a = i < tj[t] ? i : tj[t], b = i < tj[t] ? tj[t] : i;
+                    idx[w] = (int32_t)tj[t];
+                    val[w] = count_of(hash3(p->seed, (uint64_t)a, (uint64_t)b), 2.0, g[a], g[b]);
+                    w++;
+                }
+                c_n++;
+            }
+        }
+        if (!fill) indptr[i + 1] = c_n;
+    }
+    int64_t nnz;
+    if (!fill) {
+        indptr[0] = 0;
+        for (int64_t i = 0; i < n; ++i) indptr[i + 1] += indptr[i];
+    }
+    nnz = indptr[n];
+    free(off);
+    free(g);
+    free(chrom_of);
+    return nnz;
+}

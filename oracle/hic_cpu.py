@@ -1,0 +1,80 @@
+"""ctypes loader for the plain-C CPU restatement (oracle/hic_cpu.c).  TEST INFRASTRUCTURE ONLY."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+from scipy import sparse
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "libhic_cpu.so")
+
+
+class SynthParams(ctypes.Structure):
+    _fields_ = [("seed", ctypes.c_uint64), ("nchrom", ctypes.c_int32), ("band", ctypes.c_int32),
+                ("n_trans", ctypes.c_int32), ("reserved", ctypes.c_int32), ("d0", ctypes.c_double),
+                ("gamma", ctypes.c_double), ("lambda0", ctypes.c_double), ("low_frac", ctypes.c_double),
+                ("empty_frac", ctypes.c_double)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            subprocess.check_call(["make", "-s", "-C", HERE])
+        L = ctypes.CDLL(LIB)
+        vp = ctypes.c_void_p
+        L.ice_loop_coo.restype = ctypes.c_int
+        L.ice_loop_coo.argtypes = [ctypes.c_int64, ctypes.c_int64, vp, vp, vp, vp, ctypes.c_int, ctypes.c_double,
+                                   ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+        L.kr_matvec.restype = None
+        L.kr_matvec.argtypes = [ctypes.c_int64, vp, vp, vp, vp, vp, vp, vp, ctypes.c_double, vp, ctypes.c_int]
+        L.synth_generate.restype = ctypes.c_int64
+        L.synth_generate.argtypes = [ctypes.POINTER(SynthParams), vp, vp, vp, vp]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def synth_matrix(chrom_bins, seed=0, band=2000, d0=200.0, gamma=1.0, lambda0=40.0, n_trans=8, low_frac=0.02,
+                 empty_frac=0.005):
+    """Same matrix as DeviceCSR.synthetic(...) / oracle.synth_ref.synth_matrix(...), generated in C."""
+    cb = np.ascontiguousarray(chrom_bins, dtype=np.int64)
+    n = int(cb.sum())
+    p = SynthParams(seed=seed, nchrom=len(cb), band=band, n_trans=n_trans, reserved=0, d0=d0, gamma=gamma,
+                    lambda0=lambda0, low_frac=low_frac, empty_frac=empty_frac)
+    indptr = np.zeros(n + 1, dtype=np.int64)
+    nnz = lib().synth_generate(ctypes.byref(p), _p(cb), _p(indptr), None, None)
+    idx = np.empty(nnz, dtype=np.int32)
+    val = np.empty(nnz, dtype=np.float64)
+    lib().synth_generate(ctypes.byref(p), _p(cb), _p(indptr), _p(idx), _p(val))
+    return sparse.csr_matrix((val, idx, indptr), shape=(n, n))
+
+
+def ice_loop(matrix, max_iter, tol=0.0, threads=1):
+    """The reference's hot loop in C on COO triplets.  Returns (bias, iterations, deviation, scaled data)."""
+    coo = sparse.coo_matrix(matrix)
+    row = np.ascontiguousarray(coo.row, dtype=np.int32)
+    col = np.ascontiguousarray(coo.col, dtype=np.int32)
+    data = np.ascontiguousarray(coo.data, dtype=np.float64).copy()
+    bias = np.ones(matrix.shape[0], dtype=np.float64)
+    dev = ctypes.c_double()
+    it = lib().ice_loop_coo(matrix.shape[0], len(data), _p(row), _p(col), _p(data), _p(bias), int(max_iter),
+                            float(tol), int(threads), ctypes.byref(dev))
+    return bias, it, dev.value, data
+
+
+def kr_matvec(csr, u, x, v=None, p=None, eps=1e-5, threads=0):
+    n = csr.shape[0]
+    out = np.empty(n, dtype=np.float64)
+    ip = np.ascontiguousarray(csr.indptr, dtype=np.int64)
+    ix = np.ascontiguousarray(csr.indices, dtype=np.int32)
+    lib().kr_matvec(n, _p(ip), _p(ix), _p(np.ascontiguousarray(csr.data, dtype=np.float64)), _p(u), _p(x), _p(v),
+                    _p(p), float(eps), _p(out), int(threads))
+    return out

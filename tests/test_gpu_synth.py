@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 from oracle import ice_oracle
-from tests.synth_ref import synth_matrix
+from oracle.synth_ref import synth_matrix
 
 pytestmark = pytest.mark.gpu
 
