@@ -70,7 +70,7 @@ def synth_kwargs(workload, clean=True):
     method, res, target, band = WORKLOADS[workload]
     bins = chrom_bins(res)
     d0 = solve_d0(bins, band, target)
-    kw = dict(seed=0, band=band, d0=d0, gamma=1.0, lambda0=40.0, n_trans=16,
+    kw = dict(seed=0, band=band, d0=d0, gamma=1.0, lambda0=40.0, n_trans=32, lambda_trans=400.0,
               low_frac=0.0 if clean else 0.02, empty_frac=0.0 if clean else 0.005)
     return method, bins, kw
 
@@ -237,11 +237,14 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-kr", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="timed ICE loop only (for ncu captures)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
         return
     args.warmup = max(args.warmup, 3)
+    if args.quick:
+        args.no_e2e = args.no_cpu = args.no_kr = True
 
     import torch
     import torch.distributed as dist
@@ -326,7 +329,7 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for _ in range(max(args.warmup, 20)):     # let the sampler thread spin up under load (all ranks)
+    for _ in range(0 if args.quick else max(args.warmup, 20)):     # let the sampler spin up under load (all ranks)
         ice_step()
     pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -351,7 +354,7 @@ def main():
     status = torch.zeros(4, dtype=torch.int32, pin_memory=True)
     t0 = time.time()
     conv_iters = 0
-    for k in range(1, 501):
+    for k in range(1, 1 if args.quick else 501):
         check(L.hb_dev_ice_spmv(h, eptr, rank, world, sptr))
         if world > 1:
             dist.all_reduce(exch[:n + world])

@@ -44,7 +44,7 @@ class SynthParams(ctypes.Structure):
     _fields_ = [("seed", ctypes.c_uint64), ("nchrom", ctypes.c_int32), ("band", ctypes.c_int32),
                 ("n_trans", ctypes.c_int32), ("reserved", ctypes.c_int32), ("d0", ctypes.c_double),
                 ("gamma", ctypes.c_double), ("lambda0", ctypes.c_double), ("low_frac", ctypes.c_double),
-                ("empty_frac", ctypes.c_double)]
+                ("empty_frac", ctypes.c_double), ("lambda_trans", ctypes.c_double)]
 
 
 ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p)

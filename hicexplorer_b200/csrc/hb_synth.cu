@@ -33,7 +33,7 @@ struct HbSynthDev {
     int64_t n;
     int32_t band;
     int32_t n_trans;
-    double d0, gamma, lambda0, low_frac, empty_frac;
+    double d0, gamma, lambda0, low_frac, empty_frac, lambda_trans;
     int64_t trans_c[HB_SYNTH_MAX_TRANS];
 };
 
@@ -107,7 +107,7 @@ hb_synth_rows_kernel(HbSynthDev p, const int64_t* __restrict__ chrom_off, int nc
                 tj = j;
                 if (FILL) {
                     const int64_t a = i < j ? i : j, b = i < j ? j : i;
-                    tv = hb_synth_count(p, hb_hash3(p.seed, (uint64_t)a, (uint64_t)b), 2.0, gi, g[j], i < j);
+                    tv = hb_synth_count(p, hb_hash3(p.seed, (uint64_t)a, (uint64_t)b), p.lambda_trans, gi, g[j], i < j);
                 }
             }
         }
@@ -216,6 +216,7 @@ extern "C" int hb_synth_create(hb_csr** out, const hb_synth_params* prm, const i
     p.lambda0 = prm->lambda0;
     p.low_frac = prm->low_frac;
     p.empty_frac = prm->empty_frac;
+    p.lambda_trans = prm->lambda_trans;
     {
         std::vector<int64_t> cs;
         for (int k = 0; k < prm->n_trans; ++k) cs.push_back((int64_t)(hb_hash3(prm->seed, (uint64_t)k, HB_TAG_BASE + 3) % (uint64_t)n));

@@ -67,14 +67,14 @@ class DeviceCSR(object):
 
     @classmethod
     def synthetic(cls, chrom_bins, seed=0, band=2000, d0=200.0, gamma=1.0, lambda0=40.0, n_trans=8,
-                  low_frac=0.02, empty_frac=0.005, row_range=None, device=0):
+                  low_frac=0.02, empty_frac=0.005, lambda_trans=2.0, row_range=None, device=0):
         """Deterministic synthetic Hi-C matrix generated directly in HBM."""
         _lib.require_device()
         cb = np.ascontiguousarray(chrom_bins, dtype=np.int64)
         n = int(cb.sum())
         row0, row1 = (0, n) if row_range is None else row_range
         p = _lib.SynthParams(seed=seed, nchrom=len(cb), band=band, n_trans=n_trans, reserved=0, d0=d0, gamma=gamma,
-                             lambda0=lambda0, low_frac=low_frac, empty_frac=empty_frac)
+                             lambda0=lambda0, low_frac=low_frac, empty_frac=empty_frac, lambda_trans=lambda_trans)
         h = ctypes.c_void_p()
         check(lib().hb_synth_create(ctypes.byref(h), ctypes.byref(p), ptr(cb), row0, row1 - row0, device))
         return cls(h, device)

@@ -209,7 +209,7 @@ HB_API int hb_dev_spmv(hb_csr* h, const double* d_u, double eps, const double* d
 /* ---- synthetic Hi-C matrices (benchmark inputs) --------------------
  * Deterministic symmetric matrix generated directly in HBM, block by block:
  * chromosome layout chrom_bins[nchrom]; cis entry (i,j) in the same chromosome with |i-j| <= band
- * exists iff hash(seed,min,max) < min(1, (d0/(|i-j|+1))^gamma); n_trans far entries per row at
+ * exists iff hash(seed,min,max) < min(1, (d0/(|i-j|+1))^gamma); n_trans far entries per row (scale lambda_trans) at
  * j = (c_k - i) mod n; integer counts with planted per-bin biases, `low_frac` low-coverage
  * bins and `empty_frac` empty bins.  The same generator in numpy (tests/synth_ref.py) reproduces
  * it on the CPU for cross-checks.  Rows [row0, row0+n_rows). */
@@ -224,6 +224,7 @@ typedef struct hb_synth_params {
     double lambda0;
     double low_frac;
     double empty_frac;
+    double lambda_trans; /* mean scale of the far-entry counts */
 } hb_synth_params;
 HB_API int hb_synth_create(hb_csr** out, const hb_synth_params* p, const int64_t* chrom_bins, int64_t row0,
                     int64_t n_rows, int device);

@@ -112,7 +112,7 @@ static inline double u01(uint64_t h) { return (double)(h >> 11) * (1.0 / 9007199
 typedef struct {
     uint64_t seed;
     int32_t nchrom, band, n_trans, reserved;
-    double d0, gamma, lambda0, low_frac, empty_frac;
+    double d0, gamma, lambda0, low_frac, empty_frac, lambda_trans;
 } synth_params;
 
 static double count_of(uint64_t hp, double lam, double ga, double gb) {
@@ -182,7 +182,7 @@ int64_t synth_generate(const synth_params* p, const int64_t* chrom_bins, int64_t
                 if (fill) {
                     const int64_t a = i < tj[t] ? i : tj[t], b = i < tj[t] ? tj[t] : i;
                     idx[w] = (int32_t)tj[t];
-                    val[w] = count_of(hash3(p->seed, (uint64_t)a, (uint64_t)b), 2.0, g[a], g[b]);
+                    val[w] = count_of(hash3(p->seed, (uint64_t)a, (uint64_t)b), p->lambda_trans, g[a], g[b]);
                     w++;
                 }
                 c_n++;
@@ -213,7 +213,7 @@ int64_t synth_generate(const synth_params* p, const int64_t* chrom_bins, int64_t
                 if (fill) {
                     const int64_t a = i < tj[t] ? i : tj[t], b = i < tj[t] ? tj[t] : i;
                     idx[w] = (int32_t)tj[t];
-                    val[w] = count_of(hash3(p->seed, (uint64_t)a, (uint64_t)b), 2.0, g[a], g[b]);
+                    val[w] = count_of(hash3(p->seed, (uint64_t)a, (uint64_t)b), p->lambda_trans, g[a], g[b]);
                     w++;
                 }
                 c_n++;

@@ -14,7 +14,7 @@ class SynthParams(ctypes.Structure):
     _fields_ = [("seed", ctypes.c_uint64), ("nchrom", ctypes.c_int32), ("band", ctypes.c_int32),
                 ("n_trans", ctypes.c_int32), ("reserved", ctypes.c_int32), ("d0", ctypes.c_double),
                 ("gamma", ctypes.c_double), ("lambda0", ctypes.c_double), ("low_frac", ctypes.c_double),
-                ("empty_frac", ctypes.c_double)]
+                ("empty_frac", ctypes.c_double), ("lambda_trans", ctypes.c_double)]
 
 
 _lib = None
@@ -43,12 +43,12 @@ def _p(a):
 
 
 def synth_matrix(chrom_bins, seed=0, band=2000, d0=200.0, gamma=1.0, lambda0=40.0, n_trans=8, low_frac=0.02,
-                 empty_frac=0.005):
+                 empty_frac=0.005, lambda_trans=2.0):
     """Same matrix as DeviceCSR.synthetic(...) / oracle.synth_ref.synth_matrix(...), generated in C."""
     cb = np.ascontiguousarray(chrom_bins, dtype=np.int64)
     n = int(cb.sum())
     p = SynthParams(seed=seed, nchrom=len(cb), band=band, n_trans=n_trans, reserved=0, d0=d0, gamma=gamma,
-                    lambda0=lambda0, low_frac=low_frac, empty_frac=empty_frac)
+                    lambda0=lambda0, low_frac=low_frac, empty_frac=empty_frac, lambda_trans=lambda_trans)
     indptr = np.zeros(n + 1, dtype=np.int64)
     nnz = lib().synth_generate(ctypes.byref(p), _p(cb), _p(indptr), None, None)
     idx = np.empty(nnz, dtype=np.int32)

@@ -52,7 +52,7 @@ def _count(hp, lam, ga, gb):
 
 
 def synth_matrix(chrom_bins, seed=0, band=2000, d0=200.0, gamma=1.0, lambda0=40.0, n_trans=8, low_frac=0.02,
-                 empty_frac=0.005):
+                 empty_frac=0.005, lambda_trans=2.0):
     """Full symmetric CSR (float64 integer counts), identical to DeviceCSR.synthetic(...)."""
     chrom_bins = np.asarray(chrom_bins, dtype=np.int64)
     off = np.concatenate([[0], np.cumsum(chrom_bins)])
@@ -83,7 +83,7 @@ def synth_matrix(chrom_bins, seed=0, band=2000, d0=200.0, gamma=1.0, lambda0=40.
             tj = np.sort(tj[keep])
             if len(tj):
                 ta, tb = np.minimum(i, tj), np.maximum(i, tj)
-                tv = _count(hash3(seed, ta, tb), 2.0, g[ta], g[tb])
+                tv = _count(hash3(seed, ta, tb), lambda_trans, g[ta], g[tb])
             else:
                 tv = np.zeros(0)
             before = tj < blo
