@@ -509,6 +509,18 @@ def _dtype_message(dt):
     raise NotImplementedError("cannot write dtype %r" % dt)
 
 
+def _enum_message(dt, mapping):
+    dt = np.dtype(dt)
+    names = list(mapping)
+    body = struct.pack("<BBBBI", 0x18, len(names) & 0xFF, (len(names) >> 8) & 0xFF, 0, dt.itemsize)
+    body += _dtype_message(dt)
+    for nm in names:
+        enc = nm.encode("utf-8") + b"\x00"
+        body += enc + b"\x00" * (_pad8(len(enc)) - len(enc))
+    body += np.asarray([mapping[nm] for nm in names], dtype=dt).tobytes()
+    return body
+
+
 def _dataspace_message(shape):
     if shape is None:  # scalar
         return struct.pack("<BBBB4x", 1, 0, 0, 0)
@@ -566,8 +578,10 @@ class Writer(object):
         node = self._node(path)
         node["attrs"].update(attrs or {})
 
-    def dataset(self, path, array, attrs=None):
+    def dataset(self, path, array, attrs=None, enum=None):
+        """``enum`` = ordered mapping name -> integer value: store as an HDF5 enum (cooler ``bins/chrom``)."""
         node = self._node(path)
+        node["enum"] = enum
         arr = np.ascontiguousarray(array)
         if arr.dtype.kind == "U":
             arr = arr.astype("S")
@@ -598,7 +612,8 @@ class Writer(object):
             shape = arr.shape if arr.ndim else None
             msgs = [
                 _message(0x01, _dataspace_message(shape)),
-                _message(0x03, _dtype_message(arr.dtype), flags=1),
+                _message(0x03, _enum_message(arr.dtype, node["enum"]) if node.get("enum") else
+                         _dtype_message(arr.dtype), flags=1),
                 _message(0x05, struct.pack("<BBBB", 2, 2, 2, 0x02)),  # fill value: never written
                 _message(0x08, struct.pack("<BBQQ", 3, 1, daddr, len(raw))),
             ]

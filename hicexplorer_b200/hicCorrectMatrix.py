@@ -1,0 +1,201 @@
+"""``hicCorrectMatrix correct`` on a B200: same sub-command, flags, defaults, log lines, exit codes and output
+files as the reference driver (hicexplorer/hicCorrectMatrix.py:32-254, 595-779), with the numerics on the GPU.
+
+Differences, all additive or documented:
+  * ``--tolerance`` (default 1e-5 = the value hard-wired in the reference, iterativeCorrection.py:10) and
+    ``--device`` are new optional flags;
+  * the ICE branch uploads the matrix once and runs zero-bin masking, NaN/Inf scrub, the MAD filter, bin deletion
+    and the iterations on the device (``pipeline.ice_pipeline``) instead of round-tripping through scipy;
+  * ``diagnostic_plot`` (matplotlib histogram, :425-545) is out of scope and exits with an explanation;
+  * ``--transCutoff`` (hicmatrix ``truncTrans``) is not implemented yet and exits with an explanation;
+    ``--inflationCutoff`` only ever worked together with it in the reference (``pre_row_sum`` is otherwise
+    undefined, :699/:771) and is rejected the same way.
+"""
+import argparse
+import logging
+import sys
+
+import numpy as np
+from scipy.sparse import lil_matrix
+
+from . import hicmatrix_lite as hm
+from ._version import __version__
+from .krbalancing import kr_balancing
+from .pipeline import ice_pipeline
+
+log = logging.getLogger(__name__)
+
+
+def parse_arguments(args=None):
+    parser = argparse.ArgumentParser(
+        formatter_class=argparse.RawDescriptionHelpFormatter, conflict_handler='resolve',
+        description="""
+This function provides 2 balancing methods which can be applied on a raw matrix.
+
+I. KR: It balances a matrix using a fast balancing algorithm introduced by Knight and Ruiz (2012).
+
+II. ICE: Iterative correction of a Hi-C matrix (see Imakaev et al. 2012). For this method to work correctly, bins
+with zero reads assigned to them should be removed as they cannot be corrected, as well as bins with low or
+extremely high coverage (--filterThreshold).
+
+B200-native implementation: the correction runs on the GPU through libhicbalance.so.
+""")
+    parser.add_argument('--version', action='version', version='%(prog)s {}'.format(__version__))
+    subparsers = parser.add_subparsers(title="Options", dest='command', metavar='', help="""To get detailed help on each of the options: \r
+    $ hicCorrectMatrix diagnostic_plot -h \r
+    $ hicCorrectMatrix correct -h """)
+    plot_mode = subparsers.add_parser('diagnostic_plot', formatter_class=argparse.ArgumentDefaultsHelpFormatter,
+                                      help="(not available in the B200 build: plotting is out of scope)")
+    plot_mode.add_argument('--matrix', '-m', required=True)
+    plot_mode.add_argument('--plotName', '-o', required=True)
+    plot_mode.add_argument('--chromosomes', default=None, nargs='+')
+    plot_mode.add_argument('--xMax', default=None, type=float)
+    plot_mode.add_argument('--perchr', action='store_true')
+    plot_mode.add_argument('--verbose', action='store_true')
+    subparsers.add_parser('correct', formatter_class=argparse.ArgumentDefaultsHelpFormatter, parents=[correct_subparser()],
+                          help="""Run Knight-Ruiz matrix balancing algorithm (KR) or the iterative matrix correction (ICE).""",
+                          usage='%(prog)s --matrix hic_matrix.h5 --filterThreshold -1.2 5 (Only if ICE) -out corrected_matrix.h5 \n')
+    return parser
+
+
+def correct_subparser():
+    parser = argparse.ArgumentParser(add_help=False)
+    req = parser.add_argument_group('Required arguments')
+    req.add_argument('--matrix', '-m', help='Name of the Hi-C matrix to correct in .h5 format.', required=True)
+    req.add_argument('--outFileName', '-o', help='File name to save the resulting matrix. The output is a .h5 file.',
+                     required=True)
+    opt = parser.add_argument_group('Optional arguments')
+    opt.add_argument('--correctionMethod', help='Method to be used for matrix correction. It can be set to KR or ICE'
+                     ' (Default: %(default)s).', type=str, metavar='STR', default='KR', choices=['KR', 'ICE'])
+    opt.add_argument('--filterThreshold', '-t', help='Removes bins of low or large coverage. A lower and upper '
+                     'threshold are required separated by space, e.g. --filterThreshold -1.5 5. Applied only for ICE!',
+                     type=float, nargs=2, default=None)
+    opt.add_argument('--iterNum', '-n', help='Number of iterations to compute. only for ICE! (Default: %(default)s).',
+                     type=int, metavar='INT', default=500)
+    opt.add_argument('--inflationCutoff', help='Value corresponding to the maximum number of times a bin can be '
+                     'scaled up during the iterative correction. Only for ICE!', type=float)
+    opt.add_argument('--transCutoff', '-transcut', help='Clip high counts in the top -transcut trans regions '
+                     '(i.e. between chromosomes). Only for ICE!', type=float)
+    opt.add_argument('--sequencedCountCutoff', help='Each bin receives a value indicating the fraction that is '
+                     'covered by reads. A cutoff of 0.5 will discard all those bins that have less than half of the '
+                     'bin covered. Only for ICE!', default=None, type=float)
+    opt.add_argument('--chromosomes', help='List of chromosomes to be included in the iterative correction. The '
+                     'order of the given chromosomes will be then kept for the resulting corrected matrix',
+                     default=None, nargs='+')
+    opt.add_argument('--skipDiagonal', '-s', help='If set, diagonal counts are not included. Only for ICE!',
+                     action='store_true')
+    opt.add_argument('--perchr', help='Normalize each chromosome separately. This is useful for samples from cells '
+                     'with uneven number of chromosomes and/or translocations.', action='store_true')
+    opt.add_argument('--filteredBed', help='Print bins filtered our by  --filterThreshold to this file')
+    opt.add_argument('--verbose', help='Print processing status.', action='store_true')
+    opt.add_argument('--version', action='version', version='%(prog)s {}'.format(__version__))
+    # additive flags of the B200 build
+    opt.add_argument('--tolerance', help='ICE convergence tolerance on the marginals (Default: %(default)s, the '
+                     'value hard-wired in the reference).', type=float, default=1e-5)
+    opt.add_argument('--device', help='CUDA device index (Default: %(default)s).', type=int, default=0)
+    return parser
+
+
+def _is_cooler(path):
+    return str(path).endswith('.cool') or '.cool::' in str(path) or str(path).endswith('.mcool')
+
+
+def main(args=None):
+    args = parse_arguments().parse_args(args)
+    if args.verbose:
+        log.setLevel(logging.INFO)
+        logging.getLogger('hicexplorer_b200.pipeline').setLevel(logging.INFO)
+    if getattr(args, 'command', None) == 'diagnostic_plot' or 'plotName' in args:
+        log.error('diagnostic_plot is a matplotlib histogram and is out of scope of the B200 build; '
+                  'use the reference tool for the plot (the statistics it shows are those of --filterThreshold).')
+        sys.exit(1)
+
+    if _is_cooler(args.matrix) and args.chromosomes is not None and len(args.chromosomes) == 1:
+        ma = hm.hiCMatrix(args.matrix, pChrnameList=[str(c) for c in args.chromosomes])
+    else:
+        ma = hm.hiCMatrix(args.matrix)
+        if args.chromosomes:
+            ma.reorderChromosomes([str(c) for c in args.chromosomes])
+
+    if args.correctionMethod == 'ICE':
+        _correct_ice(ma, args)
+    else:
+        _correct_kr(ma, args)
+    ma.save(args.outFileName, pApplyCorrection=False)
+
+
+def _correct_ice(ma, args):
+    if not args.filterThreshold:
+        log.error('min and max filtering thresholds should be set')
+        sys.exit(1)
+    if args.transCutoff or args.inflationCutoff:
+        log.error('--transCutoff / --inflationCutoff are not implemented in the B200 build yet')
+        sys.exit(1)
+    intervals_all = list(ma.cut_intervals)
+    extra_fn = None
+    if args.sequencedCountCutoff and 0 < args.sequencedCountCutoff < 1:
+        coverage = np.array([iv[3] for iv in intervals_all], dtype=np.float64)
+
+        def extra_fn(kept_ids):
+            return coverage[kept_ids] < args.sequencedCountCutoff
+
+    res = ice_pipeline(ma.matrix, (args.filterThreshold[0], args.filterThreshold[1]), max_iter=args.iterNum,
+                       tolerance=args.tolerance, chr_offsets=ma.chromosome_offsets(), perchr=args.perchr,
+                       skip_diagonal=args.skipDiagonal, device=args.device, want_matrix=True, extra_mask_fn=extra_fn)
+    n = res['n']
+    keep1 = np.setdiff1d(np.arange(n), res['zero_bins'])
+    outlier_regions = res['outliers_rel']
+    pct_outlier = 100 * float(len(outlier_regions)) / max(len(keep1), 1)
+    log.info("Bins that are MAD outliers ({:.2f}%) out of {}: {}".format(pct_outlier, len(keep1), len(outlier_regions)))
+    if args.filteredBed:
+        with open(args.filteredBed, 'w') as f:
+            # the reference iterates a Python set of numpy integers here (hicCorrectMatrix.py:668)
+            for outlier_region in set(np.int64(v) for v in outlier_regions):
+                interval = intervals_all[keep1[outlier_region]]
+                f.write(f"{interval[0]}\t{interval[1]}\t{interval[2]}\t.\t{interval[3]}\t.\n")
+    iters = res['iterations']
+    for k, it in enumerate(iters):
+        if res['deviation'][k] < args.tolerance:
+            log.info("[iterative correction] {} iterations used\n".format(int(it) + 1))
+    # install the corrected matrix / factors in the kept frame; save() re-inserts the masked bins as nan_bins
+    corrected = res['matrix']
+    if not args.perchr or str(args.outFileName).endswith('.h5'):
+        ma.apply_mask_bookkeeping(res['kept'], matrix=corrected)
+    else:
+        ma.apply_mask_bookkeeping(res['kept'])     # perchr + .cool keeps the raw counts (hicCorrectMatrix.py:759-760)
+    ma.setCorrectionFactors(res['bias'])
+    log.info("Total regions to be removed: {}".format(n - len(res['kept'])))
+
+
+def _correct_kr(ma, args):
+    matrix = ma.matrix.astype(np.float64)
+    if args.perchr:
+        corrected_matrix = lil_matrix(matrix.shape)
+        factors = []
+        for chrname in ma.getChrNames():
+            lo, hi = ma.getChrBinRange(chrname)
+            sub = matrix[lo:hi, lo:hi].tocsr()
+            kr = kr_balancing(sub.shape[0], sub.shape[1], sub.count_nonzero(), sub.indptr.astype(np.int64, copy=False),
+                              sub.indices.astype(np.int64, copy=False), sub.data.astype(np.float64, copy=False),
+                              device=args.device)
+            kr.computeKR()
+            if str(args.outFileName).endswith('.h5'):
+                corrected_matrix[lo:hi, lo:hi] = kr.get_normalised_matrix(True)
+            factors.append(kr.get_normalisation_vector(False).todense())
+            kr.close()
+        correction_factors = np.concatenate(factors)
+    else:
+        kr = kr_balancing(matrix.shape[0], matrix.shape[1], matrix.count_nonzero(),
+                          matrix.indptr.astype(np.int64, copy=False), matrix.indices.astype(np.int64, copy=False),
+                          matrix.data.astype(np.float64, copy=False), device=args.device)
+        kr.computeKR()
+        correction_factors = kr.get_normalisation_vector(True).todense()
+        corrected_matrix = kr.get_normalised_matrix(True) if str(args.outFileName).endswith('.h5') else None
+        kr.close()
+    if str(args.outFileName).endswith('.h5'):
+        ma.setMatrixValues(corrected_matrix)
+    ma.setCorrectionFactors(correction_factors)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,151 @@
+"""GPU tests of the drop-in driver, written like the reference's own
+hicexplorer/test/general/test_hicCorrectMatrix.py (argv list -> main() -> compare the output file with the golden
+content).  Inputs are rebuilt from the committed fixtures (tests/golden/*.npz) because /root/reference does not
+exist on the GPU box."""
+import numpy as np
+import pytest
+from scipy import sparse
+
+from hicexplorer_b200 import hdf5lite
+from hicexplorer_b200.hicCorrectMatrix import main
+from hicexplorer_b200.hicmatrix_lite import hiCMatrix
+from oracle import ice_oracle, kr_oracle
+from tests.helpers import csr_from_npz, full_from_pixels
+
+pytestmark = pytest.mark.gpu
+
+
+def _small_input(tmp_path, z, pad_chrom=True):
+    """small_test_matrix restricted to chrUextra+chr3LHet (+ an unrelated chromosome that --chromosomes drops)."""
+    ma = hiCMatrix()
+    m = csr_from_npz(z, "in")
+    iv = [(c.decode(), int(s), int(e), float(x)) for c, s, e, x in zip(z["chr"], z["start"], z["end"], z["extra"])]
+    if pad_chrom:
+        k = 40
+        rng = np.random.default_rng(0)
+        blk = sparse.random(k, k, 0.2, random_state=rng, format="csr")
+        blk = sparse.csr_matrix(np.round((blk + blk.T) * 10))
+        m = sparse.block_diag([blk, m], format="csr")
+        iv = [("chrOther", i * 5000, (i + 1) * 5000, 1.0) for i in range(k)] + iv
+    ma.matrix = sparse.csr_matrix(m)
+    ma.cut_intervals = iv
+    ma._index_intervals()
+    path = str(tmp_path / "small_test_matrix.h5")
+    ma.save(path)
+    return path
+
+
+def _read_h5(path):
+    f = hdf5lite.File(path)
+    shape = tuple(int(v) for v in f["matrix/shape"].read())
+    m = sparse.csr_matrix((f["matrix/data"].read(), f["matrix/indices"].read(), f["matrix/indptr"].read()), shape=shape)
+    return f, m
+
+
+def test_correct_matrix_ICE(tmp_path, small_ice):
+    """mirrors test_correct_matrix_ICE (test_hicCorrectMatrix.py:29-49)"""
+    z = small_ice
+    src = _small_input(tmp_path, z)
+    out = str(tmp_path / "corrected.h5")
+    bed = str(tmp_path / "filtered.bed")
+    main("correct --matrix {} --correctionMethod ICE --chromosomes chrUextra chr3LHet --iterNum 500 "
+         "--outFileName {} --filteredBed {} --filterThreshold -1.5 5.0".format(src, out, bed).split())
+    f, m = _read_h5(out)
+    assert np.array_equal(m.indices, z["golden_indices"]) and np.array_equal(m.indptr, z["golden_indptr"])
+    np.testing.assert_allclose(m.data, z["golden_data"], rtol=1e-8)        # reference: assert_equal
+    assert np.array_equal(f["nan_bins"].read(), z["golden_nan_bins"])
+    cf = f["correction_factors"].read()
+    assert cf.shape == (6313,)
+    assert np.array_equal(np.isnan(cf), np.isnan(z["golden_correction_factors"]))
+    ok = ~np.isnan(cf)
+    np.testing.assert_allclose(cf[ok], z["golden_correction_factors"][ok], rtol=1e-9)
+    assert [c.decode() for c in f["intervals/chr_list"].read()[[0, -1]]] == ["chrUextra", "chr3LHet"]
+    assert np.array_equal(f["intervals/start_list"].read(), z["start"]) and np.array_equal(f["intervals/end_list"].read(), z["end"])
+    got = sorted(open(bed).read().splitlines())
+    want = sorted(str(z["filtered_bed"]).splitlines())
+    assert len(got) == len(want) == 64
+    for a, b in zip(got, want):                       # the reference tolerates 1 differing char per line (:19-26)
+        assert a.split("\t")[:3] == b.split("\t")[:3] and len(a.split("\t")) == 6
+
+
+def test_correct_matrix_KR_H5(tmp_path, small_ice, small_kr):
+    """mirrors test_correct_matrix_KR_H5 (:52-69): data to 5 decimals"""
+    src = _small_input(tmp_path, small_ice)
+    out = str(tmp_path / "kr.h5")
+    main("correct --matrix {} --correctionMethod KR --chromosomes chrUextra chr3LHet --outFileName {}".format(src, out).split())
+    f, m = _read_h5(out)
+    assert np.array_equal(m.indices, small_kr["golden_indices"]) and np.array_equal(m.indptr, small_kr["golden_indptr"])
+    np.testing.assert_almost_equal(m.data, small_kr["golden_data"], decimal=5)
+    cf = f["correction_factors"].read()
+    assert cf.shape == (6313, 1)                                                # (n,1) for KR
+    ref = kr_oracle.kr_pipeline(csr_from_npz(small_ice, "in"), rescale=True)
+    np.testing.assert_allclose(cf.ravel(), ref["x_out"], rtol=5e-6)
+
+
+def _gm_cool(tmp_path, g):
+    ma = hiCMatrix()
+    ma.matrix = full_from_pixels(g)
+    off = g["chrom_offset"]
+    ma.cut_intervals = [(str(c + 1), int((i - off[c]) * 2500000), int((i - off[c] + 1) * 2500000), 1.0)
+                        for c in range(len(off) - 1) for i in range(off[c], off[c + 1])]
+    ma._index_intervals()
+    path = str(tmp_path / "gm12878_raw_values.cool")
+    ma.save(path)
+    return path
+
+
+def test_correct_matrix_KR_cool(tmp_path, gm12878):
+    """mirrors test_correct_matrix_KR_cool (:72-91): .cool keeps the raw counts, weights = rescaled x"""
+    src = _gm_cool(tmp_path, gm12878)
+    out = str(tmp_path / "kr.cool")
+    main("correct --matrix {} --correctionMethod KR --outFileName {}".format(src, out).split())
+    new = hiCMatrix(out)
+    raw = full_from_pixels(gm12878)
+    assert abs(new.matrix - raw).sum() == 0
+    assert new.matrix.sum() // 2 > 3e9                               # lower half of the reference's sanity bound
+    ref = kr_oracle.kr_pipeline(raw, rescale=True)
+    np.testing.assert_allclose(np.asarray(new.correction_factors).ravel(), ref["x_out"], rtol=1e-9)
+
+
+def test_correct_matrix_KR_partial_cool(tmp_path, gm12878, kr_partial):
+    """mirrors test_correct_matrix_KR_partial_cool (:94-109): single chromosome through pChrnameList"""
+    src = _gm_cool(tmp_path, gm12878)
+    out = str(tmp_path / "kr_partial.cool")
+    main("correct --matrix {} --correctionMethod KR --chromosomes 3 --outFileName {}".format(src, out).split())
+    new = hiCMatrix(out)
+    assert new.matrix.shape == (80, 80)
+    w = np.asarray(new.correction_factors).ravel()
+    ratio = kr_partial["weight"] / w
+    assert np.ptp(ratio) < 1e-9 and abs(ratio.mean() - 1) < 5e-6      # the shipped file, up to its rescale constant
+
+
+def test_correct_matrix_ICE_cool_and_perchr(tmp_path, gm12878):
+    g = gm12878
+    src = _gm_cool(tmp_path, g)
+    out = str(tmp_path / "ice.cool")
+    main("correct --matrix {} --correctionMethod ICE --filterThreshold -1.5 5 --outFileName {}".format(src, out).split())
+    new = hiCMatrix(out)
+    ref = ice_oracle.correct_ice_pipeline(full_from_pixels(g), -1.5, 5.0, max_iter=500)
+    cf = np.asarray(new.correction_factors).ravel()
+    np.testing.assert_array_equal(np.flatnonzero(np.isnan(cf)), ref["nan_bins"])
+    np.testing.assert_allclose(cf[ref["kept"]], ref["ice"]["bias"], rtol=1e-9)
+    np.testing.assert_allclose(sparse.triu(new.matrix).tocsr().data, ref["upper"].data, rtol=1e-8)
+    # --perchr: per-chromosome filter + independent corrections, trans contacts dropped in the .h5 output
+    outp = str(tmp_path / "ice_perchr.h5")
+    main("correct --matrix {} --correctionMethod ICE --filterThreshold -1.5 5 --perchr --iterNum 300 "
+         "--outFileName {}".format(src, outp).split())
+    f, m = _read_h5(outp)
+    full = full_from_pixels(g)
+    keep1 = np.setdiff1d(np.arange(full.shape[0]), g["zero_bins"])
+    kept = keep1[np.setdiff1d(np.arange(len(keep1)), g["outliers_rel_perchr"])]
+    cf = f["correction_factors"].read()
+    assert np.array_equal(np.flatnonzero(~np.isnan(cf)), kept)
+    off = g["chrom_offset"]
+    chrom_of = np.searchsorted(off, np.arange(full.shape[0]), side="right") - 1
+    coo = m.tocoo()
+    assert np.all(chrom_of[coo.row] == chrom_of[coo.col])               # no inter-chromosomal entries survive
+    c = 2                                                                # check one chromosome against the oracle
+    ids = kept[chrom_of[kept] == c]
+    blk = ice_oracle.scrub(ice_oracle.select_bins(full, ids))
+    refb = ice_oracle.ice(blk, max_iter=300)
+    np.testing.assert_allclose(cf[ids], refb["bias"], rtol=1e-9)

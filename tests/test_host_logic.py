@@ -1,0 +1,121 @@
+"""CPU tests of the host side above the C ABI: file formats (hdf5lite / hicmatrix_lite), the CLI surface."""
+import numpy as np
+import pytest
+from scipy import sparse
+
+from hicexplorer_b200 import hdf5lite
+from hicexplorer_b200.hicCorrectMatrix import parse_arguments
+from hicexplorer_b200.hicmatrix_lite import hiCMatrix
+from oracle import ref_import
+from tests.helpers import csr_from_npz, full_from_pixels
+
+
+def _ma_from_small(small_ice):
+    ma = hiCMatrix()
+    ma.matrix = csr_from_npz(small_ice, "in")
+    ma.cut_intervals = [(c.decode(), int(s), int(e), float(x)) for c, s, e, x in
+                        zip(small_ice["chr"], small_ice["start"], small_ice["end"], small_ice["extra"])]
+    ma._index_intervals()
+    return ma
+
+
+def test_h5_and_cool_round_trip(tmp_path, small_ice):
+    ma = _ma_from_small(small_ice)
+    assert ma.getChrNames() == ["chrUextra", "chr3LHet"] and list(ma.chromosome_offsets()) == [0, 5801, 6313]
+    ref_full = ma.matrix.copy()
+    ma.maskBins(small_ice["zero_bins"])
+    assert ma.matrix.shape == (183, 183)
+    ma.maskBins(small_ice["outliers_rel"])                      # second call: union of both masks
+    assert ma.matrix.shape == (119, 119)
+    ma.setCorrectionFactors(np.arange(119, dtype=np.float64))
+    for ext in ("h5", "cool"):
+        m2 = _ma_from_small(small_ice)
+        m2.maskBins(small_ice["zero_bins"])
+        m2.maskBins(small_ice["outliers_rel"])
+        m2.setCorrectionFactors(np.arange(119, dtype=np.float64))
+        path = str(tmp_path / ("out." + ext))
+        m2.save(path)
+        back = hiCMatrix(path)
+        assert back.matrix.shape == (6313, 6313)
+        assert abs(back.matrix - sparse.csr_matrix(ref_full.multiply(back.matrix != 0))).sum() == 0
+        cf = np.asarray(back.correction_factors).ravel()
+        assert np.array_equal(np.flatnonzero(np.isnan(cf)), small_ice["golden_nan_bins"])
+        assert np.array_equal(cf[~np.isnan(cf)], np.arange(119, dtype=np.float64))
+        assert [iv[:3] for iv in back.cut_intervals[:2]] == [("chrUextra", 0, 5000), ("chrUextra", 5000, 10000)]
+    f = hdf5lite.File(str(tmp_path / "out.h5"))
+    assert f.attrs["TITLE"] == "HiCExplorer matrix"
+    assert sorted(f.keys()) == ["correction_factors", "intervals", "matrix", "nan_bins"]
+    assert f["matrix/indices"].dtype == np.int32 and f["matrix/indptr"].dtype == np.int32
+    assert f["matrix/data"].dtype == np.float64 and f["nan_bins"].dtype == np.int64
+    assert np.array_equal(f["nan_bins"].read(), small_ice["golden_nan_bins"])
+    up = sparse.csr_matrix((f["matrix/data"].read(), f["matrix/indices"].read(), f["matrix/indptr"].read()),
+                           shape=(6313, 6313))
+    assert sparse.tril(up, -1).nnz == 0
+    c = hdf5lite.File(str(tmp_path / "out.cool"))
+    assert c.attrs["format"] == "HDF5::Cooler" and c.attrs["nbins"] == 6313
+    assert c["bins/chrom"].enum == {"chrUextra": 0, "chr3LHet": 1}
+    b1, b2 = c["pixels/bin1_id"].read(), c["pixels/bin2_id"].read()
+    assert np.all(b1 <= b2) and np.all(np.diff(b1) >= 0)
+    assert np.array_equal(c["indexes/bin1_offset"].read(), np.concatenate([[0], np.cumsum(np.bincount(b1, minlength=6313))]))
+
+
+def test_cool_with_many_chromosomes_round_trip(tmp_path, gm12878):
+    ma = hiCMatrix()
+    ma.matrix = full_from_pixels(gm12878)
+    off = gm12878["chrom_offset"]
+    ma.cut_intervals = [("chr%d" % c, int((i - off[c]) * 2500000), int((i - off[c] + 1) * 2500000), 1.0)
+                        for c in range(len(off) - 1) for i in range(off[c], off[c + 1])]
+    ma._index_intervals()
+    path = str(tmp_path / "g.cool")
+    ma.save(path)
+    back = hiCMatrix(path)
+    assert abs(back.matrix - ma.matrix).sum() == 0 and len(back.getChrNames()) == 25
+    one = hiCMatrix(path, pChrnameList=["chr2"])
+    a, b = int(off[2]), int(off[3])
+    assert abs(one.matrix - ma.matrix[a:b, a:b]).sum() == 0
+
+
+def test_cli_defaults_mirror_the_reference():
+    a = parse_arguments().parse_args(["correct", "-m", "x.h5", "-o", "y.h5"])
+    assert a.correctionMethod == "KR" and a.iterNum == 500 and a.filterThreshold is None
+    assert a.perchr is False and a.skipDiagonal is False and a.chromosomes is None and a.filteredBed is None
+    assert a.inflationCutoff is None and a.transCutoff is None and a.sequencedCountCutoff is None
+    assert a.tolerance == 1e-5 and a.device == 0                      # additive flags
+    b = parse_arguments().parse_args(["correct", "--matrix", "x.h5", "--outFileName", "y.h5", "--correctionMethod", "ICE",
+                                      "-t", "-1.5", "5", "-n", "20", "--chromosomes", "chr1", "chr2", "--perchr", "-s",
+                                      "--filteredBed", "f.bed", "--verbose"])
+    assert b.filterThreshold == [-1.5, 5.0] and b.iterNum == 20 and b.chromosomes == ["chr1", "chr2"] and b.perchr
+    with pytest.raises(SystemExit):
+        parse_arguments().parse_args(["correct", "-m", "x.h5"])         # -o is required
+    with pytest.raises(SystemExit):
+        parse_arguments().parse_args(["correct", "-m", "x", "-o", "y", "--correctionMethod", "XX"])
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="/root/reference not present (GPU box)")
+def test_cli_flags_are_a_superset_of_the_reference_parser():
+    ref = ref_import.load()[3]()
+    mine = parse_arguments()
+
+    def flags(parser):
+        sub = [a for a in parser._actions if a.__class__.__name__ == "_SubParsersAction"][0]
+        out = {}
+        for act in sub.choices["correct"]._actions:
+            for s in act.option_strings:
+                out[s] = (act.default, act.nargs, act.required)
+        return out
+
+    r, m = flags(ref), flags(mine)
+    for flag, spec in r.items():
+        assert flag in m, "missing flag " + flag
+        assert m[flag] == spec, (flag, m[flag], spec)
+    assert set(m) - set(r) == {"--tolerance", "--device"}
+
+
+def test_ice_without_thresholds_exits_1_like_the_reference(tmp_path, small_ice):
+    from hicexplorer_b200.hicCorrectMatrix import main
+    ma = _ma_from_small(small_ice)
+    src = str(tmp_path / "in.h5")
+    ma.save(src)
+    with pytest.raises(SystemExit) as ei:
+        main(["correct", "-m", src, "-o", str(tmp_path / "o.h5"), "--correctionMethod", "ICE"])
+    assert ei.value.code == 1
