@@ -70,6 +70,14 @@ def load():
         _stub("krbalancing", __all__=[])
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
-    from hicexplorer.iterativeCorrection import iterativeCorrection
-    from hicexplorer.hicCorrectMatrix import MAD, filter_by_zscore, parse_arguments
+    # hicexplorer/__init__.py:21-22 calls multiprocessing.set_start_method('fork') at import time; neutralise
+    # that side effect (it raises if a start method is already set and must not leak into the test process)
+    import multiprocessing
+    saved = multiprocessing.set_start_method
+    multiprocessing.set_start_method = lambda *a, **k: None
+    try:
+        from hicexplorer.iterativeCorrection import iterativeCorrection
+        from hicexplorer.hicCorrectMatrix import MAD, filter_by_zscore, parse_arguments
+    finally:
+        multiprocessing.set_start_method = saved
     return iterativeCorrection, MAD, filter_by_zscore, parse_arguments
