@@ -126,17 +126,21 @@ int hb_csr_create(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t row0, in
         }                                                                  \
     } while (0)
     HB_CREATE_CUDA(cudaMalloc(&h->d_indptr, sizeof(int64_t) * (size_t)(n_rows + 1)));
-    HB_CREATE_CUDA(cudaMalloc(&h->d_indices, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1) + 16));
-    HB_CREATE_CUDA(cudaMalloc(&h->d_data, sizeof(double) * (size_t)(nnz > 0 ? nnz : 1) + 16));
+    const int64_t phase = indptr[0] & 3;
+    h->phase = phase;
+    HB_CREATE_CUDA(cudaMalloc(&h->d_indices, sizeof(int32_t) * (size_t)(nnz + phase + 4) + 16));
+    HB_CREATE_CUDA(cudaMalloc(&h->d_data, sizeof(double) * (size_t)(nnz + phase + 4) + 16));
+    HB_CREATE_CUDA(cudaMemsetAsync(h->d_indices, 0, sizeof(int32_t) * 4, s));
+    HB_CREATE_CUDA(cudaMemsetAsync(h->d_data, 0, sizeof(double) * 4, s));
     HB_CREATE_CUDA(cudaMemcpyAsync(h->d_indptr, indptr, sizeof(int64_t) * (size_t)(n_rows + 1),
                                    cudaMemcpyHostToDevice, s));
-    if (indptr[0] != 0) {
+    if (indptr[0] != phase) {
         int64_t n1 = n_rows + 1;
-        hb_rebase_indptr_kernel<<<(unsigned)((n1 + 255) / 256), 256, 0, s>>>(h->d_indptr, n1, indptr[0]);
+        hb_rebase_indptr_kernel<<<(unsigned)((n1 + 255) / 256), 256, 0, s>>>(h->d_indptr, n1, indptr[0] - phase);
         g_hb_launches.fetch_add(1);
     }
     if (nnz > 0) {
-        HB_CREATE_CUDA(cudaMemcpyAsync(h->d_data, data + indptr[0], sizeof(double) * (size_t)nnz,
+        HB_CREATE_CUDA(cudaMemcpyAsync(h->d_data + phase, data + indptr[0], sizeof(double) * (size_t)nnz,
                                        cudaMemcpyHostToDevice, s));
         if (indices_i64) {
             // krbalancing's constructor takes int64 indices (hicCorrectMatrix.py:744-747): narrow on the device
@@ -147,13 +151,13 @@ int hb_csr_create(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t row0, in
             for (int64_t o = 0; o < nnz; o += chunk) {
                 int64_t m = nnz - o < chunk ? nnz - o : chunk;
                 HB_CREATE_CUDA(cudaMemcpyAsync(d_tmp, src + o, sizeof(int64_t) * (size_t)m, cudaMemcpyHostToDevice, s));
-                hb_narrow_indices_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(d_tmp, h->d_indices + o, m);
+                hb_narrow_indices_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(d_tmp, h->d_indices + phase + o, m);
                 g_hb_launches.fetch_add(1);
             }
             HB_CREATE_CUDA(cudaStreamSynchronize(s));
             cudaFree(d_tmp);
         } else {
-            HB_CREATE_CUDA(cudaMemcpyAsync(h->d_indices, (const int32_t*)indices + indptr[0],
+            HB_CREATE_CUDA(cudaMemcpyAsync(h->d_indices + phase, (const int32_t*)indices + indptr[0],
                                            sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, s));
         }
     }
@@ -221,17 +225,21 @@ int hb_csr_download(hb_csr* h, int64_t* indptr, int32_t* indices, double* data) 
     int rc = hb_use_device(h);
     if (rc) return rc;
     HB_CUDA(cudaStreamSynchronize(h->stream));
-    if (indptr) HB_CUDA(cudaMemcpy(indptr, h->d_indptr, sizeof(int64_t) * (size_t)(h->n_rows + 1), cudaMemcpyDeviceToHost));
-    if (indices && h->nnz) HB_CUDA(cudaMemcpy(indices, h->d_indices, sizeof(int32_t) * (size_t)h->nnz, cudaMemcpyDeviceToHost));
-    if (data && h->nnz) HB_CUDA(cudaMemcpy(data, h->d_data, sizeof(double) * (size_t)h->nnz, cudaMemcpyDeviceToHost));
+    if (indptr) {
+        HB_CUDA(cudaMemcpy(indptr, h->d_indptr, sizeof(int64_t) * (size_t)(h->n_rows + 1), cudaMemcpyDeviceToHost));
+        if (h->phase)
+            for (int64_t i = 0; i <= h->n_rows; ++i) indptr[i] -= h->phase;
+    }
+    if (indices && h->nnz) HB_CUDA(cudaMemcpy(indices, h->d_indices + h->phase, sizeof(int32_t) * (size_t)h->nnz, cudaMemcpyDeviceToHost));
+    if (data && h->nnz) HB_CUDA(cudaMemcpy(data, h->d_data + h->phase, sizeof(double) * (size_t)h->nnz, cudaMemcpyDeviceToHost));
     return HB_OK;
 }
 
 int hb_dev_csr_pointers(hb_csr* h, const int64_t** d_indptr, const int32_t** d_indices, const double** d_data) {
     HB_REQUIRE(h != nullptr, "null handle");
     if (d_indptr) *d_indptr = h->d_indptr;
-    if (d_indices) *d_indices = h->d_indices;
-    if (d_data) *d_data = h->d_data;
+    if (d_indices) *d_indices = h->d_indices + h->phase;  // entry 0 of the block; d_indptr[0] == phase
+    if (d_data) *d_data = h->d_data + h->phase;
     return HB_OK;
 }
 

@@ -393,6 +393,7 @@ static int hb_compact_impl(hb_csr* h, const int32_t* d_newid, int64_t new_n, int
         cudaFree(h->d_data);
     }
     h->owns_csr = true;
+    h->phase = 0;
     h->d_indptr = d_new_indptr;
     h->d_indices = d_new_idx;
     h->d_data = d_new_val;

@@ -227,7 +227,7 @@ hb_ice_scale_bias_kernel(double* __restrict__ bias, const int64_t* __restrict__ 
 __global__ void __launch_bounds__(256)
 hb_ice_emit_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
                    int64_t n_rows, int64_t row0, const double* __restrict__ r, const int64_t* __restrict__ seg_off,
-                   const double* __restrict__ seg_corr, int nseg, double* __restrict__ out,
+                   const double* __restrict__ seg_corr, int nseg, int64_t phase, double* __restrict__ out,
                    unsigned long long* max_bits /* [0] before corr, [1] after */) {
     const int lane = threadIdx.x & 31;
     const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -246,7 +246,7 @@ hb_ice_emit_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict
         for (int64_t k = s + lane; k < e; k += 32) {
             const double w = (hb_ldg_stream_d1(val + k) * ri) * __ldg(r + hb_ldg_stream_i1(idx + k));
             const double f = w * corr * corr;
-            out[k] = f;
+            out[k - phase] = f;
             m0 = fmax(m0, w);
             m1 = fmax(m1, f);
         }
@@ -350,7 +350,7 @@ int hb_dev_ice_emit(hb_csr* h, double* d_out, double* d_max, void* stream) {
     HB_CUDA(cudaMemsetAsync(h->d_scalar_bits, 0, sizeof(unsigned long long) * 2, s));
     if (h->n_rows > 0 && h->nnz > 0) {
         hb_ice_emit_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, h->n_rows, h->row0,
-                                                          h->d_r, h->d_seg_off, h->d_seg_corr, h->nseg, d_out,
+                                                          h->d_r, h->d_seg_off, h->d_seg_corr, h->nseg, h->phase, d_out,
                                                           h->d_scalar_bits);
         HB_LAUNCH_CHECK();
     }

@@ -51,6 +51,9 @@ struct hb_csr {
     cudaStream_t stream = nullptr;
     bool owns_csr = true;
     int64_t n_rows = 0, n_cols = 0, row0 = 0, nnz = 0;
+    // entries are stored from slot `phase` (= global entry offset of the block mod 4) so that the 16-byte alignment
+    // pattern of every row -- and with it the summation order -- is the same however the matrix is sharded
+    int64_t phase = 0;
     int64_t* d_indptr = nullptr;
     int32_t* d_indices = nullptr;
     double* d_data = nullptr;
