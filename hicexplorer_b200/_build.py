@@ -29,8 +29,12 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not _stale():
+def build(force=False, verbose=False, defines=None, out=None):
+    """``defines``/``out``: build a tuning variant (e.g. {"HB_SPMV_MAP": 1}) into another .so."""
+    global LIB
+    if out is not None:
+        LIB = out
+    elif not force and not _stale():
         return LIB
     objs = []
     bdir = os.path.join(PKG, "build")
@@ -40,8 +44,10 @@ def build(force=False, verbose=False):
         path = os.path.join(CSRC, src)
         if not os.path.exists(path):
             continue
-        obj = os.path.join(bdir, src.replace(".cu", ".o"))
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-c", path, "-o", obj]
+        tag = "_" + "_".join("%s%s" % kv for kv in sorted(defines.items())) if defines else ""
+        obj = os.path.join(bdir, src.replace(".cu", tag + ".o"))
+        dflags = ["-D%s=%s" % kv for kv in (defines or {}).items()]
+        cmd = [_nvcc()] + NVCC_FLAGS + dflags + ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-c", path, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     log = []

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libhicbalance.so")
+LIB_PATH = os.environ.get("HICBALANCE_LIB") or os.path.join(_PKG, "libhicbalance.so")  # env: tuning variants
 
 HB_OK = 0
 HB_ERR_NOT_SYMMETRIC = 1

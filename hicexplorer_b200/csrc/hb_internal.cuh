@@ -12,9 +12,18 @@
 #include "hicbalance.h"
 
 #define HB_NUM_SMS 148          // B200: 2 dies x 74 SMs
+#ifndef HB_SPMV_THREADS
 #define HB_SPMV_THREADS 256     // 8 warps per CTA
-#define HB_SPMV_CTAS_PER_SM 4   // 32 resident warps per SM, <= 64 regs/thread
-#define HB_ROWS_PER_GRAB 4      // rows a warp claims per atomic on the row counter
+#endif
+#ifndef HB_SPMV_CTAS_PER_SM
+#define HB_SPMV_CTAS_PER_SM 3   // 24 resident warps per SM, <= 80 regs/thread (deep unroll beats occupancy here)
+#endif
+#ifndef HB_ROWS_PER_GRAB
+#define HB_ROWS_PER_GRAB 1      // rows a warp claims per atomic on the row counter
+#endif
+#ifndef HB_SPMV_UNROLL
+#define HB_SPMV_UNROLL 16       // independent entries per lane per step of the row dot product
+#endif
 #define HB_TILE_ROWS 1024       // fixed reduction tile (rows) -> rank-count independent sums
 #define HB_MAX_SEG 4096
 
@@ -113,14 +122,26 @@ __device__ __forceinline__ double2 hb_ldg_stream_d2(const double* p) {
     asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
     return r;
 }
+#ifndef HB_STREAM_HINT
+#define HB_STREAM_HINT 0
+#endif
+#if HB_STREAM_HINT == 1
+#define HB_STREAM_QUAL "ld.global.nc.L1::no_allocate.L2::128B"
+#elif HB_STREAM_HINT == 2
+#define HB_STREAM_QUAL "ld.global.nc.L1::no_allocate.L2::256B"
+#elif HB_STREAM_HINT == 3
+#define HB_STREAM_QUAL "ld.global.nc.L1::no_allocate.L2::evict_first"
+#else
+#define HB_STREAM_QUAL "ld.global.nc.L1::no_allocate"
+#endif
 __device__ __forceinline__ int hb_ldg_stream_i1(const int32_t* p) {
     int r;
-    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+    asm volatile(HB_STREAM_QUAL ".s32 %0, [%1];" : "=r"(r) : "l"(p));
     return r;
 }
 __device__ __forceinline__ double hb_ldg_stream_d1(const double* p) {
     double r;
-    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+    asm volatile(HB_STREAM_QUAL ".f64 %0, [%1];" : "=d"(r) : "l"(p));
     return r;
 }
 __device__ __forceinline__ double hb_warp_sum(double v) {

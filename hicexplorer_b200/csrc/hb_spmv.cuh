@@ -6,77 +6,67 @@
 // value, each read exactly once) + ~24 B per row.  The gathered vector u (n*8 B: 1-25 MB) stays
 // in L2/L1; the matrix streams through with L1::no_allocate so it does not evict u.
 //
-// Mapping: persistent grid (148 SMs x 4 CTAs x 8 warps); a warp owns a row, lanes read the row
-// with 128-bit loads (4 column ids / 2 values per load, 8 entries per lane in flight per step),
-// partial sums are combined with __shfl_xor.  Rows are claimed HB_ROWS_PER_GRAB at a time from a
-// global counter, the next claim being issued before the current rows are processed, so long and
-// short rows (Hi-C rows range from a handful to tens of thousands of entries) balance out.
+// Mapping: persistent grid (148 SMs x 3 CTAs x 8 warps, 80 registers/thread); a warp owns a row,
+// lanes read it lane-strided (coalesced 128 B / 256 B per instruction, 16 entries per lane in
+// flight per step), partial sums are combined with __shfl_xor.  Rows are claimed from a global
+// counter, the next claim being issued before the current row is processed, so long and short
+// rows (Hi-C rows range from a handful to tens of thousands of entries) balance out.
+// The constants were chosen by the sweep recorded in profiles/r1_spmv_variant_sweep.txt.
 #pragma once
 #include "hb_internal.cuh"
 
+// Row dot product, lane-strided: lane L takes entries s+L, s+L+32, ...  Every load instruction of the warp covers
+// one contiguous run (128 B of column ids, 256 B of values) and -- the point -- so does every GATHER when the row
+// has a run of consecutive columns (the near-diagonal band of a Hi-C row): 2 cache lines per gather instruction.
+// The 4-entries-per-lane mapping with 128-bit loads needs fewer instructions but spreads each gather over 8 lines
+// and ran the L1TEX pipe at 91 % (profiles/README.md): 2.93 ms vs 2.59 ms per launch on config 3.
+// HB_SPMV_UNROLL independent entries per lane are in flight per step (3 x 16 loads); the tail runs in
+// predicated groups of 4 so short rows still overlap their loads.  There is no alignment requirement,
+// so the summation order does not depend on where a row starts.
 template <bool WANT_MAX>
 __device__ __forceinline__ void hb_row_dot(const int32_t* __restrict__ idx, const double* __restrict__ val,
                                            const double* __restrict__ u, int64_t s, int64_t e, int lane,
                                            double& sum_out, double& max_out) {
+    constexpr int U = HB_SPMV_UNROLL;
     double acc0 = 0.0, acc1 = 0.0;
     double mx = -INFINITY;
-    // head: up to 3 entries until the entry index is a multiple of 4 (=> 16-byte aligned ids and values)
-    int64_t a = (s + 3) & ~(int64_t)3;
-    if (a > e) a = e;
-    {
-        int64_t k = s + lane;
-        if (k < a) {
-            double p = hb_ldg_stream_d1(val + k) * __ldg(u + hb_ldg_stream_i1(idx + k));
-            acc0 = p;
-            if (WANT_MAX) mx = p;
+    int64_t k = s + lane;
+    for (; k + 32 * (U - 1) < e; k += 32 * U) {
+        int c[U];
+        double v[U], g[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) c[j] = hb_ldg_stream_i1(idx + k + 32 * j);
+#pragma unroll
+        for (int j = 0; j < U; ++j) v[j] = hb_ldg_stream_d1(val + k + 32 * j);
+#pragma unroll
+        for (int j = 0; j < U; ++j) g[j] = __ldg(u + c[j]);
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            if (WANT_MAX) {
+                const double p = v[j] * g[j];
+                if (j & 1) acc1 += p; else acc0 += p;
+                mx = fmax(mx, p);
+            } else {
+                if (j & 1) acc1 = fma(v[j], g[j], acc1); else acc0 = fma(v[j], g[j], acc0);
+            }
         }
     }
-    const int64_t ng = (e - a) >> 2;
-    const int32_t* idx_a = idx + a;
-    const double* val_a = val + a;
-    int64_t g = lane;
-    for (; g + 32 < ng; g += 64) {
-        const int4 c0 = hb_ldg_stream_i4(idx_a + 4 * g);
-        const int4 c1 = hb_ldg_stream_i4(idx_a + 4 * (g + 32));
-        const double2 v00 = hb_ldg_stream_d2(val_a + 4 * g);
-        const double2 v01 = hb_ldg_stream_d2(val_a + 4 * g + 2);
-        const double2 v10 = hb_ldg_stream_d2(val_a + 4 * (g + 32));
-        const double2 v11 = hb_ldg_stream_d2(val_a + 4 * (g + 32) + 2);
-        const double u0 = __ldg(u + c0.x), u1 = __ldg(u + c0.y), u2 = __ldg(u + c0.z), u3 = __ldg(u + c0.w);
-        const double u4 = __ldg(u + c1.x), u5 = __ldg(u + c1.y), u6 = __ldg(u + c1.z), u7 = __ldg(u + c1.w);
-        if (WANT_MAX) {
-            const double p0 = v00.x * u0, p1 = v00.y * u1, p2 = v01.x * u2, p3 = v01.y * u3;
-            const double p4 = v10.x * u4, p5 = v10.y * u5, p6 = v11.x * u6, p7 = v11.y * u7;
-            acc0 += p0; acc0 += p1; acc0 += p2; acc0 += p3;
-            acc1 += p4; acc1 += p5; acc1 += p6; acc1 += p7;
-            mx = fmax(mx, fmax(fmax(fmax(p0, p1), fmax(p2, p3)), fmax(fmax(p4, p5), fmax(p6, p7))));
-        } else {
-            acc0 = fma(v00.x, u0, acc0); acc0 = fma(v00.y, u1, acc0);
-            acc0 = fma(v01.x, u2, acc0); acc0 = fma(v01.y, u3, acc0);
-            acc1 = fma(v10.x, u4, acc1); acc1 = fma(v10.y, u5, acc1);
-            acc1 = fma(v11.x, u6, acc1); acc1 = fma(v11.y, u7, acc1);
-        }
-    }
-    if (g < ng) {
-        const int4 c0 = hb_ldg_stream_i4(idx_a + 4 * g);
-        const double2 v00 = hb_ldg_stream_d2(val_a + 4 * g);
-        const double2 v01 = hb_ldg_stream_d2(val_a + 4 * g + 2);
-        const double u0 = __ldg(u + c0.x), u1 = __ldg(u + c0.y), u2 = __ldg(u + c0.z), u3 = __ldg(u + c0.w);
-        if (WANT_MAX) {
-            const double p0 = v00.x * u0, p1 = v00.y * u1, p2 = v01.x * u2, p3 = v01.y * u3;
-            acc0 += p0; acc0 += p1; acc0 += p2; acc0 += p3;
-            mx = fmax(mx, fmax(fmax(p0, p1), fmax(p2, p3)));
-        } else {
-            acc0 = fma(v00.x, u0, acc0); acc0 = fma(v00.y, u1, acc0);
-            acc0 = fma(v01.x, u2, acc0); acc0 = fma(v01.y, u3, acc0);
-        }
-    }
-    {
-        int64_t k = a + 4 * ng + lane;
-        if (k < e) {
-            double p = hb_ldg_stream_d1(val + k) * __ldg(u + hb_ldg_stream_i1(idx + k));
-            acc1 += p;
-            if (WANT_MAX) mx = fmax(mx, p);
+    for (; k < e; k += 32 * 4) {  // tail (< 32*U entries left): predicated groups of 4 keep loads overlapped
+        int c[4];
+        double v[4], g[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) c[j] = (k + 32 * j < e) ? hb_ldg_stream_i1(idx + k + 32 * j) : 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = (k + 32 * j < e) ? hb_ldg_stream_d1(val + k + 32 * j) : 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) g[j] = (k + 32 * j < e) ? __ldg(u + c[j]) : 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (k + 32 * j < e) {
+                const double p = v[j] * g[j];
+                if (j & 1) acc1 += p; else acc0 += p;
+                if (WANT_MAX) mx = fmax(mx, p);
+            }
         }
     }
     sum_out = hb_warp_sum(acc0 + acc1);
