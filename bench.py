@@ -423,6 +423,13 @@ def main():
             dist.destroy_process_group()
         return
     peak, peak_src = measured_peak()
+    traffic = None
+    try:   # DRAM bytes per launch of the same kernel on the same workload, from the committed ncu capture
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(args.workload)
+        if tr and tr["nnz"] == nnz_total and world == 1:
+            traffic = float(tr["dram_bytes_read"] + tr["dram_bytes_write"])
+    except Exception:
+        pass
     bytes_spmv = 12.0 * nnz_total + 24.0 * n
     achieved = bytes_spmv / world / (spmv_ms * 1e-3) / 1e9   # per GPU: each rank streams its own share
     line = {
@@ -436,7 +443,7 @@ def main():
                    "generated_in_s": round(t_gen, 2)},
         "time_to_converge": {"ms": converge_ms, "iterations": conv_iters, "converged": converged, "tolerance": 1e-5},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "hb_spmv_kernel<HbIceEpi,true>", "peak_source": peak_src,
+                     "traffic": traffic, "kernel": "hb_spmv_kernel<HbIceEpi,true>", "peak_source": peak_src,
                      "bytes_per_launch": bytes_spmv / world, "avg_launch_ms": spmv_ms,
                      "frac_of_nominal_8TBps": achieved / 8000.0},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
