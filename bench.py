@@ -412,6 +412,7 @@ def main():
             e2e = {"value": None, "unit": "nnz/s", "error": repr(exc)}
     if dev is not None:
         dev.close()
+    ip_h = ix_h = da_h = None   # release the pinned copies before the next leg
 
     # ---- KR (configs[1]) at N = 1 ------------------------------------------------------------------------------
     kr = None

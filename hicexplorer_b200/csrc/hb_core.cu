@@ -201,11 +201,7 @@ int hb_csr_destroy(hb_csr* h) {
         cudaFree(h->d_indices);
         cudaFree(h->d_data);
     }
-    cudaFree(h->d_seg_off);
-    cudaFree(h->d_tile_row0);
-    cudaFree(h->d_tile_len);
-    cudaFree(h->d_tile_seg);
-    cudaFree(h->d_seg_tile0);
+    cudaFree(h->d_tile_slab);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return HB_OK;
@@ -280,7 +276,10 @@ int hb_set_segments(hb_csr* h, int nseg, const int64_t* seg_offsets) {
 
 // Fixed reduction tiles: HB_TILE_ROWS consecutive GLOBAL rows, never crossing a segment boundary.
 // Sums over rows are always formed tile by tile in this order, so the result does not depend on
-// how many GPUs share the matrix.
+// how many GPUs share the matrix.  All tile/segment tables live in ONE device slab (allocation count
+// matters: --perchr creates and destroys a handle per chromosome).
+static inline size_t hb_align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
 int hb_build_tiles(hb_csr* h) {
     int rc = hb_use_device(h);
     if (rc) return rc;
@@ -297,49 +296,43 @@ int hb_build_tiles(hb_csr* h) {
     }
     seg_tile0[h->nseg] = (int32_t)row0.size();
     h->n_tiles = (int)row0.size();
-    cudaFree(h->d_seg_off);
-    cudaFree(h->d_tile_row0);
-    cudaFree(h->d_tile_len);
-    cudaFree(h->d_tile_seg);
-    cudaFree(h->d_seg_tile0);
-    h->d_seg_off = nullptr;
-    h->d_tile_row0 = nullptr;
-    h->d_tile_len = nullptr;
-    h->d_tile_seg = nullptr;
-    h->d_seg_tile0 = nullptr;
-    size_t nt = h->n_tiles > 0 ? (size_t)h->n_tiles : 1;
-    HB_CUDA(cudaMalloc(&h->d_seg_off, sizeof(int64_t) * (h->nseg + 1)));
-    HB_CUDA(cudaMalloc(&h->d_tile_row0, sizeof(int64_t) * nt));
-    HB_CUDA(cudaMalloc(&h->d_tile_len, sizeof(int32_t) * nt));
-    HB_CUDA(cudaMalloc(&h->d_tile_seg, sizeof(int32_t) * nt));
-    HB_CUDA(cudaMalloc(&h->d_seg_tile0, sizeof(int32_t) * (h->nseg + 1)));
-    HB_CUDA(cudaMemcpy(h->d_seg_off, h->seg_off.data(), sizeof(int64_t) * (h->nseg + 1), cudaMemcpyHostToDevice));
+    cudaFree(h->d_tile_slab);
+    h->d_tile_slab = nullptr;
+    const size_t nt = h->n_tiles > 0 ? (size_t)h->n_tiles : 1, ns1 = (size_t)h->nseg + 1;
+    const size_t o_seg = 0;
+    const size_t o_row0 = o_seg + hb_align256(sizeof(int64_t) * ns1);
+    const size_t o_len = o_row0 + hb_align256(sizeof(int64_t) * nt);
+    const size_t o_tseg = o_len + hb_align256(sizeof(int32_t) * nt);
+    const size_t o_st0 = o_tseg + hb_align256(sizeof(int32_t) * nt);
+    const size_t total = o_st0 + hb_align256(sizeof(int32_t) * ns1);
+    std::vector<unsigned char> host(total, 0);
+    memcpy(host.data() + o_seg, h->seg_off.data(), sizeof(int64_t) * ns1);
     if (h->n_tiles) {
-        HB_CUDA(cudaMemcpy(h->d_tile_row0, row0.data(), sizeof(int64_t) * nt, cudaMemcpyHostToDevice));
-        HB_CUDA(cudaMemcpy(h->d_tile_len, len.data(), sizeof(int32_t) * nt, cudaMemcpyHostToDevice));
-        HB_CUDA(cudaMemcpy(h->d_tile_seg, seg.data(), sizeof(int32_t) * nt, cudaMemcpyHostToDevice));
+        memcpy(host.data() + o_row0, row0.data(), sizeof(int64_t) * nt);
+        memcpy(host.data() + o_len, len.data(), sizeof(int32_t) * nt);
+        memcpy(host.data() + o_tseg, seg.data(), sizeof(int32_t) * nt);
     }
-    HB_CUDA(cudaMemcpy(h->d_seg_tile0, seg_tile0.data(), sizeof(int32_t) * (h->nseg + 1), cudaMemcpyHostToDevice));
+    memcpy(host.data() + o_st0, seg_tile0.data(), sizeof(int32_t) * ns1);
+    HB_CUDA(cudaMalloc(&h->d_tile_slab, total));
+    HB_CUDA(cudaMemcpy(h->d_tile_slab, host.data(), total, cudaMemcpyHostToDevice));
+    unsigned char* base = (unsigned char*)h->d_tile_slab;
+    h->d_seg_off = (int64_t*)(base + o_seg);
+    h->d_tile_row0 = (int64_t*)(base + o_row0);
+    h->d_tile_len = (int32_t*)(base + o_len);
+    h->d_tile_seg = (int32_t*)(base + o_tseg);
+    h->d_seg_tile0 = (int32_t*)(base + o_st0);
     return HB_OK;
 }
 
 void hb_free_state(hb_csr* h) {
-    cudaFree(h->d_bias);
-    cudaFree(h->d_r);
-    cudaFree(h->d_exch);
-    cudaFree(h->d_tile_sum);
-    cudaFree(h->d_tile_cnt);
-    cudaFree(h->d_seg_mean);
-    cudaFree(h->d_seg_corr);
-    cudaFree(h->d_seg_devbits);
-    cudaFree(h->d_seg_dev);
-    cudaFree(h->d_seg_done);
-    cudaFree(h->d_seg_iters);
-    cudaFree(h->d_status);
-    cudaFree(h->d_counters);
-    cudaFree(h->d_row_counter);
-    cudaFree(h->d_scalar_bits);
-    if (h->h_status) cudaFreeHost(h->h_status);
+    cudaFree(h->d_state_slab);
+    if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    cudaFree(h->d_kr_buf);
+    h->d_state_slab = nullptr;
+    h->h_pinned = nullptr;
+    h->d_kr_buf = nullptr;
+    h->kr_buf_words = 0;
+    h->h_kr_sc = nullptr;
     h->d_bias = h->d_r = h->d_exch = h->d_tile_sum = h->d_tile_cnt = h->d_seg_mean = h->d_seg_corr = h->d_seg_dev = nullptr;
     h->d_seg_devbits = nullptr;
     h->d_seg_done = h->d_seg_iters = h->d_status = nullptr;
@@ -350,32 +343,48 @@ void hb_free_state(hb_csr* h) {
     h->state_ready = false;
 }
 
+// replicated vectors + per-segment scalars: one device slab, one pinned block
 int hb_ensure_state(hb_csr* h) {
     if (h->state_ready) return HB_OK;
     int rc = hb_use_device(h);
     if (rc) return rc;
-    size_t n = (size_t)(h->n_cols > 0 ? h->n_cols : 1);
-    size_t nt = (size_t)(h->n_tiles > 0 ? h->n_tiles : 1);
-    size_t ns = (size_t)h->nseg;
-    HB_CUDA(cudaMalloc(&h->d_bias, sizeof(double) * n));
-    HB_CUDA(cudaMalloc(&h->d_r, sizeof(double) * n));
-    HB_CUDA(cudaMalloc(&h->d_exch, sizeof(double) * (n + 64)));
-    HB_CUDA(cudaMalloc(&h->d_tile_sum, sizeof(double) * nt));
-    HB_CUDA(cudaMalloc(&h->d_tile_cnt, sizeof(double) * nt));
-    HB_CUDA(cudaMalloc(&h->d_seg_mean, sizeof(double) * ns));
-    HB_CUDA(cudaMalloc(&h->d_seg_corr, sizeof(double) * ns));
-    HB_CUDA(cudaMalloc(&h->d_seg_devbits, sizeof(unsigned long long) * ns));
-    HB_CUDA(cudaMalloc(&h->d_seg_dev, sizeof(double) * ns));
-    HB_CUDA(cudaMalloc(&h->d_seg_done, sizeof(int32_t) * ns));
-    HB_CUDA(cudaMalloc(&h->d_seg_iters, sizeof(int32_t) * ns));
-    HB_CUDA(cudaMalloc(&h->d_status, sizeof(int32_t) * HB_ST_WORDS));
-    HB_CUDA(cudaMalloc(&h->d_counters, sizeof(unsigned int) * 8));
-    HB_CUDA(cudaMalloc(&h->d_row_counter, sizeof(unsigned long long) * 2));
-    HB_CUDA(cudaMalloc(&h->d_scalar_bits, sizeof(unsigned long long) * 8));
-    HB_CUDA(cudaHostAlloc((void**)&h->h_status, sizeof(int32_t) * HB_ST_WORDS * 16, cudaHostAllocDefault));
-    HB_CUDA(cudaMemset(h->d_counters, 0, sizeof(unsigned int) * 8));
-    HB_CUDA(cudaMemset(h->d_row_counter, 0, sizeof(unsigned long long) * 2));
-    HB_CUDA(cudaMemset(h->d_scalar_bits, 0, sizeof(unsigned long long) * 8));
+    const size_t n = (size_t)(h->n_cols > 0 ? h->n_cols : 1);
+    const size_t nt = (size_t)(h->n_tiles > 0 ? h->n_tiles : 1);
+    const size_t ns = (size_t)h->nseg;
+    size_t off = 0;
+    auto take = [&off](size_t bytes) {
+        size_t o = off;
+        off += hb_align256(bytes);
+        return o;
+    };
+    const size_t o_bias = take(sizeof(double) * n), o_r = take(sizeof(double) * n), o_exch = take(sizeof(double) * (n + 64));
+    const size_t o_tsum = take(sizeof(double) * nt), o_tcnt = take(sizeof(double) * nt);
+    const size_t o_mean = take(sizeof(double) * ns), o_corr = take(sizeof(double) * ns), o_dev = take(sizeof(double) * ns);
+    const size_t o_devb = take(sizeof(unsigned long long) * ns);
+    const size_t o_done = take(sizeof(int32_t) * ns), o_iters = take(sizeof(int32_t) * ns);
+    const size_t o_small = take(256);  // status (16 B) | counters (32 B) | row counters (16 B) | scalar bits (64 B)
+    const size_t total = off;
+    HB_CUDA(cudaMalloc(&h->d_state_slab, total));
+    unsigned char* b = (unsigned char*)h->d_state_slab;
+    h->d_bias = (double*)(b + o_bias);
+    h->d_r = (double*)(b + o_r);
+    h->d_exch = (double*)(b + o_exch);
+    h->d_tile_sum = (double*)(b + o_tsum);
+    h->d_tile_cnt = (double*)(b + o_tcnt);
+    h->d_seg_mean = (double*)(b + o_mean);
+    h->d_seg_corr = (double*)(b + o_corr);
+    h->d_seg_dev = (double*)(b + o_dev);
+    h->d_seg_devbits = (unsigned long long*)(b + o_devb);
+    h->d_seg_done = (int32_t*)(b + o_done);
+    h->d_seg_iters = (int32_t*)(b + o_iters);
+    h->d_status = (int32_t*)(b + o_small);
+    h->d_counters = (unsigned int*)(b + o_small + 32);
+    h->d_row_counter = (unsigned long long*)(b + o_small + 64);
+    h->d_scalar_bits = (unsigned long long*)(b + o_small + 128);
+    HB_CUDA(cudaMemset(b + o_small, 0, 256));
+    HB_CUDA(cudaHostAlloc(&h->h_pinned, 1024, cudaHostAllocDefault));
+    h->h_status = (int32_t*)h->h_pinned;                              // 16 slots x HB_ST_WORDS x 4 B = 256 B
+    h->h_kr_sc = (double*)((unsigned char*)h->h_pinned + 512);       // 16 doubles
     h->state_ready = true;
     return HB_OK;
 }

@@ -75,6 +75,7 @@ struct hb_csr {
     // segments (independent diagonal blocks) and fixed reduction tiles over GLOBAL rows
     int nseg = 1;
     std::vector<int64_t> seg_off;      // nseg+1
+    void* d_tile_slab = nullptr;       // one allocation holding the five tables below
     int64_t* d_seg_off = nullptr;      // nseg+1
     int n_tiles = 0;
     int64_t* d_tile_row0 = nullptr;    // n_tiles
@@ -84,6 +85,8 @@ struct hb_csr {
 
     // replicated n_cols-vectors and per-segment scalars (lazily allocated)
     bool state_ready = false;
+    void* d_state_slab = nullptr;      // one allocation holding every device pointer below
+    void* h_pinned = nullptr;          // one pinned block: h_status | h_kr_sc
     double* d_bias = nullptr;          // n_cols
     double* d_r = nullptr;             // n_cols
     double* d_exch = nullptr;          // n_cols + 64 (single-GPU exchange buffer)
@@ -101,6 +104,9 @@ struct hb_csr {
     int spmv_parity = 0;
     unsigned long long* d_scalar_bits = nullptr; // 8 scratch words
     int32_t* h_status = nullptr;       // pinned, 16 slots x HB_ST_WORDS
+    double* d_kr_buf = nullptr;        // Knight-Ruiz workspace (8 n-vectors + tile partials + scalars), kept across calls
+    size_t kr_buf_words = 0;
+    double* h_kr_sc = nullptr;         // pinned mirror of the KR scalars
 };
 
 int hb_build_tiles(hb_csr* h);

@@ -492,13 +492,18 @@ int hb_kr_run(hb_csr* h, double tol, double delta, double Delta, double diag_eps
     int outer = 0, mvp = 0;
     bool breakdown = false;
     {
-        cudaError_t e = cudaMalloc(&c.buf, sizeof(double) * (size_t)(8 * n + 3 * h->n_tiles + SC_WORDS));
-        if (e != cudaSuccess) return hb_cuda_fail(e, "cudaMalloc KR vectors", __FILE__, __LINE__);
-        e = cudaHostAlloc((void**)&c.h_sc, sizeof(double) * SC_WORDS, cudaHostAllocDefault);
-        if (e != cudaSuccess) {
-            cudaFree(c.buf);
-            return hb_cuda_fail(e, "cudaHostAlloc", __FILE__, __LINE__);
+        // the workspace lives in the handle: repeated calls (and --perchr loops) pay no allocation
+        const size_t words = (size_t)(8 * n + 3 * h->n_tiles + SC_WORDS);
+        if (h->kr_buf_words < words) {
+            cudaFree(h->d_kr_buf);
+            h->d_kr_buf = nullptr;
+            h->kr_buf_words = 0;
+            cudaError_t e = cudaMalloc(&h->d_kr_buf, sizeof(double) * words);
+            if (e != cudaSuccess) return hb_cuda_fail(e, "cudaMalloc KR vectors", __FILE__, __LINE__);
+            h->kr_buf_words = words;
         }
+        c.buf = h->d_kr_buf;
+        c.h_sc = h->h_kr_sc;
     }
     {
         double* b = c.buf;
@@ -641,8 +646,6 @@ int hb_kr_run(hb_csr* h, double tol, double delta, double Delta, double diag_eps
     }
 done:
     cudaStreamSynchronize(c.s);
-    cudaFree(c.buf);
-    if (c.h_sc) cudaFreeHost(c.h_sc);
     return rc;
 }
 

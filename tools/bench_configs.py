@@ -1,0 +1,184 @@
+#!/usr/bin/env python
+"""Measurements for the BASELINE.json configs that are not bench.py's headline line:
+
+  perchr5k   configs[3]: --perchr ICE + KR on a synthetic 5 kb human matrix: 24 independent chromosome blocks,
+             ICE batched as segments of ONE device matrix per rank (one launch covers all its chromosomes),
+             KR chromosome by chromosome; chromosomes are dealt to the ranks by LPT on stored entries,
+             no inter-GPU communication.
+  kr1k       configs[4]: KR on a synthetic genome-wide 1 kb matrix (~3.1 M bins, ~8e9 entries = 96 GB of CSR),
+             nnz-balanced row blocks over the ranks, one sum-allreduce of n fp64 per mat-vec.  Needs 8 GPUs.
+  kr25k_sharded / ice10k_conv   the single-GPU configs run sharded (for N = 2, 4 checks).
+
+Run: python tools/bench_configs.py CONFIG            (1 GPU)
+     python -m torch.distributed.run --nproc-per-node N ... tools/bench_configs.py CONFIG
+Prints one JSON line per config on rank 0."""
+import ctypes
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+bench.WORKLOADS.update({
+    "perchr5k": ("ICE+KR", 5000, 2.0e9, 16000),
+    "kr1k": ("KR", 1000, 8.0e9, 8000),
+})
+
+
+def lpt(weights, world):
+    """longest-processing-time assignment of chromosomes to ranks"""
+    loads = [0.0] * world
+    owner = [0] * len(weights)
+    for c in sorted(range(len(weights)), key=lambda i: -weights[i]):
+        r = int(np.argmin(loads))
+        owner[c] = r
+        loads[r] += weights[c]
+    return owner
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from hicexplorer_b200 import _lib
+    from hicexplorer_b200.dist import attach_comm, nnz_balanced_partition
+    from hicexplorer_b200.store import DeviceCSR
+    L = _lib.lib()
+    check = _lib.check
+    config = sys.argv[1] if len(sys.argv) > 1 else "perchr5k"
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allsum(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t)
+        return float(t.item())
+
+    def allmax(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    peak, peak_src = bench.measured_peak()
+    out = {"config": config, "n_gpus": world, "peak_GBps": peak, "peak_source": peak_src}
+
+    if config == "perchr5k":
+        method, bins, kw = bench.synth_kwargs("perchr5k", clean=True)
+        kw = dict(kw, n_trans=0)                    # cis only: block diagonal by construction
+        weights = [bench.expected_nnz([b], kw["band"], kw["d0"]) for b in bins]
+        owner = lpt(weights, world)
+        mine = [c for c in range(len(bins)) if owner[c] == rank]
+        my_bins = [bins[c] for c in mine]
+        dev = DeviceCSR.synthetic(my_bins, device=local, **kw)
+        offs = np.concatenate([[0], np.cumsum(my_bins)]).astype(np.int64)
+        dev.set_segments(offs)
+        n_local, nnz_local = dev.n, dev.nnz
+        h = dev.handle
+        steps = 50
+        check(L.hb_dev_ice_begin(h, None))
+        for _ in range(5):
+            check(L.hb_dev_ice_spmv(h, None, 0, 1, None))
+            check(L.hb_dev_ice_update(h, None, 1, 0.0, None))
+        barrier()
+        t0 = time.time()
+        for _ in range(steps):
+            check(L.hb_dev_ice_spmv(h, None, 0, 1, None))
+            check(L.hb_dev_ice_update(h, None, 1, 0.0, None))
+        dev.sync()
+        t_loop = allmax(time.time() - t0)
+        barrier()
+        t0 = time.time()
+        bias, iters, devn = dev.ice(500, 1e-5)
+        t_conv = allmax(time.time() - t0)
+        nnz_total = allsum(nnz_local)
+        conv_all = allsum(float(np.all(devn < 1e-5))) == world
+        dev.close()
+        # KR, chromosome by chromosome
+        barrier()
+        t0 = time.time()
+        mv_local = 0
+        work = 0.0
+        for c in mine:
+            with DeviceCSR.synthetic([bins[c]], device=local, **kw) as d1:
+                x, outer, mv, res = d1.kr()
+                mv_local += mv
+                work += float(d1.nnz) * mv
+        torch.cuda.synchronize()
+        t_kr = allmax(time.time() - t0)
+        out.update({
+            "workload": "perchr: synthetic 5 kb human, %d chromosome blocks, %d bins, %.3g stored entries (cis only)"
+                        % (len(bins), sum(bins), nnz_total),
+            "ice": {"ms_per_iteration_all_chromosomes": t_loop / steps * 1e3, "nnz_per_s": nnz_total * steps / t_loop,
+                    "GBps_per_gpu": 12.0 * nnz_total * steps / t_loop / world / 1e9,
+                    "frac_of_peak": 12.0 * nnz_total * steps / t_loop / world / 1e9 / peak,
+                    "time_to_converge_ms": t_conv * 1e3, "iterations_min_max": [int(-allmax(-float(iters.min()))), int(allmax(float(iters.max())))],
+                    "all_converged": bool(conv_all)},
+            "kr": {"time_all_chromosomes_ms": t_kr * 1e3, "matvec_entries_per_s": allsum(work) / t_kr,
+                   "includes": "generation of each chromosome block + KR to tol 1e-6"},
+            "communication": "none (independent chromosomes; LPT assignment)"})
+    else:
+        wl = {"kr1k": "kr1k", "kr25k_sharded": "kr25k", "ice10k_conv": "ice10k"}[config]
+        method, bins, kw = bench.synth_kwargs(wl, clean=(wl == "ice10k"))
+        n = int(sum(bins))
+        t0 = time.time()
+        if world == 1:
+            dev = DeviceCSR.synthetic(bins, device=local, **kw)
+        else:
+            eq = np.linspace(0, n, world + 1).astype(np.int64)
+            with DeviceCSR.synthetic(bins, row_range=(int(eq[rank]), int(eq[rank + 1])), device=local, **kw) as tmp:
+                ip = np.empty(tmp.n_rows + 1, dtype=np.int64)
+                check(L.hb_csr_download(tmp.handle, _lib.ptr(ip), None, None))
+            counts = torch.zeros(n, dtype=torch.int64, device="cuda")
+            counts[int(eq[rank]):int(eq[rank + 1])] = torch.from_numpy(np.diff(ip)).cuda()
+            dist.all_reduce(counts)
+            bounds = nnz_balanced_partition(np.concatenate([[0], np.cumsum(counts.cpu().numpy())]), world)
+            del counts
+            dev = DeviceCSR.synthetic(bins, row_range=(int(bounds[rank]), int(bounds[rank + 1])), device=local, **kw)
+        keep = attach_comm(dev, rank, world) if world > 1 else None
+        torch.cuda.synchronize()
+        t_gen = time.time() - t0
+        nnz_total = allsum(dev.nnz)
+        barrier()
+        t0 = time.time()
+        if method == "KR":
+            x, outer, mv, res = dev.kr()
+            t_run = allmax(time.time() - t0)
+            out.update({"kr": {"time_to_converge_ms": t_run * 1e3, "outer": outer, "matvecs": mv, "residual": res,
+                               "ms_per_matvec_incl_vector_ops_and_allreduce": t_run * 1e3 / (mv + 1),
+                               "nnz_per_s": nnz_total * (mv + 1) / t_run,
+                               "GBps_per_gpu": (12.0 * nnz_total + 120.0 * n) * (mv + 1) / t_run / world / 1e9,
+                               "frac_of_peak": (12.0 * nnz_total + 120.0 * n) * (mv + 1) / t_run / world / 1e9 / peak,
+                               "x_min_max": [float(x.min()), float(x.max())]}})
+        else:
+            bias, iters, devn = dev.ice(500, 1e-5)
+            t_run = allmax(time.time() - t0)
+            out.update({"ice": {"time_to_converge_ms": t_run * 1e3, "iterations": int(iters[0]), "deviation": float(devn[0]),
+                                "ms_per_iteration": t_run * 1e3 / max(int(iters[0]), 1),
+                                "nnz_per_s": nnz_total * int(iters[0]) / t_run}})
+        out.update({"workload": bench.workload_name(wl, bins, kw), "bins": n, "nnz": nnz_total, "generated_in_s": t_gen,
+                    "communication": "1 sum-allreduce of %d fp64 per mat-vec/iteration" % n if world > 1 else "none"})
+        dev.close()
+        del keep
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
