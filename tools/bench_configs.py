@@ -108,7 +108,9 @@ def main():
         nnz_total = allsum(nnz_local)
         conv_all = allsum(float(np.all(devn < 1e-5))) == world
         dev.close()
-        # KR, chromosome by chromosome
+        # KR, chromosome by chromosome (one tiny warm-up run first: CUDA loads kernels lazily)
+        with DeviceCSR.synthetic([2000], device=local, **kw) as d0:
+            d0.kr()
         barrier()
         t0 = time.time()
         mv_local = 0
