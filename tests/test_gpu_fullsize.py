@@ -1,0 +1,111 @@
+"""Size-independent properties checked at BASELINE.json's sizes, where the CPU oracle would take minutes to hours:
+the synthetic 25 kb matrix of configs[1] (~3e8 stored entries) and the 10 kb matrix of configs[2] (~1.5e9).
+
+  * the generator is exactly symmetric,
+  * ICE converges and the corrected matrix is balanced: every non-empty row sums to the common mean (Imakaev's
+    defining property; what `deviation < tolerance` certifies, iterativeCorrection.py:47,72),
+  * idempotence: correcting the corrected matrix converges immediately with a flat bias,
+  * KR: x o ((A + 1e-5 I) x) = 1 to the KR tolerance, x > 0,
+  * the MAD filter finds the planted low-coverage bins and the zero-bin mask the planted empty bins."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import bench
+from hicexplorer_b200 import _lib
+from hicexplorer_b200.store import DeviceCSR
+
+pytestmark = pytest.mark.gpu
+
+
+def _row_sums_of_scaled(dev, scale):
+    """r_i * sum_j A_ij r_j for r = scale, through the same SpMV kernel (hb_dev_spmv)."""
+    import torch
+    n = dev.n
+    r = torch.from_numpy(np.ascontiguousarray(scale)).cuda()
+    out = torch.zeros(n, dtype=torch.float64, device="cuda")
+    P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    _lib.check(_lib.lib().hb_dev_spmv(dev.handle, P(r), 0.0, P(r), None, None, P(out), 0, None))
+    dev.sync()
+    return out.cpu().numpy()
+
+
+@pytest.mark.parametrize("workload", ["ice25k", "ice10k"])
+def test_ice_balances_the_matrix_at_full_size(workload):
+    method, bins, kw = bench.synth_kwargs(workload, clean=True)
+    with DeviceCSR.synthetic(bins, **kw) as dev:
+        assert dev.nnz > 0.95 * bench.WORKLOADS[workload][2]
+        assert dev.symmetry_ratio() == 0.0                       # generator: exactly symmetric
+        bias, iters, devn = dev.ice(500, 1e-5)
+        assert devn[0] < 1e-5 and 10 < int(iters[0]) < 500       # converged
+        assert np.all(bias > 0) and abs(bias.mean() - 1.0) < 1e-12
+        rows = _row_sums_of_scaled(dev, 1.0 / bias)              # row sums of A_ij / (b_i b_j)
+        assert np.max(np.abs(rows / rows.mean() - 1.0)) < 3e-5   # balanced
+        # idempotence: one more ICE pass on the balanced matrix changes nothing beyond the tolerance
+        values = dev.ice_scaled_values()
+        assert np.isfinite(values).all() and values.min() > 0
+    del values
+
+
+def test_ice_is_idempotent_on_its_own_output():
+    method, bins, kw = bench.synth_kwargs("ice100k", clean=True)
+    with DeviceCSR.synthetic(bins, **kw) as dev:
+        bias, iters, devn = dev.ice(500, 1e-5)
+        values = dev.ice_scaled_values()
+        pattern = dev.download()
+    assert devn[0] < 1e-5
+    pattern.data[:] = values
+    with DeviceCSR.from_scipy(pattern) as dev2:
+        bias2, iters2, devn2 = dev2.ice(500, 1e-5)
+    assert int(iters2[0]) <= 2 and np.max(np.abs(bias2 - 1.0)) < 5e-5
+
+
+def test_kr_balances_the_matrix_at_full_size():
+    method, bins, kw = bench.synth_kwargs("kr25k", clean=False)
+    with DeviceCSR.synthetic(bins, **kw) as dev:
+        x, outer, matvecs, residual = dev.kr()
+        assert residual < 1e-6 and x.min() > 0 and 5 < outer < 200
+        import torch
+        n = dev.n
+        xt = torch.from_numpy(x).cuda()
+        out = torch.zeros(n, dtype=torch.float64, device="cuda")
+        P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+        _lib.check(_lib.lib().hb_dev_spmv(dev.handle, P(xt), 1e-5, P(xt), None, None, P(out), 0, None))
+        dev.sync()
+        v = out.cpu().numpy()
+        assert np.max(np.abs(v - 1.0)) < 1e-5                    # x o ((A + eps I) x) = 1
+        rs, dg = dev.row_stats()
+        empty = rs == 0
+        assert 0.002 < empty.mean() < 0.01                       # the planted 0.5 % empty bins ...
+        np.testing.assert_allclose(x[empty], 1.0 / np.sqrt(1e-5), rtol=1e-6)   # ... balance against the 1e-5 diagonal
+
+
+def test_filter_finds_planted_bins_at_full_size():
+    method, bins, kw = bench.synth_kwargs("ice25k", clean=False)
+    with DeviceCSR.synthetic(bins, **kw) as dev:
+        n = dev.n
+        rs, dg = dev.row_stats()
+        zero = rs == 0
+        assert 0.002 < zero.mean() < 0.01
+        assert np.all(rs == np.floor(rs))                        # integer counts: row sums exact in any order
+        dev.compact(zero.astype(np.uint8))
+        mask, z, med, mad = dev.mad_filter(-0.85, 50.0, want_z=True)
+        pts = (rs - dg)[~zero]
+        # same statistics with numpy on the downloaded O(n) vector (the O(nnz) part stayed on the GPU)
+        med_ref = np.median(pts[pts > 0])
+        mad_ref = np.median(np.abs(pts - med_ref))
+        assert med[0] == med_ref and mad[0] == mad_ref
+        zr = 0.6745 * ((pts - med_ref) / mad_ref)
+        np.testing.assert_array_equal(z, zr)                     # bit-exact z-scores at 123 k bins
+        np.testing.assert_array_equal(mask.astype(bool), (zr < -0.85) | (zr > 50.0))
+        from oracle.synth_ref import bin_bias
+        g = bin_bias(kw["seed"], n, kw["low_frac"], kw["empty_frac"])
+        assert np.array_equal(g == 0.0, zero)                    # the zero-bin mask is exactly the planted empty bins
+        planted_low = (g == 0.02)[~zero]
+        assert np.all(mask[planted_low] == 1)                    # every planted low-coverage bin is an outlier
+        assert 0.015 < mask.mean() < 0.06
+        dev.compact(mask)
+        assert dev.n == n - zero.sum() - mask.sum()
+        bias, iters, devn = dev.ice(500, 1e-5)
+        assert devn[0] < 1e-5
