@@ -349,7 +349,8 @@ __global__ void hb_keepflag_kernel(const uint8_t* __restrict__ remove, int32_t* 
 }
 
 // Rebuild the store with `rule`; d_newid may be NULL (no bin removal).  Full blocks only when bins are removed.
-static int hb_compact_impl(hb_csr* h, const int32_t* d_newid, int64_t new_n, int cis, int drop_diag) {
+static int hb_compact_impl(hb_csr* h, const int32_t* d_newid, int64_t new_n, int64_t blk_row0, int64_t blk_rows, int cis,
+                           int drop_diag) {
     cudaStream_t s = h->stream;
     HbKeepRule rule;
     rule.newid = d_newid;
@@ -357,8 +358,8 @@ static int hb_compact_impl(hb_csr* h, const int32_t* d_newid, int64_t new_n, int
     rule.nseg = h->nseg;
     rule.cis = (cis && h->nseg > 1) ? 1 : 0;
     rule.drop_diag = drop_diag;
-    const int64_t new_rows = d_newid ? new_n : h->n_rows;
-    const int64_t new_row0 = d_newid ? 0 : h->row0;
+    const int64_t new_rows = d_newid ? blk_rows : h->n_rows;
+    const int64_t new_row0 = d_newid ? blk_row0 : h->row0;
     int64_t* d_cnt = nullptr;
     int64_t* d_new_indptr = nullptr;
     HB_CUDA(cudaMalloc(&d_cnt, sizeof(int64_t) * (size_t)(new_rows + 1)));
@@ -399,9 +400,9 @@ static int hb_compact_impl(hb_csr* h, const int32_t* d_newid, int64_t new_n, int
     h->d_data = d_new_val;
     h->nnz = new_nnz;
     if (d_newid) {
-        h->n_rows = new_n;
+        h->n_rows = new_rows;
         h->n_cols = new_n;
-        h->row0 = 0;
+        h->row0 = new_row0;
     }
     return HB_OK;
 }
@@ -476,8 +477,10 @@ int hb_row_stats(hb_csr* h, double* row_sum, double* diag) {
     cudaStream_t s = h->stream;
     size_t n = (size_t)(h->n_rows > 0 ? h->n_rows : 1);
     double *d_rs = nullptr, *d_dg = nullptr;
-    HB_CUDA(cudaMalloc(&d_rs, sizeof(double) * n));
-    HB_CUDA(cudaMalloc(&d_dg, sizeof(double) * n));
+    // row sums and diagonals share one buffer so that a sharded run assembles both with ONE sum-allreduce
+    HB_CUDA(cudaMalloc(&d_rs, sizeof(double) * 2 * n));
+    d_dg = d_rs + n;
+    HB_CUDA(cudaMemsetAsync(d_rs, 0, sizeof(double) * 2 * n, s));
     if (h->n_rows > 0) {
         hb_row_stats_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, h->n_rows, h->row0,
                                                            h->d_seg_off, h->nseg, 0, d_rs, d_dg);
@@ -487,7 +490,6 @@ int hb_row_stats(hb_csr* h, double* row_sum, double* diag) {
     if (e == cudaSuccess && row_sum && h->n_rows) e = cudaMemcpy(row_sum, d_rs, sizeof(double) * n, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && diag && h->n_rows) e = cudaMemcpy(diag, d_dg, sizeof(double) * n, cudaMemcpyDeviceToHost);
     cudaFree(d_rs);
-    cudaFree(d_dg);
     if (e != cudaSuccess) return hb_cuda_fail(e, "row stats", __FILE__, __LINE__);
     return HB_OK;
 }
@@ -495,7 +497,8 @@ int hb_row_stats(hb_csr* h, double* row_sum, double* diag) {
 int hb_mad_filter(hb_csr* h, double lo, double hi, uint8_t* mask_out, double* zscore_out, double* median_out,
                   double* mad_out) {
     HB_REQUIRE(h != nullptr && mask_out != nullptr, "bad arguments");
-    HB_REQUIRE(h->row0 == 0 && h->n_rows == h->n_cols, "hb_mad_filter needs the full matrix on one device");
+    HB_REQUIRE(h->world > 1 || (h->row0 == 0 && h->n_rows == h->n_cols),
+               "hb_mad_filter needs the full matrix on one device unless hb_set_comm was called");
     int rc = hb_use_device(h);
     if (rc) return rc;
     cudaStream_t s = h->stream;
@@ -506,8 +509,10 @@ int hb_mad_filter(hb_csr* h, double lo, double hi, uint8_t* mask_out, double* zs
     uint8_t* d_mask;
     HbSelState* d_st;
     unsigned int* d_hist;
-    HB_CUDA(cudaMalloc(&d_rs, sizeof(double) * n));
-    HB_CUDA(cudaMalloc(&d_dg, sizeof(double) * n));
+    // row sums and diagonals share one buffer so that a sharded run assembles both with ONE sum-allreduce
+    HB_CUDA(cudaMalloc(&d_rs, sizeof(double) * 2 * n));
+    d_dg = d_rs + n;
+    HB_CUDA(cudaMemsetAsync(d_rs, 0, sizeof(double) * 2 * n, s));
     HB_CUDA(cudaMalloc(&d_pts, sizeof(double) * n));
     HB_CUDA(cudaMalloc(&d_diff, sizeof(double) * n));
     HB_CUDA(cudaMalloc(&d_abs, sizeof(double) * n));
@@ -519,9 +524,15 @@ int hb_mad_filter(hb_csr* h, double lo, double hi, uint8_t* mask_out, double* zs
     HB_CUDA(cudaMalloc(&d_hist, sizeof(unsigned int) * 256 * nseg));
     HB_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned int) * 256 * nseg, s));
     // with segments set, the statistics are those of each chromosome's diagonal block (hicCorrectMatrix.py:557-568)
-    hb_row_stats_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, h->n_rows, h->row0,
-                                                       h->d_seg_off, nseg, 1, d_rs, d_dg);
-    HB_LAUNCH_CHECK();
+    if (h->n_rows > 0) {
+        hb_row_stats_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, h->n_rows, h->row0,
+                                                           h->d_seg_off, nseg, 1, d_rs + h->row0, d_dg + h->row0);
+        HB_LAUNCH_CHECK();
+    }
+    if (h->world > 1 && h->allreduce(h->comm_ctx, d_rs, 2 * n, (void*)s) != 0) {
+        hb_set_error("collective callback failed");
+        return HB_ERR_CUDA;
+    }
     hb_points_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_rs, d_dg, d_pts, n);
     HB_LAUNCH_CHECK();
     rc = hb_segment_median(h, d_pts, 0, d_st, d_hist, d_med);
@@ -541,7 +552,7 @@ int hb_mad_filter(hb_csr* h, double lo, double hi, uint8_t* mask_out, double* zs
         if (e == cudaSuccess && median_out) e = cudaMemcpy(median_out, d_med, sizeof(double) * nseg, cudaMemcpyDeviceToHost);
         if (e == cudaSuccess && mad_out) e = cudaMemcpy(mad_out, d_mad, sizeof(double) * nseg, cudaMemcpyDeviceToHost);
     }
-    cudaFree(d_rs); cudaFree(d_dg); cudaFree(d_pts); cudaFree(d_diff); cudaFree(d_abs); cudaFree(d_z);
+    cudaFree(d_rs); cudaFree(d_pts); cudaFree(d_diff); cudaFree(d_abs); cudaFree(d_z);
     cudaFree(d_med); cudaFree(d_mad); cudaFree(d_mask); cudaFree(d_st); cudaFree(d_hist);
     if (rc) return rc;
     if (e != cudaSuccess) return hb_cuda_fail(e, "mad filter", __FILE__, __LINE__);
@@ -550,7 +561,7 @@ int hb_mad_filter(hb_csr* h, double lo, double hi, uint8_t* mask_out, double* zs
 
 int hb_csr_compact(hb_csr* h, const uint8_t* remove_mask) {
     HB_REQUIRE(h != nullptr && remove_mask != nullptr, "bad arguments");
-    HB_REQUIRE(h->row0 == 0 && h->n_rows == h->n_cols, "hb_csr_compact needs the full matrix on one device");
+    // works on a row block too: every rank passes the same global mask and keeps its own surviving rows
     int rc = hb_use_device(h);
     if (rc) return rc;
     cudaStream_t s = h->stream;
@@ -558,12 +569,16 @@ int hb_csr_compact(hb_csr* h, const uint8_t* remove_mask) {
     if (n == 0) return HB_OK;
     // new segment offsets + new size from the host mask
     std::vector<int64_t> new_off(h->nseg + 1, 0);
-    int64_t kept = 0;
+    int64_t kept = 0, kept_before_block = 0, kept_in_block = 0;
     {
         int sgi = 0;
         for (int64_t i = 0; i <= n; ++i) {
             while (sgi <= h->nseg && h->seg_off[sgi] == i) new_off[sgi++] = kept;
-            if (i < n && !remove_mask[i]) ++kept;
+            if (i == h->row0) kept_before_block = kept;
+            if (i < n && !remove_mask[i]) {
+                ++kept;
+                if (i >= h->row0 && i < h->row0 + h->n_rows) ++kept_in_block;
+            }
         }
     }
     uint8_t* d_rm = nullptr;
@@ -581,7 +596,7 @@ int hb_csr_compact(hb_csr* h, const uint8_t* remove_mask) {
     HB_LAUNCH_CHECK();
     hb_newid_kernel<<<g, 256, 0, s>>>(d_rm, d_scan, d_newid, n);
     HB_LAUNCH_CHECK();
-    rc = hb_compact_impl(h, d_newid, kept, 0, 0);
+    rc = hb_compact_impl(h, d_newid, kept, kept_before_block, kept_in_block, 0, 0);
     cudaFree(d_rm);
     cudaFree(d_keep);
     cudaFree(d_newid);
@@ -597,14 +612,14 @@ int hb_csr_keep_cis(hb_csr* h) {
     int rc = hb_use_device(h);
     if (rc) return rc;
     if (h->nseg <= 1) return HB_OK;
-    return hb_compact_impl(h, nullptr, 0, 1, 0);
+    return hb_compact_impl(h, nullptr, 0, 0, 0, 1, 0);
 }
 
 int hb_diag_zero(hb_csr* h) {
     HB_REQUIRE(h != nullptr, "null handle");
     int rc = hb_use_device(h);
     if (rc) return rc;
-    return hb_compact_impl(h, nullptr, 0, 0, 1);
+    return hb_compact_impl(h, nullptr, 0, 0, 0, 0, 1);
 }
 
 int hb_symmetry(hb_csr* h, double* ratio_out) {

@@ -124,11 +124,13 @@ HB_API int hb_set_comm(hb_csr* h, int rank, int world, hb_allreduce_fn fn, void*
  *   diag[i] (hicCorrectMatrix.py:568,588) for the block's rows; either may be NULL.
  * hb_mad_filter: modified z-score of points = row_sum - diag and the outlier
  *   mask (class MAD, hicCorrectMatrix.py:349-391; filter_by_zscore :548-592;
- *   per segment when segments are set).  Requires a full (unsharded) block.
+ *   per segment when segments are set).  On a row block (hb_set_comm) the row statistics are assembled with one
+ *   sum-allreduce and the O(n) selection runs replicated: every rank gets the same full-length mask.
  *   mask_out[i] = 1 if z < lo or z > hi; zscore_out optional (NULL).
  * hb_csr_compact: delete the rows AND columns with remove_mask[i] != 0 and
  *   renumber (hicmatrix maskBins as used at hicCorrectMatrix.py:616, 672).
- *   Segment offsets are renumbered with it. Requires a full block.
+ *   Segment offsets are renumbered with it.  On a row block every rank passes the same global mask and keeps
+ *   its own surviving rows (row0 / n_rows / n_cols are renumbered).
  * hb_diag_zero: --skipDiagonal (hicCorrectMatrix.py:648-649).
  * hb_symmetry: the reference's criterion (iterativeCorrection.py:35):
  *   ratio = mean|M - M^T| / |mean M|; the caller raises when ratio > 1e-10. */

@@ -122,3 +122,38 @@ def test_sharded_kr_is_bit_identical_to_single_block(world, gm12878):
     assert comm.calls == mv1 + 1                            # one exchange per mat-vec (+ the initial residual)
     ref = kr_oracle.kr_balance(m)
     np.testing.assert_allclose(x1, ref["x"], rtol=1e-9)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_filter_and_ice_pipeline_matches_single_block(world, gm12878):
+    """zero-bin mask -> scrub -> MAD filter -> bin deletion -> ICE, every stage on row blocks."""
+    from hicexplorer_b200.pipeline import ice_pipeline
+    full = full_from_pixels(gm12878)
+    single = ice_pipeline(full, (-1.5, 5.0), max_iter=500, want_matrix=False)
+    n = full.shape[0]
+    gather = {"rs": np.zeros(n), "lock": threading.Lock(), "barrier": threading.Barrier(world)}
+
+    def stage(dev):
+        _n_rows, _n, row0, _nnz = dev.dims()
+        rs, _dg = dev.row_stats()                         # block-local rows
+        with gather["lock"]:
+            gather["rs"][row0:row0 + len(rs)] = rs        # stands in for an all-gather of n doubles on the host
+        gather["barrier"].wait()
+        zero = gather["rs"] == 0
+        dev.compact(zero.astype(np.uint8))
+        dev.scrub()
+        mask, _z, _med, _mad = dev.mad_filter(-1.5, 5.0)  # one collective inside
+        dev.compact(mask)
+        bias, iters, devn = dev.ice(500, 1e-5)
+        return zero, mask, bias, iters, dev.dims()
+
+    results, _comm = _run_sharded(full, world, stage)
+    rows_total = 0
+    for zero, mask, bias, iters, dims in results:
+        assert np.array_equal(np.flatnonzero(zero), single["zero_bins"])
+        assert np.array_equal(np.flatnonzero(mask), single["outliers_rel"])     # bit-exact mask on every rank
+        np.testing.assert_array_equal(bias, single["bias"])                     # and bit-identical bias
+        assert int(iters[0]) == int(single["iterations"][0])
+        assert dims[1] == len(single["kept"])
+        rows_total += dims[0]
+    assert rows_total == len(single["kept"])                                    # blocks still tile the matrix
