@@ -264,19 +264,20 @@ struct FSum2 : FBase {
 // per-row sums over the upper triangle of A + eps I, off-diagonals doubled (krbalancing rescale_norm_vector)
 __global__ void __launch_bounds__(256)
 hb_kr_rescale_rows_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
-                          int64_t n_rows, const double* __restrict__ x, double eps, double* __restrict__ scaled,
-                          double* __restrict__ orig) {
+                          int64_t n_rows, int64_t row0, const double* __restrict__ x, double eps,
+                          double* __restrict__ scaled, double* __restrict__ orig) {
     const int lane = threadIdx.x & 31;
     const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t row = gwarp; row < n_rows; row += nwarps) {
-        const double xi = x[row];
+        const int64_t g = row0 + row;
+        const double xi = x[g];
         double so = 0.0, ss = 0.0, dg = 0.0;
         for (int64_t k = indptr[row] + lane; k < indptr[row + 1]; k += 32) {
             const int c = idx[k];
             const double a = val[k];
-            if (c == row) dg += a;
-            else if (c > row) {
+            if (c == g) dg += a;
+            else if (c > g) {
                 so += a * 2;
                 ss += a * xi * x[c] * 2;
             }
@@ -286,22 +287,22 @@ hb_kr_rescale_rows_kernel(const int64_t* __restrict__ indptr, const int32_t* __r
         dg = hb_warp_sum(dg);
         if (lane == 0) {
             const double d = dg + eps;
-            orig[row] = so + d;
-            scaled[row] = ss + d * xi * xi;
+            orig[g] = so + d;
+            scaled[g] = ss + d * xi * xi;
         }
     }
 }
 
 // upper triangle (diagonal always stored) of (A + eps I) o (x x^T)
 __global__ void __launch_bounds__(256)
-hb_kr_upper_count_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, int64_t n_rows,
+hb_kr_upper_count_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, int64_t n_rows, int64_t row0,
                          int64_t* __restrict__ cnt) {
     const int lane = threadIdx.x & 31;
     const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t row = gwarp; row < n_rows; row += nwarps) {
         long long c = 0;
-        for (int64_t k = indptr[row] + lane; k < indptr[row + 1]; k += 32) c += idx[k] > row ? 1 : 0;
+        for (int64_t k = indptr[row] + lane; k < indptr[row + 1]; k += 32) c += idx[k] > row0 + row ? 1 : 0;
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
         if (lane == 0) cnt[row] = c + 1;
     }
@@ -309,13 +310,14 @@ hb_kr_upper_count_kernel(const int64_t* __restrict__ indptr, const int32_t* __re
 
 __global__ void __launch_bounds__(256)
 hb_kr_upper_fill_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
-                        int64_t n_rows, const double* __restrict__ x, double eps, const int64_t* __restrict__ out_ptr,
+                        int64_t n_rows, int64_t row0, const double* __restrict__ x, double eps, const int64_t* __restrict__ out_ptr,
                         int32_t* __restrict__ out_idx, double* __restrict__ out_val) {
     const int lane = threadIdx.x & 31;
     const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t row = gwarp; row < n_rows; row += nwarps) {
-        const double xi = x[row];
+        const int64_t g = row0 + row;
+        const double xi = x[g];
         int64_t w = out_ptr[row] + 1;
         double dg = 0.0;
         const int64_t s = indptr[row], e = indptr[row + 1];
@@ -327,8 +329,8 @@ hb_kr_upper_fill_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
                 c = idx[k];
                 a = val[k];
             }
-            if (c == row) dg += a;
-            const bool kp = c > row;
+            if (c == g) dg += a;
+            const bool kp = c > g;
             const unsigned int bal = __ballot_sync(0xffffffffu, kp);
             if (kp) {
                 const int64_t pos = w + __popc(bal & ((1u << lane) - 1u));
@@ -339,7 +341,7 @@ hb_kr_upper_fill_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
         }
         dg = hb_warp_sum(dg);
         if (lane == 0) {
-            out_idx[out_ptr[row]] = (int32_t)row;
+            out_idx[out_ptr[row]] = (int32_t)g;
             out_val[out_ptr[row]] = (dg + eps) * xi * xi;
         }
     }
@@ -651,7 +653,8 @@ done:
 
 int hb_kr_rescale(hb_csr* h, double diag_eps, double* x_inout, double* factor_out) {
     HB_REQUIRE(h != nullptr && x_inout != nullptr, "bad arguments");
-    HB_REQUIRE(h->row0 == 0 && h->n_rows == h->n_cols, "hb_kr_rescale needs the full matrix on one device");
+    HB_REQUIRE(h->world > 1 || (h->row0 == 0 && h->n_rows == h->n_cols),
+               "hb_kr_rescale needs the full matrix on one device unless hb_set_comm was called");
     int rc = hb_ensure_state(h);
     if (rc) return rc;
     rc = hb_use_device(h);
@@ -665,10 +668,19 @@ int hb_kr_rescale(hb_csr* h, double diag_eps, double* x_inout, double* factor_ou
     double sc[SC_WORDS];
     cudaError_t e = cudaMemcpyAsync(d_x, x_inout, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaMemsetAsync(h->d_counters + 2, 0, sizeof(unsigned int), s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_scaled, 0, sizeof(double) * (size_t)(2 * n), s);
     if (e == cudaSuccess) {
-        hb_kr_rescale_rows_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, h->n_rows, d_x,
-                                                                 diag_eps, d_scaled, d_orig);
-        g_hb_launches.fetch_add(1);
+        if (h->n_rows > 0) {
+            hb_kr_rescale_rows_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, h->n_rows,
+                                                                     h->row0, d_x, diag_eps, d_scaled, d_orig);
+            g_hb_launches.fetch_add(1);
+        }
+        // sharded: every rank filled its rows of (scaled | orig); one sum-allreduce assembles both vectors
+        if (h->world > 1 && h->allreduce(h->comm_ctx, d_scaled, 2 * n, (void*)s) != 0) {
+            cudaFree(buf);
+            hb_set_error("collective callback failed");
+            return HB_ERR_CUDA;
+        }
         HbTiles tiles{h->d_tile_row0, h->d_tile_len, h->n_tiles};
         for (int which = 0; which < 2; ++which) {
             FSum2 f;
@@ -692,16 +704,17 @@ int hb_kr_rescale(hb_csr* h, double diag_eps, double* x_inout, double* factor_ou
 int hb_kr_scaled_upper(hb_csr* h, double diag_eps, const double* x, int64_t* nnz_out, int64_t* indptr, int32_t* indices,
                        double* data) {
     HB_REQUIRE(h != nullptr && x != nullptr && nnz_out != nullptr, "bad arguments");
-    HB_REQUIRE(h->row0 == 0 && h->n_rows == h->n_cols, "hb_kr_scaled_upper needs the full matrix on one device");
+    // row-local: on a row block the output is the block's rows (indptr[n_rows+1] block-local, global column ids)
     int rc = hb_use_device(h);
     if (rc) return rc;
-    const int64_t n = h->n_cols;
+    const int64_t n = h->n_rows;
+    const int64_t nx = h->n_cols;
     cudaStream_t s = h->stream;
     int64_t *d_cnt = nullptr, *d_ptr = nullptr;
     HB_CUDA(cudaMalloc(&d_cnt, sizeof(int64_t) * (size_t)(n + 1)));
     HB_CUDA(cudaMalloc(&d_ptr, sizeof(int64_t) * (size_t)(n + 1)));
     if (n > 0) {
-        hb_kr_upper_count_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_indptr, h->d_indices, n, d_cnt);
+        hb_kr_upper_count_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_indptr, h->d_indices, n, h->row0, d_cnt);
         g_hb_launches.fetch_add(1);
     }
     hb_kr_scan_kernel<<<1, 1024, 0, s>>>(d_cnt, d_ptr, n);
@@ -713,13 +726,13 @@ int hb_kr_scaled_upper(hb_csr* h, double diag_eps, const double* x, int64_t* nnz
     if (e == cudaSuccess && indptr != nullptr && indices != nullptr && data != nullptr && n > 0) {
         double *d_x = nullptr, *d_val = nullptr;
         int32_t* d_idx = nullptr;
-        e = cudaMalloc(&d_x, sizeof(double) * (size_t)n);
+        e = cudaMalloc(&d_x, sizeof(double) * (size_t)nx);
         if (e == cudaSuccess) e = cudaMalloc(&d_val, sizeof(double) * (size_t)total);
         if (e == cudaSuccess) e = cudaMalloc(&d_idx, sizeof(int32_t) * (size_t)total);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_x, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_x, x, sizeof(double) * (size_t)nx, cudaMemcpyHostToDevice, s);
         if (e == cudaSuccess) {
-            hb_kr_upper_fill_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, n, d_x, diag_eps,
-                                                                   d_ptr, d_idx, d_val);
+            hb_kr_upper_fill_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, n, h->row0, d_x,
+                                                                   diag_eps, d_ptr, d_idx, d_val);
             g_hb_launches.fetch_add(1);
             e = cudaStreamSynchronize(s);
         }

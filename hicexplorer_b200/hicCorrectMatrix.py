@@ -6,6 +6,8 @@ Differences, all additive or documented:
     ``--device`` are new optional flags;
   * the ICE branch uploads the matrix once and runs zero-bin masking, NaN/Inf scrub, the MAD filter, bin deletion
     and the iterations on the device (``pipeline.ice_pipeline``) instead of round-tripping through scipy;
+  * launched under ``torchrun`` (WORLD_SIZE > 1) the genome-wide ICE / KR corrections run on nnz-balanced row blocks,
+    one process per GPU, and rank 0 writes the output (``--perchr`` KR and ``--sequencedCountCutoff`` stay single-GPU);
   * ``diagnostic_plot`` (matplotlib histogram, :425-545) is out of scope and exits with an explanation;
   * ``--transCutoff`` (hicmatrix ``truncTrans``) is not implemented yet and exits with an explanation;
     ``--inflationCutoff`` only ever worked together with it in the reference (``pre_row_sum`` is otherwise
@@ -21,7 +23,7 @@ from scipy.sparse import lil_matrix
 from . import hicmatrix_lite as hm
 from ._version import __version__
 from .krbalancing import kr_balancing
-from .pipeline import ice_pipeline
+from .pipeline import ice_pipeline, ice_pipeline_sharded, kr_pipeline_sharded
 
 log = logging.getLogger(__name__)
 
@@ -110,6 +112,7 @@ def main(args=None):
                   'use the reference tool for the plot (the statistics it shows are those of --filterThreshold).')
         sys.exit(1)
 
+    world, rank = _init_distributed(args)
     if _is_cooler(args.matrix) and args.chromosomes is not None and len(args.chromosomes) == 1:
         ma = hm.hiCMatrix(args.matrix, pChrnameList=[str(c) for c in args.chromosomes])
     else:
@@ -118,13 +121,34 @@ def main(args=None):
             ma.reorderChromosomes([str(c) for c in args.chromosomes])
 
     if args.correctionMethod == 'ICE':
-        _correct_ice(ma, args)
+        _correct_ice(ma, args, world, rank)
     else:
-        _correct_kr(ma, args)
-    ma.save(args.outFileName, pApplyCorrection=False)
+        _correct_kr(ma, args, world, rank)
+    if rank == 0:
+        ma.save(args.outFileName, pApplyCorrection=False)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
 
 
-def _correct_ice(ma, args):
+def _init_distributed(args):
+    """one process per GPU when launched by torchrun; (world, rank) = (1, 0) otherwise"""
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 1, 0
+    import torch
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    args.device = local
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return world, dist.get_rank()
+
+
+def _correct_ice(ma, args, world=1, rank=0):
     if not args.filterThreshold:
         log.error('min and max filtering thresholds should be set')
         sys.exit(1)
@@ -139,9 +163,19 @@ def _correct_ice(ma, args):
         def extra_fn(kept_ids):
             return coverage[kept_ids] < args.sequencedCountCutoff
 
-    res = ice_pipeline(ma.matrix, (args.filterThreshold[0], args.filterThreshold[1]), max_iter=args.iterNum,
-                       tolerance=args.tolerance, chr_offsets=ma.chromosome_offsets(), perchr=args.perchr,
-                       skip_diagonal=args.skipDiagonal, device=args.device, want_matrix=True, extra_mask_fn=extra_fn)
+    if world > 1:
+        if extra_fn is not None:
+            log.error('--sequencedCountCutoff is not available in multi-GPU runs')
+            sys.exit(1)
+        res = ice_pipeline_sharded(ma.matrix, (args.filterThreshold[0], args.filterThreshold[1]), max_iter=args.iterNum,
+                                   tolerance=args.tolerance, chr_offsets=ma.chromosome_offsets(), perchr=args.perchr,
+                                   skip_diagonal=args.skipDiagonal, want_matrix=True)
+        if rank != 0:
+            return
+    else:
+        res = ice_pipeline(ma.matrix, (args.filterThreshold[0], args.filterThreshold[1]), max_iter=args.iterNum,
+                           tolerance=args.tolerance, chr_offsets=ma.chromosome_offsets(), perchr=args.perchr,
+                           skip_diagonal=args.skipDiagonal, device=args.device, want_matrix=True, extra_mask_fn=extra_fn)
     n = res['n']
     keep1 = np.setdiff1d(np.arange(n), res['zero_bins'])
     outlier_regions = res['outliers_rel']
@@ -167,8 +201,16 @@ def _correct_ice(ma, args):
     log.info("Total regions to be removed: {}".format(n - len(res['kept'])))
 
 
-def _correct_kr(ma, args):
+def _correct_kr(ma, args, world=1, rank=0):
     matrix = ma.matrix.astype(np.float64)
+    if world > 1 and not args.perchr and not str(args.outFileName).endswith('.h5'):
+        # genome-wide KR to .cool: only the (rescaled) vector is needed -> row blocks over the GPUs
+        res = kr_pipeline_sharded(matrix, rescale=True)
+        print("normalisation factor is {}".format(res['factor']))
+        ma.setCorrectionFactors(np.asmatrix(res['x']).T)
+        return
+    if world > 1 and rank != 0:
+        return      # remaining KR variants run on rank 0's GPU
     if args.perchr:
         corrected_matrix = lil_matrix(matrix.shape)
         factors = []

@@ -110,3 +110,119 @@ def scatter_to_frame(corrected_kept, kept, n):
     coo = corrected_kept.tocoo()
     kept = np.asarray(kept)
     return sparse.csr_matrix((coo.data, (kept[coo.row], kept[coo.col])), shape=(n, n))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Several GPUs: one process per GPU (torchrun), nnz-balanced row blocks, the same stages on every block.
+# Every rank holds the host matrix (it came from the same file) and uploads only its rows; rank 0 returns
+# the assembled result, the other ranks return None.
+# ---------------------------------------------------------------------------------------------------------
+def _dist_env():
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return None, 0, 1
+    return dist, dist.get_rank(), dist.get_world_size()
+
+
+def _gather_rows_to_root(values, dist, rank, world, device):
+    """concatenate per-rank 1-D float64 arrays on rank 0 (row blocks are contiguous and ordered by rank)."""
+    import torch
+    sizes = torch.zeros(world, dtype=torch.int64, device="cuda")
+    sizes[rank] = len(values)
+    dist.all_reduce(sizes)
+    sizes = sizes.cpu().numpy()
+    mine = torch.from_numpy(np.ascontiguousarray(values)).cuda()
+    if rank == 0:
+        parts = [values]
+        for src in range(1, world):
+            buf = torch.empty(int(sizes[src]), dtype=mine.dtype, device="cuda")
+            if sizes[src]:
+                dist.recv(buf, src=src)
+            parts.append(buf.cpu().numpy())
+        return np.concatenate(parts)
+    if len(values):
+        dist.send(mine, dst=0)
+    return None
+
+
+def ice_pipeline_sharded(matrix, filter_threshold, max_iter=500, tolerance=1e-5, chr_offsets=None, perchr=False,
+                         skip_diagonal=False, want_matrix=True):
+    """ice_pipeline on row blocks across the initialised torch.distributed group (NCCL).  The symmetry test of the
+    single-GPU path needs the transposed entries of other blocks and is skipped here."""
+    import torch
+
+    from .dist import attach_comm, nnz_balanced_partition
+    dist, rank, world = _dist_env()
+    if dist is None or world == 1:
+        return ice_pipeline(matrix, filter_threshold, max_iter, tolerance, chr_offsets, perchr, skip_diagonal,
+                            device=torch.cuda.current_device(), want_matrix=want_matrix)
+    device = torch.cuda.current_device()
+    m = canonical_csr(matrix)
+    n = m.shape[0]
+    lo, hi = filter_threshold
+    bounds = nnz_balanced_partition(m.indptr, world)
+    a, b = int(bounds[rank]), int(bounds[rank + 1])
+    with DeviceCSR.from_scipy(m, device=device, row_range=(a, b)) as dev:
+        keep_alive = attach_comm(dev, rank, world)
+        rs_local, _ = dev.row_stats()
+        rs = torch.zeros(n, dtype=torch.float64, device="cuda")
+        rs[a:b] = torch.from_numpy(rs_local).cuda()
+        dist.all_reduce(rs)                                   # x + 0: exact assembly of the row sums
+        zero_mask = (rs == 0).cpu().numpy()
+        zero_bins = np.flatnonzero(zero_mask)
+        if perchr:
+            dev.set_segments(np.asarray(chr_offsets, dtype=np.int64))
+        dev.compact(zero_mask.astype(np.uint8))
+        keep1 = np.flatnonzero(~zero_mask)
+        dev.scrub()
+        if skip_diagonal:
+            dev.diag_zero()
+        mask, _z, _med, _mad = dev.mad_filter(lo, hi)         # one collective inside, mask replicated
+        outliers_rel = np.flatnonzero(mask)
+        dev.compact(mask)
+        kept = keep1[~mask.astype(bool)]
+        if perchr:
+            dev.keep_cis()
+        bias, iters, deviation = dev.ice(max_iter, tolerance)  # one collective per iteration
+        values = dev.ice_scaled_values() if want_matrix else None
+        del keep_alive
+    out = dict(zero_bins=zero_bins, outliers_rel=outliers_rel, kept=kept, bias=bias, iterations=iters,
+               deviation=deviation, n=n)
+    if want_matrix:
+        all_values = _gather_rows_to_root(values, dist, rank, world, device)
+        if rank == 0:
+            pattern = sparse.csr_matrix(m[kept, :][:, kept])
+            pattern.sort_indices()
+            if perchr:
+                seg = np.searchsorted(np.asarray(chr_offsets), kept, side="right")
+                coo = pattern.tocoo()
+                cis = seg[coo.row] == seg[coo.col]
+                pattern = sparse.csr_matrix((coo.data[cis], (coo.row[cis], coo.col[cis])), shape=pattern.shape)
+                pattern.sort_indices()
+            if skip_diagonal:
+                pattern.setdiag(0)
+                pattern.eliminate_zeros()
+            assert pattern.nnz == len(all_values), "device and host patterns disagree"
+            out["matrix"] = sparse.csr_matrix((all_values, pattern.indices, pattern.indptr), shape=pattern.shape)
+    return out if rank == 0 else None
+
+
+def kr_pipeline_sharded(matrix, rescale=True):
+    """kr_pipeline on row blocks: x is replicated on every rank; rank 0 also gets the rescale factor."""
+    import torch
+
+    from .dist import attach_comm, nnz_balanced_partition
+    dist, rank, world = _dist_env()
+    if dist is None or world == 1:
+        return kr_pipeline(matrix, rescale=rescale, want_matrix=False, device=torch.cuda.current_device())
+    device = torch.cuda.current_device()
+    m = canonical_csr(matrix)
+    bounds = nnz_balanced_partition(m.indptr, world)
+    with DeviceCSR.from_scipy(m, device=device, row_range=(int(bounds[rank]), int(bounds[rank + 1]))) as dev:
+        keep_alive = attach_comm(dev, rank, world)
+        x, outer, matvecs, residual = dev.kr()
+        factor = 1.0
+        if rescale:
+            x, factor = dev.kr_rescale(x, KR_DIAG_EPS)
+        del keep_alive
+    return dict(x=x, factor=factor, outer=outer, matvecs=matvecs, residual=residual)

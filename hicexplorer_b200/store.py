@@ -229,12 +229,12 @@ class DeviceCSR(object):
 
     def kr_scaled_upper(self, x, diag_eps=KR_DIAG_EPS):
         x = np.ascontiguousarray(x, dtype=np.float64)
-        n = self.n
+        n_rows, n, _row0, _nnz = self.dims()
         nnz = ctypes.c_int64()
         check(lib().hb_kr_scaled_upper(self._h, diag_eps, ptr(x), ctypes.byref(nnz), None, None, None))
-        indptr = np.empty(n + 1, dtype=np.int64)
+        indptr = np.empty(n_rows + 1, dtype=np.int64)
         indices = np.empty(nnz.value, dtype=np.int32)
         data = np.empty(nnz.value, dtype=np.float64)
         check(lib().hb_kr_scaled_upper(self._h, diag_eps, ptr(x), ctypes.byref(nnz), ptr(indptr), ptr(indices),
                                        ptr(data)))
-        return sparse.csr_matrix((data, indices, indptr), shape=(n, n))
+        return sparse.csr_matrix((data, indices, indptr), shape=(n_rows, n))

@@ -157,3 +157,29 @@ def test_sharded_filter_and_ice_pipeline_matches_single_block(world, gm12878):
         assert dims[1] == len(single["kept"])
         rows_total += dims[0]
     assert rows_total == len(single["kept"])                                    # blocks still tile the matrix
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_kr_rescale_and_scaled_upper(world, kr_partial):
+    m = full_from_pixels(kr_partial)
+    with DeviceCSR.from_scipy(m) as dev:
+        x1, _o, _mv, _r = dev.kr()
+        xr1, f1 = dev.kr_rescale(x1)
+        up1 = dev.kr_scaled_upper(xr1)
+
+    def stage(dev):
+        x, _o, _mv, _r = dev.kr()
+        xr, f = dev.kr_rescale(x)
+        return xr, f, dev.kr_scaled_upper(xr), dev.dims()
+
+    results, _comm = _run_sharded(m, world, stage)
+    rows = []
+    for xr, f, up, dims in results:
+        assert f == f1
+        np.testing.assert_array_equal(xr, xr1)
+        assert up.shape == (dims[0], m.shape[0])
+        rows.append(up)
+    from scipy import sparse
+    whole = sparse.vstack(rows).tocsr()
+    assert np.array_equal(whole.indptr, up1.indptr) and np.array_equal(whole.indices, up1.indices)
+    np.testing.assert_array_equal(whole.data, up1.data)

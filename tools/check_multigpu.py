@@ -1,0 +1,89 @@
+#!/usr/bin/env python
+"""Multi-GPU parity check, run under torchrun on N >= 2 GPUs:
+  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/check_multigpu.py
+Compares the sharded pipelines (real NCCL all-reduces between processes) with the single-GPU pipelines and the CLI
+run under torchrun with the same command on one GPU.  Exit code 0 = all checks passed."""
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from scipy import sparse
+
+    from hicexplorer_b200.pipeline import ice_pipeline, ice_pipeline_sharded, kr_pipeline, kr_pipeline_sharded
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    z = np.load(os.path.join(ROOT, "tests", "golden", "gm12878.npz"))
+    n = int(z["nbins"])
+    up = sparse.csr_matrix((z["count"].astype(np.float64), (z["bin1"], z["bin2"])), shape=(n, n))
+    full = sparse.csr_matrix(up + sparse.triu(up, 1).T)
+    full.sort_indices()
+    ok = True
+
+    def check(name, cond):
+        nonlocal ok
+        if rank == 0:
+            print(("PASS " if cond else "FAIL ") + name, flush=True)
+        ok = ok and bool(cond)
+
+    got = ice_pipeline_sharded(full, (-1.5, 5.0), max_iter=500)
+    if rank == 0:
+        ref = ice_pipeline(full, (-1.5, 5.0), max_iter=500, device=local)
+        check("ICE sharded: masks bit-exact", np.array_equal(got["zero_bins"], ref["zero_bins"]) and
+              np.array_equal(got["outliers_rel"], ref["outliers_rel"]))
+        check("ICE sharded: bias bit-identical to 1 GPU", np.array_equal(got["bias"], ref["bias"]))
+        check("ICE sharded: iterations equal (%d)" % int(ref["iterations"][0]), int(got["iterations"][0]) == int(ref["iterations"][0]))
+        check("ICE sharded: corrected matrix pattern + values", np.array_equal(got["matrix"].indices, ref["matrix"].indices) and
+              np.allclose(got["matrix"].data, ref["matrix"].data, rtol=1e-12, atol=0))
+        check("ICE vs reference run (bias 1e-9)", np.allclose(got["bias"], z["ice_bias"], rtol=1e-9, atol=0))
+    offs = np.concatenate([[0], np.flatnonzero(np.diff(np.searchsorted(z["chrom_offset"], np.arange(n), side="right"))) + 1, [n]])
+    gotp = ice_pipeline_sharded(full, (-1.5, 5.0), max_iter=300, chr_offsets=offs, perchr=True)
+    if rank == 0:
+        refp = ice_pipeline(full, (-1.5, 5.0), max_iter=300, chr_offsets=offs, perchr=True, device=local)
+        check("perchr ICE sharded: masks + bias identical", np.array_equal(gotp["outliers_rel"], refp["outliers_rel"]) and
+              np.array_equal(gotp["bias"], refp["bias"]) and np.array_equal(gotp["iterations"], refp["iterations"]))
+        check("perchr ICE sharded: matrix identical", gotp["matrix"].nnz == refp["matrix"].nnz and
+              np.allclose(gotp["matrix"].data, refp["matrix"].data, rtol=1e-12, atol=0))
+    kr = kr_pipeline_sharded(full, rescale=True)
+    if rank == 0:
+        kref = kr_pipeline(full, rescale=True, want_matrix=False, device=local)
+        check("KR sharded: x bit-identical, same mat-vec count", np.array_equal(kr["x"], kref["x"]) and kr["matvecs"] == kref["matvecs"])
+        check("KR sharded: rescale factor identical", kr["factor"] == kref["factor"])
+    # the CLI under torchrun
+    from hicexplorer_b200.hicCorrectMatrix import main as cli
+    from hicexplorer_b200.hicmatrix_lite import hiCMatrix
+    tmp = tempfile.gettempdir()
+    src = os.path.join(tmp, "mg_in.cool")
+    if rank == 0:
+        ma = hiCMatrix()
+        ma.matrix = full
+        off = z["chrom_offset"]
+        ma.cut_intervals = [(str(c + 1), int((i - off[c]) * 2500000), int((i - off[c] + 1) * 2500000), 1.0)
+                            for c in range(len(off) - 1) for i in range(off[c], off[c + 1])]
+        ma._index_intervals()
+        ma.save(src)
+    dist.barrier()
+    dist.destroy_process_group()
+    out = os.path.join(tmp, "mg_out.cool")
+    cli(["correct", "-m", src, "-o", out, "--correctionMethod", "ICE", "--filterThreshold", "-1.5", "5"])
+    if rank == 0:
+        new = hiCMatrix(out)
+        cf = np.asarray(new.correction_factors).ravel()
+        check("CLI under torchrun: factors match the single-GPU pipeline", np.array_equal(cf[ref["kept"]], ref["bias"]) and
+              np.isnan(cf).sum() == n - len(ref["kept"]))
+        print("ALL PASS" if ok else "SOME FAILED", flush=True)
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
