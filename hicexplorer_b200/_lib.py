@@ -73,6 +73,9 @@ SIGNATURES = {
     "hb_dev_csr_pointers": (c_int, [vp, P(vp), P(vp), P(vp)]),
     "hb_sync": (c_int, [vp]),
     "hb_set_comm": (c_int, [vp, c_int, c_int, vp, vp]),
+    "hb_peer_export": (c_int, [vp, c_int, c_int, vp]),
+    "hb_peer_attach": (c_int, [vp, vp]),
+    "hb_peer_active": (c_int, [vp]),
     "hb_set_segments": (c_int, [vp, c_int, vp]),
     "hb_csr_keep_cis": (c_int, [vp]),
     "hb_scrub": (c_int, [vp, vp]),

@@ -202,6 +202,7 @@ int hb_csr_destroy(hb_csr* h) {
         cudaFree(h->d_data);
     }
     cudaFree(h->d_tile_slab);
+    hb_peer_release(h);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return HB_OK;
@@ -258,6 +259,56 @@ int hb_set_comm(hb_csr* h, int rank, int world, hb_allreduce_fn fn, void* ctx) {
     return HB_OK;
 }
 
+int hb_peer_export(hb_csr* h, int rank, int world, void* ipc_handle_out) {
+    HB_REQUIRE(h != nullptr && ipc_handle_out != nullptr, "bad arguments");
+    HB_REQUIRE(world >= 2 && world <= HB_MAX_PEERS && rank >= 0 && rank < world, "peer exchange needs 2..8 ranks");
+    int rc = hb_use_device(h);
+    if (rc) return rc;
+    hb_peer_release(h);
+    const size_t buf = ((sizeof(double) * (size_t)(h->n_cols + 64)) + 255) & ~(size_t)255;
+    h->sym_buf_bytes = buf;
+    h->sym_flag_off = 2 * buf;
+    const size_t total = 2 * buf + 2 * 512 + 256;
+    HB_CUDA(cudaMalloc(&h->d_sym, total));
+    HB_CUDA(cudaMemset(h->d_sym, 0, total));
+    HB_CUDA(cudaDeviceSynchronize());
+    h->d_done = (unsigned int*)((unsigned char*)h->d_sym + 2 * buf + 2 * 512);
+    cudaIpcMemHandle_t hd;
+    HB_CUDA(cudaIpcGetMemHandle(&hd, h->d_sym));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(ipc_handle_out, &hd, 64);
+    h->rank = rank;
+    h->world = world;
+    return HB_OK;
+}
+
+int hb_peer_attach(hb_csr* h, const void* all_handles) {
+    HB_REQUIRE(h != nullptr && all_handles != nullptr && h->d_sym != nullptr, "call hb_peer_export first");
+    int rc = hb_use_device(h);
+    if (rc) return rc;
+    for (int q = 0; q < h->world; ++q) {
+        if (q == h->rank) {
+            h->peer_base[q] = h->d_sym;
+            continue;
+        }
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, (const unsigned char*)all_handles + 64 * q, 64);
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            hb_peer_release(h);
+            return hb_cuda_fail(e, "cudaIpcOpenMemHandle (peer access between the GPUs is required)", __FILE__, __LINE__);
+        }
+        h->peer_base[q] = p;
+    }
+    h->peer = true;
+    h->allreduce = nullptr;
+    h->peer_seq = 0;
+    return HB_OK;
+}
+
+int hb_peer_active(const hb_csr* h) { return (h != nullptr && h->peer) ? 1 : 0; }
+
 int hb_set_segments(hb_csr* h, int nseg, const int64_t* seg_offsets) {
     HB_REQUIRE(h != nullptr, "null handle");
     HB_REQUIRE(nseg >= 1 && nseg <= HB_MAX_SEG && seg_offsets != nullptr, "bad segment count");
@@ -273,6 +324,17 @@ int hb_set_segments(hb_csr* h, int nseg, const int64_t* seg_offsets) {
 }
 
 }  // extern "C"
+
+void hb_peer_release(hb_csr* h) {
+    for (int q = 0; q < HB_MAX_PEERS; ++q) {
+        if (h->peer_base[q] != nullptr && h->peer_base[q] != h->d_sym) cudaIpcCloseMemHandle(h->peer_base[q]);
+        h->peer_base[q] = nullptr;
+    }
+    cudaFree(h->d_sym);
+    h->d_sym = nullptr;
+    h->d_done = nullptr;
+    h->peer = false;
+}
 
 // Fixed reduction tiles: HB_TILE_ROWS consecutive GLOBAL rows, never crossing a segment boundary.
 // Sums over rows are always formed tile by tile in this order, so the result does not depend on

@@ -16,8 +16,7 @@
 
 struct HbIceEpi {
     const double* __restrict__ r;
-    double* __restrict__ exch;
-    unsigned long long* wmax_slot;  // bits of a non-negative double
+    unsigned long long* wmax_slot;  // bits of a non-negative double (slot n + rank of the local exchange vector)
     const int64_t* __restrict__ seg_off;
     const int32_t* __restrict__ seg_done;
     int nseg;
@@ -32,10 +31,13 @@ struct HbIceEpi {
         }
         return seg_done[lo] == 0;
     }
-    __device__ __forceinline__ void row(int64_t g, double t, double m) {
+    __device__ __forceinline__ void row(int64_t g, double t, double m, int lane, const HbPeerOut& peer) {
         const double rg = r[g];
-        exch[g] = rg * t;
+        peer.store(g, rg * t, lane);
         wmax = fmax(wmax, rg * m);  // NaN-ignoring, like np.any(W.data > 1e100)
+    }
+    __device__ __forceinline__ double local_max() const {
+        return __longlong_as_double((long long)atomicAdd(wmax_slot, 0ull));
     }
     __device__ __forceinline__ void warp_done() const {
         if (wmax > 0.0) atomicMax(wmax_slot, (unsigned long long)__double_as_longlong(wmax));
@@ -283,15 +285,24 @@ int hb_dev_ice_spmv(hb_csr* h, double* d_exch, int rank, int world, void* stream
     HB_REQUIRE(h != nullptr && h->state_ready, "call hb_dev_ice_begin first");
     HB_REQUIRE(world >= 1 && world <= 64 && rank >= 0 && rank < world, "bad rank/world");
     cudaStream_t s = pick_stream(h, stream);
-    if (d_exch == nullptr) d_exch = h->d_exch;
-    if (world > 1)
-        HB_CUDA(cudaMemsetAsync(d_exch, 0, sizeof(double) * (size_t)(h->n_cols + world), s));
-    else
-        HB_CUDA(cudaMemsetAsync(d_exch + h->n_cols, 0, sizeof(double), s));
-    if (h->n_rows == 0) return HB_OK;
+    HbPeerOut po;
+    if (h->peer) {
+        // peer mode: rows go straight into every rank's replica (buffer seq & 1); only the local maximum slot is reset
+        HB_REQUIRE(world == h->world && rank == h->rank, "rank/world differ from hb_peer_export");
+        po = hb_next_out(h, nullptr);
+        d_exch = hb_sym_buf(h, (int)(po.seq & 1ull));
+        HB_CUDA(cudaMemsetAsync(d_exch + h->n_cols + rank, 0, sizeof(double), s));
+    } else {
+        if (d_exch == nullptr) d_exch = h->d_exch;
+        if (world > 1)
+            HB_CUDA(cudaMemsetAsync(d_exch, 0, sizeof(double) * (size_t)(h->n_cols + world), s));
+        else
+            HB_CUDA(cudaMemsetAsync(d_exch + h->n_cols, 0, sizeof(double), s));
+        if (h->n_rows == 0) return HB_OK;
+        po = hb_next_out(h, d_exch);
+    }
     HbIceEpi epi;
     epi.r = h->d_r;
-    epi.exch = d_exch;
     epi.wmax_slot = reinterpret_cast<unsigned long long*>(d_exch + h->n_cols + rank);
     epi.seg_off = h->d_seg_off;
     epi.seg_done = h->d_seg_done;
@@ -301,7 +312,7 @@ int hb_dev_ice_spmv(hb_csr* h, double* d_exch, int rank, int world, void* stream
     int p = h->spmv_parity;
     h->spmv_parity ^= 1;
     hb_spmv_kernel<HbIceEpi, true><<<hb_spmv_grid(h->n_rows), HB_SPMV_THREADS, 0, s>>>(
-        h->d_indptr, h->d_indices, h->d_data, h->n_rows, h->row0, h->d_r, h->d_row_counter, p, h->d_status, epi);
+        h->d_indptr, h->d_indices, h->d_data, h->n_rows, h->row0, h->d_r, h->d_row_counter, p, h->d_status, epi, po);
     HB_LAUNCH_CHECK();
     return HB_OK;
 }
@@ -309,7 +320,15 @@ int hb_dev_ice_spmv(hb_csr* h, double* d_exch, int rank, int world, void* stream
 int hb_dev_ice_update(hb_csr* h, const double* d_exch, int world, double tol, void* stream) {
     HB_REQUIRE(h != nullptr && h->state_ready, "call hb_dev_ice_begin first");
     cudaStream_t s = pick_stream(h, stream);
-    if (d_exch == nullptr) d_exch = h->d_exch;
+    if (h->peer) {
+        // wait for every rank's arrival flag of the exchange just issued, then read the local replica
+        const int p = (int)(h->peer_seq & 1ull);
+        d_exch = hb_sym_buf(h, p);
+        hb_peer_wait_kernel<<<1, 32, 0, s>>>(hb_sym_flags(h, p), h->peer_seq, h->world, h->d_status, nullptr);
+        HB_LAUNCH_CHECK();
+    } else if (d_exch == nullptr) {
+        d_exch = h->d_exch;
+    }
     if (h->n_tiles == 0) return HB_OK;
     hb_ice_reduce_kernel<<<h->n_tiles, 256, 0, s>>>(d_exch, h->d_tile_row0, h->d_tile_len, h->d_tile_seg,
                                                      h->d_seg_tile0, h->nseg, h->d_seg_done, h->d_tile_sum,
@@ -395,7 +414,7 @@ int hb_ice_run(hb_csr* h, int max_iter, double tol, double* bias_out, int32_t* i
     bool stop = false;
     for (int k = 0; k < max_iter && !stop; ++k) {
         rc = hb_dev_ice_spmv(h, nullptr, h->rank, h->world, nullptr);
-        if (rc == HB_OK && h->world > 1) {
+        if (rc == HB_OK && h->world > 1 && !h->peer) {
             // the one exchange of the iteration: marginals + per-rank maxima, summed over the ranks
             if (h->allreduce(h->comm_ctx, h->d_exch, h->n_cols + h->world, (void*)h->stream) != 0) {
                 hb_set_error("collective callback failed");
@@ -420,6 +439,10 @@ int hb_ice_run(hb_csr* h, int max_iter, double tol, double* bias_out, int32_t* i
     if (e != cudaSuccess) return hb_cuda_fail(e, "ICE loop", __FILE__, __LINE__);
     int32_t st[HB_ST_WORDS];
     HB_CUDA(cudaMemcpy(st, h->d_status, sizeof(st), cudaMemcpyDeviceToHost));
+    if (st[HB_ST_OVERFLOW] == 2) {
+        hb_set_error("peer exchange timed out: a rank did not publish its rows");
+        return HB_ERR_CUDA;
+    }
     if (st[HB_ST_OVERFLOW]) {
         hb_set_error("matrix correction is producing extremely large values (> 1e100)");
         return HB_ERR_OVERFLOW_ITER;

@@ -26,6 +26,7 @@
 #endif
 #define HB_TILE_ROWS 1024       // fixed reduction tile (rows) -> rank-count independent sums
 #define HB_MAX_SEG 4096
+#define HB_MAX_PEERS 8          // peer-store exchange: ranks of one NVLink domain
 
 extern std::atomic<uint64_t> g_hb_launches;
 void hb_set_error(const char* fmt, ...);
@@ -72,6 +73,14 @@ struct hb_csr {
     hb_allreduce_fn allreduce = nullptr;
     void* comm_ctx = nullptr;
 
+    // peer-store exchange (hb_peer_export / hb_peer_attach): symmetric region = 2 x (exchange vector | flags)
+    bool peer = false;
+    void* d_sym = nullptr;                          // this rank's region (cudaMalloc, exported through CUDA IPC)
+    void* peer_base[HB_MAX_PEERS] = {nullptr};      // every rank's region mapped here (own entry = d_sym)
+    size_t sym_buf_bytes = 0, sym_flag_off = 0;     // layout: buf p at p*sym_buf_bytes ; flags p at sym_flag_off + p*512
+    unsigned long long peer_seq = 0;                // exchange sequence number (monotonic)
+    unsigned int* d_done = nullptr;                 // ticket counter of the publishing SpMV
+
     // segments (independent diagonal blocks) and fixed reduction tiles over GLOBAL rows
     int nseg = 1;
     std::vector<int64_t> seg_off;      // nseg+1
@@ -114,6 +123,12 @@ int hb_ensure_state(hb_csr* h);
 void hb_free_state(hb_csr* h);
 int hb_use_device(const hb_csr* h);
 int hb_spmv_grid(int64_t n_rows);
+void hb_peer_release(hb_csr* h);
+// exchange buffer p (0/1) of this rank's symmetric region and its flag array
+static inline double* hb_sym_buf(const hb_csr* h, int p) { return (double*)((unsigned char*)h->d_sym + (size_t)p * h->sym_buf_bytes); }
+static inline unsigned long long* hb_sym_flags(const hb_csr* h, int p) {
+    return (unsigned long long*)((unsigned char*)h->d_sym + h->sym_flag_off + (size_t)p * 512);
+}
 
 // ---- device helpers ---------------------------------------------------------
 __device__ __forceinline__ int4 hb_ldg_stream_i4(const int32_t* p) {

@@ -25,6 +25,7 @@ enum {
     SC_XMIN = 7,   // min(x) (breakdown check)
     SC_A = 8,      // rescale: sum of (A+eps I) o (x x^T)
     SC_B = 9,      // rescale: sum of (A+eps I)
+    SC_ERR = 10,   // set by hb_peer_wait_kernel on a timeout
     SC_WORDS = 16
 };
 
@@ -397,22 +398,29 @@ int kr_launch(KrCtx& c, F f) {
 // out = a o ((A + eps I) u) + b o c  over the block's rows, assembled over the ranks
 int kr_spmv(KrCtx& c, const double* u, const double* a, const double* b, const double* cc, double* out, double eps) {
     hb_csr* h = c.h;
-    if (h->world > 1) HB_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * (size_t)h->n_cols, c.s));
-    if (h->n_rows > 0) {
+    if (h->world > 1 && !h->peer) HB_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * (size_t)h->n_cols, c.s));
+    if (h->n_rows > 0 || h->peer) {
         HbAffineEpi epi;
         epi.u = u;
         epi.a = a;
         epi.b = b;
         epi.c = cc;
-        epi.out = out;
         epi.eps = eps;
+        HbPeerOut po = hb_next_out(h, out);
         int p = h->spmv_parity;
         h->spmv_parity ^= 1;
         hb_spmv_kernel<HbAffineEpi, false><<<hb_spmv_grid(h->n_rows), HB_SPMV_THREADS, 0, c.s>>>(
-            h->d_indptr, h->d_indices, h->d_data, h->n_rows, h->row0, u, h->d_row_counter, p, nullptr, epi);
+            h->d_indptr, h->d_indices, h->d_data, h->n_rows, h->row0, u, h->d_row_counter, p, nullptr, epi, po);
         HB_LAUNCH_CHECK();
+        if (h->peer) {
+            // rows were stored into every replica over NVLink: wait for all arrival flags, then take the local copy
+            const int pb = (int)(po.seq & 1ull);
+            hb_peer_wait_kernel<<<1, 32, 0, c.s>>>(hb_sym_flags(h, pb), po.seq, h->world, nullptr, c.sc + SC_ERR);
+            HB_LAUNCH_CHECK();
+            HB_CUDA(cudaMemcpyAsync(out, hb_sym_buf(h, pb), sizeof(double) * (size_t)h->n_cols, cudaMemcpyDeviceToDevice, c.s));
+        }
     }
-    if (h->world > 1) {
+    if (h->world > 1 && !h->peer) {
         if (h->allreduce(h->comm_ctx, out, h->n_cols, (void*)c.s) != 0) {
             hb_set_error("collective callback failed");
             return HB_ERR_CUDA;
@@ -424,6 +432,10 @@ int kr_spmv(KrCtx& c, const double* u, const double* a, const double* b, const d
 int kr_read_scalars(KrCtx& c) {
     HB_CUDA(cudaMemcpyAsync(c.h_sc, c.sc, sizeof(double) * SC_WORDS, cudaMemcpyDeviceToHost, c.s));
     HB_CUDA(cudaStreamSynchronize(c.s));
+    if (c.h_sc[SC_ERR] != 0.0) {
+        hb_set_error("peer exchange timed out: a rank did not publish its rows");
+        return HB_ERR_CUDA;
+    }
     return HB_OK;
 }
 
@@ -450,12 +462,16 @@ int hb_dev_spmv(hb_csr* h, const double* d_u, double eps, const double* d_a, con
     epi.a = d_a;
     epi.b = d_b;
     epi.c = d_c;
-    epi.out = d_out;
     epi.eps = eps;
+    HbPeerOut po;
+    memset(&po, 0, sizeof(po));
+    po.world = 1;
+    po.out[0] = d_out;
+    po.n = h->n_cols;
     int p = h->spmv_parity;
     h->spmv_parity ^= 1;
     hb_spmv_kernel<HbAffineEpi, false><<<hb_spmv_grid(h->n_rows), HB_SPMV_THREADS, 0, s>>>(
-        h->d_indptr, h->d_indices, h->d_data, h->n_rows, h->row0, d_u, h->d_row_counter, p, nullptr, epi);
+        h->d_indptr, h->d_indices, h->d_data, h->n_rows, h->row0, d_u, h->d_row_counter, p, nullptr, epi, po);
     HB_LAUNCH_CHECK();
     return HB_OK;
 }

@@ -13,6 +13,8 @@
 // rows (Hi-C rows range from a handful to tens of thousands of entries) balance out.
 // The constants were chosen by the sweep recorded in profiles/r1_spmv_variant_sweep.txt.
 #pragma once
+#include <cstring>
+
 #include "hb_internal.cuh"
 
 // Row dot product, lane-strided: lane L takes entries s+L, s+L+32, ...  Every load instruction of the warp covers
@@ -73,15 +75,70 @@ __device__ __forceinline__ void hb_row_dot(const int32_t* __restrict__ idx, cons
     if (WANT_MAX) max_out = hb_warp_max(mx);
 }
 
+// Where a row's result goes.  Single GPU / host-collective mode: world == 1 and out[0] is the local vector.
+// Peer mode (hb_peer_attach): out[q] is rank q's replica of the exchange vector, mapped into this process through
+// CUDA IPC; lane q of the warp stores the row's value straight into it over NVLink, so the transfer of a row
+// overlaps the streaming of the next rows and no collective is launched.  When its last warp has finished, the
+// kernel publishes the per-rank maximum and an arrival flag (sequence number) in every replica; consumers wait on
+// the flags with hb_peer_wait_kernel.  Ordering: data stores -> __threadfence_system -> atomic ticket; the warp
+// that draws the last ticket -> __threadfence_system -> flag stores (the "last block" pattern at system scope).
+struct HbPeerOut {
+    double* out[HB_MAX_PEERS];
+    unsigned long long* flag[HB_MAX_PEERS];  // flag[q][rank] = seq   (NULL in non-peer mode)
+    unsigned int* done;                      // local ticket counter
+    unsigned long long seq;
+    int64_t n;                               // slot n + rank of every replica receives this rank's maximum
+    int world, rank, publish;
+    __device__ __forceinline__ void store(int64_t g, double v, int lane) const {
+        if (lane < world) out[lane][g] = v;
+    }
+};
+
+__device__ __forceinline__ void hb_st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long hb_ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// One warp: wait until every rank's arrival flag has reached `seq` (with a ~4 s guard so that a failed peer cannot
+// hang the GPU: on timeout the status words / err flag are set and every later kernel of the loop returns at once).
+static __global__ void hb_peer_wait_kernel(const unsigned long long* __restrict__ flags, unsigned long long seq, int world,
+                                    int32_t* status, double* err_flag) {
+    const int lane = threadIdx.x;
+    if (status != nullptr && status[HB_ST_ALL_DONE] != 0) return;  // converged: the producers returned early too
+    bool ok = true;
+    if (lane < world) {
+        const long long t0 = clock64();
+        while (hb_ld_acquire_sys(flags + lane) < seq) {
+            if (clock64() - t0 > 8000000000LL) {
+                ok = false;
+                break;
+            }
+            __nanosleep(200);
+        }
+    }
+    if (!__all_sync(0xffffffffu, ok) && lane == 0) {
+        if (status != nullptr) {
+            status[HB_ST_OVERFLOW] = 2;  // 2 = peer exchange timed out
+            status[HB_ST_ALL_DONE] = 1;
+        }
+        if (err_flag != nullptr) *err_flag = 1.0;
+    }
+}
+
 // Epi must provide:
-//   __device__ bool active(int64_t global_row) const;                 // skip rows of finished segments
-//   __device__ void row(int64_t global_row, double t, double m);      // lane 0 only
-//   __device__ void warp_done();                                      // lane 0 only, once per warp
+//   __device__ bool active(int64_t global_row) const;                                  // skip rows of finished segments
+//   __device__ void row(int64_t global_row, double t, double m, int lane, peer);       // all lanes, t and m warp-uniform
+//   __device__ void warp_done();                                                       // lane 0 only, once per warp
+//   __device__ double local_max() const;                                               // last warp: value for slot n+rank
 template <class Epi, bool WANT_MAX>
 __global__ void __launch_bounds__(HB_SPMV_THREADS, HB_SPMV_CTAS_PER_SM)
 hb_spmv_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
                int64_t n_rows, int64_t row0, const double* __restrict__ u, unsigned long long* counters, int parity,
-               const int32_t* __restrict__ status, Epi epi) {
+               const int32_t* __restrict__ status, Epi epi, HbPeerOut peer) {
     if (status != nullptr && status[HB_ST_ALL_DONE] != 0) return;
     const int lane = threadIdx.x & 31;
     const int64_t gwarp = (int64_t)blockIdx.x * (HB_SPMV_THREADS / 32) + (threadIdx.x >> 5);
@@ -104,13 +161,56 @@ hb_spmv_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ i
             if (row < n_rows && epi.active(row0 + row)) {
                 double t, m = 0.0;
                 hb_row_dot<WANT_MAX>(idx, val, u, s, e, lane, t, m);
-                if (lane == 0) epi.row(row0 + row, t, m);
+                epi.row(row0 + row, t, m, lane, peer);
             }
         }
         nxt = __shfl_sync(0xffffffffu, nxt, 0);
         batch = nwarps * HB_ROWS_PER_GRAB + (int64_t)nxt;
     }
     if (lane == 0) epi.warp_done();
+    if (peer.publish) {
+        int last = 0;
+        if (lane == 0) {
+            __threadfence_system();
+            last = (atomicAdd(peer.done, 1u) == (unsigned int)(nwarps - 1)) ? 1 : 0;
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+            if (lane == 0) *peer.done = 0u;
+            __threadfence_system();
+            if (lane < peer.world) {
+                if (WANT_MAX) peer.out[lane][peer.n + peer.rank] = epi.local_max();
+                __threadfence_system();
+                hb_st_release_sys(peer.flag[lane] + peer.rank, peer.seq);
+            }
+        }
+    }
+}
+
+// Destination of the next SpMV on this handle: the local vector, or (peer mode) buffer seq&1 of every replica.
+static inline HbPeerOut hb_next_out(hb_csr* h, double* local_out) {
+    HbPeerOut po;
+    memset(&po, 0, sizeof(po));
+    po.n = h->n_cols;
+    po.rank = h->rank;
+    if (!h->peer) {
+        po.world = 1;
+        po.out[0] = local_out;
+        po.publish = 0;
+        return po;
+    }
+    const unsigned long long seq = ++h->peer_seq;
+    const int p = (int)(seq & 1ull);
+    po.world = h->world;
+    po.publish = 1;
+    po.seq = seq;
+    po.done = h->d_done;
+    for (int q = 0; q < h->world; ++q) {
+        unsigned char* base = (unsigned char*)h->peer_base[q];
+        po.out[q] = (double*)(base + (size_t)p * h->sym_buf_bytes);
+        po.flag[q] = (unsigned long long*)(base + h->sym_flag_off + (size_t)p * 512);
+    }
+    return po;
 }
 
 // out[g] = a_g * (t + eps * u_g) + b_g * c_g      (Knight-Ruiz: w = x o (A (x o p)) + v o p ; v = x o (A x))
@@ -119,14 +219,14 @@ struct HbAffineEpi {
     const double* __restrict__ a;
     const double* __restrict__ b;
     const double* __restrict__ c;
-    double* __restrict__ out;
     double eps;
     __device__ __forceinline__ bool active(int64_t) const { return true; }
-    __device__ __forceinline__ void row(int64_t g, double t, double) const {
+    __device__ __forceinline__ void row(int64_t g, double t, double, int lane, const HbPeerOut& peer) const {
         double v = t + eps * u[g];
         if (a != nullptr) v *= a[g];
         if (b != nullptr && c != nullptr) v += b[g] * c[g];
-        out[g] = v;
+        peer.store(g, v, lane);
     }
     __device__ __forceinline__ void warp_done() const {}
+    __device__ __forceinline__ double local_max() const { return 0.0; }
 };

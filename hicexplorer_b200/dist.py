@@ -82,3 +82,32 @@ def attach_comm(dev, rank, world, group=None):
     fn, keep = make_allreduce_callback(group)
     _lib.check(_lib.lib().hb_set_comm(dev.handle, int(rank), int(world), ctypes.cast(fn, ctypes.c_void_p), None))
     return keep
+
+
+def attach_peer(dev, rank, world, group=None):
+    """Switch a DeviceCSR row block to the peer-store exchange: the SpMV epilogue writes each row straight into every
+    rank's replica of the exchange vector over NVLink (CUDA IPC mappings), no collective in the loop.  Needs one
+    process per GPU inside one NVLink/P2P domain and world <= 8.  Returns True on success; on failure (no peer access,
+    IPC unavailable) the handle is left untouched and the caller should fall back to attach_comm()."""
+    import torch
+    import torch.distributed as dist
+    L = _lib.lib()
+    ok = torch.ones(1, dtype=torch.int32, device="cuda")
+    handle = (ctypes.c_ubyte * 64)()
+    rc = L.hb_peer_export(dev.handle, int(rank), int(world), ctypes.cast(handle, ctypes.c_void_p))
+    if rc != 0:
+        ok[0] = 0
+    mine = torch.tensor(list(handle), dtype=torch.uint8, device="cuda")
+    gathered = [torch.empty(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+    dist.all_gather(gathered, mine, group=group)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    if int(ok.item()) == 1:
+        blob = torch.cat(gathered).cpu().numpy().tobytes()
+        rc = L.hb_peer_attach(dev.handle, blob)
+        if rc != 0:
+            ok[0] = 0
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)   # also the barrier the protocol needs after attaching
+    if int(ok.item()) != 1:
+        # leave peer mode everywhere so that all ranks take the same fallback
+        return False
+    return True

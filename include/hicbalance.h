@@ -116,6 +116,18 @@ HB_API int hb_csr_keep_cis(hb_csr* h);
 typedef int (*hb_allreduce_fn)(void* ctx, void* d_buf, int64_t count, void* stream);
 HB_API int hb_set_comm(hb_csr* h, int rank, int world, hb_allreduce_fn fn, void* ctx);
 
+/* Peer-store exchange (alternative to the callback; one process per GPU inside one NVLink domain, world <= 8).
+ * The SpMV epilogue stores every row's result directly into all ranks' replicas of the exchange vector (P2P stores
+ * through CUDA IPC mappings), then publishes an arrival flag; no collective is launched in the loop.
+ *   hb_peer_export: allocate this rank's symmetric region and return its 64-byte cudaIpcMemHandle_t.
+ *   hb_peer_attach: all_handles = world x 64 bytes in rank order (gathered by the host with any collective);
+ *                   maps the peers' regions.  The host must barrier once after every rank has attached.
+ * Afterwards hb_ice_run / hb_kr_run / hb_dev_ice_spmv / hb_dev_ice_update use the region (pass d_exch = NULL) and the
+ * host must NOT all-reduce.  hb_peer_active() tells which mode a handle is in. */
+HB_API int hb_peer_export(hb_csr* h, int rank, int world, void* ipc_handle_out);
+HB_API int hb_peer_attach(hb_csr* h, const void* all_handles);
+HB_API int hb_peer_active(const hb_csr* h);
+
 /* ---- pre-filter (device) ---------------------------------------------------
  * hb_scrub: NaN -> 0 and +-Inf -> 0 in the stored values
  *   (utilities.py:111-128 via hicCorrectMatrix.py:624-625; iterativeCorrection.py:28-30).

@@ -54,6 +54,29 @@ def main():
               np.array_equal(gotp["bias"], refp["bias"]) and np.array_equal(gotp["iterations"], refp["iterations"]))
         check("perchr ICE sharded: matrix identical", gotp["matrix"].nnz == refp["matrix"].nnz and
               np.allclose(gotp["matrix"].data, refp["matrix"].data, rtol=1e-12, atol=0))
+    # peer-store exchange (NVLink P2P stores from the SpMV epilogue instead of the NCCL callback)
+    from hicexplorer_b200.dist import attach_peer, nnz_balanced_partition
+    from hicexplorer_b200.store import DeviceCSR
+    ice_in = None
+    if True:
+        from oracle import ice_oracle
+        ice_in = ice_oracle.correct_ice_pipeline(full, -1.5, 5.0, max_iter=1)["ice_input"]
+        ice_in.sort_indices()
+        bounds = nnz_balanced_partition(ice_in.indptr, world)
+        with DeviceCSR.from_scipy(ice_in, device=local, row_range=(int(bounds[rank]), int(bounds[rank + 1]))) as dv:
+            peer_ok = attach_peer(dv, rank, world)
+            check("peer exchange: attach (CUDA IPC + P2P)", peer_ok)
+            if peer_ok:
+                pb, pit, pdev = dv.ice(500, 1e-5)
+                px, pouter, pmv, pres = dv.kr()
+                if rank == 0:
+                    with DeviceCSR.from_scipy(ice_in, device=local) as d1:
+                        b1, it1, _ = d1.ice(500, 1e-5)
+                        x1, o1, mv1, _ = d1.kr()
+                    check("peer exchange: ICE bias bit-identical to 1 GPU, %d iterations" % int(it1[0]),
+                          np.array_equal(pb, b1) and int(pit[0]) == int(it1[0]))
+                    check("peer exchange: KR x bit-identical to 1 GPU, %d mat-vecs" % mv1, np.array_equal(px, x1) and pmv == mv1)
+        dist.barrier()
     kr = kr_pipeline_sharded(full, rescale=True)
     if rank == 0:
         kref = kr_pipeline(full, rescale=True, want_matrix=False, device=local)
@@ -72,8 +95,7 @@ def main():
                             for c in range(len(off) - 1) for i in range(off[c], off[c + 1])]
         ma._index_intervals()
         ma.save(src)
-    dist.barrier()
-    dist.destroy_process_group()
+    dist.barrier()          # the CLI reuses this process group and destroys it when it is done
     out = os.path.join(tmp, "mg_out.cool")
     cli(["correct", "-m", src, "-o", out, "--correctionMethod", "ICE", "--filterThreshold", "-1.5", "5"])
     if rank == 0:
