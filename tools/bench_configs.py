@@ -45,7 +45,7 @@ def main():
     import torch
     import torch.distributed as dist
     from hicexplorer_b200 import _lib
-    from hicexplorer_b200.dist import attach_comm, nnz_balanced_partition
+    from hicexplorer_b200.dist import attach_comm, attach_peer, nnz_balanced_partition
     from hicexplorer_b200.store import DeviceCSR
     L = _lib.lib()
     check = _lib.check
@@ -151,7 +151,13 @@ def main():
             bounds = nnz_balanced_partition(np.concatenate([[0], np.cumsum(counts.cpu().numpy())]), world)
             del counts
             dev = DeviceCSR.synthetic(bins, row_range=(int(bounds[rank]), int(bounds[rank + 1])), device=local, **kw)
-        keep = attach_comm(dev, rank, world) if world > 1 else None
+        keep = None
+        peer_mode = False
+        if world > 1:
+            if os.environ.get("HB_EXCHANGE", "peer") == "peer":
+                peer_mode = attach_peer(dev, rank, world)
+            if not peer_mode:
+                keep = attach_comm(dev, rank, world)
         torch.cuda.synchronize()
         t_gen = time.time() - t0
         nnz_total = allsum(dev.nnz)
@@ -173,7 +179,8 @@ def main():
                                 "ms_per_iteration": t_run * 1e3 / max(int(iters[0]), 1),
                                 "nnz_per_s": nnz_total * int(iters[0]) / t_run}})
         out.update({"workload": bench.workload_name(wl, bins, kw), "bins": n, "nnz": nnz_total, "generated_in_s": t_gen,
-                    "communication": "1 sum-allreduce of %d fp64 per mat-vec/iteration" % n if world > 1 else "none"})
+                    "communication": ("none" if world == 1 else "peer stores into every replica over NVLink (no collective)"
+                                      if peer_mode else "1 NCCL sum-allreduce of %d fp64 per mat-vec/iteration" % n)})
         dev.close()
         del keep
     if rank == 0:
