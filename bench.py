@@ -18,7 +18,6 @@ import argparse
 import ctypes
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -212,8 +211,10 @@ def run_reference(args):
     method, bins, kw = synth_kwargs(args.workload)
     line = {"impl": "reference", "metric": "ICE stored entries processed per second (nnz x iterations / s)",
             "value": base["value"], "unit": "nnz/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": None, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": workload_name(args.workload, bins, kw)},
+            "ms_per_step": 1e3 / base["iters_per_s"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload, bins, kw),
+                       "step": "one ICE iteration of the reference algorithm on the bounded sample described in cpu_baseline.sample"},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))

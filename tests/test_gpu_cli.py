@@ -149,3 +149,43 @@ def test_correct_matrix_ICE_cool_and_perchr(tmp_path, gm12878):
     blk = ice_oracle.scrub(ice_oracle.select_bins(full, ids))
     refb = ice_oracle.ice(blk, max_iter=300)
     np.testing.assert_allclose(cf[ids], refb["bias"], rtol=1e-9)
+
+
+def test_skip_diagonal_and_sequenced_count_cutoff(tmp_path, gm12878):
+    """--skipDiagonal (hicCorrectMatrix.py:648-649) and --sequencedCountCutoff (:675-686) against the oracle run with
+    the same sequence of host operations the reference performs."""
+    g = gm12878
+    full = full_from_pixels(g)
+    n = full.shape[0]
+    rng = np.random.default_rng(7)
+    coverage = rng.uniform(0.3, 1.0, n)
+    ma = hiCMatrix()
+    ma.matrix = full
+    off = g["chrom_offset"]
+    ma.cut_intervals = [(str(c + 1), int((i - off[c]) * 2500000), int((i - off[c] + 1) * 2500000), float(coverage[i]))
+                        for c in range(len(off) - 1) for i in range(off[c], off[c + 1])]
+    ma._index_intervals()
+    src = str(tmp_path / "in.h5")
+    ma.save(src)
+    out = str(tmp_path / "out.h5")
+    main("correct --matrix {} --correctionMethod ICE --filterThreshold -1.5 5 --skipDiagonal --sequencedCountCutoff 0.5 "
+         "--iterNum 300 --outFileName {}".format(src, out).split())
+    f, m = _read_h5(out)
+    # oracle: zero bins -> scrub -> diagonal removed -> MAD mask -> coverage mask -> ICE
+    keep1 = np.setdiff1d(np.arange(n), ice_oracle.zero_bins(full))
+    st1 = ice_oracle.scrub(ice_oracle.select_bins(full, keep1)).tolil()
+    st1.setdiag(0)
+    st1 = st1.tocsr()
+    st1.eliminate_zeros()
+    outl = ice_oracle.outlier_bins(st1, -1.5, 5.0)
+    keep2 = np.delete(np.arange(st1.shape[0]), outl)
+    low_cov = coverage[keep1[keep2]] < 0.5
+    kept = keep1[keep2][~low_cov]
+    ref = ice_oracle.ice(ice_oracle.select_bins(st1, keep2[~low_cov]), max_iter=300)
+    cf = f["correction_factors"].read()
+    assert np.array_equal(np.flatnonzero(~np.isnan(cf)), kept)
+    np.testing.assert_allclose(cf[kept], ref["bias"], rtol=1e-9)
+    assert m.diagonal().sum() == 0                                   # the diagonal is gone from the output
+    up = sparse.triu(ref["matrix"], 0, format="csr")
+    up.eliminate_zeros()
+    np.testing.assert_allclose(np.sort(m.data), np.sort(up.data), rtol=1e-8)
