@@ -79,6 +79,7 @@ SIGNATURES = {
     "hb_set_segments": (c_int, [vp, c_int, vp]),
     "hb_csr_keep_cis": (c_int, [vp]),
     "hb_scrub": (c_int, [vp, vp]),
+    "hb_csr_pack_values": (c_int, [vp, P(c_int)]),
     "hb_row_stats": (c_int, [vp, vp, vp]),
     "hb_mad_filter": (c_int, [vp, c_dbl, c_dbl, vp, vp, vp, vp]),
     "hb_csr_compact": (c_int, [vp, vp]),

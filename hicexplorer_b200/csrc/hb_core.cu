@@ -202,6 +202,7 @@ int hb_csr_destroy(hb_csr* h) {
         cudaFree(h->d_data);
     }
     cudaFree(h->d_tile_slab);
+    cudaFree(h->d_pack);
     hb_peer_release(h);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;

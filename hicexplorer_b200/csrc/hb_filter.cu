@@ -393,6 +393,7 @@ static int hb_compact_impl(hb_csr* h, const int32_t* d_newid, int64_t new_n, int
         cudaFree(h->d_indices);
         cudaFree(h->d_data);
     }
+    hb_drop_pack(h);
     h->owns_csr = true;
     h->phase = 0;
     h->d_indptr = d_new_indptr;
@@ -448,13 +449,77 @@ hb_symmetry_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// lossless narrow copy of the values for the streaming kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void hb_pack_probe_kernel(const double* __restrict__ data, int64_t nnz, unsigned int* flags) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    bool not_u16 = false, not_f32 = false;
+    for (; i < nnz; i += stride) {
+        const double v = data[i];
+        if (!(v >= 0.0 && v <= 65535.0 && v == floor(v))) not_u16 = true;
+        if (!((double)(float)v == v)) not_f32 = true;  // also false for NaN: a NaN never packs
+    }
+    if (__any_sync(0xffffffffu, not_u16) && (threadIdx.x & 31) == 0) atomicOr(flags + 0, 1u);
+    if (__any_sync(0xffffffffu, not_f32) && (threadIdx.x & 31) == 0) atomicOr(flags + 1, 1u);
+}
+
+template <typename VT>
+__global__ void hb_pack_convert_kernel(const double* __restrict__ in, VT* __restrict__ out, int64_t nnz) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < nnz; i += stride) out[i] = (VT)in[i];
+}
+
+void hb_drop_pack(hb_csr* h) {
+    cudaFree(h->d_pack);
+    h->d_pack = nullptr;
+    h->pack_kind = 0;
+}
+
 extern "C" {
+
+int hb_csr_pack_values(hb_csr* h, int* kind_out) {
+    HB_REQUIRE(h != nullptr, "null handle");
+    int rc = hb_ensure_state(h);
+    if (rc) return rc;
+    rc = hb_use_device(h);
+    if (rc) return rc;
+    hb_drop_pack(h);
+    cudaStream_t s = h->stream;
+    if (kind_out) *kind_out = 0;
+    if (h->nnz == 0) return HB_OK;
+    unsigned int* d_flags = reinterpret_cast<unsigned int*>(h->d_scalar_bits);
+    HB_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(unsigned int) * 2, s));
+    const double* src = h->d_data + h->phase;
+    hb_pack_probe_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(src, h->nnz, d_flags);
+    HB_LAUNCH_CHECK();
+    unsigned int flags[2] = {1, 1};
+    HB_CUDA(cudaMemcpyAsync(flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost, s));
+    HB_CUDA(cudaStreamSynchronize(s));
+    const int kind = !flags[0] ? 1 : (!flags[1] ? 2 : 0);
+    if (kind == 0) return HB_OK;
+    const size_t elt = kind == 1 ? sizeof(uint16_t) : sizeof(float);
+    HB_CUDA(cudaMalloc(&h->d_pack, elt * (size_t)(h->nnz + h->phase + 8) + 16));
+    HB_CUDA(cudaMemsetAsync(h->d_pack, 0, elt * 8, s));
+    if (kind == 1)
+        hb_pack_convert_kernel<uint16_t><<<HB_NUM_SMS * 8, 256, 0, s>>>(src, (uint16_t*)h->d_pack + h->phase, h->nnz);
+    else
+        hb_pack_convert_kernel<float><<<HB_NUM_SMS * 8, 256, 0, s>>>(src, (float*)h->d_pack + h->phase, h->nnz);
+    HB_LAUNCH_CHECK();
+    HB_CUDA(cudaStreamSynchronize(s));
+    h->pack_kind = kind;
+    if (kind_out) *kind_out = kind;
+    return HB_OK;
+}
 
 int hb_scrub(hb_csr* h, int64_t counts[2]) {
     HB_REQUIRE(h != nullptr, "null handle");
     int rc = hb_ensure_state(h);
     if (rc) return rc;
     cudaStream_t s = h->stream;
+    hb_drop_pack(h);  // the values may change
     HB_CUDA(cudaMemsetAsync(h->d_scalar_bits, 0, sizeof(unsigned long long) * 2, s));
     if (h->nnz > 0) {
         hb_scrub_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_data, h->nnz, h->d_scalar_bits);

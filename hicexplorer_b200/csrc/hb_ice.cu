@@ -308,11 +308,7 @@ int hb_dev_ice_spmv(hb_csr* h, double* d_exch, int rank, int world, void* stream
     epi.seg_done = h->d_seg_done;
     epi.nseg = h->nseg;
     epi.wmax = 0.0;
-    // the two row counters alternate between consecutive launches on this handle
-    int p = h->spmv_parity;
-    h->spmv_parity ^= 1;
-    hb_spmv_kernel<HbIceEpi, true><<<hb_spmv_grid(h->n_rows), HB_SPMV_THREADS, 0, s>>>(
-        h->d_indptr, h->d_indices, h->d_data, h->n_rows, h->row0, h->d_r, h->d_row_counter, p, h->d_status, epi, po);
+    hb_launch_spmv<HbIceEpi, true>(h, h->d_r, h->d_status, epi, po, s);
     HB_LAUNCH_CHECK();
     return HB_OK;
 }

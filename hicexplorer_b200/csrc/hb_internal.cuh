@@ -67,6 +67,10 @@ struct hb_csr {
     int64_t* d_indptr = nullptr;
     int32_t* d_indices = nullptr;
     double* d_data = nullptr;
+    // optional lossless narrow copy of the values for the streaming kernels (hb_csr_pack_values):
+    // 0 = none, 1 = uint16 (integer counts <= 65535), 2 = float (exactly representable).  Same entry indexing as d_data.
+    int pack_kind = 0;
+    void* d_pack = nullptr;
 
     // sharded runs: the one collective of the path is delegated to the host (torch.distributed / NCCL)
     int rank = 0, world = 1;
@@ -124,6 +128,7 @@ void hb_free_state(hb_csr* h);
 int hb_use_device(const hb_csr* h);
 int hb_spmv_grid(int64_t n_rows);
 void hb_peer_release(hb_csr* h);
+void hb_drop_pack(hb_csr* h);
 // exchange buffer p (0/1) of this rank's symmetric region and its flag array
 static inline double* hb_sym_buf(const hb_csr* h, int p) { return (double*)((unsigned char*)h->d_sym + (size_t)p * h->sym_buf_bytes); }
 static inline unsigned long long* hb_sym_flags(const hb_csr* h, int p) {
@@ -164,6 +169,17 @@ __device__ __forceinline__ double hb_ldg_stream_d1(const double* p) {
     double r;
     asm volatile(HB_STREAM_QUAL ".f64 %0, [%1];" : "=d"(r) : "l"(p));
     return r;
+}
+__device__ __forceinline__ double hb_ldg_stream_val(const double* p) { return hb_ldg_stream_d1(p); }
+__device__ __forceinline__ double hb_ldg_stream_val(const float* p) {
+    float r;
+    asm volatile(HB_STREAM_QUAL ".f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return (double)r;
+}
+__device__ __forceinline__ double hb_ldg_stream_val(const uint16_t* p) {
+    unsigned short r;
+    asm volatile(HB_STREAM_QUAL ".u16 %0, [%1];" : "=h"(r) : "l"(p));
+    return (double)r;
 }
 __device__ __forceinline__ double hb_warp_sum(double v) {
 #pragma unroll

@@ -407,10 +407,7 @@ int kr_spmv(KrCtx& c, const double* u, const double* a, const double* b, const d
         epi.c = cc;
         epi.eps = eps;
         HbPeerOut po = hb_next_out(h, out);
-        int p = h->spmv_parity;
-        h->spmv_parity ^= 1;
-        hb_spmv_kernel<HbAffineEpi, false><<<hb_spmv_grid(h->n_rows), HB_SPMV_THREADS, 0, c.s>>>(
-            h->d_indptr, h->d_indices, h->d_data, h->n_rows, h->row0, u, h->d_row_counter, p, nullptr, epi, po);
+        hb_launch_spmv<HbAffineEpi, false>(h, u, nullptr, epi, po, c.s);
         HB_LAUNCH_CHECK();
         if (h->peer) {
             // rows were stored into every replica over NVLink: wait for all arrival flags, then take the local copy
@@ -468,10 +465,7 @@ int hb_dev_spmv(hb_csr* h, const double* d_u, double eps, const double* d_a, con
     po.world = 1;
     po.out[0] = d_out;
     po.n = h->n_cols;
-    int p = h->spmv_parity;
-    h->spmv_parity ^= 1;
-    hb_spmv_kernel<HbAffineEpi, false><<<hb_spmv_grid(h->n_rows), HB_SPMV_THREADS, 0, s>>>(
-        h->d_indptr, h->d_indices, h->d_data, h->n_rows, h->row0, d_u, h->d_row_counter, p, nullptr, epi, po);
+    hb_launch_spmv<HbAffineEpi, false>(h, d_u, nullptr, epi, po, s);
     HB_LAUNCH_CHECK();
     return HB_OK;
 }

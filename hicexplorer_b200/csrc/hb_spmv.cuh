@@ -25,8 +25,8 @@
 // HB_SPMV_UNROLL independent entries per lane are in flight per step (3 x 16 loads); the tail runs in
 // predicated groups of 4 so short rows still overlap their loads.  There is no alignment requirement,
 // so the summation order does not depend on where a row starts.
-template <bool WANT_MAX>
-__device__ __forceinline__ void hb_row_dot(const int32_t* __restrict__ idx, const double* __restrict__ val,
+template <bool WANT_MAX, typename VT>
+__device__ __forceinline__ void hb_row_dot(const int32_t* __restrict__ idx, const VT* __restrict__ val,
                                            const double* __restrict__ u, int64_t s, int64_t e, int lane,
                                            double& sum_out, double& max_out) {
     constexpr int U = HB_SPMV_UNROLL;
@@ -39,7 +39,7 @@ __device__ __forceinline__ void hb_row_dot(const int32_t* __restrict__ idx, cons
 #pragma unroll
         for (int j = 0; j < U; ++j) c[j] = hb_ldg_stream_i1(idx + k + 32 * j);
 #pragma unroll
-        for (int j = 0; j < U; ++j) v[j] = hb_ldg_stream_d1(val + k + 32 * j);
+        for (int j = 0; j < U; ++j) v[j] = hb_ldg_stream_val(val + k + 32 * j);
 #pragma unroll
         for (int j = 0; j < U; ++j) g[j] = __ldg(u + c[j]);
 #pragma unroll
@@ -59,7 +59,7 @@ __device__ __forceinline__ void hb_row_dot(const int32_t* __restrict__ idx, cons
 #pragma unroll
         for (int j = 0; j < 4; ++j) c[j] = (k + 32 * j < e) ? hb_ldg_stream_i1(idx + k + 32 * j) : 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = (k + 32 * j < e) ? hb_ldg_stream_d1(val + k + 32 * j) : 0.0;
+        for (int j = 0; j < 4; ++j) v[j] = (k + 32 * j < e) ? hb_ldg_stream_val(val + k + 32 * j) : 0.0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) g[j] = (k + 32 * j < e) ? __ldg(u + c[j]) : 0.0;
 #pragma unroll
@@ -134,9 +134,9 @@ static __global__ void hb_peer_wait_kernel(const unsigned long long* __restrict_
 //   __device__ void row(int64_t global_row, double t, double m, int lane, peer);       // all lanes, t and m warp-uniform
 //   __device__ void warp_done();                                                       // lane 0 only, once per warp
 //   __device__ double local_max() const;                                               // last warp: value for slot n+rank
-template <class Epi, bool WANT_MAX>
+template <class Epi, bool WANT_MAX, typename VT>
 __global__ void __launch_bounds__(HB_SPMV_THREADS, HB_SPMV_CTAS_PER_SM)
-hb_spmv_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
+hb_spmv_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const VT* __restrict__ val,
                int64_t n_rows, int64_t row0, const double* __restrict__ u, unsigned long long* counters, int parity,
                const int32_t* __restrict__ status, Epi epi, HbPeerOut peer) {
     if (status != nullptr && status[HB_ST_ALL_DONE] != 0) return;
@@ -160,7 +160,7 @@ hb_spmv_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ i
             const int64_t row = batch + q;
             if (row < n_rows && epi.active(row0 + row)) {
                 double t, m = 0.0;
-                hb_row_dot<WANT_MAX>(idx, val, u, s, e, lane, t, m);
+                hb_row_dot<WANT_MAX, VT>(idx, val, u, s, e, lane, t, m);
                 epi.row(row0 + row, t, m, lane, peer);
             }
         }
@@ -211,6 +211,26 @@ static inline HbPeerOut hb_next_out(hb_csr* h, double* local_out) {
         po.flag[q] = (unsigned long long*)(base + h->sym_flag_off + (size_t)p * 512);
     }
     return po;
+}
+
+// Launch the SpMV over the handle's block with the narrowest lossless value array it has
+// (fp64 = the contract layout, 12 B/entry; uint16 / float copies made by hb_csr_pack_values: 6 / 8 B/entry).
+// The values are widened to fp64 before the first multiply, so results are bit-identical across layouts.
+template <class Epi, bool WANT_MAX>
+static inline void hb_launch_spmv(hb_csr* h, const double* u, const int32_t* status, const Epi& epi, const HbPeerOut& po,
+                                  cudaStream_t s) {
+    const int p = h->spmv_parity;  // the two row counters alternate between consecutive launches on this handle
+    h->spmv_parity ^= 1;
+    const int grid = hb_spmv_grid(h->n_rows);
+    if (h->pack_kind == 1)
+        hb_spmv_kernel<Epi, WANT_MAX, uint16_t><<<grid, HB_SPMV_THREADS, 0, s>>>(
+            h->d_indptr, h->d_indices, (const uint16_t*)h->d_pack, h->n_rows, h->row0, u, h->d_row_counter, p, status, epi, po);
+    else if (h->pack_kind == 2)
+        hb_spmv_kernel<Epi, WANT_MAX, float><<<grid, HB_SPMV_THREADS, 0, s>>>(
+            h->d_indptr, h->d_indices, (const float*)h->d_pack, h->n_rows, h->row0, u, h->d_row_counter, p, status, epi, po);
+    else
+        hb_spmv_kernel<Epi, WANT_MAX, double><<<grid, HB_SPMV_THREADS, 0, s>>>(
+            h->d_indptr, h->d_indices, h->d_data, h->n_rows, h->row0, u, h->d_row_counter, p, status, epi, po);
 }
 
 // out[g] = a_g * (t + eps * u_g) + b_g * c_g      (Knight-Ruiz: w = x o (A (x o p)) + v o p ; v = x o (A x))

@@ -54,6 +54,7 @@ def iterativeCorrection(matrix, v=None, M=50, tolerance=1e-5, verbose=False, dev
         if dev.symmetry_ratio() > 1e-10:
             raise ValueError("Please provide symmetric matrix!")
         log.info("starting iterative correction")
+        dev.pack_values()      # lossless narrow copy of integer counts for the streaming kernel; results unchanged
         try:
             if verbose:
                 bias, iters, deviation = _ice_verbose(dev, M, tolerance)

@@ -39,6 +39,7 @@ class kr_balancing(object):
         data = np.ascontiguousarray(data, dtype=np.float64)
         m = sparse.csr_matrix((data, indices, indptr), shape=(rows, cols))
         self._dev = DeviceCSR.from_scipy(m, device=device)
+        self._dev.pack_values()    # lossless narrow copy of integer counts for the mat-vec kernel; results unchanged
         self._x = None
         self.rescaled = False
         self.outer_iterations = 0

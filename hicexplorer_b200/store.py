@@ -157,6 +157,12 @@ class DeviceCSR(object):
         check(lib().hb_scrub(self._h, ptr(counts)))
         return int(counts[0]), int(counts[1])
 
+    def pack_values(self):
+        """Lossless narrow copy of the values for the streaming kernels; returns 0 (none), 1 (uint16) or 2 (float)."""
+        kind = ctypes.c_int()
+        check(lib().hb_csr_pack_values(self._h, ctypes.byref(kind)))
+        return kind.value
+
     def row_stats(self):
         n_rows = self.n_rows
         rs = np.empty(n_rows, dtype=np.float64)

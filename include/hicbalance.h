@@ -147,6 +147,12 @@ HB_API int hb_peer_active(const hb_csr* h);
  * hb_symmetry: the reference's criterion (iterativeCorrection.py:35):
  *   ratio = mean|M - M^T| / |mean M|; the caller raises when ratio > 1e-10. */
 HB_API int hb_scrub(hb_csr* h, int64_t counts[2]);
+/* Optional: build a LOSSLESS narrow copy of the stored values for the streaming kernels (ICE / KR mat-vecs):
+ * uint16 when every value is an integer count <= 65535 (kind 1, 6 B per entry streamed instead of 12), float when
+ * every value is exactly representable in fp32 (kind 2, 8 B), none otherwise (kind 0).  Values are widened to fp64
+ * before the first multiply, so every result is bit-identical to the fp64 layout.  The fp64 array stays the store of
+ * record (filter, emit, download); the copy is dropped whenever the values change (scrub, compaction). */
+HB_API int hb_csr_pack_values(hb_csr* h, int* kind_out);
 HB_API int hb_row_stats(hb_csr* h, double* row_sum, double* diag);
 HB_API int hb_mad_filter(hb_csr* h, double lo, double hi, uint8_t* mask_out, double* zscore_out,
                   double* median_out /*nseg*/, double* mad_out /*nseg*/);
