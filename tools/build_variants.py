@@ -8,6 +8,14 @@ sys.path.insert(0, ROOT)
 from hicexplorer_b200 import _build  # noqa: E402
 
 VARIANTS = {
+    "pk_u16_c3": {"HB_SPMV_UNROLL": 16, "HB_SPMV_CTAS_PER_SM": 3},
+    "pk_u24_c3": {"HB_SPMV_UNROLL": 24, "HB_SPMV_CTAS_PER_SM": 3},
+    "pk_u32_c2": {"HB_SPMV_UNROLL": 32, "HB_SPMV_CTAS_PER_SM": 2},
+    "pk_u20_c3": {"HB_SPMV_UNROLL": 20, "HB_SPMV_CTAS_PER_SM": 3},
+    "pk_u16_c4": {"HB_SPMV_UNROLL": 16, "HB_SPMV_CTAS_PER_SM": 4},
+    "pk_u12_c4": {"HB_SPMV_UNROLL": 12, "HB_SPMV_CTAS_PER_SM": 4},
+    "pk_u12_c5": {"HB_SPMV_UNROLL": 12, "HB_SPMV_CTAS_PER_SM": 5},
+    "pk_u8_c6": {"HB_SPMV_UNROLL": 8, "HB_SPMV_CTAS_PER_SM": 6},
     "str8_c4": {"HB_SPMV_UNROLL": 8, "HB_SPMV_CTAS_PER_SM": 4},
     "str8_c5": {"HB_SPMV_UNROLL": 8, "HB_SPMV_CTAS_PER_SM": 5},
     "str4_c6": {"HB_SPMV_UNROLL": 4, "HB_SPMV_CTAS_PER_SM": 6},
@@ -43,5 +51,5 @@ if __name__ == "__main__":
         log = open(os.path.join(ROOT, "hicexplorer_b200", "build", "ptxas.log")).read()
         import re
         m = re.findall(r"hb_spmv_kernelI8HbIceEpiLb1E.*?\n.*?\n.*?Used (\d+) registers", log)
-        sp = re.findall(r"hb_spmv_kernelI8HbIceEpiLb1E.*?\n\s+(\d+) bytes stack frame, (\d+) bytes spill stores", log)
+        sp = re.findall(r"hb_spmv_kernelI8HbIceEpiLb1E.*?\n\s+\d+ bytes stack frame, (\d+) bytes spill stores", log)
         print(name, "regs", m, "stack/spill", sp)
