@@ -63,7 +63,20 @@ def build(force=False, verbose=False, defines=None, out=None):
         print("\n".join(log))
     cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
     subprocess.check_call(cmd)
+    if out is None:
+        build_io()
     return LIB
+
+
+def build_io():
+    """host-side file-format decoders (plain C, gcc) -> libhbio.so"""
+    src = os.path.join(CSRC, "hb_io.c")
+    dst = os.path.join(PKG, "libhbio.so")
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        raise RuntimeError("gcc not found: cannot build libhbio.so")
+    subprocess.check_call([cc, "-O3", "-fPIC", "-shared", "-std=c11", "-fvisibility=hidden", "-o", dst, src])
+    return dst
 
 
 if __name__ == "__main__":

@@ -103,7 +103,43 @@ def _unshuffle(buf, typesize):
     return body + bytes(buf[nelem * typesize:])
 
 
+_native = None
+
+
+def _native_lib():
+    """libhbio.so (csrc/hb_io.c): the same decoders in C; None if it was not built."""
+    global _native
+    if _native is None:
+        import ctypes
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libhbio.so")
+        if not os.path.exists(path) or os.environ.get("HDF5LITE_PURE_PYTHON") == "1":
+            _native = False
+        else:
+            lib = ctypes.CDLL(path)
+            lib.hbio_blosc_nbytes.restype = ctypes.c_int64
+            lib.hbio_blosc_nbytes.argtypes = [ctypes.c_char_p]
+            lib.hbio_blosc_blocksize.restype = ctypes.c_int64
+            lib.hbio_blosc_blocksize.argtypes = [ctypes.c_char_p]
+            lib.hbio_blosc_decode.restype = ctypes.c_int64
+            lib.hbio_blosc_decode.argtypes = [ctypes.c_char_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+            _native = lib
+    return _native or None
+
+
 def _blosc_decompress(chunk):
+    lib = _native_lib()
+    if lib is not None:
+        chunk = bytes(chunk)
+        nbytes = lib.hbio_blosc_nbytes(chunk)
+        out = np.empty(max(int(nbytes), 1), dtype=np.uint8)
+        scratch = np.empty(max(int(lib.hbio_blosc_blocksize(chunk)), 1), dtype=np.uint8)
+        got = lib.hbio_blosc_decode(chunk, len(chunk), out.ctypes.data, scratch.ctypes.data)
+        if got == nbytes:
+            return out[:nbytes].tobytes()
+        if got == -1:
+            raise ValueError("malformed Blosc chunk")
+        # -2: codec the C decoder does not handle -> pure-Python path below
     version, versionlz, flags, typesize = struct.unpack_from("<BBBB", chunk, 0)
     nbytes, blocksize, cbytes = struct.unpack_from("<III", chunk, 4)
     if flags & 0x2:  # memcpyed
