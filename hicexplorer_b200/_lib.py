@@ -84,6 +84,7 @@ SIGNATURES = {
     "hb_mad_filter": (c_int, [vp, c_dbl, c_dbl, vp, vp, vp, vp]),
     "hb_csr_compact": (c_int, [vp, vp]),
     "hb_diag_zero": (c_int, [vp]),
+    "hb_csr_merge_bins": (c_int, [vp, vp, c_i64]),
     "hb_symmetry": (c_int, [vp, P(c_dbl)]),
     "hb_ice_run": (c_int, [vp, c_int, c_dbl, vp, vp, vp]),
     "hb_ice_scaled_values": (c_int, [vp, vp, P(c_dbl)]),

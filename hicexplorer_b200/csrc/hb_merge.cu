@@ -1,0 +1,211 @@
+// Bin merging on the device CSR store: sum groups of consecutive bins (rows AND columns) into one bin.
+// Replaces hicexplorer/reduceMatrix.py:12-232 (reduce_matrix with use_triu=True, diagonal=True) as called by
+// hicexplorer/hicMergeMatrixBins.py:264 -- the step right before correction in the reference's workflow
+// (SURVEY.md 8f, rank 2).  Contract: include/hicbalance.h (hb_csr_merge_bins).
+//
+// The reference sums the UPPER triangle into the merged cells and mirrors the result, keeping the diagonal once.
+// On the full symmetric store that is: for merged row I and merged column J != I, R[I][J] = sum of A[i][j] over
+// i in I, j in J (read from the rows of I); for the diagonal cell only the entries with j >= i count.
+//
+// Mapping: a warp owns a merged row; lane r walks old row r of the group (<= 32 rows per group).  Old rows are
+// sorted by column and the bin map is monotone, so each lane sees merged column ids in ascending order: the warp
+// repeatedly takes the minimum head id over the lanes, every lane consumes its run of that id, and a fixed-order
+// shuffle reduction forms the cell -- a 32-way merge without sorting or atomics, deterministic, and exact for
+// integer counts.  Pass 1 counts the non-zero cells per merged row, a scan builds indptr, pass 2 writes them.
+#include <climits>
+
+#include "hb_internal.cuh"
+
+__device__ __forceinline__ bool hb_merge_skip(int J, int I, int c, int64_t row) { return J < 0 || (J == I && c < row); }
+
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+hb_merge_rows_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
+                     const int32_t* __restrict__ map, const int64_t* __restrict__ group_start,
+                     const int64_t* __restrict__ group_end, int64_t n_new,
+                     int64_t* __restrict__ cnt, const int64_t* __restrict__ out_ptr, int32_t* __restrict__ out_idx,
+                     double* __restrict__ out_val) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t I = gwarp; I < n_new; I += nwarps) {
+        const int64_t g0 = group_start[I], g1 = group_end[I];
+        const int64_t row = g0 + lane;
+        int64_t cur = 0, end = 0;
+        if (row < g1) {
+            cur = indptr[row];
+            end = indptr[row + 1];
+        }
+        int64_t w = FILL ? out_ptr[I] : 0;
+        long long n_out = 0;
+        for (;;) {
+            int head = INT_MAX;
+            while (cur < end) {
+                const int c = idx[cur];
+                const int J = map[c];
+                if (!hb_merge_skip(J, (int)I, c, row)) {
+                    head = J;
+                    break;
+                }
+                ++cur;
+            }
+            int m = head;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (m == INT_MAX) break;
+            double s = 0.0;
+            if (head == m) {
+                while (cur < end) {
+                    const int c = idx[cur];
+                    const int J = map[c];
+                    if (hb_merge_skip(J, (int)I, c, row)) {
+                        ++cur;
+                        continue;
+                    }
+                    if (J != m) break;
+                    s += val[cur];
+                    ++cur;
+                }
+            }
+            const double tot = hb_warp_sum(s);
+            if (tot != 0.0) {  // eliminate_zeros (reduceMatrix.py:230); NaN != 0 is kept, like scipy
+                if (FILL && lane == 0) {
+                    out_idx[w] = m;
+                    out_val[w] = tot;
+                }
+                ++w;
+                ++n_out;
+            }
+        }
+        if (!FILL && lane == 0) cnt[I] = n_out;
+    }
+}
+
+__global__ void __launch_bounds__(1024) hb_merge_scan_kernel(const int64_t* __restrict__ in, int64_t* __restrict__ out, int64_t n) {
+    __shared__ long long part[1024];
+    const int t = threadIdx.x;
+    const int64_t chunk = (n + 1023) / 1024;
+    const int64_t b = t * chunk, e = (b + chunk < n) ? b + chunk : n;
+    long long s = 0;
+    for (int64_t i = b; i < e; ++i) s += in[i];
+    part[t] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        long long v = (t >= o) ? part[t - o] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    long long run = part[t] - s;
+    for (int64_t i = b; i < e; ++i) {
+        const long long v = in[i];
+        out[i] = run;
+        run += v;
+    }
+    if (t == 1023) out[n] = part[1023];
+}
+
+extern "C" int hb_csr_merge_bins(hb_csr* h, const int32_t* bin_map, int64_t n_new) {
+    HB_REQUIRE(h != nullptr && bin_map != nullptr, "bad arguments");
+    HB_REQUIRE(h->row0 == 0 && h->n_rows == h->n_cols, "hb_csr_merge_bins needs the full matrix on one device");
+    HB_REQUIRE(n_new >= 0 && n_new <= h->n_cols, "bad merged size");
+    const int64_t n = h->n_cols;
+    // the map must send runs of consecutive bins to 0, 1, 2, ... in order (dropped bins = -1), <= 32 bins per group
+    std::vector<int64_t> g_start((size_t)(n_new > 0 ? n_new : 1), -1), g_end((size_t)(n_new > 0 ? n_new : 1), -1);
+    {
+        int64_t next = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            const int32_t J = bin_map[i];
+            if (J < 0) continue;
+            HB_REQUIRE(J < n_new, "bin map exceeds the merged size");
+            if (g_start[J] < 0) {
+                HB_REQUIRE(J == next, "merged ids must appear in ascending order");
+                g_start[J] = i;
+                ++next;
+            } else {
+                HB_REQUIRE(g_end[J] == i, "the bins of a group must be consecutive");
+            }
+            g_end[J] = i + 1;
+            HB_REQUIRE(g_end[J] - g_start[J] <= 32, "at most 32 bins per merged bin");
+        }
+        HB_REQUIRE(next == n_new, "some merged bins are empty");
+    }
+    int rc = hb_use_device(h);
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    hb_drop_pack(h);
+    int64_t *d_gs = nullptr, *d_ge = nullptr, *d_cnt = nullptr, *d_ptr = nullptr;
+    int32_t *d_map = nullptr, *d_idx = nullptr;
+    double* d_val = nullptr;
+    int64_t new_nnz = 0;
+    cudaError_t e = cudaSuccess;
+    const int grid = HB_NUM_SMS * 8;
+    const size_t ng = (size_t)(n_new > 0 ? n_new : 1);
+#define MG(expr)                                                  \
+    do {                                                          \
+        e = (expr);                                               \
+        if (e != cudaSuccess) {                                   \
+            rc = hb_cuda_fail(e, #expr, __FILE__, __LINE__);      \
+            goto fail;                                            \
+        }                                                         \
+    } while (0)
+    MG(cudaMalloc(&d_gs, sizeof(int64_t) * ng));
+    MG(cudaMalloc(&d_ge, sizeof(int64_t) * ng));
+    MG(cudaMalloc(&d_map, sizeof(int32_t) * (size_t)(n > 0 ? n : 1)));
+    MG(cudaMalloc(&d_cnt, sizeof(int64_t) * (ng + 1)));
+    MG(cudaMalloc(&d_ptr, sizeof(int64_t) * (ng + 1)));
+    MG(cudaMemcpyAsync(d_gs, g_start.data(), sizeof(int64_t) * ng, cudaMemcpyHostToDevice, s));
+    MG(cudaMemcpyAsync(d_ge, g_end.data(), sizeof(int64_t) * ng, cudaMemcpyHostToDevice, s));
+    if (n > 0) MG(cudaMemcpyAsync(d_map, bin_map, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
+    MG(cudaMemsetAsync(d_cnt, 0, sizeof(int64_t) * (ng + 1), s));
+    if (n_new > 0) {
+        hb_merge_rows_kernel<false><<<grid, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, d_map, d_gs, d_ge, n_new,
+                                                         d_cnt, nullptr, nullptr, nullptr);
+        g_hb_launches.fetch_add(1);
+    }
+    hb_merge_scan_kernel<<<1, 1024, 0, s>>>(d_cnt, d_ptr, n_new);
+    g_hb_launches.fetch_add(1);
+    MG(cudaMemcpyAsync(&new_nnz, d_ptr + n_new, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    MG(cudaStreamSynchronize(s));
+    MG(cudaGetLastError());
+    MG(cudaMalloc(&d_idx, sizeof(int32_t) * (size_t)(new_nnz > 0 ? new_nnz : 1) + 16));
+    MG(cudaMalloc(&d_val, sizeof(double) * (size_t)(new_nnz > 0 ? new_nnz : 1) + 16));
+    if (n_new > 0 && new_nnz > 0) {
+        hb_merge_rows_kernel<true><<<grid, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, d_map, d_gs, d_ge, n_new,
+                                                        nullptr, d_ptr, d_idx, d_val);
+        g_hb_launches.fetch_add(1);
+    }
+    MG(cudaStreamSynchronize(s));
+    MG(cudaGetLastError());
+#undef MG
+    cudaFree(d_gs);
+    cudaFree(d_ge);
+    cudaFree(d_map);
+    cudaFree(d_cnt);
+    if (h->owns_csr) {
+        cudaFree(h->d_indptr);
+        cudaFree(h->d_indices);
+        cudaFree(h->d_data);
+    }
+    h->owns_csr = true;
+    h->phase = 0;
+    h->d_indptr = d_ptr;
+    h->d_indices = d_idx;
+    h->d_data = d_val;
+    h->nnz = new_nnz;
+    h->n_rows = h->n_cols = n_new;
+    h->row0 = 0;
+    hb_free_state(h);
+    h->nseg = 1;
+    h->seg_off = {0, n_new};
+    return hb_build_tiles(h);
+fail:
+    cudaFree(d_gs);
+    cudaFree(d_ge);
+    cudaFree(d_map);
+    cudaFree(d_cnt);
+    cudaFree(d_ptr);
+    cudaFree(d_idx);
+    cudaFree(d_val);
+    return rc;
+}

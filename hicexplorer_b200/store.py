@@ -192,6 +192,14 @@ class DeviceCSR(object):
             raise ValueError("mask length must equal the bin count")
         check(lib().hb_csr_compact(self._h, ptr(m)))
 
+    def merge_bins(self, bin_map, n_new):
+        """Sum groups of consecutive bins (rows and columns): bin_map[i] = merged id of bin i or -1 (dropped)."""
+        m = np.ascontiguousarray(bin_map, dtype=np.int32)
+        if len(m) != self.n:
+            raise ValueError("bin map length must equal the bin count")
+        check(lib().hb_csr_merge_bins(self._h, ptr(m), int(n_new)))
+        self._segments = 1
+
     def diag_zero(self):
         check(lib().hb_diag_zero(self._h))
 

@@ -160,6 +160,14 @@ HB_API int hb_csr_compact(hb_csr* h, const uint8_t* remove_mask);
 HB_API int hb_diag_zero(hb_csr* h);
 HB_API int hb_symmetry(hb_csr* h, double* ratio_out);
 
+/* ---- bin merging (the step before correction) ----------------------------------
+ * Replaces reduce_matrix(matrix, bins_to_merge, use_triu=True, diagonal=True) (hicexplorer/reduceMatrix.py:12-232)
+ * as called by hicMergeMatrixBins (hicexplorer/hicMergeMatrixBins.py:264).  bin_map[n_cols]: merged bin id of every
+ * bin, -1 = dropped; ids must appear in ascending order 0..n_new-1, each covering <= 32 CONSECUTIVE bins (what
+ * --numBins <= 32 produces).  The store becomes the n_new x n_new full symmetric merged matrix (exact zeros
+ * eliminated, columns ascending); segments are reset.  Needs the full matrix on one device. */
+HB_API int hb_csr_merge_bins(hb_csr* h, const int32_t* bin_map, int64_t n_new);
+
 /* ---- ICE -------------------------------------------------------------------
  * Replaces iterativeCorrection(matrix, v, M, tolerance, verbose)
  * (hicexplorer/iterativeCorrection.py:10-86).

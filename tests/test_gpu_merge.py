@@ -1,0 +1,75 @@
+"""Bin merging (hicMergeMatrixBins --numBins k) on the GPU vs the reference's golden file and the CPU oracle."""
+import numpy as np
+import pytest
+from scipy import sparse
+
+from hicexplorer_b200 import hdf5lite
+from hicexplorer_b200.hicmatrix_lite import hiCMatrix
+from oracle import merge_oracle
+from tests.conftest import load_golden
+from tests.helpers import random_hic
+
+pytestmark = pytest.mark.gpu
+
+
+def _input(tmp_path):
+    z = load_golden("merge_small.npz")
+    n = len(z["in_indptr"]) - 1
+    ma = hiCMatrix()
+    up = sparse.csr_matrix((z["in_data"], z["in_indices"], z["in_indptr"]), shape=(n, n))
+    ma.matrix = sparse.csr_matrix(up + sparse.triu(up, 1).T)
+    ma.cut_intervals = [(c.decode(), int(s), int(e), float(x)) for c, s, e, x in
+                        zip(z["in_chr"], z["in_start"], z["in_end"], z["in_extra"])]
+    ma._index_intervals()
+    path = str(tmp_path / "small_test_matrix.h5")
+    ma.save(path)
+    return z, path
+
+
+def test_merge_matrix_bins_matches_reference_golden(tmp_path):
+    """mirrors test_correct_matrix in test/general/test_hicMergeMatrixBins.py:15-27 (exact data + intervals)"""
+    from hicexplorer_b200.hicMergeMatrixBins import main
+    z, src = _input(tmp_path)
+    out = str(tmp_path / "merged.h5")
+    main("--matrix {} --numBins 5 --outFileName {}".format(src, out).split())
+    f = hdf5lite.File(out)
+    np.testing.assert_array_equal(f["matrix/data"].read(), z["out_data"])          # bit-exact (integer counts)
+    np.testing.assert_array_equal(f["matrix/indices"].read(), z["out_indices"])
+    np.testing.assert_array_equal(f["matrix/indptr"].read(), z["out_indptr"])
+    assert [c.decode() for c in f["intervals/chr_list"].read()] == [c.decode() for c in z["out_chr"]]
+    np.testing.assert_array_equal(f["intervals/start_list"].read(), z["out_start"])
+    np.testing.assert_array_equal(f["intervals/end_list"].read(), z["out_end"])
+    np.testing.assert_allclose(f["intervals/extra_list"].read(), z["out_extra"], rtol=1e-12, equal_nan=True)
+    np.testing.assert_array_equal(f["nan_bins"].read(), z["out_nan_bins"])
+
+
+@pytest.mark.parametrize("n,k,seed", [(500, 2, 0), (1203, 7, 1), (64, 32, 2), (777, 3, 3)])
+def test_merge_random_matrices_match_oracle(n, k, seed):
+    from hicexplorer_b200.store import DeviceCSR
+    m = random_hic(n, 0.1, seed, empty_frac=0.02)
+    sizes = [n // 3, n // 3, n - 2 * (n // 3)]
+    iv = []
+    for c, L in enumerate(sizes):
+        iv += [("chr%d" % c, i * 100, (i + 1) * 100, 1.0) for i in range(L)]
+    ref, new_iv, _nan, bin_map = merge_oracle.merge_bins(m, iv, k)
+    with DeviceCSR.from_scipy(m) as dev:
+        dev.merge_bins(bin_map, len(new_iv))
+        got = dev.download()
+        assert dev.symmetry_ratio() == 0.0
+    assert np.array_equal(got.indptr, ref.indptr) and np.array_equal(got.indices, ref.indices)
+    np.testing.assert_array_equal(got.data, ref.data)
+
+
+def test_merge_then_correct_workflow():
+    """merge -> ICE on the same device store (the reference's documented order: merge first, then correct)"""
+    from hicexplorer_b200.store import DeviceCSR
+    from oracle import ice_oracle
+    m = random_hic(900, 0.1, 11)
+    iv = [("chr1", i * 10, (i + 1) * 10, 1.0) for i in range(900)]
+    ref_m, new_iv, _nan, bin_map = merge_oracle.merge_bins(m, iv, 4)
+    ref = ice_oracle.ice(ref_m.astype(np.float64), max_iter=100)
+    with DeviceCSR.from_scipy(m) as dev:
+        dev.merge_bins(bin_map, len(new_iv))
+        bias, iters, _ = dev.ice(100, 1e-5)
+    np.testing.assert_allclose(bias, ref["bias"], rtol=1e-9)
+    assert abs(int(iters[0]) - ref["iterations"]) <= 1

@@ -142,3 +142,38 @@ def test_kr_small_fixture_is_ill_conditioned(small_ice):
     x2[perm] = alt["x_out"]
     rel = np.max(np.abs(x2 / ref["x_out"] - 1))
     assert 1e-8 < rel < 5e-6
+
+
+def test_merge_oracle_reproduces_reference_golden_file():
+    from oracle import merge_oracle
+    from tests.conftest import load_golden
+    z = load_golden("merge_small.npz")
+    n = len(z["in_indptr"]) - 1
+    up = sparse.csr_matrix((z["in_data"], z["in_indices"], z["in_indptr"]), shape=(n, n))
+    full = sparse.csr_matrix(up + sparse.triu(up, 1).T)
+    iv = [(c.decode(), int(s), int(e), float(x)) for c, s, e, x in zip(z["in_chr"], z["in_start"], z["in_end"], z["in_extra"])]
+    m, new_iv, nan_bins, _map = merge_oracle.merge_bins(full, iv, 5)
+    u = sparse.triu(m, 0, format="csr")
+    u.sort_indices()
+    assert np.array_equal(u.data, z["out_data"]) and np.array_equal(u.indices, z["out_indices"])
+    assert np.array_equal(u.indptr, z["out_indptr"]) and np.array_equal(nan_bins, z["out_nan_bins"])
+    assert [a[0] for a in new_iv] == [c.decode() for c in z["out_chr"]]
+    assert [a[1] for a in new_iv] == z["out_start"].tolist() and [a[2] for a in new_iv] == z["out_end"].tolist()
+    np.testing.assert_allclose([a[3] for a in new_iv], z["out_extra"], rtol=1e-12, equal_nan=True)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="/root/reference not present (GPU box)")
+def test_merge_oracle_equals_reference_reduce_matrix():
+    from oracle import merge_oracle
+    ref_import.load()
+    from hicexplorer.reduceMatrix import reduce_matrix
+    m = random_hic(400, 0.1, 3, empty_frac=0.03)
+    iv = [("a" if i < 150 else "b", i * 10, (i + 1) * 10, 1.0) for i in range(400)]
+    bin_map, new_iv = merge_oracle.merge_groups(iv, 6)
+    groups = [list(np.flatnonzero(bin_map == k)) for k in range(len(new_iv))]
+    want = sparse.csr_matrix(reduce_matrix(m, groups, diagonal=True))
+    want.eliminate_zeros()
+    want.sort_indices()
+    got = merge_oracle.reduce(m, bin_map, len(new_iv))
+    assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
+    np.testing.assert_array_equal(got.data, want.data)

@@ -77,7 +77,56 @@ def main():
     peak, peak_src = bench.measured_peak()
     out = {"config": config, "n_gpus": world, "peak_GBps": peak, "peak_source": peak_src}
 
-    if config == "perchr5k":
+    if config == "merge10k":
+        # hicMergeMatrixBins --numBins 5 on the synthetic 10 kb matrix (10 kb -> 50 kb), 1 GPU
+        method, bins, kw = bench.synth_kwargs("ice10k", clean=True)
+        n = int(sum(bins))
+        iv_chrom = np.repeat(np.arange(len(bins)), bins)
+        k = 5
+        # groups of k inside each chromosome (a trailing group < k/2 bins is dropped, like the reference)
+        bin_map = np.full(n, -1, dtype=np.int32)
+        nxt = 0
+        start = 0
+        for c, L in enumerate(bins):
+            full, rest = divmod(L, k)
+            ids = np.repeat(np.arange(full), k) + nxt
+            bin_map[start:start + full * k] = ids
+            nxt += full
+            if rest and not rest < k / 2:
+                bin_map[start + full * k:start + L] = nxt
+                nxt += 1
+            start += L
+        if bin_map[-1] < 0:                       # the very last group of the matrix is always kept
+            last = np.flatnonzero(bin_map >= 0)[-1] + 1
+            bin_map[last:] = nxt
+            nxt += 1
+        times = []
+        for rep in range(3):
+            with DeviceCSR.synthetic(bins, device=local, **kw) as dev:
+                nnz_in = dev.nnz
+                dev.sync()
+                t0 = time.time()
+                dev.merge_bins(bin_map, nxt)
+                dev.sync()
+                times.append(time.time() - t0)
+                nnz_out, n_out = dev.nnz, dev.n
+        t = min(times)
+        from oracle import hic_cpu, merge_oracle
+        sample = hic_cpu.synth_matrix([bins[0]], **kw)
+        siv = [("chr1", i, i + 1, 1.0) for i in range(bins[0])]
+        t0 = time.time()
+        ref_m, _iv, _nan, _map = merge_oracle.merge_bins(sample, siv, k)
+        t_cpu = time.time() - t0
+        out.update({"workload": "merge 5 bins (10 kb -> 50 kb) of the synthetic 10 kb matrix: %d bins, %d entries -> %d bins, %d entries"
+                                % (n, nnz_in, n_out, nnz_out),
+                    "merge": {"ms": t * 1e3, "input_entries_per_s": nnz_in / t,
+                              "GBps": (2 * 12.0 * nnz_in + 12.0 * nnz_out) / t / 1e9,
+                              "frac_of_peak": (2 * 12.0 * nnz_in + 12.0 * nnz_out) / t / 1e9 / peak,
+                              "note": "two passes over the input (count, fill) + allocation of the merged store"},
+                    "cpu_baseline": {"value": sample.nnz / t_cpu, "unit": "input entries/s", "cores": 1, "kind": "port",
+                                     "sample": "oracle/merge_oracle.py (numpy/scipy restatement of reduce_matrix) on chromosome 1 "
+                                               "of the same matrix (%d entries), %.1f s" % (sample.nnz, t_cpu)}})
+    elif config == "perchr5k":
         method, bins, kw = bench.synth_kwargs("perchr5k", clean=True)
         kw = dict(kw, n_trans=0)                    # cis only: block diagonal by construction
         weights = [bench.expected_nnz([b], kw["band"], kw["d0"]) for b in bins]
