@@ -7,17 +7,22 @@
 // On the full symmetric store that is: for merged row I and merged column J != I, R[I][J] = sum of A[i][j] over
 // i in I, j in J (read from the rows of I); for the diagonal cell only the entries with j >= i count.
 //
-// Mapping: a warp owns a merged row; lane r walks old row r of the group (<= 32 rows per group).  Old rows are
-// sorted by column and the bin map is monotone, so each lane sees merged column ids in ascending order: the warp
-// repeatedly takes the minimum head id over the lanes, every lane consumes its run of that id, and a fixed-order
-// shuffle reduction forms the cell -- a 32-way merge without sorting or atomics, deterministic, and exact for
-// integer counts.  Pass 1 counts the non-zero cells per merged row, a scan builds indptr, pass 2 writes them.
+// Old rows are sorted by column and the bin map is monotone, so merged ids ascend along every old row; no sort and
+// no atomics are needed, the result is deterministic and exact for integer counts.  Pass 1 counts the non-zero
+// cells per merged row, a scan builds indptr, pass 2 writes them (kernel comment below for the mapping).
 #include <climits>
 
 #include "hb_internal.cuh"
 
-__device__ __forceinline__ bool hb_merge_skip(int J, int I, int c, int64_t row) { return J < 0 || (J == I && c < row); }
+#define HB_MERGE_WINDOW 512  // merged columns accumulated at a time per warp (4 KB of shared memory per warp)
 
+// A warp owns merged row I.  The merged row is produced window by window (HB_MERGE_WINDOW merged columns): for each
+// window the warp streams, one old row of the group after the other, the stretch of that row whose columns fall
+// into the window -- 32 consecutive entries per step, coalesced -- maps them to merged ids, combines the entries
+// of equal id inside the step with a segmented shuffle reduction (equal ids are adjacent: the row is sorted and the
+// map monotone) and lets the first lane of each run add into a dense shared-memory accumulator.  One warp touches
+// its accumulator strictly in program order (row after row, step after step), so the sums are deterministic.  The
+// window is then swept in column order: non-zero cells are counted (pass 1) or written (pass 2).
 template <bool FILL>
 __global__ void __launch_bounds__(256)
 hb_merge_rows_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
@@ -25,57 +30,100 @@ hb_merge_rows_kernel(const int64_t* __restrict__ indptr, const int32_t* __restri
                      const int64_t* __restrict__ group_end, int64_t n_new,
                      int64_t* __restrict__ cnt, const int64_t* __restrict__ out_ptr, int32_t* __restrict__ out_idx,
                      double* __restrict__ out_val) {
+    __shared__ double acc_all[8][HB_MERGE_WINDOW];
     const int lane = threadIdx.x & 31;
+    double* acc = acc_all[threadIdx.x >> 5];
     const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int i = lane; i < HB_MERGE_WINDOW; i += 32) acc[i] = 0.0;
+    __syncwarp();
     for (int64_t I = gwarp; I < n_new; I += nwarps) {
-        const int64_t g0 = group_start[I], g1 = group_end[I];
-        const int64_t row = g0 + lane;
+        const int64_t g0 = group_start[I];
+        const int k = (int)(group_end[I] - g0);
+        // lane r keeps the cursor of old row g0 + r
         int64_t cur = 0, end = 0;
-        if (row < g1) {
-            cur = indptr[row];
-            end = indptr[row + 1];
+        if (lane < k) {
+            cur = indptr[g0 + lane];
+            end = indptr[g0 + lane + 1];
         }
         int64_t w = FILL ? out_ptr[I] : 0;
         long long n_out = 0;
         for (;;) {
+            // next window = the one holding the smallest unread merged id over the k rows
             int head = INT_MAX;
-            while (cur < end) {
-                const int c = idx[cur];
-                const int J = map[c];
-                if (!hb_merge_skip(J, (int)I, c, row)) {
-                    head = J;
-                    break;
+            if (cur < end) {
+                // skip dropped columns at the cursor (map < 0) so that the head is a real id
+                while (cur < end) {
+                    const int J = map[idx[cur]];
+                    if (J >= 0) {
+                        head = J;
+                        break;
+                    }
+                    ++cur;
                 }
-                ++cur;
             }
             int m = head;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
             if (m == INT_MAX) break;
-            double s = 0.0;
-            if (head == m) {
-                while (cur < end) {
-                    const int c = idx[cur];
-                    const int J = map[c];
-                    if (hb_merge_skip(J, (int)I, c, row)) {
-                        ++cur;
-                        continue;
+            const int J_lo = m - (m % HB_MERGE_WINDOW);
+            const int J_hi = J_lo + HB_MERGE_WINDOW;
+            for (int r = 0; r < k; ++r) {
+                int64_t c0 = __shfl_sync(0xffffffffu, cur, r);
+                const int64_t e0 = __shfl_sync(0xffffffffu, end, r);
+                const int64_t row = g0 + r;
+                for (;;) {
+                    const int64_t p = c0 + lane;
+                    int J = INT_MAX;  // sentinel: beyond the row or beyond the window
+                    int c = -1;
+                    double v = 0.0;
+                    if (p < e0) {
+                        c = idx[p];
+                        const int Jm = map[c];
+                        J = Jm < 0 ? -1 : Jm;
+                        if (J < J_hi) v = val[p];
                     }
-                    if (J != m) break;
-                    s += val[cur];
-                    ++cur;
+                    // entries are consumed up to the first one that belongs to a later window
+                    const unsigned int beyond = __ballot_sync(0xffffffffu, J >= J_hi);
+                    const int take = beyond ? (__ffs(beyond) - 1) : 32;
+                    const bool mine = lane < take;
+                    // dropped column, or lower-triangle entry of the diagonal cell: contributes nothing
+                    const bool live = mine && J >= 0 && !(J == (int)I && c < row);
+                    const int key = mine ? J : INT_MAX - 1;
+                    double s = live ? v : 0.0;
+                    // segmented inclusive scan from the right: after it the first lane of a run holds the run's sum
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const double t = __shfl_down_sync(0xffffffffu, s, o);
+                        const int kt = __shfl_down_sync(0xffffffffu, key, o);
+                        if (lane + o < 32 && kt == key) s += t;
+                    }
+                    const int kprev = __shfl_up_sync(0xffffffffu, key, 1);
+                    const bool first = mine && J >= 0 && (lane == 0 || kprev != key);
+                    if (first) acc[J - J_lo] += s;
+                    __syncwarp();
+                    c0 += take;
+                    if (take < 32 || c0 >= e0) break;
+                }
+                if (lane == r) cur = c0;
+            }
+            // sweep the window in column order
+            for (int base = 0; base < HB_MERGE_WINDOW; base += 32) {
+                const double t = acc[base + lane];
+                const bool nz = t != 0.0;  // eliminate_zeros (reduceMatrix.py:230); NaN != 0 is kept, like scipy
+                const unsigned int bal = __ballot_sync(0xffffffffu, nz);
+                if (bal) {
+                    if (FILL && nz) {
+                        const int64_t pos = w + __popc(bal & ((1u << lane) - 1u));
+                        out_idx[pos] = J_lo + base + lane;
+                        out_val[pos] = t;
+                    }
+                    acc[base + lane] = 0.0;
+                    w += __popc(bal);
+                    n_out += __popc(bal);
                 }
             }
-            const double tot = hb_warp_sum(s);
-            if (tot != 0.0) {  // eliminate_zeros (reduceMatrix.py:230); NaN != 0 is kept, like scipy
-                if (FILL && lane == 0) {
-                    out_idx[w] = m;
-                    out_val[w] = tot;
-                }
-                ++w;
-                ++n_out;
-            }
+            __syncwarp();
         }
         if (!FILL && lane == 0) cnt[I] = n_out;
     }
