@@ -37,6 +37,7 @@ WORKLOADS = {
     "kr25k": ("KR", 25000, 3.0e8, 8000),
     "ice25k": ("ICE", 25000, 3.0e8, 8000),
     "ice100k": ("ICE", 100000, 4.0e7, 2000),   # small case for quick checks
+    "ice5k_big": ("ICE", 5000, 2.6e9, 16000),  # > 2^31 stored entries on one GPU (int64 offsets everywhere)
 }
 
 

@@ -140,8 +140,11 @@ int hb_csr_create(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t row0, in
         g_hb_launches.fetch_add(1);
     }
     if (nnz > 0) {
-        HB_CREATE_CUDA(cudaMemcpyAsync(h->d_data + phase, data + indptr[0], sizeof(double) * (size_t)nnz,
-                                       cudaMemcpyHostToDevice, s));
+        if (hb_copy_h2d(h->d_data + phase, data + indptr[0], sizeof(double) * (size_t)nnz, device) != HB_OK) {
+            hb_csr_destroy(h);
+            *out = nullptr;
+            return HB_ERR_CUDA;
+        }
         if (indices_i64) {
             // krbalancing's constructor takes int64 indices (hicCorrectMatrix.py:744-747): narrow on the device
             const int64_t* src = (const int64_t*)indices + indptr[0];
@@ -157,8 +160,12 @@ int hb_csr_create(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t row0, in
             HB_CREATE_CUDA(cudaStreamSynchronize(s));
             cudaFree(d_tmp);
         } else {
-            HB_CREATE_CUDA(cudaMemcpyAsync(h->d_indices + phase, (const int32_t*)indices + indptr[0],
-                                           sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, s));
+            if (hb_copy_h2d(h->d_indices + phase, (const int32_t*)indices + indptr[0], sizeof(int32_t) * (size_t)nnz,
+                            device) != HB_OK) {
+                hb_csr_destroy(h);
+                *out = nullptr;
+                return HB_ERR_CUDA;
+            }
         }
     }
     HB_CREATE_CUDA(cudaStreamSynchronize(s));
@@ -228,8 +235,14 @@ int hb_csr_download(hb_csr* h, int64_t* indptr, int32_t* indices, double* data) 
         if (h->phase)
             for (int64_t i = 0; i <= h->n_rows; ++i) indptr[i] -= h->phase;
     }
-    if (indices && h->nnz) HB_CUDA(cudaMemcpy(indices, h->d_indices + h->phase, sizeof(int32_t) * (size_t)h->nnz, cudaMemcpyDeviceToHost));
-    if (data && h->nnz) HB_CUDA(cudaMemcpy(data, h->d_data + h->phase, sizeof(double) * (size_t)h->nnz, cudaMemcpyDeviceToHost));
+    if (indices && h->nnz) {
+        rc = hb_copy_d2h(indices, h->d_indices + h->phase, sizeof(int32_t) * (size_t)h->nnz, h->device);
+        if (rc) return rc;
+    }
+    if (data && h->nnz) {
+        rc = hb_copy_d2h(data, h->d_data + h->phase, sizeof(double) * (size_t)h->nnz, h->device);
+        if (rc) return rc;
+    }
     return HB_OK;
 }
 

@@ -68,7 +68,22 @@ hb_row_stats_kernel(const int64_t* __restrict__ indptr, const int32_t* __restric
         }
         double acc = 0.0, dg = 0.0;
         const int64_t s = indptr[row], e = indptr[row + 1];
-        for (int64_t k = s + lane; k < e; k += 32) {
+        int64_t k = s + lane;
+        // 8 independent (column id, value) pairs in flight per lane: this pass is a pure stream over the matrix
+        for (; k + 32 * 7 < e; k += 32 * 8) {
+            int c[8];
+            double v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) c[j] = hb_ldg_stream_i1(idx + k + 32 * j);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = hb_ldg_stream_d1(val + k + 32 * j);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (c[j] >= clo && c[j] < chi) acc += v[j];
+                if (c[j] == g) dg += v[j];
+            }
+        }
+        for (; k < e; k += 32) {
             const int c = idx[k];
             const double v = val[k];
             if (c >= clo && c < chi) acc += v;
@@ -292,7 +307,16 @@ hb_compact_count_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
             chi = rule.seg_off[s + 1];
         }
         long long cnt = 0;
-        for (int64_t k = indptr[row] + lane; k < indptr[row + 1]; k += 32) cnt += rule.keep(g, clo, chi, idx[k]) ? 1 : 0;
+        const int64_t e = indptr[row + 1];
+        int64_t k = indptr[row] + lane;
+        for (; k + 32 * 7 < e; k += 32 * 8) {  // 8 column ids (and their renumbering look-ups) in flight per lane
+            int c[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) c[j] = hb_ldg_stream_i1(idx + k + 32 * j);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cnt += rule.keep(g, clo, chi, c[j]) ? 1 : 0;
+        }
+        for (; k < e; k += 32) cnt += rule.keep(g, clo, chi, idx[k]) ? 1 : 0;
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
         if (lane == 0) new_count[nr] = cnt;
     }
@@ -317,23 +341,35 @@ hb_compact_fill_kernel(const int64_t* __restrict__ indptr, const int32_t* __rest
         }
         int64_t w = new_indptr[nr - new_row0];
         const int64_t s = indptr[row], e = indptr[row + 1];
-        for (int64_t base = s; base < e; base += 32) {
-            const int64_t k = base + lane;
-            int c = 0;
-            double v = 0.0;
-            bool kp = false;
-            if (k < e) {
-                c = idx[k];
-                v = val[k];
-                kp = rule.keep(g, clo, chi, c);
+        for (int64_t base = s; base < e; base += 128) {  // 4 chunks of 32 entries in flight, written in order
+            int c[4];
+            double v[4];
+            bool kp[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int64_t k = base + 32 * q + lane;
+                c[q] = (k < e) ? hb_ldg_stream_i1(idx + k) : 0;
             }
-            const unsigned int bal = __ballot_sync(0xffffffffu, kp);
-            if (kp) {
-                const int64_t pos = w + __popc(bal & ((1u << lane) - 1u));
-                new_idx[pos] = rule.newid ? rule.newid[c] : c;
-                new_val[pos] = v;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int64_t k = base + 32 * q + lane;
+                v[q] = (k < e) ? hb_ldg_stream_d1(val + k) : 0.0;
             }
-            w += __popc(bal);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int64_t k = base + 32 * q + lane;
+                kp[q] = (k < e) && rule.keep(g, clo, chi, c[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const unsigned int bal = __ballot_sync(0xffffffffu, kp[q]);
+                if (kp[q]) {
+                    const int64_t pos = w + __popc(bal & ((1u << lane) - 1u));
+                    new_idx[pos] = rule.newid ? rule.newid[c[q]] : c[q];
+                    new_val[pos] = v[q];
+                }
+                w += __popc(bal);
+            }
         }
     }
 }
@@ -411,41 +447,143 @@ static int hb_compact_impl(hb_csr* h, const int32_t* d_newid, int64_t new_n, int
 // ---------------------------------------------------------------------------------------------
 // symmetry: sum |M - M^T| and sum M   (iterativeCorrection.py:35)
 // ---------------------------------------------------------------------------------------------
+// Position of column `want` in the ascending column list idx[lo..hi) of one row, or -1.  Interpolation search:
+// Hi-C rows are dense near the diagonal, so the first guess usually lands within a step or two (a plain binary
+// search costs ~12 dependent cache misses in ANOTHER row per entry and made this test slower than the whole ICE
+// solve); falls back to bisection when the guess does not shrink the range.
+__device__ __forceinline__ int64_t hb_find_col(const int32_t* __restrict__ idx, int64_t lo, int64_t hi, int want) {
+    hi -= 1;  // inclusive
+    int guard = 0;
+    while (lo <= hi) {
+        const int clo = idx[lo];
+        if (want < clo) return -1;
+        if (want == clo) return lo;
+        const int chi = idx[hi];
+        if (want > chi) return -1;
+        if (want == chi) return hi;
+        if (hi - lo < 2) return -1;
+        int64_t mid;
+        if (guard < 4) {
+            mid = lo + (int64_t)(((double)(want - clo) / (double)(chi - clo)) * (double)(hi - lo));
+            if (mid <= lo) mid = lo + 1;
+            if (mid >= hi) mid = hi - 1;
+        } else {
+            mid = (lo + hi) >> 1;
+        }
+        ++guard;
+        const int cm = idx[mid];
+        if (cm == want) return mid;
+        if (cm < want) lo = mid + 1; else hi = mid - 1;
+    }
+    return -1;
+}
+
+// Fast exact-symmetry screen: one streaming pass, no look-ups.  Every entry (i, j, a) contributes the fingerprint
+// f(i, j, bits(a)) to multiset A and f(j, i, bits(a)) to multiset B; the matrix equals its transpose iff A == B.
+// The multisets are compared through two commutative 64-bit digests each (sum and xor of a mixed key), so the
+// accumulation order is irrelevant and a false "equal" needs a ~2^-64 collision.  Matrices that are symmetric by
+// construction (what the driver produces, hicmatrix symmetric fill) take this path: ratio = 0 exactly, as numpy
+// would compute.  Anything else falls through to the exact |M - M^T| pass below, which yields the ratio itself.
+__device__ __forceinline__ unsigned long long hb_mixkey(unsigned long long z) {
+    z ^= z >> 30;
+    z *= 0xbf58476d1ce4e5b9ull;
+    z ^= z >> 27;
+    z *= 0x94d049bb133111ebull;
+    z ^= z >> 31;
+    return z;
+}
+
+__global__ void __launch_bounds__(256)
+hb_symmetry_digest_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
+                          int64_t n_rows, unsigned long long* digest /* [0..1] A: sum, xor ; [2..3] B: sum, xor */) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    unsigned long long sa = 0, xa = 0, sb = 0, xb = 0;
+    for (int64_t row = gwarp; row < n_rows; row += nwarps) {
+        const int64_t e = indptr[row + 1];
+        for (int64_t k = indptr[row] + lane; k < e; k += 32 * 4) {
+            int c[4];
+            double v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) c[j] = (k + 32 * j < e) ? hb_ldg_stream_i1(idx + k + 32 * j) : -1;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = (k + 32 * j < e) ? hb_ldg_stream_d1(val + k + 32 * j) : 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (c[j] < 0) continue;
+                const unsigned long long bits = hb_mixkey((unsigned long long)__double_as_longlong(v[j]));
+                const unsigned long long ka = hb_mixkey((((unsigned long long)row << 32) | (unsigned int)c[j]) ^ bits);
+                const unsigned long long kb = hb_mixkey((((unsigned long long)(unsigned int)c[j] << 32) | (unsigned long long)row) ^ bits);
+                sa += ka;
+                xa ^= hb_mixkey(ka + 0x9E3779B97F4A7C15ull);
+                sb += kb;
+                xb ^= hb_mixkey(kb + 0x9E3779B97F4A7C15ull);
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        sa += __shfl_xor_sync(0xffffffffu, sa, o);
+        sb += __shfl_xor_sync(0xffffffffu, sb, o);
+        xa ^= __shfl_xor_sync(0xffffffffu, xa, o);
+        xb ^= __shfl_xor_sync(0xffffffffu, xb, o);
+    }
+    if (lane == 0) {
+        atomicAdd(digest + 0, sa);
+        atomicXor(digest + 1, xa);
+        atomicAdd(digest + 2, sb);
+        atomicXor(digest + 3, xb);
+    }
+}
+
+// UPPER_ONLY: only entries above the diagonal look up their transposed partner and count twice (the pair (i,j),
+// (j,i) contributes |a-b| on both sides); the number of matched pairs is returned so that the caller can tell
+// whether every entry BELOW the diagonal has a partner too (then the one-sided sum is the complete statistic).
+template <bool UPPER_ONLY>
 __global__ void __launch_bounds__(256)
 hb_symmetry_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
-                   int64_t n_rows, double* sums /* [0] sum|M-M^T|, [1] sum M */) {
+                   int64_t n_rows, double* sums /* [0] sum|M-M^T|, [1] sum M */,
+                   unsigned long long* counts /* [0] entries below the diagonal, [1] matched upper entries */) {
     const int lane = threadIdx.x & 31;
     const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     double sd = 0.0, sm = 0.0;
+    unsigned long long n_lower = 0, n_match = 0;
     for (int64_t row = gwarp; row < n_rows; row += nwarps) {
         for (int64_t k = indptr[row] + lane; k < indptr[row + 1]; k += 32) {
             const int c = idx[k];
             const double a = val[k];
             sm += a;
-            // binary search for `row` among the (ascending) columns of row c
-            int64_t lo = indptr[c], hi = indptr[c + 1];
-            bool found = false;
-            double b = 0.0;
-            while (lo < hi) {
-                const int64_t mid = (lo + hi) >> 1;
-                const int cm = idx[mid];
-                if (cm < row) lo = mid + 1;
-                else if (cm > row) hi = mid;
-                else {
-                    found = true;
-                    b = val[mid];
-                    break;
+            if (UPPER_ONLY) {
+                if (c < row) {
+                    ++n_lower;
+                    continue;
                 }
+                if (c == row) continue;
             }
-            sd += found ? fabs(a - b) : 2.0 * fabs(a);
+            const int64_t pos = hb_find_col(idx, indptr[c], indptr[c + 1], (int)row);
+            const double d = pos >= 0 ? fabs(a - val[pos]) : 2.0 * fabs(a);
+            if (UPPER_ONLY) {
+                sd += pos >= 0 ? 2.0 * d : d;
+                if (pos >= 0) ++n_match;
+            } else {
+                sd += d;
+            }
         }
     }
     sd = hb_warp_sum(sd);
     sm = hb_warp_sum(sm);
+    for (int o = 16; o > 0; o >>= 1) {
+        n_lower += __shfl_xor_sync(0xffffffffu, n_lower, o);
+        n_match += __shfl_xor_sync(0xffffffffu, n_match, o);
+    }
     if (lane == 0) {
         atomicAdd(sums + 0, sd);
         atomicAdd(sums + 1, sm);
+        if (UPPER_ONLY) {
+            atomicAdd(counts + 0, n_lower);
+            atomicAdd(counts + 1, n_match);
+        }
     }
 }
 
@@ -694,15 +832,43 @@ int hb_symmetry(hb_csr* h, double* ratio_out) {
     if (rc) return rc;
     cudaStream_t s = h->stream;
     double* d_sums = nullptr;
-    HB_CUDA(cudaMalloc(&d_sums, sizeof(double) * 2));
-    HB_CUDA(cudaMemsetAsync(d_sums, 0, sizeof(double) * 2, s));
-    if (h->nnz > 0) {
-        hb_symmetry_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, h->n_rows, d_sums);
+    HB_CUDA(cudaMalloc(&d_sums, sizeof(double) * 4));
+    unsigned long long* d_counts = reinterpret_cast<unsigned long long*>(d_sums + 2);
+    double sums[2] = {0, 0};
+    unsigned long long counts[2] = {0, 0};
+    cudaError_t e = cudaMemsetAsync(d_sums, 0, sizeof(double) * 4, s);
+    if (e == cudaSuccess && h->nnz > 0) {
+        // screen: exactly symmetric? (one streaming pass)
+        unsigned long long dg[4] = {0, 1, 2, 3};
+        hb_symmetry_digest_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, h->n_rows,
+                                                                 reinterpret_cast<unsigned long long*>(d_sums));
+        g_hb_launches.fetch_add(1);
+        e = cudaMemcpyAsync(dg, d_sums, sizeof(dg), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e == cudaSuccess && dg[0] == dg[2] && dg[1] == dg[3]) {
+            cudaFree(d_sums);
+            *ratio_out = 0.0;
+            return HB_OK;
+        }
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_sums, 0, sizeof(double) * 4, s);
+    }
+    if (e == cudaSuccess && h->nnz > 0) {
+        hb_symmetry_kernel<true><<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, h->n_rows, d_sums, d_counts);
         g_hb_launches.fetch_add(1);
     }
-    double sums[2] = {0, 0};
-    cudaError_t e = cudaMemcpyAsync(sums, d_sums, sizeof(sums), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sums, d_sums, sizeof(sums), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(counts, d_counts, sizeof(counts), cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess && counts[0] != counts[1]) {
+        // some entry below the diagonal has no partner above it: the one-sided sum missed it -> full two-sided pass
+        e = cudaMemsetAsync(d_sums, 0, sizeof(double) * 4, s);
+        if (e == cudaSuccess) {
+            hb_symmetry_kernel<false><<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, h->n_rows, d_sums, d_counts);
+            g_hb_launches.fetch_add(1);
+            e = cudaMemcpyAsync(sums, d_sums, sizeof(sums), cudaMemcpyDeviceToHost, s);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    }
     cudaFree(d_sums);
     if (e != cudaSuccess) return hb_cuda_fail(e, "symmetry", __FILE__, __LINE__);
     const double cells = (double)h->n_cols * (double)h->n_cols;

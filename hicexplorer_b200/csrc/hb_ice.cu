@@ -460,7 +460,8 @@ int hb_ice_scaled_values(hb_csr* h, double* data_out, double* max_out) {
     cudaError_t e = cudaSuccess;
     if (rc == HB_OK) {
         e = cudaStreamSynchronize(h->stream);
-        if (e == cudaSuccess && h->nnz) e = cudaMemcpy(data_out, d_out, sizeof(double) * (size_t)h->nnz, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && h->nnz && hb_copy_d2h(data_out, d_out, sizeof(double) * (size_t)h->nnz, h->device) != HB_OK)
+            rc = HB_ERR_CUDA;
         if (e == cudaSuccess) e = cudaMemcpy(mx, h->d_scalar_bits, sizeof(mx), cudaMemcpyDeviceToHost);
     }
     cudaFree(d_out);

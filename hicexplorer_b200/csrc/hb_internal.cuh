@@ -129,6 +129,9 @@ int hb_use_device(const hb_csr* h);
 int hb_spmv_grid(int64_t n_rows);
 void hb_peer_release(hb_csr* h);
 void hb_drop_pack(hb_csr* h);
+// multi-threaded staged copies for pageable caller buffers (hb_xfer.cu); synchronous
+int hb_copy_h2d(void* d_dst, const void* h_src, size_t bytes, int device);
+int hb_copy_d2h(void* h_dst, const void* d_src, size_t bytes, int device);
 // exchange buffer p (0/1) of this rank's symmetric region and its flag array
 static inline double* hb_sym_buf(const hb_csr* h, int p) { return (double*)((unsigned char*)h->d_sym + (size_t)p * h->sym_buf_bytes); }
 static inline unsigned long long* hb_sym_flags(const hb_csr* h, int p) {
