@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Multi-GPU parity check, run under torchrun on N >= 2 GPUs:
-  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/check_multigpu.py
+  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tests/multigpu_check.py
 Compares the sharded pipelines (real NCCL all-reduces between processes) with the single-GPU pipelines and the CLI
 run under torchrun with the same command on one GPU.  Exit code 0 = all checks passed."""
 import os
