@@ -66,6 +66,7 @@ SIGNATURES = {
     "hb_pinned_free": (c_int, [vp]),
     "hb_launch_count": (c_u64, []),
     "hb_csr_create": (c_int, [P(vp), c_i64, c_i64, c_i64, c_i64, vp, vp, c_int, vp, c_int]),
+    "hb_csr_create_upper": (c_int, [P(vp), c_i64, c_i64, vp, vp, vp, c_int]),
     "hb_dev_csr_wrap": (c_int, [P(vp), c_i64, c_i64, c_i64, c_i64, vp, vp, vp, c_int]),
     "hb_csr_destroy": (c_int, [vp]),
     "hb_csr_shape": (c_int, [vp, P(c_i64), P(c_i64), P(c_i64), P(c_i64)]),
@@ -84,10 +85,12 @@ SIGNATURES = {
     "hb_mad_filter": (c_int, [vp, c_dbl, c_dbl, vp, vp, vp, vp]),
     "hb_csr_compact": (c_int, [vp, vp]),
     "hb_diag_zero": (c_int, [vp]),
+    "hb_csr_keep_upper": (c_int, [vp]),
     "hb_csr_merge_bins": (c_int, [vp, vp, c_i64]),
     "hb_symmetry": (c_int, [vp, P(c_dbl)]),
     "hb_ice_run": (c_int, [vp, c_int, c_dbl, vp, vp, vp]),
     "hb_ice_scaled_values": (c_int, [vp, vp, P(c_dbl)]),
+    "hb_ice_scaled_upper": (c_int, [vp, vp, c_i64, P(c_i64), vp, vp, vp]),
     "hb_dev_ice_begin": (c_int, [vp, vp]),
     "hb_dev_ice_spmv": (c_int, [vp, vp, c_int, c_int, vp]),
     "hb_dev_ice_update": (c_int, [vp, vp, c_int, c_dbl, vp]),

@@ -10,6 +10,7 @@
 // different order than scipy's, which is exact -- hence bit-identical -- for integer counts below
 // 2^53 (the raw matrices this filter is applied to); see DESIGN.md.
 #include "hb_internal.cuh"
+#include "hb_scan.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // scrub
@@ -244,33 +245,6 @@ static int hb_segment_median(hb_csr* h, const double* d_keys, int mode, HbSelSta
     return HB_OK;
 }
 
-// ---------------------------------------------------------------------------------------------
-// single-block exclusive scan (n up to a few million; runs once per compaction)
-// ---------------------------------------------------------------------------------------------
-template <typename TIn>
-__global__ void __launch_bounds__(1024) hb_scan_kernel(const TIn* __restrict__ in, int64_t* __restrict__ out, int64_t n) {
-    __shared__ long long part[1024];
-    const int t = threadIdx.x;
-    const int64_t chunk = (n + 1023) / 1024;
-    const int64_t b = t * chunk, e = (b + chunk < n) ? b + chunk : n;
-    long long s = 0;
-    for (int64_t i = b; i < e; ++i) s += (long long)in[i];
-    part[t] = s;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan of the 1024 partials
-        long long v = (t >= o) ? part[t - o] : 0;
-        __syncthreads();
-        part[t] += v;
-        __syncthreads();
-    }
-    long long run = part[t] - s;
-    for (int64_t i = b; i < e; ++i) {
-        const long long v = (long long)in[i];
-        out[i] = run;
-        run += v;
-    }
-    if (t == 1023) out[n] = part[1023];
-}
 
 // ---------------------------------------------------------------------------------------------
 // compaction: keep entry (row, col) iff  newid[row] >= 0 && newid[col] >= 0
@@ -281,11 +255,12 @@ struct HbKeepRule {
     const int64_t* __restrict__ seg_off;
     int nseg;
     int cis;
-    int drop_diag;
+    int drop_diag;  // 1: drop the diagonal; 2: drop everything below the diagonal (keep the upper triangle)
     __device__ __forceinline__ bool keep(int64_t grow, int64_t clo, int64_t chi, int c) const {
         if (newid != nullptr && newid[c] < 0) return false;
         if (cis && (c < clo || c >= chi)) return false;
-        if (drop_diag && c == grow) return false;
+        if (drop_diag == 1 && c == grow) return false;
+        if (drop_diag == 2 && c < grow) return false;
         return true;
     }
 };
@@ -816,6 +791,13 @@ int hb_csr_keep_cis(hb_csr* h) {
     if (rc) return rc;
     if (h->nseg <= 1) return HB_OK;
     return hb_compact_impl(h, nullptr, 0, 0, 0, 1, 0);
+}
+
+int hb_csr_keep_upper(hb_csr* h) {
+    HB_REQUIRE(h != nullptr, "null handle");
+    int rc = hb_use_device(h);
+    if (rc) return rc;
+    return hb_compact_impl(h, nullptr, 0, 0, 0, 0, 2);
 }
 
 int hb_diag_zero(hb_csr* h) {

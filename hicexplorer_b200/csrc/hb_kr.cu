@@ -12,6 +12,7 @@
 // per mat-vec (to evaluate the loop conditions), not once per vector operation.
 #include <cmath>
 
+#include "hb_scan.cuh"
 #include "hb_spmv.cuh"
 
 enum {
@@ -348,30 +349,6 @@ hb_kr_upper_fill_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
     }
 }
 
-// local single-block exclusive scan (same scheme as hb_filter.cu)
-__global__ void __launch_bounds__(1024) hb_kr_scan_kernel(const int64_t* __restrict__ in, int64_t* __restrict__ out, int64_t n) {
-    __shared__ long long part[1024];
-    const int t = threadIdx.x;
-    const int64_t chunk = (n + 1023) / 1024;
-    const int64_t b = t * chunk, e = (b + chunk < n) ? b + chunk : n;
-    long long s = 0;
-    for (int64_t i = b; i < e; ++i) s += in[i];
-    part[t] = s;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-        long long v = (t >= o) ? part[t - o] : 0;
-        __syncthreads();
-        part[t] += v;
-        __syncthreads();
-    }
-    long long run = part[t] - s;
-    for (int64_t i = b; i < e; ++i) {
-        const long long v = in[i];
-        out[i] = run;
-        run += v;
-    }
-    if (t == 1023) out[n] = part[1023];
-}
 
 namespace {
 
@@ -727,7 +704,7 @@ int hb_kr_scaled_upper(hb_csr* h, double diag_eps, const double* x, int64_t* nnz
         hb_kr_upper_count_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_indptr, h->d_indices, n, h->row0, d_cnt);
         g_hb_launches.fetch_add(1);
     }
-    hb_kr_scan_kernel<<<1, 1024, 0, s>>>(d_cnt, d_ptr, n);
+    hb_scan_kernel<int64_t><<<1, 1024, 0, s>>>(d_cnt, d_ptr, n);
     g_hb_launches.fetch_add(1);
     int64_t total = 0;
     cudaError_t e = cudaMemcpyAsync(&total, d_ptr + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s);

@@ -13,6 +13,7 @@
 #include <climits>
 
 #include "hb_internal.cuh"
+#include "hb_scan.cuh"
 
 #define HB_MERGE_WINDOW 512  // merged columns accumulated at a time per warp (4 KB of shared memory per warp)
 
@@ -129,29 +130,6 @@ hb_merge_rows_kernel(const int64_t* __restrict__ indptr, const int32_t* __restri
     }
 }
 
-__global__ void __launch_bounds__(1024) hb_merge_scan_kernel(const int64_t* __restrict__ in, int64_t* __restrict__ out, int64_t n) {
-    __shared__ long long part[1024];
-    const int t = threadIdx.x;
-    const int64_t chunk = (n + 1023) / 1024;
-    const int64_t b = t * chunk, e = (b + chunk < n) ? b + chunk : n;
-    long long s = 0;
-    for (int64_t i = b; i < e; ++i) s += in[i];
-    part[t] = s;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-        long long v = (t >= o) ? part[t - o] : 0;
-        __syncthreads();
-        part[t] += v;
-        __syncthreads();
-    }
-    long long run = part[t] - s;
-    for (int64_t i = b; i < e; ++i) {
-        const long long v = in[i];
-        out[i] = run;
-        run += v;
-    }
-    if (t == 1023) out[n] = part[1023];
-}
 
 extern "C" int hb_csr_merge_bins(hb_csr* h, const int32_t* bin_map, int64_t n_new) {
     HB_REQUIRE(h != nullptr && bin_map != nullptr, "bad arguments");
@@ -211,7 +189,7 @@ extern "C" int hb_csr_merge_bins(hb_csr* h, const int32_t* bin_map, int64_t n_ne
                                                          d_cnt, nullptr, nullptr, nullptr);
         g_hb_launches.fetch_add(1);
     }
-    hb_merge_scan_kernel<<<1, 1024, 0, s>>>(d_cnt, d_ptr, n_new);
+    hb_scan_kernel<int64_t><<<1, 1024, 0, s>>>(d_cnt, d_ptr, n_new);
     g_hb_launches.fetch_add(1);
     MG(cudaMemcpyAsync(&new_nnz, d_ptr + n_new, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     MG(cudaStreamSynchronize(s));

@@ -1,0 +1,348 @@
+// The two ends of the file path on the device:
+//   hb_csr_create_upper   what hicmatrix does when it loads a file: the file stores the UPPER triangle, the matrix in
+//                         memory is full symmetric (`M + triu(M, 1).T`; call site hicCorrectMatrix.py:603-609).  Only
+//                         the upper triangle crosses PCIe (half the bytes of hb_csr_create); the mirror image is built
+//                         in HBM.
+//   hb_ice_scaled_upper   what hicmatrix does when it saves: restoreMaskedBins (scatter the kept bins back into the
+//                         original frame) + upper triangle + eliminate_zeros (hicCorrectMatrix.py:779), fused with the
+//                         final ICE scaling (iterativeCorrection.py:56-57, 79) -- the corrected matrix leaves the
+//                         device already in file layout, 12 B per UPPER entry.
+//
+// Symmetrisation = sparse transpose of the strict upper triangle.  Row i of the result is [entries (j, U_ji), j < i,
+// ascending j] ++ [row i of U].  The lower parts are filled through per-row atomic cursors (arrival order is
+// arbitrary) and then each row's lower part is sorted by column in shared memory (bitonic network, keys are unique),
+// so the final layout -- and with it every later floating-point sum -- is deterministic.
+#include "hb_internal.cuh"
+#include "hb_scan.cuh"
+
+__global__ void __launch_bounds__(256)
+hb_sym_count_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, int64_t n,
+                    unsigned int* __restrict__ low_cnt, unsigned int* flags /* [0] = an entry below the diagonal */) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    bool bad = false;
+    for (int64_t row = gwarp; row < n; row += nwarps) {
+        const int64_t e = indptr[row + 1];
+        for (int64_t k = indptr[row] + lane; k < e; k += 32) {
+            const int c = idx[k];
+            if (c < row) bad = true;
+            else if (c > row) atomicAdd(low_cnt + c, 1u);
+        }
+    }
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(flags, 1u);
+}
+
+__global__ void hb_sym_total_kernel(const int64_t* __restrict__ indptr, const unsigned int* __restrict__ low_cnt, int64_t n,
+                                    int64_t* __restrict__ total, unsigned int* max_low) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    unsigned int m = 0;
+    if (i < n) {
+        total[i] = (int64_t)low_cnt[i] + (indptr[i + 1] - indptr[i]);
+        m = low_cnt[i];
+    }
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(max_low, m);
+}
+
+__global__ void __launch_bounds__(256)
+hb_sym_fill_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
+                   int64_t n, const int64_t* __restrict__ out_ptr, const unsigned int* __restrict__ low_cnt,
+                   unsigned int* __restrict__ cursor, int32_t* __restrict__ out_idx, double* __restrict__ out_val) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = gwarp; row < n; row += nwarps) {
+        const int64_t s = indptr[row], e = indptr[row + 1];
+        const int64_t up0 = out_ptr[row] + low_cnt[row];
+        for (int64_t k = s + lane; k < e; k += 32) {
+            const int c = idx[k];
+            const double v = val[k];
+            out_idx[up0 + (k - s)] = c;        // the row's own (upper) entries, in order
+            out_val[up0 + (k - s)] = v;
+            if (c > row) {                      // mirror image into row c, any order for now
+                const int64_t pos = out_ptr[c] + atomicAdd(cursor + c, 1u);
+                out_idx[pos] = (int32_t)row;
+                out_val[pos] = v;
+            }
+        }
+    }
+}
+
+// one CTA per row whose lower part has (P/2, P] entries: sort them by column id in shared memory
+__global__ void hb_sym_sort_kernel(const int64_t* __restrict__ out_ptr, const unsigned int* __restrict__ low_cnt, int64_t n,
+                                   int P, int32_t* __restrict__ out_idx, double* __restrict__ out_val) {
+    extern __shared__ unsigned char smem_raw[];
+    const int64_t row = blockIdx.x;
+    const int L = (int)low_cnt[row];
+    if (L < 2 || L > P || (P > 32 && L <= P / 2)) return;
+    double* sv = reinterpret_cast<double*>(smem_raw);
+    int32_t* sk = reinterpret_cast<int32_t*>(smem_raw + sizeof(double) * (size_t)P);
+    const int64_t base = out_ptr[row];
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        sk[i] = i < L ? out_idx[base + i] : INT32_MAX;
+        sv[i] = i < L ? out_val[base + i] : 0.0;
+    }
+    __syncthreads();
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < P; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const bool asc = (i & k) == 0;
+                    const int a = sk[i], b = sk[ixj];
+                    if ((a > b) == asc) {
+                        sk[i] = b;
+                        sk[ixj] = a;
+                        const double t = sv[i];
+                        sv[i] = sv[ixj];
+                        sv[ixj] = t;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+        out_idx[base + i] = sk[i];
+        out_val[base + i] = sv[i];
+    }
+}
+
+// ---- corrected matrix in file layout -------------------------------------------------------------------------
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+hb_scaled_upper_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
+                       int64_t n_rows, int64_t row0, const double* __restrict__ r, const int64_t* __restrict__ seg_off,
+                       const double* __restrict__ seg_corr, int nseg, const int64_t* __restrict__ orig,
+                       int64_t* __restrict__ cnt_orig, const int64_t* __restrict__ out_ptr, int32_t* __restrict__ out_idx,
+                       double* __restrict__ out_val, unsigned long long* max_bits) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    double m0 = 0.0, m1 = 0.0;
+    for (int64_t row = gwarp; row < n_rows; row += nwarps) {
+        const int64_t g = row0 + row;
+        int lo = 0, hi = nseg;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (seg_off[mid] <= g) lo = mid; else hi = mid;
+        }
+        const double corr = seg_corr[lo];
+        const double ri = r[g];
+        const int64_t og = orig[g];
+        int64_t w = FILL ? out_ptr[og] : 0;
+        long long n_out = 0;
+        const int64_t s = indptr[row], e = indptr[row + 1];
+        for (int64_t base = s; base < e; base += 32) {
+            const int64_t k = base + lane;
+            int c = -1;
+            double f = 0.0, wv = 0.0;
+            if (k < e) {
+                c = idx[k];
+                wv = (val[k] * ri) * r[c];      // iterativeCorrection.py:56-57
+                f = wv * corr * corr;           // :79
+                m0 = fmax(m0, wv);
+                m1 = fmax(m1, f);
+            }
+            const bool kp = c >= g && f != 0.0;  // upper triangle, explicit zeros eliminated
+            const unsigned int bal = __ballot_sync(0xffffffffu, kp);
+            if (FILL && kp) {
+                const int64_t pos = w + __popc(bal & ((1u << lane) - 1u));
+                out_idx[pos] = (int32_t)orig[c];
+                out_val[pos] = f;
+            }
+            w += __popc(bal);
+            n_out += __popc(bal);
+        }
+        if (!FILL && lane == 0) cnt_orig[og] = n_out;
+    }
+    if (FILL) {
+        m0 = hb_warp_max(m0);
+        m1 = hb_warp_max(m1);
+        if (lane == 0) {
+            if (m0 > 0.0) atomicMax(max_bits + 0, (unsigned long long)__double_as_longlong(m0));
+            if (m1 > 0.0) atomicMax(max_bits + 1, (unsigned long long)__double_as_longlong(m1));
+        }
+    }
+}
+
+extern "C" {
+
+int hb_csr_create_upper(hb_csr** out, int64_t n, int64_t nnz_upper, const int64_t* indptr, const int32_t* indices,
+                        const double* data, int device) {
+    HB_REQUIRE(out != nullptr && indptr != nullptr, "bad arguments");
+    // upload the triangle with the ordinary constructor, then replace the store by its symmetric completion
+    int rc = hb_csr_create(out, n, n, 0, nnz_upper, indptr, indices, 0, data, device);
+    if (rc != HB_OK) return rc;
+    hb_csr* h = *out;
+    cudaStream_t s = h->stream;
+    unsigned int *d_low = nullptr, *d_cursor = nullptr, *d_flags = nullptr;
+    int64_t *d_total = nullptr, *d_ptr = nullptr;
+    int32_t* d_idx = nullptr;
+    double* d_val = nullptr;
+    int64_t full_nnz = 0;
+    unsigned int flags[2] = {0, 0};
+    cudaError_t e = cudaSuccess;
+    const int grid = HB_NUM_SMS * 8;
+    const size_t nn = (size_t)(n > 0 ? n : 1);
+#define SY(expr)                                                  \
+    do {                                                          \
+        e = (expr);                                               \
+        if (e != cudaSuccess) {                                   \
+            rc = hb_cuda_fail(e, #expr, __FILE__, __LINE__);      \
+            goto fail;                                            \
+        }                                                         \
+    } while (0)
+    SY(cudaMalloc(&d_low, sizeof(unsigned int) * nn));
+    SY(cudaMalloc(&d_cursor, sizeof(unsigned int) * nn));
+    SY(cudaMalloc(&d_flags, sizeof(unsigned int) * 2));
+    SY(cudaMalloc(&d_total, sizeof(int64_t) * (nn + 1)));
+    SY(cudaMalloc(&d_ptr, sizeof(int64_t) * (nn + 1)));
+    SY(cudaMemsetAsync(d_low, 0, sizeof(unsigned int) * nn, s));
+    SY(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned int) * nn, s));
+    SY(cudaMemsetAsync(d_flags, 0, sizeof(unsigned int) * 2, s));
+    if (n > 0) {
+        hb_sym_count_kernel<<<grid, 256, 0, s>>>(h->d_indptr, h->d_indices, n, d_low, d_flags);
+        g_hb_launches.fetch_add(1);
+        hb_sym_total_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->d_indptr, d_low, n, d_total, d_flags + 1);
+        g_hb_launches.fetch_add(1);
+    }
+    hb_scan_kernel<int64_t><<<1, 1024, 0, s>>>(d_total, d_ptr, n);
+    g_hb_launches.fetch_add(1);
+    SY(cudaMemcpyAsync(&full_nnz, d_ptr + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    SY(cudaMemcpyAsync(flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost, s));
+    SY(cudaStreamSynchronize(s));
+    if (flags[0]) {
+        hb_set_error("hb_csr_create_upper: the input has entries below the diagonal");
+        rc = HB_ERR_INVALID_ARG;
+        goto fail;
+    }
+    if (flags[1] > 16384u) {
+        hb_set_error("hb_csr_create_upper: a column holds %u entries above the diagonal (limit 16384); "
+                     "symmetrise on the host and use hb_csr_create", flags[1]);
+        rc = HB_ERR_INVALID_ARG;
+        goto fail;
+    }
+    SY(cudaMalloc(&d_idx, sizeof(int32_t) * (size_t)(full_nnz > 0 ? full_nnz : 1) + 16));
+    SY(cudaMalloc(&d_val, sizeof(double) * (size_t)(full_nnz > 0 ? full_nnz : 1) + 16));
+    if (n > 0 && full_nnz > 0) {
+        hb_sym_fill_kernel<<<grid, 256, 0, s>>>(h->d_indptr + 0, h->d_indices, h->d_data, n, d_ptr, d_low, d_cursor, d_idx, d_val);
+        g_hb_launches.fetch_add(1);
+        // size classes: P = 32 sorts lower parts of 2..32 entries, P > 32 those of (P/2, P] entries
+        for (int P = 32; P <= 16384 && (P == 32 ? flags[1] >= 2u : flags[1] > (unsigned int)(P / 2)); P <<= 1) {
+            const size_t smem = (sizeof(double) + sizeof(int32_t)) * (size_t)P;
+            if (smem > 48 * 1024)
+                SY(cudaFuncSetAttribute(hb_sym_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            hb_sym_sort_kernel<<<(unsigned)n, P >= 512 ? 256 : (P >= 64 ? P / 2 : 32), smem, s>>>(d_ptr, d_low, n, P, d_idx, d_val);
+            g_hb_launches.fetch_add(1);
+        }
+    }
+    SY(cudaStreamSynchronize(s));
+    SY(cudaGetLastError());
+#undef SY
+    cudaFree(d_low);
+    cudaFree(d_cursor);
+    cudaFree(d_flags);
+    cudaFree(d_total);
+    cudaFree(h->d_indptr);
+    cudaFree(h->d_indices);
+    cudaFree(h->d_data);
+    h->d_indptr = d_ptr;
+    h->d_indices = d_idx;
+    h->d_data = d_val;
+    h->phase = 0;
+    h->nnz = full_nnz;
+    return HB_OK;
+fail:
+    cudaFree(d_low);
+    cudaFree(d_cursor);
+    cudaFree(d_flags);
+    cudaFree(d_total);
+    cudaFree(d_ptr);
+    cudaFree(d_idx);
+    cudaFree(d_val);
+    hb_csr_destroy(h);
+    *out = nullptr;
+    return rc;
+}
+
+int hb_ice_scaled_upper(hb_csr* h, const int64_t* orig_ids, int64_t n_orig, int64_t* nnz_out, int64_t* indptr,
+                        int32_t* indices, double* data) {
+    HB_REQUIRE(h != nullptr && h->state_ready && orig_ids != nullptr && nnz_out != nullptr, "run ICE first");
+    HB_REQUIRE(n_orig >= h->n_cols && n_orig < 2147483647LL, "bad original frame size");
+    int rc = hb_use_device(h);
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    const int64_t n = h->n_cols;
+    for (int64_t i = 0; i < n; ++i)
+        HB_REQUIRE(orig_ids[i] >= 0 && orig_ids[i] < n_orig && (i == 0 || orig_ids[i] > orig_ids[i - 1]),
+                   "original ids must be strictly ascending and inside the original frame");
+    int64_t *d_orig = nullptr, *d_cnt = nullptr, *d_ptr = nullptr;
+    int32_t* d_idx = nullptr;
+    double* d_val = nullptr;
+    int64_t total = 0;
+    double mx[2] = {0.0, 0.0};
+    cudaError_t e = cudaSuccess;
+    const int grid = HB_NUM_SMS * 8;
+#define SU(expr)                                                  \
+    do {                                                          \
+        e = (expr);                                               \
+        if (e != cudaSuccess) {                                   \
+            rc = hb_cuda_fail(e, #expr, __FILE__, __LINE__);      \
+            goto done;                                            \
+        }                                                         \
+    } while (0)
+    SU(cudaMalloc(&d_orig, sizeof(int64_t) * (size_t)(n > 0 ? n : 1)));
+    SU(cudaMalloc(&d_cnt, sizeof(int64_t) * (size_t)(n_orig + 1)));
+    SU(cudaMalloc(&d_ptr, sizeof(int64_t) * (size_t)(n_orig + 1)));
+    if (n > 0) SU(cudaMemcpyAsync(d_orig, orig_ids, sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, s));
+    SU(cudaMemsetAsync(d_cnt, 0, sizeof(int64_t) * (size_t)(n_orig + 1), s));
+    if (h->n_rows > 0) {
+        hb_scaled_upper_kernel<false><<<grid, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, h->n_rows, h->row0, h->d_r,
+                                                           h->d_seg_off, h->d_seg_corr, h->nseg, d_orig, d_cnt, nullptr,
+                                                           nullptr, nullptr, nullptr);
+        g_hb_launches.fetch_add(1);
+    }
+    hb_scan_kernel<int64_t><<<1, 1024, 0, s>>>(d_cnt, d_ptr, n_orig);
+    g_hb_launches.fetch_add(1);
+    SU(cudaMemcpyAsync(&total, d_ptr + n_orig, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    SU(cudaStreamSynchronize(s));
+    *nnz_out = total;
+    if (indptr != nullptr && indices != nullptr && data != nullptr) {
+        SU(cudaMalloc(&d_idx, sizeof(int32_t) * (size_t)(total > 0 ? total : 1)));
+        SU(cudaMalloc(&d_val, sizeof(double) * (size_t)(total > 0 ? total : 1)));
+        SU(cudaMemsetAsync(h->d_scalar_bits, 0, sizeof(unsigned long long) * 2, s));
+        if (h->n_rows > 0 && total > 0) {
+            hb_scaled_upper_kernel<true><<<grid, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, h->n_rows, h->row0, h->d_r,
+                                                              h->d_seg_off, h->d_seg_corr, h->nseg, d_orig, nullptr, d_ptr,
+                                                              d_idx, d_val, h->d_scalar_bits);
+            g_hb_launches.fetch_add(1);
+        }
+        SU(cudaMemcpyAsync(mx, h->d_scalar_bits, sizeof(mx), cudaMemcpyDeviceToHost, s));
+        SU(cudaStreamSynchronize(s));
+        SU(cudaGetLastError());
+        SU(cudaMemcpy(indptr, d_ptr, sizeof(int64_t) * (size_t)(n_orig + 1), cudaMemcpyDeviceToHost));
+        if (total > 0) {
+            rc = hb_copy_d2h(indices, d_idx, sizeof(int32_t) * (size_t)total, h->device);
+            if (rc == HB_OK) rc = hb_copy_d2h(data, d_val, sizeof(double) * (size_t)total, h->device);
+        }
+        if (rc == HB_OK && mx[0] > 1e100) {
+            hb_set_error("matrix correction is producing extremely large values (> 1e100)");
+            rc = HB_ERR_OVERFLOW_ITER;
+        } else if (rc == HB_OK && mx[1] > 1e10) {
+            hb_set_error("matrix correction produced extremely large values (> 1e10)");
+            rc = HB_ERR_OVERFLOW_FINAL;
+        }
+    }
+#undef SU
+done:
+    cudaFree(d_orig);
+    cudaFree(d_cnt);
+    cudaFree(d_ptr);
+    cudaFree(d_idx);
+    cudaFree(d_val);
+    return rc;
+}
+
+}  // extern "C"

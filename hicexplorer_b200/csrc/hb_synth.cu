@@ -10,6 +10,7 @@
 #include <algorithm>
 
 #include "hb_internal.cuh"
+#include "hb_scan.cuh"
 
 #define HB_SYNTH_MAX_TRANS 32
 #define HB_TAG_BASE (1ull << 40)
@@ -165,29 +166,6 @@ hb_synth_rows_kernel(HbSynthDev p, const int64_t* __restrict__ chrom_off, int nc
     }
 }
 
-__global__ void __launch_bounds__(1024) hb_synth_scan_kernel(const int64_t* __restrict__ in, int64_t* __restrict__ out, int64_t n) {
-    __shared__ long long part[1024];
-    const int t = threadIdx.x;
-    const int64_t chunk = (n + 1023) / 1024;
-    const int64_t b = t * chunk, e = (b + chunk < n) ? b + chunk : n;
-    long long s = 0;
-    for (int64_t i = b; i < e; ++i) s += in[i];
-    part[t] = s;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-        long long v = (t >= o) ? part[t - o] : 0;
-        __syncthreads();
-        part[t] += v;
-        __syncthreads();
-    }
-    long long run = part[t] - s;
-    for (int64_t i = b; i < e; ++i) {
-        const long long v = in[i];
-        out[i] = run;
-        run += v;
-    }
-    if (t == 1023) out[n] = part[1023];
-}
 
 extern "C" int hb_synth_create(hb_csr** out, const hb_synth_params* prm, const int64_t* chrom_bins, int64_t row0,
                                int64_t n_rows, int device) {
@@ -255,7 +233,7 @@ extern "C" int hb_synth_create(hb_csr** out, const hb_synth_params* prm, const i
         hb_synth_rows_kernel<false><<<grid, 256, 0, s>>>(p, d_off, prm->nchrom, d_g, row0, n_rows, d_cnt, nullptr, nullptr, nullptr);
         g_hb_launches.fetch_add(1);
     }
-    hb_synth_scan_kernel<<<1, 1024, 0, s>>>(d_cnt, d_indptr, n_rows);
+    hb_scan_kernel<int64_t><<<1, 1024, 0, s>>>(d_cnt, d_indptr, n_rows);
     g_hb_launches.fetch_add(1);
     SY(cudaMemcpyAsync(&nnz, d_indptr + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     SY(cudaStreamSynchronize(s));

@@ -173,9 +173,14 @@ def _correct_ice(ma, args, world=1, rank=0):
         if rank != 0:
             return
     else:
-        res = ice_pipeline(ma.matrix, (args.filterThreshold[0], args.filterThreshold[1]), max_iter=args.iterNum,
-                           tolerance=args.tolerance, chr_offsets=ma.chromosome_offsets(), perchr=args.perchr,
-                           skip_diagonal=args.skipDiagonal, device=args.device, want_matrix=True, extra_mask_fn=extra_fn)
+        # the file's upper triangle goes to the device as it is (the mirror image is built in HBM) and the corrected
+        # matrix comes back already in file layout, whenever nothing on the host has touched the matrix since loading
+        up = ma.upper_for_device()
+        file_layout = not args.perchr or str(args.outFileName).endswith('.h5')
+        res = ice_pipeline(up if up is not None else ma.matrix, (args.filterThreshold[0], args.filterThreshold[1]),
+                           max_iter=args.iterNum, tolerance=args.tolerance, chr_offsets=ma.chromosome_offsets(),
+                           perchr=args.perchr, skip_diagonal=args.skipDiagonal, device=args.device, want_matrix=file_layout,
+                           extra_mask_fn=extra_fn, upper_input=up is not None, file_layout=file_layout)
     n = res['n']
     keep1 = np.setdiff1d(np.arange(n), res['zero_bins'])
     outlier_regions = res['outliers_rel']
@@ -191,13 +196,19 @@ def _correct_ice(ma, args, world=1, rank=0):
     for k, it in enumerate(iters):
         if res['deviation'][k] < args.tolerance:
             log.info("[iterative correction] {} iterations used\n".format(int(it) + 1))
-    # install the corrected matrix / factors in the kept frame; save() re-inserts the masked bins as nan_bins
-    corrected = res['matrix']
-    if not args.perchr or str(args.outFileName).endswith('.h5'):
-        ma.apply_mask_bookkeeping(res['kept'], matrix=corrected)
+    if 'upper' in res:
+        # corrected upper triangle in the original frame + NaN-padded factors: what setMatrixValues,
+        # setCorrectionFactors and restoreMaskedBins (inside save) would assemble on the host
+        factors = np.full(n, np.nan)
+        factors[res['kept']] = res['bias']
+        ma.install_file_layout(res['upper'], np.setdiff1d(np.arange(n), res['kept']), factors)
     else:
-        ma.apply_mask_bookkeeping(res['kept'])     # perchr + .cool keeps the raw counts (hicCorrectMatrix.py:759-760)
-    ma.setCorrectionFactors(res['bias'])
+        # install the corrected matrix / factors in the kept frame; save() re-inserts the masked bins as nan_bins
+        if 'matrix' in res:
+            ma.apply_mask_bookkeeping(res['kept'], matrix=res['matrix'])
+        else:
+            ma.apply_mask_bookkeeping(res['kept'])     # perchr + .cool keeps the raw counts (hicCorrectMatrix.py:759-760)
+        ma.setCorrectionFactors(res['bias'])
     log.info("Total regions to be removed: {}".format(n - len(res['kept'])))
 
 

@@ -30,7 +30,9 @@ def _to_str(x):
 
 class hiCMatrix(object):
     def __init__(self, pMatrixFile=None, pChrnameList=None):
-        self.matrix = None
+        self._matrix = None          # full symmetric CSR (built lazily from _upper)
+        self._upper = None           # upper triangle as stored in the file, while nothing has modified the matrix
+        self._file_layout = None     # corrected upper triangle in the original frame, ready to be written
         self.cut_intervals = []
         self.nan_bins = np.array([], dtype=np.int64)
         self.correction_factors = None
@@ -46,13 +48,38 @@ class hiCMatrix(object):
                 self._load_h5(pMatrixFile)
             self._index_intervals()
 
+    @property
+    def matrix(self):
+        """full symmetric scipy CSR, like hicmatrix keeps it; symmetrised on first use"""
+        if self._matrix is None and self._upper is not None:
+            self._matrix = self._fill_lower(self._upper)
+        return self._matrix
+
+    @matrix.setter
+    def matrix(self, value):
+        self._matrix = value
+        self._upper = None
+        self._file_layout = None
+
+    def upper_for_device(self):
+        """the file's upper triangle if the matrix is still exactly what was loaded (the device can then build the
+        symmetric store itself and only half the bytes are uploaded), else None"""
+        return self._upper
+
+    def install_file_layout(self, upper, nan_bins, correction_factors):
+        """take a corrected matrix that is already in file layout (upper triangle, original frame): what
+        setMatrixValues + setCorrectionFactors + restoreMaskedBins would produce, computed on the device"""
+        self._file_layout = upper
+        self.nan_bins = np.asarray(nan_bins, dtype=np.int64)
+        self.correction_factors = correction_factors
+
     # ---- loading ------------------------------------------------------------------------------------
     def _load_h5(self, path):
         f = hdf5lite.File(path)
         shape = tuple(int(v) for v in f["matrix/shape"].read())
         up = sparse.csr_matrix((f["matrix/data"].read(), f["matrix/indices"].read(), f["matrix/indptr"].read()),
                                shape=shape)
-        self.matrix = self._fill_lower(up)
+        self._set_upper(up)
         chrom = f["intervals/chr_list"].read()
         start = f["intervals/start_list"].read()
         end = f["intervals/end_list"].read()
@@ -72,7 +99,7 @@ class hiCMatrix(object):
         b2 = f["pixels/bin2_id"].read()
         cnt = f["pixels/count"].read()
         up = sparse.csr_matrix((cnt, (b1, b2)), shape=(n, n))
-        self.matrix = self._fill_lower(up)
+        self._set_upper(up)
         self.cut_intervals = [(names[c], int(s), int(e), 1.0) for c, s, e in zip(chrom_id, start, end)]
         if "weight" in f["bins"].keys():
             self.correction_factors = f["bins/weight"].read()
@@ -80,6 +107,16 @@ class hiCMatrix(object):
         if chrnames:
             self._index_intervals()
             self.reorderChromosomes(chrnames)
+
+    def _set_upper(self, up):
+        up = sparse.csr_matrix(up)
+        up.sum_duplicates()
+        if sparse.tril(up, -1).nnz:          # a file that stores both triangles: nothing to mirror
+            self._matrix = up
+            self._upper = None
+        else:
+            self._matrix = None
+            self._upper = up
 
     @staticmethod
     def _fill_lower(up):
@@ -229,7 +266,8 @@ class hiCMatrix(object):
 
     # ---- saving ----------------------------------------------------------------------------------------------
     def save(self, pMatrixName, pSymmetric=True, pApplyCorrection=False):
-        self.restoreMaskedBins()
+        if self._file_layout is None:
+            self.restoreMaskedBins()
         if str(pMatrixName).endswith(".cool"):
             self._save_cool(pMatrixName)
         else:
@@ -237,14 +275,16 @@ class hiCMatrix(object):
                 pMatrixName = str(pMatrixName) + ".h5"
             self._save_h5(pMatrixName)
 
-    def _upper(self):
+    def _upper_of_matrix(self):
+        if self._file_layout is not None:
+            return self._file_layout
         up = sparse.triu(self.matrix, k=0, format="csr")
         up.eliminate_zeros()
         up.sort_indices()
         return up
 
     def _save_h5(self, path):
-        up = self._upper()
+        up = self._upper_of_matrix()
         carray = {"CLASS": "ARRAY", "VERSION": "2.4", "TITLE": "", "FLAVOR": "numpy"}
         group = {"CLASS": "GROUP", "VERSION": "1.0", "TITLE": ""}
         w = hdf5lite.Writer({"TITLE": "HiCExplorer matrix", "CLASS": "GROUP", "VERSION": "1.0",
@@ -268,7 +308,7 @@ class hiCMatrix(object):
         w.save(path)
 
     def _save_cool(self, path):
-        up = self._upper().tocoo()
+        up = self._upper_of_matrix().tocoo()
         chrom, start, end, _extra = zip(*self.cut_intervals)
         names = list(OrderedDict.fromkeys(chrom))
         ids = {c: i for i, c in enumerate(names)}

@@ -23,7 +23,8 @@ def _segment_offsets_after(mask_removed, offsets):
 
 
 def ice_pipeline(matrix, filter_threshold, max_iter=500, tolerance=1e-5, chr_offsets=None, perchr=False,
-                 skip_diagonal=False, device=0, want_matrix=True, extra_mask_fn=None):
+                 skip_diagonal=False, device=0, want_matrix=True, extra_mask_fn=None, upper_input=False,
+                 file_layout=False):
     """ICE branch of the driver.
 
     matrix           full symmetric scipy matrix in the original bin frame (n bins)
@@ -32,6 +33,11 @@ def ice_pipeline(matrix, filter_threshold, max_iter=500, tolerance=1e-5, chr_off
     perchr           statistics and correction per chromosome block (--perchr)
     extra_mask_fn    optional callable(kept_bins) -> bool mask over the bins that survived the MAD
                      filter, for the host-side --sequencedCountCutoff filter
+
+    upper_input      ``matrix`` holds only the upper triangle (what the files store): half the upload, the mirror
+                     image is built on the device (hb_csr_create_upper)
+    file_layout      return ``upper`` = corrected matrix as the files store it (upper triangle, zeros eliminated,
+                     original n-bin frame; hicmatrix restoreMaskedBins + triu, done on the device) instead of ``matrix``
 
     Returns a dict:
       zero_bins      original ids removed because their row sum is 0        (:612-616)
@@ -46,7 +52,7 @@ def ice_pipeline(matrix, filter_threshold, max_iter=500, tolerance=1e-5, chr_off
     m = canonical_csr(matrix)
     n = m.shape[0]
     lo, hi = filter_threshold
-    with DeviceCSR.from_scipy(m, device=device) as dev:
+    with (DeviceCSR.from_upper(m, device=device) if upper_input else DeviceCSR.from_scipy(m, device=device)) as dev:
         # mask all zero value bins: row sums include the diagonal and NaNs propagate, as in the
         # reference where this happens before the NaN/Inf scrub
         row_sum, _ = dev.row_stats()
@@ -83,7 +89,9 @@ def ice_pipeline(matrix, filter_threshold, max_iter=500, tolerance=1e-5, chr_off
         bias, iters, deviation = dev.ice(max_iter, tolerance)
         out = dict(zero_bins=zero_bins, outliers_rel=outliers_rel, kept=kept, bias=bias,
                    iterations=iters, deviation=deviation, n=n)
-        if want_matrix:
+        if want_matrix and file_layout:
+            out["upper"] = dev.ice_scaled_upper(kept, n)
+        elif want_matrix:
             values = dev.ice_scaled_values()
             pattern = dev.download()
             out["matrix"] = sparse.csr_matrix((values, pattern.indices, pattern.indptr), shape=pattern.shape)

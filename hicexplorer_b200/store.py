@@ -58,6 +58,19 @@ class DeviceCSR(object):
         return cls(h, device)
 
     @classmethod
+    def from_upper(cls, upper, device=0):
+        """Upload only the upper triangle (file layout) and build the full symmetric store on the device."""
+        _lib.require_device()
+        m = canonical_csr(upper)
+        n = m.shape[0]
+        indptr = np.ascontiguousarray(m.indptr, dtype=np.int64)
+        indices = np.ascontiguousarray(m.indices, dtype=np.int32)
+        data = np.ascontiguousarray(m.data, dtype=np.float64)
+        h = ctypes.c_void_p()
+        check(lib().hb_csr_create_upper(ctypes.byref(h), n, int(m.nnz), ptr(indptr), ptr(indices), ptr(data), device))
+        return cls(h, device)
+
+    @classmethod
     def wrap_device(cls, n_rows, n_cols, row0, nnz, d_indptr, d_indices, d_data, device=0):
         """Zero-copy view of arrays already in HBM (raw device pointers, e.g. ``tensor.data_ptr()``)."""
         _lib.require_device()
@@ -200,6 +213,9 @@ class DeviceCSR(object):
         check(lib().hb_csr_merge_bins(self._h, ptr(m), int(n_new)))
         self._segments = 1
 
+    def keep_upper(self):
+        check(lib().hb_csr_keep_upper(self._h))
+
     def diag_zero(self):
         check(lib().hb_diag_zero(self._h))
 
@@ -225,6 +241,18 @@ class DeviceCSR(object):
         mx = ctypes.c_double()
         check(lib().hb_ice_scaled_values(self._h, ptr(out), ctypes.byref(mx)))
         return out
+
+    def ice_scaled_upper(self, orig_ids, n_orig):
+        """Corrected matrix in file layout: upper triangle, zeros eliminated, in the original n_orig-bin frame."""
+        orig = np.ascontiguousarray(orig_ids, dtype=np.int64)
+        nnz = ctypes.c_int64()
+        check(lib().hb_ice_scaled_upper(self._h, ptr(orig), int(n_orig), ctypes.byref(nnz), None, None, None))
+        indptr = np.empty(n_orig + 1, dtype=np.int64)
+        indices = np.empty(nnz.value, dtype=np.int32)
+        data = np.empty(nnz.value, dtype=np.float64)
+        check(lib().hb_ice_scaled_upper(self._h, ptr(orig), int(n_orig), ctypes.byref(nnz), ptr(indptr), ptr(indices),
+                                        ptr(data)))
+        return sparse.csr_matrix((data, indices, indptr), shape=(n_orig, n_orig))
 
     # ---- Knight-Ruiz ------------------------------------------------------------
     def kr(self, tol=KR_TOL, delta=KR_DELTA, Delta=KR_DELTA_UPPER, diag_eps=KR_DIAG_EPS, max_outer=100000):

@@ -86,6 +86,11 @@ HB_API uint64_t hb_launch_count(void);
 HB_API int hb_csr_create(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t row0, int64_t nnz,
                   const int64_t* indptr, const void* indices, int indices_i64, const double* data,
                   int device);
+/* Same store from the UPPER triangle only (what .h5 / .cool files hold; hicmatrix symmetrises on load,
+ * call site hicCorrectMatrix.py:603-609): half the bytes cross PCIe, the mirror image is built in HBM with ascending
+ * columns.  Entries below the diagonal are an error; a column may hold at most 16384 entries above the diagonal. */
+HB_API int hb_csr_create_upper(hb_csr** out, int64_t n, int64_t nnz_upper, const int64_t* indptr, const int32_t* indices,
+                        const double* data, int device);
 /* wrap device arrays already in HBM (not copied, not owned). indptr must be block-local (indptr[0]==0). */
 HB_API int hb_dev_csr_wrap(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t row0, int64_t nnz,
                     const int64_t* d_indptr, const int32_t* d_indices, const double* d_data, int device);
@@ -158,6 +163,8 @@ HB_API int hb_mad_filter(hb_csr* h, double lo, double hi, uint8_t* mask_out, dou
                   double* median_out /*nseg*/, double* mad_out /*nseg*/);
 HB_API int hb_csr_compact(hb_csr* h, const uint8_t* remove_mask);
 HB_API int hb_diag_zero(hb_csr* h);
+/* keep only the upper triangle (column >= row) of the block: the file layout (inverse of hb_csr_create_upper) */
+HB_API int hb_csr_keep_upper(hb_csr* h);
 HB_API int hb_symmetry(hb_csr* h, double* ratio_out);
 
 /* ---- bin merging (the step before correction) ----------------------------------
@@ -185,6 +192,12 @@ HB_API int hb_csr_merge_bins(hb_csr* h, const int32_t* bin_map, int64_t n_new);
 HB_API int hb_ice_run(hb_csr* h, int max_iter, double tol, double* bias_out, int32_t* iters_out,
                double* dev_out);
 HB_API int hb_ice_scaled_values(hb_csr* h, double* data_out, double* max_out);
+/* The corrected matrix in FILE layout: upper triangle, exact zeros eliminated, scattered back into the original
+ * n_orig-bin frame (orig_ids[i] = original id of bin i, strictly ascending) -- hicmatrix restoreMaskedBins + triu at
+ * save time (hicCorrectMatrix.py:779), fused with the final scaling.  Two calls: with indptr/indices/data NULL to get
+ * nnz_out, then with indptr[n_orig+1], indices[nnz], data[nnz].  Same overflow codes as hb_ice_scaled_values. */
+HB_API int hb_ice_scaled_upper(hb_csr* h, const int64_t* orig_ids, int64_t n_orig, int64_t* nnz_out, int64_t* indptr,
+                        int32_t* indices, double* data);
 
 /* Step-level device API (all vectors are device fp64[n_cols], replicated per rank).
  *   hb_dev_ice_begin : bias = 1, r = 1, clear convergence state.

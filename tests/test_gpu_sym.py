@@ -1,0 +1,59 @@
+"""Device symmetrisation (upper triangle -> full store) and the corrected matrix in file layout."""
+import numpy as np
+import pytest
+from scipy import sparse
+
+from hicexplorer_b200 import _lib
+from hicexplorer_b200.store import DeviceCSR
+from oracle import ice_oracle
+from tests.helpers import full_from_pixels, random_hic
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n,density,seed", [(300, 0.2, 0), (2000, 0.05, 1), (50, 0.9, 2), (5000, 0.3, 3), (1, 1.0, 4)])
+def test_from_upper_equals_full_upload(n, density, seed):
+    full = random_hic(n, density, seed, empty_frac=0.02)
+    up = sparse.triu(full, 0, format="csr")
+    with DeviceCSR.from_upper(up) as dev:
+        got = dev.download()
+        assert dev.symmetry_ratio() == 0.0
+    assert np.array_equal(got.indptr, full.indptr)
+    assert np.array_equal(got.indices, full.indices)          # ascending columns, deterministic layout
+    np.testing.assert_array_equal(got.data, full.data)
+
+
+def test_from_upper_rejects_lower_entries():
+    full = random_hic(100, 0.2, 5)
+    with pytest.raises(ValueError, match="below the diagonal"):
+        DeviceCSR.from_upper(full)
+
+
+def test_from_upper_then_ice_is_bit_identical(gm12878):
+    full = full_from_pixels(gm12878)
+    with DeviceCSR.from_scipy(full) as a, DeviceCSR.from_upper(sparse.triu(full, 0, format="csr")) as b:
+        ba, ia, _ = a.ice(20, 0.0)
+        bb, ib, _ = b.ice(20, 0.0)
+    np.testing.assert_array_equal(ba, bb)
+
+
+def test_scaled_upper_is_the_file_layout(gm12878):
+    from hicexplorer_b200.pipeline import ice_pipeline, scatter_to_frame
+    full = full_from_pixels(gm12878)
+    ref = ice_pipeline(full, (-1.5, 5.0), max_iter=500)
+    want = sparse.triu(scatter_to_frame(ref["matrix"], ref["kept"], ref["n"]), 0, format="csr")
+    want.eliminate_zeros()
+    want.sort_indices()
+    n = full.shape[0]
+    keep = np.zeros(n, dtype=bool)
+    keep[ref["kept"]] = True
+    with DeviceCSR.from_scipy(full) as dev:
+        dev.compact((~keep).astype(np.uint8))
+        dev.scrub()
+        dev.ice(500, 1e-5)
+        got = dev.ice_scaled_upper(ref["kept"], n)
+    assert got.shape == (n, n)
+    assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
+    np.testing.assert_array_equal(got.data, want.data)
+    oracle = ice_oracle.correct_ice_pipeline(full, -1.5, 5.0, max_iter=500)
+    np.testing.assert_allclose(got.data, oracle["upper"].data, rtol=1e-8)
