@@ -455,8 +455,9 @@ __device__ __forceinline__ int64_t hb_find_col(const int32_t* __restrict__ idx, 
 
 // Fast exact-symmetry screen: one streaming pass, no look-ups.  Every entry (i, j, a) contributes the fingerprint
 // f(i, j, bits(a)) to multiset A and f(j, i, bits(a)) to multiset B; the matrix equals its transpose iff A == B.
-// The multisets are compared through two commutative 64-bit digests each (sum and xor of a mixed key), so the
-// accumulation order is irrelevant and a false "equal" needs a ~2^-64 collision.  Matrices that are symmetric by
+// The multisets are compared through two commutative 64-bit digests each (sums mod 2^64 of two differently mixed keys),
+// so the accumulation order -- and the sharding: row blocks add their digests with one allreduce -- is irrelevant and a
+// false "equal" needs a ~2^-64 collision.  Matrices that are symmetric by
 // construction (what the driver produces, hicmatrix symmetric fill) take this path: ratio = 0 exactly, as numpy
 // would compute.  Anything else falls through to the exact |M - M^T| pass below, which yields the ratio itself.
 __device__ __forceinline__ unsigned long long hb_mixkey(unsigned long long z) {
@@ -470,14 +471,15 @@ __device__ __forceinline__ unsigned long long hb_mixkey(unsigned long long z) {
 
 __global__ void __launch_bounds__(256)
 hb_symmetry_digest_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
-                          int64_t n_rows, unsigned long long* digest /* [0..1] A: sum, xor ; [2..3] B: sum, xor */) {
+                          int64_t n_rows, int64_t row0, unsigned long long* digest /* [0..1] A ; [2..3] B */) {
     const int lane = threadIdx.x & 31;
     const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     unsigned long long sa = 0, xa = 0, sb = 0, xb = 0;
-    for (int64_t row = gwarp; row < n_rows; row += nwarps) {
-        const int64_t e = indptr[row + 1];
-        for (int64_t k = indptr[row] + lane; k < e; k += 32 * 4) {
+    for (int64_t lrow = gwarp; lrow < n_rows; lrow += nwarps) {
+        const int64_t e = indptr[lrow + 1];
+        const unsigned long long row = (unsigned long long)(row0 + lrow);
+        for (int64_t k = indptr[lrow] + lane; k < e; k += 32 * 4) {
             int c[4];
             double v[4];
 #pragma unroll
@@ -488,27 +490,34 @@ hb_symmetry_digest_kernel(const int64_t* __restrict__ indptr, const int32_t* __r
             for (int j = 0; j < 4; ++j) {
                 if (c[j] < 0) continue;
                 const unsigned long long bits = hb_mixkey((unsigned long long)__double_as_longlong(v[j]));
-                const unsigned long long ka = hb_mixkey((((unsigned long long)row << 32) | (unsigned int)c[j]) ^ bits);
-                const unsigned long long kb = hb_mixkey((((unsigned long long)(unsigned int)c[j] << 32) | (unsigned long long)row) ^ bits);
+                const unsigned long long ka = hb_mixkey(((row << 32) | (unsigned int)c[j]) ^ bits);
+                const unsigned long long kb = hb_mixkey((((unsigned long long)(unsigned int)c[j] << 32) | row) ^ bits);
                 sa += ka;
-                xa ^= hb_mixkey(ka + 0x9E3779B97F4A7C15ull);
+                xa += hb_mixkey(ka + 0x9E3779B97F4A7C15ull);
                 sb += kb;
-                xb ^= hb_mixkey(kb + 0x9E3779B97F4A7C15ull);
+                xb += hb_mixkey(kb + 0x9E3779B97F4A7C15ull);
             }
         }
     }
     for (int o = 16; o > 0; o >>= 1) {
         sa += __shfl_xor_sync(0xffffffffu, sa, o);
         sb += __shfl_xor_sync(0xffffffffu, sb, o);
-        xa ^= __shfl_xor_sync(0xffffffffu, xa, o);
-        xb ^= __shfl_xor_sync(0xffffffffu, xb, o);
+        xa += __shfl_xor_sync(0xffffffffu, xa, o);
+        xb += __shfl_xor_sync(0xffffffffu, xb, o);
     }
     if (lane == 0) {
         atomicAdd(digest + 0, sa);
-        atomicXor(digest + 1, xa);
+        atomicAdd(digest + 1, xa);
         atomicAdd(digest + 2, sb);
-        atomicXor(digest + 3, xb);
+        atomicAdd(digest + 3, xb);
     }
+}
+
+// the path's only collective is a sum-allreduce of doubles: ship each 64-bit digest as four 16-bit limbs (limb sums
+// over <= 2^30 ranks are exact in fp64) and recombine mod 2^64 on the host
+__global__ void hb_digest_limbs_kernel(const unsigned long long* __restrict__ digest, double* __restrict__ limbs) {
+    const int t = threadIdx.x;
+    if (t < 16) limbs[t] = (double)((digest[t >> 2] >> (16 * (t & 3))) & 0xffffull);
 }
 
 // UPPER_ONLY: only entries above the diagonal look up their transposed partner and count twice (the pair (i,j),
@@ -809,22 +818,54 @@ int hb_diag_zero(hb_csr* h) {
 
 int hb_symmetry(hb_csr* h, double* ratio_out) {
     HB_REQUIRE(h != nullptr && ratio_out != nullptr, "bad arguments");
-    HB_REQUIRE(h->row0 == 0 && h->n_rows == h->n_cols, "hb_symmetry needs the full matrix on one device");
+    const bool sharded = h->world > 1;
+    HB_REQUIRE(sharded || (h->row0 == 0 && h->n_rows == h->n_cols), "hb_symmetry needs the full matrix or hb_set_comm");
+    HB_REQUIRE(!sharded || h->allreduce != nullptr, "sharded hb_symmetry needs the allreduce callback (hb_set_comm)");
     int rc = hb_use_device(h);
     if (rc) return rc;
     cudaStream_t s = h->stream;
     double* d_sums = nullptr;
-    HB_CUDA(cudaMalloc(&d_sums, sizeof(double) * 4));
+    HB_CUDA(cudaMalloc(&d_sums, sizeof(double) * (4 + 16)));
     unsigned long long* d_counts = reinterpret_cast<unsigned long long*>(d_sums + 2);
     double sums[2] = {0, 0};
     unsigned long long counts[2] = {0, 0};
-    cudaError_t e = cudaMemsetAsync(d_sums, 0, sizeof(double) * 4, s);
-    if (e == cudaSuccess && h->nnz > 0) {
+    cudaError_t e = cudaMemsetAsync(d_sums, 0, sizeof(double) * (4 + 16), s);
+    if (e == cudaSuccess && (h->nnz > 0 || sharded)) {
         // screen: exactly symmetric? (one streaming pass)
         unsigned long long dg[4] = {0, 1, 2, 3};
-        hb_symmetry_digest_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, h->n_rows,
-                                                                 reinterpret_cast<unsigned long long*>(d_sums));
-        g_hb_launches.fetch_add(1);
+        if (h->nnz > 0) {
+            hb_symmetry_digest_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, h->n_rows, h->row0,
+                                                                     reinterpret_cast<unsigned long long*>(d_sums));
+            g_hb_launches.fetch_add(1);
+        }
+        if (sharded) {
+            double limbs[16];
+            hb_digest_limbs_kernel<<<1, 32, 0, s>>>(reinterpret_cast<unsigned long long*>(d_sums), d_sums + 4);
+            g_hb_launches.fetch_add(1);
+            if (h->allreduce(h->comm_ctx, d_sums + 4, 16, (void*)s) != 0) {
+                cudaFree(d_sums);
+                hb_set_error("hb_symmetry: the allreduce callback failed");
+                return HB_ERR_CUDA;
+            }
+            e = cudaMemcpyAsync(limbs, d_sums + 4, sizeof(limbs), cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            for (int q = 0; q < 4; ++q) {
+                dg[q] = 0;
+                for (int l = 0; l < 4; ++l) dg[q] += (unsigned long long)limbs[4 * q + l] << (16 * l);
+            }
+            cudaFree(d_sums);
+            if (e != cudaSuccess) return hb_cuda_fail(e, "symmetry", __FILE__, __LINE__);
+            if (dg[0] == dg[2] && dg[1] == dg[3]) {
+                *ratio_out = 0.0;
+                return HB_OK;
+            }
+            // The exact ratio needs every entry's transposed partner, which lives in another rank's block.  Row blocks
+            // therefore accept exactly symmetric matrices only (what a symmetric fill of a file's upper triangle
+            // gives); the reference would still accept a relative asymmetry below 1e-10 (iterativeCorrection.py:35).
+            hb_set_error("the matrix is not exactly symmetric (row-block check)");
+            *ratio_out = 1.0;
+            return HB_ERR_NOT_SYMMETRIC;
+        }
         e = cudaMemcpyAsync(dg, d_sums, sizeof(dg), cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
         if (e == cudaSuccess && dg[0] == dg[2] && dg[1] == dg[3]) {

@@ -131,6 +131,7 @@ hb_scaled_upper_kernel(const int64_t* __restrict__ indptr, const int32_t* __rest
         const double corr = seg_corr[lo];
         const double ri = r[g];
         const int64_t og = orig[g];
+        if (og < 0) continue;                    // bin dropped from the output (--inflationCutoff)
         int64_t w = FILL ? out_ptr[og] : 0;
         long long n_out = 0;
         const int64_t s = indptr[row], e = indptr[row + 1];
@@ -145,11 +146,12 @@ hb_scaled_upper_kernel(const int64_t* __restrict__ indptr, const int32_t* __rest
                 m0 = fmax(m0, wv);
                 m1 = fmax(m1, f);
             }
-            const bool kp = c >= g && f != 0.0;  // upper triangle, explicit zeros eliminated
+            const int64_t oc = (c >= g && f != 0.0) ? orig[c] : -1;  // upper triangle, explicit zeros eliminated
+            const bool kp = oc >= 0;
             const unsigned int bal = __ballot_sync(0xffffffffu, kp);
             if (FILL && kp) {
                 const int64_t pos = w + __popc(bal & ((1u << lane) - 1u));
-                out_idx[pos] = (int32_t)orig[c];
+                out_idx[pos] = (int32_t)oc;
                 out_val[pos] = f;
             }
             w += __popc(bal);
@@ -275,9 +277,12 @@ int hb_ice_scaled_upper(hb_csr* h, const int64_t* orig_ids, int64_t n_orig, int6
     if (rc) return rc;
     cudaStream_t s = h->stream;
     const int64_t n = h->n_cols;
-    for (int64_t i = 0; i < n; ++i)
-        HB_REQUIRE(orig_ids[i] >= 0 && orig_ids[i] < n_orig && (i == 0 || orig_ids[i] > orig_ids[i - 1]),
+    for (int64_t i = 0, prev = -1; i < n; ++i) {
+        if (orig_ids[i] < 0) continue;           // -1: the bin is left out of the output
+        HB_REQUIRE(orig_ids[i] < n_orig && orig_ids[i] > prev,
                    "original ids must be strictly ascending and inside the original frame");
+        prev = orig_ids[i];
+    }
     int64_t *d_orig = nullptr, *d_cnt = nullptr, *d_ptr = nullptr;
     int32_t* d_idx = nullptr;
     double* d_val = nullptr;

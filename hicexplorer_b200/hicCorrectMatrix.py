@@ -9,9 +9,11 @@ Differences, all additive or documented:
   * launched under ``torchrun`` (WORLD_SIZE > 1) the genome-wide ICE / KR corrections run on nnz-balanced row blocks,
     one process per GPU, and rank 0 writes the output (``--perchr`` KR and ``--sequencedCountCutoff`` stay single-GPU);
   * ``diagnostic_plot`` (matplotlib histogram, :425-545) is out of scope and exits with an explanation;
-  * ``--transCutoff`` (hicmatrix ``truncTrans``) is not implemented yet and exits with an explanation;
-    ``--inflationCutoff`` only ever worked together with it in the reference (``pre_row_sum`` is otherwise
-    undefined, :699/:771) and is rejected the same way.
+  * ``--transCutoff`` computes hicmatrix ``truncTrans``'s percentile of the trans values on the device and keeps the
+    row sums for ``--inflationCutoff``; like the published hicmatrix code (whose clipping statement is a comparison)
+    it leaves the values unchanged unless the additive ``--clipTrans`` flag asks for the documented clipping.
+    ``--inflationCutoff`` only ever worked together with ``--transCutoff`` in the reference (``pre_row_sum`` is
+    otherwise undefined, :699/:771 -> NameError) and exits with an explanation when given alone; both are single-GPU.
 """
 import argparse
 import logging
@@ -95,6 +97,9 @@ def correct_subparser():
     opt.add_argument('--tolerance', help='ICE convergence tolerance on the marginals (Default: %(default)s, the '
                      'value hard-wired in the reference).', type=float, default=1e-5)
     opt.add_argument('--device', help='CUDA device index (Default: %(default)s).', type=int, default=0)
+    opt.add_argument('--clipTrans', help='With --transCutoff: clip the trans values at or above the percentile to it '
+                     '(what truncTrans documents; the published hicmatrix statement is a no-op comparison).',
+                     action='store_true')
     return parser
 
 
@@ -152,8 +157,13 @@ def _correct_ice(ma, args, world=1, rank=0):
     if not args.filterThreshold:
         log.error('min and max filtering thresholds should be set')
         sys.exit(1)
-    if args.transCutoff or args.inflationCutoff:
-        log.error('--transCutoff / --inflationCutoff are not implemented in the B200 build yet')
+    trans_on = bool(args.transCutoff and 0 < args.transCutoff < 100)
+    if args.inflationCutoff and args.inflationCutoff > 0 and not trans_on:
+        log.error('--inflationCutoff needs --transCutoff (the reference only defines pre_row_sum then, '
+                  'hicCorrectMatrix.py:699, 771)')
+        sys.exit(1)
+    if (trans_on or args.inflationCutoff) and world > 1:
+        log.error('--transCutoff / --inflationCutoff are not available in multi-GPU runs')
         sys.exit(1)
     intervals_all = list(ma.cut_intervals)
     extra_fn = None
@@ -180,7 +190,12 @@ def _correct_ice(ma, args, world=1, rank=0):
         res = ice_pipeline(up if up is not None else ma.matrix, (args.filterThreshold[0], args.filterThreshold[1]),
                            max_iter=args.iterNum, tolerance=args.tolerance, chr_offsets=ma.chromosome_offsets(),
                            perchr=args.perchr, skip_diagonal=args.skipDiagonal, device=args.device, want_matrix=file_layout,
-                           extra_mask_fn=extra_fn, upper_input=up is not None, file_layout=file_layout)
+                           extra_mask_fn=extra_fn, upper_input=up is not None, file_layout=file_layout,
+                           trans_cutoff=args.transCutoff, clip_trans=args.clipTrans, inflation_cutoff=args.inflationCutoff)
+        if res.get('max_inter') is not None:
+            log.info("trans contacts: {} percentile = {}".format(100 - float(args.transCutoff) / 100, res['max_inter']))
+        if 'inflated_rel' in res:
+            log.info("inflated >={} regions: {}".format(args.inflationCutoff, len(res['inflated_rel'])))
     n = res['n']
     keep1 = np.setdiff1d(np.arange(n), res['zero_bins'])
     outlier_regions = res['outliers_rel']

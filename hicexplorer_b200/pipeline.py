@@ -24,7 +24,7 @@ def _segment_offsets_after(mask_removed, offsets):
 
 def ice_pipeline(matrix, filter_threshold, max_iter=500, tolerance=1e-5, chr_offsets=None, perchr=False,
                  skip_diagonal=False, device=0, want_matrix=True, extra_mask_fn=None, upper_input=False,
-                 file_layout=False):
+                 file_layout=False, trans_cutoff=None, clip_trans=False, inflation_cutoff=None):
     """ICE branch of the driver.
 
     matrix           full symmetric scipy matrix in the original bin frame (n bins)
@@ -38,6 +38,15 @@ def ice_pipeline(matrix, filter_threshold, max_iter=500, tolerance=1e-5, chr_off
                      image is built on the device (hb_csr_create_upper)
     file_layout      return ``upper`` = corrected matrix as the files store it (upper triangle, zeros eliminated,
                      original n-bin frame; hicmatrix restoreMaskedBins + triu, done on the device) instead of ``matrix``
+
+    trans_cutoff     --transCutoff (:695-699): percentile ``100 - trans_cutoff/100`` of the values stored between
+                     chromosomes (hicmatrix truncTrans) -> ``max_inter``; the row sums at that point are kept for
+                     ``inflation_cutoff``.  ``clip_trans`` applies the clipping truncTrans documents (values >= max_inter
+                     become max_inter); off by default because the published hicmatrix statement is a comparison, not
+                     an assignment, and leaves the matrix unchanged.
+    inflation_cutoff --inflationCutoff (:765-775): after the correction, bins whose row sum grew by at least this
+                     factor are masked (``inflated_rel``, relative to ``kept_ice``); needs ``trans_cutoff`` like the
+                     reference (its ``pre_row_sum`` only exists then).
 
     Returns a dict:
       zero_bins      original ids removed because their row sum is 0        (:612-616)
@@ -81,16 +90,42 @@ def ice_pipeline(matrix, filter_threshold, max_iter=500, tolerance=1e-5, chr_off
             remove |= extra
         dev.compact(remove.astype(np.uint8))
         kept = keep1[~remove]
+        extra_out = {}
+        pre_row_sum = None
+        if trans_cutoff and 0 < trans_cutoff < 100:
+            if offsets is None:
+                raise ValueError("trans_cutoff needs chromosome offsets")
+            offsets_now = np.searchsorted(kept, offsets, side="left")       # chromosome offsets in the masked frame
+            max_inter = dev.trans_percentile(offsets_now, 100 - float(trans_cutoff) / 100)
+            extra_out["max_inter"] = max_inter
+            if clip_trans and max_inter is not None:
+                extra_out["clipped"] = dev.trans_clip(offsets_now, max_inter)
+            pre_row_sum, _ = dev.row_stats()
+        if inflation_cutoff and inflation_cutoff > 0 and pre_row_sum is None:
+            raise ValueError("inflation_cutoff needs trans_cutoff (pre_row_sum is only defined then, "
+                             "hicCorrectMatrix.py:699, 771)")
         if perchr:
             dev.keep_cis()
         if dev.symmetry_ratio() > 1e-10:
             raise ValueError("Please provide symmetric matrix!")
         dev.pack_values()      # raw counts stream as uint16 (6 B/entry instead of 12); lossless, results unchanged
         bias, iters, deviation = dev.ice(max_iter, tolerance)
+        out_ids = kept
+        if inflation_cutoff and inflation_cutoff > 0:
+            after = dev.ice_scaled_row_sums()
+            with np.errstate(divide="ignore", invalid="ignore"):
+                inflated = after / pre_row_sum >= inflation_cutoff
+            extra_out["inflated_rel"] = np.flatnonzero(inflated)
+            extra_out["kept_ice"] = kept
+            out_ids = np.where(inflated, -1, kept)      # -1: left out of the emitted matrix
+            kept = kept[~inflated]
+            bias = bias[~inflated]
         out = dict(zero_bins=zero_bins, outliers_rel=outliers_rel, kept=kept, bias=bias,
-                   iterations=iters, deviation=deviation, n=n)
+                   iterations=iters, deviation=deviation, n=n, **extra_out)
         if want_matrix and file_layout:
-            out["upper"] = dev.ice_scaled_upper(kept, n)
+            out["upper"] = dev.ice_scaled_upper(out_ids, n)
+        elif want_matrix and "inflated_rel" in extra_out:
+            raise ValueError("inflation_cutoff returns the matrix in file layout only (file_layout=True)")
         elif want_matrix:
             values = dev.ice_scaled_values()
             pattern = dev.download()
@@ -157,8 +192,9 @@ def _gather_rows_to_root(values, dist, rank, world, device):
 
 def ice_pipeline_sharded(matrix, filter_threshold, max_iter=500, tolerance=1e-5, chr_offsets=None, perchr=False,
                          skip_diagonal=False, want_matrix=True):
-    """ice_pipeline on row blocks across the initialised torch.distributed group (NCCL).  The symmetry test of the
-    single-GPU path needs the transposed entries of other blocks and is skipped here."""
+    """ice_pipeline on row blocks across the initialised torch.distributed group (NCCL).  The symmetry test is the
+    exact-symmetry digest screen summed over the blocks (one tiny allreduce); a matrix that is not exactly symmetric is
+    rejected (the exact ratio would need the transposed entries of other blocks)."""
     import torch
 
     from .dist import attach_comm, nnz_balanced_partition
@@ -193,6 +229,8 @@ def ice_pipeline_sharded(matrix, filter_threshold, max_iter=500, tolerance=1e-5,
         kept = keep1[~mask.astype(bool)]
         if perchr:
             dev.keep_cis()
+        if dev.symmetry_ratio() > 1e-10:
+            raise ValueError("Please provide symmetric matrix!")
         dev.pack_values()
         bias, iters, deviation = dev.ice(max_iter, tolerance)  # one exchange per iteration
         values = dev.ice_scaled_values() if want_matrix else None

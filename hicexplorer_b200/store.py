@@ -31,6 +31,28 @@ def canonical_csr(matrix, dtype=np.float64):
     return m
 
 
+def percentile_position(count, q):
+    """Where numpy's default ('linear') percentile looks in the sorted sample: index of the lower neighbour and the
+    interpolation weight, computed with numpy's own expressions (virtual index = (count - 1) * (q / 100))."""
+    quantile = np.true_divide(np.float64(q), 100)
+    virtual = (count - 1) * quantile
+    previous = np.floor(virtual)
+    gamma = virtual - previous
+    k = int(previous)
+    if k >= count - 1:
+        return count - 1, np.float64(0.0)
+    if k < 0:
+        return 0, np.float64(0.0)
+    return k, gamma
+
+
+def lerp_like_numpy(a, b, t):
+    """numpy's _lerp: a + (b - a) * t, switched to b - (b - a) * (1 - t) for t >= 0.5"""
+    a, b, t = np.float64(a), np.float64(b), np.float64(t)
+    diff = b - a
+    return b - diff * (1 - t) if t >= 0.5 else a + diff * t
+
+
 class DeviceCSR(object):
     def __init__(self, handle, device):
         self._h = ctypes.c_void_p(handle) if not isinstance(handle, ctypes.c_void_p) else handle
@@ -221,7 +243,10 @@ class DeviceCSR(object):
 
     def symmetry_ratio(self):
         r = ctypes.c_double()
-        check(lib().hb_symmetry(self._h, ctypes.byref(r)))
+        rc = lib().hb_symmetry(self._h, ctypes.byref(r))
+        if rc == _lib.HB_ERR_NOT_SYMMETRIC:      # row blocks: any asymmetry is reported as ratio 1
+            return r.value
+        check(rc)
         return r.value
 
     # ---- ICE ------------------------------------------------------------------
@@ -253,6 +278,33 @@ class DeviceCSR(object):
         check(lib().hb_ice_scaled_upper(self._h, ptr(orig), int(n_orig), ctypes.byref(nnz), ptr(indptr), ptr(indices),
                                         ptr(data)))
         return sparse.csr_matrix((data, indices, indptr), shape=(n_orig, n_orig))
+
+    # ---- optional steps around ICE (--transCutoff / --inflationCutoff) ------------
+    def trans_percentile(self, chr_offsets, q):
+        """np.percentile(values stored between chromosomes, q) -- what hicmatrix truncTrans computes
+        (hicCorrectMatrix.py:695-698) -- from two exact order statistics selected on the device; None when the
+        matrix has no trans entries."""
+        offs = np.ascontiguousarray(chr_offsets, dtype=np.int64)
+        nchr = len(offs) - 1
+        count = ctypes.c_int64()
+        check(lib().hb_trans_order_stats(self._h, ptr(offs), nchr, 0, ctypes.byref(count), None, None))
+        if count.value == 0:
+            return None
+        k, gamma = percentile_position(count.value, q)
+        a, b = ctypes.c_double(), ctypes.c_double()
+        check(lib().hb_trans_order_stats(self._h, ptr(offs), nchr, k, ctypes.byref(count), ctypes.byref(a), ctypes.byref(b)))
+        return lerp_like_numpy(a.value, b.value, gamma)
+
+    def trans_clip(self, chr_offsets, max_inter):
+        offs = np.ascontiguousarray(chr_offsets, dtype=np.int64)
+        clipped = ctypes.c_int64()
+        check(lib().hb_trans_clip(self._h, ptr(offs), len(offs) - 1, float(max_inter), ctypes.byref(clipped)))
+        return clipped.value
+
+    def ice_scaled_row_sums(self):
+        out = np.empty(self.n_rows, dtype=np.float64)
+        check(lib().hb_ice_scaled_row_sums(self._h, ptr(out)))
+        return out
 
     # ---- Knight-Ruiz ------------------------------------------------------------
     def kr(self, tol=KR_TOL, delta=KR_DELTA, Delta=KR_DELTA_UPPER, diag_eps=KR_DIAG_EPS, max_outer=100000):

@@ -150,7 +150,9 @@ HB_API int hb_peer_active(const hb_csr* h);
  *   its own surviving rows (row0 / n_rows / n_cols are renumbered).
  * hb_diag_zero: --skipDiagonal (hicCorrectMatrix.py:648-649).
  * hb_symmetry: the reference's criterion (iterativeCorrection.py:35):
- *   ratio = mean|M - M^T| / |mean M|; the caller raises when ratio > 1e-10. */
+ *   ratio = mean|M - M^T| / |mean M|; the caller raises when ratio > 1e-10.  On a row block (hb_set_comm) the
+ *   exact-symmetry digests of the blocks are summed with one 16-double allreduce: ratio 0 when the whole matrix equals
+ *   its transpose exactly, else HB_ERR_NOT_SYMMETRIC with ratio 1 (the exact ratio needs other ranks' entries). */
 HB_API int hb_scrub(hb_csr* h, int64_t counts[2]);
 /* Optional: build a LOSSLESS narrow copy of the stored values for the streaming kernels (ICE / KR mat-vecs):
  * uint16 when every value is an integer count <= 65535 (kind 1, 6 B per entry streamed instead of 12), float when
@@ -193,11 +195,27 @@ HB_API int hb_ice_run(hb_csr* h, int max_iter, double tol, double* bias_out, int
                double* dev_out);
 HB_API int hb_ice_scaled_values(hb_csr* h, double* data_out, double* max_out);
 /* The corrected matrix in FILE layout: upper triangle, exact zeros eliminated, scattered back into the original
- * n_orig-bin frame (orig_ids[i] = original id of bin i, strictly ascending) -- hicmatrix restoreMaskedBins + triu at
+ * n_orig-bin frame (orig_ids[i] = original id of bin i, strictly ascending; -1 = leave the bin out, which is how
+ * --inflationCutoff masks bins after the correction, hicCorrectMatrix.py:774) -- hicmatrix restoreMaskedBins + triu at
  * save time (hicCorrectMatrix.py:779), fused with the final scaling.  Two calls: with indptr/indices/data NULL to get
  * nnz_out, then with indptr[n_orig+1], indices[nnz], data[nnz].  Same overflow codes as hb_ice_scaled_values. */
 HB_API int hb_ice_scaled_upper(hb_csr* h, const int64_t* orig_ids, int64_t n_orig, int64_t* nnz_out, int64_t* indptr,
                         int32_t* indices, double* data);
+
+/* ---- optional ICE-only steps around the correction -----------------------------
+ * --transCutoff (hicCorrectMatrix.py:695-699 -> hicmatrix truncTrans): trans entries are those whose row and column lie
+ * in different chromosomes (chr_offsets[nchr+1], ascending, in the CURRENT bin frame).
+ *   hb_trans_order_stats: n_trans_out = number of stored trans entries; when v_k / v_k1 are given, the k-th and
+ *     (k+1)-th smallest trans values (0-based, exact: radix select on the fp64 bit patterns; v_k1 = v_k at the top) --
+ *     the two order statistics np.percentile interpolates between.  Call once with v_k = v_k1 = NULL for the count.
+ *   hb_trans_clip: every trans value >= max_inter becomes max_inter (the clipping truncTrans documents).
+ * --inflationCutoff (hicCorrectMatrix.py:765-775):
+ *   hb_ice_scaled_row_sums: out[i] = sum_j W_ij of the corrected matrix for the block's rows, computed from the raw
+ *     store and the ICE state with the emission's per-entry arithmetic.  Full matrix on one device, after hb_ice_run. */
+HB_API int hb_trans_order_stats(hb_csr* h, const int64_t* chr_offsets, int nchr, int64_t k, int64_t* n_trans_out,
+                         double* v_k, double* v_k1);
+HB_API int hb_trans_clip(hb_csr* h, const int64_t* chr_offsets, int nchr, double max_inter, int64_t* n_clipped_out);
+HB_API int hb_ice_scaled_row_sums(hb_csr* h, double* out);
 
 /* Step-level device API (all vectors are device fp64[n_cols], replicated per rank).
  *   hb_dev_ice_begin : bias = 1, r = 1, clear convergence state.

@@ -153,10 +153,37 @@ def chromosome_order(chr_list, wanted):
     return np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64)
 
 
-def correct_ice_pipeline(full_csr, lo, hi, max_iter=500, tolerance=1e-5):
-    """zero-bin mask -> scrub -> MAD mask -> ICE -> scatter back into the
+def trunc_trans(csr, chr_offsets, high, clip):
+    """hicmatrix ``truncTrans(high)`` as called at hicCorrectMatrix.py:695-698 (hicmatrix is third party and not under
+    /root/reference; restated from its published source [memory]): ``max_inter = np.percentile(trans values,
+    100 - high)``, trans = row and column in different chromosomes.  The documented effect is to clip the trans values
+    ``>= max_inter`` to ``max_inter`` (``clip=True``); the published statement reads
+    ``mat.data[...] == max_inter`` -- a comparison, i.e. no change (``clip=False``).  Returns (matrix, max_inter)."""
+    coo = csr.tocoo()
+    offs = np.asarray(chr_offsets)
+    trans = np.searchsorted(offs, coo.row, side="right") != np.searchsorted(offs, coo.col, side="right")
+    if np.count_nonzero(trans) == 0:
+        return csr, None
+    max_inter = np.percentile(coo.data[trans], (100 - high))
+    if clip:
+        data = coo.data.copy()
+        data[(data >= max_inter) & trans] = max_inter
+        csr = sparse.csr_matrix((data, (coo.row, coo.col)), shape=csr.shape)
+    return csr, max_inter
+
+
+def inflated_bins(corrected_csr, pre_row_sum, cutoff):
+    """hicCorrectMatrix.py:767-771: bins whose row sum grew by at least ``cutoff`` times."""
+    after = np.asarray(corrected_csr.sum(axis=1)).flatten()
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.flatnonzero(after / pre_row_sum >= cutoff)
+
+
+def correct_ice_pipeline(full_csr, lo, hi, max_iter=500, tolerance=1e-5, chr_offsets=None, trans_cutoff=None,
+                         clip_trans=False, inflation_cutoff=None):
+    """zero-bin mask -> scrub -> MAD mask -> [truncTrans] -> ICE -> [inflation mask] -> scatter back into the
     original frame; what ``hicCorrectMatrix correct --correctionMethod ICE``
-    does for a genome-wide run (hicCorrectMatrix.py:612-673, 735-740, 759-779).
+    does for a genome-wide run (hicCorrectMatrix.py:612-673, 695-699, 735-740, 759-779).
 
     Returns dict with the stages so every one of them can be compared.
     """
@@ -167,8 +194,21 @@ def correct_ice_pipeline(full_csr, lo, hi, max_iter=500, tolerance=1e-5):
     out_rel = outlier_bins(stage1, lo, hi)
     keep2 = np.delete(np.arange(stage1.shape[0]), out_rel)
     ice_in = select_bins(stage1, keep2)
-    res = ice(ice_in.copy(), max_iter=max_iter, tolerance=tolerance)
     orig = keep1[keep2]
+    extra = {}
+    pre_row_sum = None
+    if trans_cutoff and 0 < trans_cutoff < 100:
+        offs_now = np.searchsorted(orig, np.asarray(chr_offsets), side="left")     # offsets in the masked frame
+        ice_in, extra["max_inter"] = trunc_trans(ice_in, offs_now, float(trans_cutoff) / 100, clip_trans)
+        pre_row_sum = np.asarray(ice_in.sum(axis=1)).flatten()
+        extra["pre_row_sum"] = pre_row_sum
+    res = ice(ice_in.copy(), max_iter=max_iter, tolerance=tolerance)
+    if inflation_cutoff and inflation_cutoff > 0:
+        infl = inflated_bins(res["matrix"], pre_row_sum, inflation_cutoff)     # NameError in the reference without transCutoff
+        extra["inflated_rel"] = infl
+        keep3 = np.delete(np.arange(len(orig)), infl)
+        res = dict(res, matrix=select_bins(res["matrix"].tocsr(), keep3), bias=res["bias"][keep3])
+        orig = orig[keep3]
     coo = res["matrix"].tocoo()
     corrected_full = sparse.coo_matrix((coo.data, (orig[coo.row], orig[coo.col])), shape=(n, n)).tocsr()
     upper = sparse.triu(corrected_full, 0, format="csr")
@@ -178,4 +218,4 @@ def correct_ice_pipeline(full_csr, lo, hi, max_iter=500, tolerance=1e-5):
     factors[orig] = res["bias"]
     nan_bins = np.setdiff1d(np.arange(n), orig).astype(np.int64)
     return dict(zero_bins=dead, outliers_rel=out_rel, outliers_abs=keep1[out_rel], kept=orig,
-                ice_input=ice_in, ice=res, upper=upper, correction_factors=factors, nan_bins=nan_bins)
+                ice_input=ice_in, ice=res, upper=upper, correction_factors=factors, nan_bins=nan_bins, **extra)

@@ -189,3 +189,28 @@ def test_skip_diagonal_and_sequenced_count_cutoff(tmp_path, gm12878):
     up = sparse.triu(ref["matrix"], 0, format="csr")
     up.eliminate_zeros()
     np.testing.assert_allclose(np.sort(m.data), np.sort(up.data), rtol=1e-8)
+
+
+def test_trans_and_inflation_cutoff(tmp_path, gm12878):
+    """--transCutoff / --inflationCutoff (hicCorrectMatrix.py:695-699, 765-775): inflated bins become nan_bins with NaN
+    factors and leave the output matrix; --inflationCutoff alone exits 1 (the reference dies with a NameError)"""
+    g = gm12878
+    src = _gm_cool(tmp_path, g)
+    full = full_from_pixels(g)
+    out = str(tmp_path / "ice_infl.h5")
+    main("correct --matrix {} --correctionMethod ICE --filterThreshold -1.5 5 --transCutoff 0.05 --inflationCutoff 1.7 "
+         "--outFileName {}".format(src, out).split())
+    ref = ice_oracle.correct_ice_pipeline(full, -1.5, 5.0, max_iter=500, chr_offsets=g["chrom_offset"], trans_cutoff=0.05,
+                                          inflation_cutoff=1.7)
+    assert 0 < len(ref["inflated_rel"]) < 1000
+    f, m = _read_h5(out)
+    assert np.array_equal(f["nan_bins"].read(), ref["nan_bins"])
+    assert np.array_equal(m.indptr, ref["upper"].indptr) and np.array_equal(m.indices, ref["upper"].indices)
+    np.testing.assert_allclose(m.data, ref["upper"].data, rtol=1e-8)
+    cf = f["correction_factors"].read()
+    assert np.array_equal(np.isnan(cf), np.isnan(ref["correction_factors"]))
+    np.testing.assert_allclose(cf[ref["kept"]], ref["correction_factors"][ref["kept"]], rtol=1e-9)
+    with pytest.raises(SystemExit) as exc:
+        main("correct --matrix {} --correctionMethod ICE --filterThreshold -1.5 5 --inflationCutoff 3 "
+             "--outFileName {}".format(src, out).split())
+    assert exc.value.code == 1

@@ -183,3 +183,15 @@ def test_sharded_kr_rescale_and_scaled_upper(world, kr_partial):
     whole = sparse.vstack(rows).tocsr()
     assert np.array_equal(whole.indptr, up1.indptr) and np.array_equal(whole.indices, up1.indices)
     np.testing.assert_array_equal(whole.data, up1.data)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_symmetry_screen(world):
+    """row blocks add their exact-symmetry digests with one allreduce: 0 for a symmetric matrix on every rank, a
+    rejection (ratio 1) on every rank once a single entry differs from its mirror image"""
+    sym = random_hic(700, 0.1, 11)
+    assert all(r == 0.0 for r in _run_sharded(sym, world, lambda dev: dev.symmetry_ratio())[0])
+    broken = sym.copy()
+    k = int(np.flatnonzero(broken.indices > np.repeat(np.arange(700), np.diff(broken.indptr)))[5])
+    broken.data[k] += 1e-9
+    assert all(r == 1.0 for r in _run_sharded(broken, world, lambda dev: dev.symmetry_ratio())[0])

@@ -108,7 +108,7 @@ def test_cli_flags_are_a_superset_of_the_reference_parser():
     for flag, spec in r.items():
         assert flag in m, "missing flag " + flag
         assert m[flag] == spec, (flag, m[flag], spec)
-    assert set(m) - set(r) == {"--tolerance", "--device"}
+    assert set(m) - set(r) == {"--tolerance", "--device", "--clipTrans"}
 
 
 def test_ice_without_thresholds_exits_1_like_the_reference(tmp_path, small_ice):
@@ -119,3 +119,25 @@ def test_ice_without_thresholds_exits_1_like_the_reference(tmp_path, small_ice):
     with pytest.raises(SystemExit) as ei:
         main(["correct", "-m", src, "-o", str(tmp_path / "o.h5"), "--correctionMethod", "ICE"])
     assert ei.value.code == 1
+
+
+@pytest.mark.parametrize("count", [1, 2, 3, 10, 1001, 65537])
+@pytest.mark.parametrize("q", [0.0, 100.0, 99.9995, 50.0, 12.5, 99.95])
+def test_percentile_position_reproduces_numpy(count, q):
+    """the host half of --transCutoff: numpy's 'linear' percentile from two order statistics, bit for bit"""
+    from hicexplorer_b200.store import lerp_like_numpy, percentile_position
+    rng = np.random.default_rng(count)
+    x = np.floor(rng.exponential(5.0, count)) * rng.random(count)
+    srt = np.sort(x)
+    k, gamma = percentile_position(count, q)
+    got = lerp_like_numpy(srt[k], srt[min(k + 1, count - 1)], gamma)
+    assert got == np.percentile(x, q)
+
+
+def test_oracle_trunc_trans_semantics():
+    from oracle import ice_oracle
+    m = sparse.csr_matrix(np.array([[5, 1, 9, 0], [1, 5, 0, 2], [9, 0, 5, 1], [0, 2, 1, 5]], dtype=float))
+    same, mx = ice_oracle.trunc_trans(m, [0, 2, 4], 50.0, clip=False)
+    assert mx == np.percentile([9, 2, 9, 2], 50.0) and (same != m).nnz == 0
+    clipped, _ = ice_oracle.trunc_trans(m, [0, 2, 4], 50.0, clip=True)
+    assert clipped[0, 2] == mx and clipped[2, 0] == mx and clipped[0, 1] == 1 and clipped[1, 3] == 2
