@@ -30,6 +30,18 @@ def nnz_balanced_partition(indptr, world):
     return np.asarray(bounds, dtype=np.int64)
 
 
+def lpt_assignment(weights, world):
+    """Longest-processing-time assignment of independent chromosomes (``--perchr``) to ranks: owner[c] = rank.
+    Deterministic, so every rank computes the same table without talking to the others."""
+    loads = [0.0] * world
+    owner = [0] * len(weights)
+    for c in sorted(range(len(weights)), key=lambda i: (-weights[i], i)):
+        r = min(range(world), key=lambda k: (loads[k], k))
+        owner[c] = r
+        loads[r] += weights[c]
+    return owner
+
+
 class _DevicePtr(object):
     """Zero-copy view of a raw device pointer for torch.as_tensor."""
 

@@ -117,7 +117,7 @@ def main(args=None):
                   'use the reference tool for the plot (the statistics it shows are those of --filterThreshold).')
         sys.exit(1)
 
-    world, rank = _init_distributed(args)
+    world, rank, own_group = _init_distributed(args)
     if _is_cooler(args.matrix) and args.chromosomes is not None and len(args.chromosomes) == 1:
         ma = hm.hiCMatrix(args.matrix, pChrnameList=[str(c) for c in args.chromosomes])
     else:
@@ -134,23 +134,25 @@ def main(args=None):
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
-        dist.destroy_process_group()
+        if own_group:
+            dist.destroy_process_group()
 
 
 def _init_distributed(args):
-    """one process per GPU when launched by torchrun; (world, rank) = (1, 0) otherwise"""
+    """one process per GPU when launched by torchrun; (world, rank, group created here) = (1, 0, False) otherwise"""
     import os
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world <= 1:
-        return 1, 0
+        return 1, 0, False
     import torch
     import torch.distributed as dist
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     args.device = local
-    if not dist.is_initialized():
+    created = not dist.is_initialized()
+    if created:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    return world, dist.get_rank()
+    return world, dist.get_rank(), created
 
 
 def _correct_ice(ma, args, world=1, rank=0):
@@ -235,22 +237,44 @@ def _correct_kr(ma, args, world=1, rank=0):
         print("normalisation factor is {}".format(res['factor']))
         ma.setCorrectionFactors(np.asmatrix(res['x']).T)
         return
-    if world > 1 and rank != 0:
-        return      # remaining KR variants run on rank 0's GPU
+    if world > 1 and not args.perchr and rank != 0:
+        return      # genome-wide KR to .h5 runs on rank 0's GPU
     if args.perchr:
-        corrected_matrix = lil_matrix(matrix.shape)
-        factors = []
-        for chrname in ma.getChrNames():
-            lo, hi = ma.getChrBinRange(chrname)
+        # independent chromosomes: dealt to the GPUs by longest-processing-time on stored entries, no communication
+        # during the correction; rank 0 collects the factors (and the corrected blocks for .h5)
+        from .dist import lpt_assignment
+        want_matrix = str(args.outFileName).endswith('.h5')
+        names = ma.getChrNames()
+        ranges = [ma.getChrBinRange(c) for c in names]
+        owner = lpt_assignment([int(matrix.indptr[hi] - matrix.indptr[lo]) for lo, hi in ranges], world)
+        mine = {}
+        for ci, (lo, hi) in enumerate(ranges):
+            if owner[ci] != rank:
+                continue
             sub = matrix[lo:hi, lo:hi].tocsr()
             kr = kr_balancing(sub.shape[0], sub.shape[1], sub.count_nonzero(), sub.indptr.astype(np.int64, copy=False),
                               sub.indices.astype(np.int64, copy=False), sub.data.astype(np.float64, copy=False),
                               device=args.device)
             kr.computeKR()
-            if str(args.outFileName).endswith('.h5'):
-                corrected_matrix[lo:hi, lo:hi] = kr.get_normalised_matrix(True)
-            factors.append(kr.get_normalisation_vector(False).todense())
+            block = kr.get_normalised_matrix(True) if want_matrix else None
+            mine[ci] = (block, kr.get_normalisation_vector(False).todense())
             kr.close()
+        if world > 1:
+            import torch.distributed as dist
+            parts = [None] * world if rank == 0 else None
+            dist.gather_object(mine, parts, dst=0)
+            if rank != 0:
+                return
+            mine = {}
+            for p in parts:
+                mine.update(p)
+        corrected_matrix = lil_matrix(matrix.shape)
+        factors = []
+        for ci, (lo, hi) in enumerate(ranges):
+            block, vec = mine[ci]
+            if want_matrix:
+                corrected_matrix[lo:hi, lo:hi] = block
+            factors.append(vec)
         correction_factors = np.concatenate(factors)
     else:
         kr = kr_balancing(matrix.shape[0], matrix.shape[1], matrix.count_nonzero(),

@@ -95,7 +95,7 @@ def main():
                             for c in range(len(off) - 1) for i in range(off[c], off[c + 1])]
         ma._index_intervals()
         ma.save(src)
-    dist.barrier()          # the CLI reuses this process group and destroys it when it is done
+    dist.barrier()          # the CLI reuses this process group
     out = os.path.join(tmp, "mg_out.cool")
     cli(["correct", "-m", src, "-o", out, "--correctionMethod", "ICE", "--filterThreshold", "-1.5", "5"])
     if rank == 0:
@@ -103,6 +103,17 @@ def main():
         cf = np.asarray(new.correction_factors).ravel()
         check("CLI under torchrun: factors match the single-GPU pipeline", np.array_equal(cf[ref["kept"]], ref["bias"]) and
               np.isnan(cf).sum() == n - len(ref["kept"]))
+    # --perchr KR: whole chromosomes dealt to the ranks (LPT), no communication; rank 0 assembles the file
+    outk = os.path.join(tmp, "mg_kr_perchr.h5")
+    cli(["correct", "-m", src, "-o", outk, "--correctionMethod", "KR", "--perchr"])
+    if rank == 0:
+        os.environ["WORLD_SIZE"] = "1"
+        out1 = os.path.join(tmp, "mg_kr_perchr_1gpu.h5")
+        cli(["correct", "-m", src, "-o", out1, "--correctionMethod", "KR", "--perchr", "--device", str(local)])
+        a, b = hiCMatrix(outk), hiCMatrix(out1)
+        check("CLI --perchr KR under torchrun: file equals the single-GPU run",
+              np.array_equal(np.asarray(a.correction_factors), np.asarray(b.correction_factors)) and
+              (a.matrix != b.matrix).nnz == 0)
         print("ALL PASS" if ok else "SOME FAILED", flush=True)
     sys.exit(0 if ok else 1)
 

@@ -93,3 +93,13 @@ def test_sharded_ice_exchange_scheme_world2(tmp_path):
     np.testing.assert_array_equal(r0["bias"], r1["bias"])        # replicated state is bit-identical across ranks
     assert abs(int(r0["iters"]) - ref["iterations"]) <= 1
     np.testing.assert_allclose(r0["bias"], ref["bias"], rtol=1e-9)
+
+
+def test_lpt_assignment_is_deterministic_and_balanced():
+    from hicexplorer_b200.dist import lpt_assignment
+    w = [248, 242, 198, 190, 181, 170, 159, 145, 138, 133, 135, 133, 114, 107, 101, 90, 83, 80, 58, 64, 46, 50, 156, 57]
+    for world in (1, 2, 3, 8):
+        owner = lpt_assignment(w, world)
+        assert owner == lpt_assignment(list(w), world) and set(owner) == set(range(world))
+        loads = [sum(x for x, o in zip(w, owner) if o == r) for r in range(world)]
+        assert max(loads) <= sum(w) / world + max(w) * 0.5
