@@ -69,43 +69,48 @@ hb_sym_fill_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict
     }
 }
 
-// one CTA per row whose lower part has (P/2, P] entries: sort them by column id in shared memory
+// one CTA per row whose lower part has (P/2, P] entries: bitonic sort of (column id << 32 | arrival position) in shared
+// memory -- one 64-bit word per entry, half a compare-exchange per thread and step -- then the values follow their keys
+// through registers (read all, barrier, write all)
+#define HB_SYM_MAX_PER_THREAD 16
 __global__ void hb_sym_sort_kernel(const int64_t* __restrict__ out_ptr, const unsigned int* __restrict__ low_cnt, int64_t n,
                                    int P, int32_t* __restrict__ out_idx, double* __restrict__ out_val) {
-    extern __shared__ unsigned char smem_raw[];
+    extern __shared__ unsigned long long sk[];
     const int64_t row = blockIdx.x;
     const int L = (int)low_cnt[row];
     if (L < 2 || L > P || (P > 32 && L <= P / 2)) return;
-    double* sv = reinterpret_cast<double*>(smem_raw);
-    int32_t* sk = reinterpret_cast<int32_t*>(smem_raw + sizeof(double) * (size_t)P);
     const int64_t base = out_ptr[row];
-    for (int i = threadIdx.x; i < P; i += blockDim.x) {
-        sk[i] = i < L ? out_idx[base + i] : INT32_MAX;
-        sv[i] = i < L ? out_val[base + i] : 0.0;
-    }
+    for (int i = threadIdx.x; i < P; i += blockDim.x)
+        sk[i] = i < L ? (((unsigned long long)(unsigned int)out_idx[base + i] << 32) | (unsigned int)i) : ~0ull;
     __syncthreads();
     for (int k = 2; k <= P; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < P; i += blockDim.x) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const bool asc = (i & k) == 0;
-                    const int a = sk[i], b = sk[ixj];
-                    if ((a > b) == asc) {
-                        sk[i] = b;
-                        sk[ixj] = a;
-                        const double t = sv[i];
-                        sv[i] = sv[ixj];
-                        sv[ixj] = t;
-                    }
+            for (int i = threadIdx.x; i < (P >> 1); i += blockDim.x) {
+                const int lo = ((i / j) * j << 1) + (i % j);     // element whose bit j is clear
+                const int hi = lo + j;
+                const unsigned long long a = sk[lo], b = sk[hi];
+                if ((a > b) == ((lo & k) == 0)) {
+                    sk[lo] = b;
+                    sk[hi] = a;
                 }
             }
             __syncthreads();
         }
     }
-    for (int i = threadIdx.x; i < L; i += blockDim.x) {
-        out_idx[base + i] = sk[i];
-        out_val[base + i] = sv[i];
+    double v[HB_SYM_MAX_PER_THREAD];
+#pragma unroll
+    for (int q = 0; q < HB_SYM_MAX_PER_THREAD; ++q) {
+        const int i = threadIdx.x + q * blockDim.x;
+        if (i < L) v[q] = out_val[base + (unsigned int)(sk[i] & 0xffffffffull)];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < HB_SYM_MAX_PER_THREAD; ++q) {
+        const int i = threadIdx.x + q * blockDim.x;
+        if (i < L) {
+            out_idx[base + i] = (int32_t)(sk[i] >> 32);
+            out_val[base + i] = v[q];
+        }
     }
 }
 
@@ -233,10 +238,12 @@ int hb_csr_create_upper(hb_csr** out, int64_t n, int64_t nnz_upper, const int64_
         g_hb_launches.fetch_add(1);
         // size classes: P = 32 sorts lower parts of 2..32 entries, P > 32 those of (P/2, P] entries
         for (int P = 32; P <= 16384 && (P == 32 ? flags[1] >= 2u : flags[1] > (unsigned int)(P / 2)); P <<= 1) {
-            const size_t smem = (sizeof(double) + sizeof(int32_t)) * (size_t)P;
+            const size_t smem = sizeof(unsigned long long) * (size_t)P;
             if (smem > 48 * 1024)
                 SY(cudaFuncSetAttribute(hb_sym_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            hb_sym_sort_kernel<<<(unsigned)n, P >= 512 ? 256 : (P >= 64 ? P / 2 : 32), smem, s>>>(d_ptr, d_low, n, P, d_idx, d_val);
+            // P / threads <= HB_SYM_MAX_PER_THREAD (16384 / 1024) for every class
+            const int threads = P >= 2048 ? 1024 : (P >= 64 ? P / 2 : 32);
+            hb_sym_sort_kernel<<<(unsigned)n, threads, smem, s>>>(d_ptr, d_low, n, P, d_idx, d_val);
             g_hb_launches.fetch_add(1);
         }
     }

@@ -6,12 +6,33 @@
 // memcpys proceed in parallel.  Pinned / registered caller buffers (bench.py's e2e leg) take the direct DMA path.
 #include <algorithm>
 #include <cstring>
+#include <mutex>
 #include <thread>
 
 #include "hb_internal.cuh"
 
-#define HB_XFER_WORKERS 6
-#define HB_XFER_CHUNK ((size_t)16 << 20)
+#include <cstdlib>
+
+#define HB_XFER_WORKERS_DEFAULT 6
+#define HB_XFER_CHUNK_DEFAULT ((size_t)16 << 20)
+
+// tunables (environment, read once): HB_XFER_WORKERS = host threads, HB_XFER_CHUNK_MB = staging chunk size
+static int hb_xfer_workers() {
+    static const int v = [] {
+        const char* e = getenv("HB_XFER_WORKERS");
+        const int w = e ? atoi(e) : HB_XFER_WORKERS_DEFAULT;
+        return w < 1 ? 1 : (w > 64 ? 64 : w);
+    }();
+    return v;
+}
+static size_t hb_xfer_chunk() {
+    static const size_t v = [] {
+        const char* e = getenv("HB_XFER_CHUNK_MB");
+        const long mb = e ? atol(e) : 0;
+        return mb >= 1 && mb <= 1024 ? (size_t)mb << 20 : HB_XFER_CHUNK_DEFAULT;
+    }();
+    return v;
+}
 
 static bool hb_is_device_accessible_host(const void* p) {
     cudaPointerAttributes a;
@@ -22,6 +43,44 @@ static bool hb_is_device_accessible_host(const void* p) {
     return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
 }
 
+// Staging resources live for the life of the process (pinning memory costs milliseconds per buffer, more than a
+// small transfer itself); one transfer at a time uses them.
+struct HbXferWorker {
+    int device = -1;
+    size_t chunk = 0;
+    cudaStream_t st = nullptr;
+    unsigned char* stage[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+};
+static std::mutex g_xfer_mutex;
+static HbXferWorker g_xfer_worker[64];
+
+static cudaError_t hb_xfer_prepare(HbXferWorker& w, int device, size_t chunk) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return e;
+    if (w.device == device && w.chunk == chunk && w.st != nullptr) return cudaSuccess;
+    if (w.st != nullptr) {  // another device or chunk size: rebuild
+        cudaSetDevice(w.device);
+        for (int b = 0; b < 2; ++b) {
+            if (w.done[b]) cudaEventDestroy(w.done[b]);
+            if (w.stage[b]) cudaFreeHost(w.stage[b]);
+            w.done[b] = nullptr;
+            w.stage[b] = nullptr;
+        }
+        cudaStreamDestroy(w.st);
+        w.st = nullptr;
+        e = cudaSetDevice(device);
+    }
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w.st, cudaStreamNonBlocking);
+    for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+        e = cudaHostAlloc((void**)&w.stage[b], chunk, cudaHostAllocDefault);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w.done[b], cudaEventDisableTiming);
+    }
+    w.device = device;
+    w.chunk = chunk;
+    return e;
+}
+
 // dir = 0: host -> device, 1: device -> host
 static int hb_xfer(void* dst, const void* src, size_t bytes, int dir, int device) {
     if (bytes == 0) return HB_OK;
@@ -30,19 +89,17 @@ static int hb_xfer(void* dst, const void* src, size_t bytes, int dir, int device
         HB_CUDA(cudaMemcpy(dst, src, bytes, dir == 0 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost));
         return HB_OK;
     }
+    std::lock_guard<std::mutex> guard(g_xfer_mutex);
+    const size_t HB_XFER_CHUNK = hb_xfer_chunk();
     const size_t nchunks = (bytes + HB_XFER_CHUNK - 1) / HB_XFER_CHUNK;
-    const int workers = (int)std::min<size_t>(HB_XFER_WORKERS, nchunks);
+    const int workers = (int)std::min<size_t>((size_t)hb_xfer_workers(), nchunks);
     std::vector<cudaError_t> err((size_t)workers, cudaSuccess);
     auto work = [&](int t) {
-        cudaError_t e = cudaSetDevice(device);
-        cudaStream_t st = nullptr;
-        unsigned char* stage[2] = {nullptr, nullptr};
-        cudaEvent_t done[2] = {nullptr, nullptr};
-        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
-        for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
-            e = cudaHostAlloc((void**)&stage[b], HB_XFER_CHUNK, cudaHostAllocDefault);
-            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming);
-        }
+        HbXferWorker& w = g_xfer_worker[t];
+        cudaError_t e = hb_xfer_prepare(w, device, HB_XFER_CHUNK);
+        cudaStream_t st = w.st;
+        unsigned char** stage = w.stage;
+        cudaEvent_t* done = w.done;
         size_t pending_off[2] = {0, 0}, pending_len[2] = {0, 0};
         int slot = 0;
         for (size_t c = (size_t)t; c < nchunks && e == cudaSuccess; c += (size_t)workers, slot ^= 1) {
@@ -66,16 +123,12 @@ static int hb_xfer(void* dst, const void* src, size_t bytes, int dir, int device
             pending_len[slot] = len;
         }
         for (int b = 0; b < 2; ++b) {
-            if (pending_len[b] && e == cudaSuccess) {
-                e = cudaEventSynchronize(done[b]);
+            if (pending_len[b]) {   // always drain: the staging buffers outlive this call
+                const cudaError_t e2 = cudaEventSynchronize(done[b]);
+                if (e == cudaSuccess) e = e2;
                 if (e == cudaSuccess && dir == 1) memcpy((unsigned char*)dst + pending_off[b], stage[b], pending_len[b]);
             }
         }
-        for (int b = 0; b < 2; ++b) {
-            if (done[b]) cudaEventDestroy(done[b]);
-            if (stage[b]) cudaFreeHost(stage[b]);
-        }
-        if (st) cudaStreamDestroy(st);
         err[(size_t)t] = e;
     };
     std::vector<std::thread> pool;
