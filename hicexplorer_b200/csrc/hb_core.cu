@@ -130,8 +130,13 @@ int hb_csr_create(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t row0, in
     h->phase = phase;
     HB_CREATE_CUDA(cudaMalloc(&h->d_indices, sizeof(int32_t) * (size_t)(nnz + phase + 4) + 16));
     HB_CREATE_CUDA(cudaMalloc(&h->d_data, sizeof(double) * (size_t)(nnz + phase + 4) + 16));
-    HB_CREATE_CUDA(cudaMemsetAsync(h->d_indices, 0, sizeof(int32_t) * 4, s));
-    HB_CREATE_CUDA(cudaMemsetAsync(h->d_data, 0, sizeof(double) * 4, s));
+    // zero the alignment slots in front of the block.  Only those: the entries themselves arrive through hb_copy_h2d,
+    // which runs on other streams (the handle's stream is non-blocking), so a memset that overlapped them could land
+    // AFTER the copy and wipe the first entries.  The stream is drained before the copies start for the same reason.
+    if (phase > 0) {
+        HB_CREATE_CUDA(cudaMemsetAsync(h->d_indices, 0, sizeof(int32_t) * (size_t)phase, s));
+        HB_CREATE_CUDA(cudaMemsetAsync(h->d_data, 0, sizeof(double) * (size_t)phase, s));
+    }
     HB_CREATE_CUDA(cudaMemcpyAsync(h->d_indptr, indptr, sizeof(int64_t) * (size_t)(n_rows + 1),
                                    cudaMemcpyHostToDevice, s));
     if (indptr[0] != phase) {
@@ -139,6 +144,7 @@ int hb_csr_create(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t row0, in
         hb_rebase_indptr_kernel<<<(unsigned)((n1 + 255) / 256), 256, 0, s>>>(h->d_indptr, n1, indptr[0] - phase);
         g_hb_launches.fetch_add(1);
     }
+    HB_CREATE_CUDA(cudaStreamSynchronize(s));
     if (nnz > 0) {
         if (hb_copy_h2d(h->d_data + phase, data + indptr[0], sizeof(double) * (size_t)nnz, device) != HB_OK) {
             hb_csr_destroy(h);

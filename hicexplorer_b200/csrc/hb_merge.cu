@@ -15,6 +15,7 @@
 #include "hb_internal.cuh"
 #include "hb_scan.cuh"
 
+#define HB_MERGE_DEPTH 4     // steps of 32 entries in flight per warp
 #define HB_MERGE_WINDOW 512  // merged columns accumulated at a time per warp (4 KB of shared memory per warp)
 
 // A warp owns merged row I.  The merged row is produced window by window (HB_MERGE_WINDOW merged columns): for each
@@ -69,47 +70,74 @@ hb_merge_rows_kernel(const int64_t* __restrict__ indptr, const int32_t* __restri
             if (m == INT_MAX) break;
             const int J_lo = m - (m % HB_MERGE_WINDOW);
             const int J_hi = J_lo + HB_MERGE_WINDOW;
+            unsigned int touched = 0;  // 32-column chunks of the window that received something
             for (int r = 0; r < k; ++r) {
+                // far (trans) entries make most windows sparse: a row whose next entry lies beyond this window is
+                // skipped without touching memory
+                if (__shfl_sync(0xffffffffu, head, r) >= J_hi) continue;
                 int64_t c0 = __shfl_sync(0xffffffffu, cur, r);
                 const int64_t e0 = __shfl_sync(0xffffffffu, end, r);
                 const int64_t row = g0 + r;
-                for (;;) {
-                    const int64_t p = c0 + lane;
-                    int J = INT_MAX;  // sentinel: beyond the row or beyond the window
-                    int c = -1;
-                    double v = 0.0;
-                    if (p < e0) {
-                        c = idx[p];
-                        const int Jm = map[c];
-                        J = Jm < 0 ? -1 : Jm;
-                        if (J < J_hi) v = val[p];
-                    }
-                    // entries are consumed up to the first one that belongs to a later window
-                    const unsigned int beyond = __ballot_sync(0xffffffffu, J >= J_hi);
-                    const int take = beyond ? (__ffs(beyond) - 1) : 32;
-                    const bool mine = lane < take;
-                    // dropped column, or lower-triangle entry of the diagonal cell: contributes nothing
-                    const bool live = mine && J >= 0 && !(J == (int)I && c < row);
-                    const int key = mine ? J : INT_MAX - 1;
-                    double s = live ? v : 0.0;
-                    // segmented inclusive scan from the right: after it the first lane of a run holds the run's sum
+                bool stop = false;
+                while (!stop) {
+                    // HB_MERGE_DEPTH steps of 32 consecutive entries are loaded before the first one is consumed: the
+                    // stretch of a row inside a window is contiguous, so only the last step of a stretch is partial
+                    int cc[HB_MERGE_DEPTH], JJ[HB_MERGE_DEPTH];
+                    double vv[HB_MERGE_DEPTH];
 #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const double t = __shfl_down_sync(0xffffffffu, s, o);
-                        const int kt = __shfl_down_sync(0xffffffffu, key, o);
-                        if (lane + o < 32 && kt == key) s += t;
+                    for (int u = 0; u < HB_MERGE_DEPTH; ++u) {
+                        const int64_t p = c0 + 32 * u + lane;
+                        cc[u] = p < e0 ? hb_ldg_stream_i1(idx + p) : -1;
                     }
-                    const int kprev = __shfl_up_sync(0xffffffffu, key, 1);
-                    const bool first = mine && J >= 0 && (lane == 0 || kprev != key);
-                    if (first) acc[J - J_lo] += s;
-                    __syncwarp();
-                    c0 += take;
-                    if (take < 32 || c0 >= e0) break;
+#pragma unroll
+                    for (int u = 0; u < HB_MERGE_DEPTH; ++u) {
+                        const int64_t p = c0 + 32 * u + lane;
+                        vv[u] = p < e0 ? hb_ldg_stream_d1(val + p) : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < HB_MERGE_DEPTH; ++u) {
+                        int J = INT_MAX;  // sentinel: beyond the row
+                        if (cc[u] >= 0) {
+                            const int Jm = __ldg(map + cc[u]);
+                            J = Jm < 0 ? -1 : Jm;
+                        }
+                        JJ[u] = J;
+                    }
+#pragma unroll
+                    for (int u = 0; u < HB_MERGE_DEPTH; ++u) {
+                        if (stop) break;
+                        const int J = JJ[u], c = cc[u];
+                        const double v = vv[u];
+                        // entries are consumed up to the first one that belongs to a later window
+                        const unsigned int beyond = __ballot_sync(0xffffffffu, J >= J_hi);
+                        const int take = beyond ? (__ffs(beyond) - 1) : 32;
+                        const bool mine = lane < take;
+                        // dropped column, or lower-triangle entry of the diagonal cell: contributes nothing
+                        const bool live = mine && J >= 0 && !(J == (int)I && c < row);
+                        const int key = mine ? J : INT_MAX - 1;
+                        double s = live ? v : 0.0;
+                        // segmented inclusive scan from the right: after it the first lane of a run holds the run's sum
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const double t = __shfl_down_sync(0xffffffffu, s, o);
+                            const int kt = __shfl_down_sync(0xffffffffu, key, o);
+                            if (lane + o < 32 && kt == key) s += t;
+                        }
+                        const int kprev = __shfl_up_sync(0xffffffffu, key, 1);
+                        const bool first = mine && J >= 0 && (lane == 0 || kprev != key);
+                        if (first) acc[J - J_lo] += s;
+                        touched |= __reduce_or_sync(0xffffffffu, first ? (1u << ((J - J_lo) >> 5)) : 0u);
+                        __syncwarp();
+                        c0 += take;
+                        if (take < 32 || c0 >= e0) stop = true;
+                    }
                 }
                 if (lane == r) cur = c0;
             }
-            // sweep the window in column order
-            for (int base = 0; base < HB_MERGE_WINDOW; base += 32) {
+            // sweep the touched chunks of the window in column order
+            while (touched) {
+                const int base = (__ffs(touched) - 1) << 5;
+                touched &= touched - 1;
                 const double t = acc[base + lane];
                 const bool nz = t != 0.0;  // eliminate_zeros (reduceMatrix.py:230); NaN != 0 is kept, like scipy
                 const unsigned int bal = __ballot_sync(0xffffffffu, nz);

@@ -55,9 +55,12 @@ def test_merge_random_matrices_match_oracle(n, k, seed):
     with DeviceCSR.from_scipy(m) as dev:
         dev.merge_bins(bin_map, len(new_iv))
         got = dev.download()
-        assert dev.symmetry_ratio() == 0.0
+        ratio = dev.symmetry_ratio()
+        again = dev.download()
     assert np.array_equal(got.indptr, ref.indptr) and np.array_equal(got.indices, ref.indices)
     np.testing.assert_array_equal(got.data, ref.data)
+    np.testing.assert_array_equal(again.data, ref.data)
+    assert ratio == 0.0
 
 
 def test_merge_then_correct_workflow():
