@@ -91,6 +91,10 @@ SIGNATURES = {
     "hb_ice_run": (c_int, [vp, c_int, c_dbl, vp, vp, vp]),
     "hb_ice_scaled_values": (c_int, [vp, vp, P(c_dbl)]),
     "hb_ice_scaled_upper": (c_int, [vp, vp, c_i64, P(c_i64), vp, vp, vp]),
+    "hb_csr_value_stats": (c_int, [vp, c_int, P(c_dbl), P(c_dbl), P(c_dbl)]),
+    "hb_csr_normalize": (c_int, [vp, c_int, c_dbl, c_dbl, c_dbl, c_int]),
+    "hb_csr_eliminate_zeros": (c_int, [vp]),
+    "hb_csr_add": (c_int, [vp, vp]),
     "hb_trans_order_stats": (c_int, [vp, vp, c_int, c_i64, P(c_i64), P(c_dbl), P(c_dbl)]),
     "hb_trans_clip": (c_int, [vp, vp, c_int, c_dbl, P(c_i64)]),
     "hb_ice_scaled_row_sums": (c_int, [vp, vp]),

@@ -25,9 +25,14 @@
 // map monotone) and lets the first lane of each run add into a dense shared-memory accumulator.  One warp touches
 // its accumulator strictly in program order (row after row, step after step), so the sums are deterministic.  The
 // window is then swept in column order: non-zero cells are counted (pass 1) or written (pass 2).
-template <bool FILL>
+//
+// ADD = true turns the same machinery into C = A + B (hicSumMatrices.py:59): output row I is the "merge" of two rows,
+// row I of A and row I of B (second store in indptr_b / idx_b / val_b), with the identity column map and no diagonal
+// rule; cells that sum to exactly 0 are dropped, like scipy's csr_plus_csr.
+template <bool FILL, bool ADD>
 __global__ void __launch_bounds__(256)
 hb_merge_rows_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
+                     const int64_t* __restrict__ indptr_b, const int32_t* __restrict__ idx_b, const double* __restrict__ val_b,
                      const int32_t* __restrict__ map, const int64_t* __restrict__ group_start,
                      const int64_t* __restrict__ group_end, int64_t n_new,
                      int64_t* __restrict__ cnt, const int64_t* __restrict__ out_ptr, int32_t* __restrict__ out_idx,
@@ -40,11 +45,17 @@ hb_merge_rows_kernel(const int64_t* __restrict__ indptr, const int32_t* __restri
     for (int i = lane; i < HB_MERGE_WINDOW; i += 32) acc[i] = 0.0;
     __syncwarp();
     for (int64_t I = gwarp; I < n_new; I += nwarps) {
-        const int64_t g0 = group_start[I];
-        const int k = (int)(group_end[I] - g0);
-        // lane r keeps the cursor of old row g0 + r
+        const int64_t g0 = ADD ? I : group_start[I];
+        const int k = ADD ? 2 : (int)(group_end[I] - g0);
+        // lane r keeps the cursor of old row g0 + r (ADD: lane 0 = row I of A, lane 1 = row I of B)
         int64_t cur = 0, end = 0;
-        if (lane < k) {
+        if (ADD) {
+            if (lane < 2) {
+                const int64_t* ip = lane ? indptr_b : indptr;
+                cur = ip[I];
+                end = ip[I + 1];
+            }
+        } else if (lane < k) {
             cur = indptr[g0 + lane];
             end = indptr[g0 + lane + 1];
         }
@@ -53,7 +64,9 @@ hb_merge_rows_kernel(const int64_t* __restrict__ indptr, const int32_t* __restri
         for (;;) {
             // next window = the one holding the smallest unread merged id over the k rows
             int head = INT_MAX;
-            if (cur < end) {
+            if (ADD) {
+                if (cur < end) head = (lane ? idx_b : idx)[cur];
+            } else if (cur < end) {
                 // skip dropped columns at the cursor (map < 0) so that the head is a real id
                 while (cur < end) {
                     const int J = map[idx[cur]];
@@ -78,6 +91,8 @@ hb_merge_rows_kernel(const int64_t* __restrict__ indptr, const int32_t* __restri
                 int64_t c0 = __shfl_sync(0xffffffffu, cur, r);
                 const int64_t e0 = __shfl_sync(0xffffffffu, end, r);
                 const int64_t row = g0 + r;
+                const int32_t* __restrict__ idx_r = (ADD && r) ? idx_b : idx;
+                const double* __restrict__ val_r = (ADD && r) ? val_b : val;
                 bool stop = false;
                 while (!stop) {
                     // HB_MERGE_DEPTH steps of 32 consecutive entries are loaded before the first one is consumed: the
@@ -87,18 +102,18 @@ hb_merge_rows_kernel(const int64_t* __restrict__ indptr, const int32_t* __restri
 #pragma unroll
                     for (int u = 0; u < HB_MERGE_DEPTH; ++u) {
                         const int64_t p = c0 + 32 * u + lane;
-                        cc[u] = p < e0 ? hb_ldg_stream_i1(idx + p) : -1;
+                        cc[u] = p < e0 ? hb_ldg_stream_i1(idx_r + p) : -1;
                     }
 #pragma unroll
                     for (int u = 0; u < HB_MERGE_DEPTH; ++u) {
                         const int64_t p = c0 + 32 * u + lane;
-                        vv[u] = p < e0 ? hb_ldg_stream_d1(val + p) : 0.0;
+                        vv[u] = p < e0 ? hb_ldg_stream_d1(val_r + p) : 0.0;
                     }
 #pragma unroll
                     for (int u = 0; u < HB_MERGE_DEPTH; ++u) {
                         int J = INT_MAX;  // sentinel: beyond the row
                         if (cc[u] >= 0) {
-                            const int Jm = __ldg(map + cc[u]);
+                            const int Jm = ADD ? cc[u] : __ldg(map + cc[u]);
                             J = Jm < 0 ? -1 : Jm;
                         }
                         JJ[u] = J;
@@ -113,7 +128,7 @@ hb_merge_rows_kernel(const int64_t* __restrict__ indptr, const int32_t* __restri
                         const int take = beyond ? (__ffs(beyond) - 1) : 32;
                         const bool mine = lane < take;
                         // dropped column, or lower-triangle entry of the diagonal cell: contributes nothing
-                        const bool live = mine && J >= 0 && !(J == (int)I && c < row);
+                        const bool live = mine && J >= 0 && (ADD || !(J == (int)I && c < row));
                         const int key = mine ? J : INT_MAX - 1;
                         double s = live ? v : 0.0;
                         // segmented inclusive scan from the right: after it the first lane of a run holds the run's sum
@@ -213,8 +228,8 @@ extern "C" int hb_csr_merge_bins(hb_csr* h, const int32_t* bin_map, int64_t n_ne
     if (n > 0) MG(cudaMemcpyAsync(d_map, bin_map, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
     MG(cudaMemsetAsync(d_cnt, 0, sizeof(int64_t) * (ng + 1), s));
     if (n_new > 0) {
-        hb_merge_rows_kernel<false><<<grid, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, d_map, d_gs, d_ge, n_new,
-                                                         d_cnt, nullptr, nullptr, nullptr);
+        hb_merge_rows_kernel<false, false><<<grid, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, nullptr, nullptr, nullptr,
+                                                                d_map, d_gs, d_ge, n_new, d_cnt, nullptr, nullptr, nullptr);
         g_hb_launches.fetch_add(1);
     }
     hb_scan_kernel<int64_t><<<1, 1024, 0, s>>>(d_cnt, d_ptr, n_new);
@@ -225,8 +240,8 @@ extern "C" int hb_csr_merge_bins(hb_csr* h, const int32_t* bin_map, int64_t n_ne
     MG(cudaMalloc(&d_idx, sizeof(int32_t) * (size_t)(new_nnz > 0 ? new_nnz : 1) + 16));
     MG(cudaMalloc(&d_val, sizeof(double) * (size_t)(new_nnz > 0 ? new_nnz : 1) + 16));
     if (n_new > 0 && new_nnz > 0) {
-        hb_merge_rows_kernel<true><<<grid, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, d_map, d_gs, d_ge, n_new,
-                                                        nullptr, d_ptr, d_idx, d_val);
+        hb_merge_rows_kernel<true, false><<<grid, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, nullptr, nullptr, nullptr,
+                                                               d_map, d_gs, d_ge, n_new, nullptr, d_ptr, d_idx, d_val);
         g_hb_launches.fetch_add(1);
     }
     MG(cudaStreamSynchronize(s));
@@ -257,6 +272,80 @@ fail:
     cudaFree(d_gs);
     cudaFree(d_ge);
     cudaFree(d_map);
+    cudaFree(d_cnt);
+    cudaFree(d_ptr);
+    cudaFree(d_idx);
+    cudaFree(d_val);
+    return rc;
+}
+
+
+// C = A + B on two stores of the same shape (hicSumMatrices.py:59): `h` becomes the sum, `other` is left untouched
+extern "C" int hb_csr_add(hb_csr* h, const hb_csr* other) {
+    HB_REQUIRE(h != nullptr && other != nullptr && h != other, "bad arguments");
+    HB_REQUIRE(h->n_rows == other->n_rows && h->n_cols == other->n_cols && h->row0 == other->row0,
+               "the matrices have different shapes");
+    HB_REQUIRE(h->device == other->device, "both stores must live on the same device");
+    HB_REQUIRE(h->phase == 0 && other->phase == 0, "row blocks with an alignment phase are not supported here");
+    int rc = hb_use_device(h);
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    hb_drop_pack(h);
+    const int64_t n = h->n_rows;
+    int64_t *d_cnt = nullptr, *d_ptr = nullptr;
+    int32_t* d_idx = nullptr;
+    double* d_val = nullptr;
+    int64_t new_nnz = 0;
+    cudaError_t e = cudaSuccess;
+    const int grid = HB_NUM_SMS * 7;   // 32 KB of shared memory per CTA
+    const size_t nn = (size_t)(n > 0 ? n : 1);
+#define AD(expr)                                                  \
+    do {                                                          \
+        e = (expr);                                               \
+        if (e != cudaSuccess) {                                   \
+            rc = hb_cuda_fail(e, #expr, __FILE__, __LINE__);      \
+            goto fail;                                            \
+        }                                                         \
+    } while (0)
+    AD(cudaStreamSynchronize(other->stream));   // whatever produced `other` is complete before this stream reads it
+    AD(cudaMalloc(&d_cnt, sizeof(int64_t) * (nn + 1)));
+    AD(cudaMalloc(&d_ptr, sizeof(int64_t) * (nn + 1)));
+    AD(cudaMemsetAsync(d_cnt, 0, sizeof(int64_t) * (nn + 1), s));
+    if (n > 0) {
+        hb_merge_rows_kernel<false, true><<<grid, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, other->d_indptr,
+                                                               other->d_indices, other->d_data, nullptr, nullptr, nullptr, n,
+                                                               d_cnt, nullptr, nullptr, nullptr);
+        g_hb_launches.fetch_add(1);
+    }
+    hb_scan_kernel<int64_t><<<1, 1024, 0, s>>>(d_cnt, d_ptr, n);
+    g_hb_launches.fetch_add(1);
+    AD(cudaMemcpyAsync(&new_nnz, d_ptr + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    AD(cudaStreamSynchronize(s));
+    AD(cudaGetLastError());
+    AD(cudaMalloc(&d_idx, sizeof(int32_t) * (size_t)(new_nnz > 0 ? new_nnz : 1) + 16));
+    AD(cudaMalloc(&d_val, sizeof(double) * (size_t)(new_nnz > 0 ? new_nnz : 1) + 16));
+    if (n > 0 && new_nnz > 0) {
+        hb_merge_rows_kernel<true, true><<<grid, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, other->d_indptr,
+                                                              other->d_indices, other->d_data, nullptr, nullptr, nullptr, n,
+                                                              nullptr, d_ptr, d_idx, d_val);
+        g_hb_launches.fetch_add(1);
+    }
+    AD(cudaStreamSynchronize(s));
+    AD(cudaGetLastError());
+#undef AD
+    cudaFree(d_cnt);
+    if (h->owns_csr) {
+        cudaFree(h->d_indptr);
+        cudaFree(h->d_indices);
+        cudaFree(h->d_data);
+    }
+    h->owns_csr = true;
+    h->d_indptr = d_ptr;
+    h->d_indices = d_idx;
+    h->d_data = d_val;
+    h->nnz = new_nnz;
+    return HB_OK;
+fail:
     cudaFree(d_cnt);
     cudaFree(d_ptr);
     cudaFree(d_idx);

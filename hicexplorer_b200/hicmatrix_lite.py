@@ -33,6 +33,7 @@ class hiCMatrix(object):
         self._matrix = None          # full symmetric CSR (built lazily from _upper)
         self._upper = None           # upper triangle as stored in the file, while nothing has modified the matrix
         self._file_layout = None     # corrected upper triangle in the original frame, ready to be written
+        self.value_dtype = np.float64  # dtype of /matrix/data (hicNormalize writes the float32 it computes in)
         self.cut_intervals = []
         self.nan_bins = np.array([], dtype=np.int64)
         self.correction_factors = None
@@ -291,7 +292,7 @@ class hiCMatrix(object):
                              "PYTABLES_FORMAT_VERSION": "2.1"})
         w.group("/matrix", group)
         w.group("/intervals", group)
-        w.dataset("/matrix/data", up.data.astype(np.float64), carray)
+        w.dataset("/matrix/data", up.data.astype(self.value_dtype), carray)
         w.dataset("/matrix/indices", up.indices.astype(np.int32), carray)
         w.dataset("/matrix/indptr", up.indptr.astype(np.int32), carray)
         w.dataset("/matrix/shape", np.asarray(up.shape, dtype=np.int64), carray)
@@ -334,5 +335,5 @@ class hiCMatrix(object):
         w.dataset("/indexes/chrom_offset", chrom_offset)
         w.dataset("/pixels/bin1_id", up.row.astype(np.int32))
         w.dataset("/pixels/bin2_id", up.col.astype(np.int32))
-        w.dataset("/pixels/count", up.data.astype(np.float64))
+        w.dataset("/pixels/count", up.data.astype(self.value_dtype))
         w.save(path)

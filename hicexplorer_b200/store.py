@@ -279,6 +279,25 @@ class DeviceCSR(object):
                                         ptr(data)))
         return sparse.csr_matrix((data, indices, indptr), shape=(n_orig, n_orig))
 
+    # ---- hicNormalize / hicSumMatrices (element-wise steps around the correction) --
+    def value_stats(self, scrub=False):
+        """(sum of the stored values in fp64, float32 min, float32 max) -- hicNormalize.py:70, 82-83"""
+        s, mn, mx = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+        check(lib().hb_csr_value_stats(self._h, int(bool(scrub)), ctypes.byref(s), ctypes.byref(mn), ctypes.byref(mx)))
+        return s.value, mn.value, mx.value
+
+    def normalize(self, mode, a=0.0, b=1.0, threshold=0.0, scrub_first=True):
+        """float32 normalisation in place (mode: 'norm_range' (f-a)/b, 'divide' f/a, 'multiply' f*a, 'cast')"""
+        code = {"norm_range": 0, "divide": 1, "multiply": 2, "cast": 3}[mode]
+        check(lib().hb_csr_normalize(self._h, code, float(a), float(b), float(threshold), int(bool(scrub_first))))
+
+    def eliminate_zeros(self):
+        check(lib().hb_csr_eliminate_zeros(self._h))
+
+    def add(self, other):
+        """self <- self + other (same shape); exact zeros dropped like scipy's csr + csr"""
+        check(lib().hb_csr_add(self._h, other.handle))
+
     # ---- optional steps around ICE (--transCutoff / --inflationCutoff) ------------
     def trans_percentile(self, chr_offsets, q):
         """np.percentile(values stored between chromosomes, q) -- what hicmatrix truncTrans computes

@@ -202,6 +202,26 @@ HB_API int hb_ice_scaled_values(hb_csr* h, double* data_out, double* max_out);
 HB_API int hb_ice_scaled_upper(hb_csr* h, const int64_t* orig_ids, int64_t n_orig, int64_t* nnz_out, int64_t* indptr,
                         int32_t* indices, double* data);
 
+/* ---- element-wise steps of the workflow around the correction ----------------------
+ * hicNormalize (hicexplorer/hicNormalize.py:63-153), on the resident store, in the float32 arithmetic the reference
+ * computes in (`matrix.data.astype(np.float32)`):
+ *   hb_csr_value_stats: sum of the stored values (fp64; `hic_ma.matrix.sum()`, :70) and the float32 minimum / maximum of
+ *     the stored values (:82-83), after NaN/Inf -> 0 when scrub != 0 (:77-81).  min/max are NaN for an empty store.
+ *   hb_csr_normalize: value <- float32 op, then NaN/Inf -> 0, then value < threshold -> 0 (:90-96).
+ *     mode 0 norm_range  (f - a) / b   a = min, b = float32(max) - float32(min)          (:84-88)
+ *     mode 1 smallest    f / a         a = sum_i / sum_smallest                           (:110-111)
+ *     mode 2 multiplicative f * a      a = --multiplicativeValue                          (:137)
+ *     mode 3 cast only (the matrix with the smallest sum, :105-106)
+ *     scrub_first != 0: NaN/Inf -> 0 before the operation as well (:77-81, :107-109, :131-135).
+ *   hb_csr_eliminate_zeros: drop stored entries that are exactly 0 (`matrix.eliminate_zeros()`, :93, :97).
+ * hicSumMatrices (hicexplorer/hicSumMatrices.py:59):
+ *   hb_csr_add: h <- h + other (same shape, same device): union of the two sorted rows, values added, cells that sum to
+ *     exactly 0 dropped like scipy's csr + csr.  `other` is not modified. */
+HB_API int hb_csr_value_stats(hb_csr* h, int scrub, double* sum_out, double* min_out, double* max_out);
+HB_API int hb_csr_normalize(hb_csr* h, int mode, double a, double b, double threshold, int scrub_first);
+HB_API int hb_csr_eliminate_zeros(hb_csr* h);
+HB_API int hb_csr_add(hb_csr* h, const hb_csr* other);
+
 /* ---- optional ICE-only steps around the correction -----------------------------
  * --transCutoff (hicCorrectMatrix.py:695-699 -> hicmatrix truncTrans): trans entries are those whose row and column lie
  * in different chromosomes (chr_offsets[nchr+1], ascending, in the CURRENT bin frame).

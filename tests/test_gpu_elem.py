@@ -1,0 +1,128 @@
+"""hicNormalize / hicSumMatrices on the device against the reference's golden files and the oracle."""
+import numpy as np
+import pytest
+from scipy import sparse
+
+from hicexplorer_b200 import hdf5lite
+from hicexplorer_b200.hicmatrix_lite import hiCMatrix
+from hicexplorer_b200.store import DeviceCSR
+from oracle import normalize_oracle
+from tests.conftest import load_golden
+from tests.helpers import random_hic
+
+pytestmark = pytest.mark.gpu
+
+
+def _files(tmp_path):
+    z = load_golden("normalize_small.npz")
+    n = int(z["n"])
+    iv = [(c.decode(), int(s), int(e), float(x)) for c, s, e, x in zip(z["chr"], z["start"], z["end"], z["extra"])]
+    paths = []
+    for key, ext in [("one", ".h5"), ("two", ".h5"), ("one", ".cool")]:
+        up = sparse.csr_matrix((z[key + "_data"], z[key + "_indices"], z[key + "_indptr"]), shape=(n, n))
+        ma = hiCMatrix()
+        ma.matrix = sparse.csr_matrix(up + sparse.triu(up, 1).T)
+        ma.cut_intervals = iv
+        ma._index_intervals()
+        p = str(tmp_path / ("in_" + key + ext))
+        ma.save(p)
+        paths.append(p)
+    return z, paths
+
+
+def _h5(path):
+    f = hdf5lite.File(path)
+    return f["matrix/data"].read(), f["matrix/indices"].read(), f["matrix/indptr"].read()
+
+
+@pytest.mark.parametrize("mode,keys", [("smallest", ("smallest_one", "smallest_two")),
+                                       ("norm_range", ("norm_range_one", "norm_range_two"))])
+def test_hicNormalize_matches_reference_golden(tmp_path, mode, keys):
+    """mirrors test_normalize_smallest / test_normalize_norm_range (test_hicNormalize.py:23-131): exact data"""
+    from hicexplorer_b200.hicNormalize import main
+    z, (one, two, _cool) = _files(tmp_path)
+    o1, o2 = str(tmp_path / "o1.h5"), str(tmp_path / "o2.h5")
+    main("--matrices {} {} --normalize {} -o {} {}".format(one, two, mode, o1, o2).split())
+    for out, key in zip((o1, o2), keys):
+        d, i, p = _h5(out)
+        assert d.dtype == np.float32
+        assert np.array_equal(i, z[key + "_indices"]) and np.array_equal(p, z[key + "_indptr"])
+        np.testing.assert_array_equal(d, z[key + "_data"])
+
+
+def test_hicNormalize_multiplicative_cool(tmp_path):
+    """mirrors test_normalize_multiplicative_h5_cool (:239-258)"""
+    from hicexplorer_b200.hicNormalize import main
+    z, (_one, _two, cool) = _files(tmp_path)
+    out = str(tmp_path / "by2.cool")
+    main("--matrices {} --normalize multiplicative --multiplicativeValue 2 -o {}".format(cool, out).split())
+    up = hiCMatrix(out).upper_for_device()
+    assert np.array_equal(up.indices, z["by2_indices"]) and np.array_equal(up.indptr, z["by2_indptr"])
+    np.testing.assert_array_equal(up.data, z["by2_data"])
+
+
+@pytest.mark.parametrize("mode", ["smallest", "norm_range", "multiplicative"])
+def test_normalize_random_float_matrices_match_oracle(mode):
+    from hicexplorer_b200.hicNormalize import normalize_matrices
+    mats = [random_hic(700, 0.1, s, integer=False) for s in (1, 2, 3)]
+    if mode != "smallest":                    # (a NaN would make every sum ratio of `smallest` NaN: degenerate case)
+        mats[1].data[[5, 77]] = np.nan        # scrubbed to 0 and eliminated (asymmetric on purpose: element-wise path)
+        mats[2].data[11] = np.inf
+    ref = normalize_oracle.normalize(mats, mode, multiplicative_value=0.37, threshold=0.02)
+    hics = []
+    for m in mats:
+        h = hiCMatrix()
+        h.matrix = m.copy()
+        hics.append(h)
+    got = normalize_matrices(hics, mode, multiplicative_value=0.37, threshold=0.02)
+    for g, r in zip(got, ref):
+        r.sort_indices()
+        assert g.matrix.data.dtype == np.float32
+        assert np.array_equal(g.matrix.indptr, r.indptr) and np.array_equal(g.matrix.indices, r.indices)
+        np.testing.assert_array_equal(g.matrix.data, r.data)         # bit-exact float32
+
+
+def test_value_stats():
+    m = random_hic(500, 0.2, 4, integer=False)
+    with DeviceCSR.from_scipy(m) as dev:
+        s, mn, mx = dev.value_stats()
+    assert abs(s - m.sum()) <= 1e-9 * abs(m.sum())
+    assert mn == np.float32(m.data.min()) and mx == np.float32(m.data.max())
+
+
+@pytest.mark.parametrize("n,seed", [(300, 0), (1500, 1), (40, 2)])
+def test_add_matches_scipy(n, seed):
+    a = random_hic(n, 0.1, seed)
+    b = random_hic(n, 0.05, seed + 10, empty_frac=0.05)
+    c = random_hic(n, 0.3, seed + 20)
+    b.data[::7] *= -1
+    a2 = sparse.csr_matrix(a - b)             # exact cancellations: a - b + b has cells that sum to 0
+    a2.sort_indices()
+    want = normalize_oracle.sum_matrices([a2, b, c])
+    want.sort_indices()
+    with DeviceCSR.from_scipy(a2) as total, DeviceCSR.from_scipy(b) as db, DeviceCSR.from_scipy(c) as dc:
+        total.add(db)
+        total.add(dc)
+        got = total.download()
+        assert db.download().nnz == b.nnz
+    assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
+    np.testing.assert_array_equal(got.data, want.data)
+
+
+def test_hicSumMatrices_cli(tmp_path):
+    from hicexplorer_b200.hicSumMatrices import main
+    z, (one, two, cool) = _files(tmp_path)
+    out = str(tmp_path / "sum.h5")
+    main("--matrices {} {} {} --outFileName {}".format(one, two, cool, out).split())
+    a, b = hiCMatrix(one).matrix, hiCMatrix(two).matrix
+    want = sparse.triu(a + b + a, 0, format="csr")
+    want.sort_indices()
+    d, i, p = _h5(out)
+    assert np.array_equal(i, want.indices) and np.array_equal(p, want.indptr)
+    np.testing.assert_array_equal(d, want.data)
+    with pytest.raises(SystemExit):
+        bad = hiCMatrix(one)
+        bad.reorderChromosomes(list(reversed(bad.getChrNames())))
+        badp = str(tmp_path / "bad.h5")
+        bad.save(badp)
+        main("--matrices {} {} --outFileName {}".format(one, badp, out).split())

@@ -177,3 +177,44 @@ def test_merge_oracle_equals_reference_reduce_matrix():
     got = merge_oracle.reduce(m, bin_map, len(new_iv))
     assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
     np.testing.assert_array_equal(got.data, want.data)
+
+
+# ---- hicNormalize / hicSumMatrices ---------------------------------------------------------
+def _norm_inputs():
+    from tests.conftest import load_golden
+    z = load_golden("normalize_small.npz")
+    n = int(z["n"])
+
+    def full(key):
+        up = sparse.csr_matrix((z[key + "_data"], z[key + "_indices"], z[key + "_indptr"]), shape=(n, n))
+        m = sparse.csr_matrix(up + sparse.triu(up, 1).T)
+        m.sort_indices()
+        return m
+    return z, n, full
+
+
+def _upper(m):
+    up = sparse.triu(m, 0, format="csr")
+    up.sort_indices()
+    return up
+
+
+@pytest.mark.parametrize("mode,keys", [("smallest", ("smallest_one", "smallest_two")),
+                                       ("norm_range", ("norm_range_one", "norm_range_two"))])
+def test_normalize_oracle_reproduces_reference_golden_files(mode, keys):
+    from oracle import normalize_oracle
+    z, n, full = _norm_inputs()
+    got = normalize_oracle.normalize([full("one"), full("two")], mode)
+    for m, key in zip(got, keys):
+        up = _upper(m)
+        assert up.data.dtype == np.float32
+        assert np.array_equal(up.indptr, z[key + "_indptr"]) and np.array_equal(up.indices, z[key + "_indices"])
+        np.testing.assert_array_equal(up.data, z[key + "_data"])        # bit-exact float32
+
+
+def test_normalize_oracle_multiplicative_golden():
+    from oracle import normalize_oracle
+    z, n, full = _norm_inputs()
+    up = _upper(normalize_oracle.normalize([full("one")], "multiplicative", multiplicative_value=2)[0])
+    assert np.array_equal(up.indices, z["by2_indices"]) and np.array_equal(up.indptr, z["by2_indptr"])
+    np.testing.assert_array_equal(up.data, z["by2_data"])
