@@ -126,6 +126,56 @@ def main():
                     "cpu_baseline": {"value": sample.nnz / t_cpu, "unit": "input entries/s", "cores": 1, "kind": "port",
                                      "sample": "oracle/merge_oracle.py (numpy/scipy restatement of reduce_matrix) on chromosome 1 "
                                                "of the same matrix (%d entries), %.1f s" % (sample.nnz, t_cpu)}})
+    elif config == "elem10k":
+        # hicNormalize (norm_range) and hicSumMatrices (A + B) on the synthetic 10 kb matrix, 1 GPU
+        method, bins, kw = bench.synth_kwargs("ice10k", clean=True)
+        from oracle import hic_cpu, normalize_oracle
+
+        def wall(fn, dev):
+            dev.sync()
+            t0 = time.time()
+            r = fn()
+            dev.sync()
+            return r, time.time() - t0
+        res = {}
+        with DeviceCSR.synthetic(bins, device=local, **kw) as dev:
+            nnz = dev.nnz
+            dev.value_stats()                                   # warm-up (lazy module load)
+            (tot, mn, mx), t_stats = wall(lambda: dev.value_stats(scrub=True), dev)
+            _, t_norm = wall(lambda: dev.normalize("norm_range", a=mn, b=np.float32(mx) - np.float32(mn)), dev)
+            _, t_elim = wall(dev.eliminate_zeros, dev)
+            nnz_after = dev.nnz
+            res["normalize"] = {"value_stats_ms": t_stats * 1e3, "normalize_ms": t_norm * 1e3, "eliminate_zeros_ms": t_elim * 1e3,
+                                "entries_in": nnz, "entries_out": nnz_after,
+                                "stats_GBps": 8.0 * nnz / t_stats / 1e9, "normalize_GBps": 16.0 * nnz / t_norm / 1e9,
+                                "eliminate_GBps": (8.0 * nnz + 12.0 * nnz + 12.0 * nnz_after) / t_elim / 1e9,
+                                "entries_per_s_whole_tool": nnz / (t_stats + t_norm + t_elim),
+                                "frac_of_peak_normalize": 16.0 * nnz / t_norm / 1e9 / peak}
+        kw_b = dict(kw, seed=1)
+        with DeviceCSR.synthetic(bins, device=local, **kw) as a, DeviceCSR.synthetic(bins, device=local, **kw_b) as b:
+            na, nb = a.nnz, b.nnz
+            _, t_add = wall(lambda: a.add(b), a)
+            nc = a.nnz
+            res["sum"] = {"ms": t_add * 1e3, "entries_a": na, "entries_b": nb, "entries_out": nc,
+                          "input_entries_per_s": (na + nb) / t_add,
+                          "GBps": (2 * 12.0 * (na + nb) + 12.0 * nc) / t_add / 1e9,
+                          "frac_of_peak": (2 * 12.0 * (na + nb) + 12.0 * nc) / t_add / 1e9 / peak,
+                          "note": "two passes over both inputs (count, fill) + allocation of the summed store"}
+        sa = hic_cpu.synth_matrix([bins[0]], **kw)
+        sb = hic_cpu.synth_matrix([bins[0]], **kw_b)
+        t0 = time.time()
+        normalize_oracle.normalize([sa], "norm_range")
+        t_cn = time.time() - t0
+        t0 = time.time()
+        normalize_oracle.sum_matrices([sa, sb])
+        t_cs = time.time() - t0
+        res["cpu_baseline"] = {"normalize_entries_per_s": sa.nnz / t_cn, "sum_input_entries_per_s": (sa.nnz + sb.nnz) / t_cs,
+                               "cores": 1, "kind": "port",
+                               "sample": "oracle/normalize_oracle.py (numpy/scipy restatement) on chromosome 1 of the same "
+                                         "matrices (%d / %d entries)" % (sa.nnz, sb.nnz)}
+        out.update({"workload": "hicNormalize norm_range / hicSumMatrices on the synthetic 10 kb matrix (%d bins, %d entries)"
+                                % (int(sum(bins)), nnz)})
+        out.update(res)
     elif config == "perchr5k":
         method, bins, kw = bench.synth_kwargs("perchr5k", clean=True)
         kw = dict(kw, n_trans=0)                    # cis only: block diagonal by construction
