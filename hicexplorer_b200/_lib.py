@@ -95,6 +95,8 @@ SIGNATURES = {
     "hb_csr_normalize": (c_int, [vp, c_int, c_dbl, c_dbl, c_dbl, c_int]),
     "hb_csr_eliminate_zeros": (c_int, [vp]),
     "hb_csr_add": (c_int, [vp, vp]),
+    "hb_distance_stats": (c_int, [vp, vp, vp]),
+    "hb_obs_exp_apply": (c_int, [vp, vp, c_int, c_int, vp, vp]),
     "hb_trans_order_stats": (c_int, [vp, vp, c_int, c_i64, P(c_i64), P(c_dbl), P(c_dbl)]),
     "hb_trans_clip": (c_int, [vp, vp, c_int, c_dbl, P(c_i64)]),
     "hb_ice_scaled_row_sums": (c_int, [vp, vp]),

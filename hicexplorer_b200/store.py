@@ -298,6 +298,21 @@ class DeviceCSR(object):
         """self <- self + other (same shape); exact zeros dropped like scipy's csr + csr"""
         check(lib().hb_csr_add(self._h, other.handle))
 
+    # ---- hicTransform obs/exp -------------------------------------------------------
+    def distance_stats(self):
+        """(sum, count) of the stored non-zero values per genomic distance (per segment: slot seg_off[s] + d)"""
+        n = self.n
+        sums = np.zeros(n, dtype=np.float64)
+        counts = np.zeros(n, dtype=np.int64)
+        check(lib().hb_distance_stats(self._h, ptr(sums), ptr(counts)))
+        return sums, counts
+
+    def obs_exp_apply(self, expected, index_mode, out_mode, row_sum=None, seg_total=None):
+        ex = np.ascontiguousarray(expected, dtype=np.float64)
+        rs = None if row_sum is None else np.ascontiguousarray(row_sum, dtype=np.float64)
+        tot = None if seg_total is None else np.ascontiguousarray(seg_total, dtype=np.float64)
+        check(lib().hb_obs_exp_apply(self._h, ptr(ex), int(index_mode), int(out_mode), ptr(rs), ptr(tot)))
+
     # ---- optional steps around ICE (--transCutoff / --inflationCutoff) ------------
     def trans_percentile(self, chr_offsets, q):
         """np.percentile(values stored between chromosomes, q) -- what hicmatrix truncTrans computes

@@ -222,6 +222,22 @@ HB_API int hb_csr_normalize(hb_csr* h, int mode, double a, double b, double thre
 HB_API int hb_csr_eliminate_zeros(hb_csr* h);
 HB_API int hb_csr_add(hb_csr* h, const hb_csr* other);
 
+/* ---- observed / expected (hicTransform) ------------------------------------------------
+ * Replaces the per-entry work of hicexplorer/utilities.py:293-338, 356-444, 479-600 as driven by hicTransform.py:162-215.
+ * Segments (hb_set_segments + hb_csr_keep_cis) give --perChromosome: slot seg_off[s] + d of the n-vectors belongs to
+ * distance d of chromosome s.
+ *   hb_distance_stats: sums_out[.] = sum, counts_out[.] = number (may be NULL) of the stored NON-ZERO values at
+ *     genomic distance d = |row - col|.
+ *   hb_obs_exp_apply: value <- float32(value) / expected[index(d)] computed in fp64 like numpy does for
+ *     float32_array / float64_array; index_mode 0: d (obs_exp_non_zero), 1: ceil(d / 2) (obs_exp, obs_exp_lieberman --
+ *     sic, utilities.py:489, 581); NaN/Inf -> 0; out_mode 0: keep fp64, 1: truncate to an integer (`.astype(data_type)`
+ *     of an integer input), 2: round to float32.  row_sum[n] + seg_total[nseg] (both or neither): the ligation factor
+ *     expected *= row_sum[row] * row_sum[col] / total (utilities.py:533-534).  Zeros are left for
+ *     hb_csr_eliminate_zeros. */
+HB_API int hb_distance_stats(hb_csr* h, double* sums_out, int64_t* counts_out);
+HB_API int hb_obs_exp_apply(hb_csr* h, const double* expected, int index_mode, int out_mode, const double* row_sum,
+                     const double* seg_total);
+
 /* ---- optional ICE-only steps around the correction -----------------------------
  * --transCutoff (hicCorrectMatrix.py:695-699 -> hicmatrix truncTrans): trans entries are those whose row and column lie
  * in different chromosomes (chr_offsets[nchr+1], ascending, in the CURRENT bin frame).

@@ -1,0 +1,63 @@
+"""hicTransform obs/exp on the device against golden vectors produced by the reference's own
+functions (tests/golden/make_golden_transform.py), the reference's golden files, and the CPU oracle."""
+import numpy as np
+import pytest
+from scipy import sparse
+
+from hicexplorer_b200.hicmatrix_lite import hiCMatrix
+from hicexplorer_b200.hicTransform import main, obs_exp_transform
+from oracle import transform_oracle
+from tests.conftest import load_golden
+from tests.helpers import random_hic
+from tests.test_oracle import TRANSFORM_CASES, _transform_inputs, _upper
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("key,which,method,pc,lig", TRANSFORM_CASES)
+def test_obs_exp_equals_reference_functions(key, which, method, pc, lig):
+    t, ma, mb = _transform_inputs()
+    m, offs = (ma, t["offsets"]) if which == "a" else (mb, t["b_offsets"])
+    got = _upper(obs_exp_transform(m, method, offs, per_chromosome=pc, ligation_factor=lig))
+    assert np.array_equal(got.indptr, t[key + "_indptr"]) and np.array_equal(got.indices, t[key + "_indices"])
+    np.testing.assert_array_equal(got.data, t[key + "_data"])            # integer counts: bit-exact
+
+
+@pytest.mark.parametrize("method,pc,lig", [("obs_exp", False, False), ("obs_exp", True, False), ("obs_exp_non_zero", False, True),
+                                           ("obs_exp_non_zero", True, False), ("obs_exp_lieberman", False, False)])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_obs_exp_float_matrices_match_oracle(method, pc, lig, dtype):
+    m = random_hic(900, 0.15, 21, integer=False).astype(dtype)
+    offs = np.array([0, 310, 640, 900])
+    ref = transform_oracle.transform(m, method, offs, per_chromosome=pc, ligation_factor=lig)
+    got = obs_exp_transform(m, method, offs, per_chromosome=pc, ligation_factor=lig)
+    ref.sort_indices()
+    assert got.dtype == ref.dtype
+    assert np.array_equal(got.indptr, ref.indptr) and np.array_equal(got.indices, ref.indices)
+    # distance sums are accumulated with fp64 atomics (order not fixed): rounding-level agreement for float input
+    # (one float32 ulp where the reference rounds the quotient to float32)
+    rounds_to_f32 = dtype == np.float32 or method == "obs_exp_non_zero"
+    np.testing.assert_allclose(got.data, ref.data, rtol=1e-6 if rounds_to_f32 else 1e-12)
+
+
+def test_hicTransform_cli_obs_exp(tmp_path):
+    """mirrors test_hic_transfer_obs_exp / _perChromosome (test_hicTransform.py:20-48)"""
+    z = load_golden("normalize_small.npz")
+    t = load_golden("transform_small.npz")
+    n = int(z["n"])
+    up = sparse.csr_matrix((z["one_data"].astype(np.int32), z["one_indices"], z["one_indptr"]), shape=(n, n))
+    ma = hiCMatrix()
+    ma.matrix = sparse.csr_matrix(up + sparse.triu(up, 1).T)
+    ma.cut_intervals = [(c.decode(), int(s), int(e), float(x)) for c, s, e, x in zip(z["chr"], z["start"], z["end"], z["extra"])]
+    ma._index_intervals()
+    ma.value_dtype = np.int32
+    src = str(tmp_path / "small_test_matrix.cool")
+    ma.save(src)
+    for flags, key in [("", "obs_exp"), ("--perChromosome", "obs_exp_pc")]:
+        out = str(tmp_path / ("o" + key + ".cool"))
+        main("--matrix {} --outFileName {} --method obs_exp {}".format(src, out, flags).split())
+        new = _upper(hiCMatrix(out).matrix)
+        np.testing.assert_array_equal(new.data, t["ref_" + key + "_data"])
+        np.testing.assert_array_almost_equal(new.data, t["file_" + key + "_data"], decimal=0)   # the reference's own check
+    with pytest.raises(SystemExit):
+        main("--matrix {} --outFileName {} --method pearson".format(src, str(tmp_path / "p.h5")).split())

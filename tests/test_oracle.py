@@ -218,3 +218,44 @@ def test_normalize_oracle_multiplicative_golden():
     up = _upper(normalize_oracle.normalize([full("one")], "multiplicative", multiplicative_value=2)[0])
     assert np.array_equal(up.indices, z["by2_indices"]) and np.array_equal(up.indptr, z["by2_indptr"])
     np.testing.assert_array_equal(up.data, z["by2_data"])
+
+
+# ---- hicTransform obs/exp ------------------------------------------------------------------
+def _transform_inputs():
+    from tests.conftest import load_golden
+    z, n, full = _norm_inputs()
+    t = load_golden("transform_small.npz")
+    nb = int(t["b_n"])
+    ub = sparse.csr_matrix((t["b_data"], t["b_indices"], t["b_indptr"]), shape=(nb, nb))
+    mb = sparse.csr_matrix(ub + sparse.triu(ub, 1).T)
+    mb.sort_indices()
+    return t, full("one").astype(np.int32), mb
+
+
+TRANSFORM_CASES = [("ref_obs_exp", "a", "obs_exp", False, False), ("ref_obs_exp_pc", "a", "obs_exp", True, False),
+                   ("ref_non_zero_pc", "a", "obs_exp_non_zero", True, False),
+                   ("ref_lieberman_b", "b", "obs_exp_lieberman", False, False),
+                   ("ref_non_zero_lig_b", "b", "obs_exp_non_zero", False, True),
+                   ("ref_non_zero_lig_pc_b", "b", "obs_exp_non_zero", True, True)]
+
+
+@pytest.mark.parametrize("key,which,method,pc,lig", TRANSFORM_CASES)
+def test_transform_oracle_equals_reference_functions(key, which, method, pc, lig):
+    """golden vectors = outputs of the reference's own hicTransform._obs_exp* functions (make_golden_transform.py)"""
+    from oracle import transform_oracle
+    t, ma, mb = _transform_inputs()
+    m, offs = (ma, t["offsets"]) if which == "a" else (mb, t["b_offsets"])
+    got = _upper(transform_oracle.transform(m, method, offs, per_chromosome=pc, ligation_factor=lig))
+    assert np.array_equal(got.indptr, t[key + "_indptr"]) and np.array_equal(got.indices, t[key + "_indices"])
+    np.testing.assert_array_equal(got.data, t[key + "_data"])
+
+
+@pytest.mark.parametrize("key,file_key", [("ref_obs_exp", "file_obs_exp"), ("ref_obs_exp_pc", "file_obs_exp_pc"),
+                                          ("ref_non_zero_pc", "file_non_zero_pc"), ("ref_lieberman_b", "file_lieberman_b")])
+def test_transform_reference_golden_files_to_their_own_tolerance(key, file_key):
+    """the files under test_data/hicTransform were written by an older code version; the reference's tests compare them
+    with assert_array_almost_equal(decimal=0) (test_hicTransform.py:17, 31)"""
+    from tests.conftest import load_golden
+    t = load_golden("transform_small.npz")
+    assert np.array_equal(t[key + "_indices"], t[file_key + "_indices"])
+    np.testing.assert_array_almost_equal(t[key + "_data"], t[file_key + "_data"], decimal=0)
