@@ -72,7 +72,34 @@ __global__ void hb_rebase_indptr_kernel(int64_t* indptr, int64_t n1, int64_t bas
 __global__ void hb_narrow_indices_kernel(const int64_t* __restrict__ in, int32_t* __restrict__ out, int64_t n) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) out[i] = (int32_t)in[i];
+    // a value that does not fit becomes -1 and is rejected by the validation pass
+    for (; i < n; i += stride) out[i] = (in[i] >= 0 && in[i] < 2147483647LL) ? (int32_t)in[i] : -1;
+}
+
+// The kernels of the path trust the store: an out-of-range column id would be an out-of-bounds gather.  One streaming
+// pass over the column ids (4 B per entry) checks what the contract in hicbalance.h states:
+// flags bit 0: indptr decreases; bit 1: a column id outside [0, n_cols); bit 2: columns not strictly ascending in a row
+__global__ void __launch_bounds__(256)
+hb_validate_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, int64_t n_rows, int64_t n_cols,
+                   int64_t first, int64_t last, unsigned int* flags) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    unsigned int bad = 0;
+    for (int64_t row = gwarp; row < n_rows; row += nwarps) {
+        const int64_t s = indptr[row], e = indptr[row + 1];
+        if (e < s || s < first || e > last) {
+            bad |= 1u;
+            continue;
+        }
+        for (int64_t k = s + lane; k < e; k += 32) {
+            const int c = idx[k];
+            if (c < 0 || c >= n_cols) bad |= 2u;
+            if (k > s && idx[k - 1] >= c) bad |= 4u;
+        }
+    }
+    bad = __reduce_or_sync(0xffffffffu, bad);
+    if (lane == 0 && bad) atomicOr(flags, bad);
 }
 
 static int hb_new_handle(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t row0, int64_t nnz, int device) {
@@ -175,6 +202,29 @@ int hb_csr_create(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t row0, in
         }
     }
     HB_CREATE_CUDA(cudaStreamSynchronize(s));
+    {
+        // reject a malformed block before any kernel gathers through its column ids
+        unsigned int* d_flags = nullptr;
+        unsigned int flags = 0;
+        HB_CREATE_CUDA(cudaMalloc(&d_flags, sizeof(unsigned int)));
+        cudaError_t ve = cudaMemsetAsync(d_flags, 0, sizeof(unsigned int), s);
+        if (ve == cudaSuccess && n_rows > 0) {
+            hb_validate_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_indptr, h->d_indices, n_rows, n_cols, phase, phase + nnz, d_flags);
+            g_hb_launches.fetch_add(1);
+        }
+        if (ve == cudaSuccess) ve = cudaMemcpyAsync(&flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost, s);
+        if (ve == cudaSuccess) ve = cudaStreamSynchronize(s);
+        cudaFree(d_flags);
+        HB_CREATE_CUDA(ve);
+        if (flags) {
+            hb_csr_destroy(h);
+            *out = nullptr;
+            hb_set_error("hb_csr_create: malformed CSR block:%s%s%s", (flags & 1u) ? " indptr is not monotone;" : "",
+                         (flags & 2u) ? " a column id lies outside [0, n_cols);" : "",
+                         (flags & 4u) ? " column ids are not strictly ascending inside a row (sort and sum duplicates first);" : "");
+            return HB_ERR_INVALID_ARG;
+        }
+    }
 #undef HB_CREATE_CUDA
     rc = hb_build_tiles(h);
     if (rc != HB_OK) {

@@ -82,7 +82,9 @@ HB_API uint64_t hb_launch_count(void);
  * [row0, row0 + n_rows) of an n_cols x n_cols symmetric matrix (single GPU:
  * row0 = 0, n_rows = n_cols).  indptr may start at any offset; it is rebased.
  * indices_i64 != 0 means `indices` points at int64 (krbalancing's ctor
- * signature) instead of int32. */
+ * signature) instead of int32.  The block is validated on the device before the call returns (one pass over the column
+ * ids): a non-monotone indptr, a column id outside [0, n_cols) or columns that are not strictly ascending inside a row
+ * give HB_ERR_INVALID_ARG -- no later kernel ever gathers through an unchecked index. */
 HB_API int hb_csr_create(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t row0, int64_t nnz,
                   const int64_t* indptr, const void* indices, int indices_i64, const double* data,
                   int device);

@@ -68,3 +68,31 @@ def test_upload_round_trip_is_exact_every_time():
             got = dev.download()
         assert np.array_equal(got.indices[:8], m.indices[:8]) and np.array_equal(got.data[:8], m.data[:8])
     assert np.array_equal(got.indices, m.indices) and np.array_equal(got.data, m.data)
+
+
+def test_malformed_blocks_are_rejected_at_upload():
+    """the C ABI validates what it is handed (a raw ctypes caller may skip scipy's canonical form)"""
+    import ctypes
+    L = _lib.lib()
+
+    def create(indptr, indices, data, n):
+        ip = np.asarray(indptr, dtype=np.int64)
+        ix = np.asarray(indices, dtype=np.int32)
+        da = np.asarray(data, dtype=np.float64)
+        h = ctypes.c_void_p()
+        rc = L.hb_csr_create(ctypes.byref(h), n, n, 0, len(ix), _lib.ptr(ip), _lib.ptr(ix), 0, _lib.ptr(da), 0)
+        if rc == 0:
+            L.hb_csr_destroy(h)
+        return rc, _lib.last_error()
+
+    assert create([0, 2, 3, 4], [0, 2, 1, 0], [1, 2, 3, 4], 3)[0] == 0
+    rc, msg = create([0, 2, 3, 4], [0, 3, 1, 0], [1, 2, 3, 4], 3)
+    assert rc == _lib.HB_ERR_INVALID_ARG and "outside" in msg
+    rc, msg = create([0, 2, 3, 4], [0, -1, 1, 0], [1, 2, 3, 4], 3)
+    assert rc == _lib.HB_ERR_INVALID_ARG and "outside" in msg
+    rc, msg = create([0, 2, 3, 4], [2, 0, 1, 0], [1, 2, 3, 4], 3)
+    assert rc == _lib.HB_ERR_INVALID_ARG and "ascending" in msg
+    rc, msg = create([0, 2, 2, 4], [1, 1, 0, 2], [1, 2, 3, 4], 3)           # duplicate column in a row
+    assert rc == _lib.HB_ERR_INVALID_ARG and "ascending" in msg
+    rc, msg = create([0, 3, 2, 4], [0, 1, 2, 0], [1, 2, 3, 4], 3)
+    assert rc == _lib.HB_ERR_INVALID_ARG and "monotone" in msg
