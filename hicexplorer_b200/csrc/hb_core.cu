@@ -341,7 +341,7 @@ int hb_peer_export(hb_csr* h, int rank, int world, void* ipc_handle_out) {
     const size_t total = 2 * buf + 2 * 512 + 256;
     HB_CUDA(cudaMalloc(&h->d_sym, total));
     HB_CUDA(cudaMemset(h->d_sym, 0, total));
-    HB_CUDA(cudaDeviceSynchronize());
+    HB_CUDA(cudaDeviceSynchronize());   // cudaMemset is asynchronous and the handle's stream is non-blocking: finish it here
     h->d_done = (unsigned int*)((unsigned char*)h->d_sym + 2 * buf + 2 * 512);
     cudaIpcMemHandle_t hd;
     HB_CUDA(cudaIpcGetMemHandle(&hd, h->d_sym));
@@ -514,6 +514,7 @@ int hb_ensure_state(hb_csr* h) {
     h->d_row_counter = (unsigned long long*)(b + o_small + 64);
     h->d_scalar_bits = (unsigned long long*)(b + o_small + 128);
     HB_CUDA(cudaMemset(b + o_small, 0, 256));
+    HB_CUDA(cudaDeviceSynchronize());   // cudaMemset is asynchronous and the work streams are non-blocking: finish it here
     HB_CUDA(cudaHostAlloc(&h->h_pinned, 1024, cudaHostAllocDefault));
     h->h_status = (int32_t*)h->h_pinned;                              // 16 slots x HB_ST_WORDS x 4 B = 256 B
     h->h_kr_sc = (double*)((unsigned char*)h->h_pinned + 512);       // 16 doubles

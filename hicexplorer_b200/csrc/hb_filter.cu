@@ -696,19 +696,20 @@ int hb_mad_filter(hb_csr* h, double lo, double hi, uint8_t* mask_out, double* zs
     uint8_t* d_mask;
     HbSelState* d_st;
     unsigned int* d_hist;
+    HbScratch scratch;   // freed on every return path
     // row sums and diagonals share one buffer so that a sharded run assembles both with ONE sum-allreduce
-    HB_CUDA(cudaMalloc(&d_rs, sizeof(double) * 2 * n));
+    HB_CUDA(scratch.alloc(&d_rs, sizeof(double) * 2 * n));
     d_dg = d_rs + n;
     HB_CUDA(cudaMemsetAsync(d_rs, 0, sizeof(double) * 2 * n, s));
-    HB_CUDA(cudaMalloc(&d_pts, sizeof(double) * n));
-    HB_CUDA(cudaMalloc(&d_diff, sizeof(double) * n));
-    HB_CUDA(cudaMalloc(&d_abs, sizeof(double) * n));
-    if (zscore_out) HB_CUDA(cudaMalloc(&d_z, sizeof(double) * n));
-    HB_CUDA(cudaMalloc(&d_med, sizeof(double) * nseg));
-    HB_CUDA(cudaMalloc(&d_mad, sizeof(double) * nseg));
-    HB_CUDA(cudaMalloc(&d_mask, n));
-    HB_CUDA(cudaMalloc(&d_st, sizeof(HbSelState) * 2 * nseg));
-    HB_CUDA(cudaMalloc(&d_hist, sizeof(unsigned int) * 256 * nseg));
+    HB_CUDA(scratch.alloc(&d_pts, sizeof(double) * n));
+    HB_CUDA(scratch.alloc(&d_diff, sizeof(double) * n));
+    HB_CUDA(scratch.alloc(&d_abs, sizeof(double) * n));
+    if (zscore_out) HB_CUDA(scratch.alloc(&d_z, sizeof(double) * n));
+    HB_CUDA(scratch.alloc(&d_med, sizeof(double) * nseg));
+    HB_CUDA(scratch.alloc(&d_mad, sizeof(double) * nseg));
+    HB_CUDA(scratch.alloc(&d_mask, n));
+    HB_CUDA(scratch.alloc(&d_st, sizeof(HbSelState) * 2 * nseg));
+    HB_CUDA(scratch.alloc(&d_hist, sizeof(unsigned int) * 256 * nseg));
     HB_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned int) * 256 * nseg, s));
     // with segments set, the statistics are those of each chromosome's diagonal block (hicCorrectMatrix.py:557-568)
     if (h->n_rows > 0) {
@@ -739,8 +740,6 @@ int hb_mad_filter(hb_csr* h, double lo, double hi, uint8_t* mask_out, double* zs
         if (e == cudaSuccess && median_out) e = cudaMemcpy(median_out, d_med, sizeof(double) * nseg, cudaMemcpyDeviceToHost);
         if (e == cudaSuccess && mad_out) e = cudaMemcpy(mad_out, d_mad, sizeof(double) * nseg, cudaMemcpyDeviceToHost);
     }
-    cudaFree(d_rs); cudaFree(d_pts); cudaFree(d_diff); cudaFree(d_abs); cudaFree(d_z);
-    cudaFree(d_med); cudaFree(d_mad); cudaFree(d_mask); cudaFree(d_st); cudaFree(d_hist);
     if (rc) return rc;
     if (e != cudaSuccess) return hb_cuda_fail(e, "mad filter", __FILE__, __LINE__);
     return HB_OK;
@@ -771,10 +770,11 @@ int hb_csr_compact(hb_csr* h, const uint8_t* remove_mask) {
     uint8_t* d_rm = nullptr;
     int32_t *d_keep = nullptr, *d_newid = nullptr;
     int64_t* d_scan = nullptr;
-    HB_CUDA(cudaMalloc(&d_rm, n));
-    HB_CUDA(cudaMalloc(&d_keep, sizeof(int32_t) * n));
-    HB_CUDA(cudaMalloc(&d_newid, sizeof(int32_t) * n));
-    HB_CUDA(cudaMalloc(&d_scan, sizeof(int64_t) * (n + 1)));
+    HbScratch scratch;   // freed on every return path
+    HB_CUDA(scratch.alloc(&d_rm, n));
+    HB_CUDA(scratch.alloc(&d_keep, sizeof(int32_t) * n));
+    HB_CUDA(scratch.alloc(&d_newid, sizeof(int32_t) * n));
+    HB_CUDA(scratch.alloc(&d_scan, sizeof(int64_t) * (n + 1)));
     HB_CUDA(cudaMemcpyAsync(d_rm, remove_mask, n, cudaMemcpyHostToDevice, s));
     const unsigned g = (unsigned)((n + 255) / 256);
     hb_keepflag_kernel<<<g, 256, 0, s>>>(d_rm, d_keep, n);
@@ -784,10 +784,6 @@ int hb_csr_compact(hb_csr* h, const uint8_t* remove_mask) {
     hb_newid_kernel<<<g, 256, 0, s>>>(d_rm, d_scan, d_newid, n);
     HB_LAUNCH_CHECK();
     rc = hb_compact_impl(h, d_newid, kept, kept_before_block, kept_in_block, 0, 0);
-    cudaFree(d_rm);
-    cudaFree(d_keep);
-    cudaFree(d_newid);
-    cudaFree(d_scan);
     if (rc) return rc;
     hb_free_state(h);
     h->seg_off = new_off;

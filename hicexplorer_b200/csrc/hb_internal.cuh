@@ -122,6 +122,25 @@ struct hb_csr {
     double* h_kr_sc = nullptr;         // pinned mirror of the KR scalars
 };
 
+// Device scratch that is released on every exit path of a host function (early error returns included).
+struct HbScratch {
+    std::vector<void*> ptrs;
+    template <typename T>
+    cudaError_t alloc(T** p, size_t bytes) {
+        void* q = nullptr;
+        const cudaError_t e = cudaMalloc(&q, bytes ? bytes : 1);
+        if (e == cudaSuccess) ptrs.push_back(q);
+        *p = static_cast<T*>(q);
+        return e;
+    }
+    ~HbScratch() {
+        for (void* q : ptrs) cudaFree(q);
+    }
+    HbScratch() = default;
+    HbScratch(const HbScratch&) = delete;
+    HbScratch& operator=(const HbScratch&) = delete;
+};
+
 int hb_build_tiles(hb_csr* h);
 int hb_ensure_state(hb_csr* h);
 void hb_free_state(hb_csr* h);

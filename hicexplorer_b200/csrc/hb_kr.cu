@@ -698,8 +698,9 @@ int hb_kr_scaled_upper(hb_csr* h, double diag_eps, const double* x, int64_t* nnz
     const int64_t nx = h->n_cols;
     cudaStream_t s = h->stream;
     int64_t *d_cnt = nullptr, *d_ptr = nullptr;
-    HB_CUDA(cudaMalloc(&d_cnt, sizeof(int64_t) * (size_t)(n + 1)));
-    HB_CUDA(cudaMalloc(&d_ptr, sizeof(int64_t) * (size_t)(n + 1)));
+    HbScratch scratch;   // freed on every return path
+    HB_CUDA(scratch.alloc(&d_cnt, sizeof(int64_t) * (size_t)(n + 1)));
+    HB_CUDA(scratch.alloc(&d_ptr, sizeof(int64_t) * (size_t)(n + 1)));
     if (n > 0) {
         hb_kr_upper_count_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_indptr, h->d_indices, n, h->row0, d_cnt);
         g_hb_launches.fetch_add(1);
@@ -713,9 +714,9 @@ int hb_kr_scaled_upper(hb_csr* h, double diag_eps, const double* x, int64_t* nnz
     if (e == cudaSuccess && indptr != nullptr && indices != nullptr && data != nullptr && n > 0) {
         double *d_x = nullptr, *d_val = nullptr;
         int32_t* d_idx = nullptr;
-        e = cudaMalloc(&d_x, sizeof(double) * (size_t)nx);
-        if (e == cudaSuccess) e = cudaMalloc(&d_val, sizeof(double) * (size_t)total);
-        if (e == cudaSuccess) e = cudaMalloc(&d_idx, sizeof(int32_t) * (size_t)total);
+        e = scratch.alloc(&d_x, sizeof(double) * (size_t)nx);
+        if (e == cudaSuccess) e = scratch.alloc(&d_val, sizeof(double) * (size_t)total);
+        if (e == cudaSuccess) e = scratch.alloc(&d_idx, sizeof(int32_t) * (size_t)total);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_x, x, sizeof(double) * (size_t)nx, cudaMemcpyHostToDevice, s);
         if (e == cudaSuccess) {
             hb_kr_upper_fill_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, n, h->row0, d_x,
@@ -724,14 +725,12 @@ int hb_kr_scaled_upper(hb_csr* h, double diag_eps, const double* x, int64_t* nnz
             e = cudaStreamSynchronize(s);
         }
         if (e == cudaSuccess) e = cudaMemcpy(indptr, d_ptr, sizeof(int64_t) * (size_t)(n + 1), cudaMemcpyDeviceToHost);
-        if (e == cudaSuccess) e = cudaMemcpy(indices, d_idx, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost);
-        if (e == cudaSuccess) e = cudaMemcpy(data, d_val, sizeof(double) * (size_t)total, cudaMemcpyDeviceToHost);
-        cudaFree(d_x);
-        cudaFree(d_val);
-        cudaFree(d_idx);
+        // large, caller-owned pageable buffers: multi-threaded staged copies
+        if (e == cudaSuccess && total > 0 && hb_copy_d2h(indices, d_idx, sizeof(int32_t) * (size_t)total, h->device) != HB_OK)
+            return HB_ERR_CUDA;
+        if (e == cudaSuccess && total > 0 && hb_copy_d2h(data, d_val, sizeof(double) * (size_t)total, h->device) != HB_OK)
+            return HB_ERR_CUDA;
     }
-    cudaFree(d_cnt);
-    cudaFree(d_ptr);
     if (e != cudaSuccess) return hb_cuda_fail(e, "KR scaled upper", __FILE__, __LINE__);
     return HB_OK;
 }
