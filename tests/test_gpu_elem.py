@@ -126,3 +126,38 @@ def test_hicSumMatrices_cli(tmp_path):
         badp = str(tmp_path / "bad.h5")
         bad.save(badp)
         main("--matrices {} {} --outFileName {}".format(one, badp, out).split())
+
+
+def test_edge_cases_empty_and_tiny_stores():
+    """empty matrix, 1 x 1 matrix, rows that vanish completely: the element-wise entry points must not trip"""
+    from hicexplorer_b200.hicTransform import obs_exp_transform
+    empty = sparse.csr_matrix((50, 50), dtype=np.float64)
+    with DeviceCSR.from_scipy(empty) as dev, DeviceCSR.from_scipy(empty) as other:
+        s, mn, mx = dev.value_stats(scrub=True)
+        assert s == 0.0 and np.isnan(mn) and np.isnan(mx)
+        dev.normalize("multiply", a=3.0)
+        dev.eliminate_zeros()
+        dev.add(other)
+        sums, counts = dev.distance_stats()
+        assert dev.nnz == 0 and sums.sum() == 0 and counts.sum() == 0
+    one = sparse.csr_matrix(np.array([[4.0]]))
+    with DeviceCSR.from_scipy(one) as dev, DeviceCSR.from_scipy(one) as other:
+        dev.add(other)
+        assert dev.download()[0, 0] == 8.0
+        dev.normalize("divide", a=2.0)
+        assert dev.download()[0, 0] == 4.0
+        assert dev.value_stats() == (4.0, 4.0, 4.0)
+    got = obs_exp_transform(one.astype(np.int32), "obs_exp", np.array([0, 1]))
+    assert got.nnz == 1 and got[0, 0] == 2          # expected = 4 / (n + 1 - 0) = 2 -> 4 / 2
+    m = random_hic(300, 0.1, 31)
+    neg = sparse.csr_matrix(-m)
+    with DeviceCSR.from_scipy(m) as dev, DeviceCSR.from_scipy(neg) as other:
+        dev.add(other)                               # everything cancels: scipy would return an empty matrix too
+        assert dev.nnz == 0 and (m + neg).nnz == 0
+        assert dev.download().shape == (300, 300)
+    with DeviceCSR.from_scipy(m) as dev:
+        dev.normalize("multiply", a=1.0, threshold=1e9)        # every value below the threshold
+        dev.eliminate_zeros()
+        assert dev.nnz == 0
+        bias, iters, devn = dev.ice(3, 1e-5)                   # and the store is still usable
+        assert np.all(bias == 0.0) or np.all(np.isnan(bias)) or bias.shape == (300,)
