@@ -179,9 +179,10 @@ def _correct_ice(ma, args, world=1, rank=0):
         if extra_fn is not None:
             log.error('--sequencedCountCutoff is not available in multi-GPU runs')
             sys.exit(1)
+        file_layout = not args.perchr or str(args.outFileName).endswith('.h5')
         res = ice_pipeline_sharded(ma.matrix, (args.filterThreshold[0], args.filterThreshold[1]), max_iter=args.iterNum,
                                    tolerance=args.tolerance, chr_offsets=ma.chromosome_offsets(), perchr=args.perchr,
-                                   skip_diagonal=args.skipDiagonal, want_matrix=True)
+                                   skip_diagonal=args.skipDiagonal, want_matrix=file_layout, file_layout=file_layout)
         if rank != 0:
             return
     else:

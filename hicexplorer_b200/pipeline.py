@@ -190,24 +190,44 @@ def _gather_rows_to_root(values, dist, rank, world, device):
     return None
 
 
+def _gather_upper_to_root(upper, dist, rank, world):
+    """Row blocks of the file-layout matrix (every rank holds all n rows, only its own non-empty) -> one CSR on rank 0.
+    Blocks are contiguous and ordered by rank, so concatenating indices / data in rank order is row-major order."""
+    row_counts = np.diff(upper.indptr).astype(np.float64)
+    idx = _gather_rows_to_root(upper.indices.astype(np.float64), dist, rank, world, None)
+    val = _gather_rows_to_root(upper.data, dist, rank, world, None)
+    import torch
+    counts = torch.from_numpy(row_counts).cuda()
+    dist.all_reduce(counts)                                  # x + 0: each row is owned by exactly one rank
+    if rank != 0:
+        return None
+    indptr = np.concatenate([[0], np.cumsum(counts.cpu().numpy().astype(np.int64))])
+    return sparse.csr_matrix((val, idx.astype(np.int32), indptr), shape=upper.shape)
+
+
 def ice_pipeline_sharded(matrix, filter_threshold, max_iter=500, tolerance=1e-5, chr_offsets=None, perchr=False,
-                         skip_diagonal=False, want_matrix=True):
+                         skip_diagonal=False, want_matrix=True, file_layout=False):
     """ice_pipeline on row blocks across the initialised torch.distributed group (NCCL).  The symmetry test is the
     exact-symmetry digest screen summed over the blocks (one tiny allreduce); a matrix that is not exactly symmetric is
-    rejected (the exact ratio would need the transposed entries of other blocks)."""
+    rejected (the exact ratio would need the transposed entries of other blocks).
+
+    ``file_layout``: every rank emits its rows of the corrected matrix already in file layout (upper triangle, zeros
+    eliminated, original frame: hb_ice_scaled_upper works on a row block) and rank 0 concatenates the blocks -> ``upper``;
+    otherwise rank 0 rebuilds the kept-frame pattern on the host -> ``matrix``."""
     import torch
 
     from .dist import attach_comm, nnz_balanced_partition
     dist, rank, world = _dist_env()
     if dist is None or world == 1:
         return ice_pipeline(matrix, filter_threshold, max_iter, tolerance, chr_offsets, perchr, skip_diagonal,
-                            device=torch.cuda.current_device(), want_matrix=want_matrix)
+                            device=torch.cuda.current_device(), want_matrix=want_matrix, file_layout=file_layout)
     device = torch.cuda.current_device()
     m = canonical_csr(matrix)
     n = m.shape[0]
     lo, hi = filter_threshold
     bounds = nnz_balanced_partition(m.indptr, world)
     a, b = int(bounds[rank]), int(bounds[rank + 1])
+    upper_local = None
     with DeviceCSR.from_scipy(m, device=device, row_range=(a, b)) as dev:
         keep_alive = attach_comm(dev, rank, world)
         rs_local, _ = dev.row_stats()
@@ -233,11 +253,19 @@ def ice_pipeline_sharded(matrix, filter_threshold, max_iter=500, tolerance=1e-5,
             raise ValueError("Please provide symmetric matrix!")
         dev.pack_values()
         bias, iters, deviation = dev.ice(max_iter, tolerance)  # one exchange per iteration
-        values = dev.ice_scaled_values() if want_matrix else None
+        values = None
+        if want_matrix and file_layout:
+            upper_local = dev.ice_scaled_upper(kept, n)
+        elif want_matrix:
+            values = dev.ice_scaled_values()
         del keep_alive
     out = dict(zero_bins=zero_bins, outliers_rel=outliers_rel, kept=kept, bias=bias, iterations=iters,
                deviation=deviation, n=n)
-    if want_matrix:
+    if want_matrix and file_layout:
+        upper = _gather_upper_to_root(upper_local, dist, rank, world)
+        if rank == 0:
+            out["upper"] = upper
+    elif want_matrix:
         all_values = _gather_rows_to_root(values, dist, rank, world, device)
         if rank == 0:
             pattern = sparse.csr_matrix(m[kept, :][:, kept])

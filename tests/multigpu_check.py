@@ -103,6 +103,15 @@ def main():
         cf = np.asarray(new.correction_factors).ravel()
         check("CLI under torchrun: factors match the single-GPU pipeline", np.array_equal(cf[ref["kept"]], ref["bias"]) and
               np.isnan(cf).sum() == n - len(ref["kept"]))
+        from hicexplorer_b200.pipeline import scatter_to_frame
+        want = sparse.triu(scatter_to_frame(ref["matrix"], ref["kept"], n), 0, format="csr")
+        want.eliminate_zeros()
+        want.sort_indices()
+        got_up = sparse.triu(new.matrix, 0, format="csr")
+        got_up.sort_indices()
+        check("CLI under torchrun: matrix written from per-rank file-layout blocks equals the single-GPU result",
+              np.array_equal(got_up.indptr, want.indptr) and np.array_equal(got_up.indices, want.indices) and
+              np.allclose(got_up.data, want.data, rtol=1e-12, atol=0))
     # --perchr KR: whole chromosomes dealt to the ranks (LPT), no communication; rank 0 assembles the file
     outk = os.path.join(tmp, "mg_kr_perchr.h5")
     cli(["correct", "-m", src, "-o", outk, "--correctionMethod", "KR", "--perchr"])
