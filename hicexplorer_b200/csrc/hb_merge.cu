@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(256)
 hb_merge_rows_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
                      const int64_t* __restrict__ indptr_b, const int32_t* __restrict__ idx_b, const double* __restrict__ val_b,
                      const int32_t* __restrict__ map, const int64_t* __restrict__ group_start,
-                     const int64_t* __restrict__ group_end, int64_t n_new,
+                     const int64_t* __restrict__ group_end, int64_t n_new, int max_run,
                      int64_t* __restrict__ cnt, const int64_t* __restrict__ out_ptr, int32_t* __restrict__ out_idx,
                      double* __restrict__ out_val) {
     __shared__ double acc_all[8][HB_MERGE_WINDOW];
@@ -131,9 +131,12 @@ hb_merge_rows_kernel(const int64_t* __restrict__ indptr, const int32_t* __restri
                         const bool live = mine && J >= 0 && (ADD || !(J == (int)I && c < row));
                         const int key = mine ? J : INT_MAX - 1;
                         double s = live ? v : 0.0;
-                        // segmented inclusive scan from the right: after it the first lane of a run holds the run's sum
+                        // segmented inclusive scan from the right: after it the first lane of a run holds the run's sum.
+                        // A run (equal merged ids inside one old row) is at most max_run entries long -- the size of the
+                        // largest group, 1 for A + B -- so log2 steps of that suffice.
 #pragma unroll
                         for (int o = 1; o < 32; o <<= 1) {
+                            if (o >= max_run) break;
                             const double t = __shfl_down_sync(0xffffffffu, s, o);
                             const int kt = __shfl_down_sync(0xffffffffu, key, o);
                             if (lane + o < 32 && kt == key) s += t;
@@ -181,6 +184,7 @@ extern "C" int hb_csr_merge_bins(hb_csr* h, const int32_t* bin_map, int64_t n_ne
     const int64_t n = h->n_cols;
     // the map must send runs of consecutive bins to 0, 1, 2, ... in order (dropped bins = -1), <= 32 bins per group
     std::vector<int64_t> g_start((size_t)(n_new > 0 ? n_new : 1), -1), g_end((size_t)(n_new > 0 ? n_new : 1), -1);
+    int max_run = 1;   // size of the largest group = longest run of equal merged ids inside an old row
     {
         int64_t next = 0;
         for (int64_t i = 0; i < n; ++i) {
@@ -196,6 +200,7 @@ extern "C" int hb_csr_merge_bins(hb_csr* h, const int32_t* bin_map, int64_t n_ne
             }
             g_end[J] = i + 1;
             HB_REQUIRE(g_end[J] - g_start[J] <= 32, "at most 32 bins per merged bin");
+            if (g_end[J] - g_start[J] > max_run) max_run = (int)(g_end[J] - g_start[J]);
         }
         HB_REQUIRE(next == n_new, "some merged bins are empty");
     }
@@ -229,7 +234,7 @@ extern "C" int hb_csr_merge_bins(hb_csr* h, const int32_t* bin_map, int64_t n_ne
     MG(cudaMemsetAsync(d_cnt, 0, sizeof(int64_t) * (ng + 1), s));
     if (n_new > 0) {
         hb_merge_rows_kernel<false, false><<<grid, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, nullptr, nullptr, nullptr,
-                                                                d_map, d_gs, d_ge, n_new, d_cnt, nullptr, nullptr, nullptr);
+                                                                d_map, d_gs, d_ge, n_new, max_run, d_cnt, nullptr, nullptr, nullptr);
         g_hb_launches.fetch_add(1);
     }
     hb_scan_kernel<int64_t><<<1, 1024, 0, s>>>(d_cnt, d_ptr, n_new);
@@ -241,7 +246,7 @@ extern "C" int hb_csr_merge_bins(hb_csr* h, const int32_t* bin_map, int64_t n_ne
     MG(cudaMalloc(&d_val, sizeof(double) * (size_t)(new_nnz > 0 ? new_nnz : 1) + 16));
     if (n_new > 0 && new_nnz > 0) {
         hb_merge_rows_kernel<true, false><<<grid, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, nullptr, nullptr, nullptr,
-                                                               d_map, d_gs, d_ge, n_new, nullptr, d_ptr, d_idx, d_val);
+                                                               d_map, d_gs, d_ge, n_new, max_run, nullptr, d_ptr, d_idx, d_val);
         g_hb_launches.fetch_add(1);
     }
     MG(cudaStreamSynchronize(s));
@@ -313,7 +318,7 @@ extern "C" int hb_csr_add(hb_csr* h, const hb_csr* other) {
     AD(cudaMemsetAsync(d_cnt, 0, sizeof(int64_t) * (nn + 1), s));
     if (n > 0) {
         hb_merge_rows_kernel<false, true><<<grid, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, other->d_indptr,
-                                                               other->d_indices, other->d_data, nullptr, nullptr, nullptr, n,
+                                                               other->d_indices, other->d_data, nullptr, nullptr, nullptr, n, 1,
                                                                d_cnt, nullptr, nullptr, nullptr);
         g_hb_launches.fetch_add(1);
     }
@@ -326,7 +331,7 @@ extern "C" int hb_csr_add(hb_csr* h, const hb_csr* other) {
     AD(cudaMalloc(&d_val, sizeof(double) * (size_t)(new_nnz > 0 ? new_nnz : 1) + 16));
     if (n > 0 && new_nnz > 0) {
         hb_merge_rows_kernel<true, true><<<grid, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, other->d_indptr,
-                                                              other->d_indices, other->d_data, nullptr, nullptr, nullptr, n,
+                                                              other->d_indices, other->d_data, nullptr, nullptr, nullptr, n, 1,
                                                               nullptr, d_ptr, d_idx, d_val);
         g_hb_launches.fetch_add(1);
     }
