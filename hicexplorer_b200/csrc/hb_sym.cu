@@ -114,6 +114,43 @@ __global__ void hb_sym_sort_kernel(const int64_t* __restrict__ out_ptr, const un
     }
 }
 
+// rows whose lower part does not fit the shared-memory classes (more than 16384 entries: the dense rows of a coarse
+// genome-wide matrix): the same network on a global scratch slice (L2 resident), one CTA of 1024 threads per row
+__global__ void __launch_bounds__(1024)
+hb_sym_sort_big_kernel(const int64_t* __restrict__ out_ptr, const unsigned int* __restrict__ low_cnt,
+                       const int64_t* __restrict__ big_rows, const int64_t* __restrict__ big_off, unsigned long long* __restrict__ keys,
+                       double* __restrict__ vals, int32_t* __restrict__ out_idx, double* __restrict__ out_val) {
+    const int64_t row = big_rows[blockIdx.x];
+    const int64_t L = (int64_t)low_cnt[row];
+    const int64_t P = big_off[blockIdx.x + 1] - big_off[blockIdx.x];
+    unsigned long long* sk = keys + big_off[blockIdx.x];
+    double* sv = vals + big_off[blockIdx.x];
+    const int64_t base = out_ptr[row];
+    for (int64_t i = threadIdx.x; i < P; i += blockDim.x) {
+        sk[i] = i < L ? (((unsigned long long)(unsigned int)out_idx[base + i] << 32) | (unsigned long long)i) : ~0ull;
+        if (i < L) sv[i] = out_val[base + i];
+    }
+    __syncthreads();
+    for (int64_t k = 2; k <= P; k <<= 1) {
+        for (int64_t j = k >> 1; j > 0; j >>= 1) {
+            for (int64_t i = threadIdx.x; i < (P >> 1); i += blockDim.x) {
+                const int64_t lo = ((i / j) * j << 1) + (i % j);
+                const int64_t hi = lo + j;
+                const unsigned long long a = sk[lo], b = sk[hi];
+                if ((a > b) == ((lo & k) == 0)) {
+                    sk[lo] = b;
+                    sk[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int64_t i = threadIdx.x; i < L; i += blockDim.x) {
+        out_idx[base + i] = (int32_t)(sk[i] >> 32);
+        out_val[base + i] = sv[sk[i] & 0xffffffffull];
+    }
+}
+
 // ---- corrected matrix in file layout -------------------------------------------------------------------------
 template <bool FILL>
 __global__ void __launch_bounds__(256)
@@ -185,7 +222,9 @@ int hb_csr_create_upper(hb_csr** out, int64_t n, int64_t nnz_upper, const int64_
     hb_csr* h = *out;
     cudaStream_t s = h->stream;
     unsigned int *d_low = nullptr, *d_cursor = nullptr, *d_flags = nullptr;
-    int64_t *d_total = nullptr, *d_ptr = nullptr;
+    int64_t *d_total = nullptr, *d_ptr = nullptr, *d_big_rows = nullptr, *d_big_off = nullptr;
+    unsigned long long* d_big_keys = nullptr;
+    double* d_big_vals = nullptr;
     int32_t* d_idx = nullptr;
     double* d_val = nullptr;
     int64_t full_nnz = 0;
@@ -225,12 +264,6 @@ int hb_csr_create_upper(hb_csr** out, int64_t n, int64_t nnz_upper, const int64_
         rc = HB_ERR_INVALID_ARG;
         goto fail;
     }
-    if (flags[1] > 16384u) {
-        hb_set_error("hb_csr_create_upper: a column holds %u entries above the diagonal (limit 16384); "
-                     "symmetrise on the host and use hb_csr_create", flags[1]);
-        rc = HB_ERR_INVALID_ARG;
-        goto fail;
-    }
     SY(cudaMalloc(&d_idx, sizeof(int32_t) * (size_t)(full_nnz > 0 ? full_nnz : 1) + 16));
     SY(cudaMalloc(&d_val, sizeof(double) * (size_t)(full_nnz > 0 ? full_nnz : 1) + 16));
     if (n > 0 && full_nnz > 0) {
@@ -246,6 +279,30 @@ int hb_csr_create_upper(hb_csr** out, int64_t n, int64_t nnz_upper, const int64_
             hb_sym_sort_kernel<<<(unsigned)n, threads, smem, s>>>(d_ptr, d_low, n, P, d_idx, d_val);
             g_hb_launches.fetch_add(1);
         }
+        if (flags[1] > 16384u) {
+            // the few rows beyond the shared-memory classes: list them on the host, sort them on a global scratch
+            std::vector<unsigned int> low((size_t)n);
+            SY(cudaMemcpyAsync(low.data(), d_low, sizeof(unsigned int) * (size_t)n, cudaMemcpyDeviceToHost, s));
+            SY(cudaStreamSynchronize(s));
+            std::vector<int64_t> rows, off(1, 0);
+            for (int64_t i = 0; i < n; ++i) {
+                if (low[(size_t)i] <= 16384u) continue;
+                int64_t P = 32768;
+                while (P < (int64_t)low[(size_t)i]) P <<= 1;
+                rows.push_back(i);
+                off.push_back(off.back() + P);
+            }
+            SY(cudaMalloc(&d_big_rows, sizeof(int64_t) * rows.size()));
+            SY(cudaMalloc(&d_big_off, sizeof(int64_t) * off.size()));
+            SY(cudaMalloc(&d_big_keys, sizeof(unsigned long long) * (size_t)off.back()));
+            SY(cudaMalloc(&d_big_vals, sizeof(double) * (size_t)off.back()));
+            SY(cudaMemcpyAsync(d_big_rows, rows.data(), sizeof(int64_t) * rows.size(), cudaMemcpyHostToDevice, s));
+            SY(cudaMemcpyAsync(d_big_off, off.data(), sizeof(int64_t) * off.size(), cudaMemcpyHostToDevice, s));
+            hb_sym_sort_big_kernel<<<(unsigned)rows.size(), 1024, 0, s>>>(d_ptr, d_low, d_big_rows, d_big_off, d_big_keys,
+                                                                          d_big_vals, d_idx, d_val);
+            g_hb_launches.fetch_add(1);
+            SY(cudaStreamSynchronize(s));   // rows / off are host vectors of this scope
+        }
     }
     SY(cudaStreamSynchronize(s));
     SY(cudaGetLastError());
@@ -254,6 +311,10 @@ int hb_csr_create_upper(hb_csr** out, int64_t n, int64_t nnz_upper, const int64_
     cudaFree(d_cursor);
     cudaFree(d_flags);
     cudaFree(d_total);
+    cudaFree(d_big_rows);
+    cudaFree(d_big_off);
+    cudaFree(d_big_keys);
+    cudaFree(d_big_vals);
     cudaFree(h->d_indptr);
     cudaFree(h->d_indices);
     cudaFree(h->d_data);
@@ -268,6 +329,10 @@ fail:
     cudaFree(d_cursor);
     cudaFree(d_flags);
     cudaFree(d_total);
+    cudaFree(d_big_rows);
+    cudaFree(d_big_off);
+    cudaFree(d_big_keys);
+    cudaFree(d_big_vals);
     cudaFree(d_ptr);
     cudaFree(d_idx);
     cudaFree(d_val);

@@ -90,7 +90,7 @@ HB_API int hb_csr_create(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t r
                   int device);
 /* Same store from the UPPER triangle only (what .h5 / .cool files hold; hicmatrix symmetrises on load,
  * call site hicCorrectMatrix.py:603-609): half the bytes cross PCIe, the mirror image is built in HBM with ascending
- * columns.  Entries below the diagonal are an error; a column may hold at most 16384 entries above the diagonal. */
+ * columns (deterministic layout, identical to a host-side fill).  Entries below the diagonal are an error. */
 HB_API int hb_csr_create_upper(hb_csr** out, int64_t n, int64_t nnz_upper, const int64_t* indptr, const int32_t* indices,
                         const double* data, int device);
 /* wrap device arrays already in HBM (not copied, not owned). indptr must be block-local (indptr[0]==0). */

@@ -96,3 +96,25 @@ def test_malformed_blocks_are_rejected_at_upload():
     assert rc == _lib.HB_ERR_INVALID_ARG and "ascending" in msg
     rc, msg = create([0, 3, 2, 4], [0, 1, 2, 0], [1, 2, 3, 4], 3)
     assert rc == _lib.HB_ERR_INVALID_ARG and "monotone" in msg
+
+
+def test_from_upper_with_rows_beyond_the_shared_memory_classes():
+    """dense columns (coarse genome-wide matrices): lower parts of more than 16384 entries take the global-scratch sort"""
+    n = 40000
+    rng = np.random.default_rng(3)
+    dense_cols = np.array([n - 1, n - 7, 20000])
+    rows = np.concatenate([np.arange(c + 1) for c in dense_cols])
+    cols = np.concatenate([np.full(c + 1, c) for c in dense_cols])
+    extra = rng.integers(0, n, size=(2, 60000))
+    r = np.concatenate([rows, np.minimum(extra[0], extra[1])])
+    c = np.concatenate([cols, np.maximum(extra[0], extra[1])])
+    v = rng.integers(1, 100, size=len(r)).astype(np.float64)
+    up = sparse.coo_matrix((v, (r, c)), shape=(n, n)).tocsr()
+    up.sum_duplicates()
+    full = sparse.csr_matrix(up + sparse.triu(up, 1).T)
+    full.sort_indices()
+    assert np.diff(sparse.tril(full, -1).tocsr().indptr).max() > 32768        # two size classes of the big-row path
+    with DeviceCSR.from_upper(up) as dev:
+        got = dev.download()
+    assert np.array_equal(got.indptr, full.indptr) and np.array_equal(got.indices, full.indices)
+    np.testing.assert_array_equal(got.data, full.data)
