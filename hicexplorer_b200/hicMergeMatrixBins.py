@@ -3,7 +3,7 @@
 
 This is the step right before correction in the reference's documented workflow.
 ``--runningWindow`` (a smoothing variant that keeps the resolution) is not implemented and exits with an explanation;
-``--numBins`` is limited to 32 on the device.
+``--numBins`` up to 1024 (more than 32 bins per group are merged in two exact device steps).
 """
 import argparse
 import logging
@@ -77,8 +77,8 @@ def merge_groups(cut_intervals, num_bins):
 
 def merge_bins(hic, num_bins, device=0):
     """Merge ``num_bins`` consecutive bins of the hiCMatrix ``hic`` in place and return it."""
-    if num_bins > 32:
-        raise ValueError("--numBins is limited to 32 on the device")
+    if num_bins > 1024:
+        raise ValueError("--numBins is limited to 1024")
     hic = remove_nans_if_needed(hic)
     bin_map, new_bins = merge_groups(hic.cut_intervals, num_bins)
     dtype = hic.matrix.dtype

@@ -232,6 +232,31 @@ class DeviceCSR(object):
         m = np.ascontiguousarray(bin_map, dtype=np.int32)
         if len(m) != self.n:
             raise ValueError("bin map length must equal the bin count")
+        kept = m[m >= 0]
+        sizes = np.bincount(kept, minlength=int(n_new)) if len(kept) else np.zeros(0, dtype=np.int64)
+        if len(sizes) and sizes.max() > 32:
+            # The kernel merges at most 32 bins per group (one lane per old row).  Larger groups are merged in two exact
+            # steps: first sub-groups of <= 32 consecutive bins, then the sub-groups of every target group (sums of
+            # sums; the upper-triangle rule of the diagonal cells composes, see csrc/hb_merge.cu).
+            if sizes.max() > 1024:
+                raise ValueError("at most 1024 bins per merged bin")
+            first = np.full(len(m), -1, dtype=np.int32)
+            second = []
+            pos = np.flatnonzero(m >= 0)
+            starts = np.flatnonzero(np.r_[True, m[pos][1:] != m[pos][:-1]])
+            ends = np.r_[starts[1:], len(pos)]
+            nxt = 0
+            for a, b in zip(starts, ends):
+                ids = pos[a:b]
+                if len(ids) and (ids[-1] - ids[0] + 1 != len(ids)):
+                    raise ValueError("the bins of a group must be consecutive")
+                sub = np.arange(len(ids)) // 32
+                first[ids] = nxt + sub
+                n_sub = int(sub[-1]) + 1
+                second.extend([int(m[ids[0]])] * n_sub)
+                nxt += n_sub
+            check(lib().hb_csr_merge_bins(self._h, ptr(first), int(nxt)))
+            m = np.ascontiguousarray(second, dtype=np.int32)
         check(lib().hb_csr_merge_bins(self._h, ptr(m), int(n_new)))
         self._segments = 1
 

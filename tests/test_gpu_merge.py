@@ -43,7 +43,7 @@ def test_merge_matrix_bins_matches_reference_golden(tmp_path):
     np.testing.assert_array_equal(f["nan_bins"].read(), z["out_nan_bins"])
 
 
-@pytest.mark.parametrize("n,k,seed", [(500, 2, 0), (1203, 7, 1), (64, 32, 2), (777, 3, 3)])
+@pytest.mark.parametrize("n,k,seed", [(500, 2, 0), (1203, 7, 1), (64, 32, 2), (777, 3, 3), (2000, 100, 4), (1500, 33, 5)])
 def test_merge_random_matrices_match_oracle(n, k, seed):
     from hicexplorer_b200.store import DeviceCSR
     m = random_hic(n, 0.1, seed, empty_frac=0.02)
