@@ -25,7 +25,7 @@
 #define HB_SPMV_UNROLL 16       // independent entries per lane per step of the row dot product
 #endif
 #define HB_TILE_ROWS 1024       // fixed reduction tile (rows) -> rank-count independent sums
-#define HB_MAX_SEG 4096
+#define HB_MAX_SEG 65536        // chromosomes / contigs treated as independent blocks (draft assemblies have thousands)
 #define HB_MAX_PEERS 8          // peer-store exchange: ranks of one NVLink domain
 
 extern std::atomic<uint64_t> g_hb_launches;

@@ -215,3 +215,26 @@ def test_verbose_mode_reports_like_the_reference(caplog):
     with caplog.at_level(logging.INFO, logger="hicexplorer_b200.iterativeCorrection"):
         iterativeCorrection(m, M=3, tolerance=1e-12, verbose=True)
     assert "iterations used" not in caplog.text
+
+
+def test_thousands_of_segments():
+    from hicexplorer_b200.store import DeviceCSR
+    """draft assemblies have thousands of contigs: --perchr with more than 4096 independent blocks"""
+    from oracle import ice_oracle
+    rng = np.random.default_rng(12)
+    sizes = rng.integers(3, 8, size=5000)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    blocks = []
+    for s in sizes:
+        b = rng.integers(1, 50, size=(s, s)).astype(np.float64)
+        blocks.append(sparse.csr_matrix(b + b.T))
+    m = sparse.block_diag(blocks, format="csr")
+    m.sort_indices()
+    with DeviceCSR.from_scipy(m) as dev:
+        dev.set_segments(offs)
+        bias, iters, devn = dev.ice(200, 1e-5)
+    assert len(iters) == 5000
+    for k in rng.choice(5000, size=40, replace=False):
+        ref = ice_oracle.ice(blocks[k].copy(), max_iter=200, tolerance=1e-5)
+        np.testing.assert_allclose(bias[offs[k]:offs[k + 1]], ref["bias"], rtol=1e-9)
+        assert abs(int(iters[k]) - ref["iterations"]) <= 1
