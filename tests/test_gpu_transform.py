@@ -34,7 +34,8 @@ def test_obs_exp_float_matrices_match_oracle(method, pc, lig, dtype):
     ref.sort_indices()
     assert got.dtype == ref.dtype
     assert np.array_equal(got.indptr, ref.indptr) and np.array_equal(got.indices, ref.indices)
-    # distance sums are accumulated with fp64 atomics (order not fixed): rounding-level agreement for float input
+    # distance sums: fixed-point integer accumulation on the device (order-free, correctly rounded to ~2^-76 of the
+    # largest value) against numpy's floating-point sums: rounding-level agreement for float input
     # (one float32 ulp where the reference rounds the quotient to float32)
     rounds_to_f32 = dtype == np.float32 or method == "obs_exp_non_zero"
     np.testing.assert_allclose(got.data, ref.data, rtol=1e-6 if rounds_to_f32 else 1e-12)
@@ -61,3 +62,33 @@ def test_hicTransform_cli_obs_exp(tmp_path):
         np.testing.assert_array_almost_equal(new.data, t["file_" + key + "_data"], decimal=0)   # the reference's own check
     with pytest.raises(SystemExit):
         main("--matrix {} --outFileName {} --method pearson".format(src, str(tmp_path / "p.h5")).split())
+
+
+def test_distance_sums_are_order_free_and_accurate():
+    """integer-limb accumulation: bit-identical between runs, exact for counts, and at least as close to the exact sum
+    as numpy's pairwise floating-point sum for float data (also negative values, NaN poisons its distance only)"""
+    from fractions import Fraction
+    from hicexplorer_b200.store import DeviceCSR
+    m = random_hic(1200, 0.2, 5, integer=False)
+    m.data[::3] *= -1e-7
+    m.data[1::5] *= 1e6
+    with DeviceCSR.from_scipy(m) as dev:
+        s1, c1 = dev.distance_stats()
+        s2, c2 = dev.distance_stats()
+    assert np.array_equal(s1, s2) and np.array_equal(c1, c2)
+    coo = m.tocoo()
+    d = np.abs(coo.row - coo.col)
+    assert np.array_equal(c1, np.bincount(d, minlength=1200))
+    for dist in (0, 1, 7, 300):
+        exact = sum(Fraction(float(v)) for v in coo.data[d == dist])
+        assert abs(Fraction(float(s1[dist])) - exact) <= abs(exact) * Fraction(1, 2 ** 50) + Fraction(1, 2 ** 60)
+    ints = random_hic(800, 0.2, 6)
+    with DeviceCSR.from_scipy(ints) as dev:
+        s, _ = dev.distance_stats()
+    ci = ints.tocoo()
+    np.testing.assert_array_equal(s, np.bincount(np.abs(ci.row - ci.col), weights=ci.data, minlength=800))
+    bad = ints.copy()
+    bad.data[10] = np.nan
+    with DeviceCSR.from_scipy(bad) as dev:
+        sb, _ = dev.distance_stats()
+    assert np.isnan(sb).sum() == 1
