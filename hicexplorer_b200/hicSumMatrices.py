@@ -1,6 +1,12 @@
-"""``hicSumMatrices`` on a B200: same flags, checks and output as the reference tool
-(hicexplorer/hicSumMatrices.py:9-74); the sparse additions run on the GPU (``hb_csr_add``: union of the two sorted
-rows, values added, exact zeros dropped like scipy's ``csr + csr``).  SURVEY.md 8f, rank 3."""
+"""``hicSumMatrices`` on a B200.
+
+Drop-in for the reference tool of the same name (hicexplorer/hicSumMatrices.py:9-74): identical flags
+(``--matrices/-m``, ``--outFileName/-o``), identical refusal of inputs whose chromosome layout differs, identical
+output (the sum with the union of the inputs' NaN bins masked).  The additions themselves run on the GPU through
+``hb_csr_add`` -- each row of the running total is merged with the matching row of the next matrix, equal columns
+are added, and cells that cancel to exactly zero disappear, which is what scipy's ``csr + csr`` does in the reference
+(:59).  SURVEY.md 8f, rank 3.
+"""
 import argparse
 import logging
 import sys
@@ -15,51 +21,55 @@ log = logging.getLogger(__name__)
 
 
 def parse_arguments(args=None):
-    parser = argparse.ArgumentParser(
-        add_help=False, description='Adds Hi-C matrices of the same size. Format has to be hdf5 or npz')
-    req = parser.add_argument_group('Required arguments')
-    req.add_argument('--matrices', '-m', help='Space-delimited names of the matrices to add. The matrices must have the '
-                     'same shape/size.', metavar='matrix.h5', nargs='+', required=True)
-    req.add_argument('--outFileName', '-o', help='File name to save the resulting matrix. The output is also a .h5 '
-                     'file.', required=True)
-    opt = parser.add_argument_group('Optional arguments')
-    opt.add_argument('--help', '-h', action='help', help='show this help message and exit')
-    opt.add_argument('--version', action='version', version='%(prog)s {}'.format(__version__))
-    opt.add_argument('--device', help='CUDA device index.', type=int, default=0)
-    return parser
+    p = argparse.ArgumentParser(add_help=False, description="Element-wise sum of Hi-C matrices that share one bin layout.")
+    need = p.add_argument_group("Required arguments")
+    need.add_argument("--matrices", "-m", nargs="+", required=True, metavar="matrix.h5",
+                      help="Two or more matrices (.h5 or .cool) with the same bins, separated by spaces.")
+    need.add_argument("--outFileName", "-o", required=True, help="Where to write the summed matrix.")
+    extra = p.add_argument_group("Optional arguments")
+    extra.add_argument("--help", "-h", action="help", help="Print this text and leave.")
+    extra.add_argument("--version", action="version", version="%(prog)s {}".format(__version__))
+    extra.add_argument("--device", type=int, default=0, help="CUDA device to run on.")
+    return p
 
 
-def main(args=None):
-    args = parse_arguments().parse_args(args)
-    hic = hm.hiCMatrix(args.matrices[0])
-    nan_bins = set(int(b) for b in hic.nan_bins)
-    dtype = hic.matrix.dtype
-    with DeviceCSR.from_scipy(hic.matrix, device=args.device) as total:
-        for path in args.matrices[1:]:
-            other = hm.hiCMatrix(path)
-            if hic.chrBinBoundaries != other.chrBinBoundaries:
-                log.error("The two matrices have different chromosome order. Use the tool `hicConvertFormat` to change "
-                          "the order.\n{}: {}\n{}: {}".format(args.matrices[0], list(hic.chrBinBoundaries), path,
-                                                              list(other.chrBinBoundaries)))
-                sys.exit(1)
+def _same_layout_or_exit(first, first_name, other, other_name):
+    if first.chrBinBoundaries == other.chrBinBoundaries:
+        return
+    log.error("The two matrices have different chromosome order. Use the tool `hicConvertFormat` to change the order.\n"
+              "{}: {}\n{}: {}".format(first_name, list(first.chrBinBoundaries), other_name, list(other.chrBinBoundaries)))
+    sys.exit(1)
+
+
+def sum_matrices(paths, device=0):
+    """Load ``paths`` one after the other and accumulate them in one device store.  Returns the first matrix object
+    with the total installed and the union of all NaN bins masked."""
+    base = hm.hiCMatrix(paths[0])
+    masked = {int(b) for b in base.nan_bins}
+    value_type = base.matrix.dtype
+    with DeviceCSR.from_scipy(base.matrix, device=device) as running:
+        for path in paths[1:]:
+            nxt = hm.hiCMatrix(path)
+            _same_layout_or_exit(base, paths[0], nxt, path)
             try:
-                if other.matrix.shape != hic.matrix.shape:
-                    raise ValueError("inconsistent shapes")
-                with DeviceCSR.from_scipy(other.matrix, device=args.device) as addend:
-                    total.add(addend)
-                dtype = np.result_type(dtype, other.matrix.dtype)
-                if len(other.nan_bins):
-                    nan_bins = nan_bins.union(int(b) for b in other.nan_bins)
+                if nxt.matrix.shape != base.matrix.shape:
+                    raise ValueError("shape %r differs from %r" % (nxt.matrix.shape, base.matrix.shape))
+                with DeviceCSR.from_scipy(nxt.matrix, device=device) as term:
+                    running.add(term)
             except Exception:
                 log.exception("\nMatrix {} seems to be corrupted or of different shape".format(path))
                 sys.exit(1)
-        summed = total.download()
-    if dtype.kind in "iu":
-        summed = summed.astype(dtype)
-    # save only the upper triangle of the symmetric matrix
-    hic.setMatrixValues(summed)
-    hic.maskBins(sorted(nan_bins))
-    hic.save(args.outFileName)
+            value_type = np.result_type(value_type, nxt.matrix.dtype)
+            masked.update(int(b) for b in nxt.nan_bins)
+        total = running.download()
+    base.setMatrixValues(total.astype(value_type) if value_type.kind in "iu" else total)
+    base.maskBins(sorted(masked))
+    return base
+
+
+def main(args=None):
+    opts = parse_arguments().parse_args(args)
+    sum_matrices(opts.matrices, device=opts.device).save(opts.outFileName)
 
 
 if __name__ == "__main__":
