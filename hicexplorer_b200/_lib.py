@@ -67,6 +67,8 @@ SIGNATURES = {
     "hb_launch_count": (c_u64, []),
     "hb_csr_create": (c_int, [P(vp), c_i64, c_i64, c_i64, c_i64, vp, vp, c_int, vp, c_int]),
     "hb_csr_create_upper": (c_int, [P(vp), c_i64, c_i64, vp, vp, vp, c_int]),
+    "hb_csr_create_typed": (c_int, [P(vp), c_i64, c_i64, c_i64, c_i64, vp, vp, c_int, vp, c_int, c_int]),
+    "hb_csr_create_upper_typed": (c_int, [P(vp), c_i64, c_i64, vp, vp, vp, c_int, c_int]),
     "hb_dev_csr_wrap": (c_int, [P(vp), c_i64, c_i64, c_i64, c_i64, vp, vp, vp, c_int]),
     "hb_csr_destroy": (c_int, [vp]),
     "hb_csr_shape": (c_int, [vp, P(c_i64), P(c_i64), P(c_i64), P(c_i64)]),

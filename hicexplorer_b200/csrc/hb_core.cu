@@ -76,6 +76,15 @@ __global__ void hb_narrow_indices_kernel(const int64_t* __restrict__ in, int32_t
     for (; i < n; i += stride) out[i] = (in[i] >= 0 && in[i] < 2147483647LL) ? (int32_t)in[i] : -1;
 }
 
+// values that arrive in the file's own type (counts are int32 / int64 in .cool files, float32 after hicNormalize) are
+// widened to the fp64 store on the device: no fp64 copy on the host, fewer bytes over PCIe
+template <typename T>
+__global__ void hb_widen_values_kernel(const T* __restrict__ in, double* __restrict__ out, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = (double)in[i];
+}
+
 // The kernels of the path trust the store: an out-of-range column id would be an out-of-bounds gather.  One streaming
 // pass over the column ids (4 B per entry) checks what the contract in hicbalance.h states:
 // flags bit 0: indptr decreases; bit 1: a column id outside [0, n_cols); bit 2: columns not strictly ascending in a row
@@ -135,6 +144,13 @@ extern "C" {
 
 int hb_csr_create(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t row0, int64_t nnz, const int64_t* indptr,
                   const void* indices, int indices_i64, const double* data, int device) {
+    return hb_csr_create_typed(out, n_rows, n_cols, row0, nnz, indptr, indices, indices_i64, data, HB_VALUES_F64, device);
+}
+
+int hb_csr_create_typed(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t row0, int64_t nnz, const int64_t* indptr,
+                        const void* indices, int indices_i64, const void* data_any, int value_kind, int device) {
+    HB_REQUIRE(value_kind >= HB_VALUES_F64 && value_kind <= HB_VALUES_I64, "unknown value type");
+    const double* data = static_cast<const double*>(data_any);
     HB_REQUIRE(indptr != nullptr, "null indptr");
     HB_REQUIRE(nnz == 0 || (indices != nullptr && data != nullptr), "null indices/data");
     HB_REQUIRE(indptr[n_rows] - indptr[0] == nnz, "indptr does not span nnz entries");
@@ -173,10 +189,41 @@ int hb_csr_create(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t row0, in
     }
     HB_CREATE_CUDA(cudaStreamSynchronize(s));
     if (nnz > 0) {
-        if (hb_copy_h2d(h->d_data + phase, data + indptr[0], sizeof(double) * (size_t)nnz, device) != HB_OK) {
-            hb_csr_destroy(h);
-            *out = nullptr;
-            return HB_ERR_CUDA;
+        if (value_kind == HB_VALUES_F64) {
+            if (hb_copy_h2d(h->d_data + phase, data + indptr[0], sizeof(double) * (size_t)nnz, device) != HB_OK) {
+                hb_csr_destroy(h);
+                *out = nullptr;
+                return HB_ERR_CUDA;
+            }
+        } else {
+            const size_t elt = value_kind == HB_VALUES_I64 ? 8 : 4;
+            const unsigned char* src = static_cast<const unsigned char*>(data_any) + elt * (size_t)indptr[0];
+            const int64_t chunk = (int64_t)1 << 26;
+            void* d_tmp = nullptr;
+            HB_CREATE_CUDA(cudaMalloc(&d_tmp, elt * (size_t)(nnz < chunk ? nnz : chunk)));
+            for (int64_t o = 0; o < nnz; o += chunk) {
+                const int64_t m = nnz - o < chunk ? nnz - o : chunk;
+                if (hb_copy_h2d(d_tmp, src + elt * (size_t)o, elt * (size_t)m, device) != HB_OK) {
+                    cudaFree(d_tmp);
+                    hb_csr_destroy(h);
+                    *out = nullptr;
+                    return HB_ERR_CUDA;
+                }
+                double* dst = h->d_data + phase + o;
+                if (value_kind == HB_VALUES_F32)
+                    hb_widen_values_kernel<float><<<HB_NUM_SMS * 8, 256, 0, s>>>((const float*)d_tmp, dst, m);
+                else if (value_kind == HB_VALUES_I32)
+                    hb_widen_values_kernel<int32_t><<<HB_NUM_SMS * 8, 256, 0, s>>>((const int32_t*)d_tmp, dst, m);
+                else
+                    hb_widen_values_kernel<long long><<<HB_NUM_SMS * 8, 256, 0, s>>>((const long long*)d_tmp, dst, m);
+                g_hb_launches.fetch_add(1);
+                cudaError_t ce = cudaStreamSynchronize(s);   // the staging buffer is reused by the next chunk
+                if (ce != cudaSuccess) {
+                    cudaFree(d_tmp);
+                    HB_CREATE_CUDA(ce);
+                }
+            }
+            cudaFree(d_tmp);
         }
         if (indices_i64) {
             // krbalancing's constructor takes int64 indices (hicCorrectMatrix.py:744-747): narrow on the device

@@ -215,9 +215,14 @@ extern "C" {
 
 int hb_csr_create_upper(hb_csr** out, int64_t n, int64_t nnz_upper, const int64_t* indptr, const int32_t* indices,
                         const double* data, int device) {
+    return hb_csr_create_upper_typed(out, n, nnz_upper, indptr, indices, data, HB_VALUES_F64, device);
+}
+
+int hb_csr_create_upper_typed(hb_csr** out, int64_t n, int64_t nnz_upper, const int64_t* indptr, const int32_t* indices,
+                              const void* data, int value_kind, int device) {
     HB_REQUIRE(out != nullptr && indptr != nullptr, "bad arguments");
     // upload the triangle with the ordinary constructor, then replace the store by its symmetric completion
-    int rc = hb_csr_create(out, n, n, 0, nnz_upper, indptr, indices, 0, data, device);
+    int rc = hb_csr_create_typed(out, n, n, 0, nnz_upper, indptr, indices, 0, data, value_kind, device);
     if (rc != HB_OK) return rc;
     hb_csr* h = *out;
     cudaStream_t s = h->stream;

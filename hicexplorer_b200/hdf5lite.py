@@ -24,6 +24,8 @@ can open the result.
 
 This is host-side I/O, not part of the device hot path.
 """
+import mmap
+import os
 import struct
 import zlib
 
@@ -210,7 +212,9 @@ class _Dataset(object):
         """dict name -> value for enum datasets (cooler ``bins/chrom``)."""
         return self._enum
 
-    def read(self):
+    def read(self, copy=True):
+        """``copy=False``: a contiguous, unfiltered dataset comes back as a read-only view of the mapped file (no copy of
+        a multi-gigabyte payload); anything else is decoded into a fresh array as usual."""
         buf = self._f._buf
         lay = self._layout
         ver = lay[0]
@@ -227,7 +231,8 @@ class _Dataset(object):
             addr, size = struct.unpack_from("<QQ", lay, 2)
             if addr == _UNDEF:
                 return np.zeros(self.shape, dtype=self.dtype)
-            return np.frombuffer(buf, dtype=self.dtype, count=count, offset=addr).reshape(self.shape).copy()
+            view = np.frombuffer(buf, dtype=self.dtype, count=count, offset=addr).reshape(self.shape)
+            return view.copy() if copy else view
         if cls != 2:
             raise NotImplementedError("layout class %d" % cls)
         ndims = lay[2]
@@ -307,8 +312,13 @@ class File(_Group):
     """Read-only view of an HDF5 file: ``File(path)['matrix/data'].read()``."""
 
     def __init__(self, path):
+        # map the file instead of reading it: only the pages that are parsed or copied out are touched (a genome-wide
+        # matrix file is gigabytes; reading it whole doubled the peak memory and the load time)
         with open(path, "rb") as fh:
-            self._buf = fh.read()
+            try:
+                self._buf = mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ)
+            except (ValueError, OSError):
+                self._buf = fh.read()
         buf = self._buf
         if buf[:8] != _SIG:
             raise ValueError("%s is not an HDF5 file" % path)
@@ -377,7 +387,7 @@ class File(_Group):
                     name_off, hdr = struct.unpack_from("<QQ", buf, pos)
                     pos += 40
                     s = data_seg + name_off
-                    e = buf.index(b"\x00", s)
+                    e = buf.find(b"\x00", s)
                     links[buf[s:e].decode("utf-8")] = hdr
             else:
                 raise ValueError("bad group node")
@@ -627,13 +637,23 @@ class Writer(object):
         node["attrs"].update(attrs or {})
 
     def save(self, path):
-        out = bytearray(b"\x00" * 96)  # superblock placeholder
+        """Stream the file out in one pass (every address is known once its block has been written; only the superblock
+        at offset 0 is patched at the end).  Dataset payloads go from the numpy buffer straight to the file."""
+        # written beside the target and renamed at the end: an input file that is still memory-mapped (File.read with
+        # copy=False) may be the very path that is being overwritten
+        tmp_path = "%s.tmp%d" % (path, os.getpid())
+        fh = open(tmp_path, "wb")
+        fh.write(b"\x00" * 96)  # superblock placeholder
+        pos = [96]
 
         def alloc(blob):
-            while len(out) % 8:
-                out.append(0)
-            addr = len(out)
-            out.extend(blob)
+            pad = (-pos[0]) % 8
+            if pad:
+                fh.write(b"\x00" * pad)
+                pos[0] += pad
+            addr = pos[0]
+            fh.write(blob)
+            pos[0] += blob.nbytes if isinstance(blob, memoryview) else len(blob)
             return addr
 
         def write_object_header(msgs):
@@ -643,15 +663,17 @@ class Writer(object):
 
         def write_dataset(node):
             arr = node["data"]
-            raw = arr.tobytes()
-            daddr = alloc(raw) if len(raw) else _UNDEF
+            nbytes = int(arr.nbytes)
+            # a byte view of the (contiguous) array: no intermediate copy of a multi-gigabyte payload
+            raw = memoryview(arr.reshape(-1).view(np.uint8)) if nbytes and arr.dtype.kind != "S" else arr.tobytes()
+            daddr = alloc(raw) if nbytes else _UNDEF
             shape = arr.shape if arr.ndim else None
             msgs = [
                 _message(0x01, _dataspace_message(shape)),
                 _message(0x03, _enum_message(arr.dtype, node["enum"]) if node.get("enum") else
                          _dtype_message(arr.dtype), flags=1),
                 _message(0x05, struct.pack("<BBBB", 2, 2, 2, 0x02)),  # fill value: never written
-                _message(0x08, struct.pack("<BBQQ", 3, 1, daddr, len(raw))),
+                _message(0x08, struct.pack("<BBQQ", 3, 1, daddr, nbytes)),
             ]
             for k, v in node["attrs"].items():
                 msgs.append(_attr_message(k, v))
@@ -700,13 +722,14 @@ class Writer(object):
             return write_object_header(msgs), btree_addr, heap_addr
 
         root_hdr, root_btree, root_heap = write_group(self._tree)
-        eof = len(out)
+        eof = pos[0]
         sb = bytearray()
         sb += _SIG
         sb += struct.pack("<BBBBBBBB", 0, 0, 0, 0, 0, 8, 8, 0)
         sb += struct.pack("<HHI", 4, 16, 0)
         sb += struct.pack("<QQQQ", 0, _UNDEF, eof, _UNDEF)
         sb += struct.pack("<QQII", 0, root_hdr, 1, 0) + struct.pack("<QQ", root_btree, root_heap)
-        out[0:len(sb)] = sb
-        with open(path, "wb") as fh:
-            fh.write(bytes(out))
+        fh.seek(0)
+        fh.write(bytes(sb))
+        fh.close()
+        os.replace(tmp_path, path)

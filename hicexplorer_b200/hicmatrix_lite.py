@@ -78,8 +78,10 @@ class hiCMatrix(object):
     def _load_h5(self, path):
         f = hdf5lite.File(path)
         shape = tuple(int(v) for v in f["matrix/shape"].read())
-        up = sparse.csr_matrix((f["matrix/data"].read(), f["matrix/indices"].read(), f["matrix/indptr"].read()),
-                               shape=shape)
+        # the three big arrays stay views of the mapped file when it stores them plainly (files written by this package);
+        # they are only ever read (uploaded, or copied by the symmetric fill)
+        up = sparse.csr_matrix((f["matrix/data"].read(copy=False), f["matrix/indices"].read(copy=False),
+                                f["matrix/indptr"].read(copy=False)), shape=shape)
         self._set_upper(up)
         chrom = f["intervals/chr_list"].read()
         start = f["intervals/start_list"].read()
@@ -111,8 +113,16 @@ class hiCMatrix(object):
 
     def _set_upper(self, up):
         up = sparse.csr_matrix(up)
-        up.sum_duplicates()
-        if sparse.tril(up, -1).nnz:          # a file that stores both triangles: nothing to mirror
+        try:
+            up.sum_duplicates()              # also sorts the columns of every row (no-op for canonical input)
+        except ValueError:                   # read-only views of a mapped file that is not canonical: work on a copy
+            up = up.copy()
+            up.sum_duplicates()
+        # entries below the diagonal?  With sorted rows only the first column of each row has to be looked at: O(n)
+        # instead of a COO copy of a multi-gigabyte matrix
+        rows = np.flatnonzero(np.diff(up.indptr))
+        has_lower = bool(len(rows)) and bool(np.any(up.indices[up.indptr[rows]] < rows))
+        if has_lower:                        # a file that stores both triangles: nothing to mirror
             self._matrix = up
             self._upper = None
         else:
@@ -292,9 +302,10 @@ class hiCMatrix(object):
                              "PYTABLES_FORMAT_VERSION": "2.1"})
         w.group("/matrix", group)
         w.group("/intervals", group)
-        w.dataset("/matrix/data", up.data.astype(self.value_dtype), carray)
-        w.dataset("/matrix/indices", up.indices.astype(np.int32), carray)
-        w.dataset("/matrix/indptr", up.indptr.astype(np.int32), carray)
+        # (no copies when the arrays already have the file's types: these are the multi-gigabyte payloads)
+        w.dataset("/matrix/data", up.data.astype(self.value_dtype, copy=False), carray)
+        w.dataset("/matrix/indices", up.indices.astype(np.int32, copy=False), carray)
+        w.dataset("/matrix/indptr", up.indptr.astype(np.int32 if up.nnz < 2 ** 31 else np.int64, copy=False), carray)
         w.dataset("/matrix/shape", np.asarray(up.shape, dtype=np.int64), carray)
         chrom, start, end, extra = zip(*self.cut_intervals) if self.cut_intervals else ((), (), (), ())
         width = max([len(c) for c in chrom] + [1])
@@ -335,5 +346,5 @@ class hiCMatrix(object):
         w.dataset("/indexes/chrom_offset", chrom_offset)
         w.dataset("/pixels/bin1_id", up.row.astype(np.int32))
         w.dataset("/pixels/bin2_id", up.col.astype(np.int32))
-        w.dataset("/pixels/count", up.data.astype(self.value_dtype))
+        w.dataset("/pixels/count", up.data.astype(self.value_dtype, copy=False))
         w.save(path)

@@ -58,7 +58,7 @@ def ice_pipeline(matrix, filter_threshold, max_iter=500, tolerance=1e-5, chr_off
       deviation      last max|s-1| (per chromosome for perchr)
     """
     _lib.require_device()
-    m = canonical_csr(matrix)
+    m = canonical_csr(matrix, dtype=None)      # values keep the file type: widened to fp64 on the device
     n = m.shape[0]
     lo, hi = filter_threshold
     with (DeviceCSR.from_upper(m, device=device) if upper_input else DeviceCSR.from_scipy(m, device=device)) as dev:
@@ -137,7 +137,7 @@ def kr_pipeline(matrix, rescale=True, want_matrix=True, device=0):
     """KR branch of the driver (hicCorrectMatrix.py:742-757): no masking, no filter.
     Returns dict(x, factor, outer, matvecs, residual, upper)."""
     _lib.require_device()
-    m = canonical_csr(matrix)
+    m = canonical_csr(matrix, dtype=None)      # values keep the file type: widened to fp64 on the device
     with DeviceCSR.from_scipy(m, device=device) as dev:
         dev.pack_values()
         x, outer, matvecs, residual = dev.kr()
@@ -222,7 +222,7 @@ def ice_pipeline_sharded(matrix, filter_threshold, max_iter=500, tolerance=1e-5,
         return ice_pipeline(matrix, filter_threshold, max_iter, tolerance, chr_offsets, perchr, skip_diagonal,
                             device=torch.cuda.current_device(), want_matrix=want_matrix, file_layout=file_layout)
     device = torch.cuda.current_device()
-    m = canonical_csr(matrix)
+    m = canonical_csr(matrix, dtype=None)      # values keep the file type: widened to fp64 on the device
     n = m.shape[0]
     lo, hi = filter_threshold
     bounds = nnz_balanced_partition(m.indptr, world)
@@ -293,7 +293,7 @@ def kr_pipeline_sharded(matrix, rescale=True):
     if dist is None or world == 1:
         return kr_pipeline(matrix, rescale=rescale, want_matrix=False, device=torch.cuda.current_device())
     device = torch.cuda.current_device()
-    m = canonical_csr(matrix)
+    m = canonical_csr(matrix, dtype=None)      # values keep the file type: widened to fp64 on the device
     bounds = nnz_balanced_partition(m.indptr, world)
     with DeviceCSR.from_scipy(m, device=device, row_range=(int(bounds[rank]), int(bounds[rank + 1]))) as dev:
         keep_alive = attach_comm(dev, rank, world)

@@ -20,11 +20,17 @@ KR_DELTA_UPPER = 3.0
 KR_DIAG_EPS = 1e-5
 
 
+# value types the library widens to fp64 on the device (hb_csr_create_typed): no fp64 copy of the matrix on the host
+_VALUE_KINDS = {np.dtype(np.float64): 0, np.dtype(np.float32): 1, np.dtype(np.int32): 2, np.dtype(np.int64): 3}
+
+
 def canonical_csr(matrix, dtype=np.float64):
-    """float64 CSR with sorted, duplicate-free rows (a copy only when needed)."""
+    """CSR with sorted, duplicate-free rows (a copy only when needed).  ``dtype=None`` keeps a value type the device
+    can widen itself (float64, float32, int32, int64) and converts anything else to float64."""
     m = matrix if sparse.isspmatrix_csr(matrix) else sparse.csr_matrix(matrix)
-    if m.dtype != dtype:
-        m = m.astype(dtype)
+    want = dtype if dtype is not None else (m.dtype if m.dtype in _VALUE_KINDS else np.float64)
+    if m.dtype != want:
+        m = m.astype(want)
     if not m.has_canonical_format:
         m = m.copy() if m is matrix else m
         m.sum_duplicates()
@@ -64,7 +70,7 @@ class DeviceCSR(object):
         """Upload ``matrix`` (square, symmetric, canonical CSR).  ``row_range`` =
         (row0, row1) uploads only that block of rows (sharded runs)."""
         _lib.require_device()
-        m = canonical_csr(matrix)
+        m = canonical_csr(matrix, dtype=None)
         n = m.shape[0]
         if m.shape[0] != m.shape[1]:
             raise ValueError("matrix must be square")
@@ -73,23 +79,24 @@ class DeviceCSR(object):
         nnz = int(indptr[-1] - indptr[0])
         idx_i64 = 1 if m.indices.dtype == np.int64 else 0
         indices = np.ascontiguousarray(m.indices, dtype=np.int64 if idx_i64 else np.int32)
-        data = np.ascontiguousarray(m.data, dtype=np.float64)
+        data = np.ascontiguousarray(m.data)
         h = ctypes.c_void_p()
-        check(lib().hb_csr_create(ctypes.byref(h), row1 - row0, n, row0, nnz, ptr(indptr), ptr(indices), idx_i64,
-                                  ptr(data), device))
+        check(lib().hb_csr_create_typed(ctypes.byref(h), row1 - row0, n, row0, nnz, ptr(indptr), ptr(indices), idx_i64,
+                                        ptr(data), _VALUE_KINDS[data.dtype], device))
         return cls(h, device)
 
     @classmethod
     def from_upper(cls, upper, device=0):
         """Upload only the upper triangle (file layout) and build the full symmetric store on the device."""
         _lib.require_device()
-        m = canonical_csr(upper)
+        m = canonical_csr(upper, dtype=None)
         n = m.shape[0]
         indptr = np.ascontiguousarray(m.indptr, dtype=np.int64)
         indices = np.ascontiguousarray(m.indices, dtype=np.int32)
-        data = np.ascontiguousarray(m.data, dtype=np.float64)
+        data = np.ascontiguousarray(m.data)
         h = ctypes.c_void_p()
-        check(lib().hb_csr_create_upper(ctypes.byref(h), n, int(m.nnz), ptr(indptr), ptr(indices), ptr(data), device))
+        check(lib().hb_csr_create_upper_typed(ctypes.byref(h), n, int(m.nnz), ptr(indptr), ptr(indices), ptr(data),
+                                              _VALUE_KINDS[data.dtype], device))
         return cls(h, device)
 
     @classmethod

@@ -88,6 +88,15 @@ HB_API uint64_t hb_launch_count(void);
 HB_API int hb_csr_create(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t row0, int64_t nnz,
                   const int64_t* indptr, const void* indices, int indices_i64, const double* data,
                   int device);
+/* The same two constructors for values in the file's own type (counts are int32 / int64 in .cool files, float32 after
+ * hicNormalize): the values are widened to the fp64 store on the device, so the host needs no fp64 copy and fewer bytes
+ * cross PCIe.  value_kind: */
+enum { HB_VALUES_F64 = 0, HB_VALUES_F32 = 1, HB_VALUES_I32 = 2, HB_VALUES_I64 = 3 };
+HB_API int hb_csr_create_typed(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t row0, int64_t nnz,
+                        const int64_t* indptr, const void* indices, int indices_i64, const void* data, int value_kind,
+                        int device);
+HB_API int hb_csr_create_upper_typed(hb_csr** out, int64_t n, int64_t nnz_upper, const int64_t* indptr,
+                              const int32_t* indices, const void* data, int value_kind, int device);
 /* Same store from the UPPER triangle only (what .h5 / .cool files hold; hicmatrix symmetrises on load,
  * call site hicCorrectMatrix.py:603-609): half the bytes cross PCIe, the mirror image is built in HBM with ascending
  * columns (deterministic layout, identical to a host-side fill).  Entries below the diagonal are an error. */

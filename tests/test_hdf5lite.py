@@ -76,3 +76,22 @@ def test_native_and_python_decoders_agree_on_reference_fixtures(name):
     c = read_all()
     for k in py:
         np.testing.assert_array_equal(py[k], c[k])
+
+
+def test_overwriting_the_file_that_is_still_mapped(tmp_path):
+    """big datasets are read as views of the mapped file; saving to the same path must not pull the pages away"""
+    from scipy import sparse
+    from hicexplorer_b200.hicmatrix_lite import hiCMatrix
+    ma = hiCMatrix()
+    up = sparse.random(300, 300, 0.1, random_state=np.random.default_rng(0), format="csr")
+    up = sparse.triu(sparse.csr_matrix(np.round(up * 100)), 0, format="csr")
+    ma.matrix = sparse.csr_matrix(up + sparse.triu(up, 1).T)
+    ma.cut_intervals = [("chr1", i * 10, (i + 1) * 10, 1.0) for i in range(300)]
+    ma._index_intervals()
+    path = str(tmp_path / "m.h5")
+    ma.save(path)
+    again = hiCMatrix(path)                       # arrays are views of the mapping
+    assert again.upper_for_device() is not None and not again.upper_for_device().data.flags.writeable
+    again.save(path)                              # same path
+    third = hiCMatrix(path)
+    assert (third.matrix != ma.matrix).nnz == 0 and (again.matrix != ma.matrix).nnz == 0
