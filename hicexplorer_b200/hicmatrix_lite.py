@@ -98,10 +98,17 @@ class hiCMatrix(object):
         start = f["bins/start"].read()
         end = f["bins/end"].read()
         n = len(start)
-        b1 = f["pixels/bin1_id"].read()
-        b2 = f["pixels/bin2_id"].read()
-        cnt = f["pixels/count"].read()
-        up = sparse.csr_matrix((cnt, (b1, b2)), shape=(n, n))
+        b2 = f["pixels/bin2_id"].read(copy=False)
+        cnt = f["pixels/count"].read(copy=False)
+        up = None
+        if "indexes" in f and "bin1_offset" in f["indexes"].keys():
+            # the pixel table is sorted by (bin1, bin2) and indexes/bin1_offset is its row pointer (cooler schema): the
+            # CSR exists already, no COO -> CSR conversion of a multi-gigabyte table
+            offs = f["indexes/bin1_offset"].read()
+            if len(offs) == n + 1 and offs[0] == 0 and offs[-1] == len(cnt) and np.all(np.diff(offs) >= 0):
+                up = sparse.csr_matrix((cnt, b2, offs), shape=(n, n))
+        if up is None:
+            up = sparse.csr_matrix((np.asarray(cnt), (f["pixels/bin1_id"].read(), np.asarray(b2))), shape=(n, n))
         self._set_upper(up)
         self.cut_intervals = [(names[c], int(s), int(e), 1.0) for c, s, e in zip(chrom_id, start, end)]
         if "weight" in f["bins"].keys():
