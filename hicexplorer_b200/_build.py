@@ -76,7 +76,8 @@ def build_io():
     cc = shutil.which("gcc") or shutil.which("cc")
     if cc is None:
         raise RuntimeError("gcc not found: cannot build libhbio.so")
-    subprocess.check_call([cc, "-O3", "-fPIC", "-shared", "-std=c11", "-fvisibility=hidden", "-o", dst, src])
+    subprocess.check_call([cc, "-O3", "-fPIC", "-shared", "-std=gnu11", "-fvisibility=hidden", "-o", dst, src, "-lz",
+                           "-lpthread"])
     return dst
 
 

@@ -152,3 +152,138 @@ HBIO_API void hbio_unshuffle(const uint8_t* src, uint8_t* dst, int64_t nbytes, i
     }
     unshuffle(src, dst, nbytes, typesize);
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Batch decode of the chunks of ONE 1-D chunked dataset with a pool of threads: what makes a genome-wide matrix file
+ * written by PyTables (Blosc) or cooler (deflate + shuffle) load in seconds -- ~140 000 chunks of 64 KB each for a
+ * 10 kb human matrix, one Python-level call per chunk before.
+ *
+ *   file_base            start of the memory-mapped file
+ *   addr / csize / fmask per chunk: file offset, stored size, filter mask (bit i set = filter i was skipped)
+ *   out_off / out_len    per chunk: where its decoded bytes go in `out` and how many of them (the last chunk is clipped)
+ *   chunk_bytes          decoded size of a full chunk
+ *   filters / typesizes  the dataset's filter pipeline in application order (HDF5 ids 1 deflate, 2 shuffle,
+ *                        3 fletcher32, 32001 blosc) and, for shuffle, the element size
+ * Returns 0, -1 malformed data, -2 a codec / filter this decoder does not handle (the caller falls back to Python).
+ * ------------------------------------------------------------------------------------------------------------------ */
+#include <pthread.h>
+#include <stdlib.h>
+#include <zlib.h>
+
+typedef struct {
+    const uint8_t* file_base;
+    int64_t n_chunks;
+    const int64_t* addr;
+    const int64_t* csize;
+    const uint32_t* fmask;
+    const int64_t* out_off;
+    const int64_t* out_len;
+    int64_t chunk_bytes;
+    const int32_t* filters;
+    const int32_t* typesizes;
+    int nfilters;
+    uint8_t* out;
+    int nthreads;
+    int tid;
+    int64_t status;
+} hbio_job;
+
+static void* hbio_worker(void* arg) {
+    hbio_job* j = (hbio_job*)arg;
+    const int64_t cap = j->chunk_bytes + 64;
+    uint8_t* a = (uint8_t*)malloc((size_t)cap);
+    uint8_t* b = (uint8_t*)malloc((size_t)cap);
+    uint8_t* scratch = (uint8_t*)malloc((size_t)cap);
+    j->status = 0;
+    if (!a || !b || !scratch) j->status = -1;
+    for (int64_t c = j->tid; c < j->n_chunks && j->status == 0; c += j->nthreads) {
+        const uint8_t* cur = j->file_base + j->addr[c];
+        int64_t len = j->csize[c];
+        uint8_t* bufs[2] = {a, b};
+        int which = 0;
+        for (int f = j->nfilters - 1; f >= 0 && j->status == 0; --f) {
+            if (j->fmask[c] & (1u << f)) continue;
+            uint8_t* dst = bufs[which];
+            const int id = j->filters[f];
+            if (id == 32001) {
+                if (len < 16 || hbio_blosc_nbytes(cur) > cap || hbio_blosc_blocksize(cur) > cap) {
+                    j->status = -1;
+                    break;
+                }
+                const int64_t got = hbio_blosc_decode(cur, len, dst, scratch);
+                if (got < 0) {
+                    j->status = got;
+                    break;
+                }
+                len = got;
+            } else if (id == 1) {
+                uLongf dlen = (uLongf)cap;
+                if (uncompress(dst, &dlen, cur, (uLong)len) != Z_OK) {
+                    j->status = -1;
+                    break;
+                }
+                len = (int64_t)dlen;
+            } else if (id == 2) {
+                if (len > cap) {
+                    j->status = -1;
+                    break;
+                }
+                hbio_unshuffle(cur, dst, len, j->typesizes[f]);
+            } else if (id == 3) {
+                if (len < 4) {
+                    j->status = -1;
+                    break;
+                }
+                len -= 4; /* checksum dropped, data untouched */
+                continue;
+            } else {
+                j->status = -2;
+                break;
+            }
+            cur = dst;
+            which ^= 1;
+        }
+        if (j->status == 0) {
+            if (len < j->out_len[c]) j->status = -1;
+            else memcpy(j->out + j->out_off[c], cur, (size_t)j->out_len[c]);
+        }
+    }
+    free(a);
+    free(b);
+    free(scratch);
+    return NULL;
+}
+
+HBIO_API int64_t hbio_decode_chunks(const uint8_t* file_base, int64_t n_chunks, const int64_t* addr, const int64_t* csize,
+                                    const uint32_t* fmask, const int64_t* out_off, const int64_t* out_len, int64_t chunk_bytes,
+                                    const int32_t* filters, const int32_t* typesizes, int nfilters, uint8_t* out, int nthreads) {
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 64) nthreads = 64;
+    if ((int64_t)nthreads > n_chunks) nthreads = n_chunks > 0 ? (int)n_chunks : 1;
+    hbio_job jobs[64];
+    pthread_t th[64];
+    for (int t = 0; t < nthreads; ++t) {
+        hbio_job j = {file_base, n_chunks, addr, csize, fmask, out_off, out_len, chunk_bytes, filters, typesizes, nfilters,
+                      out, nthreads, t, 0};
+        jobs[t] = j;
+    }
+    int started = 0;
+    for (int t = 1; t < nthreads; ++t) {
+        if (pthread_create(&th[t], NULL, hbio_worker, &jobs[t]) != 0) break;
+        started = t;
+    }
+    int64_t status = 0;
+    if (started != nthreads - 1) {
+        /* could not start every thread: let the started ones finish, then decode everything here */
+        for (int t = 1; t <= started; ++t) pthread_join(th[t], NULL);
+        hbio_job j = {file_base, n_chunks, addr, csize, fmask, out_off, out_len, chunk_bytes, filters, typesizes, nfilters,
+                      out, 1, 0, 0};
+        hbio_worker(&j);
+        return j.status;
+    }
+    hbio_worker(&jobs[0]);
+    for (int t = 1; t < nthreads; ++t) pthread_join(th[t], NULL);
+    for (int t = 0; t < nthreads; ++t)
+        if (jobs[t].status != 0) status = jobs[t].status;
+    return status;
+}

@@ -125,6 +125,10 @@ def _native_lib():
             lib.hbio_blosc_blocksize.argtypes = [ctypes.c_char_p]
             lib.hbio_blosc_decode.restype = ctypes.c_int64
             lib.hbio_blosc_decode.argtypes = [ctypes.c_char_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+            if hasattr(lib, "hbio_decode_chunks"):
+                lib.hbio_decode_chunks.restype = ctypes.c_int64
+                lib.hbio_decode_chunks.argtypes = [ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_void_p] * 5 + [
+                    ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
             _native = lib
     return _native or None
 
@@ -243,6 +247,8 @@ class _Dataset(object):
         if btree == _UNDEF or count == 0:
             return out
         chunk_bytes = int(np.prod(chunk_shape, dtype=np.int64)) * itemsize
+        if len(self.shape) == 1 and self._read_chunks_native(out, btree, ndims, chunk_shape[0], chunk_bytes, itemsize):
+            return out
         for size, fmask, offs, addr in self._f._iter_chunks(btree, ndims):
             raw = buf[addr:addr + size]
             for i in range(len(self._filters) - 1, -1, -1):
@@ -271,6 +277,40 @@ class _Dataset(object):
                 sl_in.append(slice(0, hi - lo))
             out[tuple(sl_out)] = arr[tuple(sl_in)]
         return out
+
+    def _read_chunks_native(self, out, btree, ndims, chunk_len, chunk_bytes, itemsize):
+        """1-D chunked dataset: all chunks decoded by libhbio's thread pool in one call.  False = not handled here."""
+        lib = _native_lib()
+        buf = self._f._buf
+        if lib is None or not hasattr(lib, "hbio_decode_chunks") or not isinstance(buf, mmap.mmap):
+            return False
+        if any(fid not in (1, 2, 3, 32001) for fid, _cd in self._filters):
+            return False
+        chunks = list(self._f._iter_chunks(btree, ndims))
+        if not chunks:
+            return True
+        n = len(chunks)
+        addr = np.fromiter((c[3] for c in chunks), dtype=np.int64, count=n)
+        csize = np.fromiter((c[0] for c in chunks), dtype=np.int64, count=n)
+        fmask = np.fromiter((c[1] for c in chunks), dtype=np.uint32, count=n)
+        start = np.fromiter((c[2][0] for c in chunks), dtype=np.int64, count=n)
+        stop = np.minimum(start + chunk_len, self.shape[0])
+        if np.any(start >= self.shape[0]) or np.any(addr + csize > len(buf)):
+            return False
+        out_off = start * itemsize
+        out_len = (stop - start) * itemsize
+        filters = np.asarray([fid for fid, _cd in self._filters], dtype=np.int32)
+        tsizes = np.asarray([(cd[0] if (fid == 2 and cd) else itemsize) for fid, cd in self._filters], dtype=np.int32)
+        base = np.frombuffer(buf, dtype=np.uint8)
+        import os
+        threads = int(os.environ.get("HDF5LITE_THREADS", "0")) or min(16, os.cpu_count() or 1)
+        view = out.view(np.uint8).reshape(-1)
+        rc = lib.hbio_decode_chunks(base.ctypes.data, n, addr.ctypes.data, csize.ctypes.data, fmask.ctypes.data,
+                                    out_off.ctypes.data, out_len.ctypes.data, chunk_bytes, filters.ctypes.data,
+                                    tsizes.ctypes.data, len(filters), view.ctypes.data, threads)
+        if rc == -1:
+            raise ValueError("malformed chunk data")
+        return rc == 0
 
     def __getitem__(self, key):
         return self.read()[key]
