@@ -20,12 +20,13 @@ import logging
 import sys
 
 import numpy as np
+from scipy import sparse
 from scipy.sparse import lil_matrix
 
 from . import hicmatrix_lite as hm
 from ._version import __version__
 from .krbalancing import kr_balancing
-from .pipeline import ice_pipeline, ice_pipeline_sharded, kr_pipeline_sharded
+from .pipeline import ice_pipeline, ice_pipeline_sharded, kr_pipeline, kr_pipeline_sharded
 
 log = logging.getLogger(__name__)
 
@@ -230,7 +231,67 @@ def _correct_ice(ma, args, world=1, rank=0):
     log.info("Total regions to be removed: {}".format(n - len(res['kept'])))
 
 
+def _block_diag_upper(blocks, offsets, n):
+    """file-layout CSR (n x n) from per-chromosome upper-triangular blocks placed on the diagonal"""
+    indptr = np.zeros(n + 1, dtype=np.int64)
+    idx_parts, val_parts = [], []
+    base = 0
+    for (lo, hi), blk in zip(zip(offsets[:-1], offsets[1:]), blocks):
+        blk = sparse.csr_matrix(blk)
+        indptr[lo + 1:hi + 1] = base + blk.indptr[1:]
+        idx_parts.append(blk.indices.astype(np.int32, copy=False) + np.int32(lo))
+        val_parts.append(blk.data)
+        base += blk.nnz
+    indptr[offsets[-1] + 1:] = base
+    idx = np.concatenate(idx_parts) if idx_parts else np.zeros(0, dtype=np.int32)
+    val = np.concatenate(val_parts) if val_parts else np.zeros(0)
+    return sparse.csr_matrix((val, idx, indptr), shape=(n, n))
+
+
+def _drop_explicit_zeros(m):
+    if m.nnz and np.any(m.data == 0):
+        m.eliminate_zeros()
+    return m
+
+
+def _correct_kr_from_upper(ma, up, args):
+    """KR when the loaded matrix is untouched (single GPU): the file's upper triangle is uploaded as it is, the symmetric
+    store is built on the device and the balanced matrix comes back in file layout; the full symmetric matrix never
+    exists on the host.  Same results as the kr_balancing object protocol of the reference (:718-732, :744-757)."""
+    want_matrix = str(args.outFileName).endswith('.h5')
+    n = up.shape[0]
+    if not args.perchr:
+        res = kr_pipeline(up, rescale=True, want_matrix=want_matrix, device=args.device, upper_input=True)
+        print("normalisation factor is {}".format(res['factor']))
+        upper = _drop_explicit_zeros(res['upper']) if want_matrix else up
+        ma.install_file_layout(upper, ma.nan_bins, np.asarray(res['x']).reshape(-1, 1))
+        return
+    offsets = ma.chromosome_offsets()
+
+    def balance(ci):
+        lo, hi = int(offsets[ci]), int(offsets[ci + 1])
+        res = kr_pipeline(up[lo:hi, lo:hi].tocsr(), rescale=want_matrix, want_matrix=want_matrix, device=args.device,
+                          upper_input=True)
+        if want_matrix:
+            print("normalisation factor is {}".format(res['factor']))
+        return ci, res
+
+    from concurrent.futures import ThreadPoolExecutor
+    order = sorted(range(len(offsets) - 1), key=lambda ci: -(offsets[ci + 1] - offsets[ci]))
+    with ThreadPoolExecutor(max_workers=4) as pool:
+        done = dict(pool.map(balance, order))
+    factors = np.concatenate([np.asarray(done[ci]['x']).reshape(-1, 1) for ci in range(len(offsets) - 1)])
+    if want_matrix:
+        upper = _drop_explicit_zeros(_block_diag_upper([done[ci]['upper'] for ci in range(len(offsets) - 1)], offsets, n))
+    else:
+        upper = up
+    ma.install_file_layout(upper, ma.nan_bins, factors)
+
+
 def _correct_kr(ma, args, world=1, rank=0):
+    up = ma.upper_for_device() if world == 1 else None
+    if up is not None:
+        return _correct_kr_from_upper(ma, up, args)
     matrix = ma.matrix.astype(np.float64)
     if world > 1 and not args.perchr and not str(args.outFileName).endswith('.h5'):
         # genome-wide KR to .cool: only the (rescaled) vector is needed -> row blocks over the GPUs

@@ -133,18 +133,26 @@ def ice_pipeline(matrix, filter_threshold, max_iter=500, tolerance=1e-5, chr_off
     return out
 
 
-def kr_pipeline(matrix, rescale=True, want_matrix=True, device=0):
+def kr_pipeline(matrix, rescale=True, want_matrix=True, device=0, upper_input=False, rescale_vector=None):
     """KR branch of the driver (hicCorrectMatrix.py:742-757): no masking, no filter.
-    Returns dict(x, factor, outer, matvecs, residual, upper)."""
+    Returns dict(x, factor, outer, matvecs, residual, upper).
+
+    upper_input     ``matrix`` holds only the upper triangle (what the files store); the symmetric store is built on the
+                    device (hb_csr_create_upper)
+    rescale_vector  whether the returned ``x`` is the rescaled one (default: same as ``rescale``).  The reference's
+                    --perchr + .cool branch returns the un-rescaled vector (:731) while --perchr + .h5 rescales through
+                    get_normalised_matrix(True) first (:727-732)."""
     _lib.require_device()
     m = canonical_csr(matrix, dtype=None)      # values keep the file type: widened to fp64 on the device
-    with DeviceCSR.from_scipy(m, device=device) as dev:
+    with (DeviceCSR.from_upper(m, device=device) if upper_input else DeviceCSR.from_scipy(m, device=device)) as dev:
         dev.pack_values()
         x, outer, matvecs, residual = dev.kr()
         factor = 1.0
+        x_raw = x
         if rescale:
             x, factor = dev.kr_rescale(x, KR_DIAG_EPS)
-        out = dict(x=x, factor=factor, outer=outer, matvecs=matvecs, residual=residual)
+        out = dict(x=x if (rescale if rescale_vector is None else rescale_vector) else x_raw, factor=factor, outer=outer,
+                   matvecs=matvecs, residual=residual)
         if want_matrix:
             out["upper"] = dev.kr_scaled_upper(x, KR_DIAG_EPS)
     return out

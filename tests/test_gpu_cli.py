@@ -214,3 +214,42 @@ def test_trans_and_inflation_cutoff(tmp_path, gm12878):
         main("correct --matrix {} --correctionMethod ICE --filterThreshold -1.5 5 --inflationCutoff 3 "
              "--outFileName {}".format(src, out).split())
     assert exc.value.code == 1
+
+
+def test_kr_from_the_files_upper_triangle(tmp_path, gm12878):
+    """the default method on an untouched input: upper triangle uploaded as stored, symmetric store built on the device,
+    balanced matrix back in file layout -- genome-wide and --perchr, .h5 (matrix + factors) and .cool (factors only)"""
+    g = gm12878
+    src = _gm_cool(tmp_path, g)
+    raw = full_from_pixels(g)
+    ref = kr_oracle.kr_pipeline(raw, rescale=True)
+    out = str(tmp_path / "kr.h5")
+    main("correct --matrix {} --correctionMethod KR --outFileName {}".format(src, out).split())
+    f, m = _read_h5(out)
+    assert np.array_equal(m.indices, ref["upper"].indices) and np.array_equal(m.indptr, ref["upper"].indptr)
+    np.testing.assert_allclose(m.data, ref["upper"].data, rtol=1e-8)
+    cf = f["correction_factors"].read()
+    assert cf.shape == (raw.shape[0], 1)
+    np.testing.assert_allclose(cf.ravel(), ref["x_out"], rtol=1e-9)
+    # --perchr: every chromosome balanced on its own, trans entries dropped from the .h5 matrix
+    offs = g["chrom_offset"]
+    outp = str(tmp_path / "kr_perchr.h5")
+    main("correct --matrix {} --correctionMethod KR --perchr --outFileName {}".format(src, outp).split())
+    fp, mp = _read_h5(outp)
+    cfp = fp["correction_factors"].read().ravel()
+    for c in (0, 5, len(offs) - 2):
+        lo, hi = int(offs[c]), int(offs[c + 1])
+        blk = kr_oracle.kr_pipeline(sparse.csr_matrix(raw[lo:hi, lo:hi]), rescale=True)
+        np.testing.assert_allclose(cfp[lo:hi], blk["x_out"], rtol=1e-9)
+        got = mp[lo:hi, lo:hi].tocsr()
+        got.sort_indices()
+        assert np.array_equal(got.indices, blk["upper"].indices)
+        np.testing.assert_allclose(got.data, blk["upper"].data, rtol=1e-8)
+    assert mp[int(offs[0]):int(offs[1]), int(offs[1]):].nnz == 0          # no trans entries
+    outc = str(tmp_path / "kr_perchr.cool")
+    main("correct --matrix {} --correctionMethod KR --perchr --outFileName {}".format(src, outc).split())
+    newc = hiCMatrix(outc)
+    assert abs(newc.matrix - raw).sum() == 0                               # .cool keeps the raw counts
+    lo, hi = int(offs[2]), int(offs[3])
+    unres = kr_oracle.kr_pipeline(sparse.csr_matrix(raw[lo:hi, lo:hi]), rescale=False)
+    np.testing.assert_allclose(np.asarray(newc.correction_factors).ravel()[lo:hi], unres["x_out"], rtol=1e-9)

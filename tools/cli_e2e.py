@@ -3,7 +3,7 @@
     hicCorrectMatrix correct -m <synthetic 10 kb .h5> -o out.h5 --correctionMethod ICE --filterThreshold -0.85 50
 The input file is written first (synthetic matrix generated on the device, upper triangle, this repo's writer); the
 command then runs in-process under cProfile so that the host-side stages show up next to the device time.
-Usage: python tools/cli_e2e.py [workload] [--cool]      Prints one JSON line."""
+Usage: python tools/cli_e2e.py [workload] [--cool] [--kr]      Prints one JSON line.  (--kr: the default method instead)"""
 import cProfile
 import io
 import json
@@ -46,13 +46,16 @@ def main():
     prof = cProfile.Profile()
     t0 = time.time()
     prof.enable()
-    hicCorrectMatrix.main(["correct", "-m", src, "-o", dst, "--correctionMethod", "ICE", "--filterThreshold", "-0.85", "50"])
+    if "--kr" in sys.argv:
+        hicCorrectMatrix.main(["correct", "-m", src, "-o", dst, "--correctionMethod", "KR"])
+    else:
+        hicCorrectMatrix.main(["correct", "-m", src, "-o", dst, "--correctionMethod", "ICE", "--filterThreshold", "-0.85", "50"])
     prof.disable()
     t_cmd = time.time() - t0
     buf = io.StringIO()
     pstats.Stats(prof, stream=buf).sort_stats("cumulative").print_stats(28)
     top = [ln.strip() for ln in buf.getvalue().splitlines() if ln.strip() and ln.lstrip()[0].isdigit()][:28]
-    out = {"workload": bench.workload_name(workload, bins, kw), "file": ext, "input_bytes": os.path.getsize(src),
+    out = {"workload": bench.workload_name(workload, bins, kw), "file": ext, "method": "KR" if "--kr" in sys.argv else "ICE", "input_bytes": os.path.getsize(src),
            "output_bytes": os.path.getsize(dst), "prepare_input_s": round(t_prepare, 2), "command_s": round(t_cmd, 2),
            "profile_top_cumulative": top}
     print(json.dumps(out))
