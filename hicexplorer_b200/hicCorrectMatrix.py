@@ -195,7 +195,8 @@ def _correct_ice(ma, args, world=1, rank=0):
                            max_iter=args.iterNum, tolerance=args.tolerance, chr_offsets=ma.chromosome_offsets(),
                            perchr=args.perchr, skip_diagonal=args.skipDiagonal, device=args.device, want_matrix=file_layout,
                            extra_mask_fn=extra_fn, upper_input=up is not None, file_layout=file_layout,
-                           trans_cutoff=args.transCutoff, clip_trans=args.clipTrans, inflation_cutoff=args.inflationCutoff)
+                           trans_cutoff=args.transCutoff, clip_trans=args.clipTrans, inflation_cutoff=args.inflationCutoff,
+                           drop_mask=ma.upper_drop_mask() if up is not None else None)
         if res.get('max_inter') is not None:
             log.info("trans contacts: {} percentile = {}".format(100 - float(args.transCutoff) / 100, res['max_inter']))
         if 'inflated_rel' in res:
@@ -259,9 +260,16 @@ def _correct_kr_from_upper(ma, up, args):
     store is built on the device and the balanced matrix comes back in file layout; the full symmetric matrix never
     exists on the host.  Same results as the kr_balancing object protocol of the reference (:718-732, :744-757)."""
     want_matrix = str(args.outFileName).endswith('.h5')
-    n = up.shape[0]
+    drop = ma.upper_drop_mask()
+    if drop is not None and (args.perchr or not want_matrix):
+        # the raw counts of the selected chromosomes are needed on the host (blocks / .cool pixels): select them there
+        keep = np.flatnonzero(drop == 0)
+        up = sparse.csr_matrix(up[keep, :][:, keep])
+        up.sort_indices()
+        drop = None
+    n = len(ma.cut_intervals)
     if not args.perchr:
-        res = kr_pipeline(up, rescale=True, want_matrix=want_matrix, device=args.device, upper_input=True)
+        res = kr_pipeline(up, rescale=True, want_matrix=want_matrix, device=args.device, upper_input=True, drop_mask=drop)
         print("normalisation factor is {}".format(res['factor']))
         upper = _drop_explicit_zeros(res['upper']) if want_matrix else up
         ma.install_file_layout(upper, ma.nan_bins, np.asarray(res['x']).reshape(-1, 1))

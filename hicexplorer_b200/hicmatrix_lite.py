@@ -33,6 +33,8 @@ class hiCMatrix(object):
         self._matrix = None          # full symmetric CSR (built lazily from _upper)
         self._upper = None           # upper triangle as stored in the file, while nothing has modified the matrix
         self._file_layout = None     # corrected upper triangle in the original frame, ready to be written
+        self._upper_keep = None      # bins of _upper that are still part of the matrix (a chromosome subset in file
+                                     # order was selected); None = all.  The selection itself is left to the device.
         self.value_dtype = np.float64  # dtype of /matrix/data (hicNormalize writes the float32 it computes in)
         self.cut_intervals = []
         self.nan_bins = np.array([], dtype=np.int64)
@@ -53,19 +55,35 @@ class hiCMatrix(object):
     def matrix(self):
         """full symmetric scipy CSR, like hicmatrix keeps it; symmetrised on first use"""
         if self._matrix is None and self._upper is not None:
-            self._matrix = self._fill_lower(self._upper)
+            full = self._fill_lower(self._upper)
+            if self._upper_keep is not None:
+                keep = np.flatnonzero(self._upper_keep)
+                full = sparse.csr_matrix(full[keep, :][:, keep])
+                full.sort_indices()
+                self._upper = None           # it still has the file's bins: no longer the same matrix
+                self._upper_keep = None
+            self._matrix = full
         return self._matrix
 
     @matrix.setter
     def matrix(self, value):
         self._matrix = value
         self._upper = None
+        self._upper_keep = None
         self._file_layout = None
 
     def upper_for_device(self):
         """the file's upper triangle if the matrix is still exactly what was loaded (the device can then build the
-        symmetric store itself and only half the bytes are uploaded), else None"""
+        symmetric store itself and only half the bytes are uploaded), else None.  When a chromosome subset has been
+        selected (``upper_drop_mask()`` is not None) the triangle still has the file's bins and the device deletes the
+        others."""
         return self._upper
+
+    def upper_drop_mask(self):
+        """uint8 mask over the bins of ``upper_for_device()``: 1 = not part of the matrix any more; None = keep all"""
+        if self._upper is None or self._upper_keep is None:
+            return None
+        return (~self._upper_keep).astype(np.uint8)
 
     def install_file_layout(self, upper, nan_bins, correction_factors):
         """take a corrected matrix that is already in file layout (upper triangle, original frame): what
@@ -182,8 +200,16 @@ class hiCMatrix(object):
             if c not in self.chrBinBoundaries:
                 raise ValueError("Chromosome name '%s' not in matrix." % c)
         order = np.concatenate([np.arange(*self.chrBinBoundaries[c]) for c in new_chr_order]).astype(np.int64)
-        self.matrix = sparse.csr_matrix(self.matrix[order, :][:, order])
-        self.matrix.sort_indices()
+        if (self._upper is not None and self._matrix is None and self._upper_keep is None and len(order)
+                and np.all(np.diff(order) > 0)):
+            # a subset of the chromosomes in file order: the upper triangle stays an upper triangle, so the selection is
+            # a bin deletion -- recorded here, carried out on the device (hb_csr_compact) right after the upload
+            keep = np.zeros(self._upper.shape[0], dtype=bool)
+            keep[order] = True
+            self._upper_keep = keep
+        else:
+            self.matrix = sparse.csr_matrix(self.matrix[order, :][:, order])
+            self.matrix.sort_indices()
         self.cut_intervals = [self.cut_intervals[i] for i in order]
         if self.correction_factors is not None:
             self.correction_factors = np.asarray(self.correction_factors).ravel()[order]

@@ -24,7 +24,7 @@ def _segment_offsets_after(mask_removed, offsets):
 
 def ice_pipeline(matrix, filter_threshold, max_iter=500, tolerance=1e-5, chr_offsets=None, perchr=False,
                  skip_diagonal=False, device=0, want_matrix=True, extra_mask_fn=None, upper_input=False,
-                 file_layout=False, trans_cutoff=None, clip_trans=False, inflation_cutoff=None):
+                 file_layout=False, trans_cutoff=None, clip_trans=False, inflation_cutoff=None, drop_mask=None):
     """ICE branch of the driver.
 
     matrix           full symmetric scipy matrix in the original bin frame (n bins)
@@ -36,6 +36,9 @@ def ice_pipeline(matrix, filter_threshold, max_iter=500, tolerance=1e-5, chr_off
 
     upper_input      ``matrix`` holds only the upper triangle (what the files store): half the upload, the mirror
                      image is built on the device (hb_csr_create_upper)
+    drop_mask        uint8[bins of ``matrix``], 1 = delete the bin right after the upload (a chromosome subset chosen with
+                     --chromosomes, hicCorrectMatrix.py:606-609); every other argument and every result then refers to
+                     the remaining bins
     file_layout      return ``upper`` = corrected matrix as the files store it (upper triangle, zeros eliminated,
                      original n-bin frame; hicmatrix restoreMaskedBins + triu, done on the device) instead of ``matrix``
 
@@ -62,6 +65,9 @@ def ice_pipeline(matrix, filter_threshold, max_iter=500, tolerance=1e-5, chr_off
     n = m.shape[0]
     lo, hi = filter_threshold
     with (DeviceCSR.from_upper(m, device=device) if upper_input else DeviceCSR.from_scipy(m, device=device)) as dev:
+        if drop_mask is not None:
+            dev.compact(np.ascontiguousarray(drop_mask, dtype=np.uint8))
+            n = dev.n
         # mask all zero value bins: row sums include the diagonal and NaNs propagate, as in the
         # reference where this happens before the NaN/Inf scrub
         row_sum, _ = dev.row_stats()
@@ -133,7 +139,8 @@ def ice_pipeline(matrix, filter_threshold, max_iter=500, tolerance=1e-5, chr_off
     return out
 
 
-def kr_pipeline(matrix, rescale=True, want_matrix=True, device=0, upper_input=False, rescale_vector=None):
+def kr_pipeline(matrix, rescale=True, want_matrix=True, device=0, upper_input=False, rescale_vector=None,
+                drop_mask=None):
     """KR branch of the driver (hicCorrectMatrix.py:742-757): no masking, no filter.
     Returns dict(x, factor, outer, matvecs, residual, upper).
 
@@ -145,6 +152,8 @@ def kr_pipeline(matrix, rescale=True, want_matrix=True, device=0, upper_input=Fa
     _lib.require_device()
     m = canonical_csr(matrix, dtype=None)      # values keep the file type: widened to fp64 on the device
     with (DeviceCSR.from_upper(m, device=device) if upper_input else DeviceCSR.from_scipy(m, device=device)) as dev:
+        if drop_mask is not None:              # chromosome subset (--chromosomes): delete the other bins first
+            dev.compact(np.ascontiguousarray(drop_mask, dtype=np.uint8))
         dev.pack_values()
         x, outer, matvecs, residual = dev.kr()
         factor = 1.0

@@ -253,3 +253,41 @@ def test_kr_from_the_files_upper_triangle(tmp_path, gm12878):
     lo, hi = int(offs[2]), int(offs[3])
     unres = kr_oracle.kr_pipeline(sparse.csr_matrix(raw[lo:hi, lo:hi]), rescale=False)
     np.testing.assert_allclose(np.asarray(newc.correction_factors).ravel()[lo:hi], unres["x_out"], rtol=1e-9)
+
+
+def test_chromosome_subset_in_file_order_is_selected_on_the_device(tmp_path, gm12878):
+    """--chromosomes with a subset in file order: the upper triangle is uploaded untouched and the other bins are
+    deleted on the device (hicmatrix reorderChromosomes on the host otherwise); ICE and KR"""
+    g = gm12878
+    src = _gm_cool(tmp_path, g)
+    offs = g["chrom_offset"]
+    chroms = [2, 3, 7]                                        # names "2", "3", "7" of _gm_cool: file order
+    keep = np.concatenate([np.arange(offs[c - 1], offs[c]) for c in chroms])
+    sub = sparse.csr_matrix(full_from_pixels(g)[keep, :][:, keep])
+    sub.sort_indices()
+    ma = hiCMatrix(src)
+    ma.reorderChromosomes([str(c) for c in chroms])
+    assert ma.upper_for_device() is not None and ma.upper_drop_mask().sum() == g["nbins"] - len(keep)
+    assert (ma.matrix != sub).nnz == 0 and ma.upper_for_device() is None          # host view applies the selection
+    out = str(tmp_path / "ice_sub.h5")
+    main("correct --matrix {} --correctionMethod ICE --filterThreshold -1.5 5 --chromosomes 2 3 7 "
+         "--outFileName {}".format(src, out).split())
+    ref = ice_oracle.correct_ice_pipeline(sub, -1.5, 5.0, max_iter=500)
+    f, m = _read_h5(out)
+    assert m.shape == sub.shape
+    assert np.array_equal(f["nan_bins"].read(), ref["nan_bins"])
+    assert np.array_equal(m.indptr, ref["upper"].indptr) and np.array_equal(m.indices, ref["upper"].indices)
+    np.testing.assert_allclose(m.data, ref["upper"].data, rtol=1e-8)
+    assert [c.decode() for c in np.unique(f["intervals/chr_list"].read())] == ["2", "3", "7"]
+    outk = str(tmp_path / "kr_sub.h5")
+    main("correct --matrix {} --correctionMethod KR --chromosomes 2 3 7 --outFileName {}".format(src, outk).split())
+    kref = kr_oracle.kr_pipeline(sub, rescale=True)
+    fk, mk = _read_h5(outk)
+    np.testing.assert_allclose(fk["correction_factors"].read().ravel(), kref["x_out"], rtol=1e-9)
+    assert np.array_equal(mk.indices, kref["upper"].indices)
+    np.testing.assert_allclose(mk.data, kref["upper"].data, rtol=1e-8)
+    outc = str(tmp_path / "kr_sub.cool")
+    main("correct --matrix {} --correctionMethod KR --chromosomes 2 3 7 --outFileName {}".format(src, outc).split())
+    newc = hiCMatrix(outc)
+    assert abs(newc.matrix - sub).sum() == 0
+    np.testing.assert_allclose(np.asarray(newc.correction_factors).ravel(), kref["x_out"], rtol=1e-9)
