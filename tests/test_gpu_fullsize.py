@@ -109,3 +109,27 @@ def test_filter_finds_planted_bins_at_full_size():
         assert dev.n == n - zero.sum() - mask.sum()
         bias, iters, devn = dev.ice(500, 1e-5)
         assert devn[0] < 1e-5
+
+
+def test_genome_wide_100kb_pipeline_matches_the_reference_run():
+    """4.0e7-entry genome-wide matrix (far/trans entries, planted empty and low-coverage bins) against what the
+    REFERENCE's own functions produced for it (tests/golden/make_golden_synth100k.py): masks bit-exact, same iteration
+    count +-1, bias 1e-9, corrected values 1e-8"""
+    from hicexplorer_b200.pipeline import ice_pipeline
+    from tests.conftest import load_golden
+    z = load_golden("synth100k_ice.npz")
+    method, bins, kw = bench.synth_kwargs("ice100k", clean=False)
+    with DeviceCSR.synthetic(bins, **kw) as dev:
+        m = dev.download()
+    assert m.shape[0] == int(z["n"])
+    got = ice_pipeline(m, (float(z["lo"]), float(z["hi"])), max_iter=500)
+    assert np.array_equal(got["zero_bins"], z["zero_bins"])
+    assert np.array_equal(got["outliers_rel"], z["outliers_rel"])            # bit-exact filter mask
+    assert np.array_equal(got["kept"], z["kept"])
+    assert abs(int(got["iterations"][0]) - int(z["iterations"])) <= 1
+    np.testing.assert_allclose(got["bias"], z["bias"], rtol=1e-9)
+    w = got["matrix"]
+    assert w.nnz == int(z["nnz"])
+    np.testing.assert_allclose(w.data[z["sample_idx"]], z["sample_val"], rtol=1e-8)
+    np.testing.assert_allclose(np.asarray(w.sum(axis=1)).ravel(), z["row_sums"], rtol=1e-8)
+    np.testing.assert_allclose(w.data.sum(), float(z["data_sum"]), rtol=1e-9)
