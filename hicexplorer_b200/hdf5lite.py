@@ -682,18 +682,19 @@ class Writer(object):
         # written beside the target and renamed at the end: an input file that is still memory-mapped (File.read with
         # copy=False) may be the very path that is being overwritten
         tmp_path = "%s.tmp%d" % (path, os.getpid())
-        fh = open(tmp_path, "wb")
-        fh.write(b"\x00" * 96)  # superblock placeholder
-        pos = [96]
+        fd = os.open(tmp_path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+        pos = [96]                       # the superblock goes to offset 0 at the end
+        big = []                         # (offset, byte view) of multi-megabyte payloads, written by a thread pool
 
         def alloc(blob):
-            pad = (-pos[0]) % 8
-            if pad:
-                fh.write(b"\x00" * pad)
-                pos[0] += pad
+            pos[0] += (-pos[0]) % 8
             addr = pos[0]
-            fh.write(blob)
-            pos[0] += blob.nbytes if isinstance(blob, memoryview) else len(blob)
+            nbytes = blob.nbytes if isinstance(blob, memoryview) else len(blob)
+            if nbytes >= (32 << 20):
+                big.append((addr, blob))
+            else:
+                os.pwrite(fd, blob, addr)
+            pos[0] += nbytes
             return addr
 
         def write_object_header(msgs):
@@ -769,7 +770,21 @@ class Writer(object):
         sb += struct.pack("<HHI", 4, 16, 0)
         sb += struct.pack("<QQQQ", 0, _UNDEF, eof, _UNDEF)
         sb += struct.pack("<QQII", 0, root_hdr, 1, 0) + struct.pack("<QQ", root_btree, root_heap)
-        fh.seek(0)
-        fh.write(bytes(sb))
-        fh.close()
+        os.pwrite(fd, bytes(sb), 0)
+        if big:
+            # page-cache copies of a single write() run at a few GB/s; several threads on disjoint regions scale
+            from concurrent.futures import ThreadPoolExecutor
+            step = 64 << 20
+            jobs = [(addr + o, blob[o:o + step]) for addr, blob in big for o in range(0, blob.nbytes, step)]
+
+            def put(job):
+                off, view = job
+                while view.nbytes:
+                    done = os.pwrite(fd, view, off)
+                    off += done
+                    view = view[done:]
+
+            with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+                list(pool.map(put, jobs))
+        os.close(fd)
         os.replace(tmp_path, path)
