@@ -49,7 +49,7 @@ def iterativeCorrection(matrix, v=None, M=50, tolerance=1e-5, verbose=False, dev
         log.warning("[iterative correction] the matrix contains nans, they will be replaced by zeros.")
         data[np.isnan(data)] = 0
 
-    m = canonical_csr(matrix)
+    m = canonical_csr(matrix, dtype=None)      # counts keep their type on the host: widened to fp64 on the device
     with DeviceCSR.from_scipy(m, device=device) as dev:
         if dev.symmetry_ratio() > 1e-10:
             raise ValueError("Please provide symmetric matrix!")
