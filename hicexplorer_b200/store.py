@@ -37,6 +37,24 @@ def canonical_csr(matrix, dtype=np.float64):
     return m
 
 
+def parallel_copy(arr, threads=8):
+    """np.copy of a large 1-D array on a few threads (numpy releases the GIL for the slices): the first touch of the
+    fresh pages and the copy itself both scale, a multi-gigabyte index array comes out in a fraction of the time."""
+    arr = np.ascontiguousarray(arr)
+    if arr.nbytes < (64 << 20) or arr.ndim != 1:
+        return arr.copy()
+    from concurrent.futures import ThreadPoolExecutor
+    out = np.empty_like(arr)
+    step = -(-len(arr) // threads)
+
+    def part(k):
+        out[k * step:(k + 1) * step] = arr[k * step:(k + 1) * step]
+
+    with ThreadPoolExecutor(max_workers=threads) as pool:
+        list(pool.map(part, range(threads)))
+    return out
+
+
 def percentile_position(count, q):
     """Where numpy's default ('linear') percentile looks in the sorted sample: index of the lower neighbour and the
     interpolation weight, computed with numpy's own expressions (virtual index = (count - 1) * (q / 100))."""
@@ -69,21 +87,37 @@ class DeviceCSR(object):
     def from_scipy(cls, matrix, device=0, row_range=None):
         """Upload ``matrix`` (square, symmetric, canonical CSR).  ``row_range`` =
         (row0, row1) uploads only that block of rows (sharded runs)."""
+        return cls.from_scipy_as_uploaded(matrix, device=device, row_range=row_range)[0]
+
+    @classmethod
+    def from_scipy_as_uploaded(cls, matrix, device=0, row_range=None):
+        """``from_scipy`` that also returns the host matrix whose pattern the store has.  A CSR input is uploaded as it
+        is -- the library checks sorted, duplicate-free rows on the device in a few milliseconds
+        (hb_csr_create validation), scipy's host-side check of a genome-wide matrix takes the better part of a second --
+        and only a rejected block is canonicalised on the host (a copy) and uploaded again."""
         _lib.require_device()
-        m = canonical_csr(matrix, dtype=None)
-        n = m.shape[0]
+        m = matrix if sparse.isspmatrix_csr(matrix) else sparse.csr_matrix(matrix)
+        if m.dtype not in _VALUE_KINDS:
+            m = m.astype(np.float64)
         if m.shape[0] != m.shape[1]:
             raise ValueError("matrix must be square")
+        n = m.shape[0]
         row0, row1 = (0, n) if row_range is None else row_range
-        indptr = np.ascontiguousarray(m.indptr[row0:row1 + 1], dtype=np.int64)
-        nnz = int(indptr[-1] - indptr[0])
-        idx_i64 = 1 if m.indices.dtype == np.int64 else 0
-        indices = np.ascontiguousarray(m.indices, dtype=np.int64 if idx_i64 else np.int32)
-        data = np.ascontiguousarray(m.data)
-        h = ctypes.c_void_p()
-        check(lib().hb_csr_create_typed(ctypes.byref(h), row1 - row0, n, row0, nnz, ptr(indptr), ptr(indices), idx_i64,
-                                        ptr(data), _VALUE_KINDS[data.dtype], device))
-        return cls(h, device)
+        for attempt in (0, 1):
+            indptr = np.ascontiguousarray(m.indptr[row0:row1 + 1], dtype=np.int64)
+            nnz = int(indptr[-1] - indptr[0])
+            idx_i64 = 1 if m.indices.dtype == np.int64 else 0
+            indices = np.ascontiguousarray(m.indices, dtype=np.int64 if idx_i64 else np.int32)
+            data = np.ascontiguousarray(m.data)
+            h = ctypes.c_void_p()
+            rc = lib().hb_csr_create_typed(ctypes.byref(h), row1 - row0, n, row0, nnz, ptr(indptr), ptr(indices), idx_i64,
+                                           ptr(data), _VALUE_KINDS[data.dtype], device)
+            if rc == _lib.HB_ERR_INVALID_ARG and attempt == 0 and "ascending" in _lib.last_error():
+                m = m.copy() if m is matrix else m
+                m.sum_duplicates()               # sorts the columns and merges duplicates
+                continue
+            check(rc)
+            return cls(h, device), m
 
     @classmethod
     def from_upper(cls, upper, device=0):
