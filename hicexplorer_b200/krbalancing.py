@@ -70,7 +70,7 @@ class kr_balancing(object):
         """upper triangle (diagonal always stored) of (A + 1e-5 I) o (x x^T)."""
         self._need_x()
         self._rescale_once(rescale)
-        return self._dev.kr_scaled_upper(self._x, KR_DIAG_EPS).tocsc()
+        return self._dev.kr_scaled_upper(self._x, KR_DIAG_EPS)      # CSR: what every caller converts to anyway
 
     def close(self):
         if self._dev is not None:
