@@ -84,9 +84,9 @@ __global__ void hb_sym_sort_kernel(const int64_t* __restrict__ out_ptr, const un
         sk[i] = i < L ? (((unsigned long long)(unsigned int)out_idx[base + i] << 32) | (unsigned int)i) : ~0ull;
     __syncthreads();
     for (int k = 2; k <= P; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int j = k >> 1, sj = 31 - __clz(k >> 1); j > 0; j >>= 1, --sj) {
             for (int i = threadIdx.x; i < (P >> 1); i += blockDim.x) {
-                const int lo = ((i / j) * j << 1) + (i % j);     // element whose bit j is clear
+                const int lo = ((i >> sj) << (sj + 1)) | (i & (j - 1));     // element whose bit j is clear (j = 2^sj)
                 const int hi = lo + j;
                 const unsigned long long a = sk[lo], b = sk[hi];
                 if ((a > b) == ((lo & k) == 0)) {
