@@ -291,3 +291,27 @@ def test_chromosome_subset_in_file_order_is_selected_on_the_device(tmp_path, gm1
     newc = hiCMatrix(outc)
     assert abs(newc.matrix - sub).sum() == 0
     np.testing.assert_allclose(np.asarray(newc.correction_factors).ravel(), kref["x_out"], rtol=1e-9)
+
+
+def test_device_side_chromosome_selection_equals_a_presliced_input(tmp_path, gm12878):
+    """--chromosomes (subset in file order, selected on the device) gives byte-for-byte the matrix and factors of the
+    same command run on an input that holds only those chromosomes -- also with --perchr"""
+    g = gm12878
+    src = _gm_cool(tmp_path, g)
+    pre = hiCMatrix(src)
+    pre.reorderChromosomes(["4", "9", "10"])
+    _ = pre.matrix                                   # host-side selection
+    sliced = str(tmp_path / "sliced.cool")
+    pre.save(sliced)
+    for extra in ("", "--perchr"):
+        a, b = str(tmp_path / "a.h5"), str(tmp_path / "b.h5")
+        main("correct --matrix {} --correctionMethod ICE --filterThreshold -1.5 5 --chromosomes 4 9 10 {} "
+             "--outFileName {}".format(src, extra, a).split())
+        main("correct --matrix {} --correctionMethod ICE --filterThreshold -1.5 5 {} --outFileName {}".format(
+            sliced, extra, b).split())
+        fa, ma_ = _read_h5(a)
+        fb, mb_ = _read_h5(b)
+        assert np.array_equal(ma_.indptr, mb_.indptr) and np.array_equal(ma_.indices, mb_.indices)
+        np.testing.assert_array_equal(ma_.data, mb_.data)
+        np.testing.assert_array_equal(fa["correction_factors"].read(), fb["correction_factors"].read())
+        assert np.array_equal(fa["nan_bins"].read(), fb["nan_bins"].read())
