@@ -426,6 +426,60 @@ int hb_peer_attach(hb_csr* h, const void* all_handles) {
 
 int hb_peer_active(const hb_csr* h) { return (h != nullptr && h->peer) ? 1 : 0; }
 
+int hb_csr_keep_rows(hb_csr* h, int64_t row_begin, int64_t row_end) {
+    HB_REQUIRE(h != nullptr, "null handle");
+    HB_REQUIRE(h->row0 == 0 && h->n_rows == h->n_cols, "hb_csr_keep_rows starts from the full matrix");
+    HB_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= h->n_rows, "bad row range");
+    int rc = hb_use_device(h);
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    hb_drop_pack(h);
+    const int64_t nb = row_end - row_begin;
+    int64_t ends[2] = {0, 0};
+    HB_CUDA(cudaMemcpyAsync(&ends[0], h->d_indptr + row_begin, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    HB_CUDA(cudaMemcpyAsync(&ends[1], h->d_indptr + row_end, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    HB_CUDA(cudaStreamSynchronize(s));
+    const int64_t nnz_b = ends[1] - ends[0];
+    int64_t* d_ptr = nullptr;
+    int32_t* d_idx = nullptr;
+    double* d_val = nullptr;
+    cudaError_t e = cudaMalloc(&d_ptr, sizeof(int64_t) * (size_t)(nb + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&d_idx, sizeof(int32_t) * (size_t)(nnz_b + 4) + 16);
+    if (e == cudaSuccess) e = cudaMalloc(&d_val, sizeof(double) * (size_t)(nnz_b + 4) + 16);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(d_ptr, h->d_indptr + row_begin, sizeof(int64_t) * (size_t)(nb + 1), cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess && ends[0] != 0) {
+        hb_rebase_indptr_kernel<<<(unsigned)((nb + 1 + 255) / 256), 256, 0, s>>>(d_ptr, nb + 1, ends[0]);
+        g_hb_launches.fetch_add(1);
+    }
+    if (e == cudaSuccess && nnz_b > 0) {
+        e = cudaMemcpyAsync(d_idx, h->d_indices + ends[0], sizeof(int32_t) * (size_t)nnz_b, cudaMemcpyDeviceToDevice, s);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(d_val, h->d_data + ends[0], sizeof(double) * (size_t)nnz_b, cudaMemcpyDeviceToDevice, s);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+        cudaFree(d_ptr);
+        cudaFree(d_idx);
+        cudaFree(d_val);
+        return hb_cuda_fail(e, "keep rows", __FILE__, __LINE__);
+    }
+    if (h->owns_csr) {
+        cudaFree(h->d_indptr);
+        cudaFree(h->d_indices);
+        cudaFree(h->d_data);
+    }
+    h->owns_csr = true;
+    h->d_indptr = d_ptr;
+    h->d_indices = d_idx;
+    h->d_data = d_val;
+    h->phase = 0;
+    h->row0 = row_begin;
+    h->n_rows = nb;
+    h->nnz = nnz_b;
+    return HB_OK;
+}
+
 int hb_set_segments(hb_csr* h, int nseg, const int64_t* seg_offsets) {
     HB_REQUIRE(h != nullptr, "null handle");
     HB_REQUIRE(nseg >= 1 && nseg <= HB_MAX_SEG && seg_offsets != nullptr, "bad segment count");

@@ -181,9 +181,14 @@ def _correct_ice(ma, args, world=1, rank=0):
             log.error('--sequencedCountCutoff is not available in multi-GPU runs')
             sys.exit(1)
         file_layout = not args.perchr or str(args.outFileName).endswith('.h5')
-        res = ice_pipeline_sharded(ma.matrix, (args.filterThreshold[0], args.filterThreshold[1]), max_iter=args.iterNum,
-                                   tolerance=args.tolerance, chr_offsets=ma.chromosome_offsets(), perchr=args.perchr,
-                                   skip_diagonal=args.skipDiagonal, want_matrix=file_layout, file_layout=file_layout)
+        # every rank maps the same file; when the matrix is untouched each uploads the stored upper triangle, builds the
+        # symmetric store on its GPU and keeps its own rows -- no symmetric matrix on any host
+        up = ma.upper_for_device()
+        res = ice_pipeline_sharded(up if up is not None else ma.matrix, (args.filterThreshold[0], args.filterThreshold[1]),
+                                   max_iter=args.iterNum, tolerance=args.tolerance, chr_offsets=ma.chromosome_offsets(),
+                                   perchr=args.perchr, skip_diagonal=args.skipDiagonal, want_matrix=file_layout,
+                                   file_layout=file_layout, upper_input=up is not None,
+                                   drop_mask=ma.upper_drop_mask() if up is not None else None)
         if rank != 0:
             return
     else:
@@ -297,16 +302,28 @@ def _correct_kr_from_upper(ma, up, args):
 
 
 def _correct_kr(ma, args, world=1, rank=0):
-    up = ma.upper_for_device() if world == 1 else None
-    if up is not None:
+    up = ma.upper_for_device()
+    if up is not None and world == 1:
         return _correct_kr_from_upper(ma, up, args)
-    matrix = ma.matrix.astype(np.float64)
     if world > 1 and not args.perchr and not str(args.outFileName).endswith('.h5'):
         # genome-wide KR to .cool: only the (rescaled) vector is needed -> row blocks over the GPUs
-        res = kr_pipeline_sharded(matrix, rescale=True)
+        if up is not None:
+            drop = ma.upper_drop_mask()
+            res = kr_pipeline_sharded(up, rescale=True, upper_input=True, drop_mask=drop)
+            if rank == 0:
+                print("normalisation factor is {}".format(res['factor']))
+                raw = up
+                if drop is not None:                  # the .cool keeps the raw counts of the selected chromosomes
+                    keep = np.flatnonzero(drop == 0)
+                    raw = sparse.csr_matrix(up[keep, :][:, keep])
+                    raw.sort_indices()
+                ma.install_file_layout(raw, ma.nan_bins, np.asarray(res['x']).reshape(-1, 1))
+            return
+        res = kr_pipeline_sharded(ma.matrix.astype(np.float64), rescale=True)
         print("normalisation factor is {}".format(res['factor']))
-        ma.setCorrectionFactors(np.asmatrix(res['x']).T)
+        ma.setCorrectionFactors(np.asarray(res['x']).reshape(-1, 1))
         return
+    matrix = ma.matrix.astype(np.float64)
     if world > 1 and not args.perchr and rank != 0:
         return      # genome-wide KR to .h5 runs on rank 0's GPU
     if args.perchr:

@@ -305,7 +305,8 @@ class hiCMatrix(object):
         self.matrix = sparse.csr_matrix(newMatrix)
 
     def setCorrectionFactors(self, correction_factors):
-        assert len(correction_factors) == self.matrix.shape[0], "length of correction factors and length of matrix are different."
+        n_bins = self._matrix.shape[0] if self._matrix is not None else len(self.cut_intervals)   # no host symmetrisation
+        assert len(correction_factors) == n_bins, "length of correction factors and length of matrix are different."
         self.correction_factors = correction_factors
 
     # ---- saving ----------------------------------------------------------------------------------------------

@@ -222,8 +222,28 @@ def _gather_upper_to_root(upper, dist, rank, world):
     return sparse.csr_matrix((val, idx.astype(np.int32), indptr), shape=upper.shape)
 
 
+def _open_row_block(m, upper_input, drop_mask, rank, world, device):
+    """this rank's nnz-balanced row block of the symmetric matrix on its GPU -> (DeviceCSR, (a, b), n).
+    ``upper_input``: every rank uploads the file's upper triangle, builds the symmetric store in HBM, deletes the bins of
+    ``drop_mask`` and keeps its own rows (hb_csr_keep_rows): the symmetric matrix never exists on the host."""
+    from .dist import nnz_balanced_partition
+    if upper_input:
+        dev = DeviceCSR.from_upper(m, device=device)
+        if drop_mask is not None:
+            dev.compact(np.ascontiguousarray(drop_mask, dtype=np.uint8))
+        n = dev.n
+        bounds = nnz_balanced_partition(dev.download_indptr(), world)
+        a, b = int(bounds[rank]), int(bounds[rank + 1])
+        dev.keep_rows(a, b)
+        return dev, (a, b), n
+    n = m.shape[0]
+    bounds = nnz_balanced_partition(m.indptr, world)
+    a, b = int(bounds[rank]), int(bounds[rank + 1])
+    return DeviceCSR.from_scipy(m, device=device, row_range=(a, b)), (a, b), n
+
+
 def ice_pipeline_sharded(matrix, filter_threshold, max_iter=500, tolerance=1e-5, chr_offsets=None, perchr=False,
-                         skip_diagonal=False, want_matrix=True, file_layout=False):
+                         skip_diagonal=False, want_matrix=True, file_layout=False, upper_input=False, drop_mask=None):
     """ice_pipeline on row blocks across the initialised torch.distributed group (NCCL).  The symmetry test is the
     exact-symmetry digest screen summed over the blocks (one tiny allreduce); a matrix that is not exactly symmetric is
     rejected (the exact ratio would need the transposed entries of other blocks).
@@ -237,15 +257,16 @@ def ice_pipeline_sharded(matrix, filter_threshold, max_iter=500, tolerance=1e-5,
     dist, rank, world = _dist_env()
     if dist is None or world == 1:
         return ice_pipeline(matrix, filter_threshold, max_iter, tolerance, chr_offsets, perchr, skip_diagonal,
-                            device=torch.cuda.current_device(), want_matrix=want_matrix, file_layout=file_layout)
+                            device=torch.cuda.current_device(), want_matrix=want_matrix, file_layout=file_layout,
+                            upper_input=upper_input, drop_mask=drop_mask)
     device = torch.cuda.current_device()
     m = canonical_csr(matrix, dtype=None)      # values keep the file type: widened to fp64 on the device
-    n = m.shape[0]
     lo, hi = filter_threshold
-    bounds = nnz_balanced_partition(m.indptr, world)
-    a, b = int(bounds[rank]), int(bounds[rank + 1])
+    if upper_input and want_matrix and not file_layout:
+        raise ValueError("with upper_input the corrected matrix is returned in file layout only (file_layout=True)")
     upper_local = None
-    with DeviceCSR.from_scipy(m, device=device, row_range=(a, b)) as dev:
+    dev, (a, b), n = _open_row_block(m, upper_input, drop_mask, rank, world, device)
+    with dev:
         keep_alive = attach_comm(dev, rank, world)
         rs_local, _ = dev.row_stats()
         rs = torch.zeros(n, dtype=torch.float64, device="cuda")
@@ -301,18 +322,19 @@ def ice_pipeline_sharded(matrix, filter_threshold, max_iter=500, tolerance=1e-5,
     return out if rank == 0 else None
 
 
-def kr_pipeline_sharded(matrix, rescale=True):
+def kr_pipeline_sharded(matrix, rescale=True, upper_input=False, drop_mask=None):
     """kr_pipeline on row blocks: x is replicated on every rank; rank 0 also gets the rescale factor."""
     import torch
 
     from .dist import attach_comm, nnz_balanced_partition
     dist, rank, world = _dist_env()
     if dist is None or world == 1:
-        return kr_pipeline(matrix, rescale=rescale, want_matrix=False, device=torch.cuda.current_device())
+        return kr_pipeline(matrix, rescale=rescale, want_matrix=False, device=torch.cuda.current_device(),
+                           upper_input=upper_input, drop_mask=drop_mask)
     device = torch.cuda.current_device()
     m = canonical_csr(matrix, dtype=None)      # values keep the file type: widened to fp64 on the device
-    bounds = nnz_balanced_partition(m.indptr, world)
-    with DeviceCSR.from_scipy(m, device=device, row_range=(int(bounds[rank]), int(bounds[rank + 1]))) as dev:
+    dev, _block, _n = _open_row_block(m, upper_input, drop_mask, rank, world, device)
+    with dev:
         keep_alive = attach_comm(dev, rank, world)
         dev.pack_values()
         x, outer, matvecs, residual = dev.kr()

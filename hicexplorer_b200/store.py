@@ -301,6 +301,16 @@ class DeviceCSR(object):
         check(lib().hb_csr_merge_bins(self._h, ptr(m), int(n_new)))
         self._segments = 1
 
+    def keep_rows(self, row_begin, row_end):
+        """full matrix -> row block [row_begin, row_end) (sharded runs that uploaded the whole upper triangle)"""
+        check(lib().hb_csr_keep_rows(self._h, int(row_begin), int(row_end)))
+
+    def download_indptr(self):
+        """row pointer of the block (int64[n_rows + 1]); the entries stay on the device"""
+        ip = np.empty(self.n_rows + 1, dtype=np.int64)
+        check(lib().hb_csr_download(self._h, ptr(ip), None, None))
+        return ip
+
     def keep_upper(self):
         check(lib().hb_csr_keep_upper(self._h))
 

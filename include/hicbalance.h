@@ -129,6 +129,10 @@ HB_API int hb_csr_keep_cis(hb_csr* h);
  * the work already enqueued on `stream` and complete (stream-ordered) when it returns.  The Python
  * host passes a torch.distributed (NCCL) all_reduce here.  With comm set, hb_ice_run / hb_kr_run
  * accept a row block instead of the full matrix; the O(n) vector work runs replicated on every rank. */
+/* Turn a handle that holds the FULL matrix into the row block [row_begin, row_end) of it (global column ids kept), as if
+ * it had been created with row0 = row_begin: how a rank of a sharded run gets its block when the whole upper triangle
+ * was uploaded and symmetrised on the device (hb_csr_create_upper) -- no symmetric matrix on the host. */
+HB_API int hb_csr_keep_rows(hb_csr* h, int64_t row_begin, int64_t row_end);
 typedef int (*hb_allreduce_fn)(void* ctx, void* d_buf, int64_t count, void* stream);
 HB_API int hb_set_comm(hb_csr* h, int rank, int world, hb_allreduce_fn fn, void* ctx);
 

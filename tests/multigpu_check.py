@@ -112,6 +112,30 @@ def main():
         check("CLI under torchrun: matrix written from per-rank file-layout blocks equals the single-GPU result",
               np.array_equal(got_up.indptr, want.indptr) and np.array_equal(got_up.indices, want.indices) and
               np.allclose(got_up.data, want.data, rtol=1e-12, atol=0))
+    # genome-wide KR to .cool under torchrun: row blocks built on the device from the stored upper triangle
+    outkc = os.path.join(tmp, "mg_kr.cool")
+    cli(["correct", "-m", src, "-o", outkc, "--correctionMethod", "KR"])
+    if rank == 0:
+        kc = hiCMatrix(outkc)
+        kr1 = kr_pipeline(full, rescale=True, want_matrix=False, device=local)
+        check("CLI KR under torchrun (.cool): factors bit-identical to 1 GPU, counts untouched",
+              np.array_equal(np.asarray(kc.correction_factors).ravel(), kr1["x"]) and abs(kc.matrix - full).sum() == 0)
+    # a chromosome subset in file order, selected on the device on every rank before the rows are dealt out
+    outs = os.path.join(tmp, "mg_sub.h5")
+    cli(["correct", "-m", src, "-o", outs, "--correctionMethod", "ICE", "--filterThreshold", "-1.5", "5", "--chromosomes",
+         "2", "3", "7"])
+    if rank == 0:
+        os.environ["WORLD_SIZE"] = "1"
+        outs1 = os.path.join(tmp, "mg_sub_1gpu.h5")
+        cli(["correct", "-m", src, "-o", outs1, "--correctionMethod", "ICE", "--filterThreshold", "-1.5", "5", "--chromosomes",
+             "2", "3", "7", "--device", str(local)])
+        os.environ["WORLD_SIZE"] = str(world)
+        a, b = hiCMatrix(outs), hiCMatrix(outs1)
+        check("CLI --chromosomes subset under torchrun: file equals the single-GPU run",
+              np.array_equal(np.isnan(np.asarray(a.correction_factors)), np.isnan(np.asarray(b.correction_factors))) and
+              np.array_equal(np.nan_to_num(np.asarray(a.correction_factors)), np.nan_to_num(np.asarray(b.correction_factors))) and
+              (a.matrix != b.matrix).nnz == 0)
+    dist.barrier()
     # --perchr KR: whole chromosomes dealt to the ranks (LPT), no communication; rank 0 assembles the file
     outk = os.path.join(tmp, "mg_kr_perchr.h5")
     cli(["correct", "-m", src, "-o", outk, "--correctionMethod", "KR", "--perchr"])

@@ -118,3 +118,20 @@ def test_from_upper_with_rows_beyond_the_shared_memory_classes():
         got = dev.download()
     assert np.array_equal(got.indptr, full.indptr) and np.array_equal(got.indices, full.indices)
     np.testing.assert_array_equal(got.data, full.data)
+
+
+def test_keep_rows_equals_a_row_block_upload():
+    """sharded runs build their block on the device: upper triangle -> symmetric store -> hb_csr_keep_rows"""
+    full = random_hic(1500, 0.08, 17, empty_frac=0.01)
+    up = sparse.triu(full, 0, format="csr")
+    for a, b in [(0, 400), (400, 1100), (1100, 1500), (700, 700)]:
+        with DeviceCSR.from_upper(up) as dev, DeviceCSR.from_scipy(full, row_range=(a, b)) as ref:
+            dev.keep_rows(a, b)
+            assert dev.dims() == ref.dims()
+            got, want = dev.download(), ref.download()
+            assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
+            np.testing.assert_array_equal(got.data, want.data)
+            rs_got, dg_got = dev.row_stats()
+            rs_want, dg_want = ref.row_stats()
+            np.testing.assert_array_equal(rs_got, rs_want)
+            np.testing.assert_array_equal(dg_got, dg_want)
