@@ -105,7 +105,8 @@ def correct_subparser():
 
 
 def _is_cooler(path):
-    return str(path).endswith('.cool') or '.cool::' in str(path) or str(path).endswith('.mcool')
+    fname = str(path).partition('::')[0]
+    return fname.endswith('.cool') or fname.endswith('.mcool')
 
 
 def main(args=None):

@@ -45,7 +45,8 @@ class hiCMatrix(object):
         self.chrBinBoundaries = OrderedDict()
         self.matrixFileName = pMatrixFile
         if pMatrixFile is not None:
-            if str(pMatrixFile).endswith(".cool") or ".cool::" in str(pMatrixFile) or str(pMatrixFile).endswith(".mcool"):
+            fname = str(pMatrixFile).partition("::")[0]
+            if fname.endswith(".cool") or fname.endswith(".mcool"):
                 self._load_cool(pMatrixFile, pChrnameList)
             else:
                 self._load_h5(pMatrixFile)
@@ -110,7 +111,11 @@ class hiCMatrix(object):
         self.correction_factors = f["correction_factors"].read() if "correction_factors" in f else None
 
     def _load_cool(self, path, chrnames):
-        f = hdf5lite.File(path)
+        # cooler URIs: "file.mcool::/resolutions/10000" selects one matrix of a multi-resolution file
+        fname, _sep, group = str(path).partition("::")
+        f = hdf5lite.File(fname)
+        if group.strip("/"):
+            f = f[group]
         names = [_to_str(c) for c in f["chroms/name"].read()]
         chrom_id = f["bins/chrom"].read()
         start = f["bins/start"].read()

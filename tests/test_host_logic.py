@@ -141,3 +141,26 @@ def test_oracle_trunc_trans_semantics():
     assert mx == np.percentile([9, 2, 9, 2], 50.0) and (same != m).nnz == 0
     clipped, _ = ice_oracle.trunc_trans(m, [0, 2, 4], 50.0, clip=True)
     assert clipped[0, 2] == mx and clipped[2, 0] == mx and clipped[0, 1] == 1 and clipped[1, 3] == 2
+
+
+def test_mcool_uri_selects_a_resolution(tmp_path):
+    """`file.mcool::/resolutions/N` (cooler URI syntax) loads the matrix stored under that group"""
+    import numpy as np
+    from hicexplorer_b200 import hdf5lite
+    ma = hiCMatrix()
+    up = sparse.triu(sparse.csr_matrix(np.arange(36, dtype=np.float64).reshape(6, 6) % 5), 0, format="csr")
+    ma.matrix = sparse.csr_matrix(up + sparse.triu(up, 1).T)
+    ma.cut_intervals = [("chr1" if i < 4 else "chr2", (i % 4) * 100, (i % 4 + 1) * 100, 1.0) for i in range(6)]
+    ma._index_intervals()
+    single = str(tmp_path / "single.cool")
+    ma.save(single)
+    src = hdf5lite.File(single)
+    w = hdf5lite.Writer({"format": "HDF5::MCOOL"})
+    for grp in ("bins", "chroms", "indexes", "pixels"):
+        for name in src[grp].keys():
+            ds = src[grp + "/" + name]
+            w.dataset("/resolutions/100/%s/%s" % (grp, name), ds.read(), enum=ds.enum)
+    path = str(tmp_path / "multi.mcool")
+    w.save(path)
+    got = hiCMatrix(path + "::/resolutions/100")
+    assert (got.matrix != ma.matrix).nnz == 0 and got.getChrNames() == ["chr1", "chr2"]
