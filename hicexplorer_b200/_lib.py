@@ -89,6 +89,8 @@ SIGNATURES = {
     "hb_diag_zero": (c_int, [vp]),
     "hb_csr_keep_upper": (c_int, [vp]),
     "hb_csr_keep_rows": (c_int, [vp, c_i64, c_i64]),
+    "hb_csr_symmetrize_upper": (c_int, [vp]),
+    "hb_csr_shifted_copy": (c_int, [P(vp), vp, c_i64, c_i64]),
     "hb_csr_merge_bins": (c_int, [vp, vp, c_i64]),
     "hb_symmetry": (c_int, [vp, P(c_dbl)]),
     "hb_ice_run": (c_int, [vp, c_int, c_dbl, vp, vp, vp]),

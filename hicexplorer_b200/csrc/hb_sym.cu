@@ -224,7 +224,21 @@ int hb_csr_create_upper_typed(hb_csr** out, int64_t n, int64_t nnz_upper, const 
     // upload the triangle with the ordinary constructor, then replace the store by its symmetric completion
     int rc = hb_csr_create_typed(out, n, n, 0, nnz_upper, indptr, indices, 0, data, value_kind, device);
     if (rc != HB_OK) return rc;
-    hb_csr* h = *out;
+    rc = hb_csr_symmetrize_upper(*out);
+    if (rc != HB_OK) {
+        hb_csr_destroy(*out);
+        *out = nullptr;
+    }
+    return rc;
+}
+
+int hb_csr_symmetrize_upper(hb_csr* h) {
+    HB_REQUIRE(h != nullptr, "null handle");
+    HB_REQUIRE(h->row0 == 0 && h->n_rows == h->n_cols, "hb_csr_symmetrize_upper needs the full (upper-triangular) matrix");
+    int rc = hb_use_device(h);
+    if (rc) return rc;
+    hb_drop_pack(h);
+    const int64_t n = h->n_cols;
     cudaStream_t s = h->stream;
     unsigned int *d_low = nullptr, *d_cursor = nullptr, *d_flags = nullptr;
     int64_t *d_total = nullptr, *d_ptr = nullptr, *d_big_rows = nullptr, *d_big_off = nullptr;
@@ -341,9 +355,112 @@ fail:
     cudaFree(d_ptr);
     cudaFree(d_idx);
     cudaFree(d_val);
-    hb_csr_destroy(h);
-    *out = nullptr;
     return rc;
+}
+
+// ---- shifted copy: C[i + dr][j + dc] = A[i][j] for the targets inside the n x n frame (one term of the running-window
+// merge of hicMergeMatrixBins.py:88-186, which sums (2h+1)^2 shifted copies of the upper triangle) ---------------------
+__global__ void hb_shift_count_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, int64_t n, int dr,
+                                      int dc, int64_t* __restrict__ cnt) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t out_row = gwarp; out_row < n; out_row += nwarps) {
+        const int64_t src = out_row - dr;
+        long long c = 0;
+        if (src >= 0 && src < n) {
+            for (int64_t k = indptr[src] + lane; k < indptr[src + 1]; k += 32) {
+                const int64_t j = (int64_t)idx[k] + dc;
+                c += (j >= 0 && j < n) ? 1 : 0;
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0) cnt[out_row] = c;
+    }
+}
+
+__global__ void hb_shift_fill_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx,
+                                     const double* __restrict__ val, int64_t n, int dr, int dc, const int64_t* __restrict__ out_ptr,
+                                     int32_t* __restrict__ out_idx, double* __restrict__ out_val) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t out_row = gwarp; out_row < n; out_row += nwarps) {
+        const int64_t src = out_row - dr;
+        if (src < 0 || src >= n) continue;
+        int64_t w = out_ptr[out_row];
+        const int64_t s = indptr[src], e = indptr[src + 1];
+        for (int64_t base = s; base < e; base += 32) {
+            const int64_t k = base + lane;
+            int64_t j = -1;
+            double v = 0.0;
+            if (k < e) {
+                j = (int64_t)idx[k] + dc;
+                v = val[k];
+            }
+            const bool kp = j >= 0 && j < n;      // columns stay ascending: a shift keeps the order
+            const unsigned int bal = __ballot_sync(0xffffffffu, kp);
+            if (kp) {
+                const int64_t pos = w + __popc(bal & ((1u << lane) - 1u));
+                out_idx[pos] = (int32_t)j;
+                out_val[pos] = v;
+            }
+            w += __popc(bal);
+        }
+    }
+}
+
+int hb_csr_shifted_copy(hb_csr** out, const hb_csr* src, int64_t dr, int64_t dc) {
+    HB_REQUIRE(out != nullptr && src != nullptr, "bad arguments");
+    HB_REQUIRE(src->row0 == 0 && src->n_rows == src->n_cols && src->phase == 0, "hb_csr_shifted_copy needs a full matrix");
+    const int64_t n = src->n_cols;
+    HB_REQUIRE(dr > -n && dr < n && dc > -n && dc < n, "shift outside the matrix");
+    int rc = hb_use_device(src);
+    if (rc) return rc;
+    cudaStream_t s = src->stream;
+    int64_t *d_cnt = nullptr, *d_ptr = nullptr;
+    int32_t* d_idx = nullptr;
+    double* d_val = nullptr;
+    int64_t nnz = 0;
+    const size_t nn = (size_t)(n > 0 ? n : 1);
+    HbScratch scratch;
+    HB_CUDA(scratch.alloc(&d_cnt, sizeof(int64_t) * (nn + 1)));
+    HB_CUDA(cudaMalloc(&d_ptr, sizeof(int64_t) * (nn + 1)));
+    cudaError_t e = cudaMemsetAsync(d_cnt, 0, sizeof(int64_t) * (nn + 1), s);
+    if (e == cudaSuccess && n > 0) {
+        hb_shift_count_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(src->d_indptr, src->d_indices, n, (int)dr, (int)dc, d_cnt);
+        g_hb_launches.fetch_add(1);
+    }
+    if (e == cudaSuccess) {
+        hb_scan_kernel<int64_t><<<1, 1024, 0, s>>>(d_cnt, d_ptr, n);
+        g_hb_launches.fetch_add(1);
+        e = cudaMemcpyAsync(&nnz, d_ptr + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = cudaMalloc(&d_idx, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1) + 16);
+    if (e == cudaSuccess) e = cudaMalloc(&d_val, sizeof(double) * (size_t)(nnz > 0 ? nnz : 1) + 16);
+    if (e == cudaSuccess && n > 0 && nnz > 0) {
+        hb_shift_fill_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(src->d_indptr, src->d_indices, src->d_data, n, (int)dr, (int)dc, d_ptr,
+                                                            d_idx, d_val);
+        g_hb_launches.fetch_add(1);
+        e = cudaStreamSynchronize(s);
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        cudaFree(d_ptr);
+        cudaFree(d_idx);
+        cudaFree(d_val);
+        return hb_cuda_fail(e, "shifted copy", __FILE__, __LINE__);
+    }
+    rc = hb_dev_csr_wrap(out, n, n, 0, nnz, d_ptr, d_idx, d_val, src->device);
+    if (rc != HB_OK) {
+        cudaFree(d_ptr);
+        cudaFree(d_idx);
+        cudaFree(d_val);
+        return rc;
+    }
+    (*out)->owns_csr = true;   // the new handle owns the arrays made here
+    return HB_OK;
 }
 
 int hb_ice_scaled_upper(hb_csr* h, const int64_t* orig_ids, int64_t n_orig, int64_t* nnz_out, int64_t* indptr,

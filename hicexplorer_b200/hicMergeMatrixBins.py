@@ -2,8 +2,10 @@
 (hicexplorer/hicMergeMatrixBins.py:16-283), the summation on the GPU (``hb_csr_merge_bins``).
 
 This is the step right before correction in the reference's documented workflow.
-``--runningWindow`` (a smoothing variant that keeps the resolution) is not implemented and exits with an explanation;
-``--numBins`` up to 1024 (more than 32 bins per group are merged in two exact device steps).
+``--numBins`` up to 1024 (more than 32 bins per group are merged in two exact device steps).  ``--runningWindow``
+(hicMergeMatrixBins.py:88-186: every cell becomes the sum of the (numBins x numBins) box around it, taken over the upper
+triangle, resolution unchanged) runs on the device as the sum of the numBins^2 shifted copies of the upper triangle
+(``hb_csr_shifted_copy`` + ``hb_csr_add``), cut back to the upper triangle and mirrored (``hb_csr_symmetrize_upper``).
 """
 import argparse
 import logging
@@ -94,13 +96,44 @@ def merge_bins(hic, num_bins, device=0):
     return hic
 
 
+def running_window_merge(hic, num_bins, device=0):
+    """'running window' merge that keeps the resolution (hicMergeMatrixBins.py:88-186): with U = upper triangle,
+    new = sum over (dr, dc) in [-h, h]^2 of U shifted by (dr, dc); result = triu(new) mirrored.  ``num_bins`` must be odd."""
+    hic = remove_nans_if_needed(hic)
+    if num_bins == 1:
+        return hic
+    assert num_bins % 2 == 1, "num_bins has to be an odd number"
+    half = (num_bins - 1) // 2
+    dtype = hic.matrix.dtype
+    with DeviceCSR.from_scipy(hic.matrix, device=device) as base:
+        base.keep_upper()
+        total = base.shifted_copy(0, 0)
+        try:
+            for dr in range(-half, half + 1):
+                for dc in range(-half, half + 1):
+                    if dr == 0 and dc == 0:
+                        continue
+                    with base.shifted_copy(dr, dc) as term:
+                        total.add(term)
+            total.keep_upper()
+            total.symmetrize_upper()
+            merged = total.download()
+        finally:
+            total.close()
+    if dtype.kind in "iu":
+        merged = merged.astype(dtype)
+    hic.matrix = merged
+    hic.nan_bins = np.flatnonzero(np.asarray(hic.matrix.sum(axis=0)).ravel() == 0)
+    return hic
+
+
 def main(args=None):
     args = parse_arguments().parse_args(args)
     hic = hm.hiCMatrix(args.matrix)
     if args.runningWindow:
-        log.error('--runningWindow is not implemented in the B200 build')
-        sys.exit(1)
-    merged = merge_bins(hic, args.numBins, device=args.device)
+        merged = running_window_merge(hic, args.numBins, device=args.device)
+    else:
+        merged = merge_bins(hic, args.numBins, device=args.device)
     nan_bins = merged.nan_bins
     merged.save(args.outFileName)
     return nan_bins

@@ -311,6 +311,16 @@ class DeviceCSR(object):
         check(lib().hb_csr_download(self._h, ptr(ip), None, None))
         return ip
 
+    def symmetrize_upper(self):
+        """upper-triangular store -> full symmetric store (M + triu(M, 1)^T), on the device"""
+        check(lib().hb_csr_symmetrize_upper(self._h))
+
+    def shifted_copy(self, dr, dc):
+        """new store C with C[i + dr][j + dc] = self[i][j] (targets outside the frame dropped)"""
+        h = ctypes.c_void_p()
+        check(lib().hb_csr_shifted_copy(ctypes.byref(h), self._h, int(dr), int(dc)))
+        return DeviceCSR(h, self.device)
+
     def keep_upper(self):
         check(lib().hb_csr_keep_upper(self._h))
 

@@ -102,6 +102,12 @@ HB_API int hb_csr_create_upper_typed(hb_csr** out, int64_t n, int64_t nnz_upper,
  * columns (deterministic layout, identical to a host-side fill).  Entries below the diagonal are an error. */
 HB_API int hb_csr_create_upper(hb_csr** out, int64_t n, int64_t nnz_upper, const int64_t* indptr, const int32_t* indices,
                         const double* data, int device);
+/* The device half of hb_csr_create_upper on a handle that already holds an upper-triangular matrix (e.g. after
+ * hb_csr_keep_upper): the store becomes the full symmetric matrix M + triu(M, 1)^T. */
+HB_API int hb_csr_symmetrize_upper(hb_csr* h);
+/* New store C with C[i + dr][j + dc] = A[i][j] for the targets inside the frame: one term of the running-window merge
+ * (hicMergeMatrixBins.py:88-186 sums (2h+1)^2 shifted copies of the upper triangle). */
+HB_API int hb_csr_shifted_copy(hb_csr** out, const hb_csr* src, int64_t dr, int64_t dc);
 /* wrap device arrays already in HBM (not copied, not owned). indptr must be block-local (indptr[0]==0). */
 HB_API int hb_dev_csr_wrap(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t row0, int64_t nnz,
                     const int64_t* d_indptr, const int32_t* d_indices, const double* d_data, int device);

@@ -58,3 +58,22 @@ def merge_bins(matrix, intervals, num_bins):
     merged = reduce(matrix, bin_map, len(new_intervals))
     nan_bins = np.flatnonzero(np.asarray(merged.sum(axis=0)).ravel() == 0)
     return merged, new_intervals, nan_bins, bin_map
+
+
+def running_window(matrix, num_bins):
+    """``running_window_merge`` (hicexplorer/hicMergeMatrixBins.py:88-186) restated: the reference concatenates the
+    num_bins^2 shifted copies of the upper triangle's COO triplets and drops the ones that leave the frame -- that is
+    S U S^T with the banded 0/1 matrix S[a, i] = (|a - i| <= h) -- then keeps triu and mirrors it."""
+    if num_bins == 1:
+        return sparse.csr_matrix(matrix)
+    assert num_bins % 2 == 1, "num_bins has to be an odd number"
+    half = (num_bins - 1) // 2
+    n = matrix.shape[0]
+    offsets = list(range(-half, half + 1))
+    band = sparse.diags([np.ones(n - abs(d), dtype=matrix.dtype) for d in offsets], offsets, format="csr", dtype=matrix.dtype)
+    upper = sparse.triu(matrix, 0, format="csr")
+    new = sparse.triu(band @ upper @ band.T, 0, format="csr")
+    full = sparse.csr_matrix(new + new.T - sparse.diags(new.diagonal(), dtype=matrix.dtype)).astype(matrix.dtype)
+    full.eliminate_zeros()
+    full.sort_indices()
+    return full

@@ -76,3 +76,41 @@ def test_merge_then_correct_workflow():
         bias, iters, _ = dev.ice(100, 1e-5)
     np.testing.assert_allclose(bias, ref["bias"], rtol=1e-9)
     assert abs(int(iters[0]) - ref["iterations"]) <= 1
+
+
+@pytest.mark.parametrize("n,k,seed", [(200, 3, 0), (777, 5, 1), (64, 7, 2), (30, 1, 3)])
+def test_running_window_matches_oracle(n, k, seed):
+    """--runningWindow (hicMergeMatrixBins.py:88-186): sum of the k^2 shifted copies of the upper triangle on the device"""
+    from hicexplorer_b200.hicMergeMatrixBins import running_window_merge
+    m = random_hic(n, 0.1, seed, empty_frac=0.03).astype(np.int32)
+    want = merge_oracle.running_window(m, k)
+    hic = hiCMatrix()
+    hic.matrix = m.copy()
+    hic.cut_intervals = [("chr1", i * 10, (i + 1) * 10, 1.0) for i in range(n)]
+    hic._index_intervals()
+    got = running_window_merge(hic, k).matrix
+    got.sort_indices()
+    assert got.dtype == want.dtype
+    assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
+    np.testing.assert_array_equal(got.data, want.data)
+
+
+def test_shifted_copy_and_symmetrize_in_place():
+    from hicexplorer_b200.store import DeviceCSR
+    m = random_hic(300, 0.1, 9)
+    with DeviceCSR.from_scipy(m) as dev:
+        for dr, dc in [(0, 0), (1, -2), (-3, 3), (5, 0)]:
+            with dev.shifted_copy(dr, dc) as sh:
+                got = sh.download()
+            coo = m.tocoo()
+            r, c = coo.row + dr, coo.col + dc
+            ok = (r >= 0) & (r < 300) & (c >= 0) & (c < 300)
+            want = sparse.csr_matrix((coo.data[ok], (r[ok], c[ok])), shape=m.shape)
+            want.sort_indices()
+            assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
+            np.testing.assert_array_equal(got.data, want.data)
+        dev.keep_upper()
+        dev.symmetrize_upper()
+        back = dev.download()
+    assert np.array_equal(back.indices, m.indices)
+    np.testing.assert_array_equal(back.data, m.data)

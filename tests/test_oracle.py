@@ -259,3 +259,25 @@ def test_transform_reference_golden_files_to_their_own_tolerance(key, file_key):
     t = load_golden("transform_small.npz")
     assert np.array_equal(t[key + "_indices"], t[file_key + "_indices"])
     np.testing.assert_array_almost_equal(t[key + "_data"], t[file_key + "_data"], decimal=0)
+
+
+@pytest.mark.parametrize("k", [3, 5])
+def test_running_window_oracle_equals_the_reference_function(k):
+    """oracle/merge_oracle.running_window vs hicMergeMatrixBins.running_window_merge imported from /root/reference"""
+    from oracle import merge_oracle, ref_import
+    if not ref_import.available():
+        pytest.skip("reference tree not present")
+    ref_import.load()
+    import hicexplorer.hicMergeMatrixBins as ref_mb
+    rng = np.random.default_rng(k)
+    a = sparse.random(90, 90, 0.12, random_state=rng, format="csr")
+    a = sparse.csr_matrix(np.round((a + a.T) * 10)).astype(np.int32)
+
+    class _H(object):
+        pass
+    h = _H()
+    h.matrix = a.copy()
+    h.nan_bins = []
+    want = sparse.csr_matrix(ref_mb.running_window_merge(h, k).matrix)
+    got = merge_oracle.running_window(a, k)
+    assert (want != got).nnz == 0 and got.dtype == want.dtype
