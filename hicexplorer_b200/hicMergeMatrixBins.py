@@ -9,7 +9,6 @@ triangle, resolution unchanged) runs on the device as the sum of the numBins^2 s
 """
 import argparse
 import logging
-import sys
 
 import numpy as np
 

@@ -12,7 +12,6 @@
 Run: python tools/bench_configs.py CONFIG            (1 GPU)
      python -m torch.distributed.run --nproc-per-node N ... tools/bench_configs.py CONFIG
 Prints one JSON line per config on rank 0."""
-import ctypes
 import json
 import os
 import sys

@@ -9,7 +9,6 @@ import sys
 import time
 
 import numpy as np
-from scipy import sparse
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
