@@ -180,7 +180,20 @@ def cpu_ice_baseline(workload, seconds_budget=25.0, use_gpu_generator=False):
     ice_oracle.ice(m.copy(), max_iter=1 + k, tolerance=0.0)
     t2 = time.time() - t0
     per_iter = max((t2 - t1) / k, 1e-9)
-    return {"value": nnz / per_iter, "unit": "nnz/s", "cores": 1, "kind": "port",
+    # the same loop restated in C on every host core (pthreads; the reference itself is single-threaded numpy and cannot
+    # do this): an upper bound on what parallelising the reference's algorithm on this host would give
+    all_cores = None
+    try:
+        from oracle import hic_cpu as _hc
+        cores = os.cpu_count() or 1
+        _hc.ice_loop_mt(m, 1, 0.0, threads=cores)
+        _b, it_mt, _d, _data, secs = _hc.ice_loop_mt(m, 8, 0.0, threads=cores)
+        all_cores = {"value": nnz * it_mt / secs, "unit": "nnz/s", "cores": cores, "kind": "port",
+                     "what": "oracle/hic_cpu.c ice_loop_coo_mt: the reference's loop (row sums + two-factor rescale of "
+                             "every entry) in C with pthreads, %d iterations on the same sample" % it_mt}
+    except Exception as exc:
+        all_cores = {"error": repr(exc)}
+    return {"value": nnz / per_iter, "unit": "nnz/s", "cores": 1, "kind": "port", "c_port_all_cores": all_cores,
             "iters_per_s": 1.0 / per_iter, "host_cores_available": os.cpu_count(),
             "sample": "chromosome 1 of the same synthetic layout (%d bins, %d stored entries, same band/d0); "
                       "%d loop iterations of the reference's numpy ICE (oracle/ice_oracle.py), setup excluded; "

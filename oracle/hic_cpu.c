@@ -21,6 +21,102 @@
 #include <omp.h>
 #endif
 
+/* ---- the same loop on all host cores with plain pthreads (this image has no libgomp) ---------------------------------
+ * The reference itself cannot use more than one core (numpy ufuncs + scipy's coo_matvec are single-threaded); this is the
+ * "what if the reference's algorithm were parallelised" figure bench.py reports next to the single-threaded port.
+ * COO triplets must be sorted by row (a CSR expanded to COO is): thread t owns the entries of a contiguous row range,
+ * so the row sums need no atomics and come out in the same order as the serial loop. */
+#include <pthread.h>
+
+typedef struct {
+    int64_t k0, k1;
+    const int32_t* row;
+    const int32_t* col;
+    double* data;
+    double* s;
+    int phase; /* 0: row sums, 1: rescale */
+    int overflow;
+} ice_mt_job;
+
+static void* ice_mt_worker(void* arg) {
+    ice_mt_job* j = (ice_mt_job*)arg;
+    if (j->phase == 0) {
+        for (int64_t k = j->k0; k < j->k1; ++k) j->s[j->row[k]] += j->data[k];
+    } else {
+        int of = 0;
+        for (int64_t k = j->k0; k < j->k1; ++k) {
+            double v = j->data[k];
+            v *= j->s[j->row[k]];
+            v *= j->s[j->col[k]];
+            j->data[k] = v;
+            if (v > 1e100) of = 1;
+        }
+        j->overflow = of;
+    }
+    return NULL;
+}
+
+int ice_loop_coo_mt(int64_t n, int64_t nnz, const int32_t* row, const int32_t* col, double* data, double* bias, int max_iter,
+                    double tol, int threads, double* deviation_out) {
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    double* s = (double*)malloc(sizeof(double) * (size_t)n);
+    ice_mt_job* jobs = (ice_mt_job*)calloc((size_t)threads, sizeof(ice_mt_job));
+    pthread_t* th = (pthread_t*)calloc((size_t)threads, sizeof(pthread_t));
+    /* entry ranges cut at row boundaries */
+    for (int t = 0; t < threads; ++t) {
+        int64_t k = nnz * t / threads;
+        while (t > 0 && k > 0 && k < nnz && row[k] == row[k - 1]) ++k;
+        jobs[t].k0 = k;
+        jobs[t].row = row;
+        jobs[t].col = col;
+        jobs[t].data = data;
+        jobs[t].s = s;
+    }
+    for (int t = 0; t < threads; ++t) jobs[t].k1 = t + 1 < threads ? jobs[t + 1].k0 : nnz;
+    int done = 0, overflow = 0;
+    double dev = NAN;
+    for (int it = 0; it < max_iter && !overflow; ++it) {
+        done++;
+        memset(s, 0, sizeof(double) * (size_t)n);
+        for (int phase = 0; phase < 2; ++phase) {
+            if (phase == 1) {
+                double tot = 0.0;
+                int64_t cnt = 0;
+                for (int64_t i = 0; i < n; ++i)
+                    if (s[i] != 0.0) {
+                        tot += s[i];
+                        cnt++;
+                    }
+                const double mean = tot / (double)cnt;
+                dev = 0.0;
+                for (int64_t i = 0; i < n; ++i) {
+                    s[i] = s[i] / mean;
+                    bias[i] *= s[i];
+                    const double d = fabs(s[i] - 1.0);
+                    if (d > dev || d != d) dev = d;
+                    s[i] = 1.0 / s[i];
+                }
+            }
+            for (int t = 0; t < threads; ++t) {
+                jobs[t].phase = phase;
+                jobs[t].overflow = 0;
+                if (t > 0) pthread_create(&th[t], NULL, ice_mt_worker, &jobs[t]);
+            }
+            ice_mt_worker(&jobs[0]);
+            for (int t = 1; t < threads; ++t) pthread_join(th[t], NULL);
+            if (phase == 1)
+                for (int t = 0; t < threads; ++t) overflow |= jobs[t].overflow;
+        }
+        if (dev < tol) break;
+    }
+    free(s);
+    free(jobs);
+    free(th);
+    if (deviation_out) *deviation_out = dev;
+    return overflow ? -1 : done;
+}
+
 /* returns iterations done; *deviation_out = last max|s-1|; -1 on overflow (> 1e100) */
 int ice_loop_coo(int64_t n, int64_t nnz, const int32_t* row, const int32_t* col, double* data, double* bias,
                  int max_iter, double tol, int threads, double* deviation_out) {

@@ -30,6 +30,8 @@ def lib():
         L.ice_loop_coo.restype = ctypes.c_int
         L.ice_loop_coo.argtypes = [ctypes.c_int64, ctypes.c_int64, vp, vp, vp, vp, ctypes.c_int, ctypes.c_double,
                                    ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+        L.ice_loop_coo_mt.restype = ctypes.c_int
+        L.ice_loop_coo_mt.argtypes = L.ice_loop_coo.argtypes
         L.kr_matvec.restype = None
         L.kr_matvec.argtypes = [ctypes.c_int64, vp, vp, vp, vp, vp, vp, vp, ctypes.c_double, vp, ctypes.c_int]
         L.synth_generate.restype = ctypes.c_int64
@@ -68,6 +70,24 @@ def ice_loop(matrix, max_iter, tol=0.0, threads=1):
     it = lib().ice_loop_coo(matrix.shape[0], len(data), _p(row), _p(col), _p(data), _p(bias), int(max_iter),
                             float(tol), int(threads), ctypes.byref(dev))
     return bias, it, dev.value, data
+
+
+def ice_loop_mt(matrix, max_iter, tol=0.0, threads=0):
+    """ice_loop on all host cores (pthreads; row sums in the serial order, so the results equal ice_loop's bit for bit).
+    Returns (bias, iterations, deviation, scaled data, seconds spent inside the C loop)."""
+    import os
+    import time
+    coo = sparse.coo_matrix(sparse.csr_matrix(matrix))          # row-sorted triplets
+    row = np.ascontiguousarray(coo.row, dtype=np.int32)
+    col = np.ascontiguousarray(coo.col, dtype=np.int32)
+    data = np.ascontiguousarray(coo.data, dtype=np.float64).copy()
+    bias = np.ones(matrix.shape[0], dtype=np.float64)
+    dev = ctypes.c_double()
+    threads = int(threads) or (os.cpu_count() or 1)
+    t0 = time.time()
+    it = lib().ice_loop_coo_mt(matrix.shape[0], len(data), _p(row), _p(col), _p(data), _p(bias), int(max_iter), float(tol),
+                               threads, ctypes.byref(dev))
+    return bias, it, dev.value, data, time.time() - t0
 
 
 def kr_matvec(csr, u, x, v=None, p=None, eps=1e-5, threads=0):

@@ -281,3 +281,17 @@ def test_running_window_oracle_equals_the_reference_function(k):
     want = sparse.csr_matrix(ref_mb.running_window_merge(h, k).matrix)
     got = merge_oracle.running_window(a, k)
     assert (want != got).nnz == 0 and got.dtype == want.dtype
+
+
+def test_c_port_on_all_cores_equals_the_serial_c_loop():
+    """oracle/hic_cpu.c: the pthread version of the reference's loop (bench.py's all-cores CPU figure) keeps the serial
+    summation order, so it equals the single-threaded loop bit for bit"""
+    from oracle import hic_cpu
+    from tests.helpers import random_hic
+    m = random_hic(900, 0.1, 3, integer=False)
+    b1, it1, d1, data1 = hic_cpu.ice_loop(m, 12, 0.0, threads=1)
+    for threads in (2, 5):
+        b, it, d, data, _secs = hic_cpu.ice_loop_mt(m, 12, 0.0, threads=threads)
+        assert it == it1 and d == d1
+        np.testing.assert_array_equal(b, b1)
+        np.testing.assert_array_equal(data, data1)
