@@ -84,6 +84,7 @@ SIGNATURES = {
     "hb_scrub": (c_int, [vp, vp]),
     "hb_csr_pack_values": (c_int, [vp, P(c_int)]),
     "hb_row_stats": (c_int, [vp, vp, vp]),
+    "hb_row_stats_cis": (c_int, [vp, vp, vp]),
     "hb_mad_filter": (c_int, [vp, c_dbl, c_dbl, vp, vp, vp, vp]),
     "hb_csr_compact": (c_int, [vp, vp]),
     "hb_diag_zero": (c_int, [vp]),

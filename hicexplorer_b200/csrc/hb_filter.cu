@@ -657,7 +657,13 @@ int hb_scrub(hb_csr* h, int64_t counts[2]) {
     return HB_OK;
 }
 
-int hb_row_stats(hb_csr* h, double* row_sum, double* diag) {
+static int hb_row_stats_impl(hb_csr* h, double* row_sum, double* diag, int cis_only);
+
+int hb_row_stats(hb_csr* h, double* row_sum, double* diag) { return hb_row_stats_impl(h, row_sum, diag, 0); }
+
+int hb_row_stats_cis(hb_csr* h, double* row_sum, double* diag) { return hb_row_stats_impl(h, row_sum, diag, 1); }
+
+static int hb_row_stats_impl(hb_csr* h, double* row_sum, double* diag, int cis_only) {
     HB_REQUIRE(h != nullptr, "null handle");
     int rc = hb_use_device(h);
     if (rc) return rc;
@@ -670,7 +676,7 @@ int hb_row_stats(hb_csr* h, double* row_sum, double* diag) {
     HB_CUDA(cudaMemsetAsync(d_rs, 0, sizeof(double) * 2 * n, s));
     if (h->n_rows > 0) {
         hb_row_stats_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, h->n_rows, h->row0,
-                                                           h->d_seg_off, h->nseg, 0, d_rs, d_dg);
+                                                           h->d_seg_off, h->nseg, cis_only, d_rs, d_dg);
         HB_LAUNCH_CHECK();
     }
     cudaError_t e = cudaStreamSynchronize(s);

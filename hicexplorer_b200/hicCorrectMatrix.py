@@ -7,8 +7,11 @@ Differences, all additive or documented:
   * the ICE branch uploads the matrix once and runs zero-bin masking, NaN/Inf scrub, the MAD filter, bin deletion
     and the iterations on the device (``pipeline.ice_pipeline``) instead of round-tripping through scipy;
   * launched under ``torchrun`` (WORLD_SIZE > 1) the genome-wide ICE / KR corrections run on nnz-balanced row blocks,
-    one process per GPU, and rank 0 writes the output (``--perchr`` KR and ``--sequencedCountCutoff`` stay single-GPU);
-  * ``diagnostic_plot`` (matplotlib histogram, :425-545) is out of scope and exits with an explanation;
+    one process per GPU, ``--perchr`` KR deals whole chromosomes to the GPUs, and rank 0 writes the output
+    (``--sequencedCountCutoff``, ``--transCutoff`` and ``--inflationCutoff`` stay single-GPU);
+  * ``diagnostic_plot`` (:425-545) computes its statistics on the device -- coverage per bin, modified z-scores, the
+    100-bin histogram of the bins with z < 5 and the z-score of its first local minimum, logged as "mad threshold" like
+    the reference -- and draws the histogram with matplotlib when it is installed, else as a hand-written SVG;
   * ``--transCutoff`` computes hicmatrix ``truncTrans``'s percentile of the trans values on the device and keeps the
     row sums for ``--inflationCutoff``; like the published hicmatrix code (whose clipping statement is a comparison)
     it leaves the values unchanged unless the additive ``--clipTrans`` flag asks for the documented clipping.
@@ -50,13 +53,17 @@ B200-native implementation: the correction runs on the GPU through libhicbalance
     $ hicCorrectMatrix diagnostic_plot -h \r
     $ hicCorrectMatrix correct -h """)
     plot_mode = subparsers.add_parser('diagnostic_plot', formatter_class=argparse.ArgumentDefaultsHelpFormatter,
-                                      help="(not available in the B200 build: plotting is out of scope)")
-    plot_mode.add_argument('--matrix', '-m', required=True)
-    plot_mode.add_argument('--plotName', '-o', required=True)
-    plot_mode.add_argument('--chromosomes', default=None, nargs='+')
-    plot_mode.add_argument('--xMax', default=None, type=float)
-    plot_mode.add_argument('--perchr', action='store_true')
-    plot_mode.add_argument('--verbose', action='store_true')
+                                      help="Plots a histogram of the coverage per bin together with the modified "
+                                           "z-score based on the median absolute deviation method.",
+                                      usage='%(prog)s --matrix hic_matrix.h5 -o file.png')
+    plot_mode.add_argument('--matrix', '-m', help='Name of the Hi-C matrix to correct in .h5 format.', required=True)
+    plot_mode.add_argument('--plotName', '-o', help='File name to save the diagnostic plot.', required=True)
+    plot_mode.add_argument('--chromosomes', help='List of chromosomes to be included in the iterative correction.',
+                           default=None, nargs='+')
+    plot_mode.add_argument('--xMax', help='Max value for the x-axis in counts per bin.', default=None, type=float)
+    plot_mode.add_argument('--perchr', help='Compute histogram per chromosome.', action='store_true')
+    plot_mode.add_argument('--verbose', help='Print processing status.', action='store_true')
+    plot_mode.add_argument('--device', help='CUDA device index.', type=int, default=0)
     subparsers.add_parser('correct', formatter_class=argparse.ArgumentDefaultsHelpFormatter, parents=[correct_subparser()],
                           help="""Run Knight-Ruiz matrix balancing algorithm (KR) or the iterative matrix correction (ICE).""",
                           usage='%(prog)s --matrix hic_matrix.h5 --filterThreshold -1.2 5 (Only if ICE) -out corrected_matrix.h5 \n')
@@ -115,9 +122,17 @@ def main(args=None):
         log.setLevel(logging.INFO)
         logging.getLogger('hicexplorer_b200.pipeline').setLevel(logging.INFO)
     if getattr(args, 'command', None) == 'diagnostic_plot' or 'plotName' in args:
-        log.error('diagnostic_plot is a matplotlib histogram and is out of scope of the B200 build; '
-                  'use the reference tool for the plot (the statistics it shows are those of --filterThreshold).')
-        sys.exit(1)
+        if _is_cooler(args.matrix) and args.chromosomes is not None and len(args.chromosomes) == 1:
+            ma = hm.hiCMatrix(args.matrix, pChrnameList=[str(c) for c in args.chromosomes])
+        else:
+            ma = hm.hiCMatrix(args.matrix)
+            if args.chromosomes:
+                ma.reorderChromosomes([str(c) for c in args.chromosomes])
+        log.setLevel(logging.INFO)
+        panels = diagnostic_statistics(ma, perchr=args.perchr, x_max=args.xMax, device=args.device)
+        draw_diagnostic_plot(panels, args.plotName)
+        log.info("Saving diagnostic plot {}\n".format(args.plotName))
+        return panels
 
     world, rank, own_group = _init_distributed(args)
     if _is_cooler(args.matrix) and args.chromosomes is not None and len(args.chromosomes) == 1:
@@ -138,6 +153,136 @@ def main(args=None):
         dist.barrier()
         if own_group:
             dist.destroy_process_group()
+
+
+def diagnostic_statistics(ma, perchr=False, x_max=None, device=0):
+    """What ``diagnostic_plot`` shows (hicCorrectMatrix.py:425-545), as numbers.  Coverage (row sum minus diagonal, per
+    chromosome block with ``perchr``), medians / MADs and modified z-scores come from the device (hb_row_stats[_cis],
+    hb_mad_filter); the 100-bin histogram of the bins with z < 5 and its first local minimum are O(n) host work.
+    Returns one dict per histogram: title, values, counts, edges, threshold, mad_threshold, median, mad."""
+    from .store import DeviceCSR
+    up = ma.upper_for_device()
+    with (DeviceCSR.from_upper(up, device=device) if up is not None else DeviceCSR.from_scipy(ma.matrix, device=device)) as dev:
+        drop = ma.upper_drop_mask() if up is not None else None
+        if drop is not None:
+            dev.compact(drop)
+        dev.scrub()                                         # convertNansToZeros / convertInfsToZeros (:486-487)
+        offsets = ma.chromosome_offsets() if perchr else np.asarray([0, dev.n], dtype=np.int64)
+        if perchr:
+            dev.set_segments(offsets)
+        row_sum, diag = dev.row_stats(cis_only=perchr)
+        _mask, z, med, mad = dev.mad_filter(-np.inf, np.inf, want_z=True)
+    points = row_sum - diag
+    names = ma.getChrNames() if perchr else [None]
+    if perchr and len(names) > 30:
+        log.warning("The matrix contains {} chromosomes. It is not practical to plot each. Try using --chromosomes to "
+                    "select some chromosomes or plot a single histogram.".format(len(names)))
+    panels = []
+    for k, title in enumerate(names):
+        lo, hi = int(offsets[k]), int(offsets[k + 1])
+        if title is not None:
+            log.info("Plotting chromosome {}".format(title))
+        values = points[lo:hi][z[lo:hi] < 5]                # high remove outliers (:510, :529)
+        panel = dict(title=title, values=values, counts=None, edges=None, threshold=None, mad_threshold=None,
+                     median=float(med[k]), mad=float(mad[k]))
+        if len(values) == 0:
+            if title is None:
+                log.error('No data available, exit.')
+                sys.exit(1)
+            log.error('No data for chromosome {}. Continue with next chromosome.'.format(title))
+        if x_max:
+            values = values[values < x_max]
+        if len(values):
+            counts, edges = np.histogram(values, 100)       # ax1.hist(row_sum_values, 100)
+            local_min = [x for x, y in enumerate(counts) if 1 <= x < len(counts) - 1 and counts[x - 1] > y < counts[x + 1]]
+            threshold = edges[local_min[0]] if local_min else None
+            panel.update(values=values, counts=counts, edges=edges, threshold=threshold)
+            if threshold:
+                diff = threshold - panel["median"]
+                mad_threshold = 0.6745 * diff if panel["mad"] == 0.0 else 0.6745 * diff / panel["mad"]
+                panel["mad_threshold"] = mad_threshold
+                if title:
+                    log.info("{}: mad threshold {}".format(title, mad_threshold))
+                else:
+                    log.info("mad threshold {}".format(mad_threshold))
+        panels.append(panel)
+    return panels
+
+
+def _value_to_mad(panel, value):
+    diff = np.asarray(value, dtype=np.float64) - panel["median"]
+    return 0.6745 * diff if panel["mad"] == 0.0 else 0.6745 * diff / panel["mad"]
+
+
+def draw_diagnostic_plot(panels, path):
+    """histogram of the coverage per bin with the modified z-score on the top axis and the first local minimum marked;
+    matplotlib if it is installed (same figure layout as the reference), otherwise a plain SVG written by hand"""
+    try:
+        import matplotlib
+        matplotlib.use('Agg')
+        import matplotlib.pyplot as plt
+    except ImportError:
+        return _draw_svg(panels, path)
+    cols = min(len(panels), 5)
+    rows = int(np.ceil(len(panels) / 5.0))
+    fig = plt.figure(figsize=(6 * cols, 5 * rows)) if len(panels) > 1 else plt.figure()
+    for k, panel in enumerate(panels):
+        ax1 = fig.add_subplot(rows, cols, k + 1)
+        ax1.set_xlabel("total counts per bin")
+        ax1.set_ylabel("frequency")
+        if panel["counts"] is not None:
+            ax1.bar(panel["edges"][:-1], panel["counts"], width=np.diff(panel["edges"]), align='edge', color='green')
+            ax2 = ax1.twiny()
+            ax2.set_xlabel("modified z-score")
+            ax2.set_xlim(_value_to_mad(panel, np.array(ax1.get_xlim())))
+            if panel["mad_threshold"] is not None:
+                ymin, ymax = ax2.get_ylim()
+                ax2.vlines(panel["mad_threshold"], ymin, ymax)
+        if panel["title"]:
+            ax1.set_title(panel["title"])
+    plt.tight_layout()
+    plt.savefig(path)
+    plt.close()
+
+
+def _draw_svg(panels, path):
+    if not str(path).lower().endswith('.svg'):
+        log.warning("matplotlib is not installed: writing the plot as SVG to {}.svg".format(path))
+        path = str(path) + '.svg'
+    cols = min(len(panels), 5)
+    rows = int(np.ceil(len(panels) / 5.0))
+    pw, ph, ml, mt, mb = 420, 320, 55, 45, 40
+    out = ['<svg xmlns="http://www.w3.org/2000/svg" width="{}" height="{}" font-family="sans-serif" font-size="11">'.format(
+        cols * pw, rows * ph), '<rect width="100%" height="100%" fill="white"/>']
+    for k, panel in enumerate(panels):
+        x0, y0 = (k % 5) * pw + ml, (k // 5) * ph + mt
+        w, h = pw - ml - 15, ph - mt - mb
+        out.append('<rect x="{}" y="{}" width="{}" height="{}" fill="none" stroke="black"/>'.format(x0, y0, w, h))
+        if panel["title"]:
+            out.append('<text x="{}" y="{}" text-anchor="middle" font-weight="bold">{}</text>'.format(x0 + w / 2, y0 - 30, panel["title"]))
+        out.append('<text x="{}" y="{}" text-anchor="middle">total counts per bin</text>'.format(x0 + w / 2, y0 + h + 32))
+        out.append('<text x="{}" y="{}" text-anchor="middle">modified z-score</text>'.format(x0 + w / 2, y0 - 18))
+        if panel["counts"] is None:
+            continue
+        edges, counts = panel["edges"], panel["counts"]
+        lo, hi, top = float(edges[0]), float(edges[-1]), float(max(counts.max(), 1))
+        span = (hi - lo) or 1.0
+        for c, a, b in zip(counts, edges[:-1], edges[1:]):
+            bh = h * float(c) / top
+            out.append('<rect x="{:.2f}" y="{:.2f}" width="{:.2f}" height="{:.2f}" fill="green"/>'.format(
+                x0 + w * (a - lo) / span, y0 + h - bh, max(w * (b - a) / span, 0.5), bh))
+        for frac in (0.0, 0.25, 0.5, 0.75, 1.0):
+            v = lo + frac * span
+            out.append('<text x="{:.1f}" y="{}" text-anchor="middle">{:.4g}</text>'.format(x0 + w * frac, y0 + h + 14, v))
+            out.append('<text x="{:.1f}" y="{}" text-anchor="middle">{:.2f}</text>'.format(x0 + w * frac, y0 - 5, float(_value_to_mad(panel, v))))
+        out.append('<text x="{}" y="{}" text-anchor="end">{:.0f}</text>'.format(x0 - 4, y0 + 10, top))
+        if panel["threshold"] is not None and panel["mad_threshold"] is not None:
+            xt = x0 + w * (float(panel["threshold"]) - lo) / span
+            out.append('<line x1="{0:.2f}" y1="{1}" x2="{0:.2f}" y2="{2}" stroke="black"/>'.format(xt, y0, y0 + h))
+            out.append('<text x="{:.1f}" y="{}" font-size="10">z = {:.2f}</text>'.format(xt + 3, y0 + 12, panel["mad_threshold"]))
+    out.append('</svg>')
+    with open(path, 'w') as fh:
+        fh.write("\n".join(out))
 
 
 def _init_distributed(args):

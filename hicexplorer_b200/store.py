@@ -239,11 +239,13 @@ class DeviceCSR(object):
         check(lib().hb_csr_pack_values(self._h, ctypes.byref(kind)))
         return kind.value
 
-    def row_stats(self):
+    def row_stats(self, cis_only=False):
+        """(row sums, diagonal) of the block's rows; ``cis_only``: sums restricted to each row's own segment"""
         n_rows = self.n_rows
         rs = np.empty(n_rows, dtype=np.float64)
         dg = np.empty(n_rows, dtype=np.float64)
-        check(lib().hb_row_stats(self._h, ptr(rs), ptr(dg)))
+        fn = lib().hb_row_stats_cis if cis_only else lib().hb_row_stats
+        check(fn(self._h, ptr(rs), ptr(dg)))
         return rs, dg
 
     def mad_filter(self, lo, hi, want_z=False):

@@ -175,6 +175,9 @@ HB_API int hb_peer_active(const hb_csr* h);
  *   exact-symmetry digests of the blocks are summed with one 16-double allreduce: ratio 0 when the whole matrix equals
  *   its transpose exactly, else HB_ERR_NOT_SYMMETRIC with ratio 1 (the exact ratio needs other ranks' entries). */
 HB_API int hb_scrub(hb_csr* h, int64_t counts[2]);
+/* hb_row_stats restricted to each row's own segment (chromosome block): what `diagnostic_plot --perchr` histograms
+ * (hicCorrectMatrix.py:503-507) and what the per-chromosome MAD filter works on (:557-568). */
+HB_API int hb_row_stats_cis(hb_csr* h, double* row_sum, double* diag);
 /* Optional: build a LOSSLESS narrow copy of the stored values for the streaming kernels (ICE / KR mat-vecs):
  * uint16 when every value is an integer count <= 65535 (kind 1, 6 B per entry streamed instead of 12), float when
  * every value is exactly representable in fp32 (kind 2, 8 B), none otherwise (kind 0).  Values are widened to fp64

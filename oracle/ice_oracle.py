@@ -121,6 +121,34 @@ def outlier_bins(csr, lo, hi, chr_ranges=None):
     return np.array(sorted(found), dtype=np.int64)
 
 
+def diagnostic_histograms(csr, chr_ranges=None, x_max=None):
+    """The numbers behind ``hicCorrectMatrix diagnostic_plot`` (hicCorrectMatrix.py:425-545, the matplotlib calls left
+    out): per histogram (one for the whole matrix, or one per chromosome block with ``chr_ranges``) the coverage values
+    with a modified z-score below 5, their 100-bin histogram (``ax.hist(values, 100)`` = ``np.histogram``), and the
+    modified z-score of the first local minimum of the histogram -- the "mad threshold" the tool logs and marks."""
+    m = scrub(csr)
+    out = []
+    for a, b in (chr_ranges if chr_ranges is not None else [(0, m.shape[0])]):
+        block = m[a:b, a:b] if chr_ranges is not None else m
+        points = coverage_points(block)
+        mad = MadScores(points)
+        values = points[mad.z < 5]
+        if x_max:
+            values = values[values < x_max]
+        if len(values) == 0:
+            out.append(dict(values=values, counts=None, edges=None, threshold=None, mad_threshold=None))
+            continue
+        counts, edges = np.histogram(values, 100)
+        local_min = [x for x, y in enumerate(counts) if 1 <= x < len(counts) - 1 and counts[x - 1] > y < counts[x + 1]]
+        threshold = edges[local_min[0]] if local_min else None
+        mad_threshold = None
+        if threshold:
+            diff = threshold - mad.median
+            mad_threshold = mad.B * diff if mad.mad == 0.0 else mad.B * diff / mad.mad
+        out.append(dict(values=values, counts=counts, edges=edges, threshold=threshold, mad_threshold=mad_threshold))
+    return out
+
+
 def zero_bins(csr):
     """Bins whose row sum (diagonal included) is exactly 0 (hicCorrectMatrix.py:612-616)."""
     return np.flatnonzero(np.asarray(csr.sum(axis=1)).flatten() == 0)

@@ -315,3 +315,37 @@ def test_device_side_chromosome_selection_equals_a_presliced_input(tmp_path, gm1
         np.testing.assert_array_equal(ma_.data, mb_.data)
         np.testing.assert_array_equal(fa["correction_factors"].read(), fb["correction_factors"].read())
         assert np.array_equal(fa["nan_bins"].read(), fb["nan_bins"].read())
+
+
+def test_diagnostic_plot_statistics(tmp_path, gm12878):
+    """`hicCorrectMatrix diagnostic_plot` (hicCorrectMatrix.py:425-545): the histogram, the first local minimum and its
+    modified z-score ("mad threshold") equal the oracle's restatement; whole matrix and --perchr; the figure is written"""
+    import os
+    g = gm12878
+    src = _gm_cool(tmp_path, g)
+    full = full_from_pixels(g)
+    out = str(tmp_path / "diag.svg")
+    panels = main("diagnostic_plot --matrix {} --plotName {}".format(src, out).split())
+    ref = ice_oracle.diagnostic_histograms(full)
+    assert len(panels) == 1 and os.path.getsize(out) > 1000
+    np.testing.assert_array_equal(panels[0]["values"], ref[0]["values"])
+    np.testing.assert_array_equal(panels[0]["counts"], ref[0]["counts"])
+    assert panels[0]["threshold"] == ref[0]["threshold"] and panels[0]["mad_threshold"] == ref[0]["mad_threshold"]
+    cut = float(np.percentile(ref[0]["values"], 80))
+    px = main("diagnostic_plot --matrix {} --plotName {} --xMax {}".format(src, out, cut).split())
+    rx = ice_oracle.diagnostic_histograms(full, x_max=cut)
+    np.testing.assert_array_equal(px[0]["counts"], rx[0]["counts"])
+    assert px[0]["mad_threshold"] == rx[0]["mad_threshold"]
+    offs = g["chrom_offset"]
+    ranges = list(zip(offs[:-1], offs[1:]))
+    outp = str(tmp_path / "diag_perchr.svg")
+    pan = main("diagnostic_plot --matrix {} --plotName {} --perchr".format(src, outp).split())
+    refp = ice_oracle.diagnostic_histograms(full, chr_ranges=ranges)
+    assert sum(p["mad_threshold"] is not None for p in refp) > 10
+    assert len(pan) == len(ranges) and os.path.getsize(outp) > 1000
+    for a, b in zip(pan, refp):
+        np.testing.assert_array_equal(a["values"], b["values"])
+        assert (a["counts"] is None) == (b["counts"] is None)
+        if a["counts"] is not None:
+            np.testing.assert_array_equal(a["counts"], b["counts"])
+        assert a["mad_threshold"] == b["mad_threshold"]
