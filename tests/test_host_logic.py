@@ -164,3 +164,31 @@ def test_mcool_uri_selects_a_resolution(tmp_path):
     w.save(path)
     got = hiCMatrix(path + "::/resolutions/100")
     assert (got.matrix != ma.matrix).nnz == 0 and got.getChrNames() == ["chr1", "chr2"]
+
+
+def test_diagnostic_plot_svg_writer(tmp_path):
+    """the hand-written SVG of `diagnostic_plot` (used when matplotlib is not installed) is well-formed and holds one
+    bar per histogram bin, the threshold line and both axis captions"""
+    import xml.etree.ElementTree as ET
+    from hicexplorer_b200.hicCorrectMatrix import _draw_svg
+    rng = np.random.default_rng(0)
+    panels = []
+    for title in ("chr1", "chr2", None):
+        values = rng.gamma(5.0, 100.0, size=3000)
+        counts, edges = np.histogram(values, 100)
+        panels.append(dict(title=title, values=values, counts=counts, edges=edges, threshold=float(edges[7]),
+                           mad_threshold=-1.8, median=float(np.median(values)), mad=80.0))
+    panels.append(dict(title="empty", values=np.zeros(0), counts=None, edges=None, threshold=None, mad_threshold=None,
+                       median=0.0, mad=0.0))
+    path = str(tmp_path / "plot.svg")
+    _draw_svg(panels, path)
+    root = ET.parse(path).getroot()
+    ns = "{http://www.w3.org/2000/svg}"
+    bars = [r for r in root.iter(ns + "rect") if r.get("fill") == "green"]
+    assert len(bars) == 300
+    assert len(list(root.iter(ns + "line"))) == 3
+    texts = [t.text for t in root.iter(ns + "text")]
+    assert texts.count("total counts per bin") == 4 and texts.count("modified z-score") == 4 and "chr2" in texts
+    other = str(tmp_path / "plot.png")
+    _draw_svg(panels[:1], other)                         # not an .svg name: written next to it, with a warning
+    assert (tmp_path / "plot.png.svg").exists()
