@@ -334,73 +334,171 @@ def main():
 
     exch = torch.zeros(n + 64, dtype=torch.float64, device="cuda")
     eptr = None if peer_mode else ctypes.c_void_p(exch.data_ptr())
+    # One GPU, or row blocks in peer mode: K iterations = ONE cooperative launch (hb_dev_ice_loop: SpMV + update per
+    # iteration separated by grid barriers, nothing on the host).  With the NCCL exchange the host has to sit between the
+    # SpMV and the update, so that mode keeps one launch per operation.
+    use_loop = (world == 1 or peer_mode) and os.environ.get("HB_NO_PERSISTENT") != "1"
 
-    def ice_step(timed_events=None):
-        if timed_events is not None:
-            timed_events[0].record(stream)
+    def ice_step():
         check(L.hb_dev_ice_spmv(h, eptr, rank, world, sptr))
-        if timed_events is not None:
-            timed_events[1].record(stream)
         if world > 1 and not peer_mode:
             dist.all_reduce(exch[:n + world])
         check(L.hb_dev_ice_update(h, eptr, world, 0.0, sptr))
+
+    def run_steps(k, tol=0.0):
+        if use_loop:
+            check(L.hb_dev_ice_loop(h, k, tol, sptr))
+        else:
+            for _ in range(k):
+                ice_step()
 
     if os.environ.get("HB_BENCH_PACK") == "1":     # tuning sweeps only: time the packed layout in the main loop
         dev.pack_values()
     # ---- device-resident timing -------------------------------------------------------------------------
     check(L.hb_dev_ice_begin(h, sptr))
-    for _ in range(args.warmup):
-        ice_step()
+    run_steps(args.warmup)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for _ in range(0 if args.quick else max(args.warmup, 20)):     # let the sampler spin up under load (all ranks)
-        ice_step()
-    pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if not args.quick:
+        run_steps(max(args.warmup, 20))     # let the sampler spin up under load (all ranks)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = L.hb_launch_count()
     barrier()
     sampler.begin_region()
     ev0.record(stream)
-    for k in range(args.steps):
-        ice_step(pairs[k])
+    run_steps(args.steps)
     ev1.record(stream)
     barrier()
     launches = L.hb_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
-    spmv_ms = max_over_ranks(float(np.mean([a.elapsed_time(b) for a, b in pairs])))
     ms_step = ms_total / args.steps
     value = nnz_total * args.steps / (ms_total * 1e-3)
+    # the dominant kernel for the roofline: the loop kernel's launch IS the timed region (K iterations per launch, so
+    # bytes per launch = K x bytes per iteration); in step-level mode the SpMV launches are timed one by one
+    if use_loop:
+        spmv_ms = ms_step
+        kernel_name = "hb_ice_loop_kernel<double> (one cooperative launch = %d iterations: SpMV + vector update)" % args.steps
+    else:
+        pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for a, b in pairs:
+            a.record(stream)
+            check(L.hb_dev_ice_spmv(h, eptr, rank, world, sptr))
+            b.record(stream)
+            if world > 1 and not peer_mode:
+                dist.all_reduce(exch[:n + world])
+            check(L.hb_dev_ice_update(h, eptr, world, 0.0, sptr))
+        barrier()
+        spmv_ms = max_over_ranks(float(np.mean([a.elapsed_time(b) for a, b in pairs])))
+        kernel_name = "hb_spmv_kernel<HbIceEpi,true>"
+    # the stand-alone SpMV kernel of the step-level API next to it (N = 1): what one pass over the CSR costs without the
+    # vector phases and grid barriers of the loop kernel
+    spmv_alone_ms = None
+    if world == 1 and not args.quick:
+        check(L.hb_dev_ice_begin(h, sptr))
+        for _ in range(3):
+            ice_step()
+        pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
+        for a, b in pairs:
+            a.record(stream)
+            check(L.hb_dev_ice_spmv(h, eptr, rank, world, sptr))
+            b.record(stream)
+            check(L.hb_dev_ice_update(h, eptr, world, 0.0, sptr))
+        torch.cuda.synchronize()
+        spmv_alone_ms = float(np.mean([a.elapsed_time(b) for a, b in pairs]))
 
     # ---- time to converge (tol 1e-5, the reference default), device resident ------------------------------
     barrier()
-    check(L.hb_dev_ice_begin(h, sptr))
     status = torch.zeros(4, dtype=torch.int32, pin_memory=True)
-    t0 = time.time()
     conv_iters = 0
-    for k in range(1, 1 if args.quick else 501):
-        check(L.hb_dev_ice_spmv(h, eptr, rank, world, sptr))
-        if world > 1 and not peer_mode:
-            dist.all_reduce(exch[:n + world])
-        check(L.hb_dev_ice_update(h, eptr, world, 1e-5, sptr))
-        if k % 4 == 0:
-            check(L.hb_dev_ice_status(h, ctypes.c_void_p(status.data_ptr()), sptr))
-            stream.synchronize()
-            if int(status[0]):
-                break
-    check(L.hb_dev_ice_status(h, ctypes.c_void_p(status.data_ptr()), sptr))
-    stream.synchronize()
-    conv_iters = int(status[2])
-    converge_ms = max_over_ranks((time.time() - t0) * 1e3)
-    converged = bool(int(status[0])) and not bool(int(status[1]))
-    check(L.hb_dev_ice_finish(h, sptr))
-    stream.synchronize()
-    # size-independent property at full size: the balanced matrix has unit row sums (mean-normalised)
-    dptr = ctypes.c_void_p()
-    rptr = ctypes.c_void_p()
-    check(L.hb_dev_ice_vectors(h, ctypes.byref(dptr), ctypes.byref(rptr)))
+    converged = False
+    converge_ms = None
+    parity = None
+    if not args.quick:
+        check(L.hb_dev_ice_begin(h, sptr))
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        if use_loop:
+            check(L.hb_dev_ice_loop(h, 500, 1e-5, sptr))
+        else:
+            for k in range(1, 501):
+                check(L.hb_dev_ice_spmv(h, eptr, rank, world, sptr))
+                if world > 1 and not peer_mode:
+                    dist.all_reduce(exch[:n + world])
+                check(L.hb_dev_ice_update(h, eptr, world, 1e-5, sptr))
+                if k % 4 == 0:
+                    check(L.hb_dev_ice_status(h, ctypes.c_void_p(status.data_ptr()), sptr))
+                    stream.synchronize()
+                    if int(status[0]):
+                        break
+        c1.record(stream)
+        check(L.hb_dev_ice_status(h, ctypes.c_void_p(status.data_ptr()), sptr))
+        stream.synchronize()
+        conv_iters = int(status[2])
+        converge_ms = max_over_ranks(c0.elapsed_time(c1))
+        converged = bool(int(status[0])) and not bool(int(status[1]))
+        check(L.hb_dev_ice_finish(h, sptr))
+        stream.synchronize()
+        # ---- parity record: the converged bias (and, below, the KR vector) must be BIT-identical for every N -------
+        import hashlib
+        bias_h = np.empty(n, dtype=np.float64)
+        it_h = np.zeros(1, dtype=np.int32)
+        check(L.hb_ice_results(h, _lib.ptr(bias_h), _lib.ptr(it_h), None))
+        parity = {"bias_sha256": hashlib.sha256(bias_h.tobytes()).hexdigest(), "iterations": int(it_h[0]),
+                  "bias_row_sum_check": None}
+
+    # ---- KR on the SAME matrix, same sharding (north star: "10 kb ICE and KR ... on 8 x B200") -----------------
+    kr10 = None
+    if not args.quick and not args.no_kr and (world == 1 or peer_mode or keep is not None):
+        import hashlib
+        barrier()
+        t0 = time.time()
+        xk, kouter, kmv, kres = dev.kr()
+        torch.cuda.synchronize()
+        kr_s = max_over_ranks(time.time() - t0)
+        peak_k, _ = measured_peak()
+        bytes_mv = 12.0 * nnz_total + 120.0 * n
+        per_mv_ms = kr_s * 1e3 / max(kmv + 1, 1)
+        kr10 = {"what": "hb_kr_run to tol 1e-6 on the %s matrix of this run, %d row block(s): ONE cooperative launch "
+                        "(hb_kr_solve_kernel) per rank, host-timed call (x copied back inside)" % (args.workload, world),
+                "time_to_converge_ms": kr_s * 1e3, "outer_iterations": int(kouter), "matvecs": int(kmv),
+                "residual": float(kres), "ms_per_matvec_incl_vector_work": per_mv_ms,
+                "GBps_per_gpu": bytes_mv / world / (per_mv_ms * 1e-3) / 1e9,
+                "frac_of_peak_per_gpu": bytes_mv / world / (per_mv_ms * 1e-3) / 1e9 / peak_k,
+                "frac_of_nominal_8TBps": bytes_mv / world / (per_mv_ms * 1e-3) / 1e9 / 8000.0,
+                "nnz_per_s": nnz_total * (kmv + 1) / kr_s}
+        if parity is not None:
+            parity["kr_x_sha256"] = hashlib.sha256(np.ascontiguousarray(xk).tobytes()).hexdigest()
+            parity["kr_matvecs"] = int(kmv)
+            parity["kr_outer"] = int(kouter)
+
+    # ---- N > 1: rank 0 repeats both solves on ONE GPU with the whole matrix and compares the digests ----------
+    if parity is not None and world > 1:
+        ok_flag = torch.ones(1, dtype=torch.int32, device="cuda")
+        if rank == 0:
+            try:
+                import hashlib
+                with DeviceCSR.synthetic(bins, device=local, **kw) as one:
+                    b1, it1, _d1 = one.ice(500, 1e-5)
+                    single = {"bias_sha256": hashlib.sha256(np.ascontiguousarray(b1).tobytes()).hexdigest(),
+                              "iterations": int(it1[0])}
+                    if "kr_x_sha256" in parity:
+                        x1, o1, mv1, _r1 = one.kr()
+                        single.update(kr_x_sha256=hashlib.sha256(np.ascontiguousarray(x1).tobytes()).hexdigest(),
+                                      kr_matvecs=int(mv1), kr_outer=int(o1))
+                parity["single_gpu_same_run"] = single
+                parity["identical_to_single_gpu"] = all(parity.get(k) == v for k, v in single.items())
+            except Exception as exc:
+                parity["single_gpu_same_run"] = {"error": repr(exc)}
+                parity["identical_to_single_gpu"] = None
+            if parity.get("identical_to_single_gpu") is False:
+                ok_flag[0] = 0
+        dist.all_reduce(ok_flag, op=dist.ReduceOp.MIN)
+        if int(ok_flag.item()) != 1:
+            raise SystemExit("PARITY FAILURE: the sharded result differs from the single-GPU result: %r" % (parity,))
 
     # ---- optional lossless narrow value layout (hb_csr_pack_values): same results bit for bit, fewer bytes streamed
     packed = None
@@ -409,14 +507,12 @@ def main():
         if kind:
             vbytes = {1: 2, 2: 4}[kind]
             check(L.hb_dev_ice_begin(h, sptr))
-            for _ in range(5):
-                ice_step()
+            run_steps(5)
             barrier()
             pk0, pk1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             psteps = min(args.steps, 100)
             pk0.record(stream)
-            for _ in range(psteps):
-                ice_step()
+            run_steps(psteps)
             pk1.record(stream)
             barrier()
             pms = max_over_ranks(pk0.elapsed_time(pk1)) / psteps
@@ -518,10 +614,20 @@ def main():
         return
     peak, peak_src = measured_peak()
     traffic = None
-    try:   # DRAM bytes per launch of the same kernel on the same workload, from the committed ncu capture
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(args.workload)
+    traffic_note = None
+    try:
+        # DRAM bytes of the same kernel on the same workload from this round's `ncu --set full` capture
+        # (profiles/r2_traffic.json, written by tools/ncu_traffic.py next to the raw export); per ITERATION, like
+        # `achieved`.  The entry is only used while the kernel sources it was measured on are unchanged.
+        import hashlib
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json"))).get(args.workload)
+        src = b"".join(open(os.path.join(ROOT, "hicexplorer_b200", "csrc", f), "rb").read()
+                       for f in ("hb_spmv.cuh", "hb_ice.cu", "hb_internal.cuh"))
         if tr and tr["nnz"] == nnz_total and world == 1:
-            traffic = float(tr["dram_bytes_read"] + tr["dram_bytes_write"])
+            if tr.get("source_sha256") == hashlib.sha256(src).hexdigest():
+                traffic = float(tr["dram_bytes_read"] + tr["dram_bytes_write"]) / float(tr.get("iterations", 1))
+            else:
+                traffic_note = "profiles/r2_traffic.json was captured on older kernel sources: not reported"
     except Exception:
         pass
     bytes_spmv = 12.0 * nnz_total + 24.0 * n
@@ -534,19 +640,29 @@ def main():
         "config": {"workload": workload_name(args.workload, bins, kw), "bins": n, "nnz": nnz_total,
                    "parallelism": ("%d nnz-balanced row block(s); " % world) + (
                        "rows stored into every rank's replica over NVLink by the SpMV epilogue (CUDA IPC peer stores + "
-                       "arrival flags), no collective in the loop" if peer_mode else
+                       "arrival flags), no collective and no host in the loop: ONE persistent cooperative launch per rank "
+                       "runs all timed iterations" if peer_mode else
                        "1 NCCL sum-allreduce of n fp64 per iteration" if world > 1 else "single GPU"),
                    "l2": "inputs larger than L2 (%.1f GB of CSR per GPU vs 126 MB)" % (12e-9 * nnz_total / world),
                    "generated_in_s": round(t_gen, 2)},
         "time_to_converge": {"ms": converge_ms, "iterations": conv_iters, "converged": converged, "tolerance": 1e-5},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "hb_spmv_kernel<HbIceEpi,true>", "peak_source": peak_src,
-                     "bytes_per_launch": bytes_spmv / world, "avg_launch_ms": spmv_ms,
+                     "traffic": traffic, "kernel": kernel_name, "peak_source": peak_src,
+                     "bytes_per_iteration": bytes_spmv / world, "avg_iteration_ms": spmv_ms,
+                     "launch": ("one launch = %d iterations; bytes and time are per iteration" % args.steps) if use_loop
+                     else "one launch = one iteration's SpMV",
+                     "standalone_spmv_kernel_ms": spmv_alone_ms,
+                     "standalone_spmv_GBps": (bytes_spmv / (spmv_alone_ms * 1e-3) / 1e9) if spmv_alone_ms else None,
+                     "traffic_note": traffic_note,
                      "frac_of_nominal_8TBps": achieved / 8000.0},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
     if packed is not None:
         line["packed_values"] = packed
+    if parity is not None:
+        line["parity"] = parity
+    if kr10 is not None:
+        line["kr_same_matrix"] = kr10
     if kr is not None:
         line["kr"] = kr
     if not args.no_cpu and world == 1:

@@ -53,10 +53,10 @@ def build(force=False, verbose=False, defines=None, out=None):
         objs.append(obj)
     log = []
     for src, p in procs:
-        out = p.communicate()[0]
-        log.append("== %s ==\n%s" % (src, out))
+        text = p.communicate()[0]
+        log.append("== %s ==\n%s" % (src, text))
         if p.returncode != 0:
-            sys.stderr.write(out)
+            sys.stderr.write(text)
             raise RuntimeError("nvcc failed on %s" % src)
     with open(os.path.join(bdir, "ptxas.log"), "w") as fh:
         fh.write("\n".join(log))

@@ -78,6 +78,7 @@ SIGNATURES = {
     "hb_set_comm": (c_int, [vp, c_int, c_int, vp, vp]),
     "hb_peer_export": (c_int, [vp, c_int, c_int, vp]),
     "hb_peer_attach": (c_int, [vp, vp]),
+    "hb_peer_attach_inprocess": (c_int, [vp, vp]),
     "hb_peer_active": (c_int, [vp]),
     "hb_set_segments": (c_int, [vp, c_int, vp]),
     "hb_csr_keep_cis": (c_int, [vp]),
@@ -107,6 +108,7 @@ SIGNATURES = {
     "hb_trans_clip": (c_int, [vp, vp, c_int, c_dbl, P(c_i64)]),
     "hb_ice_scaled_row_sums": (c_int, [vp, vp]),
     "hb_dev_ice_begin": (c_int, [vp, vp]),
+    "hb_dev_ice_loop": (c_int, [vp, c_int, c_dbl, vp]),
     "hb_dev_ice_spmv": (c_int, [vp, vp, c_int, c_int, vp]),
     "hb_dev_ice_update": (c_int, [vp, vp, c_int, c_dbl, vp]),
     "hb_dev_ice_status": (c_int, [vp, vp, vp]),

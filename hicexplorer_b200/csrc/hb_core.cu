@@ -314,6 +314,7 @@ int hb_csr_destroy(hb_csr* h) {
     cudaFree(h->d_tile_slab);
     cudaFree(h->d_pack);
     hb_peer_release(h);
+    if (h->loop_event) cudaEventDestroy(h->loop_event);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return HB_OK;
@@ -417,9 +418,34 @@ int hb_peer_attach(hb_csr* h, const void* all_handles) {
             return hb_cuda_fail(e, "cudaIpcOpenMemHandle (peer access between the GPUs is required)", __FILE__, __LINE__);
         }
         h->peer_base[q] = p;
+        h->peer_ipc[q] = true;
+    }
+    h->peer = true;          // the SpMV exchange goes over peer stores; a registered callback stays for the other collectives
+    h->peer_seq = 0;
+    return HB_OK;
+}
+
+int hb_peer_attach_inprocess(hb_csr* h, hb_csr* const* ranks) {
+    HB_REQUIRE(h != nullptr && ranks != nullptr && h->d_sym != nullptr, "call hb_peer_export first");
+    int rc = hb_use_device(h);
+    if (rc) return rc;
+    for (int q = 0; q < h->world; ++q) {
+        hb_csr* o = ranks[q];
+        HB_REQUIRE(o != nullptr && o->d_sym != nullptr && o->world == h->world && o->rank == q &&
+                       o->sym_buf_bytes == h->sym_buf_bytes,
+                   "every rank must have called hb_peer_export with the same world and matrix size");
+        if (o->device != h->device) {
+            int can = 0;
+            HB_CUDA(cudaDeviceCanAccessPeer(&can, h->device, o->device));
+            HB_REQUIRE(can, "no peer access between the devices");
+            cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) return hb_cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+        }
+        h->peer_base[q] = o->d_sym;
+        h->peer_ipc[q] = false;
     }
     h->peer = true;
-    h->allreduce = nullptr;
     h->peer_seq = 0;
     return HB_OK;
 }
@@ -497,9 +523,11 @@ int hb_set_segments(hb_csr* h, int nseg, const int64_t* seg_offsets) {
 }  // extern "C"
 
 void hb_peer_release(hb_csr* h) {
+    if (h->loop_pending) hb_loop_settle(h);
     for (int q = 0; q < HB_MAX_PEERS; ++q) {
-        if (h->peer_base[q] != nullptr && h->peer_base[q] != h->d_sym) cudaIpcCloseMemHandle(h->peer_base[q]);
+        if (h->peer_base[q] != nullptr && h->peer_ipc[q]) cudaIpcCloseMemHandle(h->peer_base[q]);
         h->peer_base[q] = nullptr;
+        h->peer_ipc[q] = false;
     }
     cudaFree(h->d_sym);
     h->d_sym = nullptr;
@@ -558,6 +586,7 @@ int hb_build_tiles(hb_csr* h) {
 }
 
 void hb_free_state(hb_csr* h) {
+    if (h->loop_pending) hb_loop_settle(h);
     cudaFree(h->d_state_slab);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     cudaFree(h->d_kr_buf);
@@ -573,7 +602,38 @@ void hb_free_state(hb_csr* h) {
     h->d_row_counter = nullptr;
     h->d_scalar_bits = nullptr;
     h->h_status = nullptr;
+    h->d_loop_devbits = h->d_loop_wmax = nullptr;
+    h->d_loop_err = nullptr;
+    h->h_loop = h->h_loop_dev = nullptr;
     h->state_ready = false;
+}
+
+// A persistent solver kernel reports how many exchanges it performed (it may stop early on convergence); the host
+// folds that into the handle's sequence number before the next exchange is issued.
+int hb_loop_settle(hb_csr* h) {
+    if (!h->loop_pending) return HB_OK;
+    HB_CUDA(cudaEventSynchronize(h->loop_event));
+    h->peer_seq += (unsigned long long)(unsigned int)((volatile int32_t*)h->h_loop)[HB_LP_EXCHANGES];
+    h->loop_pending = false;
+    return HB_OK;
+}
+
+// Grid of a cooperative (grid-synchronising) persistent kernel: what hb_spmv_grid asks for, capped by what is
+// co-resident on this device for THIS kernel.
+int hb_coop_grid(const void* kernel, int64_t n_rows, int device) {
+    int per_sm = 0, sms = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, HB_SPMV_THREADS, 0) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 1;
+    }
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms < 1) {
+        cudaGetLastError();
+        sms = HB_NUM_SMS;
+    }
+    if (per_sm > HB_SPMV_CTAS_PER_SM) per_sm = HB_SPMV_CTAS_PER_SM;
+    const int want = hb_spmv_grid(n_rows);
+    const int cap = per_sm * sms;
+    return want < cap ? want : cap;
 }
 
 // replicated vectors + per-segment scalars: one device slab, one pinned block
@@ -594,8 +654,10 @@ int hb_ensure_state(hb_csr* h) {
     const size_t o_tsum = take(sizeof(double) * nt), o_tcnt = take(sizeof(double) * nt);
     const size_t o_mean = take(sizeof(double) * ns), o_corr = take(sizeof(double) * ns), o_dev = take(sizeof(double) * ns);
     const size_t o_devb = take(sizeof(unsigned long long) * ns);
+    const size_t o_ldevb = take(sizeof(unsigned long long) * 2 * ns);
     const size_t o_done = take(sizeof(int32_t) * ns), o_iters = take(sizeof(int32_t) * ns);
-    const size_t o_small = take(256);  // status (16 B) | counters (32 B) | row counters (16 B) | scalar bits (64 B)
+    // status (16 B) | counters (32 B) | row counters (16 B) | scalar bits (64 B) | loop wmax (16 B) | loop err (8 B)
+    const size_t o_small = take(256);
     const size_t total = off;
     HB_CUDA(cudaMalloc(&h->d_state_slab, total));
     unsigned char* b = (unsigned char*)h->d_state_slab;
@@ -614,11 +676,22 @@ int hb_ensure_state(hb_csr* h) {
     h->d_counters = (unsigned int*)(b + o_small + 32);
     h->d_row_counter = (unsigned long long*)(b + o_small + 64);
     h->d_scalar_bits = (unsigned long long*)(b + o_small + 128);
+    h->d_loop_wmax = (unsigned long long*)(b + o_small + 192);
+    h->d_loop_err = (double*)(b + o_small + 208);
+    h->d_loop_devbits = (unsigned long long*)(b + o_ldevb);
     HB_CUDA(cudaMemset(b + o_small, 0, 256));
     HB_CUDA(cudaDeviceSynchronize());   // cudaMemset is asynchronous and the work streams are non-blocking: finish it here
-    HB_CUDA(cudaHostAlloc(&h->h_pinned, 1024, cudaHostAllocDefault));
+    HB_CUDA(cudaHostAlloc(&h->h_pinned, 1024, cudaHostAllocMapped));
+    memset(h->h_pinned, 0, 1024);
     h->h_status = (int32_t*)h->h_pinned;                              // 16 slots x HB_ST_WORDS x 4 B = 256 B
     h->h_kr_sc = (double*)((unsigned char*)h->h_pinned + 512);       // 16 doubles
+    h->h_loop = (int32_t*)((unsigned char*)h->h_pinned + 768);       // HB_LOOP_WORDS x 4 B
+    {
+        void* dp = nullptr;
+        HB_CUDA(cudaHostGetDevicePointer(&dp, h->h_loop, 0));
+        h->h_loop_dev = (int32_t*)dp;
+    }
+    if (h->loop_event == nullptr) HB_CUDA(cudaEventCreateWithFlags(&h->loop_event, cudaEventDisableTiming));
     h->state_ready = true;
     return HB_OK;
 }

@@ -644,7 +644,7 @@ int hb_scrub(hb_csr* h, int64_t counts[2]) {
     hb_drop_pack(h);  // the values may change
     HB_CUDA(cudaMemsetAsync(h->d_scalar_bits, 0, sizeof(unsigned long long) * 2, s));
     if (h->nnz > 0) {
-        hb_scrub_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_data, h->nnz, h->d_scalar_bits);
+        hb_scrub_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_data + h->phase, h->nnz, h->d_scalar_bits);
         HB_LAUNCH_CHECK();
     }
     unsigned long long c[2] = {0, 0};
@@ -670,8 +670,9 @@ static int hb_row_stats_impl(hb_csr* h, double* row_sum, double* diag, int cis_o
     cudaStream_t s = h->stream;
     size_t n = (size_t)(h->n_rows > 0 ? h->n_rows : 1);
     double *d_rs = nullptr, *d_dg = nullptr;
+    HbScratch scratch;   // freed on every return path
     // row sums and diagonals share one buffer so that a sharded run assembles both with ONE sum-allreduce
-    HB_CUDA(cudaMalloc(&d_rs, sizeof(double) * 2 * n));
+    HB_CUDA(scratch.alloc(&d_rs, sizeof(double) * 2 * n));
     d_dg = d_rs + n;
     HB_CUDA(cudaMemsetAsync(d_rs, 0, sizeof(double) * 2 * n, s));
     if (h->n_rows > 0) {
@@ -682,7 +683,6 @@ static int hb_row_stats_impl(hb_csr* h, double* row_sum, double* diag, int cis_o
     cudaError_t e = cudaStreamSynchronize(s);
     if (e == cudaSuccess && row_sum && h->n_rows) e = cudaMemcpy(row_sum, d_rs, sizeof(double) * n, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && diag && h->n_rows) e = cudaMemcpy(diag, d_dg, sizeof(double) * n, cudaMemcpyDeviceToHost);
-    cudaFree(d_rs);
     if (e != cudaSuccess) return hb_cuda_fail(e, "row stats", __FILE__, __LINE__);
     return HB_OK;
 }
@@ -723,6 +723,7 @@ int hb_mad_filter(hb_csr* h, double lo, double hi, uint8_t* mask_out, double* zs
                                                            h->d_seg_off, nseg, 1, d_rs + h->row0, d_dg + h->row0);
         HB_LAUNCH_CHECK();
     }
+    HB_REQUIRE(h->world == 1 || h->allreduce != nullptr, "sharded hb_mad_filter needs the allreduce callback (hb_set_comm)");
     if (h->world > 1 && h->allreduce(h->comm_ctx, d_rs, 2 * n, (void*)s) != 0) {
         hb_set_error("collective callback failed");
         return HB_ERR_CUDA;

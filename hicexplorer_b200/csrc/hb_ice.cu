@@ -12,7 +12,13 @@
 // Between the first and the second, a sharded run sum-allreduces the exchange vector (each rank
 // has written only its own rows, the rest is zero); the two O(n) kernels then run identically on
 // every rank.  Convergence lives on the device (per-segment flags), the host only polls.
+#include <cooperative_groups.h>
+
+#include <cstdlib>
+
 #include "hb_spmv.cuh"
+
+namespace cg = cooperative_groups;
 
 struct HbIceEpi {
     const double* __restrict__ r;
@@ -31,7 +37,8 @@ struct HbIceEpi {
         }
         return seg_done[lo] == 0;
     }
-    __device__ __forceinline__ void row(int64_t g, double t, double m, int lane, const HbPeerOut& peer) {
+    template <class Out>
+    __device__ __forceinline__ void row(int64_t g, double t, double m, int lane, const Out& peer) {
         const double rg = r[g];
         peer.store(g, rg * t, lane);
         wmax = fmax(wmax, rg * m);  // NaN-ignoring, like np.any(W.data > 1e100)
@@ -261,6 +268,254 @@ hb_ice_emit_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// The whole ICE loop in ONE cooperative launch (hb_ice_loop_kernel).  A persistent grid of 148 x 3 CTAs runs, per
+// iteration:   A  the SpMV over the block's rows (same row loop as hb_spmv_kernel; in peer mode every row goes
+//                 straight into every rank's replica over NVLink)
+//              -- grid barrier; peer mode: publish this rank's arrival flag, wait for everybody's
+//              B  sum / count of the non-zero marginals per fixed tile            (iterativeCorrection.py:43-44)
+//              -- grid barrier
+//              C  mean per segment (every CTA folds the tile partials in tile order -> bit-identical everywhere),
+//                 s = s_raw / mean ; bias *= s ; deviation = max|s - 1| ; r *= 1/s (:44-57); 1e100 guard (:58)
+//              -- grid barrier
+//              D  every CTA evaluates the strict '<' convergence test (:72) per segment from the same maxima
+// so an iteration costs three grid barriers instead of three kernel launches, a memset, a status copy and an event,
+// and the host never synchronises inside the loop (progress is mirrored into pinned memory for whoever wants to
+// look).  Arithmetic and summation order are those of the step-level kernels above: results are bit-identical.
+// Cross-CTA data is read with ld.cg; the gathered vector r is read with plain (coherent, L1-cached) loads -- the
+// acquire side of a grid barrier invalidates L1 -- never through the non-coherent path, since r changes every
+// iteration inside this kernel.
+struct HbIceLoopArgs {
+    const int64_t* indptr;
+    const int32_t* idx;
+    const void* val;
+    int64_t n_rows, row0, n_cols;
+    const int64_t* tile_row0;
+    const int32_t* tile_len;
+    const int32_t* tile_seg;
+    const int32_t* seg_tile0;
+    const int64_t* seg_off;
+    int n_tiles, nseg;
+    double* bias;
+    double* r;
+    double* exch;  // single GPU: the marginals (n_cols + 64)
+    double* tile_sum;
+    double* tile_cnt;
+    unsigned long long* devbits;  // 2 x nseg, zero on entry
+    unsigned long long* wmax;     // 2 words, zero on entry
+    double* seg_dev;
+    int32_t* seg_done;
+    int32_t* seg_iters;
+    int32_t* status;
+    int32_t* h_loop;  // pinned, device alias
+    unsigned long long* row_counters;
+    double* err;
+    int iters, row_parity;
+    double tol;
+    HbLoopPeer peer;
+};
+
+struct HbIceLoopEpi {
+    const double* r;  // written by this kernel between iterations: no __restrict__, no non-coherent loads
+    unsigned long long* wmax_slot;
+    const int64_t* __restrict__ seg_off;
+    const int32_t* seg_done;
+    int nseg;
+    double wmax;
+    __device__ __forceinline__ bool active(int64_t g) const {
+        if (nseg <= 1) return true;
+        int lo = 0, hi = nseg;
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (seg_off[mid] <= g) lo = mid; else hi = mid;
+        }
+        return __ldcg(seg_done + lo) == 0;
+    }
+    template <class Out>
+    __device__ __forceinline__ void row(int64_t g, double t, double m, int lane, const Out& peer) {
+        const double rg = __ldcg(r + g);
+        peer.store(g, rg * t, lane);
+        wmax = fmax(wmax, rg * m);
+    }
+    __device__ __forceinline__ double local_max() const { return 0.0; }
+    __device__ __forceinline__ void warp_done() const {
+        if (wmax > 0.0) atomicMax(wmax_slot, (unsigned long long)__double_as_longlong(wmax));
+    }
+};
+
+template <typename VT>
+__global__ void __launch_bounds__(HB_SPMV_THREADS, HB_SPMV_CTAS_PER_SM)
+hb_ice_loop_kernel(const __grid_constant__ HbIceLoopArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double smem[64];
+    __shared__ unsigned long long smax[HB_SPMV_THREADS / 32];
+    __shared__ double s_mean;
+    __shared__ int s_active;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool peer = a.peer.world > 1;
+    const int world = peer ? a.peer.world : 1;
+    // status is stable here: it was last written before the previous launch on this stream ended
+    if (a.status[HB_ST_ALL_DONE] != 0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.h_loop[HB_LP_EXCHANGES] = 0;
+        return;
+    }
+    const int it_base = a.status[HB_ST_ITER];
+    int executed = 0;
+    for (int it = 0; it < a.iters; ++it) {
+        const int par = (a.row_parity + it) & 1;
+        const int cur = it & 1;
+        const unsigned long long seq = a.peer.seq0 + 1ull + (unsigned long long)it;
+        const int pb = (int)(seq & 1ull);
+        double* exch = peer ? a.peer.buf[pb][a.peer.rank] : a.exch;
+        // ---- A: marginals of the block's rows
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.row_counters[par ^ 1] = 0ull;
+        {
+            HbIceLoopEpi epi;
+            epi.r = a.r;
+            epi.wmax_slot = a.wmax + cur;
+            epi.seg_off = a.seg_off;
+            epi.seg_done = a.seg_done;
+            epi.nseg = a.nseg;
+            epi.wmax = 0.0;
+            HbLoopOut po;
+            po.peer = &a.peer;
+            po.local = exch;
+            po.pb = pb;
+            po.world = world;
+            hb_spmv_rows<HbIceLoopEpi, true, VT, true, HbLoopOut>(a.indptr, a.idx, (const VT*)a.val, a.n_rows, a.row0, a.r,
+                                                                  a.row_counters + par, epi, po);
+        }
+        if (peer && lane < world) __threadfence_system();   // each storing lane releases its own peer stores
+        grid.sync();
+        if (peer)
+            hb_loop_publish_and_wait(a.peer, pb, seq, a.n_cols, __longlong_as_double((long long)__ldcg(a.wmax + cur)), a.err);
+        // ---- B: per-tile sum / count of the non-zero marginals
+        for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+            double s = 0.0, c = 0.0;
+            if (__ldcg(a.seg_done + a.tile_seg[t]) == 0) {
+                const int64_t r0 = a.tile_row0[t];
+                const int len = a.tile_len[t];
+                for (int i = threadIdx.x; i < len; i += blockDim.x) {
+                    const double v = __ldcg(exch + r0 + i);
+                    if (v != 0.0) {
+                        s += v;
+                        c += 1.0;
+                    }
+                }
+            }
+            hb_block_sum2(s, c, smem);
+            if (threadIdx.x == 0) {
+                a.tile_sum[t] = s;
+                a.tile_cnt[t] = c;
+            }
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.wmax[cur ^ 1] = 0ull;   // next iteration's accumulator
+        grid.sync();
+        if (peer && __ldcg(a.err) != 0.0) {   // consistent: every writer of err arrived at the barrier before
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                a.status[HB_ST_OVERFLOW] = 2;
+                a.status[HB_ST_ALL_DONE] = 1;
+                a.h_loop[HB_ST_OVERFLOW] = 2;
+                a.h_loop[HB_ST_ALL_DONE] = 1;
+            }
+            executed = it + 1;
+            break;
+        }
+        // ---- C: normalise, accumulate the bias, deviation, next scaling vector
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            double wm = 0.0;
+            if (peer) {
+                for (int q = 0; q < world; ++q) wm = fmax(wm, __ldcg(exch + a.n_cols + q));
+            } else {
+                wm = __longlong_as_double((long long)__ldcg(a.wmax + cur));
+            }
+            if (wm > 1e100) a.status[HB_ST_OVERFLOW] = 1;   // iterativeCorrection.py:58
+        }
+        int cached_seg = -1;
+        double mean = 0.0;
+        for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+            const int seg = a.tile_seg[t];
+            if (__ldcg(a.seg_done + seg) != 0) continue;
+            if (seg != cached_seg) {
+                double sa = 0.0, sb = 0.0;
+                for (int i = a.seg_tile0[seg] + threadIdx.x; i < a.seg_tile0[seg + 1]; i += blockDim.x) {
+                    sa += __ldcg(a.tile_sum + i);
+                    sb += __ldcg(a.tile_cnt + i);
+                }
+                hb_block_sum2(sa, sb, smem);
+                if (threadIdx.x == 0) s_mean = sa / sb;
+                __syncthreads();
+                mean = s_mean;
+                cached_seg = seg;
+            }
+            const int64_t r0 = a.tile_row0[t];
+            const int len = a.tile_len[t];
+            unsigned long long dmax = 0ull;
+            for (int i = threadIdx.x; i < len; i += blockDim.x) {
+                const int64_t g = r0 + i;
+                const double sraw = __ldcg(exch + g);
+                const double sv = sraw / mean;
+                a.bias[g] *= sv;
+                const unsigned long long d = (unsigned long long)__double_as_longlong(fabs(sv - 1.0));
+                dmax = d > dmax ? d : dmax;
+                a.r[g] = (sraw == 0.0) ? 0.0 : a.r[g] * (1.0 / sv);
+            }
+            dmax = hb_warp_max_u64(dmax);
+            __syncthreads();
+            if (lane == 0) smax[warp] = dmax;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (int i = 1; i < (int)(blockDim.x >> 5); ++i) dmax = smax[i] > dmax ? smax[i] : dmax;
+                atomicMax(a.devbits + (size_t)cur * a.nseg + seg, dmax);
+            }
+        }
+        grid.sync();
+        // ---- D: convergence per segment; every CTA computes the same answers from the same maxima
+        if (threadIdx.x == 0) s_active = 0;
+        __syncthreads();
+        int my_active = 0;
+        for (int sg = threadIdx.x; sg < a.nseg; sg += blockDim.x) {
+            if (__ldcg(a.seg_done + sg) == 0) {
+                const double dev = __longlong_as_double((long long)__ldcg(a.devbits + (size_t)cur * a.nseg + sg));
+                if (dev < a.tol) {   // strict '<', tested after the rescale (iterativeCorrection.py:72)
+                    // idempotent writes: every CTA stores the same values
+                    a.seg_dev[sg] = dev;
+                    a.seg_iters[sg] = it_base + it + 1;
+                    a.seg_done[sg] = 1;
+                } else {
+                    a.seg_dev[sg] = dev;
+                    a.seg_iters[sg] = it_base + it + 1;
+                    my_active += 1;
+                }
+            }   // else: finished earlier, or another CTA has just recorded its convergence -- not active either way
+            a.devbits[(size_t)(cur ^ 1) * a.nseg + sg] = 0ull;
+        }
+        if (my_active) atomicAdd(&s_active, my_active);
+        __syncthreads();
+        const int active = s_active;
+        const int overflow = __ldcg(a.status + HB_ST_OVERFLOW);
+        executed = it + 1;
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            a.status[HB_ST_ITER] = it_base + it + 1;
+            a.status[HB_ST_ACTIVE] = active;
+            a.h_loop[HB_ST_ITER] = it_base + it + 1;
+            a.h_loop[HB_ST_ACTIVE] = active;
+            if (active == 0 || overflow != 0) {
+                a.status[HB_ST_ALL_DONE] = 1;
+                a.h_loop[HB_ST_OVERFLOW] = overflow;
+                a.h_loop[HB_ST_ALL_DONE] = 1;
+            }
+        }
+        if (active == 0 || overflow != 0) break;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        a.row_counters[0] = a.row_counters[1] = 0ull;   // both armed for whichever launch comes next
+        a.h_loop[HB_LP_EXCHANGES] = executed;
+        __threadfence_system();
+    }
+}
+
 static cudaStream_t pick_stream(hb_csr* h, void* stream) { return stream ? (cudaStream_t)stream : h->stream; }
 
 extern "C" {
@@ -269,6 +524,9 @@ int hb_dev_ice_begin(hb_csr* h, void* stream) {
     HB_REQUIRE(h != nullptr, "null handle");
     int rc = hb_ensure_state(h);
     if (rc) return rc;
+    rc = hb_loop_settle(h);
+    if (rc) return rc;
+    for (int i = 0; i < HB_LOOP_WORDS; ++i) ((volatile int32_t*)h->h_loop)[i] = 0;
     cudaStream_t s = pick_stream(h, stream);
     int64_t n = h->n_cols;
     int grid = (int)((n + 255) / 256);
@@ -338,6 +596,71 @@ int hb_dev_ice_update(hb_csr* h, const double* d_exch, int world, double tol, vo
     return HB_OK;
 }
 
+// Enqueue ONE cooperative launch that runs up to `iters` ICE iterations (fewer if every segment converges, a value
+// exceeds 1e100 or a peer times out).  Asynchronous; the state continues from wherever hb_dev_ice_begin / earlier
+// launches left it.  Needs the whole exchange on the device: one GPU, or peer mode.
+static bool hb_persistent_enabled() {
+    const char* e = getenv("HB_NO_PERSISTENT");
+    return !(e != nullptr && e[0] == '1');
+}
+
+int hb_dev_ice_loop(hb_csr* h, int iters, double tol, void* stream) {
+    HB_REQUIRE(h != nullptr && h->state_ready, "call hb_dev_ice_begin first");
+    HB_REQUIRE(iters >= 0, "negative iteration count");
+    HB_REQUIRE(h->world == 1 || h->peer, "hb_dev_ice_loop needs the exchange on the device (one GPU or hb_peer_attach)");
+    if (iters == 0) return HB_OK;
+    int rc = hb_loop_settle(h);
+    if (rc) return rc;
+    cudaStream_t s = pick_stream(h, stream);
+    HbIceLoopArgs a;
+    memset(&a, 0, sizeof(a));
+    a.indptr = h->d_indptr;
+    a.idx = h->d_indices;
+    a.val = h->pack_kind ? h->d_pack : (const void*)h->d_data;
+    a.n_rows = h->n_rows;
+    a.row0 = h->row0;
+    a.n_cols = h->n_cols;
+    a.tile_row0 = h->d_tile_row0;
+    a.tile_len = h->d_tile_len;
+    a.tile_seg = h->d_tile_seg;
+    a.seg_tile0 = h->d_seg_tile0;
+    a.seg_off = h->d_seg_off;
+    a.n_tiles = h->n_tiles;
+    a.nseg = h->nseg;
+    a.bias = h->d_bias;
+    a.r = h->d_r;
+    a.exch = h->d_exch;
+    a.tile_sum = h->d_tile_sum;
+    a.tile_cnt = h->d_tile_cnt;
+    a.devbits = h->d_loop_devbits;
+    a.wmax = h->d_loop_wmax;
+    a.seg_dev = h->d_seg_dev;
+    a.seg_done = h->d_seg_done;
+    a.seg_iters = h->d_seg_iters;
+    a.status = h->d_status;
+    a.h_loop = h->h_loop_dev;
+    a.row_counters = h->d_row_counter;
+    a.err = h->d_loop_err;
+    a.iters = iters;
+    a.row_parity = h->spmv_parity;
+    a.tol = tol;
+    hb_fill_loop_peer(h, &a.peer);
+    HB_CUDA(cudaMemsetAsync(h->d_loop_devbits, 0, sizeof(unsigned long long) * 2 * (size_t)h->nseg, s));
+    HB_CUDA(cudaMemsetAsync(h->d_loop_wmax, 0, 24, s));   // wmax[2] | err
+    const void* fn = h->pack_kind == 1   ? (const void*)hb_ice_loop_kernel<uint16_t>
+                     : h->pack_kind == 2 ? (const void*)hb_ice_loop_kernel<float>
+                                         : (const void*)hb_ice_loop_kernel<double>;
+    const int grid = hb_coop_grid(fn, h->n_rows, h->device);
+    void* params[] = {(void*)&a};
+    HB_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(HB_SPMV_THREADS), params, 0, s));
+    g_hb_launches.fetch_add(1, std::memory_order_relaxed);
+    if (h->peer) {
+        HB_CUDA(cudaEventRecord(h->loop_event, s));
+        h->loop_pending = true;
+    }
+    return HB_OK;
+}
+
 int hb_dev_ice_status(hb_csr* h, int32_t* pinned_status4, void* stream) {
     HB_REQUIRE(h != nullptr && h->state_ready && pinned_status4 != nullptr, "bad arguments");
     HB_CUDA(cudaMemcpyAsync(pinned_status4, h->d_status, sizeof(int32_t) * HB_ST_WORDS, cudaMemcpyDeviceToHost,
@@ -404,35 +727,46 @@ int hb_ice_run(hb_csr* h, int max_iter, double tol, double* bias_out, int32_t* i
     if (rc) return rc;
     rc = hb_dev_ice_begin(h, nullptr);
     if (rc) return rc;
-    const int LAG = 4, SLOTS = 16;
-    cudaEvent_t ev[SLOTS];
-    for (int i = 0; i < SLOTS; ++i) HB_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
-    bool stop = false;
-    for (int k = 0; k < max_iter && !stop; ++k) {
-        rc = hb_dev_ice_spmv(h, nullptr, h->rank, h->world, nullptr);
-        if (rc == HB_OK && h->world > 1 && !h->peer) {
-            // the one exchange of the iteration: marginals + per-rank maxima, summed over the ranks
-            if (h->allreduce(h->comm_ctx, h->d_exch, h->n_cols + h->world, (void*)h->stream) != 0) {
-                hb_set_error("collective callback failed");
-                rc = HB_ERR_CUDA;
+    if ((h->world == 1 || h->peer) && hb_persistent_enabled()) {
+        // the whole loop is one cooperative launch; the host waits once
+        rc = hb_dev_ice_loop(h, max_iter, tol, nullptr);
+        if (rc != HB_OK) return rc;
+        HB_CUDA(cudaStreamSynchronize(h->stream));
+        rc = hb_loop_settle(h);
+        if (rc != HB_OK) return rc;
+    } else {
+        // step-level path (host collective between the SpMV and the update, or HB_NO_PERSISTENT=1)
+        const int LAG = 4, SLOTS = 16;
+        cudaEvent_t ev[SLOTS];
+        for (int i = 0; i < SLOTS; ++i) HB_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+        bool stop = false;
+        for (int k = 0; k < max_iter && !stop; ++k) {
+            rc = hb_dev_ice_spmv(h, nullptr, h->rank, h->world, nullptr);
+            if (rc == HB_OK && h->world > 1 && !h->peer) {
+                // the one exchange of the iteration: marginals + per-rank maxima, summed over the ranks
+                if (h->allreduce == nullptr ||
+                    h->allreduce(h->comm_ctx, h->d_exch, h->n_cols + h->world, (void*)h->stream) != 0) {
+                    hb_set_error("collective callback failed");
+                    rc = HB_ERR_CUDA;
+                }
+            }
+            if (rc == HB_OK) rc = hb_dev_ice_update(h, nullptr, h->world, tol, nullptr);
+            if (rc == HB_OK) rc = hb_dev_ice_status(h, h->h_status + (k % SLOTS) * HB_ST_WORDS, nullptr);
+            if (rc != HB_OK) break;
+            cudaEventRecord(ev[k % SLOTS], h->stream);
+            if (k >= LAG) {
+                // look at the status of iteration k-LAG: the device queue stays LAG iterations deep and
+                // iterations enqueued after convergence are no-ops (every kernel returns on ALL_DONE)
+                int j = (k - LAG) % SLOTS;
+                cudaEventSynchronize(ev[j]);
+                if (h->h_status[j * HB_ST_WORDS + HB_ST_ALL_DONE]) stop = true;
             }
         }
-        if (rc == HB_OK) rc = hb_dev_ice_update(h, nullptr, h->world, tol, nullptr);
-        if (rc == HB_OK) rc = hb_dev_ice_status(h, h->h_status + (k % SLOTS) * HB_ST_WORDS, nullptr);
-        if (rc != HB_OK) break;
-        cudaEventRecord(ev[k % SLOTS], h->stream);
-        if (k >= LAG) {
-            // look at the status of iteration k-LAG: the device queue stays LAG iterations deep and
-            // iterations enqueued after convergence are no-ops (every kernel returns on ALL_DONE)
-            int j = (k - LAG) % SLOTS;
-            cudaEventSynchronize(ev[j]);
-            if (h->h_status[j * HB_ST_WORDS + HB_ST_ALL_DONE]) stop = true;
-        }
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        for (int i = 0; i < SLOTS; ++i) cudaEventDestroy(ev[i]);
+        if (rc != HB_OK) return rc;
+        if (e != cudaSuccess) return hb_cuda_fail(e, "ICE loop", __FILE__, __LINE__);
     }
-    cudaError_t e = cudaStreamSynchronize(h->stream);
-    for (int i = 0; i < SLOTS; ++i) cudaEventDestroy(ev[i]);
-    if (rc != HB_OK) return rc;
-    if (e != cudaSuccess) return hb_cuda_fail(e, "ICE loop", __FILE__, __LINE__);
     int32_t st[HB_ST_WORDS];
     HB_CUDA(cudaMemcpy(st, h->d_status, sizeof(st), cudaMemcpyDeviceToHost));
     if (st[HB_ST_OVERFLOW] == 2) {

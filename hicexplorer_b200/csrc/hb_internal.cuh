@@ -55,6 +55,8 @@ int hb_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 // status words kept on the device (int32 each)
 enum { HB_ST_ALL_DONE = 0, HB_ST_OVERFLOW = 1, HB_ST_ITER = 2, HB_ST_ACTIVE = 3, HB_ST_WORDS = 4 };
+// pinned progress words of the persistent solver kernels: the first four mirror the status words above
+enum { HB_LP_EXCHANGES = 4, HB_LP_OUTER = 5, HB_LP_MATVECS = 6, HB_LP_FLAGS = 7, HB_LOOP_WORDS = 16 };
 
 struct hb_csr {
     int device = 0;
@@ -81,6 +83,7 @@ struct hb_csr {
     bool peer = false;
     void* d_sym = nullptr;                          // this rank's region (cudaMalloc, exported through CUDA IPC)
     void* peer_base[HB_MAX_PEERS] = {nullptr};      // every rank's region mapped here (own entry = d_sym)
+    bool peer_ipc[HB_MAX_PEERS] = {false};          // mapping came from cudaIpcOpenMemHandle (to be closed)
     size_t sym_buf_bytes = 0, sym_flag_off = 0;     // layout: buf p at p*sym_buf_bytes ; flags p at sym_flag_off + p*512
     unsigned long long peer_seq = 0;                // exchange sequence number (monotonic)
     unsigned int* d_done = nullptr;                 // ticket counter of the publishing SpMV
@@ -117,6 +120,14 @@ struct hb_csr {
     int spmv_parity = 0;
     unsigned long long* d_scalar_bits = nullptr; // 8 scratch words
     int32_t* h_status = nullptr;       // pinned, 16 slots x HB_ST_WORDS
+    // persistent solver kernels (hb_ice_loop_kernel / hb_kr_solve_kernel): one cooperative launch runs the whole loop
+    unsigned long long* d_loop_devbits = nullptr;  // 2 x nseg: deviation maxima, ping-pong by iteration parity
+    unsigned long long* d_loop_wmax = nullptr;     // 2 words: running maximum of the rescaled values, ping-pong
+    double* d_loop_err = nullptr;                  // != 0: a peer did not publish in time
+    int32_t* h_loop = nullptr;         // pinned + mapped, HB_LOOP_WORDS: progress written by the kernel itself
+    int32_t* h_loop_dev = nullptr;     // device alias of h_loop
+    bool loop_pending = false;         // a loop kernel is in flight whose exchange count is not yet added to peer_seq
+    cudaEvent_t loop_event = nullptr;
     double* d_kr_buf = nullptr;        // Knight-Ruiz workspace (8 n-vectors + tile partials + scalars), kept across calls
     size_t kr_buf_words = 0;
     double* h_kr_sc = nullptr;         // pinned mirror of the KR scalars
@@ -147,6 +158,8 @@ void hb_free_state(hb_csr* h);
 int hb_use_device(const hb_csr* h);
 int hb_spmv_grid(int64_t n_rows);
 void hb_peer_release(hb_csr* h);
+int hb_loop_settle(hb_csr* h);                       // fold a finished loop kernel's exchange count into peer_seq
+int hb_coop_grid(const void* kernel, int64_t n_rows, int device);   // co-resident persistent grid for a cooperative launch
 void hb_drop_pack(hb_csr* h);
 // multi-threaded staged copies for pageable caller buffers (hb_xfer.cu); synchronous
 int hb_copy_h2d(void* d_dst, const void* h_src, size_t bytes, int device);

@@ -10,10 +10,15 @@
 // row tiles (deterministic, rank-count independent) into device-resident scalars.  alpha, beta
 // and the step decisions are computed FROM those device scalars, so the host synchronises once
 // per mat-vec (to evaluate the loop conditions), not once per vector operation.
+#include <cooperative_groups.h>
+
 #include <cmath>
+#include <cstdlib>
 
 #include "hb_scan.cuh"
 #include "hb_spmv.cuh"
+
+namespace cg = cooperative_groups;
 
 enum {
     SC_RHO = 0,    // rho_km1
@@ -40,12 +45,59 @@ struct HbTiles {
     int n_tiles;
 };
 
-// Generic tiled vector kernel: F::elem runs per row and may contribute to a sum / min / max; the
-// last block to finish folds the per-tile partials in tile order and calls F::finalize (thread 0).
+// Block-wide (256 threads) fixed-order reduction of (sum, min, max); the result is valid in thread 0.
+__device__ __forceinline__ void hb_block_red3(double& s, double& mn, double& mx, double* sh /* 24 */) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    s = hb_warp_sum(s);
+    mx = hb_warp_max(mx);
+    mn = -hb_warp_max(-mn);
+    __syncthreads();   // sh may still be read from the previous use
+    if (lane == 0) {
+        sh[w] = s;
+        sh[8 + w] = mn;
+        sh[16 + w] = mx;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) {
+            s += sh[i];
+            mn = fmin(mn, sh[8 + i]);
+            mx = fmax(mx, sh[16 + i]);
+        }
+    }
+}
+
+// Fold the per-tile partials (sum, min, max) in tile order; every thread of the block returns the result.
+__device__ __forceinline__ void hb_fold3(const double* part, int n_tiles, double& s, double& mn, double& mx,
+                                         double* sh /* 24 */, double* bc /* 3 */) {
+    s = 0.0;
+    mn = INFINITY;
+    mx = -INFINITY;
+    for (int i = threadIdx.x; i < n_tiles; i += blockDim.x) {
+        s += __ldcg(part + 3 * i + 0);
+        mn = fmin(mn, __ldcg(part + 3 * i + 1));
+        mx = fmax(mx, __ldcg(part + 3 * i + 2));
+    }
+    hb_block_red3(s, mn, mx, sh);
+    if (threadIdx.x == 0) {
+        bc[0] = s;
+        bc[1] = mn;
+        bc[2] = mx;
+    }
+    __syncthreads();
+    s = bc[0];
+    mn = bc[1];
+    mx = bc[2];
+}
+
+// Generic tiled vector kernel (step-level path: one launch per vector operation): F::elem runs per row and may
+// contribute to a sum / min / max; the last block to finish folds the per-tile partials in tile order and calls
+// F::finalize (thread 0).  The persistent solver kernel below runs the same element code and the same two reduction
+// helpers, so both paths give bit-identical results.
 template <class F>
 __global__ void __launch_bounds__(256)
 hb_kr_vec_kernel(HbTiles tiles, F f, double* __restrict__ part /* 3*n_tiles */, unsigned int* counter, double* sc) {
-    __shared__ double ssum[8], smin[8], smax[8];
+    __shared__ double sh[24], bc[3];
     __shared__ int s_last;
     if (f.skip(sc)) return;
     f.prepare(sc);
@@ -55,22 +107,8 @@ hb_kr_vec_kernel(HbTiles tiles, F f, double* __restrict__ part /* 3*n_tiles */, 
     double s = 0.0, mn = INFINITY, mx = -INFINITY;
     for (int i = threadIdx.x; i < len; i += blockDim.x) f.elem(r0 + i, s, mn, mx);
     if (!F::REDUCES) return;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    s = hb_warp_sum(s);
-    mx = hb_warp_max(mx);
-    mn = -hb_warp_max(-mn);
-    if (lane == 0) {
-        ssum[w] = s;
-        smin[w] = mn;
-        smax[w] = mx;
-    }
-    __syncthreads();
+    hb_block_red3(s, mn, mx, sh);
     if (threadIdx.x == 0) {
-        for (int i = 1; i < 8; ++i) {
-            s += ssum[i];
-            mn = fmin(mn, smin[i]);
-            mx = fmax(mx, smax[i]);
-        }
         part[3 * t + 0] = s;
         part[3 * t + 1] = mn;
         part[3 * t + 2] = mx;
@@ -80,30 +118,8 @@ hb_kr_vec_kernel(HbTiles tiles, F f, double* __restrict__ part /* 3*n_tiles */, 
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    s = 0.0;
-    mn = INFINITY;
-    mx = -INFINITY;
-    for (int i = threadIdx.x; i < tiles.n_tiles; i += blockDim.x) {
-        s += __ldcg(part + 3 * i + 0);
-        mn = fmin(mn, __ldcg(part + 3 * i + 1));
-        mx = fmax(mx, __ldcg(part + 3 * i + 2));
-    }
-    s = hb_warp_sum(s);
-    mx = hb_warp_max(mx);
-    mn = -hb_warp_max(-mn);
-    __syncthreads();
-    if (lane == 0) {
-        ssum[w] = s;
-        smin[w] = mn;
-        smax[w] = mx;
-    }
-    __syncthreads();
+    hb_fold3(part, tiles.n_tiles, s, mn, mx, sh, bc);
     if (threadIdx.x == 0) {
-        for (int i = 1; i < 8; ++i) {
-            s += ssum[i];
-            mn = fmin(mn, smin[i]);
-            mx = fmax(mx, smax[i]);
-        }
         *counter = 0u;
         f.finalize(s, mn, mx, sc);
     }
@@ -132,7 +148,7 @@ struct FResid : FBase {
     __device__ __forceinline__ void elem(int64_t g, double& s, double&, double&) const {
         const double r = 1.0 - q.v[g];
         q.rk[g] = r;
-        s += r * r;
+        s = fma(r, r, s);
     }
     __device__ __forceinline__ void finalize(double s, double, double, double* sc) const {
         sc[SC_ROUT] = s;
@@ -149,7 +165,7 @@ struct FFirst : FBase {
         q.z[g] = z;
         q.p[g] = z;
         q.u[g] = q.x[g] * z;
-        s += r * z;
+        s = fma(r, z, s);
     }
     __device__ __forceinline__ void finalize(double s, double, double, double* sc) const { sc[SC_RHO] = s; }
 };
@@ -171,7 +187,7 @@ struct FDir : FBase {
 // PTW = p^T w
 struct FDot : FBase {
     HbKrVec q;
-    __device__ __forceinline__ void elem(int64_t g, double& s, double&, double&) const { s += q.p[g] * q.w[g]; }
+    __device__ __forceinline__ void elem(int64_t g, double& s, double&, double&) const { s = fma(q.p[g], q.w[g], s); }
     __device__ __forceinline__ void finalize(double s, double, double, double* sc) const { sc[SC_PTW] = s; }
 };
 
@@ -204,7 +220,7 @@ struct FStep : FBase {
         q.rk[g] = r;
         const double z = r / q.v[g];
         q.z[g] = z;
-        s += r * z;
+        s = fma(r, z, s);
     }
     __device__ __forceinline__ void finalize(double s, double, double, double* sc) const {
         sc[SC_RHO2] = sc[SC_RHO];
@@ -350,7 +366,303 @@ hb_kr_upper_fill_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
 }
 
 
+// ---------------------------------------------------------------------------------------------------------------
+// The whole Knight-Ruiz solve in ONE cooperative launch (hb_kr_solve_kernel): `bnewt`'s outer Newton loop, the inner
+// conjugate-gradient loop, its cone-boundary branches and the eta update all run on the device.  Every CG step is
+//     P1  [apply the previous step: y += alpha p ; rk -= alpha w]  p = rk/v + beta p ; u = x o p      -- grid barrier
+//     SpMV  w = x o ((A + eps I) u) + v o p  over the block's rows, Hadamard update fused in the row epilogue
+//           (peer mode: rows stored into every replica over NVLink)                                   -- grid barrier
+//     P2  per-tile partials of p^T w                                                                  -- grid barrier
+//     P3  alpha = rho / p^T w ; per-tile min / max of y + alpha p and the rk^T Z of the tentative step -- grid barrier
+// after each barrier EVERY CTA folds the per-tile partials in tile order, so all CTAs (and all ranks) hold the same
+// scalars bit for bit and take the same branches; nothing is ever read back by the host.  The element arithmetic and
+// the two reduction helpers are those of the step-level kernels above -> identical results.
+struct HbKrSolveArgs {
+    const int64_t* indptr;
+    const int32_t* idx;
+    const void* val;
+    int64_t n_rows, row0, n_cols;
+    const int64_t* tile_row0;
+    const int32_t* tile_len;
+    int n_tiles;
+    double *x, *y, *p, *rk, *v, *w, *u;
+    double* part;   // 6 x 3 x n_tiles
+    double* sc;     // SC_WORDS: results
+    int32_t* h_loop;
+    unsigned long long* row_counters;
+    double* err;
+    double tol, delta, Delta, eps;
+    int max_outer, row_parity;
+    HbLoopPeer peer;
+};
+
+enum { KP_FIRST = 0, KP_DOT = 1, KP_STEP = 2, KP_GAMMA = 3, KP_RESID = 4, KP_XMIN = 5, KP_ARRAYS = 6 };
+
+// w_g = x_g (t + eps u_g) [+ v_g p_g]; all operands are rewritten inside the launch -> L2 loads
+struct HbKrLoopEpi {
+    const double* u;
+    const double* x;
+    const double* v;   // nullptr: outer residual  v = x o ((A + eps I) x)
+    const double* p;
+    double eps;
+    __device__ __forceinline__ bool active(int64_t) const { return true; }
+    template <class Out>
+    __device__ __forceinline__ void row(int64_t g, double t, double, int lane, const Out& out) const {
+        double r = fma(eps, __ldcg(u + g), t);
+        r *= __ldcg(x + g);
+        if (v != nullptr) r = fma(__ldcg(v + g), __ldcg(p + g), r);
+        out.store(g, r, lane);
+    }
+    __device__ __forceinline__ void warp_done() const {}
+    __device__ __forceinline__ double local_max() const { return 0.0; }
+};
+
+template <typename VT>
+__global__ void __launch_bounds__(HB_SPMV_THREADS, HB_SPMV_CTAS_PER_SM)
+hb_kr_solve_kernel(const __grid_constant__ HbKrSolveArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sh[24], bc[3];
+    const int lane = threadIdx.x & 31;
+    const bool peer = a.peer.world > 1;
+    const int world = peer ? a.peer.world : 1;
+    const int nt = a.n_tiles;
+    double* const part = a.part;
+    int exchanges = 0;
+    int code = 0;   // 0 ok, 1 breakdown, 2 peer timeout
+
+    // one exchange: SpMV over the block's rows + grid barrier (+ flags); returns where the assembled vector is
+    auto exchange = [&](const double* gathered, bool with_vp) -> const double* {
+        const unsigned long long seq = a.peer.seq0 + 1ull + (unsigned long long)exchanges;
+        const int pb = (int)(seq & 1ull);
+        const int par = (a.row_parity + exchanges) & 1;
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.row_counters[par ^ 1] = 0ull;
+        HbKrLoopEpi epi;
+        epi.u = gathered;
+        epi.x = a.x;
+        epi.v = with_vp ? a.v : nullptr;
+        epi.p = a.p;
+        epi.eps = a.eps;
+        HbLoopOut po;
+        po.peer = &a.peer;
+        po.local = a.w;
+        po.pb = pb;
+        po.world = world;
+        hb_spmv_rows<HbKrLoopEpi, false, VT, true, HbLoopOut>(a.indptr, a.idx, (const VT*)a.val, a.n_rows, a.row0, gathered,
+                                                               a.row_counters + par, epi, po);
+        if (peer && lane < world) __threadfence_system();
+        grid.sync();
+        if (peer) hb_loop_publish_and_wait(a.peer, pb, seq, a.n_cols, 0.0, a.err);
+        ++exchanges;
+        return peer ? a.peer.buf[pb][a.peer.rank] : a.w;
+    };
+    // per-tile pass: f(g, s, mn, mx) over this CTA's tiles, partials into array `which` (or none)
+    auto tile_pass = [&](int which, auto f) {
+        for (int t = blockIdx.x; t < nt; t += gridDim.x) {
+            const int64_t r0 = a.tile_row0[t];
+            const int len = a.tile_len[t];
+            double s = 0.0, mn = INFINITY, mx = -INFINITY;
+            for (int i = threadIdx.x; i < len; i += blockDim.x) f(r0 + i, s, mn, mx);
+            if (which >= 0) {
+                hb_block_red3(s, mn, mx, sh);
+                if (threadIdx.x == 0) {
+                    double* q = part + (size_t)which * 3 * nt + 3 * t;
+                    q[0] = s;
+                    q[1] = mn;
+                    q[2] = mx;
+                }
+            }
+        }
+    };
+    auto fold = [&](int which, double& s, double& mn, double& mx) {
+        hb_fold3(part + (size_t)which * 3 * nt, nt, s, mn, mx, sh, bc);
+    };
+
+    const double g = 0.9, etamax = 0.1;
+    double eta = etamax;
+    const double stop_tol = a.tol * 0.5, rt = a.tol * a.tol;
+    double rho = 0.0, rho2 = 0.0, rout = 0.0, rold = 0.0, dummy0, dummy1;
+    int outer = 0, mvp = 0;
+
+    // x = y = 1 ; v = x o ((A + eps I) x) ; rk = 1 - v ; rho = rout = rk^T rk
+    tile_pass(-1, [&](int64_t i, double&, double&, double&) {
+        a.x[i] = 1.0;
+        a.y[i] = 1.0;
+    });
+    grid.sync();
+    {
+        const double* vin = exchange(a.x, false);
+        tile_pass(KP_RESID, [&](int64_t i, double& s, double&, double&) {
+            const double vv = __ldcg(vin + i);
+            a.v[i] = vv;
+            const double r = 1.0 - vv;
+            a.rk[i] = r;
+            s = fma(r, r, s);
+        });
+        grid.sync();
+        if (peer && __ldcg(a.err) != 0.0) code = 2;
+        fold(KP_RESID, rho, dummy0, dummy1);
+        rout = rold = rho;
+    }
+    while (code == 0 && rout > rt && outer < a.max_outer) {
+        ++outer;
+        int k = 0;
+        const double innertol = fmax(eta * eta * rout, rt);
+        bool pending = false;
+        double alpha = 0.0;
+        const double* wv = a.w;
+        while (rho > innertol) {
+            ++k;
+            if (k == 1) {
+                // Z = rk / v ; p = Z ; u = x o p ; rho = rk^T Z
+                tile_pass(KP_FIRST, [&](int64_t i, double& s, double&, double&) {
+                    const double r = a.rk[i];
+                    const double z = r / a.v[i];
+                    a.p[i] = z;
+                    a.u[i] = a.x[i] * z;
+                    s = fma(r, z, s);
+                });
+            } else {
+                // the step accepted last time, then the new direction: beta = rho / rho2 ; p = Z + beta p ; u = x o p
+                const double beta = rho / rho2;
+                const double al = alpha;
+                const double* wl = wv;
+                tile_pass(-1, [&](int64_t i, double&, double&, double&) {
+                    const double pi = a.p[i];
+                    a.y[i] = a.y[i] + __dmul_rn(al, pi);
+                    const double r = a.rk[i] - __dmul_rn(al, __ldcg(wl + i));
+                    a.rk[i] = r;
+                    const double z = r / a.v[i];
+                    const double pn = z + __dmul_rn(beta, pi);
+                    a.p[i] = pn;
+                    a.u[i] = a.x[i] * pn;
+                });
+                pending = false;
+            }
+            grid.sync();
+            if (k == 1) fold(KP_FIRST, rho, dummy0, dummy1);
+            // w = x o ((A + eps I)(x o p)) + v o p
+            wv = exchange(a.u, true);
+            {
+                const double* wl = wv;
+                tile_pass(KP_DOT, [&](int64_t i, double& s, double&, double&) { s = fma(a.p[i], __ldcg(wl + i), s); });
+            }
+            grid.sync();
+            if (peer && __ldcg(a.err) != 0.0) {
+                code = 2;
+                break;
+            }
+            double ptw;
+            fold(KP_DOT, ptw, dummy0, dummy1);
+            alpha = rho / ptw;
+            // ynew = y + alpha p : min / max ; tentative step rk - alpha w -> rk^T Z
+            {
+                const double al = alpha;
+                const double* wl = wv;
+                tile_pass(KP_STEP, [&](int64_t i, double& s, double& mn, double& mx) {
+                    const double yn = a.y[i] + __dmul_rn(al, a.p[i]);
+                    mn = fmin(mn, yn);
+                    mx = fmax(mx, yn);
+                    const double r = a.rk[i] - __dmul_rn(al, __ldcg(wl + i));
+                    const double z = r / a.v[i];
+                    s = fma(r, z, s);
+                });
+            }
+            grid.sync();
+            double rho_new, ymin, ymax;
+            fold(KP_STEP, rho_new, ymin, ymax);
+            const bool low = ymin <= a.delta;
+            const bool high = !low && ymax >= a.Delta;
+            if (low || high) {
+                if (low && a.delta == 0.0) break;
+                // boundary step: gamma = min (bound - y) / (alpha p) over the offending entries ; y += gamma alpha p
+                const double bound = low ? a.delta : a.Delta;
+                const double al = alpha;
+                tile_pass(KP_GAMMA, [&](int64_t i, double&, double& mn, double&) {
+                    const double ap = __dmul_rn(al, a.p[i]);
+                    const double yy = a.y[i];
+                    const bool sel = high ? (yy + ap > bound) : (ap < 0.0);
+                    if (sel) mn = fmin(mn, (bound - yy) / ap);
+                });
+                grid.sync();
+                double gamma;
+                fold(KP_GAMMA, dummy0, gamma, dummy1);
+                tile_pass(-1, [&](int64_t i, double&, double&, double&) {
+                    a.y[i] = a.y[i] + __dmul_rn(gamma, __dmul_rn(al, a.p[i]));
+                });
+                break;
+            }
+            pending = true;   // y, rk are updated by the next pass that touches them
+            rho2 = rho;
+            rho = rho_new;
+            if (!(rho == rho)) {
+                code = 1;
+                break;
+            }
+        }
+        if (code != 0) break;
+        // x = x o y ; y = 1 ; min(x)   (with the last accepted step folded in)
+        {
+            const double al = alpha;
+            const bool pend = pending;
+            tile_pass(KP_XMIN, [&](int64_t i, double&, double& mn, double&) {
+                double yy = a.y[i];
+                if (pend) yy = yy + __dmul_rn(al, a.p[i]);
+                const double xn = a.x[i] * yy;
+                a.x[i] = xn;
+                a.y[i] = 1.0;
+                mn = fmin(mn, xn);
+            });
+        }
+        grid.sync();
+        {
+            const double* vin = exchange(a.x, false);
+            tile_pass(KP_RESID, [&](int64_t i, double& s, double&, double&) {
+                const double vv = __ldcg(vin + i);
+                a.v[i] = vv;
+                const double r = 1.0 - vv;
+                a.rk[i] = r;
+                s = fma(r, r, s);
+            });
+        }
+        grid.sync();
+        if (peer && __ldcg(a.err) != 0.0) {
+            code = 2;
+            break;
+        }
+        double xmin;
+        fold(KP_RESID, rho, dummy0, dummy1);
+        fold(KP_XMIN, dummy0, xmin, dummy1);
+        rout = rho;
+        mvp += k + 1;
+        if (!(rout == rout) || !(xmin > 0.0)) {
+            code = 1;
+            break;
+        }
+        const double rat = rout / rold;
+        rold = rout;
+        const double res_norm = sqrt(rout);
+        const double eta_o = eta;
+        eta = g * rat;
+        if (g * eta_o * eta_o > 0.1) eta = fmax(eta, g * eta_o * eta_o);
+        eta = fmax(fmin(eta, etamax), stop_tol / res_norm);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        a.row_counters[0] = a.row_counters[1] = 0ull;
+        a.sc[SC_ROUT] = rout;
+        a.h_loop[HB_LP_OUTER] = outer;
+        a.h_loop[HB_LP_MATVECS] = mvp;
+        a.h_loop[HB_LP_FLAGS] = code;
+        a.h_loop[HB_LP_EXCHANGES] = exchanges;
+        __threadfence_system();
+    }
+}
+
 namespace {
+
+bool hb_kr_persistent_enabled() {
+    const char* e = getenv("HB_NO_PERSISTENT");
+    return !(e != nullptr && e[0] == '1');
+}
 
 struct KrCtx {
     hb_csr* h;
@@ -395,7 +707,7 @@ int kr_spmv(KrCtx& c, const double* u, const double* a, const double* b, const d
         }
     }
     if (h->world > 1 && !h->peer) {
-        if (h->allreduce(h->comm_ctx, out, h->n_cols, (void*)c.s) != 0) {
+        if (h->allreduce == nullptr || h->allreduce(h->comm_ctx, out, h->n_cols, (void*)c.s) != 0) {
             hb_set_error("collective callback failed");
             return HB_ERR_CUDA;
         }
@@ -482,7 +794,7 @@ int hb_kr_run(hb_csr* h, double tol, double delta, double Delta, double diag_eps
     bool breakdown = false;
     {
         // the workspace lives in the handle: repeated calls (and --perchr loops) pay no allocation
-        const size_t words = (size_t)(8 * n + 3 * h->n_tiles + SC_WORDS);
+        const size_t words = (size_t)(8 * n + 3 * KP_ARRAYS * h->n_tiles + SC_WORDS);
         if (h->kr_buf_words < words) {
             cudaFree(h->d_kr_buf);
             h->d_kr_buf = nullptr;
@@ -504,9 +816,11 @@ int hb_kr_run(hb_csr* h, double tol, double delta, double Delta, double diag_eps
         c.q.v = b; b += n;
         c.q.w = b; b += n;
         c.q.u = b; b += n;
-        c.part = b; b += 3 * h->n_tiles;
+        c.part = b; b += 3 * KP_ARRAYS * h->n_tiles;
         c.sc = b;
     }
+    rc = hb_loop_settle(h);
+    if (rc) return rc;
     {
         cudaError_t e = cudaMemsetAsync(c.sc, 0, sizeof(double) * SC_WORDS, c.s);
         if (e == cudaSuccess) e = cudaMemsetAsync(c.counter, 0, sizeof(unsigned int), c.s);
@@ -515,6 +829,65 @@ int hb_kr_run(hb_csr* h, double tol, double delta, double Delta, double diag_eps
             goto done;
         }
     }
+    if ((h->world == 1 || h->peer) && hb_kr_persistent_enabled()) {
+        // the whole solve is one cooperative launch; the host waits once
+        HbKrSolveArgs a;
+        memset(&a, 0, sizeof(a));
+        a.indptr = h->d_indptr;
+        a.idx = h->d_indices;
+        a.val = h->pack_kind ? h->d_pack : (const void*)h->d_data;
+        a.n_rows = h->n_rows;
+        a.row0 = h->row0;
+        a.n_cols = n;
+        a.tile_row0 = h->d_tile_row0;
+        a.tile_len = h->d_tile_len;
+        a.n_tiles = h->n_tiles;
+        a.x = c.q.x;
+        a.y = c.q.y;
+        a.p = c.q.p;
+        a.rk = c.q.rk;
+        a.v = c.q.v;
+        a.w = c.q.w;
+        a.u = c.q.u;
+        a.part = c.part;
+        a.sc = c.sc;
+        a.h_loop = h->h_loop_dev;
+        a.row_counters = h->d_row_counter;
+        a.err = h->d_loop_err;
+        a.tol = tol;
+        a.delta = delta;
+        a.Delta = Delta;
+        a.eps = diag_eps;
+        a.max_outer = max_outer;
+        a.row_parity = h->spmv_parity;
+        hb_fill_loop_peer(h, &a.peer);
+        const void* fn = h->pack_kind == 1   ? (const void*)hb_kr_solve_kernel<uint16_t>
+                         : h->pack_kind == 2 ? (const void*)hb_kr_solve_kernel<float>
+                                             : (const void*)hb_kr_solve_kernel<double>;
+        const int grid = hb_coop_grid(fn, h->n_rows, h->device);
+        void* params[] = {(void*)&a};
+        for (int i = 0; i < HB_LOOP_WORDS; ++i) ((volatile int32_t*)h->h_loop)[i] = 0;
+        cudaError_t e = cudaMemsetAsync(h->d_loop_wmax, 0, 24, c.s);   // wmax[2] | err
+        if (e == cudaSuccess) e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(HB_SPMV_THREADS), params, 0, c.s);
+        g_hb_launches.fetch_add(1, std::memory_order_relaxed);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c.h_sc, c.sc, sizeof(double) * SC_WORDS, cudaMemcpyDeviceToHost, c.s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c.s);
+        if (e != cudaSuccess) {
+            rc = hb_cuda_fail(e, "KR solve kernel", __FILE__, __LINE__);
+            goto done;
+        }
+        const volatile int32_t* lp = (const volatile int32_t*)h->h_loop;
+        h->peer_seq += (unsigned long long)(unsigned int)lp[HB_LP_EXCHANGES];
+        outer = lp[HB_LP_OUTER];
+        mvp = lp[HB_LP_MATVECS];
+        rout = c.h_sc[SC_ROUT];
+        if (lp[HB_LP_FLAGS] == 2) {
+            hb_set_error("peer exchange timed out: a rank did not publish its rows");
+            rc = HB_ERR_CUDA;
+            goto done;
+        }
+        breakdown = lp[HB_LP_FLAGS] == 1;
+    } else {
     {
         FInit f0;
         f0.q = c.q;
@@ -621,6 +994,7 @@ int hb_kr_run(hb_csr* h, double tol, double delta, double Delta, double diag_eps
         if (g * eta_o * eta_o > 0.1) eta = fmax(eta, g * eta_o * eta_o);
         eta = fmax(fmin(eta, etamax), stop_tol / res_norm);
     }
+    }   // step-level path
     {
         cudaError_t e = cudaMemcpyAsync(x_out, c.q.x, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c.s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c.s);
@@ -648,6 +1022,7 @@ int hb_kr_rescale(hb_csr* h, double diag_eps, double* x_inout, double* factor_ou
     if (rc) return rc;
     const int64_t n = h->n_cols;
     if (n == 0) return HB_OK;
+    HB_REQUIRE(h->world == 1 || h->allreduce != nullptr, "sharded hb_kr_rescale needs the allreduce callback (hb_set_comm)");
     cudaStream_t s = h->stream;
     double* buf = nullptr;
     HB_CUDA(cudaMalloc(&buf, sizeof(double) * (size_t)(3 * n + 3 * h->n_tiles + SC_WORDS)));

@@ -25,9 +25,22 @@
 // HB_SPMV_UNROLL independent entries per lane are in flight per step (3 x 16 loads); the tail runs in
 // predicated groups of 4 so short rows still overlap their loads.  There is no alignment requirement,
 // so the summation order does not depend on where a row starts.
-template <bool WANT_MAX, typename VT>
+// COHERENT selects how the gathered vector is read: false = non-coherent read-only path (__ldg; the vector is constant
+// for the whole launch), true = ordinary L1-cached loads that the acquire side of a grid barrier invalidates (the
+// persistent solver kernels rewrite the vector between iterations of one launch).
+template <bool COHERENT>
+__device__ __forceinline__ double hb_ld_gather(const double* p) {
+    if (COHERENT) {
+        double r;
+        asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(r) : "l"(p));
+        return r;
+    }
+    return __ldg(p);
+}
+
+template <bool WANT_MAX, typename VT, bool COHERENT = false>
 __device__ __forceinline__ void hb_row_dot(const int32_t* __restrict__ idx, const VT* __restrict__ val,
-                                           const double* __restrict__ u, int64_t s, int64_t e, int lane,
+                                           const double* u, int64_t s, int64_t e, int lane,
                                            double& sum_out, double& max_out) {
     constexpr int U = HB_SPMV_UNROLL;
     double acc0 = 0.0, acc1 = 0.0;
@@ -41,11 +54,11 @@ __device__ __forceinline__ void hb_row_dot(const int32_t* __restrict__ idx, cons
 #pragma unroll
         for (int j = 0; j < U; ++j) v[j] = hb_ldg_stream_val(val + k + 32 * j);
 #pragma unroll
-        for (int j = 0; j < U; ++j) g[j] = __ldg(u + c[j]);
+        for (int j = 0; j < U; ++j) g[j] = hb_ld_gather<COHERENT>(u + c[j]);
 #pragma unroll
         for (int j = 0; j < U; ++j) {
             if (WANT_MAX) {
-                const double p = v[j] * g[j];
+                const double p = __dmul_rn(v[j], g[j]);   // the product is also the value under the 1e100 guard: no contraction
                 if (j & 1) acc1 += p; else acc0 += p;
                 mx = fmax(mx, p);
             } else {
@@ -61,13 +74,17 @@ __device__ __forceinline__ void hb_row_dot(const int32_t* __restrict__ idx, cons
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] = (k + 32 * j < e) ? hb_ldg_stream_val(val + k + 32 * j) : 0.0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) g[j] = (k + 32 * j < e) ? __ldg(u + c[j]) : 0.0;
+        for (int j = 0; j < 4; ++j) g[j] = (k + 32 * j < e) ? hb_ld_gather<COHERENT>(u + c[j]) : 0.0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             if (k + 32 * j < e) {
-                const double p = v[j] * g[j];
-                if (j & 1) acc1 += p; else acc0 += p;
-                if (WANT_MAX) mx = fmax(mx, p);
+                if (WANT_MAX) {
+                    const double p = __dmul_rn(v[j], g[j]);
+                    if (j & 1) acc1 += p; else acc0 += p;
+                    mx = fmax(mx, p);
+                } else {
+                    if (j & 1) acc1 = fma(v[j], g[j], acc1); else acc0 = fma(v[j], g[j], acc0);
+                }
             }
         }
     }
@@ -134,18 +151,17 @@ static __global__ void hb_peer_wait_kernel(const unsigned long long* __restrict_
 //   __device__ void row(int64_t global_row, double t, double m, int lane, peer);       // all lanes, t and m warp-uniform
 //   __device__ void warp_done();                                                       // lane 0 only, once per warp
 //   __device__ double local_max() const;                                               // last warp: value for slot n+rank
-template <class Epi, bool WANT_MAX, typename VT>
-__global__ void __launch_bounds__(HB_SPMV_THREADS, HB_SPMV_CTAS_PER_SM)
-hb_spmv_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const VT* __restrict__ val,
-               int64_t n_rows, int64_t row0, const double* __restrict__ u, unsigned long long* counters, int parity,
-               const int32_t* __restrict__ status, Epi epi, HbPeerOut peer) {
-    if (status != nullptr && status[HB_ST_ALL_DONE] != 0) return;
+//
+// hb_spmv_rows: the row loop shared by the stand-alone kernel below and by the persistent solver kernels
+// (hb_ice_loop_kernel, hb_kr_solve_kernel).  `counter` must be 0 on entry; whoever calls it re-arms the OTHER counter.
+template <class Epi, bool WANT_MAX, typename VT, bool COHERENT = false, class Out = HbPeerOut>
+__device__ __forceinline__ void hb_spmv_rows(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx,
+                                             const VT* __restrict__ val, int64_t n_rows, int64_t row0,
+                                             const double* u, unsigned long long* counter, Epi& epi,
+                                             const Out& peer) {
     const int lane = threadIdx.x & 31;
     const int64_t gwarp = (int64_t)blockIdx.x * (HB_SPMV_THREADS / 32) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (HB_SPMV_THREADS / 32);
-    unsigned long long* counter = counters + parity;
-    if (blockIdx.x == 0 && threadIdx.x == 0) counters[parity ^ 1] = 0ull;  // arm the next launch's counter
-
     int64_t batch = gwarp * HB_ROWS_PER_GRAB;
     while (batch < n_rows) {
         // claim the next batch now; its latency hides behind this batch's rows
@@ -160,7 +176,7 @@ hb_spmv_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ i
             const int64_t row = batch + q;
             if (row < n_rows && epi.active(row0 + row)) {
                 double t, m = 0.0;
-                hb_row_dot<WANT_MAX, VT>(idx, val, u, s, e, lane, t, m);
+                hb_row_dot<WANT_MAX, VT, COHERENT>(idx, val, u, s, e, lane, t, m);
                 epi.row(row0 + row, t, m, lane, peer);
             }
         }
@@ -168,23 +184,113 @@ hb_spmv_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ i
         batch = nwarps * HB_ROWS_PER_GRAB + (int64_t)nxt;
     }
     if (lane == 0) epi.warp_done();
+}
+
+template <class Epi, bool WANT_MAX, typename VT>
+__global__ void __launch_bounds__(HB_SPMV_THREADS, HB_SPMV_CTAS_PER_SM)
+hb_spmv_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const VT* __restrict__ val,
+               int64_t n_rows, int64_t row0, const double* __restrict__ u, unsigned long long* counters, int parity,
+               const int32_t* __restrict__ status, Epi epi, HbPeerOut peer) {
+    if (status != nullptr && status[HB_ST_ALL_DONE] != 0) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = (int64_t)gridDim.x * (HB_SPMV_THREADS / 32);
+    if (blockIdx.x == 0 && threadIdx.x == 0) counters[parity ^ 1] = 0ull;  // arm the next launch's counter
+    hb_spmv_rows<Epi, WANT_MAX, VT>(indptr, idx, val, n_rows, row0, u, counters + parity, epi, peer);
     if (peer.publish) {
+        // Release chain (PTX memory model, system scope): every lane that stored into a peer replica fences ITS OWN
+        // stores, the warp barrier orders those fences before lane 0's ticket, the ticket chain (gpu-scope atomics
+        // bracketed by fences) reaches the last warp's lane 0, whose fence + warp barrier precede the st.release.sys
+        // of every flag.  A consumer that ld.acquire.sys-es a flag therefore observes every row of this rank.
+        if (lane < peer.world) __threadfence_system();
+        __syncwarp();
         int last = 0;
         if (lane == 0) {
-            __threadfence_system();
+            __threadfence();
             last = (atomicAdd(peer.done, 1u) == (unsigned int)(nwarps - 1)) ? 1 : 0;
+            __threadfence_system();
         }
-        last = __shfl_sync(0xffffffffu, last, 0);
+        last = __shfl_sync(0xffffffffu, last, 0);   // also a warp barrier: lanes 1.. are ordered after lane 0's fence
         if (last) {
             if (lane == 0) *peer.done = 0u;
-            __threadfence_system();
+            __syncwarp();
             if (lane < peer.world) {
                 if (WANT_MAX) peer.out[lane][peer.n + peer.rank] = epi.local_max();
-                __threadfence_system();
-                hb_st_release_sys(peer.flag[lane] + peer.rank, peer.seq);
+                hb_st_release_sys(peer.flag[lane] + peer.rank, peer.seq);   // release = fence.sys + store
             }
         }
     }
+}
+
+// ---- persistent solver kernels (hb_ice_loop_kernel, hb_kr_solve_kernel): exchange state for a whole launch ----------
+struct HbLoopPeer {
+    double* buf[2][HB_MAX_PEERS];               // exchange buffer p of every rank's replica (own entry = local memory)
+    unsigned long long* flag[2][HB_MAX_PEERS];  // arrival flags p of every replica; slot [rank] is written by `rank`
+    unsigned long long seq0;                    // exchanges performed on this handle before this launch
+    int world, rank;
+};
+
+// Destination of a row inside a persistent kernel: the local vector (one GPU) or buffer pb of every rank's replica,
+// read straight from the kernel parameters (`peer` points into the __grid_constant__ argument block).
+struct HbLoopOut {
+    const HbLoopPeer* peer;
+    double* local;
+    int pb, world;
+    __device__ __forceinline__ void store(int64_t g, double v, int lane) const {
+        if (world == 1) {
+            if (lane == 0) local[g] = v;
+        } else if (lane < world) {
+            peer->buf[pb][lane][g] = v;
+        }
+    }
+};
+
+// every rank's arrival flag of exchange `seq` (one warp per CTA polls; ~4 s guard so a dead peer cannot hang the GPU)
+__device__ __forceinline__ void hb_loop_wait_flags(const unsigned long long* flags, unsigned long long seq, int world,
+                                                   double* err) {
+    if ((threadIdx.x >> 5) == 0) {
+        const int lane = threadIdx.x & 31;
+        if (lane < world) {
+            const long long t0 = clock64();
+            while (hb_ld_acquire_sys(flags + lane) < seq) {
+                if (clock64() - t0 > 8000000000LL) {
+                    *err = 1.0;
+                    break;
+                }
+                __nanosleep(100);
+            }
+        }
+    }
+    __syncthreads();
+}
+
+
+// Exchange `seq` of a persistent kernel, after its rows were stored and the grid has synchronised: block 0 releases
+// this rank's arrival flag in every replica (and ships `slot_value` into slot n + rank), then every CTA waits for all
+// ranks' flags in the local replica.  Each storing lane has fenced its own peer stores before the grid barrier.
+__device__ __forceinline__ void hb_loop_publish_and_wait(const HbLoopPeer& peer, int pb, unsigned long long seq,
+                                                         int64_t n_cols, double slot_value, double* err) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (blockIdx.x == 0 && warp == 0 && lane < peer.world) {
+        peer.buf[pb][lane][n_cols + peer.rank] = slot_value;
+        hb_st_release_sys(peer.flag[pb][lane] + peer.rank, seq);
+    }
+    hb_loop_wait_flags(peer.flag[pb][peer.rank], seq, peer.world, err);
+}
+
+// Fill the launch-constant exchange description of a handle in peer mode (world = 1 otherwise).
+static inline void hb_fill_loop_peer(const hb_csr* h, HbLoopPeer* lp) {
+    memset(lp, 0, sizeof(*lp));
+    lp->world = 1;
+    lp->rank = h->rank;
+    lp->seq0 = h->peer_seq;
+    if (!h->peer) return;
+    lp->world = h->world;
+    for (int p = 0; p < 2; ++p)
+        for (int q = 0; q < h->world; ++q) {
+            unsigned char* base = (unsigned char*)h->peer_base[q];
+            lp->buf[p][q] = (double*)(base + (size_t)p * h->sym_buf_bytes);
+            lp->flag[p][q] = (unsigned long long*)(base + h->sym_flag_off + (size_t)p * 512);
+        }
 }
 
 // Destination of the next SpMV on this handle: the local vector, or (peer mode) buffer seq&1 of every replica.
@@ -199,6 +305,7 @@ static inline HbPeerOut hb_next_out(hb_csr* h, double* local_out) {
         po.publish = 0;
         return po;
     }
+    hb_loop_settle(h);   // a persistent kernel still in flight owns part of the sequence: wait for its count
     const unsigned long long seq = ++h->peer_seq;
     const int p = (int)(seq & 1ull);
     po.world = h->world;
@@ -241,10 +348,11 @@ struct HbAffineEpi {
     const double* __restrict__ c;
     double eps;
     __device__ __forceinline__ bool active(int64_t) const { return true; }
-    __device__ __forceinline__ void row(int64_t g, double t, double, int lane, const HbPeerOut& peer) const {
-        double v = t + eps * u[g];
+    template <class Out>
+    __device__ __forceinline__ void row(int64_t g, double t, double, int lane, const Out& peer) const {
+        double v = fma(eps, u[g], t);
         if (a != nullptr) v *= a[g];
-        if (b != nullptr && c != nullptr) v += b[g] * c[g];
+        if (b != nullptr && c != nullptr) v = fma(b[g], c[g], v);
         peer.store(g, v, lane);
     }
     __device__ __forceinline__ void warp_done() const {}

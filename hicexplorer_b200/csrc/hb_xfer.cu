@@ -55,30 +55,43 @@ struct HbXferWorker {
 static std::mutex g_xfer_mutex;
 static HbXferWorker g_xfer_worker[64];
 
+static void hb_xfer_teardown(HbXferWorker& w) {
+    if (w.device >= 0) cudaSetDevice(w.device);
+    for (int b = 0; b < 2; ++b) {
+        if (w.done[b]) cudaEventDestroy(w.done[b]);
+        if (w.stage[b]) cudaFreeHost(w.stage[b]);
+        w.done[b] = nullptr;
+        w.stage[b] = nullptr;
+    }
+    if (w.st) cudaStreamDestroy(w.st);
+    w.st = nullptr;
+    w.device = -1;
+    w.chunk = 0;
+}
+
+// A worker is marked ready (device / chunk recorded) only after EVERY allocation succeeded; a partial failure
+// (e.g. a transient pinned-memory shortage) releases what was taken, so the next transfer rebuilds the worker
+// instead of copying into a null staging buffer.
 static cudaError_t hb_xfer_prepare(HbXferWorker& w, int device, size_t chunk) {
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return e;
     if (w.device == device && w.chunk == chunk && w.st != nullptr) return cudaSuccess;
-    if (w.st != nullptr) {  // another device or chunk size: rebuild
-        cudaSetDevice(w.device);
-        for (int b = 0; b < 2; ++b) {
-            if (w.done[b]) cudaEventDestroy(w.done[b]);
-            if (w.stage[b]) cudaFreeHost(w.stage[b]);
-            w.done[b] = nullptr;
-            w.stage[b] = nullptr;
-        }
-        cudaStreamDestroy(w.st);
-        w.st = nullptr;
-        e = cudaSetDevice(device);
-    }
+    hb_xfer_teardown(w);  // another device or chunk size (or a half-built worker): rebuild
+    e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w.st, cudaStreamNonBlocking);
     for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
         e = cudaHostAlloc((void**)&w.stage[b], chunk, cudaHostAllocDefault);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w.done[b], cudaEventDisableTiming);
     }
+    if (e != cudaSuccess) {
+        w.device = device;   // so that teardown selects the right device
+        hb_xfer_teardown(w);
+        cudaGetLastError();
+        return e;
+    }
     w.device = device;
     w.chunk = chunk;
-    return e;
+    return cudaSuccess;
 }
 
 // dir = 0: host -> device, 1: device -> host

@@ -123,3 +123,16 @@ def attach_peer(dev, rank, world, group=None):
         # leave peer mode everywhere so that all ranks take the same fallback
         return False
     return True
+
+
+def attach_peer_inprocess(devs):
+    """Peer-store exchange between row-block handles that live in ONE process (``devs`` in rank order; one host thread
+    per rank drives its handle afterwards): several GPUs with peer access, or several blocks on one GPU (tests)."""
+    L = _lib.lib()
+    world = len(devs)
+    scratch = (ctypes.c_ubyte * 64)()
+    for rank, dev in enumerate(devs):
+        _lib.check(L.hb_peer_export(dev.handle, rank, world, ctypes.cast(scratch, ctypes.c_void_p)))
+    table = (ctypes.c_void_p * world)(*[d.handle for d in devs])
+    for dev in devs:
+        _lib.check(L.hb_peer_attach_inprocess(dev.handle, ctypes.cast(table, ctypes.c_void_p)))

@@ -242,6 +242,20 @@ def _open_row_block(m, upper_input, drop_mask, rank, world, device):
     return DeviceCSR.from_scipy(m, device=device, row_range=(a, b)), (a, b), n
 
 
+def _attach_exchange(dev, rank, world):
+    """Register the host collective (row sums of the filter, symmetry digests, KR rescale sums) and, where the GPUs can
+    reach each other (one NVLink / P2P domain, <= 8 ranks), switch the per-iteration exchange of ICE / KR to peer stores
+    from the SpMV epilogue: the solvers then run as ONE persistent launch per rank with no host or NCCL call inside.
+    Same results bit for bit either way.  HB_EXCHANGE=nccl keeps the host collective for everything."""
+    import os
+
+    from .dist import attach_comm, attach_peer
+    keep = attach_comm(dev, rank, world)
+    if os.environ.get("HB_EXCHANGE", "peer") != "nccl" and world <= 8:
+        attach_peer(dev, rank, world)
+    return keep
+
+
 def ice_pipeline_sharded(matrix, filter_threshold, max_iter=500, tolerance=1e-5, chr_offsets=None, perchr=False,
                          skip_diagonal=False, want_matrix=True, file_layout=False, upper_input=False, drop_mask=None):
     """ice_pipeline on row blocks across the initialised torch.distributed group (NCCL).  The symmetry test is the
@@ -267,7 +281,7 @@ def ice_pipeline_sharded(matrix, filter_threshold, max_iter=500, tolerance=1e-5,
     upper_local = None
     dev, (a, b), n = _open_row_block(m, upper_input, drop_mask, rank, world, device)
     with dev:
-        keep_alive = attach_comm(dev, rank, world)
+        keep_alive = _attach_exchange(dev, rank, world)
         rs_local, _ = dev.row_stats()
         rs = torch.zeros(n, dtype=torch.float64, device="cuda")
         rs[a:b] = torch.from_numpy(rs_local).cuda()
@@ -335,7 +349,7 @@ def kr_pipeline_sharded(matrix, rescale=True, upper_input=False, drop_mask=None)
     m = canonical_csr(matrix, dtype=None)      # values keep the file type: widened to fp64 on the device
     dev, _block, _n = _open_row_block(m, upper_input, drop_mask, rank, world, device)
     with dev:
-        keep_alive = attach_comm(dev, rank, world)
+        keep_alive = _attach_exchange(dev, rank, world)
         dev.pack_values()
         x, outer, matvecs, residual = dev.kr()
         factor = 1.0

@@ -152,6 +152,10 @@ HB_API int hb_set_comm(hb_csr* h, int rank, int world, hb_allreduce_fn fn, void*
  * host must NOT all-reduce.  hb_peer_active() tells which mode a handle is in. */
 HB_API int hb_peer_export(hb_csr* h, int rank, int world, void* ipc_handle_out);
 HB_API int hb_peer_attach(hb_csr* h, const void* all_handles);
+/* Same exchange when all ranks live in ONE process (one host thread + handle per rank; several GPUs with peer access,
+ * or several row blocks on one GPU): ranks[world] = every rank's handle after its hb_peer_export, in rank order.
+ * Ranks that share a GPU must fit on it together: their persistent kernels wait for each other. */
+HB_API int hb_peer_attach_inprocess(hb_csr* h, hb_csr* const* ranks);
 HB_API int hb_peer_active(const hb_csr* h);
 
 /* ---- pre-filter (device) ---------------------------------------------------
@@ -290,6 +294,14 @@ HB_API int hb_ice_scaled_row_sums(hb_csr* h, double* out);
  *   hb_dev_ice_finish: bias normalisation (lines 77-78); r is rescaled so that
  *                      A_ij r_i r_j is the final corrected value.
  *   hb_dev_ice_emit  : d_out[k] = A_k r_i r_j for the block (+ max into d_max[0], may be NULL). */
+/*   hb_dev_ice_loop  : ONE cooperative launch that runs up to `iters` whole iterations (SpMV + update) back to back
+ *                      on the device -- three grid barriers per iteration instead of kernel launches, no host in the
+ *                      loop; stops early once every segment has converged, a value exceeds 1e100 or a peer times out.
+ *                      Continues from the state hb_dev_ice_begin / earlier calls left; asynchronous.  Needs the
+ *                      exchange on the device: a full matrix on one GPU, or row blocks in peer mode (hb_peer_attach).
+ *                      Results are bit-identical to `iters` x (hb_dev_ice_spmv, hb_dev_ice_update).  hb_ice_run uses it
+ *                      whenever it can (set HB_NO_PERSISTENT=1 in the environment to force the step-level path). */
+HB_API int hb_dev_ice_loop(hb_csr* h, int iters, double tol, void* stream);
 HB_API int hb_dev_ice_begin(hb_csr* h, void* stream);
 HB_API int hb_dev_ice_spmv(hb_csr* h, double* d_exch, int rank, int world, void* stream);
 HB_API int hb_dev_ice_update(hb_csr* h, const double* d_exch, int world, double tol, void* stream);

@@ -56,6 +56,7 @@ def kr_balance(csr, tol=TOL, max_outer=100000):
     rt = tol * tol
     outer = 0
     matvecs = 0
+    boundary_steps = 0
     z = p = None
     while rout > rt and outer < max_outer:
         outer += 1
@@ -81,11 +82,13 @@ def kr_balance(csr, tol=TOL, max_outer=100000):
                 sel = ap < 0
                 gamma = np.min((DELTA_LO - y[sel]) / ap[sel])
                 y = y + gamma * ap
+                boundary_steps += 1
                 break
             if ynew.max() >= DELTA_HI:
                 sel = ynew > DELTA_HI
                 gamma = np.min((DELTA_HI - y[sel]) / ap[sel])
                 y = y + gamma * ap
+                boundary_steps += 1
                 break
             y = ynew
             rk = rk - alpha * w
@@ -106,7 +109,7 @@ def kr_balance(csr, tol=TOL, max_outer=100000):
         if G * eta_o * eta_o > 0.1:
             eta = max(eta, G * eta_o * eta_o)
         eta = max(min(eta, ETA_MAX), stop_tol / res_norm)
-    return dict(x=x, outer=outer, matvecs=matvecs, residual=float(np.sqrt(rout)), A=a)
+    return dict(x=x, outer=outer, matvecs=matvecs, residual=float(np.sqrt(rout)), A=a, boundary_steps=boundary_steps)
 
 
 def rescale_factor(a, x):

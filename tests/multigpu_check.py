@@ -36,9 +36,17 @@ def main():
             print(("PASS " if cond else "FAIL ") + name, flush=True)
         ok = ok and bool(cond)
 
+    # the host-collective exchange first (one NCCL allreduce per SpMV, step-level kernels) ...
+    os.environ["HB_EXCHANGE"] = "nccl"
+    got_n = ice_pipeline_sharded(full, (-1.5, 5.0), max_iter=500)
+    kr_n = kr_pipeline_sharded(full, rescale=True)
+    # ... then the default: peer stores from the SpMV epilogue inside ONE persistent launch per rank
+    os.environ["HB_EXCHANGE"] = "peer"
     got = ice_pipeline_sharded(full, (-1.5, 5.0), max_iter=500)
     if rank == 0:
         ref = ice_pipeline(full, (-1.5, 5.0), max_iter=500, device=local)
+        check("ICE sharded, NCCL exchange: bias bit-identical to 1 GPU", np.array_equal(got_n["bias"], ref["bias"]) and
+              int(got_n["iterations"][0]) == int(ref["iterations"][0]))
         check("ICE sharded: masks bit-exact", np.array_equal(got["zero_bins"], ref["zero_bins"]) and
               np.array_equal(got["outliers_rel"], ref["outliers_rel"]))
         check("ICE sharded: bias bit-identical to 1 GPU", np.array_equal(got["bias"], ref["bias"]))
@@ -80,6 +88,8 @@ def main():
     kr = kr_pipeline_sharded(full, rescale=True)
     if rank == 0:
         kref = kr_pipeline(full, rescale=True, want_matrix=False, device=local)
+        check("KR sharded, NCCL exchange: x bit-identical, same mat-vec count", np.array_equal(kr_n["x"], kref["x"]) and
+              kr_n["matvecs"] == kref["matvecs"])
         check("KR sharded: x bit-identical, same mat-vec count", np.array_equal(kr["x"], kref["x"]) and kr["matvecs"] == kref["matvecs"])
         check("KR sharded: rescale factor identical", kr["factor"] == kref["factor"])
     # the CLI under torchrun
