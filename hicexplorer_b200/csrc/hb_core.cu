@@ -429,6 +429,11 @@ int hb_peer_attach_inprocess(hb_csr* h, hb_csr* const* ranks) {
     HB_REQUIRE(h != nullptr && ranks != nullptr && h->d_sym != nullptr, "call hb_peer_export first");
     int rc = hb_use_device(h);
     if (rc) return rc;
+    // Ranks of one process may share a GPU, where an allocation made by one rank (cudaMalloc synchronises the device)
+    // would wait for another rank's persistent kernel -- which in turn waits for this rank's flags.  Everything the
+    // solvers need is therefore reserved now, before any of them runs.
+    rc = hb_kr_reserve(h);
+    if (rc) return rc;
     for (int q = 0; q < h->world; ++q) {
         hb_csr* o = ranks[q];
         HB_REQUIRE(o != nullptr && o->d_sym != nullptr && o->world == h->world && o->rank == q &&

@@ -158,6 +158,7 @@ void hb_free_state(hb_csr* h);
 int hb_use_device(const hb_csr* h);
 int hb_spmv_grid(int64_t n_rows);
 void hb_peer_release(hb_csr* h);
+int hb_kr_reserve(hb_csr* h);                        // allocate the Knight-Ruiz workspace of the handle (idempotent)
 int hb_loop_settle(hb_csr* h);                       // fold a finished loop kernel's exchange count into peer_seq
 int hb_coop_grid(const void* kernel, int64_t n_rows, int device);   // co-resident persistent grid for a cooperative launch
 void hb_drop_pack(hb_csr* h);

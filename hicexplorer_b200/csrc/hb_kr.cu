@@ -727,6 +727,23 @@ int kr_read_scalars(KrCtx& c) {
 
 }  // namespace
 
+// Knight-Ruiz workspace of a handle: 8 n-vectors, the per-tile partials of every reduction, the scalars.
+int hb_kr_reserve(hb_csr* h) {
+    int rc = hb_ensure_state(h);
+    if (rc) return rc;
+    const size_t n = (size_t)(h->n_cols > 0 ? h->n_cols : 1);
+    const size_t words = 8 * n + 3 * KP_ARRAYS * (size_t)(h->n_tiles > 0 ? h->n_tiles : 1) + SC_WORDS;
+    if (h->kr_buf_words < words) {
+        cudaFree(h->d_kr_buf);
+        h->d_kr_buf = nullptr;
+        h->kr_buf_words = 0;
+        cudaError_t e = cudaMalloc(&h->d_kr_buf, sizeof(double) * words);
+        if (e != cudaSuccess) return hb_cuda_fail(e, "cudaMalloc KR vectors", __FILE__, __LINE__);
+        h->kr_buf_words = words;
+    }
+    return HB_OK;
+}
+
 #define KR_TRY(expr)            \
     do {                        \
         rc = (expr);            \
@@ -792,20 +809,10 @@ int hb_kr_run(hb_csr* h, double tol, double delta, double Delta, double diag_eps
     double rho_km1 = 0.0, rout = 0.0, rold = 0.0;
     int outer = 0, mvp = 0;
     bool breakdown = false;
-    {
-        // the workspace lives in the handle: repeated calls (and --perchr loops) pay no allocation
-        const size_t words = (size_t)(8 * n + 3 * KP_ARRAYS * h->n_tiles + SC_WORDS);
-        if (h->kr_buf_words < words) {
-            cudaFree(h->d_kr_buf);
-            h->d_kr_buf = nullptr;
-            h->kr_buf_words = 0;
-            cudaError_t e = cudaMalloc(&h->d_kr_buf, sizeof(double) * words);
-            if (e != cudaSuccess) return hb_cuda_fail(e, "cudaMalloc KR vectors", __FILE__, __LINE__);
-            h->kr_buf_words = words;
-        }
-        c.buf = h->d_kr_buf;
-        c.h_sc = h->h_kr_sc;
-    }
+    rc = hb_kr_reserve(h);   // the workspace lives in the handle: repeated calls (and --perchr loops) pay no allocation
+    if (rc) return rc;
+    c.buf = h->d_kr_buf;
+    c.h_sc = h->h_kr_sc;
     {
         double* b = c.buf;
         c.q.x = b; b += n;

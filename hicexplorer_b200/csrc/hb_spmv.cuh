@@ -32,7 +32,7 @@ template <bool COHERENT>
 __device__ __forceinline__ double hb_ld_gather(const double* p) {
     if (COHERENT) {
         double r;
-        asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(r) : "l"(p));
+        asm volatile("ld.global.f64 %0, [%1];" : "=d"(r) : "l"(p));   // weak, default caching: LDG.E.64
         return r;
     }
     return __ldg(p);

@@ -28,6 +28,40 @@
  * so the row sums need no atomics and come out in the same order as the serial loop. */
 #include <pthread.h>
 
+/* numpy's float64 add.reduce over a contiguous array (np.sum / np.mean): pairwise summation with an 8-way unrolled
+ * base case of at most 128 elements (numpy/_core/src/umath/loops_utils.h.src, @TYPE@_pairwise_sum).  The reference
+ * takes np.mean(s[s != 0]) (iterativeCorrection.py:44), so the restatement sums in the same order. */
+static double np_pairwise_sum(const double* a, int64_t n) {
+    if (n < 8) {
+        double res = 0.;
+        for (int64_t i = 0; i < n; ++i) res += a[i];
+        return res;
+    } else if (n <= 128) {
+        double r[8];
+        int64_t i;
+        for (int j = 0; j < 8; ++j) r[j] = a[j];
+        for (i = 8; i < n - (n % 8); i += 8)
+            for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; ++i) res += a[i];
+        return res;
+    } else {
+        int64_t n2 = n / 2;
+        n2 -= n2 % 8;
+        return np_pairwise_sum(a, n2) + np_pairwise_sum(a + n2, n - n2);
+    }
+}
+
+/* np.mean(s[keep & (s != 0)]) ; tmp has room for n doubles */
+static double mean_nonzero(const double* s, const uint8_t* keep, int64_t n, double* tmp) {
+    int64_t cnt = 0;
+    for (int64_t i = 0; i < n; ++i)
+        if ((keep == NULL || keep[i]) && s[i] != 0.0) tmp[cnt++] = s[i];
+    return np_pairwise_sum(tmp, cnt) / (double)cnt;
+}
+
+double np_sum_f64(const double* a, int64_t n) { return np_pairwise_sum(a, n); }
+
 typedef struct {
     int64_t k0, k1;
     const int32_t* row;
@@ -61,6 +95,7 @@ int ice_loop_coo_mt(int64_t n, int64_t nnz, const int32_t* row, const int32_t* c
     if (threads < 1) threads = 1;
     if (threads > 256) threads = 256;
     double* s = (double*)malloc(sizeof(double) * (size_t)n);
+    double* tmp = (double*)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
     ice_mt_job* jobs = (ice_mt_job*)calloc((size_t)threads, sizeof(ice_mt_job));
     pthread_t* th = (pthread_t*)calloc((size_t)threads, sizeof(pthread_t));
     /* entry ranges cut at row boundaries */
@@ -81,14 +116,7 @@ int ice_loop_coo_mt(int64_t n, int64_t nnz, const int32_t* row, const int32_t* c
         memset(s, 0, sizeof(double) * (size_t)n);
         for (int phase = 0; phase < 2; ++phase) {
             if (phase == 1) {
-                double tot = 0.0;
-                int64_t cnt = 0;
-                for (int64_t i = 0; i < n; ++i)
-                    if (s[i] != 0.0) {
-                        tot += s[i];
-                        cnt++;
-                    }
-                const double mean = tot / (double)cnt;
+                const double mean = mean_nonzero(s, NULL, n, tmp);
                 dev = 0.0;
                 for (int64_t i = 0; i < n; ++i) {
                     s[i] = s[i] / mean;
@@ -111,16 +139,235 @@ int ice_loop_coo_mt(int64_t n, int64_t nnz, const int32_t* row, const int32_t* c
         if (dev < tol) break;
     }
     free(s);
+    free(tmp);
     free(jobs);
     free(th);
     if (deviation_out) *deviation_out = dev;
     return overflow ? -1 : done;
 }
 
+/* ---- the reference's loop on a CSR store with a bin mask, all host cores ------------------------------------------------
+ * What iterativeCorrection() computes on matrix[keep][:, keep] (the matrix hicCorrectMatrix hands it after maskBins),
+ * without building that sub-matrix: entries whose row or column is masked are skipped.  Arithmetic and order are the
+ * reference's: row sums accumulate sequentially in stored order (scipy's coo_matvec over row-major triplets,
+ * iterativeCorrection.py:42), every kept entry is rescaled in place by s[row] then s[col] (:56-57), the 1e100 scan (:58),
+ * the strict '<' test after the rescale (:72).  The O(n) part runs over the kept bins in order, like numpy on the
+ * compacted vectors.  Threads own contiguous row ranges (balanced by entries), so nothing depends on the thread count.
+ * data[] is overwritten with the scaled values of the last iteration (masked entries untouched).
+ * bias[] is indexed by ORIGINAL bin (masked bins keep 1).  Returns iterations done, -1 on overflow. */
+typedef struct {
+    int64_t r0, r1;
+    const int64_t* indptr;
+    const int32_t* idx;
+    double* data;
+    const uint8_t* keep;
+    double* s;
+    int phase;
+    int overflow;
+} ice_csr_job;
+
+static void* ice_csr_worker(void* arg) {
+    ice_csr_job* j = (ice_csr_job*)arg;
+    if (j->phase == 0) {
+        for (int64_t i = j->r0; i < j->r1; ++i) {
+            if (!j->keep[i]) continue;
+            double acc = 0.0;
+            for (int64_t k = j->indptr[i]; k < j->indptr[i + 1]; ++k)
+                if (j->keep[j->idx[k]]) acc += j->data[k];
+            j->s[i] = acc;
+        }
+    } else {
+        int of = 0;
+        for (int64_t i = j->r0; i < j->r1; ++i) {
+            if (!j->keep[i]) continue;
+            const double si = j->s[i];
+            for (int64_t k = j->indptr[i]; k < j->indptr[i + 1]; ++k) {
+                const int32_t c = j->idx[k];
+                if (!j->keep[c]) continue;
+                double v = j->data[k];
+                v *= si;
+                v *= j->s[c];
+                j->data[k] = v;
+                if (v > 1e100) of = 1;
+            }
+        }
+        j->overflow = of;
+    }
+    return NULL;
+}
+
+int ice_loop_csr_masked_mt(int64_t n, const int64_t* indptr, const int32_t* idx, double* data, const uint8_t* keep,
+                           double* bias, int max_iter, double tol, int threads, double* deviation_out) {
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    double* s = (double*)calloc((size_t)(n > 0 ? n : 1), sizeof(double));
+    double* tmp = (double*)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    ice_csr_job* jobs = (ice_csr_job*)calloc((size_t)threads, sizeof(ice_csr_job));
+    pthread_t* th = (pthread_t*)calloc((size_t)threads, sizeof(pthread_t));
+    const int64_t nnz = indptr[n] - indptr[0];
+    {
+        int64_t r = 0;
+        for (int t = 0; t < threads; ++t) {
+            jobs[t].r0 = r;
+            const int64_t target = indptr[0] + nnz * (t + 1) / threads;
+            while (r < n && indptr[r] < target) ++r;
+            if (t == threads - 1) r = n;
+            jobs[t].r1 = r;
+            jobs[t].indptr = indptr;
+            jobs[t].idx = idx;
+            jobs[t].data = data;
+            jobs[t].keep = keep;
+            jobs[t].s = s;
+        }
+    }
+    int done = 0, overflow = 0;
+    double dev = NAN;
+    for (int it = 0; it < max_iter && !overflow; ++it) {
+        done++;
+        for (int phase = 0; phase < 2; ++phase) {
+            if (phase == 1) {
+                const double mean = mean_nonzero(s, keep, n, tmp);
+                dev = 0.0;
+                for (int64_t i = 0; i < n; ++i) {
+                    if (!keep[i]) continue;
+                    s[i] = s[i] / mean;
+                    bias[i] *= s[i];
+                    const double d = fabs(s[i] - 1.0);
+                    if (d > dev || d != d) dev = d;
+                    s[i] = 1.0 / s[i];
+                }
+            }
+            for (int t = 0; t < threads; ++t) {
+                jobs[t].phase = phase;
+                jobs[t].overflow = 0;
+                if (t > 0) pthread_create(&th[t], NULL, ice_csr_worker, &jobs[t]);
+            }
+            ice_csr_worker(&jobs[0]);
+            for (int t = 1; t < threads; ++t) pthread_join(th[t], NULL);
+            if (phase == 1)
+                for (int t = 0; t < threads; ++t) overflow |= jobs[t].overflow;
+        }
+        if (dev < tol) break;
+    }
+    free(s);
+    free(tmp);
+    free(jobs);
+    free(th);
+    if (deviation_out) *deviation_out = dev;
+    return overflow ? -1 : done;
+}
+
+/* row sums and diagonal over the kept bins (hicCorrectMatrix.py:588, 614): sequential per row, threads over rows */
+typedef struct {
+    int64_t r0, r1;
+    const int64_t* indptr;
+    const int32_t* idx;
+    const double* data;
+    const uint8_t* keep;
+    double* rs;
+    double* dg;
+} rowstat_job;
+
+static void* rowstat_worker(void* arg) {
+    rowstat_job* j = (rowstat_job*)arg;
+    for (int64_t i = j->r0; i < j->r1; ++i) {
+        double acc = 0.0, d = 0.0;
+        if (j->keep == NULL || j->keep[i]) {
+            for (int64_t k = j->indptr[i]; k < j->indptr[i + 1]; ++k) {
+                const int32_t c = j->idx[k];
+                if (j->keep != NULL && !j->keep[c]) continue;
+                acc += j->data[k];
+                if (c == i) d += j->data[k];
+            }
+        }
+        j->rs[i] = acc;
+        j->dg[i] = d;
+    }
+    return NULL;
+}
+
+void row_stats_csr_mt(int64_t n, const int64_t* indptr, const int32_t* idx, const double* data, const uint8_t* keep,
+                      double* rs, double* dg, int threads) {
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    rowstat_job* jobs = (rowstat_job*)calloc((size_t)threads, sizeof(rowstat_job));
+    pthread_t* th = (pthread_t*)calloc((size_t)threads, sizeof(pthread_t));
+    for (int t = 0; t < threads; ++t) {
+        jobs[t].r0 = n * t / threads;
+        jobs[t].r1 = n * (t + 1) / threads;
+        jobs[t].indptr = indptr;
+        jobs[t].idx = idx;
+        jobs[t].data = data;
+        jobs[t].keep = keep;
+        jobs[t].rs = rs;
+        jobs[t].dg = dg;
+        if (t > 0) pthread_create(&th[t], NULL, rowstat_worker, &jobs[t]);
+    }
+    rowstat_worker(&jobs[0]);
+    for (int t = 1; t < threads; ++t) pthread_join(th[t], NULL);
+    free(jobs);
+    free(th);
+}
+
+/* y = x o ((A + eps I) u) [+ v o p] with threads over rows (same per-row arithmetic as kr_matvec) */
+typedef struct {
+    int64_t r0, r1;
+    const int64_t* indptr;
+    const int32_t* idx;
+    const double* val;
+    const double *u, *x, *v, *p;
+    double eps;
+    double* out;
+} krmv_job;
+
+static void* krmv_worker(void* arg) {
+    krmv_job* j = (krmv_job*)arg;
+    for (int64_t i = j->r0; i < j->r1; ++i) {
+        double acc = 0.0;
+        for (int64_t k = j->indptr[i]; k < j->indptr[i + 1]; ++k) acc += j->val[k] * j->u[j->idx[k]];
+        double r = j->x[i] * (acc + j->eps * j->u[i]);
+        if (j->v && j->p) r += j->v[i] * j->p[i];
+        j->out[i] = r;
+    }
+    return NULL;
+}
+
+void kr_matvec_mt(int64_t n, const int64_t* indptr, const int32_t* idx, const double* val, const double* u, const double* x,
+                  const double* v, const double* p, double eps, double* out, int threads) {
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    krmv_job* jobs = (krmv_job*)calloc((size_t)threads, sizeof(krmv_job));
+    pthread_t* th = (pthread_t*)calloc((size_t)threads, sizeof(pthread_t));
+    const int64_t nnz = indptr[n] - indptr[0];
+    int64_t r = 0;
+    for (int t = 0; t < threads; ++t) {
+        jobs[t].r0 = r;
+        const int64_t target = indptr[0] + nnz * (t + 1) / threads;
+        while (r < n && indptr[r] < target) ++r;
+        if (t == threads - 1) r = n;
+        jobs[t].r1 = r;
+        jobs[t].indptr = indptr;
+        jobs[t].idx = idx;
+        jobs[t].val = val;
+        jobs[t].u = u;
+        jobs[t].x = x;
+        jobs[t].v = v;
+        jobs[t].p = p;
+        jobs[t].eps = eps;
+        jobs[t].out = out;
+        if (t > 0) pthread_create(&th[t], NULL, krmv_worker, &jobs[t]);
+    }
+    krmv_worker(&jobs[0]);
+    for (int t = 1; t < threads; ++t) pthread_join(th[t], NULL);
+    free(jobs);
+    free(th);
+}
+
 /* returns iterations done; *deviation_out = last max|s-1|; -1 on overflow (> 1e100) */
 int ice_loop_coo(int64_t n, int64_t nnz, const int32_t* row, const int32_t* col, double* data, double* bias,
                  int max_iter, double tol, int threads, double* deviation_out) {
     double* s = (double*)malloc(sizeof(double) * (size_t)n);
+    double* tmp = (double*)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
     int done = 0;
     double dev = NAN;
 #ifdef _OPENMP
@@ -138,14 +385,7 @@ int ice_loop_coo(int64_t n, int64_t nnz, const int32_t* row, const int32_t* col,
                 s[row[k]] += data[k];
             }
         }
-        double tot = 0.0;
-        int64_t cnt = 0;
-        for (int64_t i = 0; i < n; ++i)
-            if (s[i] != 0.0) {
-                tot += s[i];
-                cnt++;
-            }
-        const double mean = tot / (double)cnt; /* line 44 */
+        const double mean = mean_nonzero(s, NULL, n, tmp); /* line 44 */
         dev = 0.0;
         for (int64_t i = 0; i < n; ++i) {
             s[i] = s[i] / mean;
@@ -165,11 +405,13 @@ int ice_loop_coo(int64_t n, int64_t nnz, const int32_t* row, const int32_t* col,
         }
         if (overflow) {
             free(s);
+            free(tmp);
             return -1;
         }
         if (dev < tol) break; /* line 72 */
     }
     free(s);
+    free(tmp);
     if (deviation_out) *deviation_out = dev;
     return done;
 }

@@ -34,6 +34,15 @@ def lib():
         L.ice_loop_coo_mt.argtypes = L.ice_loop_coo.argtypes
         L.kr_matvec.restype = None
         L.kr_matvec.argtypes = [ctypes.c_int64, vp, vp, vp, vp, vp, vp, vp, ctypes.c_double, vp, ctypes.c_int]
+        L.ice_loop_csr_masked_mt.restype = ctypes.c_int
+        L.ice_loop_csr_masked_mt.argtypes = [ctypes.c_int64, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_double, ctypes.c_int,
+                                             ctypes.POINTER(ctypes.c_double)]
+        L.row_stats_csr_mt.restype = None
+        L.row_stats_csr_mt.argtypes = [ctypes.c_int64, vp, vp, vp, vp, vp, vp, ctypes.c_int]
+        L.kr_matvec_mt.restype = None
+        L.kr_matvec_mt.argtypes = [ctypes.c_int64, vp, vp, vp, vp, vp, vp, vp, ctypes.c_double, vp, ctypes.c_int]
+        L.np_sum_f64.restype = ctypes.c_double
+        L.np_sum_f64.argtypes = [vp, ctypes.c_int64]
         L.synth_generate.restype = ctypes.c_int64
         L.synth_generate.argtypes = [ctypes.POINTER(SynthParams), vp, vp, vp, vp]
         _lib = L
@@ -97,4 +106,49 @@ def kr_matvec(csr, u, x, v=None, p=None, eps=1e-5, threads=0):
     ix = np.ascontiguousarray(csr.indices, dtype=np.int32)
     lib().kr_matvec(n, _p(ip), _p(ix), _p(np.ascontiguousarray(csr.data, dtype=np.float64)), _p(u), _p(x), _p(v),
                     _p(p), float(eps), _p(out), int(threads))
+    return out
+
+
+def _csr_arrays(csr):
+    """(indptr int64, indices int32, data float64) views of a canonical scipy CSR (copies only where the dtype differs)"""
+    return (np.ascontiguousarray(csr.indptr, dtype=np.int64), np.ascontiguousarray(csr.indices, dtype=np.int32),
+            np.ascontiguousarray(csr.data, dtype=np.float64))
+
+
+def row_stats_masked(csr, keep=None, threads=0):
+    """(row sums, diagonal) of csr[keep][:, keep] in the ORIGINAL frame (masked bins -> 0), all host cores."""
+    import os
+    ip, ix, da = _csr_arrays(csr)
+    n = csr.shape[0]
+    rs = np.zeros(n)
+    dg = np.zeros(n)
+    k = None if keep is None else np.ascontiguousarray(keep, dtype=np.uint8)
+    lib().row_stats_csr_mt(n, _p(ip), _p(ix), _p(da), _p(k), _p(rs), _p(dg), int(threads) or (os.cpu_count() or 1))
+    return rs, dg
+
+
+def ice_loop_masked(csr, keep, max_iter, tol=1e-5, threads=0, inplace=False):
+    """iterativeCorrection.py:40-74 on csr[keep][:, keep] without building the sub-matrix (see ice_loop_csr_masked_mt).
+    Returns (bias of the kept bins, iterations, deviation, scaled data array in the ORIGINAL pattern, seconds)."""
+    import os
+    import time
+    ip, ix, da = _csr_arrays(csr)
+    if not inplace and da is csr.data:
+        da = da.copy()
+    keep = np.ascontiguousarray(keep, dtype=np.uint8)
+    n = csr.shape[0]
+    bias = np.ones(n)
+    dev = ctypes.c_double()
+    t0 = time.time()
+    it = lib().ice_loop_csr_masked_mt(n, _p(ip), _p(ix), _p(da), _p(keep), _p(bias), int(max_iter), float(tol),
+                                      int(threads) or (os.cpu_count() or 1), ctypes.byref(dev))
+    return bias[keep.astype(bool)], it, dev.value, da, time.time() - t0
+
+
+def kr_matvec_mt(csr_arrays, n, u, x, v=None, p=None, eps=1e-5, threads=0):
+    import os
+    ip, ix, da = csr_arrays
+    out = np.empty(n, dtype=np.float64)
+    lib().kr_matvec_mt(n, _p(ip), _p(ix), _p(da), _p(u), _p(x), _p(v), _p(p), float(eps), _p(out),
+                       int(threads) or (os.cpu_count() or 1))
     return out

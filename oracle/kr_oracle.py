@@ -41,9 +41,26 @@ def _augment(csr):
     return sparse.csr_matrix(a + DIAG_EPS * sparse.identity(n, dtype=np.float64, format="csr"))
 
 
-def kr_balance(csr, tol=TOL, max_outer=100000):
+class _ThreadedOperator(object):
+    """(A + 1e-5 I) @ u through oracle/hic_cpu.c's row-parallel mat-vec (all host cores) -- for inputs of 1e8+ entries,
+    where scipy's single-threaded product and the augmented copy of the matrix cost minutes and gigabytes.  The diagonal
+    term is added per row (acc + eps * u_i) instead of being stored, a difference of one rounding per row."""
+
+    def __init__(self, csr):
+        from . import hic_cpu
+        self._hc = hic_cpu
+        self._arrays = hic_cpu._csr_arrays(csr)
+        self.shape = csr.shape
+        self._ones = np.ones(csr.shape[0])
+
+    def __matmul__(self, u):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        return self._hc.kr_matvec_mt(self._arrays, self.shape[0], u, self._ones, eps=DIAG_EPS)
+
+
+def kr_balance(csr, tol=TOL, max_outer=100000, threaded=False):
     """Returns dict(x, outer, matvecs, residual, A) for A = csr + 1e-5*I."""
-    a = _augment(csr)
+    a = _ThreadedOperator(csr) if threaded else _augment(csr)
     n = a.shape[0]
     x = np.ones(n)
     v = x * (a @ x)

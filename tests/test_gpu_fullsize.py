@@ -133,3 +133,75 @@ def test_genome_wide_100kb_pipeline_matches_the_reference_run():
     np.testing.assert_allclose(w.data[z["sample_idx"]], z["sample_val"], rtol=1e-8)
     np.testing.assert_allclose(np.asarray(w.sum(axis=1)).ravel(), z["row_sums"], rtol=1e-8)
     np.testing.assert_allclose(w.data.sum(), float(z["data_sum"]), rtol=1e-9)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Oracle parity AT BASELINE.json's sizes.  The checker is oracle/hic_cpu.c on every host core: the reference's loop
+# (row sums, mean over non-empty rows with numpy's pairwise summation, two in-place rescaling passes, 1e100 scan,
+# strict '<' test) on matrix[keep][:, keep] without building the sub-matrix -- pinned bit for bit to
+# oracle/ice_oracle.ice, itself pinned to the reference (tests/test_oracle.py).  Input: the synthetic matrix WITH the
+# planted empty and low-coverage bins, generated on the device and downloaded, so that both masks do real work.
+def _host_memory_ok(nnz):
+    try:
+        import psutil
+        return psutil.virtual_memory().available > 2.2 * 12.0 * nnz + 8e9
+    except Exception:
+        return True
+
+
+def _oracle_ice_pipeline_fullsize(m, lo, hi, max_iter=500, tol=1e-5):
+    from oracle import hic_cpu, ice_oracle
+    n = m.shape[0]
+    rs, _dg = hic_cpu.row_stats_masked(m)                       # hicCorrectMatrix.py:612-617 (diagonal included)
+    zero = rs == 0
+    keep1 = ~zero
+    rs1, dg1 = hic_cpu.row_stats_masked(m, keep1.astype(np.uint8))
+    pts = (rs1 - dg1)[keep1]                                    # :584-588
+    out = ice_oracle.MadScores(pts).outliers(lo, hi)            # :349-391
+    keep2 = keep1.copy()
+    keep2[np.flatnonzero(keep1)[out]] = False
+    bias, iters, dev, _data, secs = hic_cpu.ice_loop_masked(m, keep2.astype(np.uint8), max_iter, tol, inplace=True)
+    bias = bias / bias[bias != 0].mean()                        # iterativeCorrection.py:77-78
+    return dict(zero_bins=np.flatnonzero(zero), outliers_rel=np.flatnonzero(out), kept=np.flatnonzero(keep2), bias=bias,
+                iterations=iters, deviation=dev, seconds=secs, n=n)
+
+
+@pytest.mark.parametrize("workload", ["ice25k", "ice10k"])
+@pytest.mark.timeout(1500)
+def test_ice_pipeline_equals_the_oracle_at_full_size(workload):
+    """configs[1]'s matrix (3.0e8 entries) and configs[2]'s (1.5e9): both masks exactly, iterations +-1, bias 1e-9"""
+    from hicexplorer_b200.pipeline import ice_pipeline
+    method, bins, kw = bench.synth_kwargs(workload, clean=False)
+    if not _host_memory_ok(bench.WORKLOADS[workload][2]):
+        pytest.skip("not enough host memory for the CPU oracle at this size")
+    with DeviceCSR.synthetic(bins, **kw) as dev:
+        m = dev.download()
+    got = ice_pipeline(m, (-0.85, 50.0), max_iter=500, want_matrix=False)
+    ref = _oracle_ice_pipeline_fullsize(m, -0.85, 50.0)          # overwrites m.data with the oracle's scaled values
+    assert len(ref["zero_bins"]) > 0 and len(ref["outliers_rel"]) > 0
+    np.testing.assert_array_equal(got["zero_bins"], ref["zero_bins"])         # bit-exact masks
+    np.testing.assert_array_equal(got["outliers_rel"], ref["outliers_rel"])
+    np.testing.assert_array_equal(got["kept"], ref["kept"])
+    assert ref["deviation"] < 1e-5
+    assert abs(int(got["iterations"][0]) - ref["iterations"]) <= 1
+    np.testing.assert_allclose(got["bias"], ref["bias"], rtol=1e-9)
+    print("%s: %d bins, %d entries, %d / %d iterations (GPU / oracle), oracle loop %.1f s, max rel bias error %.2e"
+          % (workload, m.shape[0], m.nnz, int(got["iterations"][0]), ref["iterations"], ref["seconds"],
+             float(np.max(np.abs(got["bias"] / ref["bias"] - 1.0)))))
+
+
+@pytest.mark.timeout(900)
+def test_kr_equals_the_oracle_at_full_size():
+    """configs[1]: KR on the 25 kb matrix (3.0e8 entries, planted empty / low-coverage bins) against the restated bnewt
+    driven by the row-parallel C mat-vec: same outer / mat-vec counts, x within 1e-9"""
+    from hicexplorer_b200.pipeline import kr_pipeline
+    from oracle import kr_oracle
+    method, bins, kw = bench.synth_kwargs("kr25k", clean=False)
+    with DeviceCSR.synthetic(bins, **kw) as dev:
+        m = dev.download()
+    got = kr_pipeline(m, rescale=False, want_matrix=False)
+    ref = kr_oracle.kr_balance(m, threaded=True)
+    assert (got["outer"], got["matvecs"]) == (ref["outer"], ref["matvecs"])
+    np.testing.assert_allclose(got["x"], ref["x"], rtol=1e-9)
+    print("kr25k: %d bins, %d entries, %d outer / %d mat-vecs, max rel x error %.2e"
+          % (m.shape[0], m.nnz, got["outer"], got["matvecs"], float(np.max(np.abs(got["x"] / ref["x"] - 1.0)))))

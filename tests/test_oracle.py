@@ -295,3 +295,49 @@ def test_c_port_on_all_cores_equals_the_serial_c_loop():
         assert it == it1 and d == d1
         np.testing.assert_array_equal(b, b1)
         np.testing.assert_array_equal(data, data1)
+
+
+def test_c_loop_equals_the_numpy_restatement_bit_for_bit():
+    """oracle/hic_cpu.c (what the full-size GPU tests and bench.py's CPU legs run) against oracle/ice_oracle.ice, itself
+    pinned to the reference: same iteration count, same deviation, same bias to the last bit -- including the mean, which
+    numpy forms by pairwise summation (np_pairwise_sum in C restates numpy's @TYPE@_pairwise_sum)."""
+    from oracle import hic_cpu
+    from tests.helpers import random_hic
+    rng = np.random.default_rng(0)
+    L = hic_cpu.lib()
+    for n in list(range(0, 300)) + [1000, 1023, 1024, 1025, 4097, 12345, 100001]:
+        a = rng.random(n) * rng.integers(1, 1000)
+        assert L.np_sum_f64(a.ctypes.data, n) == a.sum()
+    for seed, (n, dens, integer, empty) in enumerate([(900, 0.1, False, 0.0), (1500, 0.05, True, 0.03), (2500, 0.02, True, 0.0)]):
+        m = random_hic(n, dens, seed, integer=integer, empty_frac=empty)
+        with np.errstate(divide="ignore"):
+            ref = ice_oracle.ice(m.copy(), max_iter=60, tolerance=1e-5)
+        for run in (lambda: hic_cpu.ice_loop(m, 60, 1e-5, threads=1)[:3], lambda: hic_cpu.ice_loop_mt(m, 60, 1e-5, threads=3)[:3]):
+            b, it, d = run()
+            assert it == ref["iterations"] and d == ref["deviation"]
+            np.testing.assert_array_equal(b / b[b != 0].mean(), ref["bias"])
+        # the masked CSR form: iterativeCorrection on matrix[keep][:, keep] without building the sub-matrix
+        keep = rng.random(n) > 0.1
+        sub = m[keep][:, keep].tocsr()
+        sub.sort_indices()
+        with np.errstate(divide="ignore"):
+            ref2 = ice_oracle.ice(sub.copy(), max_iter=60, tolerance=1e-5)
+        for threads in (1, 4):
+            b2, it2, d2, data2, _s = hic_cpu.ice_loop_masked(m, keep.astype(np.uint8), 60, 1e-5, threads=threads)
+            assert it2 == ref2["iterations"] and d2 == ref2["deviation"]
+            np.testing.assert_array_equal(b2 / b2[b2 != 0].mean(), ref2["bias"])
+        rs, dg = hic_cpu.row_stats_masked(m, keep.astype(np.uint8), threads=3)
+        # row sums: exact for counts (any order); scipy's own summation order is not restated for non-integer values
+        (np.testing.assert_array_equal if integer else np.testing.assert_allclose)(rs[keep], np.asarray(sub.sum(axis=1)).ravel())
+        np.testing.assert_array_equal(dg[keep], sub.diagonal())
+
+
+def test_threaded_kr_operator_equals_the_scipy_restatement():
+    from oracle import kr_oracle
+    from tests.helpers import random_hic
+    for seed in range(2):
+        m = random_hic(1200, 0.05, seed, low_frac=0.05)
+        a = kr_oracle.kr_balance(m)
+        b = kr_oracle.kr_balance(m, threaded=True)
+        assert (a["outer"], a["matvecs"]) == (b["outer"], b["matvecs"])
+        np.testing.assert_allclose(b["x"], a["x"], rtol=1e-13)
