@@ -149,6 +149,7 @@ int hb_csr_create(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t row0, in
 
 int hb_csr_create_typed(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t row0, int64_t nnz, const int64_t* indptr,
                         const void* indices, int indices_i64, const void* data_any, int value_kind, int device) {
+    HB_RANGE("hb_csr_create_typed");
     HB_REQUIRE(value_kind >= HB_VALUES_F64 && value_kind <= HB_VALUES_I64, "unknown value type");
     const double* data = static_cast<const double*>(data_any);
     HB_REQUIRE(indptr != nullptr, "null indptr");
@@ -378,6 +379,7 @@ int hb_set_comm(hb_csr* h, int rank, int world, hb_allreduce_fn fn, void* ctx) {
 }
 
 int hb_peer_export(hb_csr* h, int rank, int world, void* ipc_handle_out) {
+    HB_RANGE("hb_peer_export");
     HB_REQUIRE(h != nullptr && ipc_handle_out != nullptr, "bad arguments");
     HB_REQUIRE(world >= 2 && world <= HB_MAX_PEERS && rank >= 0 && rank < world, "peer exchange needs 2..8 ranks");
     int rc = hb_use_device(h);
@@ -401,6 +403,7 @@ int hb_peer_export(hb_csr* h, int rank, int world, void* ipc_handle_out) {
 }
 
 int hb_peer_attach(hb_csr* h, const void* all_handles) {
+    HB_RANGE("hb_peer_attach");
     HB_REQUIRE(h != nullptr && all_handles != nullptr && h->d_sym != nullptr, "call hb_peer_export first");
     int rc = hb_use_device(h);
     if (rc) return rc;
@@ -458,6 +461,7 @@ int hb_peer_attach_inprocess(hb_csr* h, hb_csr* const* ranks) {
 int hb_peer_active(const hb_csr* h) { return (h != nullptr && h->peer) ? 1 : 0; }
 
 int hb_csr_keep_rows(hb_csr* h, int64_t row_begin, int64_t row_end) {
+    HB_RANGE("hb_csr_keep_rows");
     HB_REQUIRE(h != nullptr, "null handle");
     HB_REQUIRE(h->row0 == 0 && h->n_rows == h->n_cols, "hb_csr_keep_rows starts from the full matrix");
     HB_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= h->n_rows, "bad row range");

@@ -117,6 +117,7 @@ hb_nonzero_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict_
 extern "C" {
 
 int hb_csr_value_stats(hb_csr* h, int scrub, double* sum_out, double* min_out, double* max_out) {
+    HB_RANGE("hb_csr_value_stats");
     HB_REQUIRE(h != nullptr, "null handle");
     int rc = hb_use_device(h);
     if (rc) return rc;
@@ -155,6 +156,7 @@ int hb_csr_value_stats(hb_csr* h, int scrub, double* sum_out, double* min_out, d
 }
 
 int hb_csr_normalize(hb_csr* h, int mode, double a, double b, double threshold, int scrub_first) {
+    HB_RANGE("hb_csr_normalize");
     HB_REQUIRE(h != nullptr && mode >= 0 && mode <= 3, "bad arguments");
     int rc = hb_use_device(h);
     if (rc) return rc;
@@ -169,6 +171,7 @@ int hb_csr_normalize(hb_csr* h, int mode, double a, double b, double threshold, 
 }
 
 int hb_csr_eliminate_zeros(hb_csr* h) {
+    HB_RANGE("hb_csr_eliminate_zeros");
     HB_REQUIRE(h != nullptr, "null handle");
     HB_REQUIRE(h->phase == 0, "row blocks with an alignment phase are not supported here");
     int rc = hb_use_device(h);

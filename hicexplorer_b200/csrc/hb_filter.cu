@@ -603,6 +603,7 @@ void hb_drop_pack(hb_csr* h) {
 extern "C" {
 
 int hb_csr_pack_values(hb_csr* h, int* kind_out) {
+    HB_RANGE("hb_csr_pack_values");
     HB_REQUIRE(h != nullptr, "null handle");
     int rc = hb_ensure_state(h);
     if (rc) return rc;
@@ -637,6 +638,7 @@ int hb_csr_pack_values(hb_csr* h, int* kind_out) {
 }
 
 int hb_scrub(hb_csr* h, int64_t counts[2]) {
+    HB_RANGE("hb_scrub");
     HB_REQUIRE(h != nullptr, "null handle");
     int rc = hb_ensure_state(h);
     if (rc) return rc;
@@ -664,6 +666,7 @@ int hb_row_stats(hb_csr* h, double* row_sum, double* diag) { return hb_row_stats
 int hb_row_stats_cis(hb_csr* h, double* row_sum, double* diag) { return hb_row_stats_impl(h, row_sum, diag, 1); }
 
 static int hb_row_stats_impl(hb_csr* h, double* row_sum, double* diag, int cis_only) {
+    HB_RANGE("hb_row_stats_impl");
     HB_REQUIRE(h != nullptr, "null handle");
     int rc = hb_use_device(h);
     if (rc) return rc;
@@ -689,6 +692,7 @@ static int hb_row_stats_impl(hb_csr* h, double* row_sum, double* diag, int cis_o
 
 int hb_mad_filter(hb_csr* h, double lo, double hi, uint8_t* mask_out, double* zscore_out, double* median_out,
                   double* mad_out) {
+    HB_RANGE("hb_mad_filter");
     HB_REQUIRE(h != nullptr && mask_out != nullptr, "bad arguments");
     HB_REQUIRE(h->world > 1 || (h->row0 == 0 && h->n_rows == h->n_cols),
                "hb_mad_filter needs the full matrix on one device unless hb_set_comm was called");
@@ -753,6 +757,7 @@ int hb_mad_filter(hb_csr* h, double lo, double hi, uint8_t* mask_out, double* zs
 }
 
 int hb_csr_compact(hb_csr* h, const uint8_t* remove_mask) {
+    HB_RANGE("hb_csr_compact");
     HB_REQUIRE(h != nullptr && remove_mask != nullptr, "bad arguments");
     // works on a row block too: every rank passes the same global mask and keeps its own surviving rows
     int rc = hb_use_device(h);
@@ -798,6 +803,7 @@ int hb_csr_compact(hb_csr* h, const uint8_t* remove_mask) {
 }
 
 int hb_csr_keep_cis(hb_csr* h) {
+    HB_RANGE("hb_csr_keep_cis");
     HB_REQUIRE(h != nullptr, "null handle");
     int rc = hb_use_device(h);
     if (rc) return rc;
@@ -813,6 +819,7 @@ int hb_csr_keep_upper(hb_csr* h) {
 }
 
 int hb_diag_zero(hb_csr* h) {
+    HB_RANGE("hb_diag_zero");
     HB_REQUIRE(h != nullptr, "null handle");
     int rc = hb_use_device(h);
     if (rc) return rc;
@@ -820,6 +827,7 @@ int hb_diag_zero(hb_csr* h) {
 }
 
 int hb_symmetry(hb_csr* h, double* ratio_out) {
+    HB_RANGE("hb_symmetry");
     HB_REQUIRE(h != nullptr && ratio_out != nullptr, "bad arguments");
     const bool sharded = h->world > 1;
     HB_REQUIRE(sharded || (h->row0 == 0 && h->n_rows == h->n_cols), "hb_symmetry needs the full matrix or hb_set_comm");

@@ -14,6 +14,7 @@
 // every rank.  Convergence lives on the device (per-segment flags), the host only polls.
 #include <cooperative_groups.h>
 
+#include <cstdio>
 #include <cstdlib>
 
 #include "hb_spmv.cuh"
@@ -37,11 +38,18 @@ struct HbIceEpi {
         }
         return seg_done[lo] == 0;
     }
+    struct Pre {
+        double r;
+    };
+    __device__ __forceinline__ Pre pre(int64_t g) const {
+        Pre q;
+        q.r = r[g];
+        return q;
+    }
     template <class Out>
-    __device__ __forceinline__ void row(int64_t g, double t, double m, int lane, const Out& peer) {
-        const double rg = r[g];
-        peer.store(g, rg * t, lane);
-        wmax = fmax(wmax, rg * m);  // NaN-ignoring, like np.any(W.data > 1e100)
+    __device__ __forceinline__ void row(int64_t g, double t, double m, int lane, const Out& peer, const Pre& q) {
+        peer.store(g, q.r * t, lane);
+        wmax = fmax(wmax, q.r * m);  // NaN-ignoring, like np.any(W.data > 1e100)
     }
     __device__ __forceinline__ double local_max() const {
         return __longlong_as_double((long long)atomicAdd(wmax_slot, 0ull));
@@ -313,8 +321,19 @@ struct HbIceLoopArgs {
     double* err;
     int iters, row_parity;
     double tol;
+    unsigned long long* timing;   // debug (HB_LOOP_TIMING=1): block 0 stamps %globaltimer at the phase boundaries
     HbLoopPeer peer;
 };
+
+__device__ __forceinline__ unsigned long long hb_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define HB_STAMP(slot)                                                                              \
+    do {                                                                                            \
+        if (a.timing != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && it < 32) a.timing[it * 8 + (slot)] = hb_globaltimer(); \
+    } while (0)
 
 struct HbIceLoopEpi {
     const double* r;  // written by this kernel between iterations: no __restrict__, no non-coherent loads
@@ -332,11 +351,18 @@ struct HbIceLoopEpi {
         }
         return __ldcg(seg_done + lo) == 0;
     }
+    struct Pre {
+        double r;
+    };
+    __device__ __forceinline__ Pre pre(int64_t g) const {
+        Pre q;
+        q.r = hb_ld_gather<true>(r + g);   // coherent, L1-cached: the row gathers its own diagonal neighbourhood anyway
+        return q;
+    }
     template <class Out>
-    __device__ __forceinline__ void row(int64_t g, double t, double m, int lane, const Out& peer) {
-        const double rg = __ldcg(r + g);
-        peer.store(g, rg * t, lane);
-        wmax = fmax(wmax, rg * m);
+    __device__ __forceinline__ void row(int64_t g, double t, double m, int lane, const Out& peer, const Pre& q) {
+        peer.store(g, q.r * t, lane);
+        wmax = fmax(wmax, q.r * m);
     }
     __device__ __forceinline__ double local_max() const { return 0.0; }
     __device__ __forceinline__ void warp_done() const {
@@ -369,6 +395,7 @@ hb_ice_loop_kernel(const __grid_constant__ HbIceLoopArgs a) {
         const int pb = (int)(seq & 1ull);
         double* exch = peer ? a.peer.buf[pb][a.peer.rank] : a.exch;
         // ---- A: marginals of the block's rows
+        HB_STAMP(0);
         if (blockIdx.x == 0 && threadIdx.x == 0) a.row_counters[par ^ 1] = 0ull;
         {
             HbIceLoopEpi epi;
@@ -387,10 +414,13 @@ hb_ice_loop_kernel(const __grid_constant__ HbIceLoopArgs a) {
                                                                   a.row_counters + par, epi, po);
         }
         if (peer && lane < world) __threadfence_system();   // each storing lane releases its own peer stores
+        HB_STAMP(1);
         grid.sync();
+        HB_STAMP(2);
         if (peer)
             hb_loop_publish_and_wait(a.peer, pb, seq, a.n_cols, __longlong_as_double((long long)__ldcg(a.wmax + cur)), a.err);
         // ---- B: per-tile sum / count of the non-zero marginals
+        HB_STAMP(3);
         for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
             double s = 0.0, c = 0.0;
             if (__ldcg(a.seg_done + a.tile_seg[t]) == 0) {
@@ -411,7 +441,9 @@ hb_ice_loop_kernel(const __grid_constant__ HbIceLoopArgs a) {
             }
         }
         if (blockIdx.x == 0 && threadIdx.x == 0) a.wmax[cur ^ 1] = 0ull;   // next iteration's accumulator
+        HB_STAMP(4);
         grid.sync();
+        HB_STAMP(5);
         if (peer && __ldcg(a.err) != 0.0) {   // consistent: every writer of err arrived at the barrier before
             if (blockIdx.x == 0 && threadIdx.x == 0) {
                 a.status[HB_ST_OVERFLOW] = 2;
@@ -470,7 +502,9 @@ hb_ice_loop_kernel(const __grid_constant__ HbIceLoopArgs a) {
                 atomicMax(a.devbits + (size_t)cur * a.nseg + seg, dmax);
             }
         }
+        HB_STAMP(6);
         grid.sync();
+        HB_STAMP(7);
         // ---- D: convergence per segment; every CTA computes the same answers from the same maxima
         if (threadIdx.x == 0) s_active = 0;
         __syncthreads();
@@ -605,6 +639,7 @@ static bool hb_persistent_enabled() {
 }
 
 int hb_dev_ice_loop(hb_csr* h, int iters, double tol, void* stream) {
+    HB_RANGE("hb_dev_ice_loop");
     HB_REQUIRE(h != nullptr && h->state_ready, "call hb_dev_ice_begin first");
     HB_REQUIRE(iters >= 0, "negative iteration count");
     HB_REQUIRE(h->world == 1 || h->peer, "hb_dev_ice_loop needs the exchange on the device (one GPU or hb_peer_attach)");
@@ -651,12 +686,40 @@ int hb_dev_ice_loop(hb_csr* h, int iters, double tol, void* stream) {
                      : h->pack_kind == 2 ? (const void*)hb_ice_loop_kernel<float>
                                          : (const void*)hb_ice_loop_kernel<double>;
     const int grid = hb_coop_grid(fn, h->n_rows, h->device);
+    const bool timing = getenv("HB_LOOP_TIMING") != nullptr;
+    unsigned long long* d_timing = nullptr;
+    if (timing) {
+        HB_CUDA(cudaMalloc(&d_timing, sizeof(unsigned long long) * 256));
+        HB_CUDA(cudaMemsetAsync(d_timing, 0, sizeof(unsigned long long) * 256, s));
+        a.timing = d_timing;
+    }
     void* params[] = {(void*)&a};
     HB_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(HB_SPMV_THREADS), params, 0, s));
     g_hb_launches.fetch_add(1, std::memory_order_relaxed);
     if (h->peer) {
         HB_CUDA(cudaEventRecord(h->loop_event, s));
         h->loop_pending = true;
+    }
+    if (timing) {   // debug aid: where an iteration spends its time, as seen by block 0 (ns)
+        unsigned long long t[256];
+        HB_CUDA(cudaStreamSynchronize(s));
+        HB_CUDA(cudaMemcpy(t, d_timing, sizeof(t), cudaMemcpyDeviceToHost));
+        cudaFree(d_timing);
+        const int m = iters < 32 ? iters : 32;
+        double acc[8] = {0};
+        int cnt = 0;
+        for (int it = 1; it + 1 < m; ++it) {   // skip the first and the last iteration of the launch
+            if (t[it * 8 + 7] == 0 || t[(it + 1) * 8] == 0) break;
+            for (int k = 0; k < 7; ++k) acc[k] += (double)(t[it * 8 + k + 1] - t[it * 8 + k]);
+            acc[7] += (double)(t[(it + 1) * 8] - t[it * 8 + 7]);
+            ++cnt;
+        }
+        if (cnt > 0)
+            fprintf(stderr,
+                    "[hb loop timing, block 0, us, mean of %d iterations, grid %d] rows %.1f | barrier1 %.1f | publish+wait %.1f | tile sums %.1f | "
+                    "barrier2 %.1f | update %.1f | barrier3 %.1f | convergence %.1f\n",
+                    cnt, grid, acc[0] / cnt / 1e3, acc[1] / cnt / 1e3, acc[2] / cnt / 1e3, acc[3] / cnt / 1e3, acc[4] / cnt / 1e3,
+                    acc[5] / cnt / 1e3, acc[6] / cnt / 1e3, acc[7] / cnt / 1e3);
     }
     return HB_OK;
 }
@@ -669,6 +732,7 @@ int hb_dev_ice_status(hb_csr* h, int32_t* pinned_status4, void* stream) {
 }
 
 int hb_dev_ice_finish(hb_csr* h, void* stream) {
+    HB_RANGE("hb_dev_ice_finish");
     HB_REQUIRE(h != nullptr && h->state_ready, "call hb_dev_ice_begin first");
     cudaStream_t s = pick_stream(h, stream);
     if (h->n_tiles == 0) return HB_OK;
@@ -719,6 +783,7 @@ int hb_ice_results(hb_csr* h, double* bias_out, int32_t* iters_out, double* dev_
 }
 
 int hb_ice_run(hb_csr* h, int max_iter, double tol, double* bias_out, int32_t* iters_out, double* dev_out) {
+    HB_RANGE("hb_ice_run");
     HB_REQUIRE(h != nullptr, "null handle");
     HB_REQUIRE(h->world > 1 || (h->row0 == 0 && h->n_rows == h->n_cols),
                "hb_ice_run needs the full matrix on one device unless hb_set_comm was called");
@@ -783,6 +848,7 @@ int hb_ice_run(hb_csr* h, int max_iter, double tol, double* bias_out, int32_t* i
 }
 
 int hb_ice_scaled_values(hb_csr* h, double* data_out, double* max_out) {
+    HB_RANGE("hb_ice_scaled_values");
     HB_REQUIRE(h != nullptr && h->state_ready, "run ICE first");
     HB_REQUIRE(data_out != nullptr || h->nnz == 0, "null output");
     int rc = hb_use_device(h);

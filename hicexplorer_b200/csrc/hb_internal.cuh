@@ -3,6 +3,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 
 #include <atomic>
@@ -151,6 +152,16 @@ struct HbScratch {
     HbScratch(const HbScratch&) = delete;
     HbScratch& operator=(const HbScratch&) = delete;
 };
+
+// NVTX range over a phase of the path (tracing): shows up in Nsight Systems / Compute timelines; costs
+// one function-pointer test when no profiler is attached (header-only NVTX v3).
+struct HbRange {
+    explicit HbRange(const char* name) { nvtxRangePushA(name); }
+    ~HbRange() { nvtxRangePop(); }
+    HbRange(const HbRange&) = delete;
+    HbRange& operator=(const HbRange&) = delete;
+};
+#define HB_RANGE(name) HbRange hb_range_guard_(name)
 
 int hb_build_tiles(hb_csr* h);
 int hb_ensure_state(hb_csr* h);

@@ -405,12 +405,23 @@ struct HbKrLoopEpi {
     const double* v;   // nullptr: outer residual  v = x o ((A + eps I) x)
     const double* p;
     double eps;
+    struct Pre {
+        double u, x, v, p;
+    };
     __device__ __forceinline__ bool active(int64_t) const { return true; }
+    __device__ __forceinline__ Pre pre(int64_t g) const {
+        Pre q;
+        q.u = hb_ld_gather<true>(u + g);
+        q.x = hb_ld_gather<true>(x + g);
+        q.v = v != nullptr ? hb_ld_gather<true>(v + g) : 0.0;
+        q.p = v != nullptr ? hb_ld_gather<true>(p + g) : 0.0;
+        return q;
+    }
     template <class Out>
-    __device__ __forceinline__ void row(int64_t g, double t, double, int lane, const Out& out) const {
-        double r = fma(eps, __ldcg(u + g), t);
-        r *= __ldcg(x + g);
-        if (v != nullptr) r = fma(__ldcg(v + g), __ldcg(p + g), r);
+    __device__ __forceinline__ void row(int64_t g, double t, double, int lane, const Out& out, const Pre& q) const {
+        double r = fma(eps, q.u, t);
+        r *= q.x;
+        if (v != nullptr) r = fma(q.v, q.p, r);
         out.store(g, r, lane);
     }
     __device__ __forceinline__ void warp_done() const {}
@@ -778,6 +789,7 @@ int hb_dev_spmv(hb_csr* h, const double* d_u, double eps, const double* d_a, con
 
 int hb_kr_run(hb_csr* h, double tol, double delta, double Delta, double diag_eps, int max_outer, double* x_out,
               int32_t* outer_out, int32_t* matvecs_out, double* residual_out) {
+    HB_RANGE("hb_kr_run");
     HB_REQUIRE(h != nullptr && x_out != nullptr, "bad arguments");
     HB_REQUIRE(h->world > 1 || (h->row0 == 0 && h->n_rows == h->n_cols),
                "hb_kr_run needs the full matrix on one device unless hb_set_comm was called");
@@ -1020,6 +1032,7 @@ done:
 }
 
 int hb_kr_rescale(hb_csr* h, double diag_eps, double* x_inout, double* factor_out) {
+    HB_RANGE("hb_kr_rescale");
     HB_REQUIRE(h != nullptr && x_inout != nullptr, "bad arguments");
     HB_REQUIRE(h->world > 1 || (h->row0 == 0 && h->n_rows == h->n_cols),
                "hb_kr_rescale needs the full matrix on one device unless hb_set_comm was called");
@@ -1072,6 +1085,7 @@ int hb_kr_rescale(hb_csr* h, double diag_eps, double* x_inout, double* factor_ou
 
 int hb_kr_scaled_upper(hb_csr* h, double diag_eps, const double* x, int64_t* nnz_out, int64_t* indptr, int32_t* indices,
                        double* data) {
+    HB_RANGE("hb_kr_scaled_upper");
     HB_REQUIRE(h != nullptr && x != nullptr && nnz_out != nullptr, "bad arguments");
     // row-local: on a row block the output is the block's rows (indptr[n_rows+1] block-local, global column ids)
     int rc = hb_use_device(h);

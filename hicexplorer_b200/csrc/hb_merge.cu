@@ -178,6 +178,7 @@ hb_merge_rows_kernel(const int64_t* __restrict__ indptr, const int32_t* __restri
 
 
 extern "C" int hb_csr_merge_bins(hb_csr* h, const int32_t* bin_map, int64_t n_new) {
+    HB_RANGE("hb_csr_merge_bins");
     HB_REQUIRE(h != nullptr && bin_map != nullptr, "bad arguments");
     HB_REQUIRE(h->row0 == 0 && h->n_rows == h->n_cols, "hb_csr_merge_bins needs the full matrix on one device");
     HB_REQUIRE(n_new >= 0 && n_new <= h->n_cols, "bad merged size");
@@ -287,6 +288,7 @@ fail:
 
 // C = A + B on two stores of the same shape (hicSumMatrices.py:59): `h` becomes the sum, `other` is left untouched
 extern "C" int hb_csr_add(hb_csr* h, const hb_csr* other) {
+    HB_RANGE("hb_csr_add");
     HB_REQUIRE(h != nullptr && other != nullptr && h != other, "bad arguments");
     HB_REQUIRE(h->n_rows == other->n_rows && h->n_cols == other->n_cols && h->row0 == other->row0,
                "the matrices have different shapes");

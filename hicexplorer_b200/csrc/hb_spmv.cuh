@@ -28,11 +28,18 @@
 // COHERENT selects how the gathered vector is read: false = non-coherent read-only path (__ldg; the vector is constant
 // for the whole launch), true = ordinary L1-cached loads that the acquire side of a grid barrier invalidates (the
 // persistent solver kernels rewrite the vector between iterations of one launch).
+#ifndef HB_LOOP_GATHER
+#define HB_LOOP_GATHER 0   // 0: weak ld.global (shipped) ; tuning experiments only: 1 = non-coherent, 2 = weak + L1::evict_last
+#endif
 template <bool COHERENT>
 __device__ __forceinline__ double hb_ld_gather(const double* p) {
-    if (COHERENT) {
+    if (COHERENT && HB_LOOP_GATHER != 1) {
         double r;
+#if HB_LOOP_GATHER == 2
+        asm volatile("ld.global.L1::evict_last.f64 %0, [%1];" : "=d"(r) : "l"(p));
+#else
         asm volatile("ld.global.f64 %0, [%1];" : "=d"(r) : "l"(p));   // weak, default caching: LDG.E.64
+#endif
         return r;
     }
     return __ldg(p);
@@ -148,7 +155,8 @@ static __global__ void hb_peer_wait_kernel(const unsigned long long* __restrict_
 
 // Epi must provide:
 //   __device__ bool active(int64_t global_row) const;                                  // skip rows of finished segments
-//   __device__ void row(int64_t global_row, double t, double m, int lane, peer);       // all lanes, t and m warp-uniform
+//   struct Pre; __device__ Pre pre(int64_t global_row) const;                          // per-row operands, loaded early
+//   __device__ void row(int64_t global_row, double t, double m, int lane, peer, pre);  // all lanes, t and m warp-uniform
 //   __device__ void warp_done();                                                       // lane 0 only, once per warp
 //   __device__ double local_max() const;                                               // last warp: value for slot n+rank
 //
@@ -175,9 +183,12 @@ __device__ __forceinline__ void hb_spmv_rows(const int64_t* __restrict__ indptr,
             const int64_t e = __shfl_sync(0xffffffffu, bounds, q + 1);
             const int64_t row = batch + q;
             if (row < n_rows && epi.active(row0 + row)) {
+                // the epilogue's own operands (r_i; x_i, u_i, v_i, p_i) are requested BEFORE the row is streamed: at the
+                // end of the row their latency would sit, un-overlapped, in front of the next row's first loads
+                const typename Epi::Pre pre = epi.pre(row0 + row);
                 double t, m = 0.0;
                 hb_row_dot<WANT_MAX, VT, COHERENT>(idx, val, u, s, e, lane, t, m);
-                epi.row(row0 + row, t, m, lane, peer);
+                epi.row(row0 + row, t, m, lane, peer, pre);
             }
         }
         nxt = __shfl_sync(0xffffffffu, nxt, 0);
@@ -347,12 +358,23 @@ struct HbAffineEpi {
     const double* __restrict__ b;
     const double* __restrict__ c;
     double eps;
+    struct Pre {
+        double u, a, b, c;
+    };
     __device__ __forceinline__ bool active(int64_t) const { return true; }
+    __device__ __forceinline__ Pre pre(int64_t g) const {
+        Pre q;
+        q.u = u[g];
+        q.a = a != nullptr ? a[g] : 1.0;
+        q.b = (b != nullptr && c != nullptr) ? b[g] : 0.0;
+        q.c = (b != nullptr && c != nullptr) ? c[g] : 0.0;
+        return q;
+    }
     template <class Out>
-    __device__ __forceinline__ void row(int64_t g, double t, double, int lane, const Out& peer) const {
-        double v = fma(eps, u[g], t);
-        if (a != nullptr) v *= a[g];
-        if (b != nullptr && c != nullptr) v = fma(b[g], c[g], v);
+    __device__ __forceinline__ void row(int64_t g, double t, double, int lane, const Out& peer, const Pre& q) const {
+        double v = fma(eps, q.u, t);
+        if (a != nullptr) v *= q.a;
+        if (b != nullptr && c != nullptr) v = fma(q.b, q.c, v);
         peer.store(g, v, lane);
     }
     __device__ __forceinline__ void warp_done() const {}

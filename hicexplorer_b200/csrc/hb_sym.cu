@@ -220,6 +220,7 @@ int hb_csr_create_upper(hb_csr** out, int64_t n, int64_t nnz_upper, const int64_
 
 int hb_csr_create_upper_typed(hb_csr** out, int64_t n, int64_t nnz_upper, const int64_t* indptr, const int32_t* indices,
                               const void* data, int value_kind, int device) {
+    HB_RANGE("hb_csr_create_upper_typed");
     HB_REQUIRE(out != nullptr && indptr != nullptr, "bad arguments");
     // upload the triangle with the ordinary constructor, then replace the store by its symmetric completion
     int rc = hb_csr_create_typed(out, n, n, 0, nnz_upper, indptr, indices, 0, data, value_kind, device);
@@ -233,6 +234,7 @@ int hb_csr_create_upper_typed(hb_csr** out, int64_t n, int64_t nnz_upper, const 
 }
 
 int hb_csr_symmetrize_upper(hb_csr* h) {
+    HB_RANGE("hb_csr_symmetrize_upper");
     HB_REQUIRE(h != nullptr, "null handle");
     HB_REQUIRE(h->row0 == 0 && h->n_rows == h->n_cols, "hb_csr_symmetrize_upper needs the full (upper-triangular) matrix");
     int rc = hb_use_device(h);
@@ -465,6 +467,7 @@ int hb_csr_shifted_copy(hb_csr** out, const hb_csr* src, int64_t dr, int64_t dc)
 
 int hb_ice_scaled_upper(hb_csr* h, const int64_t* orig_ids, int64_t n_orig, int64_t* nnz_out, int64_t* indptr,
                         int32_t* indices, double* data) {
+    HB_RANGE("hb_ice_scaled_upper");
     HB_REQUIRE(h != nullptr && h->state_ready && orig_ids != nullptr && nnz_out != nullptr, "run ICE first");
     HB_REQUIRE(n_orig >= h->n_cols && n_orig < 2147483647LL, "bad original frame size");
     int rc = hb_use_device(h);

@@ -169,6 +169,7 @@ hb_synth_rows_kernel(HbSynthDev p, const int64_t* __restrict__ chrom_off, int nc
 
 extern "C" int hb_synth_create(hb_csr** out, const hb_synth_params* prm, const int64_t* chrom_bins, int64_t row0,
                                int64_t n_rows, int device) {
+    HB_RANGE("hb_synth_create");
     HB_REQUIRE(out != nullptr && prm != nullptr && chrom_bins != nullptr, "bad arguments");
     HB_REQUIRE(prm->nchrom >= 1 && prm->nchrom <= 4096, "bad chromosome count");
     HB_REQUIRE(prm->n_trans >= 0 && prm->n_trans <= HB_SYNTH_MAX_TRANS, "n_trans must be <= 32");

@@ -169,6 +169,7 @@ extern "C" {
 
 int hb_trans_order_stats(hb_csr* h, const int64_t* chr_offsets, int nchr, int64_t k, int64_t* n_trans_out, double* v_k,
                          double* v_k1) {
+    HB_RANGE("hb_trans_order_stats");
     HB_REQUIRE(h != nullptr && chr_offsets != nullptr && nchr >= 1 && n_trans_out != nullptr, "bad arguments");
     HB_REQUIRE(h->row0 == 0 && h->n_rows == h->n_cols, "hb_trans_order_stats needs the full matrix on one device");
     HB_REQUIRE(chr_offsets[0] == 0 && chr_offsets[nchr] == h->n_cols, "chromosome offsets must span [0, n]");
@@ -226,6 +227,7 @@ int hb_trans_order_stats(hb_csr* h, const int64_t* chr_offsets, int nchr, int64_
 }
 
 int hb_trans_clip(hb_csr* h, const int64_t* chr_offsets, int nchr, double max_inter, int64_t* n_clipped_out) {
+    HB_RANGE("hb_trans_clip");
     HB_REQUIRE(h != nullptr && chr_offsets != nullptr && nchr >= 1, "bad arguments");
     HB_REQUIRE(h->row0 == 0 && h->n_rows == h->n_cols, "hb_trans_clip needs the full matrix on one device");
     HB_REQUIRE(chr_offsets[0] == 0 && chr_offsets[nchr] == h->n_cols, "chromosome offsets must span [0, n]");
@@ -260,6 +262,7 @@ int hb_trans_clip(hb_csr* h, const int64_t* chr_offsets, int nchr, double max_in
 }
 
 int hb_ice_scaled_row_sums(hb_csr* h, double* out) {
+    HB_RANGE("hb_ice_scaled_row_sums");
     HB_REQUIRE(h != nullptr && h->state_ready && out != nullptr, "run ICE first");
     int rc = hb_use_device(h);
     if (rc) return rc;

@@ -149,6 +149,7 @@ hb_obs_exp_apply_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
 extern "C" {
 
 int hb_distance_stats(hb_csr* h, double* sums_out, int64_t* counts_out) {
+    HB_RANGE("hb_distance_stats");
     HB_REQUIRE(h != nullptr && sums_out != nullptr, "bad arguments");
     HB_REQUIRE(h->row0 == 0 && h->n_rows == h->n_cols, "hb_distance_stats needs the full matrix on one device");
     int rc = hb_ensure_state(h);   // segment table on the device
@@ -193,6 +194,7 @@ int hb_distance_stats(hb_csr* h, double* sums_out, int64_t* counts_out) {
 
 int hb_obs_exp_apply(hb_csr* h, const double* expected, int index_mode, int out_mode, const double* row_sum,
                      const double* seg_total) {
+    HB_RANGE("hb_obs_exp_apply");
     HB_REQUIRE(h != nullptr && expected != nullptr, "bad arguments");
     HB_REQUIRE(h->row0 == 0 && h->n_rows == h->n_cols, "hb_obs_exp_apply needs the full matrix on one device");
     HB_REQUIRE(index_mode >= 0 && index_mode <= 1 && out_mode >= 0 && out_mode <= 2, "bad mode");
