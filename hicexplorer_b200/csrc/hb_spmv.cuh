@@ -49,10 +49,10 @@ template <bool WANT_MAX, typename VT, bool COHERENT = false>
 __device__ __forceinline__ void hb_row_dot(const int32_t* __restrict__ idx, const VT* __restrict__ val,
                                            const double* u, int64_t s, int64_t e, int lane,
                                            double& sum_out, double& max_out) {
-    constexpr int U = HB_SPMV_UNROLL;
     double acc0 = 0.0, acc1 = 0.0;
     double mx = -INFINITY;
     int64_t k = s + lane;
+    constexpr int U = HB_SPMV_UNROLL;
     for (; k + 32 * (U - 1) < e; k += 32 * U) {
         int c[U];
         double v[U], g[U];
