@@ -9,6 +9,8 @@
 //                      state (the corrected matrix is never materialised for it).
 #include "hb_internal.cuh"
 
+#define HB_MAX_SLOTS 64
+
 struct HbTransSel {
     unsigned long long prefix;  // decided high bits of the ordered key
     unsigned long long mask;    // which bits are decided
@@ -39,8 +41,8 @@ __device__ __forceinline__ void hb_chr_range(const int64_t* __restrict__ off, in
 template <int MODE>
 __global__ void __launch_bounds__(256)
 hb_trans_pass_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, double* __restrict__ val, int64_t n_rows,
-                     const int64_t* __restrict__ chr_off, int nchr, HbTransSel* st, int shift, unsigned long long* __restrict__ hist,
-                     double limit, unsigned long long* n_clipped) {
+                     int64_t row0, const int64_t* __restrict__ chr_off, int nchr, HbTransSel* st, int shift,
+                     unsigned long long* __restrict__ hist, double limit, unsigned long long* n_clipped) {
     __shared__ unsigned int sh[256];
     if (MODE == 0) {
         sh[threadIdx.x] = 0;
@@ -53,7 +55,7 @@ hb_trans_pass_kernel(const int64_t* __restrict__ indptr, const int32_t* __restri
     unsigned long long cnt = 0, mn = ~0ull;
     for (int64_t row = gwarp; row < n_rows; row += nwarps) {
         int64_t clo, chi;
-        hb_chr_range(chr_off, nchr, row, clo, chi);
+        hb_chr_range(chr_off, nchr, row0 + row, clo, chi);
         const int64_t e = indptr[row + 1];
         for (int64_t k0 = indptr[row]; k0 < e; k0 += 32 * 4) {
             int c[4];
@@ -137,6 +139,16 @@ __global__ void hb_trans_pick_kernel(HbTransSel* st, unsigned long long* hist, i
     }
 }
 
+// sharded runs: the path's one collective sums doubles; counts below 2^53 travel exactly
+__global__ void hb_u64_to_f64_kernel(const unsigned long long* __restrict__ in, double* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (double)in[i];
+}
+__global__ void hb_f64_to_u64_kernel(const double* __restrict__ in, unsigned long long* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (unsigned long long)in[i];
+}
+
 // row sums of the corrected matrix, same per-entry arithmetic as the emission (hb_ice_emit_kernel)
 __global__ void __launch_bounds__(256)
 hb_scaled_row_sums_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
@@ -171,7 +183,10 @@ int hb_trans_order_stats(hb_csr* h, const int64_t* chr_offsets, int nchr, int64_
                          double* v_k1) {
     HB_RANGE("hb_trans_order_stats");
     HB_REQUIRE(h != nullptr && chr_offsets != nullptr && nchr >= 1 && n_trans_out != nullptr, "bad arguments");
-    HB_REQUIRE(h->row0 == 0 && h->n_rows == h->n_cols, "hb_trans_order_stats needs the full matrix on one device");
+    const bool sharded = h->world > 1;
+    HB_REQUIRE(sharded || (h->row0 == 0 && h->n_rows == h->n_cols),
+               "hb_trans_order_stats needs the full matrix on one device unless hb_set_comm was called");
+    HB_REQUIRE(!sharded || h->allreduce != nullptr, "sharded hb_trans_order_stats needs the allreduce callback (hb_set_comm)");
     HB_REQUIRE(chr_offsets[0] == 0 && chr_offsets[nchr] == h->n_cols, "chromosome offsets must span [0, n]");
     for (int c = 0; c < nchr; ++c) HB_REQUIRE(chr_offsets[c] <= chr_offsets[c + 1], "chromosome offsets must ascend");
     int rc = hb_use_device(h);
@@ -180,37 +195,71 @@ int hb_trans_order_stats(hb_csr* h, const int64_t* chr_offsets, int nchr, int64_
     int64_t* d_off = nullptr;
     HbTransSel* d_st = nullptr;
     unsigned long long* d_hist = nullptr;
+    double* d_f = nullptr;   // sharded: histogram / final slots as doubles for the collective
     HbTransSel st = {0, 0, (unsigned long long)(k > 0 ? k : 0), 0, ~0ull, 0};
     const bool want = v_k != nullptr || v_k1 != nullptr;
-    cudaError_t e = cudaMalloc(&d_off, sizeof(int64_t) * (size_t)(nchr + 1));
-    if (e == cudaSuccess) e = cudaMalloc(&d_st, sizeof(HbTransSel));
-    if (e == cudaSuccess) e = cudaMalloc(&d_hist, sizeof(unsigned long long) * 256);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_off, chr_offsets, sizeof(int64_t) * (size_t)(nchr + 1), cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_st, &st, sizeof(st), cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess) e = cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * 256, s);
-    if (e == cudaSuccess && h->n_rows > 0) {
-        const int grid = HB_NUM_SMS * 8;
-        // the first pass also counts the trans entries; a pure count (v_k == v_k1 == NULL) stops after it
-        for (int pass = 0; pass < (want ? 8 : 1); ++pass) {
-            const int shift = 56 - 8 * pass;
-            hb_trans_pass_kernel<0><<<grid, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, h->n_rows, d_off, nchr, d_st, shift,
-                                                         d_hist, 0.0, nullptr);
-            hb_trans_pick_kernel<<<1, 256, 0, s>>>(d_st, d_hist, shift, pass == 0);
-            g_hb_launches.fetch_add(2);
-        }
-        if (want) {
-            hb_trans_pass_kernel<1><<<grid, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, h->n_rows, d_off, nchr, d_st, 0, d_hist,
-                                                         0.0, nullptr);
+    HbScratch scratch;
+    HB_CUDA(scratch.alloc(&d_off, sizeof(int64_t) * (size_t)(nchr + 1)));
+    HB_CUDA(scratch.alloc(&d_st, sizeof(HbTransSel)));
+    HB_CUDA(scratch.alloc(&d_hist, sizeof(unsigned long long) * 256));
+    HB_CUDA(scratch.alloc(&d_f, sizeof(double) * 512));
+    HB_CUDA(cudaMemcpyAsync(d_off, chr_offsets, sizeof(int64_t) * (size_t)(nchr + 1), cudaMemcpyHostToDevice, s));
+    HB_CUDA(cudaMemcpyAsync(d_st, &st, sizeof(st), cudaMemcpyHostToDevice, s));
+    HB_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * 256, s));
+    const int grid = HB_NUM_SMS * 8;
+    // the first pass also counts the trans entries; a pure count (v_k == v_k1 == NULL) stops after it
+    for (int pass = 0; pass < (want ? 8 : 1); ++pass) {
+        const int shift = 56 - 8 * pass;
+        if (h->n_rows > 0) {
+            hb_trans_pass_kernel<0><<<grid, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, h->n_rows, h->row0, d_off, nchr, d_st,
+                                                         shift, d_hist, 0.0, nullptr);
             g_hb_launches.fetch_add(1);
         }
+        if (sharded) {
+            // every rank holds the histogram of its rows: sum them, then all ranks pick the same digit
+            hb_u64_to_f64_kernel<<<1, 256, 0, s>>>(d_hist, d_f, 256);
+            if (h->allreduce(h->comm_ctx, d_f, 256, (void*)s) != 0) {
+                hb_set_error("collective callback failed");
+                return HB_ERR_CUDA;
+            }
+            hb_f64_to_u64_kernel<<<1, 256, 0, s>>>(d_f, d_hist, 256);
+            g_hb_launches.fetch_add(2);
+        }
+        hb_trans_pick_kernel<<<1, 256, 0, s>>>(d_st, d_hist, shift, pass == 0);
+        g_hb_launches.fetch_add(1);
     }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(&st, d_st, sizeof(st), cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    if (e == cudaSuccess) e = cudaGetLastError();
-    cudaFree(d_off);
-    cudaFree(d_st);
-    cudaFree(d_hist);
-    if (e != cudaSuccess) return hb_cuda_fail(e, "trans order statistics", __FILE__, __LINE__);
+    if (want && h->n_rows > 0) {
+        hb_trans_pass_kernel<1><<<grid, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, h->n_rows, h->row0, d_off, nchr, d_st, 0,
+                                                     d_hist, 0.0, nullptr);
+        g_hb_launches.fetch_add(1);
+    }
+    HB_CUDA(cudaMemcpyAsync(&st, d_st, sizeof(st), cudaMemcpyDeviceToHost, s));
+    HB_CUDA(cudaStreamSynchronize(s));
+    HB_CUDA(cudaGetLastError());
+    if (want && sharded) {
+        // n_le adds up; min_gt is the smallest over the ranks: each rank ships (n_le, four 16-bit limbs of min_gt) in its
+        // own slot of a zeroed vector, one sum-allreduce assembles all slots
+        double slots[HB_MAX_SLOTS * 5];
+        HB_REQUIRE(h->world <= HB_MAX_SLOTS, "too many ranks");
+        for (int i = 0; i < h->world * 5; ++i) slots[i] = 0.0;
+        slots[h->rank * 5 + 0] = (double)st.n_le;
+        for (int l = 0; l < 4; ++l) slots[h->rank * 5 + 1 + l] = (double)((st.min_gt >> (16 * l)) & 0xffffull);
+        HB_CUDA(cudaMemcpyAsync(d_f, slots, sizeof(double) * (size_t)(h->world * 5), cudaMemcpyHostToDevice, s));
+        if (h->allreduce(h->comm_ctx, d_f, h->world * 5, (void*)s) != 0) {
+            hb_set_error("collective callback failed");
+            return HB_ERR_CUDA;
+        }
+        HB_CUDA(cudaMemcpyAsync(slots, d_f, sizeof(double) * (size_t)(h->world * 5), cudaMemcpyDeviceToHost, s));
+        HB_CUDA(cudaStreamSynchronize(s));
+        st.n_le = 0;
+        st.min_gt = ~0ull;
+        for (int q = 0; q < h->world; ++q) {
+            st.n_le += (unsigned long long)slots[q * 5];
+            unsigned long long m = 0;
+            for (int l = 0; l < 4; ++l) m |= ((unsigned long long)slots[q * 5 + 1 + l]) << (16 * l);
+            if (m < st.min_gt) st.min_gt = m;
+        }
+    }
     *n_trans_out = (int64_t)st.n_trans;
     if (want) {
         HB_REQUIRE(k >= 0 && (unsigned long long)k < st.n_trans, "rank outside the trans entries");
@@ -229,7 +278,7 @@ int hb_trans_order_stats(hb_csr* h, const int64_t* chr_offsets, int nchr, int64_
 int hb_trans_clip(hb_csr* h, const int64_t* chr_offsets, int nchr, double max_inter, int64_t* n_clipped_out) {
     HB_RANGE("hb_trans_clip");
     HB_REQUIRE(h != nullptr && chr_offsets != nullptr && nchr >= 1, "bad arguments");
-    HB_REQUIRE(h->row0 == 0 && h->n_rows == h->n_cols, "hb_trans_clip needs the full matrix on one device");
+    // row-local: on a row block the count is that of the block's rows
     HB_REQUIRE(chr_offsets[0] == 0 && chr_offsets[nchr] == h->n_cols, "chromosome offsets must span [0, n]");
     int rc = hb_use_device(h);
     if (rc) return rc;
@@ -239,24 +288,21 @@ int hb_trans_clip(hb_csr* h, const int64_t* chr_offsets, int nchr, double max_in
     HbTransSel* d_st = nullptr;
     unsigned long long* d_cnt = nullptr;
     unsigned long long cnt = 0;
-    cudaError_t e = cudaMalloc(&d_off, sizeof(int64_t) * (size_t)(nchr + 1));
-    if (e == cudaSuccess) e = cudaMalloc(&d_st, sizeof(HbTransSel));
-    if (e == cudaSuccess) e = cudaMalloc(&d_cnt, sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_off, chr_offsets, sizeof(int64_t) * (size_t)(nchr + 1), cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess) e = cudaMemsetAsync(d_st, 0, sizeof(HbTransSel), s);
-    if (e == cudaSuccess) e = cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), s);
-    if (e == cudaSuccess && h->n_rows > 0) {
-        hb_trans_pass_kernel<2><<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, h->n_rows, d_off, nchr, d_st, 0,
-                                                               nullptr, max_inter, d_cnt);
+    HbScratch scratch;
+    HB_CUDA(scratch.alloc(&d_off, sizeof(int64_t) * (size_t)(nchr + 1)));
+    HB_CUDA(scratch.alloc(&d_st, sizeof(HbTransSel)));
+    HB_CUDA(scratch.alloc(&d_cnt, sizeof(unsigned long long)));
+    HB_CUDA(cudaMemcpyAsync(d_off, chr_offsets, sizeof(int64_t) * (size_t)(nchr + 1), cudaMemcpyHostToDevice, s));
+    HB_CUDA(cudaMemsetAsync(d_st, 0, sizeof(HbTransSel), s));
+    HB_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), s));
+    if (h->n_rows > 0) {
+        hb_trans_pass_kernel<2><<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, h->n_rows, h->row0, d_off, nchr,
+                                                               d_st, 0, nullptr, max_inter, d_cnt);
         g_hb_launches.fetch_add(1);
     }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(&cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    if (e == cudaSuccess) e = cudaGetLastError();
-    cudaFree(d_off);
-    cudaFree(d_st);
-    cudaFree(d_cnt);
-    if (e != cudaSuccess) return hb_cuda_fail(e, "trans clip", __FILE__, __LINE__);
+    HB_CUDA(cudaMemcpyAsync(&cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, s));
+    HB_CUDA(cudaStreamSynchronize(s));
+    HB_CUDA(cudaGetLastError());
     if (n_clipped_out) *n_clipped_out = (int64_t)cnt;
     return HB_OK;
 }

@@ -8,7 +8,7 @@ Differences, all additive or documented:
     and the iterations on the device (``pipeline.ice_pipeline``) instead of round-tripping through scipy;
   * launched under ``torchrun`` (WORLD_SIZE > 1) the genome-wide ICE / KR corrections run on nnz-balanced row blocks,
     one process per GPU, ``--perchr`` KR deals whole chromosomes to the GPUs, and rank 0 writes the output
-    (``--sequencedCountCutoff``, ``--transCutoff`` and ``--inflationCutoff`` stay single-GPU);
+    (``--sequencedCountCutoff``, ``--transCutoff`` and ``--inflationCutoff`` work on the row blocks too);
   * ``diagnostic_plot`` (:425-545) computes its statistics on the device -- coverage per bin, modified z-scores, the
     100-bin histogram of the bins with z < 5 and the z-score of its first local minimum, logged as "mad threshold" like
     the reference -- and draws the histogram with matplotlib when it is installed, else as a hand-written SVG;
@@ -16,7 +16,7 @@ Differences, all additive or documented:
     row sums for ``--inflationCutoff``; like the published hicmatrix code (whose clipping statement is a comparison)
     it leaves the values unchanged unless the additive ``--clipTrans`` flag asks for the documented clipping.
     ``--inflationCutoff`` only ever worked together with ``--transCutoff`` in the reference (``pre_row_sum`` is
-    otherwise undefined, :699/:771 -> NameError) and exits with an explanation when given alone; both are single-GPU.
+    otherwise undefined, :699/:771 -> NameError) and exits with an explanation when given alone.
 """
 import argparse
 import logging
@@ -166,8 +166,18 @@ def diagnostic_statistics(ma, perchr=False, x_max=None, device=0):
         drop = ma.upper_drop_mask() if up is not None else None
         if drop is not None:
             dev.compact(drop)
-        dev.scrub()                                         # convertNansToZeros / convertInfsToZeros (:486-487)
-        offsets = ma.chromosome_offsets() if perchr else np.asarray([0, dev.n], dtype=np.int64)
+        # "mask all zero value bins" happens for the plot too (:616-619), on row sums that include the diagonal and
+        # still see NaNs; the medians, z-scores and the histogram are those of the remaining bins
+        row_sum_all, _ = dev.row_stats()
+        zero = row_sum_all == 0
+        log.info("Removing {} zero value bins".format(int(zero.sum())))
+        chrom_offsets = ma.chromosome_offsets()
+        if zero.any():
+            dev.compact(zero.astype(np.uint8))
+            from .pipeline import _segment_offsets_after
+            chrom_offsets = _segment_offsets_after(zero, chrom_offsets)
+        dev.scrub()                                         # convertNansToZeros / convertInfsToZeros (:624-625, :486-487)
+        offsets = np.asarray(chrom_offsets, dtype=np.int64) if perchr else np.asarray([0, dev.n], dtype=np.int64)
         if perchr:
             dev.set_segments(offsets)
         row_sum, diag = dev.row_stats(cis_only=perchr)
@@ -311,9 +321,6 @@ def _correct_ice(ma, args, world=1, rank=0):
         log.error('--inflationCutoff needs --transCutoff (the reference only defines pre_row_sum then, '
                   'hicCorrectMatrix.py:699, 771)')
         sys.exit(1)
-    if (trans_on or args.inflationCutoff) and world > 1:
-        log.error('--transCutoff / --inflationCutoff are not available in multi-GPU runs')
-        sys.exit(1)
     intervals_all = list(ma.cut_intervals)
     extra_fn = None
     if args.sequencedCountCutoff and 0 < args.sequencedCountCutoff < 1:
@@ -323,9 +330,6 @@ def _correct_ice(ma, args, world=1, rank=0):
             return coverage[kept_ids] < args.sequencedCountCutoff
 
     if world > 1:
-        if extra_fn is not None:
-            log.error('--sequencedCountCutoff is not available in multi-GPU runs')
-            sys.exit(1)
         file_layout = not args.perchr or str(args.outFileName).endswith('.h5')
         # every rank maps the same file; when the matrix is untouched each uploads the stored upper triangle, builds the
         # symmetric store on its GPU and keeps its own rows -- no symmetric matrix on any host
@@ -334,9 +338,15 @@ def _correct_ice(ma, args, world=1, rank=0):
                                    max_iter=args.iterNum, tolerance=args.tolerance, chr_offsets=ma.chromosome_offsets(),
                                    perchr=args.perchr, skip_diagonal=args.skipDiagonal, want_matrix=file_layout,
                                    file_layout=file_layout, upper_input=up is not None,
-                                   drop_mask=ma.upper_drop_mask() if up is not None else None)
+                                   drop_mask=ma.upper_drop_mask() if up is not None else None, extra_mask_fn=extra_fn,
+                                   trans_cutoff=args.transCutoff, clip_trans=args.clipTrans,
+                                   inflation_cutoff=args.inflationCutoff)
         if rank != 0:
             return
+        if res.get('max_inter') is not None:
+            log.info("trans contacts: {} percentile = {}".format(100 - float(args.transCutoff) / 100, res['max_inter']))
+        if 'inflated_rel' in res:
+            log.info("inflated >={} regions: {}".format(args.inflationCutoff, len(res['inflated_rel'])))
     else:
         # the file's upper triangle goes to the device as it is (the mirror image is built in HBM) and the corrected
         # matrix comes back already in file layout, whenever nothing on the host has touched the matrix since loading
@@ -420,7 +430,8 @@ def _correct_kr_from_upper(ma, up, args):
         drop = None
     n = len(ma.cut_intervals)
     if not args.perchr:
-        res = kr_pipeline(up, rescale=True, want_matrix=want_matrix, device=args.device, upper_input=True, drop_mask=drop)
+        res = kr_pipeline(up, rescale=True, want_matrix=want_matrix, device=args.device, upper_input=True, drop_mask=drop,
+                          skip_diagonal=args.skipDiagonal)
         print("normalisation factor is {}".format(res['factor']))
         upper = _drop_explicit_zeros(res['upper']) if want_matrix else up
         ma.install_file_layout(upper, ma.nan_bins, np.asarray(res['x']).reshape(-1, 1))
@@ -430,7 +441,7 @@ def _correct_kr_from_upper(ma, up, args):
     def balance(ci):
         lo, hi = int(offsets[ci]), int(offsets[ci + 1])
         res = kr_pipeline(up[lo:hi, lo:hi].tocsr(), rescale=want_matrix, want_matrix=want_matrix, device=args.device,
-                          upper_input=True)
+                          upper_input=True, skip_diagonal=args.skipDiagonal)
         if want_matrix:
             print("normalisation factor is {}".format(res['factor']))
         return ci, res
@@ -447,31 +458,49 @@ def _correct_kr_from_upper(ma, up, args):
     ma.install_file_layout(upper, ma.nan_bins, factors)
 
 
+def _scrubbed(matrix, skip_diagonal):
+    """what both methods see (hicCorrectMatrix.py:624-626, 648-649): NaN / Inf -> 0, float64, optionally a zero diagonal
+    (host-side route of re-ordered matrices; the device routes call hb_scrub / hb_diag_zero)"""
+    m = sparse.csr_matrix(matrix, dtype=np.float64, copy=True)
+    m.data[~np.isfinite(m.data)] = 0
+    if skip_diagonal:
+        m.setdiag(0)
+    return m
+
+
 def _correct_kr(ma, args, world=1, rank=0):
     up = ma.upper_for_device()
     if up is not None and world == 1:
         return _correct_kr_from_upper(ma, up, args)
-    if world > 1 and not args.perchr and not str(args.outFileName).endswith('.h5'):
-        # genome-wide KR to .cool: only the (rescaled) vector is needed -> row blocks over the GPUs
+    if world > 1 and not args.perchr:
+        # genome-wide KR on nnz-balanced row blocks over the GPUs: the (rescaled) vector is replicated; for .h5 every rank
+        # also emits its rows of the balanced matrix in file layout and rank 0 concatenates them
+        want_matrix = str(args.outFileName).endswith('.h5')
         if up is not None:
             drop = ma.upper_drop_mask()
-            res = kr_pipeline_sharded(up, rescale=True, upper_input=True, drop_mask=drop)
+            res = kr_pipeline_sharded(up, rescale=True, upper_input=True, drop_mask=drop, skip_diagonal=args.skipDiagonal,
+                                      want_matrix=want_matrix)
             if rank == 0:
                 print("normalisation factor is {}".format(res['factor']))
-                raw = up
-                if drop is not None:                  # the .cool keeps the raw counts of the selected chromosomes
-                    keep = np.flatnonzero(drop == 0)
-                    raw = sparse.csr_matrix(up[keep, :][:, keep])
-                    raw.sort_indices()
-                ma.install_file_layout(raw, ma.nan_bins, np.asarray(res['x']).reshape(-1, 1))
+                if want_matrix:
+                    out_upper = _drop_explicit_zeros(res['upper'])
+                else:
+                    out_upper = up
+                    if drop is not None:              # the .cool keeps the raw counts of the selected chromosomes
+                        keep = np.flatnonzero(drop == 0)
+                        out_upper = sparse.csr_matrix(up[keep, :][:, keep])
+                        out_upper.sort_indices()
+                ma.install_file_layout(out_upper, ma.nan_bins, np.asarray(res['x']).reshape(-1, 1))
             return
-        res = kr_pipeline_sharded(ma.matrix.astype(np.float64), rescale=True)
-        print("normalisation factor is {}".format(res['factor']))
-        ma.setCorrectionFactors(np.asarray(res['x']).reshape(-1, 1))
+        res = kr_pipeline_sharded(_scrubbed(ma.matrix, args.skipDiagonal), rescale=True, want_matrix=want_matrix)
+        if rank == 0:
+            print("normalisation factor is {}".format(res['factor']))
+            if want_matrix:
+                full = res['upper'] + sparse.triu(res['upper'], 1).T
+                ma.setMatrixValues(sparse.csr_matrix(full))
+            ma.setCorrectionFactors(np.asarray(res['x']).reshape(-1, 1))
         return
-    matrix = ma.matrix.astype(np.float64)
-    if world > 1 and not args.perchr and rank != 0:
-        return      # genome-wide KR to .h5 runs on rank 0's GPU
+    matrix = _scrubbed(ma.matrix, args.skipDiagonal)
     if args.perchr:
         # independent chromosomes: dealt to the GPUs by longest-processing-time on stored entries, no communication
         # during the correction; rank 0 collects the factors (and the corrected blocks for .h5)

@@ -118,7 +118,7 @@ def main(args=None):
     else:
         hic_ma = hm.hiCMatrix(pMatrixFile=args.matrix)
         if args.chromosomes:
-            hic_ma.reorderChromosomes([str(c) for c in args.chromosomes])
+            hic_ma.keepOnlyTheseChr([str(c) for c in args.chromosomes])     # file order kept (hicTransform.py:156)
     result = obs_exp_transform(hic_ma.matrix, args.method, hic_ma.chromosome_offsets(), per_chromosome=args.perChromosome,
                                ligation_factor=args.ligation_factor, device=args.device)
     hic_ma.matrix = result

@@ -222,6 +222,16 @@ class hiCMatrix(object):
         self.nan_bins = np.array(sorted(pos[b] for b in self.nan_bins if b in pos), dtype=np.int64)
         self._index_intervals()
 
+    def keepOnlyTheseChr(self, chromosome_list):
+        """hicmatrix keepOnlyTheseChr: drop every chromosome that is not listed; unlike reorderChromosomes the FILE order
+        of the chromosomes is kept (what hicTransform --chromosomes uses, hicTransform.py:156)"""
+        wanted = set(_to_str(c) for c in chromosome_list)
+        for c in wanted:
+            if c not in self.chrBinBoundaries:
+                raise ValueError("Chromosome name '%s' not in matrix." % c)
+        self.reorderChromosomes([c for c in self.chrBinBoundaries if c in wanted])
+        return self.matrix
+
     def maskBins(self, bin_ids=None):
         """delete rows+columns; a second call first restores, then removes the union"""
         if bin_ids is None or len(bin_ids) == 0:

@@ -140,7 +140,7 @@ def ice_pipeline(matrix, filter_threshold, max_iter=500, tolerance=1e-5, chr_off
 
 
 def kr_pipeline(matrix, rescale=True, want_matrix=True, device=0, upper_input=False, rescale_vector=None,
-                drop_mask=None):
+                drop_mask=None, skip_diagonal=False):
     """KR branch of the driver (hicCorrectMatrix.py:742-757): no masking, no filter.
     Returns dict(x, factor, outer, matvecs, residual, upper).
 
@@ -154,6 +154,9 @@ def kr_pipeline(matrix, rescale=True, want_matrix=True, device=0, upper_input=Fa
     with (DeviceCSR.from_upper(m, device=device) if upper_input else DeviceCSR.from_scipy(m, device=device)) as dev:
         if drop_mask is not None:              # chromosome subset (--chromosomes): delete the other bins first
             dev.compact(np.ascontiguousarray(drop_mask, dtype=np.uint8))
+        dev.scrub()                            # NaN / Inf -> 0 happens before the method switch (:624-625)
+        if skip_diagonal:
+            dev.diag_zero()                    # so does --skipDiagonal (:648-649)
         dev.pack_values()
         x, outer, matvecs, residual = dev.kr()
         factor = 1.0
@@ -256,8 +259,20 @@ def _attach_exchange(dev, rank, world):
     return keep
 
 
+def _assemble_rows(dev, local_values, dist):
+    """row-block vector -> the whole n-vector on every rank (x + 0 over the ranks: exact)"""
+    import torch
+    n_rows, n_cols, row0, _nnz = dev.dims()
+    full = torch.zeros(n_cols, dtype=torch.float64, device="cuda")
+    if n_rows:
+        full[row0:row0 + n_rows] = torch.from_numpy(np.ascontiguousarray(local_values, dtype=np.float64)).cuda()
+    dist.all_reduce(full)
+    return full.cpu().numpy()
+
+
 def ice_pipeline_sharded(matrix, filter_threshold, max_iter=500, tolerance=1e-5, chr_offsets=None, perchr=False,
-                         skip_diagonal=False, want_matrix=True, file_layout=False, upper_input=False, drop_mask=None):
+                         skip_diagonal=False, want_matrix=True, file_layout=False, upper_input=False, drop_mask=None,
+                         extra_mask_fn=None, trans_cutoff=None, clip_trans=False, inflation_cutoff=None):
     """ice_pipeline on row blocks across the initialised torch.distributed group (NCCL).  The symmetry test is the
     exact-symmetry digest screen summed over the blocks (one tiny allreduce); a matrix that is not exactly symmetric is
     rejected (the exact ratio would need the transposed entries of other blocks).
@@ -272,7 +287,8 @@ def ice_pipeline_sharded(matrix, filter_threshold, max_iter=500, tolerance=1e-5,
     if dist is None or world == 1:
         return ice_pipeline(matrix, filter_threshold, max_iter, tolerance, chr_offsets, perchr, skip_diagonal,
                             device=torch.cuda.current_device(), want_matrix=want_matrix, file_layout=file_layout,
-                            upper_input=upper_input, drop_mask=drop_mask)
+                            upper_input=upper_input, drop_mask=drop_mask, extra_mask_fn=extra_mask_fn,
+                            trans_cutoff=trans_cutoff, clip_trans=clip_trans, inflation_cutoff=inflation_cutoff)
     device = torch.cuda.current_device()
     m = canonical_csr(matrix, dtype=None)      # values keep the file type: widened to fp64 on the device
     lo, hi = filter_threshold
@@ -297,22 +313,58 @@ def ice_pipeline_sharded(matrix, filter_threshold, max_iter=500, tolerance=1e-5,
             dev.diag_zero()
         mask, _z, _med, _mad = dev.mad_filter(lo, hi)         # one collective inside, mask replicated
         outliers_rel = np.flatnonzero(mask)
-        dev.compact(mask)
-        kept = keep1[~mask.astype(bool)]
+        remove = mask.astype(bool)
+        if extra_mask_fn is not None:                         # --sequencedCountCutoff: O(n) host work, replicated
+            extra = np.zeros(len(keep1), dtype=bool)
+            surv = np.flatnonzero(~remove)
+            extra[surv] = extra_mask_fn(keep1[surv])
+            remove |= extra
+        dev.compact(remove.astype(np.uint8))
+        kept = keep1[~remove]
+        extra_out = {}
+        pre_row_sum = None
+        offsets = None if chr_offsets is None else np.asarray(chr_offsets, dtype=np.int64)
+        if trans_cutoff and 0 < trans_cutoff < 100:
+            if offsets is None:
+                raise ValueError("trans_cutoff needs chromosome offsets")
+            offsets_now = np.searchsorted(kept, offsets, side="left")
+            # 8 histogram passes of the radix select, each summed over the row blocks by one small allreduce
+            max_inter = dev.trans_percentile(offsets_now, 100 - float(trans_cutoff) / 100)
+            extra_out["max_inter"] = max_inter
+            if clip_trans and max_inter is not None:
+                clipped = torch.tensor([float(dev.trans_clip(offsets_now, max_inter))], dtype=torch.float64, device="cuda")
+                dist.all_reduce(clipped)
+                extra_out["clipped"] = int(clipped.item())
+            pre_row_sum = _assemble_rows(dev, dev.row_stats()[0], dist)
+        if inflation_cutoff and inflation_cutoff > 0 and pre_row_sum is None:
+            raise ValueError("inflation_cutoff needs trans_cutoff (pre_row_sum is only defined then, "
+                             "hicCorrectMatrix.py:699, 771)")
         if perchr:
             dev.keep_cis()
         if dev.symmetry_ratio() > 1e-10:
             raise ValueError("Please provide symmetric matrix!")
         dev.pack_values()
         bias, iters, deviation = dev.ice(max_iter, tolerance)  # one exchange per iteration
+        out_ids = kept
+        if inflation_cutoff and inflation_cutoff > 0:
+            if want_matrix and not file_layout:
+                raise ValueError("inflation_cutoff returns the matrix in file layout only (file_layout=True)")
+            after = _assemble_rows(dev, dev.ice_scaled_row_sums(), dist)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                inflated = after / pre_row_sum >= inflation_cutoff
+            extra_out["inflated_rel"] = np.flatnonzero(inflated)
+            extra_out["kept_ice"] = kept
+            out_ids = np.where(inflated, -1, kept)
+            kept = kept[~inflated]
+            bias = bias[~inflated]
         values = None
         if want_matrix and file_layout:
-            upper_local = dev.ice_scaled_upper(kept, n)
+            upper_local = dev.ice_scaled_upper(out_ids, n)
         elif want_matrix:
             values = dev.ice_scaled_values()
         del keep_alive
     out = dict(zero_bins=zero_bins, outliers_rel=outliers_rel, kept=kept, bias=bias, iterations=iters,
-               deviation=deviation, n=n)
+               deviation=deviation, n=n, **extra_out)
     if want_matrix and file_layout:
         upper = _gather_upper_to_root(upper_local, dist, rank, world)
         if rank == 0:
@@ -336,24 +388,41 @@ def ice_pipeline_sharded(matrix, filter_threshold, max_iter=500, tolerance=1e-5,
     return out if rank == 0 else None
 
 
-def kr_pipeline_sharded(matrix, rescale=True, upper_input=False, drop_mask=None):
-    """kr_pipeline on row blocks: x is replicated on every rank; rank 0 also gets the rescale factor."""
+def kr_pipeline_sharded(matrix, rescale=True, upper_input=False, drop_mask=None, skip_diagonal=False, want_matrix=False):
+    """kr_pipeline on row blocks: x is replicated on every rank; rank 0 also gets the rescale factor.
+    ``want_matrix``: every rank emits its rows of the balanced matrix in file layout (hb_kr_scaled_upper works on a row
+    block) and rank 0 concatenates them -> ``upper`` (what a genome-wide KR run to .h5 stores)."""
     import torch
 
     from .dist import attach_comm, nnz_balanced_partition
     dist, rank, world = _dist_env()
     if dist is None or world == 1:
-        return kr_pipeline(matrix, rescale=rescale, want_matrix=False, device=torch.cuda.current_device(),
-                           upper_input=upper_input, drop_mask=drop_mask)
+        return kr_pipeline(matrix, rescale=rescale, want_matrix=want_matrix, device=torch.cuda.current_device(),
+                           upper_input=upper_input, drop_mask=drop_mask, skip_diagonal=skip_diagonal)
     device = torch.cuda.current_device()
     m = canonical_csr(matrix, dtype=None)      # values keep the file type: widened to fp64 on the device
     dev, _block, _n = _open_row_block(m, upper_input, drop_mask, rank, world, device)
     with dev:
         keep_alive = _attach_exchange(dev, rank, world)
+        dev.scrub()
+        if skip_diagonal:
+            dev.diag_zero()
         dev.pack_values()
         x, outer, matvecs, residual = dev.kr()
         factor = 1.0
         if rescale:
             x, factor = dev.kr_rescale(x, KR_DIAG_EPS)
+        upper = None
+        if want_matrix:
+            n_rows, n_cols, row0, _nnz = dev.dims()
+            block = dev.kr_scaled_upper(x, KR_DIAG_EPS)           # the block's rows, global column ids
+            indptr = np.zeros(n_cols + 1, dtype=np.int64)
+            indptr[row0 + 1:row0 + n_rows + 1] = block.indptr[1:]
+            indptr[row0 + n_rows + 1:] = block.indptr[-1]
+            upper = _gather_upper_to_root(sparse.csr_matrix((block.data, block.indices, indptr), shape=(n_cols, n_cols)),
+                                          dist, rank, world)
         del keep_alive
-    return dict(x=x, factor=factor, outer=outer, matvecs=matvecs, residual=residual)
+    out = dict(x=x, factor=factor, outer=outer, matvecs=matvecs, residual=residual)
+    if want_matrix and rank == 0:
+        out["upper"] = upper
+    return out

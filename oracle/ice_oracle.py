@@ -126,6 +126,15 @@ def diagnostic_histograms(csr, chr_ranges=None, x_max=None):
     out): per histogram (one for the whole matrix, or one per chromosome block with ``chr_ranges``) the coverage values
     with a modified z-score below 5, their 100-bin histogram (``ax.hist(values, 100)`` = ``np.histogram``), and the
     modified z-score of the first local minimum of the histogram -- the "mad threshold" the tool logs and marks."""
+    # main() masks the zero-value bins for the plot as well (hicCorrectMatrix.py:616-619), on row sums taken before
+    # the NaN / Inf scrub; the chromosome ranges shrink accordingly
+    rs = np.asarray(csr.sum(axis=1)).flatten()
+    keep = rs != 0
+    if not keep.all():
+        before = np.concatenate([[0], np.cumsum(keep)])
+        csr = select_bins(csr, np.flatnonzero(keep))
+        if chr_ranges is not None:
+            chr_ranges = [(int(before[a]), int(before[b])) for a, b in chr_ranges]
     m = scrub(csr)
     out = []
     for a, b in (chr_ranges if chr_ranges is not None else [(0, m.shape[0])]):

@@ -146,6 +146,35 @@ def main():
               np.array_equal(np.nan_to_num(np.asarray(a.correction_factors)), np.nan_to_num(np.asarray(b.correction_factors))) and
               (a.matrix != b.matrix).nnz == 0)
     dist.barrier()
+
+    def same_file(a_path, b_path):
+        a, b = hiCMatrix(a_path), hiCMatrix(b_path)
+        fa, fb = np.asarray(a.correction_factors).ravel(), np.asarray(b.correction_factors).ravel()
+        return (np.array_equal(np.isnan(fa), np.isnan(fb)) and np.array_equal(np.nan_to_num(fa), np.nan_to_num(fb)) and
+                a.matrix.shape == b.matrix.shape and (a.matrix != b.matrix).nnz == 0 and
+                np.array_equal(np.asarray(a.nan_bins), np.asarray(b.nan_bins)))
+
+    def both_ways(name, argv_tail, suffix):
+        """the same command under torchrun (all ranks) and on one GPU (rank 0): the files must be identical"""
+        out_n = os.path.join(tmp, "mg_%s_n%s" % (name, suffix))
+        cli(["correct", "-m", src, "-o", out_n] + argv_tail)
+        if rank == 0:
+            os.environ["WORLD_SIZE"] = "1"
+            out_1 = os.path.join(tmp, "mg_%s_1%s" % (name, suffix))
+            cli(["correct", "-m", src, "-o", out_1] + argv_tail + ["--device", str(local)])
+            os.environ["WORLD_SIZE"] = str(world)
+            check("CLI %s under torchrun: file equals the single-GPU run" % name, same_file(out_n, out_1))
+        dist.barrier()
+
+    # genome-wide KR to .h5: every rank emits its rows of the balanced matrix (hb_kr_scaled_upper on a row block)
+    both_ways("KR_h5", ["--correctionMethod", "KR"], ".h5")
+    both_ways("KR_h5_subset", ["--correctionMethod", "KR", "--chromosomes", "2", "3", "7"], ".h5")
+    # the optional ICE steps on row blocks: trans percentile (8 summed histogram passes), clipping, inflation mask,
+    # coverage filter
+    both_ways("ICE_transcut_inflation", ["--correctionMethod", "ICE", "--filterThreshold", "-1.5", "5", "--transCutoff", "5",
+                                         "--clipTrans", "--inflationCutoff", "3", "--sequencedCountCutoff", "0.5"], ".h5")
+    both_ways("ICE_skipdiag_perchr", ["--correctionMethod", "ICE", "--filterThreshold", "-1.5", "5", "--perchr",
+                                      "--skipDiagonal"], ".h5")
     # --perchr KR: whole chromosomes dealt to the ranks (LPT), no communication; rank 0 assembles the file
     outk = os.path.join(tmp, "mg_kr_perchr.h5")
     cli(["correct", "-m", src, "-o", outk, "--correctionMethod", "KR", "--perchr"])

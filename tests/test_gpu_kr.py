@@ -73,3 +73,29 @@ def test_kr_gm12878_genome_wide(gm12878):
     # the reference's own test for this file: 3e9 < sum // 2 < 3688003604 (test_hicCorrectMatrix.py:72-91)
     full = got["upper"] + sparse.triu(got["upper"], 1).T
     assert 3e9 < full.sum() // 2 < 3688003604
+
+
+def test_kr_scrubs_nan_inf_and_honours_skip_diagonal(kr_partial):
+    """NaN / Inf -> 0 and --skipDiagonal are applied before the method switch in the reference
+    (hicCorrectMatrix.py:624-625, 648-649), so KR sees them too"""
+    from hicexplorer_b200.pipeline import kr_pipeline
+    m = full_from_pixels(kr_partial).astype(np.float64)
+    dirty = m.copy()
+    rows = np.repeat(np.arange(m.shape[0]), np.diff(m.indptr))
+    off = np.flatnonzero(m.indices > rows)[::37][:6]
+    for pos, bad in zip(off, [np.nan, np.inf, np.nan, -np.inf, np.nan, np.inf]):
+        i, j = int(rows[pos]), int(m.indices[pos])
+        dirty[i, j] = bad
+        dirty[j, i] = bad
+    clean = dirty.copy()
+    clean.data[~np.isfinite(clean.data)] = 0
+    got = kr_pipeline(dirty, rescale=True, want_matrix=False)
+    ref = kr_oracle.kr_pipeline(clean, rescale=True)
+    assert np.isfinite(got["x"]).all()
+    np.testing.assert_allclose(got["x"], ref["x_out"], rtol=1e-9)
+    nodiag = clean.copy()
+    nodiag.setdiag(0)
+    got2 = kr_pipeline(dirty, rescale=True, want_matrix=False, skip_diagonal=True)
+    ref2 = kr_oracle.kr_pipeline(nodiag, rescale=True)
+    np.testing.assert_allclose(got2["x"], ref2["x_out"], rtol=1e-9)
+    assert np.max(np.abs(got2["x"] / got["x"] - 1)) > 1e-3          # the flag did change the problem

@@ -192,3 +192,28 @@ def test_diagnostic_plot_svg_writer(tmp_path):
     other = str(tmp_path / "plot.png")
     _draw_svg(panels[:1], other)                         # not an .svg name: written next to it, with a warning
     assert (tmp_path / "plot.png.svg").exists()
+
+
+def test_keep_only_these_chr_keeps_the_file_order(tmp_path, gm12878):
+    """hicTransform --chromosomes goes through hicmatrix keepOnlyTheseChr (hicTransform.py:156): a selection in FILE
+    order, unlike reorderChromosomes which follows the order of the list"""
+    from hicexplorer_b200.hicmatrix_lite import hiCMatrix
+    from tests.helpers import full_from_pixels
+    ma = hiCMatrix()
+    ma.matrix = full_from_pixels(gm12878)
+    off = gm12878["chrom_offset"]
+    ma.cut_intervals = [(str(c + 1), int((i - off[c]) * 100), int((i - off[c] + 1) * 100), 1.0)
+                        for c in range(len(off) - 1) for i in range(off[c], off[c + 1])]
+    ma._index_intervals()
+    path = str(tmp_path / "m.cool")
+    ma.save(path)
+    a = hiCMatrix(path)
+    a.keepOnlyTheseChr(["7", "2", "3"])
+    assert a.getChrNames() == ["2", "3", "7"]
+    b = hiCMatrix(path)
+    b.reorderChromosomes(["7", "2", "3"])
+    assert b.getChrNames() == ["7", "2", "3"]
+    assert a.matrix.shape == b.matrix.shape and a.matrix.sum() == b.matrix.sum()
+    lo, hi = a.getChrBinRange("2")
+    want = full_from_pixels(gm12878)[off[1]:off[2], off[1]:off[2]]
+    assert (a.matrix[lo:hi, lo:hi] != want).nnz == 0
