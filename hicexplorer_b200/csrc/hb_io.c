@@ -287,3 +287,252 @@ HBIO_API int64_t hbio_decode_chunks(const uint8_t* file_base, int64_t n_chunks, 
         if (jobs[t].status != 0) status = jobs[t].status;
     return status;
 }
+
+/* ==================================================================================================================
+ * Encoders: what the reference's writers put on disk (docs/content/file-formats.rst:9-31, 64-76):
+ *   .h5    PyTables CArrays with the Blosc filter (id 32001): blosclz codec, level 5, byte shuffle
+ *   .cool  cooler datasets with shuffle (id 2) + deflate (id 1)
+ * The Blosc-1 container and the blosclz stream are produced in exactly the form blosclz_decode / hbio_blosc_decode
+ * above (and c-blosc) read: 16-byte header, block offsets, every full block split into `typesize` byte-plane streams
+ * (each: int32 compressed size + data; size == plane size means "stored"), 32 KB blocks like PyTables' files.
+ * ================================================================================================================== */
+#define HBIO_HASH_LOG 13
+#define HBIO_MAX_NEAR 8191            /* distances 1..8191 fit the two-byte form */
+#define HBIO_MAX_FAR (65535 + 8191)   /* far form: 16-bit offset on top of 8191 */
+
+static inline uint32_t hbio_hash3(const uint8_t* p) {
+    const uint32_t v = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
+    return (v * 2654435761u) >> (32 - HBIO_HASH_LOG);
+}
+
+/* blosclz (FastLZ-style) compressor.  Returns the compressed size, or 0 when the result would not be smaller than
+ * `maxout` (the caller then stores the stream verbatim). */
+static int64_t blosclz_encode(const uint8_t* ip, int64_t length, uint8_t* op, int64_t maxout) {
+    if (length < 16 || maxout < 66) return 0;
+    int32_t htab[1 << HBIO_HASH_LOG];
+    for (int i = 0; i < (1 << HBIO_HASH_LOG); ++i) htab[i] = -1;
+    uint8_t* const op_start = op;
+    uint8_t* const op_limit = op + maxout;
+    int64_t anchor = 0; /* start of the pending literals */
+    int64_t i = 0;
+    const int64_t last = length - 3;
+#define HBIO_FLUSH_LITERALS(upto)                                        \
+    do {                                                                 \
+        int64_t n_ = (upto)-anchor;                                      \
+        while (n_ > 0) {                                                 \
+            const int64_t run_ = n_ > 32 ? 32 : n_;                      \
+            if (op + 1 + run_ > op_limit) return 0;                      \
+            *op++ = (uint8_t)(run_ - 1);                                 \
+            memcpy(op, ip + anchor, (size_t)run_);                       \
+            op += run_;                                                  \
+            anchor += run_;                                              \
+            n_ -= run_;                                                  \
+        }                                                                \
+    } while (0)
+    /* the stream has to open with a literal (the decoder masks the first control byte to 5 bits) */
+    i = 1;
+    while (i < last) {
+        const uint32_t h = hbio_hash3(ip + i);
+        const int32_t cand = htab[h];
+        htab[h] = (int32_t)i;
+        int64_t dist = cand >= 0 ? i - cand : 0;
+        if (cand >= 0 && dist <= HBIO_MAX_FAR && ip[cand] == ip[i] && ip[cand + 1] == ip[i + 1] && ip[cand + 2] == ip[i + 2]) {
+            int64_t len = 3;
+            while (i + len < length && ip[cand + len] == ip[i + len]) ++len;
+            HBIO_FLUSH_LITERALS(i);
+            /* copy length = field + 3 ; field <= 5 sits in the control byte, larger ones continue in 255-steps */
+            int64_t field = len - 3;
+            const int64_t ofs = dist - 1;
+            const int far = ofs >= HBIO_MAX_NEAR;   /* 8191 itself would read as the far marker */
+            const uint32_t hi = far ? 31u : (uint32_t)(ofs >> 8);
+            if (op + 8 + field / 255 > op_limit) return 0;
+            if (field < 6) {
+                *op++ = (uint8_t)(((field + 1) << 5) | hi);
+            } else {
+                *op++ = (uint8_t)((7u << 5) | hi);
+                field -= 6;
+                while (field >= 255) {
+                    *op++ = 255;
+                    field -= 255;
+                }
+                *op++ = (uint8_t)field;
+            }
+            if (far) {
+                const int64_t f = ofs - HBIO_MAX_NEAR;
+                *op++ = 255;
+                *op++ = (uint8_t)(f >> 8);
+                *op++ = (uint8_t)(f & 255);
+            } else {
+                *op++ = (uint8_t)(ofs & 255);
+            }
+            /* index a few positions inside the match so that later data can refer to them */
+            const int64_t end = i + len;
+            for (int64_t k = i + 1; k < end && k < last; k += (len > 64 ? 16 : 1)) htab[hbio_hash3(ip + k)] = (int32_t)k;
+            i = end;
+            anchor = i;
+        } else {
+            ++i;
+        }
+    }
+    HBIO_FLUSH_LITERALS(length);
+#undef HBIO_FLUSH_LITERALS
+    const int64_t out = op - op_start;
+    return out < maxout ? out : 0;
+}
+
+static void shuffle_bytes(const uint8_t* src, uint8_t* dst, int64_t nbytes, int typesize) {
+    const int64_t nelem = nbytes / typesize;
+    for (int t = 0; t < typesize; ++t) {
+        uint8_t* plane = dst + (int64_t)t * nelem;
+        for (int64_t i = 0; i < nelem; ++i) plane[i] = src[i * typesize + t];
+    }
+    memcpy(dst + nelem * typesize, src + nelem * typesize, (size_t)(nbytes - nelem * typesize));
+}
+
+HBIO_API int64_t hbio_blosc_bound(int64_t nbytes, int typesize) {
+    const int64_t blocksize = 32768;
+    const int64_t nblocks = (nbytes + blocksize - 1) / blocksize;
+    return 16 + 4 * nblocks + nbytes + 4 * nblocks * (typesize > 0 ? typesize : 1) + 64;
+}
+
+/* One Blosc-1 chunk (blosclz, byte shuffle).  `scratch` holds one block.  Returns the chunk size. */
+HBIO_API int64_t hbio_blosc_encode(const uint8_t* src, int64_t nbytes, int typesize, uint8_t* out, uint8_t* scratch) {
+    int64_t blocksize = 32768;
+    if (blocksize > nbytes) blocksize = nbytes;
+    if (typesize > 1 && blocksize >= typesize) blocksize -= blocksize % typesize;
+    const int doshuffle = typesize > 1;
+    const int rule = typesize <= 16 && blocksize / (typesize > 0 ? typesize : 1) >= 128;
+    const int64_t nblocks = nbytes > 0 ? (nbytes + blocksize - 1) / blocksize : 0;
+    uint8_t flags = (uint8_t)((doshuffle ? 0x1 : 0x0) | (rule ? 0x0 : 0x10)); /* codec 0 = blosclz in bits 5-7 */
+    int64_t pos = 16 + 4 * nblocks;
+    int ok = nbytes >= 128;   /* tiny buffers are stored */
+    for (int64_t b = 0; ok && b < nblocks; ++b) {
+        int64_t bsize = blocksize;
+        if ((b + 1) * blocksize > nbytes) bsize = nbytes - b * blocksize;
+        const int leftover = bsize != blocksize;
+        const uint8_t* blk = src + b * blocksize;
+        if (doshuffle) {
+            shuffle_bytes(blk, scratch, bsize, typesize);
+            blk = scratch;
+        }
+        const int nsplits = (rule && !leftover) ? typesize : 1;
+        const int64_t neblock = bsize / nsplits;
+        const int32_t bstart = (int32_t)pos;
+        memcpy(out + 16 + 4 * b, &bstart, 4);
+        for (int s = 0; s < nsplits; ++s) {
+            const uint8_t* sp = blk + (int64_t)s * neblock;
+            int64_t c = blosclz_encode(sp, neblock, out + pos + 4, neblock - 1);
+            if (c <= 0) {   /* not compressible: stored (size == plane size tells the decoder) */
+                memcpy(out + pos + 4, sp, (size_t)neblock);
+                c = neblock;
+            }
+            const int32_t c32 = (int32_t)c;
+            memcpy(out + pos, &c32, 4);
+            pos += 4 + c;
+        }
+        if (pos >= nbytes + 16) ok = 0;   /* no gain: fall back to a plain copy */
+    }
+    if (!ok) {
+        flags = (uint8_t)(0x2 | (doshuffle ? 0x1 : 0x0));   /* memcpyed */
+        memcpy(out + 16, src, (size_t)nbytes);
+        pos = 16 + nbytes;
+    }
+    out[0] = 2;   /* BLOSC_VERSION_FORMAT */
+    out[1] = 1;   /* blosclz format version */
+    out[2] = flags;
+    out[3] = (uint8_t)typesize;
+    const uint32_t nb = (uint32_t)nbytes, bs = (uint32_t)blocksize, cb = (uint32_t)pos;
+    memcpy(out + 4, &nb, 4);
+    memcpy(out + 8, &bs, 4);
+    memcpy(out + 12, &cb, 4);
+    return pos;
+}
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Batch encode of consecutive chunks of one 1-D dataset on a pool of threads.
+ *   src / nbytes   the dataset's bytes; chunk c covers [c * chunk_bytes, (c+1) * chunk_bytes) and is zero-padded to a
+ *                  full chunk at the end of the dataset (HDF5 chunks always have the full shape)
+ *   mode           1 = Blosc(blosclz + shuffle)   2 = shuffle + deflate   3 = deflate
+ *   slots          n_chunks * slot_bytes scratch (slot_bytes >= hbio_encode_bound): every chunk is encoded into its slot
+ *   dst            receives the encoded chunks back to back; offsets[c] / sizes[c] locate chunk c inside dst
+ * Returns the total number of bytes in dst, or -1.
+ * ------------------------------------------------------------------------------------------------------------------ */
+HBIO_API int64_t hbio_encode_bound(int64_t chunk_bytes, int typesize, int mode) {
+    if (mode == 1) return hbio_blosc_bound(chunk_bytes, typesize);
+    return (int64_t)compressBound((uLong)chunk_bytes) + 64;
+}
+
+typedef struct {
+    const uint8_t* src;
+    int64_t nbytes, chunk_bytes, n_chunks, slot_bytes;
+    int typesize, mode, level, nthreads, tid;
+    uint8_t* slots;
+    int64_t* sizes;
+    int64_t status;
+} hbio_enc_job;
+
+static void* hbio_enc_worker(void* arg) {
+    hbio_enc_job* j = (hbio_enc_job*)arg;
+    uint8_t* padded = (uint8_t*)malloc((size_t)j->chunk_bytes + 64);
+    uint8_t* scratch = (uint8_t*)malloc((size_t)j->chunk_bytes + 64);
+    j->status = (padded && scratch) ? 0 : -1;
+    for (int64_t c = j->tid; c < j->n_chunks && j->status == 0; c += j->nthreads) {
+        const int64_t off = c * j->chunk_bytes;
+        const uint8_t* in = j->src + off;
+        if (off + j->chunk_bytes > j->nbytes) {
+            const int64_t have = j->nbytes - off;
+            memcpy(padded, in, (size_t)have);
+            memset(padded + have, 0, (size_t)(j->chunk_bytes - have));
+            in = padded;
+        }
+        uint8_t* out = j->slots + c * j->slot_bytes;
+        if (j->mode == 1) {
+            j->sizes[c] = hbio_blosc_encode(in, j->chunk_bytes, j->typesize, out, scratch);
+        } else {
+            const uint8_t* zin = in;
+            if (j->mode == 2 && j->typesize > 1) {
+                shuffle_bytes(in, scratch, j->chunk_bytes, j->typesize);
+                zin = scratch;
+            }
+            uLongf dlen = (uLongf)j->slot_bytes;
+            if (compress2(out, &dlen, zin, (uLong)j->chunk_bytes, j->level) != Z_OK) j->status = -1;
+            j->sizes[c] = (int64_t)dlen;
+        }
+    }
+    free(padded);
+    free(scratch);
+    return NULL;
+}
+
+HBIO_API int64_t hbio_encode_chunks(const uint8_t* src, int64_t nbytes, int64_t chunk_bytes, int typesize, int mode, int level,
+                                    int nthreads, uint8_t* slots, int64_t slot_bytes, uint8_t* dst, int64_t* offsets,
+                                    int64_t* sizes) {
+    if (chunk_bytes <= 0 || nbytes < 0 || mode < 1 || mode > 3) return -1;
+    const int64_t n_chunks = (nbytes + chunk_bytes - 1) / chunk_bytes;
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 64) nthreads = 64;
+    if ((int64_t)nthreads > n_chunks) nthreads = n_chunks > 0 ? (int)n_chunks : 1;
+    hbio_enc_job jobs[64];
+    pthread_t th[64];
+    int started[64] = {0};
+    for (int t = 0; t < nthreads; ++t) {
+        hbio_enc_job j = {src, nbytes, chunk_bytes, n_chunks, slot_bytes, typesize, mode, level, nthreads, t, slots, sizes, 0};
+        jobs[t] = j;
+    }
+    for (int t = 1; t < nthreads; ++t) started[t] = pthread_create(&th[t], NULL, hbio_enc_worker, &jobs[t]) == 0;
+    hbio_enc_worker(&jobs[0]);
+    int64_t status = jobs[0].status;
+    for (int t = 1; t < nthreads; ++t) {
+        if (started[t]) pthread_join(th[t], NULL);
+        else hbio_enc_worker(&jobs[t]);   /* could not start the thread: do its share here */
+        if (jobs[t].status != 0) status = jobs[t].status;
+    }
+    if (status != 0) return -1;
+    int64_t pos = 0;
+    for (int64_t c = 0; c < n_chunks; ++c) {
+        offsets[c] = pos;
+        memcpy(dst + pos, slots + c * slot_bytes, (size_t)sizes[c]);
+        pos += sizes[c];
+    }
+    return pos;
+}

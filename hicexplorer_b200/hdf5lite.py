@@ -129,6 +129,13 @@ def _native_lib():
                 lib.hbio_decode_chunks.restype = ctypes.c_int64
                 lib.hbio_decode_chunks.argtypes = [ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_void_p] * 5 + [
                     ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+            if hasattr(lib, "hbio_encode_chunks"):
+                lib.hbio_encode_bound.restype = ctypes.c_int64
+                lib.hbio_encode_bound.argtypes = [ctypes.c_int64, ctypes.c_int, ctypes.c_int]
+                lib.hbio_encode_chunks.restype = ctypes.c_int64
+                lib.hbio_encode_chunks.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                                   ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                                   ctypes.c_void_p, ctypes.c_void_p]
             _native = lib
     return _native or None
 
@@ -184,6 +191,121 @@ def _blosc_decompress(chunk):
             blk = _unshuffle(blk, typesize)
         out += blk
     return bytes(out[:nbytes])
+
+
+# filter pipelines of the reference's writers: PyTables CArrays (Blosc / blosclz, level 5, byte shuffle inside Blosc) and
+# cooler datasets (HDF5 shuffle + deflate); name -> (mode of hbio_encode_chunks, [(filter id, name, client data)])
+def _pipeline(kind, itemsize, chunk_bytes):
+    if kind == "blosc":
+        return 1, [(32001, b"blosc", (2, 2, itemsize, chunk_bytes, 5, 1))]
+    if kind == "gzip-shuffle":
+        if itemsize > 1:
+            return 2, [(2, b"shuffle", (itemsize,)), (1, b"deflate", (_GZIP_LEVEL,))]
+        return 3, [(1, b"deflate", (_GZIP_LEVEL,))]
+    if kind == "gzip":
+        return 3, [(1, b"deflate", (_GZIP_LEVEL,))]
+    raise ValueError("unknown filter pipeline %r" % (kind,))
+
+
+_GZIP_LEVEL = 4   # what this writer asks zlib for (cooler's default is 6; readers do not care)
+
+
+def _encode_chunks(raw, chunk_bytes, itemsize, mode):
+    """Encode consecutive chunks of ``raw`` (uint8 view of the dataset; the last chunk is zero-padded to full size).
+    Returns (buffer with the encoded chunks back to back, offsets, sizes).  libhbio.so does it on all host cores;
+    without it the chunks are written in a form every reader accepts but that does not compress (Blosc "memcpyed"
+    chunks) or through Python's zlib."""
+    import os
+    nbytes = int(raw.nbytes)
+    n = (nbytes + chunk_bytes - 1) // chunk_bytes
+    lib = _native_lib()
+    if lib is not None and hasattr(lib, "hbio_encode_chunks"):
+        slot = int(lib.hbio_encode_bound(chunk_bytes, itemsize, mode))
+        slots = np.empty(n * slot, dtype=np.uint8)
+        dst = np.empty(n * slot, dtype=np.uint8)
+        offsets = np.zeros(n, dtype=np.int64)
+        sizes = np.zeros(n, dtype=np.int64)
+        threads = int(os.environ.get("HDF5LITE_THREADS", "0")) or min(32, os.cpu_count() or 1)
+        total = lib.hbio_encode_chunks(raw.ctypes.data, nbytes, chunk_bytes, itemsize, mode, _GZIP_LEVEL, threads,
+                                       slots.ctypes.data, slot, dst.ctypes.data, offsets.ctypes.data, sizes.ctypes.data)
+        if total < 0:
+            raise RuntimeError("chunk encoder failed")
+        return dst[:total], offsets, sizes
+    parts, offsets, sizes, pos = [], [], [], 0
+    for c in range(n):
+        blk = bytes(raw[c * chunk_bytes:(c + 1) * chunk_bytes])
+        blk += b"\x00" * (chunk_bytes - len(blk))
+        if mode == 1:      # Blosc container, "memcpyed" flag: header + the bytes as they are
+            enc = struct.pack("<BBBBIII", 2, 1, 0x2 | (0x1 if itemsize > 1 else 0), itemsize, chunk_bytes, chunk_bytes,
+                              chunk_bytes + 16) + blk
+        else:
+            if mode == 2 and itemsize > 1:
+                blk = np.frombuffer(blk, dtype=np.uint8).reshape(-1, itemsize).T.tobytes()
+            enc = zlib.compress(blk, _GZIP_LEVEL)
+        parts.append(enc)
+        offsets.append(pos)
+        sizes.append(len(enc))
+        pos += len(enc)
+    return np.frombuffer(b"".join(parts), dtype=np.uint8), np.asarray(offsets, dtype=np.int64), np.asarray(sizes, dtype=np.int64)
+
+
+def _filter_message(filters):
+    """filter pipeline message, version 1 (what libhdf5 1.8 / PyTables / h5py write)"""
+    body = struct.pack("<BB6x", 1, len(filters))
+    for fid, name, cd in filters:
+        nm = name + b"\x00"
+        nm += b"\x00" * (_pad8(len(nm)) - len(nm))
+        body += struct.pack("<HHHH", fid, len(nm), 1, len(cd)) + nm + struct.pack("<%dI" % len(cd), *cd)
+        if len(cd) % 2:
+            body += b"\x00" * 4
+    return body
+
+
+_CHUNK_BTREE_K = 32   # "indexed storage internal node K": superblock v0 does not store it, the library default applies
+
+
+def _chunk_btree(alloc_at, first_addr, chunk_addrs, chunk_sizes, chunk_len, itemsize, n_chunks, rank=1):
+    """version-1 B-tree of type 1 over the chunks of a 1-D dataset, as node blobs placed from ``first_addr`` on.
+    Every node has the library's fixed size for K = 32; leaves hold up to 64 chunks; siblings are linked.
+    Returns (root address, list of (address, bytes))."""
+    K = _CHUNK_BTREE_K
+    key_size = 8 + 8 * (rank + 1)
+    node_size = 24 + (2 * K + 1) * key_size + 2 * K * 8
+
+    def key(nbytes, offset, last_dim):
+        # offsets of the chunk in elements per dimension (trailing dimensions of length 1 stay 0) + the element-size slot
+        return struct.pack("<IIQ", nbytes, 0, offset) + b"\x00" * (8 * (rank - 1)) + struct.pack("<Q", last_dim)
+
+    # level 0: (first key fields, child address) per chunk
+    entries = [((int(chunk_sizes[c]), c * chunk_len), int(chunk_addrs[c])) for c in range(n_chunks)]
+    end_key = key(0, n_chunks * chunk_len, itemsize)     # PyTables' files close the tree like this
+    blobs = []
+    addr = first_addr
+    level = 0
+    while True:
+        groups = [entries[i:i + 2 * K] for i in range(0, len(entries), 2 * K)]
+        addrs = [addr + i * node_size for i in range(len(groups))]
+        nxt = []
+        for gi, grp in enumerate(groups):
+            left = addrs[gi - 1] if gi > 0 else _UNDEF
+            right = addrs[gi + 1] if gi + 1 < len(groups) else _UNDEF
+            blob = bytearray(b"TREE" + struct.pack("<BBHQQ", 1, level, len(grp), left, right))
+            for (nbytes, off), child in grp:
+                blob += key(nbytes, off, 0) + struct.pack("<Q", child)
+            # closing key of the node: the first key of the next node, or the end of the dataset
+            if gi + 1 < len(groups):
+                (nb, off), _child = groups[gi + 1][0]
+                blob += key(nb, off, 0)
+            else:
+                blob += end_key
+            blob += b"\x00" * (node_size - len(blob))
+            blobs.append((addrs[gi], bytes(blob)))
+            nxt.append((grp[0][0], addrs[gi]))
+        addr += len(groups) * node_size
+        if len(groups) == 1:
+            return addrs[0], blobs, addr
+        entries = nxt
+        level += 1
 
 
 # --------------------------------------------------------------------------
@@ -643,6 +765,18 @@ def _attr_message(name, value):
     return _message(0x0C, body)
 
 
+def _default_chunk_len(n, itemsize):
+    """PyTables' CArrays of the reference's files use 64 KB chunks (8192 x 8 B, 16384 x 4 B, 5461 x 12 B); for arrays of
+    hundreds of megabytes the chunk grows to 1 MiB so that the chunk index stays small"""
+    target = (1 << 20) if n * itemsize >= (128 << 20) else (1 << 16)
+    return max(1, target // itemsize)
+
+
+def _compression_enabled():
+    import os
+    return os.environ.get("HDF5LITE_COMPRESS", "1") != "0"
+
+
 class Writer(object):
     """Build an HDF5 file in memory: ``w = Writer(); w.group('/matrix', attrs);
     w.dataset('/matrix/data', array, attrs); w.save(path)``."""
@@ -664,10 +798,14 @@ class Writer(object):
         node = self._node(path)
         node["attrs"].update(attrs or {})
 
-    def dataset(self, path, array, attrs=None, enum=None):
-        """``enum`` = ordered mapping name -> integer value: store as an HDF5 enum (cooler ``bins/chrom``)."""
+    def dataset(self, path, array, attrs=None, enum=None, filters=None, chunk_len=None):
+        """``enum`` = ordered mapping name -> integer value: store as an HDF5 enum (cooler ``bins/chrom``).
+        ``filters``: None = contiguous, uncompressed; "blosc" = chunked + Blosc (blosclz, shuffle) like PyTables CArrays;
+        "gzip-shuffle" / "gzip" = chunked + (shuffle +) deflate like cooler / h5py.  1-D datasets only."""
         node = self._node(path)
         node["enum"] = enum
+        node["filters"] = filters
+        node["chunk_len"] = chunk_len
         arr = np.ascontiguousarray(array)
         if arr.dtype.kind == "U":
             arr = arr.astype("S")
@@ -702,9 +840,53 @@ class Writer(object):
             hdr = struct.pack("<BxHII4x", 1, len(msgs), 1, len(body))
             return alloc(hdr + body)
 
+        def write_chunked(node):
+            """1-D chunked dataset: encoded chunks, then the chunk B-tree, then the object header"""
+            arr = node["data"]
+            itemsize = arr.dtype.itemsize
+            n = int(arr.shape[0])
+            chunk_len = node.get("chunk_len") or _default_chunk_len(n, itemsize)
+            chunk_bytes = chunk_len * itemsize
+            mode, filters = _pipeline(node["filters"], itemsize, chunk_bytes)
+            raw = arr.reshape(-1).view(np.uint8) if arr.dtype.kind != "S" else np.frombuffer(arr.tobytes(), dtype=np.uint8)
+            n_chunks = (n + chunk_len - 1) // chunk_len
+            addrs = np.zeros(n_chunks, dtype=np.int64)
+            sizes = np.zeros(n_chunks, dtype=np.int64)
+            # encode and write in batches of ~256 MB of input so that the scratch stays bounded
+            per_batch = max(1, (256 << 20) // chunk_bytes)
+            for c0 in range(0, n_chunks, per_batch):
+                c1 = min(n_chunks, c0 + per_batch)
+                part = raw[c0 * chunk_bytes:min(c1 * chunk_bytes, raw.nbytes)]
+                # the zero padding of the final chunk is defined relative to its own start: hand the encoder whole chunks
+                enc, offs, szs = _encode_chunks(part, chunk_bytes, itemsize, mode)
+                base = alloc(memoryview(enc))
+                addrs[c0:c1] = base + offs
+                sizes[c0:c1] = szs
+            pos[0] += (-pos[0]) % 8
+            rank = arr.ndim
+            root, blobs, end = _chunk_btree(None, pos[0], addrs, sizes, chunk_len, itemsize, n_chunks, rank)
+            for a, blob in blobs:
+                os.pwrite(fd, blob, a)
+            pos[0] = end
+            msgs = [
+                _message(0x01, _dataspace_message(arr.shape)),
+                _message(0x03, _enum_message(arr.dtype, node["enum"]) if node.get("enum") else
+                         _dtype_message(arr.dtype), flags=1),
+                _message(0x05, struct.pack("<BBBB4x", 2, 3, 0, 1)),       # fill value as PyTables writes it
+                _message(0x0B, _filter_message(filters)),
+                _message(0x08, struct.pack("<BBBQ", 3, 2, rank + 1, root) +
+                         struct.pack("<%dI" % (rank + 1), *([chunk_len] + [1] * (rank - 1) + [itemsize]))),
+            ]
+            for k, v in node["attrs"].items():
+                msgs.append(_attr_message(k, v))
+            return write_object_header(msgs)
+
         def write_dataset(node):
             arr = node["data"]
             nbytes = int(arr.nbytes)
+            if (node.get("filters") and arr.ndim >= 1 and all(d == 1 for d in arr.shape[1:]) and nbytes > 0
+                    and _compression_enabled()):
+                return write_chunked(node)
             # a byte view of the (contiguous) array: no intermediate copy of a multi-gigabyte payload
             raw = memoryview(arr.reshape(-1).view(np.uint8)) if nbytes and arr.dtype.kind != "S" else arr.tobytes()
             daddr = alloc(raw) if nbytes else _UNDEF

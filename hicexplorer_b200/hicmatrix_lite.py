@@ -345,27 +345,29 @@ class hiCMatrix(object):
 
     def _save_h5(self, path):
         up = self._upper_of_matrix()
-        carray = {"CLASS": "ARRAY", "VERSION": "2.4", "TITLE": "", "FLAVOR": "numpy"}
+        # chunked + Blosc like the reference's files (PyTables CArray); HDF5LITE_COMPRESS=0 writes plain contiguous Arrays
+        carray = ({"CLASS": "CARRAY", "VERSION": "1.1", "TITLE": ""} if hdf5lite._compression_enabled() else
+                  {"CLASS": "ARRAY", "VERSION": "2.4", "TITLE": "", "FLAVOR": "numpy"})
         group = {"CLASS": "GROUP", "VERSION": "1.0", "TITLE": ""}
         w = hdf5lite.Writer({"TITLE": "HiCExplorer matrix", "CLASS": "GROUP", "VERSION": "1.0",
                              "PYTABLES_FORMAT_VERSION": "2.1"})
         w.group("/matrix", group)
         w.group("/intervals", group)
         # (no copies when the arrays already have the file's types: these are the multi-gigabyte payloads)
-        w.dataset("/matrix/data", up.data.astype(self.value_dtype, copy=False), carray)
-        w.dataset("/matrix/indices", up.indices.astype(np.int32, copy=False), carray)
-        w.dataset("/matrix/indptr", up.indptr.astype(np.int32 if up.nnz < 2 ** 31 else np.int64, copy=False), carray)
-        w.dataset("/matrix/shape", np.asarray(up.shape, dtype=np.int64), carray)
+        w.dataset("/matrix/data", up.data.astype(self.value_dtype, copy=False), carray, filters="blosc")
+        w.dataset("/matrix/indices", up.indices.astype(np.int32, copy=False), carray, filters="blosc")
+        w.dataset("/matrix/indptr", up.indptr.astype(np.int32 if up.nnz < 2 ** 31 else np.int64, copy=False), carray, filters="blosc")
+        w.dataset("/matrix/shape", np.asarray(up.shape, dtype=np.int64), carray, filters="blosc")
         chrom, start, end, extra = zip(*self.cut_intervals) if self.cut_intervals else ((), (), (), ())
         width = max([len(c) for c in chrom] + [1])
-        w.dataset("/intervals/chr_list", np.asarray([c.encode() for c in chrom], dtype="S%d" % width), carray)
-        w.dataset("/intervals/start_list", np.asarray(start, dtype=np.int64), carray)
-        w.dataset("/intervals/end_list", np.asarray(end, dtype=np.int64), carray)
-        w.dataset("/intervals/extra_list", np.asarray(extra, dtype=np.float64), carray)
+        w.dataset("/intervals/chr_list", np.asarray([c.encode() for c in chrom], dtype="S%d" % width), carray, filters="blosc")
+        w.dataset("/intervals/start_list", np.asarray(start, dtype=np.int64), carray, filters="blosc")
+        w.dataset("/intervals/end_list", np.asarray(end, dtype=np.int64), carray, filters="blosc")
+        w.dataset("/intervals/extra_list", np.asarray(extra, dtype=np.float64), carray, filters="blosc")
         if len(self.nan_bins):
-            w.dataset("/nan_bins", np.asarray(self.nan_bins, dtype=np.int64), carray)
+            w.dataset("/nan_bins", np.asarray(self.nan_bins, dtype=np.int64), carray, filters="blosc")
         if self.correction_factors is not None:
-            w.dataset("/correction_factors", np.asarray(self.correction_factors, dtype=np.float64), carray)
+            w.dataset("/correction_factors", np.asarray(self.correction_factors, dtype=np.float64), carray, filters="blosc")
         w.save(path)
 
     def _save_cool(self, path):
@@ -384,16 +386,16 @@ class hiCMatrix(object):
                              "nbins": np.int64(n), "nchroms": np.int64(len(names)), "nnz": np.int64(up.nnz),
                              "sum": np.float64(up.data.sum()), "generated-by": "hicexplorer_b200"})
         width = max([len(c) for c in names] + [1])
-        w.dataset("/chroms/name", np.asarray([c.encode() for c in names], dtype="S%d" % width))
-        w.dataset("/chroms/length", np.asarray(lengths, dtype=np.int32))
-        w.dataset("/bins/chrom", chrom_id, enum=OrderedDict((c, i) for i, c in enumerate(names)))
-        w.dataset("/bins/start", np.asarray(start, dtype=np.int32))
-        w.dataset("/bins/end", np.asarray(end, dtype=np.int32))
+        w.dataset("/chroms/name", np.asarray([c.encode() for c in names], dtype="S%d" % width), filters="gzip-shuffle")
+        w.dataset("/chroms/length", np.asarray(lengths, dtype=np.int32), filters="gzip-shuffle")
+        w.dataset("/bins/chrom", chrom_id, enum=OrderedDict((c, i) for i, c in enumerate(names)), filters="gzip-shuffle")
+        w.dataset("/bins/start", np.asarray(start, dtype=np.int32), filters="gzip-shuffle")
+        w.dataset("/bins/end", np.asarray(end, dtype=np.int32), filters="gzip-shuffle")
         if self.correction_factors is not None:
-            w.dataset("/bins/weight", np.asarray(self.correction_factors, dtype=np.float64).ravel())
-        w.dataset("/indexes/bin1_offset", bin1_offset)
-        w.dataset("/indexes/chrom_offset", chrom_offset)
-        w.dataset("/pixels/bin1_id", up.row.astype(np.int32))
-        w.dataset("/pixels/bin2_id", up.col.astype(np.int32))
-        w.dataset("/pixels/count", up.data.astype(self.value_dtype, copy=False))
+            w.dataset("/bins/weight", np.asarray(self.correction_factors, dtype=np.float64).ravel(), filters="gzip-shuffle")
+        w.dataset("/indexes/bin1_offset", bin1_offset, filters="gzip-shuffle")
+        w.dataset("/indexes/chrom_offset", chrom_offset, filters="gzip-shuffle")
+        w.dataset("/pixels/bin1_id", up.row.astype(np.int32), filters="gzip-shuffle")
+        w.dataset("/pixels/bin2_id", up.col.astype(np.int32), filters="gzip-shuffle")
+        w.dataset("/pixels/count", up.data.astype(self.value_dtype, copy=False), filters="gzip-shuffle")
         w.save(path)

@@ -78,8 +78,10 @@ def test_native_and_python_decoders_agree_on_reference_fixtures(name):
         np.testing.assert_array_equal(py[k], c[k])
 
 
-def test_overwriting_the_file_that_is_still_mapped(tmp_path):
-    """big datasets are read as views of the mapped file; saving to the same path must not pull the pages away"""
+def test_overwriting_the_file_that_is_still_mapped(tmp_path, monkeypatch):
+    """big datasets of an uncompressed file are read as views of the mapped file; saving to the same path must not
+    pull the pages away"""
+    monkeypatch.setenv("HDF5LITE_COMPRESS", "0")
     from scipy import sparse
     from hicexplorer_b200.hicmatrix_lite import hiCMatrix
     ma = hiCMatrix()
@@ -95,3 +97,66 @@ def test_overwriting_the_file_that_is_still_mapped(tmp_path):
     again.save(path)                              # same path
     third = hiCMatrix(path)
     assert (third.matrix != ma.matrix).nnz == 0 and (again.matrix != ma.matrix).nnz == 0
+
+
+@pytest.mark.parametrize("ext", [".h5", ".cool"])
+def test_compressed_files_mirror_the_reference_layout_and_round_trip(tmp_path, ext):
+    """the writer produces what the reference's writers produce (docs/content/file-formats.rst:9-31, 64-76): chunked
+    datasets with PyTables' Blosc pipeline (.h5) / cooler's shuffle + deflate (.cool), a version-1 chunk B-tree closed
+    like the golden files'; both decoders (C and pure Python) read them back bit for bit"""
+    from scipy import sparse
+    from hicexplorer_b200.hicmatrix_lite import hiCMatrix
+    rng = np.random.default_rng(1)
+    n = 3000
+    up = sparse.random(n, n, 0.06, random_state=rng, format="csr")     # ~270 k entries: several chunks, 2 B-tree levels in pixels
+    up = sparse.triu(sparse.csr_matrix(np.round(up * 50)), 0, format="csr")
+    up.eliminate_zeros()
+    ma = hiCMatrix()
+    ma.matrix = sparse.csr_matrix(up + sparse.triu(up, 1).T)
+    ma.cut_intervals = [("chr%d" % (1 + i // 1000), (i % 1000) * 10, (i % 1000 + 1) * 10, 1.0) for i in range(n)]
+    ma._index_intervals()
+    ma.correction_factors = rng.random(n)
+    path = str(tmp_path / ("m" + ext))
+    ma.save(path)
+    f = hdf5lite.File(path)
+    big = f["matrix/data"] if ext == ".h5" else f["pixels/count"]
+    if ext == ".h5":
+        assert big._filters == [(32001, (2, 2, 8, 65536, 5, 1))]              # as in the golden files
+        assert f["matrix/indices"]._filters == [(32001, (2, 2, 4, 65536, 5, 1))]
+        assert f["matrix/data"].attrs["CLASS"] == "CARRAY" and f.attrs["TITLE"] == "HiCExplorer matrix"
+    else:
+        assert big._filters == [(2, (8,)), (1, (hdf5lite._GZIP_LEVEL,))]
+        assert f["bins/chrom"].enum is not None
+    assert os.path.getsize(path) < 0.6 * (12 * up.nnz)                        # it does compress
+    # the chunk index: fixed-size nodes for K = 32, closing key = (end of the last chunk, element size)
+    lay = big._layout
+    import struct as st
+    (root,) = st.unpack_from("<Q", lay, 3)
+    buf = f._buf
+    assert buf[root:root + 4] == b"TREE" and buf[root + 4] == 1
+    level, nent = buf[root + 5], st.unpack_from("<H", buf, root + 6)[0]
+    nchunks = -(-big.shape[0] // 8192)
+    assert (level == 0 and nent == nchunks) if nchunks <= 64 else level >= 1
+    for mode in ("native", "python"):
+        if mode == "python":
+            os.environ["HDF5LITE_PURE_PYTHON"] = "1"
+        hdf5lite._native = None
+        try:
+            back = hiCMatrix(path)
+        finally:
+            os.environ.pop("HDF5LITE_PURE_PYTHON", None)
+            hdf5lite._native = None
+        assert (back.matrix != ma.matrix).nnz == 0
+        assert [iv[:3] for iv in back.cut_intervals] == [iv[:3] for iv in ma.cut_intervals]
+        np.testing.assert_array_equal(np.asarray(back.correction_factors).ravel(), ma.correction_factors)
+
+
+def test_chunk_btree_with_several_levels(tmp_path):
+    """more than 64 chunks -> internal nodes; more than 4096 -> three levels"""
+    for n in (8192 * 70 + 5, 8192 * 4100):
+        a = (np.arange(n, dtype=np.int64) * 7919) % 1000
+        w = hdf5lite.Writer()
+        w.dataset("/x", a, filters="blosc", chunk_len=8192)
+        path = str(tmp_path / "t.h5")
+        w.save(path)
+        np.testing.assert_array_equal(hdf5lite.File(path)["x"].read(), a)
