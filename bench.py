@@ -555,14 +555,22 @@ def main():
             h2 = ctypes.c_void_p()
             check(L.hb_csr_create(ctypes.byref(h2), n_rows, n_cols, row0, nnz_local, ctypes.c_void_p(ip_h.data_ptr()),
                                   ctypes.c_void_p(ix_h.data_ptr()), 0, ctypes.c_void_p(da_h.data_ptr()), local))
+            t_create = time.time() - t0
             dev2 = DeviceCSR(h2, local)
             keep2 = None
             if world > 1 and not (peer_mode and attach_peer(dev2, rank, world)):
                 keep2 = attach_comm(dev2, rank, world)
+            t_attach = time.time() - t0 - t_create
             check(L.hb_ice_run(h2, args.steps, 0.0, ctypes.c_void_p(bias_h.data_ptr()), _lib.ptr(iters_h),
                                _lib.ptr(devv)))
+            t_run = time.time() - t0 - t_create - t_attach
             barrier()
             e2e_s = max_over_ranks(time.time() - t0)
+            breakdown = {"hb_csr_create_s": max_over_ranks(t_create), "attach_exchange_s": max_over_ranks(t_attach),
+                         "hb_ice_run_s": max_over_ranks(t_run),
+                         "h2d_GBps_per_gpu_inside_create": 12.0 * nnz_local / max(t_create, 1e-9) / 1e9,
+                         "note": "rank-wise maxima of host timestamps; the upload dominates hb_csr_create (pinned host memory, "
+                                 "PCIe Gen5 x16 per GPU; with N ranks the host's memory bandwidth is shared)"}
             dev2.close()
             del keep2
             # the same call sequence run to the reference's own stopping rule (tolerance 1e-5): the whole job a caller of
@@ -607,6 +615,7 @@ def main():
                    "d2h_bytes_per_step": 8.0 * n * world / args.steps, "seconds": e2e_s, "iterations": int(iters_h[0]),
                    "what": "hb_csr_create (pinned host CSR -> HBM) + hb_ice_run(max_iter=steps, tol=0) + bias to host; "
                            "one call = `steps` iterations, so the one-off copy is amortised over them",
+                   "breakdown": breakdown,
                    "to_convergence": {"seconds": conv_s, "iterations": int(iters_c[0]), "tolerance": 1e-5,
                                       "nnz_per_s": nnz_total * int(iters_c[0]) / conv_s,
                                       "what": "same calls with max_iter=500, tol=1e-5: upload + every iteration the "

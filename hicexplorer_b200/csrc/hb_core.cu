@@ -2,6 +2,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 
 #include "hb_internal.cuh"
 
@@ -378,6 +379,18 @@ int hb_set_comm(hb_csr* h, int rank, int world, hb_allreduce_fn fn, void* ctx) {
     return HB_OK;
 }
 
+// ---- peer regions: process-wide registry -------------------------------------------------------------------------
+static std::mutex g_peer_mutex;
+static std::vector<HbPeerCtx*> g_peer_ctxs;
+
+static void hb_peer_ctx_free(HbPeerCtx* c) {
+    cudaSetDevice(c->device);
+    for (int q = 0; q < HB_MAX_PEERS; ++q)
+        if (c->base[q] != nullptr && c->ipc[q]) cudaIpcCloseMemHandle(c->base[q]);
+    cudaFree(c->d_sym);
+    delete c;
+}
+
 int hb_peer_export(hb_csr* h, int rank, int world, void* ipc_handle_out) {
     HB_RANGE("hb_peer_export");
     HB_REQUIRE(h != nullptr && ipc_handle_out != nullptr, "bad arguments");
@@ -385,18 +398,56 @@ int hb_peer_export(hb_csr* h, int rank, int world, void* ipc_handle_out) {
     int rc = hb_use_device(h);
     if (rc) return rc;
     hb_peer_release(h);
-    const size_t buf = ((sizeof(double) * (size_t)(h->n_cols + 64)) + 255) & ~(size_t)255;
-    h->sym_buf_bytes = buf;
-    h->sym_flag_off = 2 * buf;
-    const size_t total = 2 * buf + 2 * 512 + 256;
-    HB_CUDA(cudaMalloc(&h->d_sym, total));
-    HB_CUDA(cudaMemset(h->d_sym, 0, total));
-    HB_CUDA(cudaDeviceSynchronize());   // cudaMemset is asynchronous and the handle's stream is non-blocking: finish it here
-    h->d_done = (unsigned int*)((unsigned char*)h->d_sym + 2 * buf + 2 * 512);
-    cudaIpcMemHandle_t hd;
-    HB_CUDA(cudaIpcGetMemHandle(&hd, h->d_sym));
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    memcpy(ipc_handle_out, &hd, 64);
+    std::lock_guard<std::mutex> guard(g_peer_mutex);
+    // every rank sees the same sequence of requests, so every rank takes the same decision here
+    HbPeerCtx* c = nullptr;
+    for (HbPeerCtx* k : g_peer_ctxs)
+        if (k->device == h->device && k->rank == rank && k->world == world && k->users == 0 && k->capacity_cols >= h->n_cols) {
+            c = k;
+            break;
+        }
+    if (c == nullptr) {
+        // retire idle regions of this rank that are too small, then build a new one
+        for (size_t i = 0; i < g_peer_ctxs.size();) {
+            HbPeerCtx* k = g_peer_ctxs[i];
+            if (k->device == h->device && k->rank == rank && k->world == world && k->users == 0) {
+                hb_peer_ctx_free(k);
+                g_peer_ctxs.erase(g_peer_ctxs.begin() + (long)i);
+            } else {
+                ++i;
+            }
+        }
+        c = new HbPeerCtx();
+        c->device = h->device;
+        c->rank = rank;
+        c->world = world;
+        c->capacity_cols = h->n_cols;
+        c->buf_bytes = ((sizeof(double) * (size_t)(h->n_cols + 64)) + 255) & ~(size_t)255;
+        c->flag_off = 2 * c->buf_bytes;
+        c->total = 2 * c->buf_bytes + 2 * 512 + 256;
+        cudaError_t e = cudaMalloc(&c->d_sym, c->total);
+        if (e == cudaSuccess) e = cudaMemset(c->d_sym, 0, c->total);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();   // cudaMemset is asynchronous and the work streams are non-blocking
+        if (e != cudaSuccess) {
+            cudaFree(c->d_sym);
+            delete c;
+            return hb_cuda_fail(e, "peer region", __FILE__, __LINE__);
+        }
+        c->d_done = (unsigned int*)((unsigned char*)c->d_sym + 2 * c->buf_bytes + 2 * 512);
+        cudaIpcMemHandle_t hd;
+        e = cudaIpcGetMemHandle(&hd, c->d_sym);
+        if (e != cudaSuccess) {
+            cudaFree(c->d_sym);
+            delete c;
+            return hb_cuda_fail(e, "cudaIpcGetMemHandle", __FILE__, __LINE__);
+        }
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        memcpy(c->handles + 64 * rank, &hd, 64);
+        g_peer_ctxs.push_back(c);
+    }
+    memcpy(ipc_handle_out, c->handles + 64 * rank, 64);
+    c->users = 1;
+    h->pc = c;
     h->rank = rank;
     h->world = world;
     return HB_OK;
@@ -404,32 +455,45 @@ int hb_peer_export(hb_csr* h, int rank, int world, void* ipc_handle_out) {
 
 int hb_peer_attach(hb_csr* h, const void* all_handles) {
     HB_RANGE("hb_peer_attach");
-    HB_REQUIRE(h != nullptr && all_handles != nullptr && h->d_sym != nullptr, "call hb_peer_export first");
+    HB_REQUIRE(h != nullptr && all_handles != nullptr && h->pc != nullptr, "call hb_peer_export first");
     int rc = hb_use_device(h);
     if (rc) return rc;
-    for (int q = 0; q < h->world; ++q) {
-        if (q == h->rank) {
-            h->peer_base[q] = h->d_sym;
-            continue;
+    HbPeerCtx* c = h->pc;
+    bool same = c->attached;
+    for (int q = 0; same && q < c->world; ++q)
+        if (q != c->rank && memcmp(c->handles + 64 * q, (const unsigned char*)all_handles + 64 * q, 64) != 0) same = false;
+    if (!same) {
+        for (int q = 0; q < c->world; ++q) {
+            if (c->base[q] != nullptr && c->ipc[q]) cudaIpcCloseMemHandle(c->base[q]);
+            c->base[q] = nullptr;
+            c->ipc[q] = false;
         }
-        cudaIpcMemHandle_t hd;
-        memcpy(&hd, (const unsigned char*)all_handles + 64 * q, 64);
-        void* p = nullptr;
-        cudaError_t e = cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess);
-        if (e != cudaSuccess) {
-            hb_peer_release(h);
-            return hb_cuda_fail(e, "cudaIpcOpenMemHandle (peer access between the GPUs is required)", __FILE__, __LINE__);
+        c->attached = false;
+        for (int q = 0; q < c->world; ++q) {
+            if (q == c->rank) {
+                c->base[q] = c->d_sym;
+                continue;
+            }
+            cudaIpcMemHandle_t hd;
+            memcpy(&hd, (const unsigned char*)all_handles + 64 * q, 64);
+            void* p = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                hb_peer_release(h);
+                return hb_cuda_fail(e, "cudaIpcOpenMemHandle (peer access between the GPUs is required)", __FILE__, __LINE__);
+            }
+            c->base[q] = p;
+            c->ipc[q] = true;
+            memcpy(c->handles + 64 * q, &hd, 64);
         }
-        h->peer_base[q] = p;
-        h->peer_ipc[q] = true;
+        c->attached = true;
     }
     h->peer = true;          // the SpMV exchange goes over peer stores; a registered callback stays for the other collectives
-    h->peer_seq = 0;
     return HB_OK;
 }
 
 int hb_peer_attach_inprocess(hb_csr* h, hb_csr* const* ranks) {
-    HB_REQUIRE(h != nullptr && ranks != nullptr && h->d_sym != nullptr, "call hb_peer_export first");
+    HB_REQUIRE(h != nullptr && ranks != nullptr && h->pc != nullptr, "call hb_peer_export first");
     int rc = hb_use_device(h);
     if (rc) return rc;
     // Ranks of one process may share a GPU, where an allocation made by one rank (cudaMalloc synchronises the device)
@@ -437,10 +501,10 @@ int hb_peer_attach_inprocess(hb_csr* h, hb_csr* const* ranks) {
     // solvers need is therefore reserved now, before any of them runs.
     rc = hb_kr_reserve(h);
     if (rc) return rc;
+    HbPeerCtx* c = h->pc;
     for (int q = 0; q < h->world; ++q) {
         hb_csr* o = ranks[q];
-        HB_REQUIRE(o != nullptr && o->d_sym != nullptr && o->world == h->world && o->rank == q &&
-                       o->sym_buf_bytes == h->sym_buf_bytes,
+        HB_REQUIRE(o != nullptr && o->pc != nullptr && o->world == h->world && o->rank == q && o->pc->buf_bytes == c->buf_bytes,
                    "every rank must have called hb_peer_export with the same world and matrix size");
         if (o->device != h->device) {
             int can = 0;
@@ -450,11 +514,12 @@ int hb_peer_attach_inprocess(hb_csr* h, hb_csr* const* ranks) {
             if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
             else if (e != cudaSuccess) return hb_cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
         }
-        h->peer_base[q] = o->d_sym;
-        h->peer_ipc[q] = false;
+        if (c->base[q] != nullptr && c->ipc[q]) cudaIpcCloseMemHandle(c->base[q]);
+        c->base[q] = o->pc->d_sym;
+        c->ipc[q] = false;
     }
+    c->attached = false;   // raw pointers of this process: never matched against IPC handles later
     h->peer = true;
-    h->peer_seq = 0;
     return HB_OK;
 }
 
@@ -533,14 +598,12 @@ int hb_set_segments(hb_csr* h, int nseg, const int64_t* seg_offsets) {
 
 void hb_peer_release(hb_csr* h) {
     if (h->loop_pending) hb_loop_settle(h);
-    for (int q = 0; q < HB_MAX_PEERS; ++q) {
-        if (h->peer_base[q] != nullptr && h->peer_ipc[q]) cudaIpcCloseMemHandle(h->peer_base[q]);
-        h->peer_base[q] = nullptr;
-        h->peer_ipc[q] = false;
+    if (h->pc != nullptr) {
+        // the region stays in the registry (mapped on every peer) for the next handle of this rank
+        std::lock_guard<std::mutex> guard(g_peer_mutex);
+        h->pc->users = 0;
+        h->pc = nullptr;
     }
-    cudaFree(h->d_sym);
-    h->d_sym = nullptr;
-    h->d_done = nullptr;
     h->peer = false;
 }
 
@@ -622,7 +685,7 @@ void hb_free_state(hb_csr* h) {
 int hb_loop_settle(hb_csr* h) {
     if (!h->loop_pending) return HB_OK;
     HB_CUDA(cudaEventSynchronize(h->loop_event));
-    h->peer_seq += (unsigned long long)(unsigned int)((volatile int32_t*)h->h_loop)[HB_LP_EXCHANGES];
+    if (h->pc != nullptr) h->pc->seq += (unsigned long long)(unsigned int)((volatile int32_t*)h->h_loop)[HB_LP_EXCHANGES];
     h->loop_pending = false;
     return HB_OK;
 }

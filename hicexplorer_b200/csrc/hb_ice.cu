@@ -610,9 +610,9 @@ int hb_dev_ice_update(hb_csr* h, const double* d_exch, int world, double tol, vo
     cudaStream_t s = pick_stream(h, stream);
     if (h->peer) {
         // wait for every rank's arrival flag of the exchange just issued, then read the local replica
-        const int p = (int)(h->peer_seq & 1ull);
+        const int p = (int)(h->pc->seq & 1ull);
         d_exch = hb_sym_buf(h, p);
-        hb_peer_wait_kernel<<<1, 32, 0, s>>>(hb_sym_flags(h, p), h->peer_seq, h->world, h->d_status, nullptr);
+        hb_peer_wait_kernel<<<1, 32, 0, s>>>(hb_sym_flags(h, p), h->pc->seq, h->world, h->d_status, nullptr);
         HB_LAUNCH_CHECK();
     } else if (d_exch == nullptr) {
         d_exch = h->d_exch;

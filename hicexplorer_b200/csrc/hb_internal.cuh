@@ -59,6 +59,24 @@ enum { HB_ST_ALL_DONE = 0, HB_ST_OVERFLOW = 1, HB_ST_ITER = 2, HB_ST_ACTIVE = 3,
 // pinned progress words of the persistent solver kernels: the first four mirror the status words above
 enum { HB_LP_EXCHANGES = 4, HB_LP_OUTER = 5, HB_LP_MATVECS = 6, HB_LP_FLAGS = 7, HB_LOOP_WORDS = 16 };
 
+// Symmetric region of one rank: 2 x (exchange vector | arrival flags) + the ticket counter, exported through CUDA IPC and
+// mapped by every peer.  Kept in a process-wide registry keyed by (device, rank, world): attaching costs an allocation,
+// a device synchronisation and world-1 cudaIpcOpenMemHandle calls the first time only.  The exchange sequence number
+// belongs to the region (flags are monotone), not to the handle.
+struct HbPeerCtx {
+    int device = -1, world = 0, rank = 0;
+    void* d_sym = nullptr;                          // this rank's region (cudaMalloc)
+    size_t buf_bytes = 0, flag_off = 0, total = 0;  // layout: buf p at p*buf_bytes ; flags p at flag_off + p*512
+    int64_t capacity_cols = 0;
+    void* base[HB_MAX_PEERS] = {nullptr};           // every rank's region mapped here (own entry = d_sym)
+    bool ipc[HB_MAX_PEERS] = {false};               // mapping came from cudaIpcOpenMemHandle (to be closed)
+    unsigned char handles[HB_MAX_PEERS * 64] = {0}; // the IPC handles the mappings were opened from
+    bool attached = false;
+    unsigned long long seq = 0;                     // exchange sequence number (monotonic)
+    unsigned int* d_done = nullptr;                 // ticket counter of the publishing SpMV
+    int users = 0;                                  // handles currently bound to the region
+};
+
 struct hb_csr {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -80,14 +98,10 @@ struct hb_csr {
     hb_allreduce_fn allreduce = nullptr;
     void* comm_ctx = nullptr;
 
-    // peer-store exchange (hb_peer_export / hb_peer_attach): symmetric region = 2 x (exchange vector | flags)
+    // peer-store exchange (hb_peer_export / hb_peer_attach): the symmetric region lives in a process-wide context that
+    // outlives the handle, so a second handle of the same rank (next matrix, next call) re-uses the mapped regions
     bool peer = false;
-    void* d_sym = nullptr;                          // this rank's region (cudaMalloc, exported through CUDA IPC)
-    void* peer_base[HB_MAX_PEERS] = {nullptr};      // every rank's region mapped here (own entry = d_sym)
-    bool peer_ipc[HB_MAX_PEERS] = {false};          // mapping came from cudaIpcOpenMemHandle (to be closed)
-    size_t sym_buf_bytes = 0, sym_flag_off = 0;     // layout: buf p at p*sym_buf_bytes ; flags p at sym_flag_off + p*512
-    unsigned long long peer_seq = 0;                // exchange sequence number (monotonic)
-    unsigned int* d_done = nullptr;                 // ticket counter of the publishing SpMV
+    struct HbPeerCtx* pc = nullptr;
 
     // segments (independent diagonal blocks) and fixed reduction tiles over GLOBAL rows
     int nseg = 1;
@@ -177,9 +191,9 @@ void hb_drop_pack(hb_csr* h);
 int hb_copy_h2d(void* d_dst, const void* h_src, size_t bytes, int device);
 int hb_copy_d2h(void* h_dst, const void* d_src, size_t bytes, int device);
 // exchange buffer p (0/1) of this rank's symmetric region and its flag array
-static inline double* hb_sym_buf(const hb_csr* h, int p) { return (double*)((unsigned char*)h->d_sym + (size_t)p * h->sym_buf_bytes); }
+static inline double* hb_sym_buf(const hb_csr* h, int p) { return (double*)((unsigned char*)h->pc->d_sym + (size_t)p * h->pc->buf_bytes); }
 static inline unsigned long long* hb_sym_flags(const hb_csr* h, int p) {
-    return (unsigned long long*)((unsigned char*)h->d_sym + h->sym_flag_off + (size_t)p * 512);
+    return (unsigned long long*)((unsigned char*)h->pc->d_sym + h->pc->flag_off + (size_t)p * 512);
 }
 
 // ---- device helpers ---------------------------------------------------------

@@ -896,7 +896,7 @@ int hb_kr_run(hb_csr* h, double tol, double delta, double Delta, double diag_eps
             goto done;
         }
         const volatile int32_t* lp = (const volatile int32_t*)h->h_loop;
-        h->peer_seq += (unsigned long long)(unsigned int)lp[HB_LP_EXCHANGES];
+        if (h->pc != nullptr) h->pc->seq += (unsigned long long)(unsigned int)lp[HB_LP_EXCHANGES];
         outer = lp[HB_LP_OUTER];
         mvp = lp[HB_LP_MATVECS];
         rout = c.h_sc[SC_ROUT];

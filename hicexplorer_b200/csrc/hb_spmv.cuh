@@ -293,14 +293,14 @@ static inline void hb_fill_loop_peer(const hb_csr* h, HbLoopPeer* lp) {
     memset(lp, 0, sizeof(*lp));
     lp->world = 1;
     lp->rank = h->rank;
-    lp->seq0 = h->peer_seq;
+    lp->seq0 = h->pc != nullptr ? h->pc->seq : 0ull;
     if (!h->peer) return;
     lp->world = h->world;
     for (int p = 0; p < 2; ++p)
         for (int q = 0; q < h->world; ++q) {
-            unsigned char* base = (unsigned char*)h->peer_base[q];
-            lp->buf[p][q] = (double*)(base + (size_t)p * h->sym_buf_bytes);
-            lp->flag[p][q] = (unsigned long long*)(base + h->sym_flag_off + (size_t)p * 512);
+            unsigned char* base = (unsigned char*)h->pc->base[q];
+            lp->buf[p][q] = (double*)(base + (size_t)p * h->pc->buf_bytes);
+            lp->flag[p][q] = (unsigned long long*)(base + h->pc->flag_off + (size_t)p * 512);
         }
 }
 
@@ -317,16 +317,16 @@ static inline HbPeerOut hb_next_out(hb_csr* h, double* local_out) {
         return po;
     }
     hb_loop_settle(h);   // a persistent kernel still in flight owns part of the sequence: wait for its count
-    const unsigned long long seq = ++h->peer_seq;
+    const unsigned long long seq = ++h->pc->seq;
     const int p = (int)(seq & 1ull);
     po.world = h->world;
     po.publish = 1;
     po.seq = seq;
-    po.done = h->d_done;
+    po.done = h->pc->d_done;
     for (int q = 0; q < h->world; ++q) {
-        unsigned char* base = (unsigned char*)h->peer_base[q];
-        po.out[q] = (double*)(base + (size_t)p * h->sym_buf_bytes);
-        po.flag[q] = (unsigned long long*)(base + h->sym_flag_off + (size_t)p * 512);
+        unsigned char* base = (unsigned char*)h->pc->base[q];
+        po.out[q] = (double*)(base + (size_t)p * h->pc->buf_bytes);
+        po.flag[q] = (unsigned long long*)(base + h->pc->flag_off + (size_t)p * 512);
     }
     return po;
 }
