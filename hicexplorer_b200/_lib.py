@@ -109,6 +109,7 @@ SIGNATURES = {
     "hb_ice_scaled_row_sums": (c_int, [vp, vp]),
     "hb_dev_ice_begin": (c_int, [vp, vp]),
     "hb_dev_ice_loop": (c_int, [vp, c_int, c_dbl, vp]),
+    "hb_loop_progress": (c_int, [vp, vp]),
     "hb_dev_ice_spmv": (c_int, [vp, vp, c_int, c_int, vp]),
     "hb_dev_ice_update": (c_int, [vp, vp, c_int, c_dbl, vp]),
     "hb_dev_ice_status": (c_int, [vp, vp, vp]),

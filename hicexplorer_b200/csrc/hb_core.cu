@@ -692,9 +692,9 @@ int hb_loop_settle(hb_csr* h) {
 
 // Grid of a cooperative (grid-synchronising) persistent kernel: what hb_spmv_grid asks for, capped by what is
 // co-resident on this device for THIS kernel.
-int hb_coop_grid(const void* kernel, int64_t n_rows, int device) {
+int hb_coop_grid(const void* kernel, int64_t n_rows, int device, int dyn_smem) {
     int per_sm = 0, sms = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, HB_SPMV_THREADS, 0) != cudaSuccess || per_sm < 1) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, HB_SPMV_THREADS, (size_t)dyn_smem) != cudaSuccess || per_sm < 1) {
         cudaGetLastError();
         per_sm = 1;
     }

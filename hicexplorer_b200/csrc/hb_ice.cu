@@ -724,6 +724,12 @@ int hb_dev_ice_loop(hb_csr* h, int iters, double tol, void* stream) {
     return HB_OK;
 }
 
+int hb_loop_progress(hb_csr* h, int32_t* words16) {
+    HB_REQUIRE(h != nullptr && h->state_ready && words16 != nullptr, "bad arguments");
+    for (int i = 0; i < HB_LOOP_WORDS; ++i) words16[i] = ((volatile int32_t*)h->h_loop)[i];
+    return HB_OK;
+}
+
 int hb_dev_ice_status(hb_csr* h, int32_t* pinned_status4, void* stream) {
     HB_REQUIRE(h != nullptr && h->state_ready && pinned_status4 != nullptr, "bad arguments");
     HB_CUDA(cudaMemcpyAsync(pinned_status4, h->d_status, sizeof(int32_t) * HB_ST_WORDS, cudaMemcpyDeviceToHost,

@@ -185,7 +185,7 @@ int hb_spmv_grid(int64_t n_rows);
 void hb_peer_release(hb_csr* h);
 int hb_kr_reserve(hb_csr* h);                        // allocate the Knight-Ruiz workspace of the handle (idempotent)
 int hb_loop_settle(hb_csr* h);                       // fold a finished loop kernel's exchange count into peer_seq
-int hb_coop_grid(const void* kernel, int64_t n_rows, int device);   // co-resident persistent grid for a cooperative launch
+int hb_coop_grid(const void* kernel, int64_t n_rows, int device, int dyn_smem = 0);   // co-resident persistent grid for a cooperative launch
 void hb_drop_pack(hb_csr* h);
 // multi-threaded staged copies for pageable caller buffers (hb_xfer.cu); synchronous
 int hb_copy_h2d(void* d_dst, const void* h_src, size_t bytes, int device);

@@ -887,7 +887,8 @@ int hb_kr_run(hb_csr* h, double tol, double delta, double Delta, double diag_eps
         void* params[] = {(void*)&a};
         for (int i = 0; i < HB_LOOP_WORDS; ++i) ((volatile int32_t*)h->h_loop)[i] = 0;
         cudaError_t e = cudaMemsetAsync(h->d_loop_wmax, 0, 24, c.s);   // wmax[2] | err
-        if (e == cudaSuccess) e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(HB_SPMV_THREADS), params, 0, c.s);
+        if (e == cudaSuccess)
+            e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(HB_SPMV_THREADS), params, 0, c.s);
         g_hb_launches.fetch_add(1, std::memory_order_relaxed);
         if (e == cudaSuccess) e = cudaMemcpyAsync(c.h_sc, c.sc, sizeof(double) * SC_WORDS, cudaMemcpyDeviceToHost, c.s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c.s);

@@ -13,6 +13,7 @@
 // rows (Hi-C rows range from a handful to tens of thousands of entries) balance out.
 // The constants were chosen by the sweep recorded in profiles/r1_spmv_variant_sweep.txt.
 #pragma once
+#include <cstdlib>
 #include <cstring>
 
 #include "hb_internal.cuh"

@@ -302,6 +302,10 @@ HB_API int hb_ice_scaled_row_sums(hb_csr* h, double* out);
  *                      Results are bit-identical to `iters` x (hb_dev_ice_spmv, hb_dev_ice_update).  hb_ice_run uses it
  *                      whenever it can (set HB_NO_PERSISTENT=1 in the environment to force the step-level path). */
 HB_API int hb_dev_ice_loop(hb_csr* h, int iters, double tol, void* stream);
+/* The 16 int32 progress words the persistent kernels mirror into pinned host memory while they run (no synchronisation):
+ * [0] all done, [1] overflow, [2] iterations completed, [3] active segments, [4] exchanges of the last launch,
+ * [5] KR outer iterations, [6] KR mat-vecs, [7] KR status, [8..15] diagnostics of a stage wait that gave up. */
+HB_API int hb_loop_progress(hb_csr* h, int32_t* words16);
 HB_API int hb_dev_ice_begin(hb_csr* h, void* stream);
 HB_API int hb_dev_ice_spmv(hb_csr* h, double* d_exch, int rank, int world, void* stream);
 HB_API int hb_dev_ice_update(hb_csr* h, const double* d_exch, int world, double tol, void* stream);
