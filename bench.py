@@ -253,6 +253,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-kr", action="store_true")
     ap.add_argument("--quick", action="store_true", help="timed ICE loop only (for ncu captures)")
+    ap.add_argument("--no-all-configs", dest="all_configs", action="store_false",
+                    help="skip BASELINE.json configs[3] (--perchr 5 kb) and configs[4] (KR 1 kb, 8e9 entries) after the headline")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: rows stored into peer replicas over NVLink by the SpMV epilogue (default, falls back "
                          "to nccl when peer access is unavailable) or one NCCL sum-allreduce per iteration")
@@ -632,6 +634,24 @@ def main():
     if world == 1 and not args.no_kr:
         kr = bench_kr(torch, L, check, _lib, DeviceCSR, local, stream, sptr)
 
+    # ---- BASELINE.json configs[3] and configs[4] on the same N GPUs (tools/bench_configs.py) ---------------------
+    # --perchr ICE + KR on the 5 kb matrix (24 chromosomes, no communication) and KR on the genome-wide 1 kb matrix
+    # (3.09 M bins, 8.0e9 entries = 96 GB of CSR, row blocks over the N GPUs)
+    other_configs = None
+    if args.all_configs and not args.quick:
+        other_configs = {}
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_configs
+        torch.cuda.set_stream(torch.cuda.default_stream())
+        for name in ("perchr5k", "kr1k"):
+            try:
+                barrier()
+                torch.cuda.empty_cache()
+                other_configs[name] = bench_configs.run(name)
+            except Exception as exc:
+                other_configs[name] = {"error": repr(exc)}
+        torch.cuda.set_stream(stream)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -688,6 +708,8 @@ def main():
         line["parity"] = parity
     if kr10 is not None:
         line["kr_same_matrix"] = kr10
+    if other_configs is not None:
+        line["other_configs"] = other_configs
     if kr is not None:
         line["kr"] = kr
     if not args.no_cpu and world == 1:

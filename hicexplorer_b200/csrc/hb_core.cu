@@ -36,6 +36,14 @@ int hb_spmv_grid(int64_t n_rows) {
     return (int)(ctas_needed < 1 ? 1 : ctas_needed);
 }
 
+// ---- device memory --------------------------------------------------------------------------------------------------
+// One place for every allocation of the library.  A stream-ordered pool (cudaMallocAsync, release threshold raised) was
+// tried here in round 2: it saves ~1.5 ms per per-chromosome handle, but its first use costs ~125 ms per process and
+// growing / trimming it by tens of gigabytes is slower than mapping the stores directly (bin deletion on the 10 kb
+// matrix: 150-190 ms instead of 24 ms) -- so this stays plain cudaMalloc / cudaFree.
+cudaError_t hb_pool_alloc(void** p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 1); }
+cudaError_t hb_pool_free(void* p) { return p != nullptr ? cudaFree(p) : cudaSuccess; }
+
 extern "C" {
 
 int hb_abi_version(void) { return HB_ABI_VERSION; }
@@ -170,11 +178,11 @@ int hb_csr_create_typed(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t ro
             return hb_cuda_fail(_e, #expr, __FILE__, __LINE__);            \
         }                                                                  \
     } while (0)
-    HB_CREATE_CUDA(cudaMalloc(&h->d_indptr, sizeof(int64_t) * (size_t)(n_rows + 1)));
+    HB_CREATE_CUDA(hb_dmalloc(&h->d_indptr, sizeof(int64_t) * (size_t)(n_rows + 1)));
     const int64_t phase = indptr[0] & 3;
     h->phase = phase;
-    HB_CREATE_CUDA(cudaMalloc(&h->d_indices, sizeof(int32_t) * (size_t)(nnz + phase + 4) + 16));
-    HB_CREATE_CUDA(cudaMalloc(&h->d_data, sizeof(double) * (size_t)(nnz + phase + 4) + 16));
+    HB_CREATE_CUDA(hb_dmalloc(&h->d_indices, sizeof(int32_t) * (size_t)(nnz + phase + 4) + 16));
+    HB_CREATE_CUDA(hb_dmalloc(&h->d_data, sizeof(double) * (size_t)(nnz + phase + 4) + 16));
     // zero the alignment slots in front of the block.  Only those: the entries themselves arrive through hb_copy_h2d,
     // which runs on other streams (the handle's stream is non-blocking), so a memset that overlapped them could land
     // AFTER the copy and wipe the first entries.  The stream is drained before the copies start for the same reason.
@@ -202,11 +210,11 @@ int hb_csr_create_typed(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t ro
             const unsigned char* src = static_cast<const unsigned char*>(data_any) + elt * (size_t)indptr[0];
             const int64_t chunk = (int64_t)1 << 26;
             void* d_tmp = nullptr;
-            HB_CREATE_CUDA(cudaMalloc(&d_tmp, elt * (size_t)(nnz < chunk ? nnz : chunk)));
+            HB_CREATE_CUDA(hb_dmalloc(&d_tmp, elt * (size_t)(nnz < chunk ? nnz : chunk)));
             for (int64_t o = 0; o < nnz; o += chunk) {
                 const int64_t m = nnz - o < chunk ? nnz - o : chunk;
                 if (hb_copy_h2d(d_tmp, src + elt * (size_t)o, elt * (size_t)m, device) != HB_OK) {
-                    cudaFree(d_tmp);
+                    hb_dfree(d_tmp);
                     hb_csr_destroy(h);
                     *out = nullptr;
                     return HB_ERR_CUDA;
@@ -221,18 +229,18 @@ int hb_csr_create_typed(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t ro
                 g_hb_launches.fetch_add(1);
                 cudaError_t ce = cudaStreamSynchronize(s);   // the staging buffer is reused by the next chunk
                 if (ce != cudaSuccess) {
-                    cudaFree(d_tmp);
+                    hb_dfree(d_tmp);
                     HB_CREATE_CUDA(ce);
                 }
             }
-            cudaFree(d_tmp);
+            hb_dfree(d_tmp);
         }
         if (indices_i64) {
             // krbalancing's constructor takes int64 indices (hicCorrectMatrix.py:744-747): narrow on the device
             const int64_t* src = (const int64_t*)indices + indptr[0];
             const int64_t chunk = (int64_t)1 << 26;
             int64_t* d_tmp = nullptr;
-            HB_CREATE_CUDA(cudaMalloc(&d_tmp, sizeof(int64_t) * (size_t)(nnz < chunk ? nnz : chunk)));
+            HB_CREATE_CUDA(hb_dmalloc(&d_tmp, sizeof(int64_t) * (size_t)(nnz < chunk ? nnz : chunk)));
             for (int64_t o = 0; o < nnz; o += chunk) {
                 int64_t m = nnz - o < chunk ? nnz - o : chunk;
                 HB_CREATE_CUDA(cudaMemcpyAsync(d_tmp, src + o, sizeof(int64_t) * (size_t)m, cudaMemcpyHostToDevice, s));
@@ -240,7 +248,7 @@ int hb_csr_create_typed(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t ro
                 g_hb_launches.fetch_add(1);
             }
             HB_CREATE_CUDA(cudaStreamSynchronize(s));
-            cudaFree(d_tmp);
+            hb_dfree(d_tmp);
         } else {
             if (hb_copy_h2d(h->d_indices + phase, (const int32_t*)indices + indptr[0], sizeof(int32_t) * (size_t)nnz,
                             device) != HB_OK) {
@@ -255,7 +263,7 @@ int hb_csr_create_typed(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t ro
         // reject a malformed block before any kernel gathers through its column ids
         unsigned int* d_flags = nullptr;
         unsigned int flags = 0;
-        HB_CREATE_CUDA(cudaMalloc(&d_flags, sizeof(unsigned int)));
+        HB_CREATE_CUDA(hb_dmalloc(&d_flags, sizeof(unsigned int)));
         cudaError_t ve = cudaMemsetAsync(d_flags, 0, sizeof(unsigned int), s);
         if (ve == cudaSuccess && n_rows > 0) {
             hb_validate_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_indptr, h->d_indices, n_rows, n_cols, phase, phase + nnz, d_flags);
@@ -263,7 +271,7 @@ int hb_csr_create_typed(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t ro
         }
         if (ve == cudaSuccess) ve = cudaMemcpyAsync(&flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost, s);
         if (ve == cudaSuccess) ve = cudaStreamSynchronize(s);
-        cudaFree(d_flags);
+        hb_dfree(d_flags);
         HB_CREATE_CUDA(ve);
         if (flags) {
             hb_csr_destroy(h);
@@ -309,12 +317,12 @@ int hb_csr_destroy(hb_csr* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     hb_free_state(h);
     if (h->owns_csr) {
-        cudaFree(h->d_indptr);
-        cudaFree(h->d_indices);
-        cudaFree(h->d_data);
+        hb_dfree(h->d_indptr);
+        hb_dfree(h->d_indices);
+        hb_dfree(h->d_data);
     }
-    cudaFree(h->d_tile_slab);
-    cudaFree(h->d_pack);
+    hb_dfree(h->d_tile_slab);
+    hb_dfree(h->d_pack);
     hb_peer_release(h);
     if (h->loop_event) cudaEventDestroy(h->loop_event);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -543,9 +551,9 @@ int hb_csr_keep_rows(hb_csr* h, int64_t row_begin, int64_t row_end) {
     int64_t* d_ptr = nullptr;
     int32_t* d_idx = nullptr;
     double* d_val = nullptr;
-    cudaError_t e = cudaMalloc(&d_ptr, sizeof(int64_t) * (size_t)(nb + 1));
-    if (e == cudaSuccess) e = cudaMalloc(&d_idx, sizeof(int32_t) * (size_t)(nnz_b + 4) + 16);
-    if (e == cudaSuccess) e = cudaMalloc(&d_val, sizeof(double) * (size_t)(nnz_b + 4) + 16);
+    cudaError_t e = hb_dmalloc(&d_ptr, sizeof(int64_t) * (size_t)(nb + 1));
+    if (e == cudaSuccess) e = hb_dmalloc(&d_idx, sizeof(int32_t) * (size_t)(nnz_b + 4) + 16);
+    if (e == cudaSuccess) e = hb_dmalloc(&d_val, sizeof(double) * (size_t)(nnz_b + 4) + 16);
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(d_ptr, h->d_indptr + row_begin, sizeof(int64_t) * (size_t)(nb + 1), cudaMemcpyDeviceToDevice, s);
     if (e == cudaSuccess && ends[0] != 0) {
@@ -559,15 +567,15 @@ int hb_csr_keep_rows(hb_csr* h, int64_t row_begin, int64_t row_end) {
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) {
-        cudaFree(d_ptr);
-        cudaFree(d_idx);
-        cudaFree(d_val);
+        hb_dfree(d_ptr);
+        hb_dfree(d_idx);
+        hb_dfree(d_val);
         return hb_cuda_fail(e, "keep rows", __FILE__, __LINE__);
     }
     if (h->owns_csr) {
-        cudaFree(h->d_indptr);
-        cudaFree(h->d_indices);
-        cudaFree(h->d_data);
+        hb_dfree(h->d_indptr);
+        hb_dfree(h->d_indices);
+        hb_dfree(h->d_data);
     }
     h->owns_csr = true;
     h->d_indptr = d_ptr;
@@ -629,7 +637,7 @@ int hb_build_tiles(hb_csr* h) {
     }
     seg_tile0[h->nseg] = (int32_t)row0.size();
     h->n_tiles = (int)row0.size();
-    cudaFree(h->d_tile_slab);
+    hb_dfree(h->d_tile_slab);
     h->d_tile_slab = nullptr;
     const size_t nt = h->n_tiles > 0 ? (size_t)h->n_tiles : 1, ns1 = (size_t)h->nseg + 1;
     const size_t o_seg = 0;
@@ -646,7 +654,7 @@ int hb_build_tiles(hb_csr* h) {
         memcpy(host.data() + o_tseg, seg.data(), sizeof(int32_t) * nt);
     }
     memcpy(host.data() + o_st0, seg_tile0.data(), sizeof(int32_t) * ns1);
-    HB_CUDA(cudaMalloc(&h->d_tile_slab, total));
+    HB_CUDA(hb_dmalloc(&h->d_tile_slab, total));
     HB_CUDA(cudaMemcpy(h->d_tile_slab, host.data(), total, cudaMemcpyHostToDevice));
     unsigned char* base = (unsigned char*)h->d_tile_slab;
     h->d_seg_off = (int64_t*)(base + o_seg);
@@ -659,9 +667,9 @@ int hb_build_tiles(hb_csr* h) {
 
 void hb_free_state(hb_csr* h) {
     if (h->loop_pending) hb_loop_settle(h);
-    cudaFree(h->d_state_slab);
+    hb_dfree(h->d_state_slab);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
-    cudaFree(h->d_kr_buf);
+    hb_dfree(h->d_kr_buf);
     h->d_state_slab = nullptr;
     h->h_pinned = nullptr;
     h->d_kr_buf = nullptr;
@@ -731,7 +739,7 @@ int hb_ensure_state(hb_csr* h) {
     // status (16 B) | counters (32 B) | row counters (16 B) | scalar bits (64 B) | loop wmax (16 B) | loop err (8 B)
     const size_t o_small = take(256);
     const size_t total = off;
-    HB_CUDA(cudaMalloc(&h->d_state_slab, total));
+    HB_CUDA(hb_dmalloc(&h->d_state_slab, total));
     unsigned char* b = (unsigned char*)h->d_state_slab;
     h->d_bias = (double*)(b + o_bias);
     h->d_r = (double*)(b + o_r);

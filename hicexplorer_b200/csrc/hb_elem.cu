@@ -124,7 +124,7 @@ int hb_csr_value_stats(hb_csr* h, int scrub, double* sum_out, double* min_out, d
     cudaStream_t s = h->stream;
     const size_t n = (size_t)(h->n_rows > 0 ? h->n_rows : 1);
     double* d_rows = nullptr;
-    HB_CUDA(cudaMalloc(&d_rows, sizeof(double) * (n + 2)));
+    HB_CUDA(hb_dmalloc(&d_rows, sizeof(double) * (n + 2)));
     unsigned int* d_mm = reinterpret_cast<unsigned int*>(d_rows + n + 1);
     const unsigned int init[2] = {0xffffffffu, 0u};
     double total = 0.0;
@@ -140,7 +140,7 @@ int hb_csr_value_stats(hb_csr* h, int scrub, double* sum_out, double* min_out, d
     if (e == cudaSuccess) e = cudaMemcpyAsync(mm, d_mm, sizeof(mm), cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e == cudaSuccess) e = cudaGetLastError();
-    cudaFree(d_rows);
+    hb_dfree(d_rows);
     if (e != cudaSuccess) return hb_cuda_fail(e, "value statistics", __FILE__, __LINE__);
     auto unord = [](unsigned int k) {
         const unsigned int b = (k >> 31) ? (k & 0x7fffffffu) : ~k;
@@ -194,8 +194,8 @@ int hb_csr_eliminate_zeros(hb_csr* h) {
             goto fail;                                            \
         }                                                         \
     } while (0)
-    EZ(cudaMalloc(&d_cnt, sizeof(int64_t) * (nn + 1)));
-    EZ(cudaMalloc(&d_ptr, sizeof(int64_t) * (nn + 1)));
+    EZ(hb_dmalloc(&d_cnt, sizeof(int64_t) * (nn + 1)));
+    EZ(hb_dmalloc(&d_ptr, sizeof(int64_t) * (nn + 1)));
     EZ(cudaMemsetAsync(d_cnt, 0, sizeof(int64_t) * (nn + 1), s));
     if (n > 0) {
         hb_nonzero_kernel<false><<<grid, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, n, d_cnt, nullptr, nullptr, nullptr);
@@ -207,12 +207,12 @@ int hb_csr_eliminate_zeros(hb_csr* h) {
     EZ(cudaStreamSynchronize(s));
     EZ(cudaGetLastError());
     if (new_nnz == h->nnz) {   // nothing to drop
-        cudaFree(d_cnt);
-        cudaFree(d_ptr);
+        hb_dfree(d_cnt);
+        hb_dfree(d_ptr);
         return HB_OK;
     }
-    EZ(cudaMalloc(&d_idx, sizeof(int32_t) * (size_t)(new_nnz > 0 ? new_nnz : 1) + 16));
-    EZ(cudaMalloc(&d_val, sizeof(double) * (size_t)(new_nnz > 0 ? new_nnz : 1) + 16));
+    EZ(hb_dmalloc(&d_idx, sizeof(int32_t) * (size_t)(new_nnz > 0 ? new_nnz : 1) + 16));
+    EZ(hb_dmalloc(&d_val, sizeof(double) * (size_t)(new_nnz > 0 ? new_nnz : 1) + 16));
     if (n > 0 && new_nnz > 0) {
         hb_nonzero_kernel<true><<<grid, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, n, nullptr, d_ptr, d_idx, d_val);
         g_hb_launches.fetch_add(1);
@@ -220,11 +220,11 @@ int hb_csr_eliminate_zeros(hb_csr* h) {
     EZ(cudaStreamSynchronize(s));
     EZ(cudaGetLastError());
 #undef EZ
-    cudaFree(d_cnt);
+    hb_dfree(d_cnt);
     if (h->owns_csr) {
-        cudaFree(h->d_indptr);
-        cudaFree(h->d_indices);
-        cudaFree(h->d_data);
+        hb_dfree(h->d_indptr);
+        hb_dfree(h->d_indices);
+        hb_dfree(h->d_data);
     }
     h->owns_csr = true;
     h->d_indptr = d_ptr;
@@ -233,10 +233,10 @@ int hb_csr_eliminate_zeros(hb_csr* h) {
     h->nnz = new_nnz;
     return HB_OK;
 fail:
-    cudaFree(d_cnt);
-    cudaFree(d_ptr);
-    cudaFree(d_idx);
-    cudaFree(d_val);
+    hb_dfree(d_cnt);
+    hb_dfree(d_ptr);
+    hb_dfree(d_idx);
+    hb_dfree(d_val);
     return rc;
 }
 

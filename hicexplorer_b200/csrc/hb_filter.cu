@@ -373,8 +373,8 @@ static int hb_compact_impl(hb_csr* h, const int32_t* d_newid, int64_t new_n, int
     const int64_t new_row0 = d_newid ? blk_row0 : h->row0;
     int64_t* d_cnt = nullptr;
     int64_t* d_new_indptr = nullptr;
-    HB_CUDA(cudaMalloc(&d_cnt, sizeof(int64_t) * (size_t)(new_rows + 1)));
-    HB_CUDA(cudaMalloc(&d_new_indptr, sizeof(int64_t) * (size_t)(new_rows + 1)));
+    HB_CUDA(hb_dmalloc(&d_cnt, sizeof(int64_t) * (size_t)(new_rows + 1)));
+    HB_CUDA(hb_dmalloc(&d_new_indptr, sizeof(int64_t) * (size_t)(new_rows + 1)));
     HB_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int64_t) * (size_t)(new_rows + 1), s));
     const int grid = HB_NUM_SMS * 8;
     if (h->n_rows > 0) {
@@ -390,19 +390,19 @@ static int hb_compact_impl(hb_csr* h, const int32_t* d_newid, int64_t new_n, int
     HB_CUDA(cudaStreamSynchronize(s));
     int32_t* d_new_idx = nullptr;
     double* d_new_val = nullptr;
-    HB_CUDA(cudaMalloc(&d_new_idx, sizeof(int32_t) * (size_t)(new_nnz > 0 ? new_nnz : 1) + 16));
-    HB_CUDA(cudaMalloc(&d_new_val, sizeof(double) * (size_t)(new_nnz > 0 ? new_nnz : 1) + 16));
+    HB_CUDA(hb_dmalloc(&d_new_idx, sizeof(int32_t) * (size_t)(new_nnz > 0 ? new_nnz : 1) + 16));
+    HB_CUDA(hb_dmalloc(&d_new_val, sizeof(double) * (size_t)(new_nnz > 0 ? new_nnz : 1) + 16));
     if (h->n_rows > 0 && new_nnz > 0) {
         hb_compact_fill_kernel<<<grid, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, h->n_rows, h->row0, rule,
                                                     new_row0, d_new_indptr, d_new_idx, d_new_val);
         HB_LAUNCH_CHECK();
     }
     HB_CUDA(cudaStreamSynchronize(s));
-    cudaFree(d_cnt);
+    hb_dfree(d_cnt);
     if (h->owns_csr) {
-        cudaFree(h->d_indptr);
-        cudaFree(h->d_indices);
-        cudaFree(h->d_data);
+        hb_dfree(h->d_indptr);
+        hb_dfree(h->d_indices);
+        hb_dfree(h->d_data);
     }
     hb_drop_pack(h);
     h->owns_csr = true;
@@ -595,7 +595,7 @@ __global__ void hb_pack_convert_kernel(const double* __restrict__ in, VT* __rest
 }
 
 void hb_drop_pack(hb_csr* h) {
-    cudaFree(h->d_pack);
+    hb_dfree(h->d_pack);
     h->d_pack = nullptr;
     h->pack_kind = 0;
 }
@@ -624,7 +624,7 @@ int hb_csr_pack_values(hb_csr* h, int* kind_out) {
     const int kind = !flags[0] ? 1 : (!flags[1] ? 2 : 0);
     if (kind == 0) return HB_OK;
     const size_t elt = kind == 1 ? sizeof(uint16_t) : sizeof(float);
-    HB_CUDA(cudaMalloc(&h->d_pack, elt * (size_t)(h->nnz + h->phase + 8) + 16));
+    HB_CUDA(hb_dmalloc(&h->d_pack, elt * (size_t)(h->nnz + h->phase + 8) + 16));
     HB_CUDA(cudaMemsetAsync(h->d_pack, 0, elt * 8, s));
     if (kind == 1)
         hb_pack_convert_kernel<uint16_t><<<HB_NUM_SMS * 8, 256, 0, s>>>(src, (uint16_t*)h->d_pack + h->phase, h->nnz);
@@ -836,7 +836,7 @@ int hb_symmetry(hb_csr* h, double* ratio_out) {
     if (rc) return rc;
     cudaStream_t s = h->stream;
     double* d_sums = nullptr;
-    HB_CUDA(cudaMalloc(&d_sums, sizeof(double) * (4 + 16)));
+    HB_CUDA(hb_dmalloc(&d_sums, sizeof(double) * (4 + 16)));
     unsigned long long* d_counts = reinterpret_cast<unsigned long long*>(d_sums + 2);
     double sums[2] = {0, 0};
     unsigned long long counts[2] = {0, 0};
@@ -854,7 +854,7 @@ int hb_symmetry(hb_csr* h, double* ratio_out) {
             hb_digest_limbs_kernel<<<1, 32, 0, s>>>(reinterpret_cast<unsigned long long*>(d_sums), d_sums + 4);
             g_hb_launches.fetch_add(1);
             if (h->allreduce(h->comm_ctx, d_sums + 4, 16, (void*)s) != 0) {
-                cudaFree(d_sums);
+                hb_dfree(d_sums);
                 hb_set_error("hb_symmetry: the allreduce callback failed");
                 return HB_ERR_CUDA;
             }
@@ -864,7 +864,7 @@ int hb_symmetry(hb_csr* h, double* ratio_out) {
                 dg[q] = 0;
                 for (int l = 0; l < 4; ++l) dg[q] += (unsigned long long)limbs[4 * q + l] << (16 * l);
             }
-            cudaFree(d_sums);
+            hb_dfree(d_sums);
             if (e != cudaSuccess) return hb_cuda_fail(e, "symmetry", __FILE__, __LINE__);
             if (dg[0] == dg[2] && dg[1] == dg[3]) {
                 *ratio_out = 0.0;
@@ -880,7 +880,7 @@ int hb_symmetry(hb_csr* h, double* ratio_out) {
         e = cudaMemcpyAsync(dg, d_sums, sizeof(dg), cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
         if (e == cudaSuccess && dg[0] == dg[2] && dg[1] == dg[3]) {
-            cudaFree(d_sums);
+            hb_dfree(d_sums);
             *ratio_out = 0.0;
             return HB_OK;
         }
@@ -903,7 +903,7 @@ int hb_symmetry(hb_csr* h, double* ratio_out) {
         }
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     }
-    cudaFree(d_sums);
+    hb_dfree(d_sums);
     if (e != cudaSuccess) return hb_cuda_fail(e, "symmetry", __FILE__, __LINE__);
     const double cells = (double)h->n_cols * (double)h->n_cols;
     const double num = sums[0] / cells;

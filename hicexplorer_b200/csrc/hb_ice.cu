@@ -689,7 +689,7 @@ int hb_dev_ice_loop(hb_csr* h, int iters, double tol, void* stream) {
     const bool timing = getenv("HB_LOOP_TIMING") != nullptr;
     unsigned long long* d_timing = nullptr;
     if (timing) {
-        HB_CUDA(cudaMalloc(&d_timing, sizeof(unsigned long long) * 256));
+        HB_CUDA(hb_dmalloc(&d_timing, sizeof(unsigned long long) * 256));
         HB_CUDA(cudaMemsetAsync(d_timing, 0, sizeof(unsigned long long) * 256, s));
         a.timing = d_timing;
     }
@@ -704,7 +704,7 @@ int hb_dev_ice_loop(hb_csr* h, int iters, double tol, void* stream) {
         unsigned long long t[256];
         HB_CUDA(cudaStreamSynchronize(s));
         HB_CUDA(cudaMemcpy(t, d_timing, sizeof(t), cudaMemcpyDeviceToHost));
-        cudaFree(d_timing);
+        hb_dfree(d_timing);
         const int m = iters < 32 ? iters : 32;
         double acc[8] = {0};
         int cnt = 0;
@@ -860,7 +860,7 @@ int hb_ice_scaled_values(hb_csr* h, double* data_out, double* max_out) {
     int rc = hb_use_device(h);
     if (rc) return rc;
     double* d_out = nullptr;
-    HB_CUDA(cudaMalloc(&d_out, sizeof(double) * (size_t)(h->nnz > 0 ? h->nnz : 1)));
+    HB_CUDA(hb_dmalloc(&d_out, sizeof(double) * (size_t)(h->nnz > 0 ? h->nnz : 1)));
     rc = hb_dev_ice_emit(h, d_out, nullptr, nullptr);
     double mx[2] = {0.0, 0.0};
     cudaError_t e = cudaSuccess;
@@ -870,7 +870,7 @@ int hb_ice_scaled_values(hb_csr* h, double* data_out, double* max_out) {
             rc = HB_ERR_CUDA;
         if (e == cudaSuccess) e = cudaMemcpy(mx, h->d_scalar_bits, sizeof(mx), cudaMemcpyDeviceToHost);
     }
-    cudaFree(d_out);
+    hb_dfree(d_out);
     if (rc) return rc;
     if (e != cudaSuccess) return hb_cuda_fail(e, "emit", __FILE__, __LINE__);
     if (max_out) *max_out = mx[1];

@@ -148,19 +148,32 @@ struct hb_csr {
     double* h_kr_sc = nullptr;         // pinned mirror of the KR scalars
 };
 
+// Every device allocation of the library goes through these two (hb_core.cu); the peer regions alone call cudaMalloc
+// directly (CUDA IPC).
+cudaError_t hb_pool_alloc(void** p, size_t bytes);
+cudaError_t hb_pool_free(void* p);
+template <typename T>
+static inline cudaError_t hb_dmalloc(T** p, size_t bytes) {
+    void* q = nullptr;
+    const cudaError_t e = hb_pool_alloc(&q, bytes);
+    *p = static_cast<T*>(q);
+    return e;
+}
+static inline cudaError_t hb_dfree(void* p) { return hb_pool_free(p); }
+
 // Device scratch that is released on every exit path of a host function (early error returns included).
 struct HbScratch {
     std::vector<void*> ptrs;
     template <typename T>
     cudaError_t alloc(T** p, size_t bytes) {
         void* q = nullptr;
-        const cudaError_t e = cudaMalloc(&q, bytes ? bytes : 1);
+        const cudaError_t e = hb_dmalloc(&q, bytes ? bytes : 1);
         if (e == cudaSuccess) ptrs.push_back(q);
         *p = static_cast<T*>(q);
         return e;
     }
     ~HbScratch() {
-        for (void* q : ptrs) cudaFree(q);
+        for (void* q : ptrs) hb_dfree(q);
     }
     HbScratch() = default;
     HbScratch(const HbScratch&) = delete;

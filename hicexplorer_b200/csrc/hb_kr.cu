@@ -745,10 +745,10 @@ int hb_kr_reserve(hb_csr* h) {
     const size_t n = (size_t)(h->n_cols > 0 ? h->n_cols : 1);
     const size_t words = 8 * n + 3 * KP_ARRAYS * (size_t)(h->n_tiles > 0 ? h->n_tiles : 1) + SC_WORDS;
     if (h->kr_buf_words < words) {
-        cudaFree(h->d_kr_buf);
+        hb_dfree(h->d_kr_buf);
         h->d_kr_buf = nullptr;
         h->kr_buf_words = 0;
-        cudaError_t e = cudaMalloc(&h->d_kr_buf, sizeof(double) * words);
+        cudaError_t e = hb_dmalloc(&h->d_kr_buf, sizeof(double) * words);
         if (e != cudaSuccess) return hb_cuda_fail(e, "cudaMalloc KR vectors", __FILE__, __LINE__);
         h->kr_buf_words = words;
     }
@@ -1046,7 +1046,7 @@ int hb_kr_rescale(hb_csr* h, double diag_eps, double* x_inout, double* factor_ou
     HB_REQUIRE(h->world == 1 || h->allreduce != nullptr, "sharded hb_kr_rescale needs the allreduce callback (hb_set_comm)");
     cudaStream_t s = h->stream;
     double* buf = nullptr;
-    HB_CUDA(cudaMalloc(&buf, sizeof(double) * (size_t)(3 * n + 3 * h->n_tiles + SC_WORDS)));
+    HB_CUDA(hb_dmalloc(&buf, sizeof(double) * (size_t)(3 * n + 3 * h->n_tiles + SC_WORDS)));
     double *d_x = buf, *d_scaled = buf + n, *d_orig = buf + 2 * n, *d_part = buf + 3 * n, *d_sc = d_part + 3 * h->n_tiles;
     double sc[SC_WORDS];
     cudaError_t e = cudaMemcpyAsync(d_x, x_inout, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s);
@@ -1060,7 +1060,7 @@ int hb_kr_rescale(hb_csr* h, double diag_eps, double* x_inout, double* factor_ou
         }
         // sharded: every rank filled its rows of (scaled | orig); one sum-allreduce assembles both vectors
         if (h->world > 1 && h->allreduce(h->comm_ctx, d_scaled, 2 * n, (void*)s) != 0) {
-            cudaFree(buf);
+            hb_dfree(buf);
             hb_set_error("collective callback failed");
             return HB_ERR_CUDA;
         }
@@ -1076,7 +1076,7 @@ int hb_kr_rescale(hb_csr* h, double diag_eps, double* x_inout, double* factor_ou
         e = cudaMemcpyAsync(sc, d_sc, sizeof(sc), cudaMemcpyDeviceToHost, s);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    cudaFree(buf);
+    hb_dfree(buf);
     if (e != cudaSuccess) return hb_cuda_fail(e, "KR rescale", __FILE__, __LINE__);
     const double factor = sqrt(sc[SC_A] / sc[SC_B]);
     for (int64_t i = 0; i < n; ++i) x_inout[i] /= factor;

@@ -224,11 +224,11 @@ extern "C" int hb_csr_merge_bins(hb_csr* h, const int32_t* bin_map, int64_t n_ne
             goto fail;                                            \
         }                                                         \
     } while (0)
-    MG(cudaMalloc(&d_gs, sizeof(int64_t) * ng));
-    MG(cudaMalloc(&d_ge, sizeof(int64_t) * ng));
-    MG(cudaMalloc(&d_map, sizeof(int32_t) * (size_t)(n > 0 ? n : 1)));
-    MG(cudaMalloc(&d_cnt, sizeof(int64_t) * (ng + 1)));
-    MG(cudaMalloc(&d_ptr, sizeof(int64_t) * (ng + 1)));
+    MG(hb_dmalloc(&d_gs, sizeof(int64_t) * ng));
+    MG(hb_dmalloc(&d_ge, sizeof(int64_t) * ng));
+    MG(hb_dmalloc(&d_map, sizeof(int32_t) * (size_t)(n > 0 ? n : 1)));
+    MG(hb_dmalloc(&d_cnt, sizeof(int64_t) * (ng + 1)));
+    MG(hb_dmalloc(&d_ptr, sizeof(int64_t) * (ng + 1)));
     MG(cudaMemcpyAsync(d_gs, g_start.data(), sizeof(int64_t) * ng, cudaMemcpyHostToDevice, s));
     MG(cudaMemcpyAsync(d_ge, g_end.data(), sizeof(int64_t) * ng, cudaMemcpyHostToDevice, s));
     if (n > 0) MG(cudaMemcpyAsync(d_map, bin_map, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
@@ -243,8 +243,8 @@ extern "C" int hb_csr_merge_bins(hb_csr* h, const int32_t* bin_map, int64_t n_ne
     MG(cudaMemcpyAsync(&new_nnz, d_ptr + n_new, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     MG(cudaStreamSynchronize(s));
     MG(cudaGetLastError());
-    MG(cudaMalloc(&d_idx, sizeof(int32_t) * (size_t)(new_nnz > 0 ? new_nnz : 1) + 16));
-    MG(cudaMalloc(&d_val, sizeof(double) * (size_t)(new_nnz > 0 ? new_nnz : 1) + 16));
+    MG(hb_dmalloc(&d_idx, sizeof(int32_t) * (size_t)(new_nnz > 0 ? new_nnz : 1) + 16));
+    MG(hb_dmalloc(&d_val, sizeof(double) * (size_t)(new_nnz > 0 ? new_nnz : 1) + 16));
     if (n_new > 0 && new_nnz > 0) {
         hb_merge_rows_kernel<true, false><<<grid, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, nullptr, nullptr, nullptr,
                                                                d_map, d_gs, d_ge, n_new, max_run, nullptr, d_ptr, d_idx, d_val);
@@ -253,14 +253,14 @@ extern "C" int hb_csr_merge_bins(hb_csr* h, const int32_t* bin_map, int64_t n_ne
     MG(cudaStreamSynchronize(s));
     MG(cudaGetLastError());
 #undef MG
-    cudaFree(d_gs);
-    cudaFree(d_ge);
-    cudaFree(d_map);
-    cudaFree(d_cnt);
+    hb_dfree(d_gs);
+    hb_dfree(d_ge);
+    hb_dfree(d_map);
+    hb_dfree(d_cnt);
     if (h->owns_csr) {
-        cudaFree(h->d_indptr);
-        cudaFree(h->d_indices);
-        cudaFree(h->d_data);
+        hb_dfree(h->d_indptr);
+        hb_dfree(h->d_indices);
+        hb_dfree(h->d_data);
     }
     h->owns_csr = true;
     h->phase = 0;
@@ -275,13 +275,13 @@ extern "C" int hb_csr_merge_bins(hb_csr* h, const int32_t* bin_map, int64_t n_ne
     h->seg_off = {0, n_new};
     return hb_build_tiles(h);
 fail:
-    cudaFree(d_gs);
-    cudaFree(d_ge);
-    cudaFree(d_map);
-    cudaFree(d_cnt);
-    cudaFree(d_ptr);
-    cudaFree(d_idx);
-    cudaFree(d_val);
+    hb_dfree(d_gs);
+    hb_dfree(d_ge);
+    hb_dfree(d_map);
+    hb_dfree(d_cnt);
+    hb_dfree(d_ptr);
+    hb_dfree(d_idx);
+    hb_dfree(d_val);
     return rc;
 }
 
@@ -315,8 +315,8 @@ extern "C" int hb_csr_add(hb_csr* h, const hb_csr* other) {
         }                                                         \
     } while (0)
     AD(cudaStreamSynchronize(other->stream));   // whatever produced `other` is complete before this stream reads it
-    AD(cudaMalloc(&d_cnt, sizeof(int64_t) * (nn + 1)));
-    AD(cudaMalloc(&d_ptr, sizeof(int64_t) * (nn + 1)));
+    AD(hb_dmalloc(&d_cnt, sizeof(int64_t) * (nn + 1)));
+    AD(hb_dmalloc(&d_ptr, sizeof(int64_t) * (nn + 1)));
     AD(cudaMemsetAsync(d_cnt, 0, sizeof(int64_t) * (nn + 1), s));
     if (n > 0) {
         hb_merge_rows_kernel<false, true><<<grid, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, other->d_indptr,
@@ -329,8 +329,8 @@ extern "C" int hb_csr_add(hb_csr* h, const hb_csr* other) {
     AD(cudaMemcpyAsync(&new_nnz, d_ptr + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     AD(cudaStreamSynchronize(s));
     AD(cudaGetLastError());
-    AD(cudaMalloc(&d_idx, sizeof(int32_t) * (size_t)(new_nnz > 0 ? new_nnz : 1) + 16));
-    AD(cudaMalloc(&d_val, sizeof(double) * (size_t)(new_nnz > 0 ? new_nnz : 1) + 16));
+    AD(hb_dmalloc(&d_idx, sizeof(int32_t) * (size_t)(new_nnz > 0 ? new_nnz : 1) + 16));
+    AD(hb_dmalloc(&d_val, sizeof(double) * (size_t)(new_nnz > 0 ? new_nnz : 1) + 16));
     if (n > 0 && new_nnz > 0) {
         hb_merge_rows_kernel<true, true><<<grid, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, other->d_indptr,
                                                               other->d_indices, other->d_data, nullptr, nullptr, nullptr, n, 1,
@@ -340,11 +340,11 @@ extern "C" int hb_csr_add(hb_csr* h, const hb_csr* other) {
     AD(cudaStreamSynchronize(s));
     AD(cudaGetLastError());
 #undef AD
-    cudaFree(d_cnt);
+    hb_dfree(d_cnt);
     if (h->owns_csr) {
-        cudaFree(h->d_indptr);
-        cudaFree(h->d_indices);
-        cudaFree(h->d_data);
+        hb_dfree(h->d_indptr);
+        hb_dfree(h->d_indices);
+        hb_dfree(h->d_data);
     }
     h->owns_csr = true;
     h->d_indptr = d_ptr;
@@ -353,9 +353,9 @@ extern "C" int hb_csr_add(hb_csr* h, const hb_csr* other) {
     h->nnz = new_nnz;
     return HB_OK;
 fail:
-    cudaFree(d_cnt);
-    cudaFree(d_ptr);
-    cudaFree(d_idx);
-    cudaFree(d_val);
+    hb_dfree(d_cnt);
+    hb_dfree(d_ptr);
+    hb_dfree(d_idx);
+    hb_dfree(d_val);
     return rc;
 }

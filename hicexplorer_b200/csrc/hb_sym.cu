@@ -261,11 +261,11 @@ int hb_csr_symmetrize_upper(hb_csr* h) {
             goto fail;                                            \
         }                                                         \
     } while (0)
-    SY(cudaMalloc(&d_low, sizeof(unsigned int) * nn));
-    SY(cudaMalloc(&d_cursor, sizeof(unsigned int) * nn));
-    SY(cudaMalloc(&d_flags, sizeof(unsigned int) * 2));
-    SY(cudaMalloc(&d_total, sizeof(int64_t) * (nn + 1)));
-    SY(cudaMalloc(&d_ptr, sizeof(int64_t) * (nn + 1)));
+    SY(hb_dmalloc(&d_low, sizeof(unsigned int) * nn));
+    SY(hb_dmalloc(&d_cursor, sizeof(unsigned int) * nn));
+    SY(hb_dmalloc(&d_flags, sizeof(unsigned int) * 2));
+    SY(hb_dmalloc(&d_total, sizeof(int64_t) * (nn + 1)));
+    SY(hb_dmalloc(&d_ptr, sizeof(int64_t) * (nn + 1)));
     SY(cudaMemsetAsync(d_low, 0, sizeof(unsigned int) * nn, s));
     SY(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned int) * nn, s));
     SY(cudaMemsetAsync(d_flags, 0, sizeof(unsigned int) * 2, s));
@@ -285,8 +285,8 @@ int hb_csr_symmetrize_upper(hb_csr* h) {
         rc = HB_ERR_INVALID_ARG;
         goto fail;
     }
-    SY(cudaMalloc(&d_idx, sizeof(int32_t) * (size_t)(full_nnz > 0 ? full_nnz : 1) + 16));
-    SY(cudaMalloc(&d_val, sizeof(double) * (size_t)(full_nnz > 0 ? full_nnz : 1) + 16));
+    SY(hb_dmalloc(&d_idx, sizeof(int32_t) * (size_t)(full_nnz > 0 ? full_nnz : 1) + 16));
+    SY(hb_dmalloc(&d_val, sizeof(double) * (size_t)(full_nnz > 0 ? full_nnz : 1) + 16));
     if (n > 0 && full_nnz > 0) {
         hb_sym_fill_kernel<<<grid, 256, 0, s>>>(h->d_indptr + 0, h->d_indices, h->d_data, n, d_ptr, d_low, d_cursor, d_idx, d_val);
         g_hb_launches.fetch_add(1);
@@ -313,10 +313,10 @@ int hb_csr_symmetrize_upper(hb_csr* h) {
                 rows.push_back(i);
                 off.push_back(off.back() + P);
             }
-            SY(cudaMalloc(&d_big_rows, sizeof(int64_t) * rows.size()));
-            SY(cudaMalloc(&d_big_off, sizeof(int64_t) * off.size()));
-            SY(cudaMalloc(&d_big_keys, sizeof(unsigned long long) * (size_t)off.back()));
-            SY(cudaMalloc(&d_big_vals, sizeof(double) * (size_t)off.back()));
+            SY(hb_dmalloc(&d_big_rows, sizeof(int64_t) * rows.size()));
+            SY(hb_dmalloc(&d_big_off, sizeof(int64_t) * off.size()));
+            SY(hb_dmalloc(&d_big_keys, sizeof(unsigned long long) * (size_t)off.back()));
+            SY(hb_dmalloc(&d_big_vals, sizeof(double) * (size_t)off.back()));
             SY(cudaMemcpyAsync(d_big_rows, rows.data(), sizeof(int64_t) * rows.size(), cudaMemcpyHostToDevice, s));
             SY(cudaMemcpyAsync(d_big_off, off.data(), sizeof(int64_t) * off.size(), cudaMemcpyHostToDevice, s));
             hb_sym_sort_big_kernel<<<(unsigned)rows.size(), 1024, 0, s>>>(d_ptr, d_low, d_big_rows, d_big_off, d_big_keys,
@@ -328,17 +328,17 @@ int hb_csr_symmetrize_upper(hb_csr* h) {
     SY(cudaStreamSynchronize(s));
     SY(cudaGetLastError());
 #undef SY
-    cudaFree(d_low);
-    cudaFree(d_cursor);
-    cudaFree(d_flags);
-    cudaFree(d_total);
-    cudaFree(d_big_rows);
-    cudaFree(d_big_off);
-    cudaFree(d_big_keys);
-    cudaFree(d_big_vals);
-    cudaFree(h->d_indptr);
-    cudaFree(h->d_indices);
-    cudaFree(h->d_data);
+    hb_dfree(d_low);
+    hb_dfree(d_cursor);
+    hb_dfree(d_flags);
+    hb_dfree(d_total);
+    hb_dfree(d_big_rows);
+    hb_dfree(d_big_off);
+    hb_dfree(d_big_keys);
+    hb_dfree(d_big_vals);
+    hb_dfree(h->d_indptr);
+    hb_dfree(h->d_indices);
+    hb_dfree(h->d_data);
     h->d_indptr = d_ptr;
     h->d_indices = d_idx;
     h->d_data = d_val;
@@ -346,17 +346,17 @@ int hb_csr_symmetrize_upper(hb_csr* h) {
     h->nnz = full_nnz;
     return HB_OK;
 fail:
-    cudaFree(d_low);
-    cudaFree(d_cursor);
-    cudaFree(d_flags);
-    cudaFree(d_total);
-    cudaFree(d_big_rows);
-    cudaFree(d_big_off);
-    cudaFree(d_big_keys);
-    cudaFree(d_big_vals);
-    cudaFree(d_ptr);
-    cudaFree(d_idx);
-    cudaFree(d_val);
+    hb_dfree(d_low);
+    hb_dfree(d_cursor);
+    hb_dfree(d_flags);
+    hb_dfree(d_total);
+    hb_dfree(d_big_rows);
+    hb_dfree(d_big_off);
+    hb_dfree(d_big_keys);
+    hb_dfree(d_big_vals);
+    hb_dfree(d_ptr);
+    hb_dfree(d_idx);
+    hb_dfree(d_val);
     return rc;
 }
 
@@ -427,7 +427,7 @@ int hb_csr_shifted_copy(hb_csr** out, const hb_csr* src, int64_t dr, int64_t dc)
     const size_t nn = (size_t)(n > 0 ? n : 1);
     HbScratch scratch;
     HB_CUDA(scratch.alloc(&d_cnt, sizeof(int64_t) * (nn + 1)));
-    HB_CUDA(cudaMalloc(&d_ptr, sizeof(int64_t) * (nn + 1)));
+    HB_CUDA(hb_dmalloc(&d_ptr, sizeof(int64_t) * (nn + 1)));
     cudaError_t e = cudaMemsetAsync(d_cnt, 0, sizeof(int64_t) * (nn + 1), s);
     if (e == cudaSuccess && n > 0) {
         hb_shift_count_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(src->d_indptr, src->d_indices, n, (int)dr, (int)dc, d_cnt);
@@ -439,8 +439,8 @@ int hb_csr_shifted_copy(hb_csr** out, const hb_csr* src, int64_t dr, int64_t dc)
         e = cudaMemcpyAsync(&nnz, d_ptr + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    if (e == cudaSuccess) e = cudaMalloc(&d_idx, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1) + 16);
-    if (e == cudaSuccess) e = cudaMalloc(&d_val, sizeof(double) * (size_t)(nnz > 0 ? nnz : 1) + 16);
+    if (e == cudaSuccess) e = hb_dmalloc(&d_idx, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1) + 16);
+    if (e == cudaSuccess) e = hb_dmalloc(&d_val, sizeof(double) * (size_t)(nnz > 0 ? nnz : 1) + 16);
     if (e == cudaSuccess && n > 0 && nnz > 0) {
         hb_shift_fill_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(src->d_indptr, src->d_indices, src->d_data, n, (int)dr, (int)dc, d_ptr,
                                                             d_idx, d_val);
@@ -449,16 +449,16 @@ int hb_csr_shifted_copy(hb_csr** out, const hb_csr* src, int64_t dr, int64_t dc)
     }
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
-        cudaFree(d_ptr);
-        cudaFree(d_idx);
-        cudaFree(d_val);
+        hb_dfree(d_ptr);
+        hb_dfree(d_idx);
+        hb_dfree(d_val);
         return hb_cuda_fail(e, "shifted copy", __FILE__, __LINE__);
     }
     rc = hb_dev_csr_wrap(out, n, n, 0, nnz, d_ptr, d_idx, d_val, src->device);
     if (rc != HB_OK) {
-        cudaFree(d_ptr);
-        cudaFree(d_idx);
-        cudaFree(d_val);
+        hb_dfree(d_ptr);
+        hb_dfree(d_idx);
+        hb_dfree(d_val);
         return rc;
     }
     (*out)->owns_csr = true;   // the new handle owns the arrays made here
@@ -495,9 +495,9 @@ int hb_ice_scaled_upper(hb_csr* h, const int64_t* orig_ids, int64_t n_orig, int6
             goto done;                                            \
         }                                                         \
     } while (0)
-    SU(cudaMalloc(&d_orig, sizeof(int64_t) * (size_t)(n > 0 ? n : 1)));
-    SU(cudaMalloc(&d_cnt, sizeof(int64_t) * (size_t)(n_orig + 1)));
-    SU(cudaMalloc(&d_ptr, sizeof(int64_t) * (size_t)(n_orig + 1)));
+    SU(hb_dmalloc(&d_orig, sizeof(int64_t) * (size_t)(n > 0 ? n : 1)));
+    SU(hb_dmalloc(&d_cnt, sizeof(int64_t) * (size_t)(n_orig + 1)));
+    SU(hb_dmalloc(&d_ptr, sizeof(int64_t) * (size_t)(n_orig + 1)));
     if (n > 0) SU(cudaMemcpyAsync(d_orig, orig_ids, sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, s));
     SU(cudaMemsetAsync(d_cnt, 0, sizeof(int64_t) * (size_t)(n_orig + 1), s));
     if (h->n_rows > 0) {
@@ -512,8 +512,8 @@ int hb_ice_scaled_upper(hb_csr* h, const int64_t* orig_ids, int64_t n_orig, int6
     SU(cudaStreamSynchronize(s));
     *nnz_out = total;
     if (indptr != nullptr && indices != nullptr && data != nullptr) {
-        SU(cudaMalloc(&d_idx, sizeof(int32_t) * (size_t)(total > 0 ? total : 1)));
-        SU(cudaMalloc(&d_val, sizeof(double) * (size_t)(total > 0 ? total : 1)));
+        SU(hb_dmalloc(&d_idx, sizeof(int32_t) * (size_t)(total > 0 ? total : 1)));
+        SU(hb_dmalloc(&d_val, sizeof(double) * (size_t)(total > 0 ? total : 1)));
         SU(cudaMemsetAsync(h->d_scalar_bits, 0, sizeof(unsigned long long) * 2, s));
         if (h->n_rows > 0 && total > 0) {
             hb_scaled_upper_kernel<true><<<grid, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, h->n_rows, h->row0, h->d_r,
@@ -539,11 +539,11 @@ int hb_ice_scaled_upper(hb_csr* h, const int64_t* orig_ids, int64_t n_orig, int6
     }
 #undef SU
 done:
-    cudaFree(d_orig);
-    cudaFree(d_cnt);
-    cudaFree(d_ptr);
-    cudaFree(d_idx);
-    cudaFree(d_val);
+    hb_dfree(d_orig);
+    hb_dfree(d_cnt);
+    hb_dfree(d_ptr);
+    hb_dfree(d_idx);
+    hb_dfree(d_val);
     return rc;
 }
 

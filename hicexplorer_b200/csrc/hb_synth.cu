@@ -223,10 +223,10 @@ extern "C" int hb_synth_create(hb_csr** out, const hb_synth_params* prm, const i
         }                                                          \
     } while (0)
     SY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-    SY(cudaMalloc(&d_off, sizeof(int64_t) * off.size()));
-    SY(cudaMalloc(&d_g, sizeof(double) * (size_t)n));
-    SY(cudaMalloc(&d_cnt, sizeof(int64_t) * (size_t)(n_rows + 1)));
-    SY(cudaMalloc(&d_indptr, sizeof(int64_t) * (size_t)(n_rows + 1)));
+    SY(hb_dmalloc(&d_off, sizeof(int64_t) * off.size()));
+    SY(hb_dmalloc(&d_g, sizeof(double) * (size_t)n));
+    SY(hb_dmalloc(&d_cnt, sizeof(int64_t) * (size_t)(n_rows + 1)));
+    SY(hb_dmalloc(&d_indptr, sizeof(int64_t) * (size_t)(n_rows + 1)));
     SY(cudaMemcpyAsync(d_off, off.data(), sizeof(int64_t) * off.size(), cudaMemcpyHostToDevice, s));
     hb_synth_bins_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, d_g);
     g_hb_launches.fetch_add(1);
@@ -238,8 +238,8 @@ extern "C" int hb_synth_create(hb_csr** out, const hb_synth_params* prm, const i
     g_hb_launches.fetch_add(1);
     SY(cudaMemcpyAsync(&nnz, d_indptr + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     SY(cudaStreamSynchronize(s));
-    SY(cudaMalloc(&d_idx, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1) + 16));
-    SY(cudaMalloc(&d_val, sizeof(double) * (size_t)(nnz > 0 ? nnz : 1) + 16));
+    SY(hb_dmalloc(&d_idx, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1) + 16));
+    SY(hb_dmalloc(&d_val, sizeof(double) * (size_t)(nnz > 0 ? nnz : 1) + 16));
     if (n_rows > 0 && nnz > 0) {
         hb_synth_rows_kernel<true><<<grid, 256, 0, s>>>(p, d_off, prm->nchrom, d_g, row0, n_rows, nullptr, d_indptr, d_idx, d_val);
         g_hb_launches.fetch_add(1);
@@ -247,26 +247,26 @@ extern "C" int hb_synth_create(hb_csr** out, const hb_synth_params* prm, const i
     SY(cudaStreamSynchronize(s));
     SY(cudaGetLastError());
 #undef SY
-    cudaFree(d_off);
-    cudaFree(d_g);
-    cudaFree(d_cnt);
+    hb_dfree(d_off);
+    hb_dfree(d_g);
+    hb_dfree(d_cnt);
     cudaStreamDestroy(s);
     rc = hb_dev_csr_wrap(out, n_rows, n, row0, nnz, d_indptr, d_idx, d_val, device);
     if (rc != HB_OK) {
-        cudaFree(d_indptr);
-        cudaFree(d_idx);
-        cudaFree(d_val);
+        hb_dfree(d_indptr);
+        hb_dfree(d_idx);
+        hb_dfree(d_val);
         return rc;
     }
     (*out)->owns_csr = true;  // the generator's buffers now belong to the handle
     return HB_OK;
 fail:
-    cudaFree(d_off);
-    cudaFree(d_g);
-    cudaFree(d_cnt);
-    cudaFree(d_indptr);
-    cudaFree(d_idx);
-    cudaFree(d_val);
+    hb_dfree(d_off);
+    hb_dfree(d_g);
+    hb_dfree(d_cnt);
+    hb_dfree(d_indptr);
+    hb_dfree(d_idx);
+    hb_dfree(d_val);
     if (s) cudaStreamDestroy(s);
     return rc;
 }

@@ -315,14 +315,14 @@ int hb_ice_scaled_row_sums(hb_csr* h, double* out) {
     cudaStream_t s = h->stream;
     if (h->n_rows == 0) return HB_OK;
     double* d_out = nullptr;
-    HB_CUDA(cudaMalloc(&d_out, sizeof(double) * (size_t)h->n_rows));
+    HB_CUDA(hb_dmalloc(&d_out, sizeof(double) * (size_t)h->n_rows));
     hb_scaled_row_sums_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, h->n_rows, h->row0, h->d_r,
                                                              h->d_seg_off, h->d_seg_corr, h->nseg, d_out);
     g_hb_launches.fetch_add(1);
     cudaError_t e = cudaStreamSynchronize(s);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpy(out, d_out, sizeof(double) * (size_t)h->n_rows, cudaMemcpyDeviceToHost);
-    cudaFree(d_out);
+    hb_dfree(d_out);
     if (e != cudaSuccess) return hb_cuda_fail(e, "scaled row sums", __FILE__, __LINE__);
     return HB_OK;
 }

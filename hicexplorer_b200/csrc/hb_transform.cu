@@ -207,7 +207,7 @@ int hb_obs_exp_apply(hb_csr* h, const double* expected, int index_mode, int out_
     hb_drop_pack(h);
     const size_t n = (size_t)(h->n_cols > 0 ? h->n_cols : 1);
     double* d_buf = nullptr;
-    HB_CUDA(cudaMalloc(&d_buf, sizeof(double) * (2 * n + (size_t)h->nseg)));
+    HB_CUDA(hb_dmalloc(&d_buf, sizeof(double) * (2 * n + (size_t)h->nseg)));
     double* d_rs = row_sum ? d_buf + n : nullptr;
     double* d_tot = row_sum ? d_buf + 2 * n : nullptr;
     cudaError_t e = cudaMemcpyAsync(d_buf, expected, sizeof(double) * n, cudaMemcpyHostToDevice, s);
@@ -220,7 +220,7 @@ int hb_obs_exp_apply(hb_csr* h, const double* expected, int index_mode, int out_
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e == cudaSuccess) e = cudaGetLastError();
-    cudaFree(d_buf);
+    hb_dfree(d_buf);
     if (e != cudaSuccess) return hb_cuda_fail(e, "obs/exp", __FILE__, __LINE__);
     return HB_OK;
 }

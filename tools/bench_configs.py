@@ -43,11 +43,6 @@ def lpt(weights, world):
 def main():
     import torch
     import torch.distributed as dist
-    from hicexplorer_b200 import _lib
-    from hicexplorer_b200.dist import attach_comm, attach_peer, nnz_balanced_partition
-    from hicexplorer_b200.store import DeviceCSR
-    L = _lib.lib()
-    check = _lib.check
     config = sys.argv[1] if len(sys.argv) > 1 else "perchr5k"
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -55,6 +50,26 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    out = run(config)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run(config):
+    """one configuration on the already initialised process group (or a single GPU); every rank calls it, the returned
+    dict is complete on rank 0"""
+    import torch
+    import torch.distributed as dist
+    from hicexplorer_b200 import _lib
+    from hicexplorer_b200.dist import attach_comm, attach_peer, nnz_balanced_partition
+    from hicexplorer_b200.store import DeviceCSR
+    L = _lib.lib()
+    check = _lib.check
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
 
     def barrier():
         if world > 1:
@@ -316,10 +331,7 @@ def main():
                                       if peer_mode else "1 NCCL sum-allreduce of %d fp64 per mat-vec/iteration" % n)})
         dev.close()
         del keep
-    if rank == 0:
-        print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    return out
 
 
 if __name__ == "__main__":
