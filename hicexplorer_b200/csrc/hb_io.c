@@ -331,7 +331,14 @@ static int64_t blosclz_encode(const uint8_t* ip, int64_t length, uint8_t* op, in
     } while (0)
     /* the stream has to open with a literal (the decoder masks the first control byte to 5 bits) */
     i = 1;
+    const int64_t probe = length / 8 > 256 ? length / 8 : 256;   /* give up early on byte planes that do not compress */
+    int probed = 0;
     while (i < last) {
+        if (!probed && i >= probe) {
+            probed = 1;
+            /* (mantissa planes of floating-point values: no matches, the stream would be stored anyway) */
+            if ((op - op_start) + (i - anchor) > i - i / 32) return 0;
+        }
         const uint32_t h = hbio_hash3(ip + i);
         const int32_t cand = htab[h];
         htab[h] = (int32_t)i;

@@ -822,14 +822,27 @@ class Writer(object):
         tmp_path = "%s.tmp%d" % (path, os.getpid())
         fd = os.open(tmp_path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
         pos = [96]                       # the superblock goes to offset 0 at the end
-        big = []                         # (offset, byte view) of multi-megabyte payloads, written by a thread pool
+        # multi-megabyte payloads go to a small pool of writer threads right away (page-cache copies of a single write()
+        # run at a few GB/s; several threads on disjoint regions scale) and overlap the encoding of the next batch
+        from concurrent.futures import ThreadPoolExecutor
+        writers = ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1))
+        pending = []
+
+        def put(off, view):
+            while view.nbytes:
+                done = os.pwrite(fd, view, off)
+                off += done
+                view = view[done:]
 
         def alloc(blob):
             pos[0] += (-pos[0]) % 8
             addr = pos[0]
             nbytes = blob.nbytes if isinstance(blob, memoryview) else len(blob)
             if nbytes >= (32 << 20):
-                big.append((addr, blob))
+                step = 64 << 20
+                view = blob if isinstance(blob, memoryview) else memoryview(blob)
+                for o in range(0, nbytes, step):
+                    pending.append(writers.submit(put, addr + o, view[o:o + step]))
             else:
                 os.pwrite(fd, blob, addr)
             pos[0] += nbytes
@@ -953,20 +966,8 @@ class Writer(object):
         sb += struct.pack("<QQQQ", 0, _UNDEF, eof, _UNDEF)
         sb += struct.pack("<QQII", 0, root_hdr, 1, 0) + struct.pack("<QQ", root_btree, root_heap)
         os.pwrite(fd, bytes(sb), 0)
-        if big:
-            # page-cache copies of a single write() run at a few GB/s; several threads on disjoint regions scale
-            from concurrent.futures import ThreadPoolExecutor
-            step = 64 << 20
-            jobs = [(addr + o, blob[o:o + step]) for addr, blob in big for o in range(0, blob.nbytes, step)]
-
-            def put(job):
-                off, view = job
-                while view.nbytes:
-                    done = os.pwrite(fd, view, off)
-                    off += done
-                    view = view[done:]
-
-            with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
-                list(pool.map(put, jobs))
+        for fut in pending:
+            fut.result()
+        writers.shutdown()
         os.close(fd)
         os.replace(tmp_path, path)
