@@ -95,6 +95,8 @@ SIGNATURES = {
     "hb_csr_shifted_copy": (c_int, [P(vp), vp, c_i64, c_i64]),
     "hb_csr_merge_bins": (c_int, [vp, vp, c_i64]),
     "hb_symmetry": (c_int, [vp, P(c_dbl)]),
+    "hb_dev_extract_cols": (c_int, [vp, c_i64, c_i64, P(c_i64), vp, vp, vp]),
+    "hb_dev_partner_sums": (c_int, [vp, c_i64, vp, vp, vp, P(c_dbl)]),
     "hb_ice_run": (c_int, [vp, c_int, c_dbl, vp, vp, vp]),
     "hb_ice_scaled_values": (c_int, [vp, vp, P(c_dbl)]),
     "hb_ice_scaled_upper": (c_int, [vp, vp, c_i64, P(c_i64), vp, vp, vp]),

@@ -571,6 +571,97 @@ hb_symmetry_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict
     }
 }
 
+// ---- exact |M - M^T| on row blocks ------------------------------------------------------------------------------------
+// The partner of entry (i, j) lives in the row block that owns row j.  Every rank hands the owner of each column range
+// the entries it stores there (hb_dev_extract_cols: (row, col, value) triplets, any order); the owner looks every
+// received a_ij up in its own row j (hb_dev_partner_sums) and adds |a_ij - a_ji|, or 2 |a_ij| when it stores no a_ji --
+// the cell (j, i) then contributes the same amount and nobody else visits it.  Summed over all ranks this is
+// sum |M - M^T| over all cells, the numerator of iterativeCorrection.py:35.  The host moves the triplets (all-to-all).
+__global__ void __launch_bounds__(256)
+hb_extract_cols_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
+                       int64_t n_rows, int64_t row0, int col_lo, int col_hi, unsigned long long* cursor, int32_t* __restrict__ rows,
+                       int32_t* __restrict__ cols, double* __restrict__ vals) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = gwarp; row < n_rows; row += nwarps) {
+        const int64_t e = indptr[row + 1];
+        for (int64_t base = indptr[row]; base < e; base += 32) {
+            const int64_t k = base + lane;
+            const int c = k < e ? idx[k] : -1;
+            const bool take = c >= col_lo && c < col_hi;
+            const unsigned int bal = __ballot_sync(0xffffffffu, take);
+            if (bal == 0) continue;
+            unsigned long long at = 0;
+            if (lane == 0) at = atomicAdd(cursor, (unsigned long long)__popc(bal));
+            at = __shfl_sync(0xffffffffu, at, 0);
+            if (take && rows != nullptr) {
+                const unsigned long long p = at + __popc(bal & ((1u << lane) - 1u));
+                rows[p] = (int32_t)(row0 + row);
+                cols[p] = c;
+                vals[p] = val[k];
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+hb_partner_sums_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
+                       int64_t n_rows, int64_t row0, int64_t n, const int32_t* __restrict__ rows, const int32_t* __restrict__ cols,
+                       const double* __restrict__ vals, double* sum_out) {
+    double sd = 0.0;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = (int64_t)cols[t] - row0;   // local row that owns the partner
+        const double a = vals[t];
+        if (j < 0 || j >= n_rows) {
+            sd += 2.0 * fabs(a);                     // (cannot happen when the host routed the triplets by owner)
+            continue;
+        }
+        const int64_t pos = hb_find_col(idx, indptr[j], indptr[j + 1], rows[t]);
+        sd += pos >= 0 ? fabs(a - val[pos]) : 2.0 * fabs(a);
+    }
+    sd = hb_warp_sum(sd);
+    if ((threadIdx.x & 31) == 0 && sd != 0.0) atomicAdd(sum_out, sd);
+}
+
+extern "C" int hb_dev_extract_cols(hb_csr* h, int64_t col_lo, int64_t col_hi, int64_t* count_out, int32_t* d_rows, int32_t* d_cols,
+                                   double* d_vals) {
+    HB_REQUIRE(h != nullptr && count_out != nullptr && col_lo >= 0 && col_lo <= col_hi && col_hi <= h->n_cols, "bad arguments");
+    HB_REQUIRE((d_rows == nullptr) == (d_cols == nullptr) && (d_rows == nullptr) == (d_vals == nullptr), "all three outputs or none");
+    int rc = hb_ensure_state(h);
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    HB_CUDA(cudaMemsetAsync(h->d_scalar_bits, 0, sizeof(unsigned long long), s));
+    if (h->n_rows > 0 && h->nnz > 0) {
+        hb_extract_cols_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, h->n_rows, h->row0, (int)col_lo,
+                                                              (int)col_hi, h->d_scalar_bits, d_rows, d_cols, d_vals);
+        HB_LAUNCH_CHECK();
+    }
+    unsigned long long c = 0;
+    HB_CUDA(cudaMemcpyAsync(&c, h->d_scalar_bits, sizeof(c), cudaMemcpyDeviceToHost, s));
+    HB_CUDA(cudaStreamSynchronize(s));
+    *count_out = (int64_t)c;
+    return HB_OK;
+}
+
+extern "C" int hb_dev_partner_sums(hb_csr* h, int64_t n, const int32_t* d_rows, const int32_t* d_cols, const double* d_vals,
+                                   double* sum_out) {
+    HB_REQUIRE(h != nullptr && sum_out != nullptr && n >= 0, "bad arguments");
+    int rc = hb_ensure_state(h);
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    double* d_sum = reinterpret_cast<double*>(h->d_scalar_bits + 2);
+    HB_CUDA(cudaMemsetAsync(d_sum, 0, sizeof(double), s));
+    if (n > 0) {
+        hb_partner_sums_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(h->d_indptr, h->d_indices, h->d_data, h->n_rows, h->row0, n, d_rows,
+                                                              d_cols, d_vals, d_sum);
+        HB_LAUNCH_CHECK();
+    }
+    HB_CUDA(cudaMemcpyAsync(sum_out, d_sum, sizeof(double), cudaMemcpyDeviceToHost, s));
+    HB_CUDA(cudaStreamSynchronize(s));
+    return HB_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // lossless narrow copy of the values for the streaming kernels
 // ---------------------------------------------------------------------------------------------
@@ -870,10 +961,10 @@ int hb_symmetry(hb_csr* h, double* ratio_out) {
                 *ratio_out = 0.0;
                 return HB_OK;
             }
-            // The exact ratio needs every entry's transposed partner, which lives in another rank's block.  Row blocks
-            // therefore accept exactly symmetric matrices only (what a symmetric fill of a file's upper triangle
-            // gives); the reference would still accept a relative asymmetry below 1e-10 (iterativeCorrection.py:35).
-            hb_set_error("the matrix is not exactly symmetric (row-block check)");
+            // The exact ratio needs every entry's transposed partner, which lives in another rank's block: the host
+            // moves the entries to their partners' owners and calls hb_dev_extract_cols / hb_dev_partner_sums
+            // (store.py: symmetry_ratio_sharded) -- the reference accepts a relative asymmetry below 1e-10.
+            hb_set_error("the matrix is not exactly symmetric (row-block screen); the exact ratio needs the block exchange");
             *ratio_out = 1.0;
             return HB_ERR_NOT_SYMMETRIC;
         }

@@ -274,8 +274,9 @@ def ice_pipeline_sharded(matrix, filter_threshold, max_iter=500, tolerance=1e-5,
                          skip_diagonal=False, want_matrix=True, file_layout=False, upper_input=False, drop_mask=None,
                          extra_mask_fn=None, trans_cutoff=None, clip_trans=False, inflation_cutoff=None):
     """ice_pipeline on row blocks across the initialised torch.distributed group (NCCL).  The symmetry test is the
-    exact-symmetry digest screen summed over the blocks (one tiny allreduce); a matrix that is not exactly symmetric is
-    rejected (the exact ratio would need the transposed entries of other blocks).
+    exact-symmetry digest screen summed over the blocks (one tiny allreduce); only a matrix that is not exactly symmetric
+    pays for the reference's ratio (iterativeCorrection.py:35): one all-to-all that brings every entry to the owner of its
+    transposed partner (DeviceCSR.symmetry_ratio_sharded).
 
     ``file_layout``: every rank emits its rows of the corrected matrix already in file layout (upper triangle, zeros
     eliminated, original frame: hb_ice_scaled_upper works on a row block) and rank 0 concatenates the blocks -> ``upper``;
@@ -341,7 +342,7 @@ def ice_pipeline_sharded(matrix, filter_threshold, max_iter=500, tolerance=1e-5,
                              "hicCorrectMatrix.py:699, 771)")
         if perchr:
             dev.keep_cis()
-        if dev.symmetry_ratio() > 1e-10:
+        if dev.symmetry_ratio_sharded(dist, rank, world) > 1e-10:   # exact screen; exact ratio via a block exchange if needed
             raise ValueError("Please provide symmetric matrix!")
         dev.pack_values()
         bias, iters, deviation = dev.ice(max_iter, tolerance)  # one exchange per iteration

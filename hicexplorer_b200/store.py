@@ -337,6 +337,58 @@ class DeviceCSR(object):
         check(rc)
         return r.value
 
+    def symmetry_ratio_sharded(self, dist, rank, world):
+        """iterativeCorrection.py:35 on row blocks.  The exact-symmetry screen first (one tiny allreduce); only a matrix
+        that is not identical to its transpose pays for the exact ratio: every rank sends each entry to the owner of its
+        column (one all-to-all of (row, column, value) triplets over NCCL), the owners sum |a_ij - a_ji|."""
+        import torch
+        r = self.symmetry_ratio()
+        if r == 0.0:
+            return 0.0
+        n_rows, n_cols, row0, _nnz = self.dims()
+        span = torch.zeros(world + 1, dtype=torch.int64, device="cuda")
+        span[rank] = row0
+        if rank == world - 1:
+            span[world] = row0 + n_rows
+        dist.all_reduce(span)
+        bounds = span.cpu().numpy()
+        L = lib()
+        counts = np.zeros(world, dtype=np.int64)
+        cnt = ctypes.c_int64()
+        for q in range(world):
+            check(L.hb_dev_extract_cols(self._h, int(bounds[q]), int(bounds[q + 1]), ctypes.byref(cnt), None, None, None))
+            counts[q] = cnt.value
+        total = int(counts.sum())
+        rows = torch.empty(max(total, 1), dtype=torch.int32, device="cuda")
+        cols = torch.empty(max(total, 1), dtype=torch.int32, device="cuda")
+        vals = torch.empty(max(total, 1), dtype=torch.float64, device="cuda")
+        off = np.concatenate([[0], np.cumsum(counts)])
+        for q in range(world):
+            if counts[q]:
+                a = int(off[q])
+                check(L.hb_dev_extract_cols(self._h, int(bounds[q]), int(bounds[q + 1]), ctypes.byref(cnt),
+                                            ctypes.c_void_p(rows.data_ptr() + 4 * a), ctypes.c_void_p(cols.data_ptr() + 4 * a),
+                                            ctypes.c_void_p(vals.data_ptr() + 8 * a)))
+        send = torch.from_numpy(counts).cuda()
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send)
+        recv_counts = recv.cpu().numpy()
+        n_in = int(recv_counts.sum())
+        got = []
+        for t in (rows, cols, vals):
+            buf = torch.empty(max(n_in, 1), dtype=t.dtype, device="cuda")
+            dist.all_to_all_single(buf[:n_in], t[:total], [int(c) for c in recv_counts], [int(c) for c in counts])
+            got.append(buf)
+        torch.cuda.current_stream().synchronize()   # the collectives ran on torch's stream, the look-up runs on the handle's
+        part = ctypes.c_double()
+        check(L.hb_dev_partner_sums(self._h, n_in, ctypes.c_void_p(got[0].data_ptr()), ctypes.c_void_p(got[1].data_ptr()),
+                                    ctypes.c_void_p(got[2].data_ptr()), ctypes.byref(part)))
+        sums = torch.tensor([part.value, float(self.value_stats()[0])], dtype=torch.float64, device="cuda")
+        dist.all_reduce(sums)
+        num, den = float(sums[0].item()), abs(float(sums[1].item()))
+        cells = float(n_cols) * float(n_cols)
+        return (num / cells) / (den / cells) if den else float("inf")
+
     # ---- ICE ------------------------------------------------------------------
     def ice(self, max_iter=50, tolerance=1e-5):
         """Returns (bias[n], iterations[nseg], deviation[nseg]).  Raises OverflowIter."""

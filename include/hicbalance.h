@@ -196,6 +196,16 @@ HB_API int hb_diag_zero(hb_csr* h);
 /* keep only the upper triangle (column >= row) of the block: the file layout (inverse of hb_csr_create_upper) */
 HB_API int hb_csr_keep_upper(hb_csr* h);
 HB_API int hb_symmetry(hb_csr* h, double* ratio_out);
+/* Exact sum |M - M^T| on row blocks (the numerator of iterativeCorrection.py:35 when hb_symmetry's exact-symmetry
+ * screen says "not identical" on a sharded matrix).  hb_dev_extract_cols: the block's entries whose column lies in
+ * [col_lo, col_hi) as DEVICE triplets (global row, column, value), any order; call once with NULL outputs for the
+ * count.  The host sends them to the rank that owns those rows; hb_dev_partner_sums looks every received entry
+ * a_ij up in the local row j and returns sum of |a_ij - a_ji| (2 |a_ij| where a_ji is not stored).  Summed over the
+ * ranks, divided by sum M: the reference's ratio. */
+HB_API int hb_dev_extract_cols(hb_csr* h, int64_t col_lo, int64_t col_hi, int64_t* count_out, int32_t* d_rows, int32_t* d_cols,
+                               double* d_vals);
+HB_API int hb_dev_partner_sums(hb_csr* h, int64_t n, const int32_t* d_rows, const int32_t* d_cols, const double* d_vals,
+                               double* sum_out);
 
 /* ---- bin merging (the step before correction) ----------------------------------
  * Replaces reduce_matrix(matrix, bins_to_merge, use_triu=True, diagonal=True) (hicexplorer/reduceMatrix.py:12-232)

@@ -85,6 +85,27 @@ def main():
                           np.array_equal(pb, b1) and int(pit[0]) == int(it1[0]))
                     check("peer exchange: KR x bit-identical to 1 GPU, %d mat-vecs" % mv1, np.array_equal(px, x1) and pmv == mv1)
         dist.barrier()
+    # the reference's tolerant symmetry test (iterativeCorrection.py:35) on row blocks: exact ratio through the block exchange
+    from hicexplorer_b200.dist import attach_comm
+    for delta, accept in ((1e-3, True), (25.0, False)):
+        skew = ice_in.copy().tolil()
+        i0, j0 = 3, int(ice_in[3].indices[ice_in[3].indices > 3][0])
+        skew[i0, j0] = skew[i0, j0] + delta                     # one entry differs from its mirror image
+        skew = sparse.csr_matrix(skew)
+        skew.sort_indices()
+        bounds = nnz_balanced_partition(skew.indptr, world)
+        with DeviceCSR.from_scipy(skew, device=local, row_range=(int(bounds[rank]), int(bounds[rank + 1]))) as dv:
+            keep_cb = attach_comm(dv, rank, world)
+            ratio_n = dv.symmetry_ratio_sharded(dist, rank, world)
+            del keep_cb
+        if rank == 0:
+            with DeviceCSR.from_scipy(skew, device=local) as d1:
+                ratio_1 = d1.symmetry_ratio()
+            want = abs(skew - skew.T).mean() / abs(skew.mean())
+            check("asymmetric input (delta %g): sharded ratio %.3e == single-GPU ratio == numpy, %s like the reference"
+                  % (delta, ratio_n, "accepted" if accept else "rejected"),
+                  abs(ratio_n / ratio_1 - 1) < 1e-9 and abs(ratio_n / want - 1) < 1e-9 and (ratio_n <= 1e-10) == accept)
+        dist.barrier()
     kr = kr_pipeline_sharded(full, rescale=True)
     if rank == 0:
         kref = kr_pipeline(full, rescale=True, want_matrix=False, device=local)
