@@ -210,11 +210,11 @@ int hb_csr_create_typed(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t ro
             const unsigned char* src = static_cast<const unsigned char*>(data_any) + elt * (size_t)indptr[0];
             const int64_t chunk = (int64_t)1 << 26;
             void* d_tmp = nullptr;
-            HB_CREATE_CUDA(hb_dmalloc(&d_tmp, elt * (size_t)(nnz < chunk ? nnz : chunk)));
+            HbScratch staging;   // released on every exit path
+            HB_CREATE_CUDA(staging.alloc(&d_tmp, elt * (size_t)(nnz < chunk ? nnz : chunk)));
             for (int64_t o = 0; o < nnz; o += chunk) {
                 const int64_t m = nnz - o < chunk ? nnz - o : chunk;
                 if (hb_copy_h2d(d_tmp, src + elt * (size_t)o, elt * (size_t)m, device) != HB_OK) {
-                    hb_dfree(d_tmp);
                     hb_csr_destroy(h);
                     *out = nullptr;
                     return HB_ERR_CUDA;
@@ -227,28 +227,23 @@ int hb_csr_create_typed(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t ro
                 else
                     hb_widen_values_kernel<long long><<<HB_NUM_SMS * 8, 256, 0, s>>>((const long long*)d_tmp, dst, m);
                 g_hb_launches.fetch_add(1);
-                cudaError_t ce = cudaStreamSynchronize(s);   // the staging buffer is reused by the next chunk
-                if (ce != cudaSuccess) {
-                    hb_dfree(d_tmp);
-                    HB_CREATE_CUDA(ce);
-                }
+                HB_CREATE_CUDA(cudaStreamSynchronize(s));   // the staging buffer is reused by the next chunk
             }
-            hb_dfree(d_tmp);
         }
         if (indices_i64) {
             // krbalancing's constructor takes int64 indices (hicCorrectMatrix.py:744-747): narrow on the device
             const int64_t* src = (const int64_t*)indices + indptr[0];
             const int64_t chunk = (int64_t)1 << 26;
             int64_t* d_tmp = nullptr;
-            HB_CREATE_CUDA(hb_dmalloc(&d_tmp, sizeof(int64_t) * (size_t)(nnz < chunk ? nnz : chunk)));
+            HbScratch staging;   // released on every exit path
+            HB_CREATE_CUDA(staging.alloc(&d_tmp, sizeof(int64_t) * (size_t)(nnz < chunk ? nnz : chunk)));
             for (int64_t o = 0; o < nnz; o += chunk) {
                 int64_t m = nnz - o < chunk ? nnz - o : chunk;
                 HB_CREATE_CUDA(cudaMemcpyAsync(d_tmp, src + o, sizeof(int64_t) * (size_t)m, cudaMemcpyHostToDevice, s));
                 hb_narrow_indices_kernel<<<HB_NUM_SMS * 8, 256, 0, s>>>(d_tmp, h->d_indices + phase + o, m);
                 g_hb_launches.fetch_add(1);
+                HB_CREATE_CUDA(cudaStreamSynchronize(s));   // the staging buffer is reused by the next chunk
             }
-            HB_CREATE_CUDA(cudaStreamSynchronize(s));
-            hb_dfree(d_tmp);
         } else {
             if (hb_copy_h2d(h->d_indices + phase, (const int32_t*)indices + indptr[0], sizeof(int32_t) * (size_t)nnz,
                             device) != HB_OK) {
