@@ -9,7 +9,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libhicbalance.so")
-SOURCES = ["hb_core.cu", "hb_ice.cu", "hb_filter.cu", "hb_kr.cu", "hb_synth.cu", "hb_merge.cu", "hb_xfer.cu", "hb_sym.cu", "hb_trans.cu", "hb_elem.cu", "hb_transform.cu"]
+SOURCES = ["hb_core.cu", "hb_ice.cu", "hb_filter.cu", "hb_kr.cu", "hb_synth.cu", "hb_merge.cu", "hb_xfer.cu", "hb_sym.cu", "hb_trans.cu", "hb_elem.cu", "hb_transform.cu", "hb_dense.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xptxas", "-v"]
 
@@ -62,7 +62,7 @@ def build(force=False, verbose=False, defines=None, out=None):
         fh.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
     subprocess.check_call(cmd)
     if out is None:
         build_io()

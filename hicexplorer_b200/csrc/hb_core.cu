@@ -665,6 +665,9 @@ void hb_free_state(hb_csr* h) {
     hb_dfree(h->d_state_slab);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     hb_dfree(h->d_kr_buf);
+    hb_dfree(h->d_dense);
+    h->d_dense = nullptr;
+    h->dense_m = 0;
     h->d_state_slab = nullptr;
     h->h_pinned = nullptr;
     h->d_kr_buf = nullptr;

@@ -146,6 +146,8 @@ struct hb_csr {
     double* d_kr_buf = nullptr;        // Knight-Ruiz workspace (8 n-vectors + tile partials + scalars), kept across calls
     size_t kr_buf_words = 0;
     double* h_kr_sc = nullptr;         // pinned mirror of the KR scalars
+    double* d_dense = nullptr;         // hb_block_correlation: the dense block between its two calls
+    int64_t dense_m = 0;
 };
 
 // Every device allocation of the library goes through these two (hb_core.cu); the peer regions alone call cudaMalloc

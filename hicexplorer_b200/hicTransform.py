@@ -9,8 +9,9 @@ value (``hb_obs_exp_apply``).  The O(n) step in between uses the reference's own
 ``ceil(d / 2)`` (utilities.py:364, 489, 581); the quotient is cast back to the input dtype (integer count matrices are
 truncated), ``--perChromosome`` assembles into a float64 ``lil_matrix`` and ``obs_exp_non_zero`` yields float32.
 
-``pearson`` and ``covariance`` (dense n x n results through ``np.corrcoef`` / ``np.cov``) are not part of the sparse path
-and exit with an explanation.
+``pearson`` and ``covariance`` (``np.corrcoef`` / ``np.cov`` of the dense matrix or, with ``--perChromosome``, of every
+chromosome block; hicTransform.py:105-113, 213-248) densify the block on the device, take the product with one fp64
+cuBLAS DGEMM and return the non-zero cells (``hb_block_correlation``).
 """
 import argparse
 import logging
@@ -102,6 +103,16 @@ def obs_exp_transform(matrix, method, chr_offsets, per_chromosome=False, ligatio
     return out
 
 
+def correlation_transform(matrix, method, chr_offsets, per_chromosome=False, device=0):
+    """the pearson / covariance branches of hicTransform.main (:213-248) for a loaded full symmetric matrix"""
+    import scipy.sparse as sp
+    n = matrix.shape[0]
+    offsets = np.asarray(chr_offsets, dtype=np.int64) if per_chromosome else np.asarray([0, n], dtype=np.int64)
+    with DeviceCSR.from_scipy(matrix, device=device) as dev:
+        blocks = [dev.block_correlation(lo, hi, pearson=(method == 'pearson')) for lo, hi in zip(offsets[:-1], offsets[1:])]
+    return sp.vstack(blocks, format='csr') if blocks else sp.csr_matrix((n, n), dtype=np.float64)
+
+
 def main(args=None):
     args = parse_arguments().parse_args(args)
     if not args.outFileName.endswith('.h5') and not args.outFileName.endswith('.cool'):
@@ -109,18 +120,18 @@ def main(args=None):
         log.error('It is: {}'.format(args.outFileName))
         log.error('Accepted is .h5 or .cool')
         sys.exit(1)
-    if args.method in ('pearson', 'covariance'):
-        log.error('--method {} produces a dense n x n matrix (np.corrcoef / np.cov) and is not part of the sparse path of '
-                  'the B200 build; use the reference tool for it.'.format(args.method))
-        sys.exit(1)
     if args.matrix.endswith('cool') and args.chromosomes is not None and len(args.chromosomes) == 1:
         hic_ma = hm.hiCMatrix(pMatrixFile=args.matrix, pChrnameList=args.chromosomes)
     else:
         hic_ma = hm.hiCMatrix(pMatrixFile=args.matrix)
         if args.chromosomes:
             hic_ma.keepOnlyTheseChr([str(c) for c in args.chromosomes])     # file order kept (hicTransform.py:156)
-    result = obs_exp_transform(hic_ma.matrix, args.method, hic_ma.chromosome_offsets(), per_chromosome=args.perChromosome,
-                               ligation_factor=args.ligation_factor, device=args.device)
+    if args.method in ('pearson', 'covariance'):
+        result = correlation_transform(hic_ma.matrix, args.method, hic_ma.chromosome_offsets(), per_chromosome=args.perChromosome,
+                                       device=args.device)
+    else:
+        result = obs_exp_transform(hic_ma.matrix, args.method, hic_ma.chromosome_offsets(), per_chromosome=args.perChromosome,
+                                   ligation_factor=args.ligation_factor, device=args.device)
     hic_ma.matrix = result
     hic_ma.value_dtype = result.dtype
     hic_ma.save(args.outFileName, pSymmetric=True, pApplyCorrection=False)

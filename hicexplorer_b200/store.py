@@ -453,6 +453,22 @@ class DeviceCSR(object):
         tot = None if seg_total is None else np.ascontiguousarray(seg_total, dtype=np.float64)
         check(lib().hb_obs_exp_apply(self._h, ptr(ex), int(index_mode), int(out_mode), ptr(rs), ptr(tot)))
 
+    # ---- hicTransform covariance / pearson -----------------------------------------
+    def block_correlation(self, lo, hi, pearson=False):
+        """np.cov / np.corrcoef of the dense diagonal block [lo, hi) (hicTransform.py:105-113, 236) as a scipy CSR of
+        its non-zero cells: shape (hi - lo, n), columns in the frame of the whole matrix"""
+        import scipy.sparse as sp
+        lo, hi = int(lo), int(hi)
+        nnz = ctypes.c_int64()
+        check(lib().hb_block_correlation(self._h, lo, hi, int(bool(pearson)), ctypes.byref(nnz), None, None, None))
+        indptr = np.zeros(hi - lo + 1, dtype=np.int64)
+        indices = np.empty(nnz.value, dtype=np.int32)
+        data = np.empty(nnz.value, dtype=np.float64)
+        if hi > lo:
+            check(lib().hb_block_correlation(self._h, lo, hi, int(bool(pearson)), ctypes.byref(nnz), ptr(indptr), ptr(indices),
+                                             ptr(data)))
+        return sp.csr_matrix((data, indices, indptr), shape=(hi - lo, self.n))
+
     # ---- optional steps around ICE (--transCutoff / --inflationCutoff) ------------
     def trans_percentile(self, chr_offsets, q):
         """np.percentile(values stored between chromosomes, q) -- what hicmatrix truncTrans computes

@@ -276,6 +276,18 @@ HB_API int hb_distance_stats(hb_csr* h, double* sums_out, int64_t* counts_out);
 HB_API int hb_obs_exp_apply(hb_csr* h, const double* expected, int index_mode, int out_mode, const double* row_sum,
                      const double* seg_total);
 
+/* ---- covariance / Pearson correlation (hicTransform --method covariance | pearson) -----------------------
+ * Replaces np.cov(submatrix.todense()) / np.corrcoef(...) + convertNansToZeros + convertInfsToZeros + csr_matrix(...)
+ * (hicexplorer/hicTransform.py:105-113), per chromosome block [lo, hi) (hicTransform.py:213-248) or on the whole matrix
+ * (lo = 0, hi = n).  Rows of the block are the variables, its columns the observations, ddof = 1; pearson != 0 divides by
+ * the standard deviations and clips to [-1, 1] like np.corrcoef.  The block is densified on the device (16 m^2 bytes)
+ * and the product is one fp64 cuBLAS DGEMM (libcublas is opened at run time).  Two calls: with indptr = indices = data
+ * = NULL the block is computed and kept, *nnz_out = number of non-zero cells; the second call (same lo, hi) fills
+ * indptr[m+1] (block-local rows), indices (GLOBAL columns, ascending) and data, and releases the block.  Full matrix on
+ * one device. */
+HB_API int hb_block_correlation(hb_csr* h, int64_t lo, int64_t hi, int pearson, int64_t* nnz_out, int64_t* indptr,
+                         int32_t* indices, double* data);
+
 /* ---- optional ICE-only steps around the correction -----------------------------
  * --transCutoff (hicCorrectMatrix.py:695-699 -> hicmatrix truncTrans): trans entries are those whose row and column lie
  * in different chromosomes (chr_offsets[nchr+1], ascending, in the CURRENT bin frame).

@@ -6,6 +6,10 @@
 * ``obs_exp`` / ``obs_exp_non_zero`` / ``obs_exp_lieberman`` <- ``:554-600``, ``:500-551``, ``:479-497`` followed by the
   NaN/Inf scrub + eliminate_zeros of ``hicTransform.py:93-141`` (``_obs_exp`` and friends)
 * ``transform``             <- the method / --perChromosome dispatch of ``hicTransform.py:162-215``
+* ``covariance`` / ``pearson`` / ``correlation_transform`` <- ``hicTransform.py:105-113, 213-248``: ``np.cov`` /
+  ``np.corrcoef`` of the dense block (numpy itself is the dependency that holds the algorithm: ``np.cov`` centres the
+  rows, takes ``X @ X.T`` and multiplies by ``1 / (m - 1)``; ``np.corrcoef`` divides by the standard deviations, rows
+  then columns, and clips to [-1, 1])
 
 Quirks kept on purpose: the expected value of ``obs_exp`` and ``obs_exp_lieberman`` is looked up at ``ceil(d / 2)``
 (``:489, :581``), ``obs_exp`` divides the distance sums by ``n + 1 - d`` (``occurrences``, ``:364``), and the quotient is
@@ -15,6 +19,10 @@ Pinned (tests/test_oracle.py): equal to the reference's own functions (imported 
 container) bit for bit on its test matrices and on random input; the golden vectors produced by those functions are
 committed in tests/golden/transform_small.npz; the reference's golden files (``test_data/hicTransform/*.cool``) are
 matched to the tolerance of the reference's own tests (``decimal=0``; they were written by an older code version).
+``correlation_transform(..., "covariance", per_chromosome=True)`` reproduces the reference's golden file
+``test_data/hicTransform/covariance_perChromosome.h5`` (same 572 647 upper-triangle cells, values to 1.4e-14;
+tests/golden/transform_cov.npz); the reference holds no golden file for ``pearson``, whose vectors in the same npz come
+from the reference's own ``_pearson`` run in the build container.
 """
 import numpy as np
 from scipy import sparse
@@ -140,3 +148,36 @@ def transform(matrix, method, chr_offsets=None, per_chromosome=False, ligation_f
     if method == "obs_exp_non_zero":
         return obs_exp_non_zero(m, ligation_factor)
     raise ValueError(method)
+
+
+def covariance(dense):
+    """hicTransform.py:236, 243: np.cov of the dense block, every stored NaN kept"""
+    return sparse.csr_matrix(np.cov(np.asarray(dense, dtype=np.float64)))
+
+
+def pearson(dense):
+    """hicTransform.py:105-113 (_pearson): np.corrcoef, NaN / Inf -> 0"""
+    dense = np.asarray(dense)
+    if dense.shape[0] == 0:
+        return sparse.csr_matrix(dense.shape, dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        c = np.corrcoef(dense)
+    c = sparse.csr_matrix(c)
+    c.data[np.isnan(c.data)] = 0
+    c.data[np.isinf(c.data)] = 0
+    return c
+
+
+def correlation_transform(matrix, method, chr_offsets=None, per_chromosome=False):
+    """the pearson / covariance branches of hicTransform.main (:213-248); zeros eliminated like the saved file"""
+    m = sparse.csr_matrix(matrix)
+    fn = pearson if method == "pearson" else covariance
+    if per_chromosome:
+        offs = np.asarray(chr_offsets, dtype=np.int64)
+        out = sparse.block_diag([fn(m[lo:hi, lo:hi].toarray()) for lo, hi in zip(offs[:-1], offs[1:])], format="csr")
+    else:
+        out = sparse.csr_matrix(fn(m.toarray()))
+    out = out.astype(np.float64)
+    out.eliminate_zeros()
+    out.sort_indices()
+    return out

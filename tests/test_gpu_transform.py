@@ -5,7 +5,7 @@ import pytest
 from scipy import sparse
 
 from hicexplorer_b200.hicmatrix_lite import hiCMatrix
-from hicexplorer_b200.hicTransform import main, obs_exp_transform
+from hicexplorer_b200.hicTransform import correlation_transform, main, obs_exp_transform
 from oracle import transform_oracle
 from tests.conftest import load_golden
 from tests.helpers import random_hic
@@ -60,8 +60,6 @@ def test_hicTransform_cli_obs_exp(tmp_path):
         new = _upper(hiCMatrix(out).matrix)
         np.testing.assert_array_equal(new.data, t["ref_" + key + "_data"])
         np.testing.assert_array_almost_equal(new.data, t["file_" + key + "_data"], decimal=0)   # the reference's own check
-    with pytest.raises(SystemExit):
-        main("--matrix {} --outFileName {} --method pearson".format(src, str(tmp_path / "p.h5")).split())
 
 
 def test_distance_sums_are_order_free_and_accurate():
@@ -92,3 +90,73 @@ def test_distance_sums_are_order_free_and_accurate():
     with DeviceCSR.from_scipy(bad) as dev:
         sb, _ = dev.distance_stats()
     assert np.isnan(sb).sum() == 1
+
+
+# ---- covariance / pearson (hicTransform.py:105-113, 213-248) ---------------------------------------------------
+def _check_against_packed_golden(up, t, key, rtol):
+    """the expected matrix is stored as indptr + sha256(indices) + row sums + every 16th cell (make_golden_cov.py)"""
+    import hashlib
+    assert np.array_equal(up.indptr, t[key + "_indptr"])
+    assert hashlib.sha256(up.indices.astype(np.int32).tobytes()).digest() == t[key + "_indices_sha256"].tobytes()
+    scale = np.abs(t[key + "_sample"]).max()
+    np.testing.assert_allclose(up.data[::int(t["stride"])], t[key + "_sample"], rtol=rtol, atol=rtol * scale)
+    np.testing.assert_allclose(np.asarray(up.sum(axis=1)).ravel(), t[key + "_row_sums"], rtol=1e-9, atol=1e-9 * scale)
+
+
+@pytest.mark.parametrize("method,key", [("covariance", "cov_pc_file"), ("pearson", "pearson_pc_ref")])
+def test_correlation_per_chromosome_matches_the_reference_golden(method, key):
+    """covariance: the reference's golden FILE test_data/hicTransform/covariance_perChromosome.h5
+    (test_hicTransform.py::test_covariance_per_chromosome); pearson: the reference's own _pearson per chromosome"""
+    t, _ma, mb = _transform_inputs()
+    g = load_golden("transform_cov.npz")
+    got = correlation_transform(mb, method, t["b_offsets"], per_chromosome=True)
+    assert got.dtype == np.float64 and got.shape == mb.shape
+    _check_against_packed_golden(_upper(got), g, key, rtol=1e-11)
+
+
+@pytest.mark.parametrize("method", ["covariance", "pearson"])
+@pytest.mark.parametrize("pc", [False, True])
+def test_correlation_matches_oracle(method, pc):
+    """random matrices with empty rows (constant variables: pearson's 0/0 -> NaN -> 0) and a one-bin chromosome
+    (np.cov's `Degrees of freedom <= 0`: NaN stored by covariance, 0 by pearson)"""
+    m = random_hic(700, 0.15, 11, integer=True).tolil()
+    for r in (0, 5, 340, 699):
+        m[r, :] = 0
+        m[:, r] = 0
+    m = sparse.csr_matrix(m.tocsr())
+    m.eliminate_zeros()
+    offs = np.asarray([0, 200, 201, 480, 700], dtype=np.int64)
+    with np.errstate(all="ignore"):
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref = transform_oracle.correlation_transform(m, method, offs, per_chromosome=pc)
+    got = sparse.csr_matrix(correlation_transform(m, method, offs, per_chromosome=pc))
+    got.eliminate_zeros()
+    got.sort_indices()
+    gd, rd = got.toarray(), ref.toarray()
+    assert np.array_equal(np.isnan(gd), np.isnan(rd))
+    scale = np.nanmax(np.abs(rd))
+    np.testing.assert_allclose(np.nan_to_num(gd), np.nan_to_num(rd), rtol=0, atol=1e-12 * scale)
+    if method == "pearson":
+        assert np.nanmax(np.abs(gd)) <= 1.0
+        live = np.asarray(m.sum(axis=1)).ravel() > 0
+        if not pc:
+            np.testing.assert_allclose(gd.diagonal()[live], 1.0, atol=1e-12)
+
+
+def test_hicTransform_cli_covariance(tmp_path):
+    """mirrors test_covariance_per_chromosome (test_hicTransform.py: `--method covariance --perChromosome` on
+    small_test_matrix_50kb_res.h5 against hicTransform/covariance_perChromosome.h5)"""
+    t, _ma, mb = _transform_inputs()
+    g = load_golden("transform_cov.npz")
+    ma = hiCMatrix()
+    ma.matrix = mb
+    ma.cut_intervals = [(c.decode(), int(s), int(e), 1.0) for c, s, e in zip(t["b_chr"], t["b_start"], t["b_end"])]
+    ma._index_intervals()
+    ma.value_dtype = mb.dtype
+    src = str(tmp_path / "small_test_matrix_50kb_res.h5")
+    ma.save(src)
+    out = str(tmp_path / "covariance_perChromosome.h5")
+    main("--matrix {} --outFileName {} --method covariance --perChromosome".format(src, out).split())
+    _check_against_packed_golden(_upper(hiCMatrix(out).matrix), g, "cov_pc_file", rtol=1e-11)

@@ -261,6 +261,22 @@ def test_transform_reference_golden_files_to_their_own_tolerance(key, file_key):
     np.testing.assert_array_almost_equal(t[key + "_data"], t[file_key + "_data"], decimal=0)
 
 
+def test_correlation_oracle_reproduces_the_reference_golden_file():
+    """np.cov per chromosome == test_data/hicTransform/covariance_perChromosome.h5 (same cells; the reference's test
+    compares with decimal=0), np.corrcoef per chromosome == the reference's own _pearson (make_golden_cov.py)"""
+    import hashlib
+    from oracle import transform_oracle
+    from tests.conftest import load_golden
+    t, _ma, mb = _transform_inputs()
+    g = load_golden("transform_cov.npz")
+    for method, key in (("covariance", "cov_pc_file"), ("pearson", "pearson_pc_ref")):
+        up = _upper(transform_oracle.correlation_transform(mb, method, t["b_offsets"], per_chromosome=True))
+        assert np.array_equal(up.indptr, g[key + "_indptr"])
+        assert hashlib.sha256(up.indices.astype(np.int32).tobytes()).digest() == g[key + "_indices_sha256"].tobytes()
+        np.testing.assert_allclose(up.data[::int(g["stride"])], g[key + "_sample"], rtol=1e-11, atol=1e-11)
+        np.testing.assert_allclose(np.asarray(up.sum(axis=1)).ravel(), g[key + "_row_sums"], rtol=1e-9, atol=1e-9)
+
+
 @pytest.mark.parametrize("k", [3, 5])
 def test_running_window_oracle_equals_the_reference_function(k):
     """oracle/merge_oracle.running_window vs hicMergeMatrixBins.running_window_merge imported from /root/reference"""
