@@ -299,6 +299,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
     method, bins, kw = synth_kwargs(args.workload, clean=True)
     n = int(sum(bins))
 
@@ -558,6 +565,8 @@ def main():
             check(L.hb_csr_create(ctypes.byref(h2), n_rows, n_cols, row0, nnz_local, ctypes.c_void_p(ip_h.data_ptr()),
                                   ctypes.c_void_p(ix_h.data_ptr()), 0, ctypes.c_void_p(da_h.data_ptr()), local))
             t_create = time.time() - t0
+            ingest_kind, ingest_bytes = ctypes.c_int(0), ctypes.c_int64(0)
+            check(L.hb_csr_ingest_info(h2, ctypes.byref(ingest_kind), ctypes.byref(ingest_bytes)))
             dev2 = DeviceCSR(h2, local)
             keep2 = None
             if world > 1 and not (peer_mode and attach_peer(dev2, rank, world)):
@@ -568,11 +577,16 @@ def main():
             t_run = time.time() - t0 - t_create - t_attach
             barrier()
             e2e_s = max_over_ranks(time.time() - t0)
+            h2d_total = sum_over_ranks(float(ingest_bytes.value))
             breakdown = {"hb_csr_create_s": max_over_ranks(t_create), "attach_exchange_s": max_over_ranks(t_attach),
                          "hb_ice_run_s": max_over_ranks(t_run),
-                         "h2d_GBps_per_gpu_inside_create": 12.0 * nnz_local / max(t_create, 1e-9) / 1e9,
+                         "host_bytes_read_per_gpu": 12.0 * nnz_local + 8.0 * (n_rows + 1),
+                         "pcie_bytes_per_gpu": float(ingest_bytes.value),
+                         "value_layout_after_create": {0: "fp64 only", 1: "fp64 + uint16 (narrow ingest: counts converted on "
+                                                       "the host, 2 B per entry over PCIe)", 2: "fp64 + float"}[ingest_kind.value],
+                         "host_GBps_per_gpu_inside_create": 12.0 * nnz_local / max(t_create, 1e-9) / 1e9,
                          "note": "rank-wise maxima of host timestamps; the upload dominates hb_csr_create (pinned host memory, "
-                                 "PCIe Gen5 x16 per GPU; with N ranks the host's memory bandwidth is shared)"}
+                                 "PCIe Gen5 x16 per GPU; with N ranks the host's cores and memory bandwidth are shared)"}
             dev2.close()
             del keep2
             # the same call sequence run to the reference's own stopping rule (tolerance 1e-5): the whole job a caller of
@@ -613,9 +627,10 @@ def main():
                 except Exception as exc:
                     dropin = {"error": repr(exc)}
             e2e = {"value": nnz_total * args.steps / e2e_s, "unit": "nnz/s",
-                   "h2d_bytes_per_step": (12.0 * nnz_total + 8.0 * (n + world)) / args.steps,
+                   "h2d_bytes_per_step": h2d_total / args.steps,
                    "d2h_bytes_per_step": 8.0 * n * world / args.steps, "seconds": e2e_s, "iterations": int(iters_h[0]),
-                   "what": "hb_csr_create (pinned host CSR -> HBM) + hb_ice_run(max_iter=steps, tol=0) + bias to host; "
+                   "what": "hb_csr_create (pinned host CSR int64/int32/fp64 -> HBM; h2d bytes are what crossed PCIe, as "
+                           "reported by hb_csr_ingest_info) + hb_ice_run(max_iter=steps, tol=0) + bias to host; "
                            "one call = `steps` iterations, so the one-off copy is amortised over them",
                    "breakdown": breakdown,
                    "to_convergence": {"seconds": conv_s, "iterations": int(iters_c[0]), "tolerance": 1e-5,

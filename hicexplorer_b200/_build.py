@@ -9,7 +9,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libhicbalance.so")
-SOURCES = ["hb_core.cu", "hb_ice.cu", "hb_filter.cu", "hb_kr.cu", "hb_synth.cu", "hb_merge.cu", "hb_xfer.cu", "hb_sym.cu", "hb_trans.cu", "hb_elem.cu", "hb_transform.cu", "hb_dense.cu"]
+SOURCES = ["hb_core.cu", "hb_ice.cu", "hb_filter.cu", "hb_kr.cu", "hb_synth.cu", "hb_merge.cu", "hb_xfer.cu", "hb_sym.cu", "hb_trans.cu", "hb_elem.cu", "hb_transform.cu", "hb_dense.cu", "hb_hostpack.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xptxas", "-v"]
 
@@ -46,9 +46,15 @@ def build(force=False, verbose=False, defines=None, out=None):
         if not os.path.exists(path):
             continue
         tag = "_" + "_".join("%s%s" % kv for kv in sorted(defines.items())) if defines else ""
-        obj = os.path.join(bdir, src.replace(".cu", tag + ".o"))
+        obj = os.path.join(bdir, os.path.splitext(src)[0] + tag + ".o")
         dflags = ["-D%s=%s" % kv for kv in (defines or {}).items()]
-        cmd = [_nvcc()] + NVCC_FLAGS + dflags + ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-c", path, "-o", obj]
+        if src.endswith(".cpp"):     # host-only helpers: the host compiler directly (no -march: built here, run elsewhere)
+            cxx = shutil.which("g++") or shutil.which("c++")
+            if cxx is None:
+                raise RuntimeError("g++ not found: cannot build libhicbalance.so")
+            cmd = [cxx, "-O3", "-std=c++17", "-fPIC", "-fvisibility=hidden"] + dflags + ["-c", path, "-o", obj]
+        else:
+            cmd = [_nvcc()] + NVCC_FLAGS + dflags + ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-c", path, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     log = []

@@ -98,6 +98,7 @@ SIGNATURES = {
     "hb_dev_extract_cols": (c_int, [vp, c_i64, c_i64, P(c_i64), vp, vp, vp]),
     "hb_dev_partner_sums": (c_int, [vp, c_i64, vp, vp, vp, P(c_dbl)]),
     "hb_block_correlation": (c_int, [vp, c_i64, c_i64, c_int, P(c_i64), vp, vp, vp]),
+    "hb_csr_ingest_info": (c_int, [vp, P(c_int), P(c_i64)]),
     "hb_ice_run": (c_int, [vp, c_int, c_dbl, vp, vp, vp]),
     "hb_ice_scaled_values": (c_int, [vp, vp, P(c_dbl)]),
     "hb_ice_scaled_upper": (c_int, [vp, vp, c_i64, P(c_i64), vp, vp, vp]),

@@ -1,8 +1,12 @@
 // Handle management of the device-resident CSR store (include/hicbalance.h).
+#include <chrono>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+
+#include <thread>
 
 #include "hb_internal.cuh"
 
@@ -169,15 +173,21 @@ int hb_csr_create_typed(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t ro
     hb_csr* h = *out;
     h->owns_csr = true;
     cudaStream_t s = h->stream;
+    std::thread idx_thread;   // uploads the column ids beside the values; joined before any exit path frees the handle
 #define HB_CREATE_CUDA(expr)                                               \
     do {                                                                   \
         cudaError_t _e = (expr);                                           \
         if (_e != cudaSuccess) {                                           \
+            if (idx_thread.joinable()) idx_thread.join();                  \
             hb_csr_destroy(h);                                             \
             *out = nullptr;                                                \
             return hb_cuda_fail(_e, #expr, __FILE__, __LINE__);            \
         }                                                                  \
     } while (0)
+    static const bool create_timing = getenv("HB_INGEST_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_stamp[6] = {now(), 0, 0, 0, 0, 0};   // start | allocations | values | column ids joined | validated | tiles
+    double t_idx = 0.0;
     HB_CREATE_CUDA(hb_dmalloc(&h->d_indptr, sizeof(int64_t) * (size_t)(n_rows + 1)));
     const int64_t phase = indptr[0] & 3;
     h->phase = phase;
@@ -198,14 +208,49 @@ int hb_csr_create_typed(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t ro
         g_hb_launches.fetch_add(1);
     }
     HB_CREATE_CUDA(cudaStreamSynchronize(s));
+    t_stamp[1] = t_stamp[2] = t_stamp[3] = now();
     if (nnz > 0) {
+        // int32 column ids go over the bus from a second host thread while this one deals with the values
+        int idx_rc = HB_OK;
+        auto fail_create = [&]() {
+            if (idx_thread.joinable()) idx_thread.join();
+            hb_csr_destroy(h);
+            *out = nullptr;
+            return (int)HB_ERR_CUDA;
+        };
+        if (!indices_i64)
+            idx_thread = std::thread([&] {
+                const double t0 = now();
+                idx_rc = cudaSetDevice(device) == cudaSuccess
+                             ? hb_copy_h2d(h->d_indices + phase, (const int32_t*)indices + indptr[0], sizeof(int32_t) * (size_t)nnz, device)
+                             : HB_ERR_CUDA;
+                t_idx = now() - t0;
+            });
+        h->h2d_bytes = (int64_t)sizeof(int64_t) * (n_rows + 1) + (int64_t)(indices_i64 ? 8 : 4) * nnz;
         if (value_kind == HB_VALUES_F64) {
-            if (hb_copy_h2d(h->d_data + phase, data + indptr[0], sizeof(double) * (size_t)nnz, device) != HB_OK) {
-                hb_csr_destroy(h);
-                *out = nullptr;
-                return HB_ERR_CUDA;
+            // raw counts: 2 bytes per entry cross the bus and the device keeps both forms (hb_ingest_values)
+            int narrowed = 0;
+            uint16_t* d_pack = nullptr;
+            HB_CREATE_CUDA(hb_dmalloc(&d_pack, sizeof(uint16_t) * (size_t)(nnz + phase + 8) + 16));
+            h->d_pack = d_pack;
+            HB_CREATE_CUDA(cudaMemsetAsync(d_pack, 0, sizeof(uint16_t) * 8, s));
+            HB_CREATE_CUDA(cudaStreamSynchronize(s));
+            if (hb_ingest_values(h->d_data + phase, d_pack + phase, data + indptr[0], nnz, device, &narrowed) != HB_OK) {
+                return fail_create();
+            }
+            if (narrowed) {
+                h->pack_kind = 1;
+                h->h2d_bytes += (int64_t)sizeof(uint16_t) * nnz;
+            } else {
+                hb_dfree(h->d_pack);
+                h->d_pack = nullptr;
+                if (hb_copy_h2d(h->d_data + phase, data + indptr[0], sizeof(double) * (size_t)nnz, device) != HB_OK) {
+                    return fail_create();
+                }
+                h->h2d_bytes += (int64_t)sizeof(double) * nnz;
             }
         } else {
+            h->h2d_bytes += (int64_t)(value_kind == HB_VALUES_I64 ? 8 : 4) * nnz;
             const size_t elt = value_kind == HB_VALUES_I64 ? 8 : 4;
             const unsigned char* src = static_cast<const unsigned char*>(data_any) + elt * (size_t)indptr[0];
             const int64_t chunk = (int64_t)1 << 26;
@@ -215,9 +260,7 @@ int hb_csr_create_typed(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t ro
             for (int64_t o = 0; o < nnz; o += chunk) {
                 const int64_t m = nnz - o < chunk ? nnz - o : chunk;
                 if (hb_copy_h2d(d_tmp, src + elt * (size_t)o, elt * (size_t)m, device) != HB_OK) {
-                    hb_csr_destroy(h);
-                    *out = nullptr;
-                    return HB_ERR_CUDA;
+                    return fail_create();
                 }
                 double* dst = h->d_data + phase + o;
                 if (value_kind == HB_VALUES_F32)
@@ -230,6 +273,7 @@ int hb_csr_create_typed(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t ro
                 HB_CREATE_CUDA(cudaStreamSynchronize(s));   // the staging buffer is reused by the next chunk
             }
         }
+        t_stamp[2] = now();
         if (indices_i64) {
             // krbalancing's constructor takes int64 indices (hicCorrectMatrix.py:744-747): narrow on the device
             const int64_t* src = (const int64_t*)indices + indptr[0];
@@ -245,13 +289,10 @@ int hb_csr_create_typed(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t ro
                 HB_CREATE_CUDA(cudaStreamSynchronize(s));   // the staging buffer is reused by the next chunk
             }
         } else {
-            if (hb_copy_h2d(h->d_indices + phase, (const int32_t*)indices + indptr[0], sizeof(int32_t) * (size_t)nnz,
-                            device) != HB_OK) {
-                hb_csr_destroy(h);
-                *out = nullptr;
-                return HB_ERR_CUDA;
-            }
+            idx_thread.join();
+            if (idx_rc != HB_OK) return fail_create();
         }
+        t_stamp[3] = now();
     }
     HB_CREATE_CUDA(cudaStreamSynchronize(s));
     {
@@ -278,11 +319,18 @@ int hb_csr_create_typed(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t ro
         }
     }
 #undef HB_CREATE_CUDA
+    t_stamp[4] = now();
     rc = hb_build_tiles(h);
     if (rc != HB_OK) {
         hb_csr_destroy(h);
         *out = nullptr;
     }
+    t_stamp[5] = now();
+    if (create_timing)
+        fprintf(stderr, "[hb create] %lld entries: allocations %.1f ms | values %.1f | wait for column ids %.1f (their copy took %.1f) | "
+                        "validation %.1f | tiles %.1f | total %.1f ms\n",
+                (long long)nnz, 1e3 * (t_stamp[1] - t_stamp[0]), 1e3 * (t_stamp[2] - t_stamp[1]), 1e3 * (t_stamp[3] - t_stamp[2]),
+                1e3 * t_idx, 1e3 * (t_stamp[4] - t_stamp[3]), 1e3 * (t_stamp[5] - t_stamp[4]), 1e3 * (t_stamp[5] - t_stamp[0]));
     return rc;
 }
 
@@ -322,6 +370,13 @@ int hb_csr_destroy(hb_csr* h) {
     if (h->loop_event) cudaEventDestroy(h->loop_event);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
+    return HB_OK;
+}
+
+int hb_csr_ingest_info(const hb_csr* h, int* pack_kind, int64_t* h2d_bytes) {
+    HB_REQUIRE(h != nullptr, "null handle");
+    if (pack_kind) *pack_kind = h->pack_kind;
+    if (h2d_bytes) *h2d_bytes = h->h2d_bytes;
     return HB_OK;
 }
 

@@ -700,6 +700,12 @@ int hb_csr_pack_values(hb_csr* h, int* kind_out) {
     if (rc) return rc;
     rc = hb_use_device(h);
     if (rc) return rc;
+    if (h->pack_kind != 0 && h->d_pack != nullptr) {
+        // already there: hb_csr_create's narrow ingest wrote it, or an earlier call (every operation that changes the
+        // values or the structure drops the copy, so what exists is current)
+        if (kind_out) *kind_out = h->pack_kind;
+        return HB_OK;
+    }
     hb_drop_pack(h);
     cudaStream_t s = h->stream;
     if (kind_out) *kind_out = 0;

@@ -146,6 +146,7 @@ struct hb_csr {
     double* d_kr_buf = nullptr;        // Knight-Ruiz workspace (8 n-vectors + tile partials + scalars), kept across calls
     size_t kr_buf_words = 0;
     double* h_kr_sc = nullptr;         // pinned mirror of the KR scalars
+    int64_t h2d_bytes = 0;             // bytes hb_csr_create* moved over the bus for this store
     double* d_dense = nullptr;         // hb_block_correlation: the dense block between its two calls
     int64_t dense_m = 0;
 };
@@ -205,6 +206,9 @@ void hb_drop_pack(hb_csr* h);
 // multi-threaded staged copies for pageable caller buffers (hb_xfer.cu); synchronous
 int hb_copy_h2d(void* d_dst, const void* h_src, size_t bytes, int device);
 int hb_copy_d2h(void* h_dst, const void* d_src, size_t bytes, int device);
+// fp64 counts -> uint16 on the host, 2 bytes per entry over the bus, both device forms written (hb_xfer.cu); *narrowed = 0
+// when some value does not fit and nothing was kept
+int hb_ingest_values(double* d_data, uint16_t* d_pack, const double* h_src, int64_t nnz, int device, int* narrowed);
 // exchange buffer p (0/1) of this rank's symmetric region and its flag array
 static inline double* hb_sym_buf(const hb_csr* h, int p) { return (double*)((unsigned char*)h->pc->d_sym + (size_t)p * h->pc->buf_bytes); }
 static inline unsigned long long* hb_sym_flags(const hb_csr* h, int p) {

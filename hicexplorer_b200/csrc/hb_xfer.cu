@@ -5,6 +5,9 @@
 // (memcpy) one chunk while its other buffer is in flight over PCIe, and the workers' first-touch page faults and
 // memcpys proceed in parallel.  Pinned / registered caller buffers (bench.py's e2e leg) take the direct DMA path.
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -98,8 +101,34 @@ static cudaError_t hb_xfer_prepare(HbXferWorker& w, int device, size_t chunk) {
 static int hb_xfer(void* dst, const void* src, size_t bytes, int dir, int device) {
     if (bytes == 0) return HB_OK;
     const void* host = dir == 0 ? src : dst;
-    if (bytes < ((size_t)8 << 20) || hb_is_device_accessible_host(host)) {
+    if (bytes < ((size_t)8 << 20)) {
         HB_CUDA(cudaMemcpy(dst, src, bytes, dir == 0 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost));
+        return HB_OK;
+    }
+    if (hb_is_device_accessible_host(host)) {
+        // direct DMA, on a stream of its own: a synchronous cudaMemcpy would go through the null stream and stall the API
+        // calls of every other host thread (the narrow ingest's workers) for as long as it runs
+        cudaStream_t st = nullptr;
+        HB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        // in pieces, at most two of them queued: the copy engine serves its queue in order, so a copy queued whole would
+        // hold back every chunk the other streams submit while it runs
+        const size_t piece = (size_t)16 << 20;
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        cudaError_t e = cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+        size_t k = 0;
+        for (size_t off = 0; off < bytes && e == cudaSuccess; off += piece, ++k) {
+            if (k >= 2) e = cudaEventSynchronize(ev[k & 1]);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync((unsigned char*)dst + off, (const unsigned char*)src + off, std::min(piece, bytes - off),
+                                    dir == 0 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaEventRecord(ev[k & 1], st);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        for (int b = 0; b < 2; ++b)
+            if (ev[b]) cudaEventDestroy(ev[b]);
+        cudaStreamDestroy(st);
+        HB_CUDA(e);
         return HB_OK;
     }
     std::lock_guard<std::mutex> guard(g_xfer_mutex);
@@ -155,3 +184,172 @@ static int hb_xfer(void* dst, const void* src, size_t bytes, int dir, int device
 
 int hb_copy_h2d(void* d_dst, const void* h_src, size_t bytes, int device) { return hb_xfer(d_dst, h_src, bytes, 0, device); }
 int hb_copy_d2h(void* h_dst, const void* d_src, size_t bytes, int device) { return hb_xfer(h_dst, d_src, bytes, 1, device); }
+
+
+// ---- narrow ingest: fp64 counts leave the host as uint16 ------------------------------------------------------
+// hb_csr_create's value upload when every value is an integer in [0, 65535] (raw Hi-C counts): host threads convert
+// chunk after chunk into pinned staging (hb_hostpack.cpp; lossless or refused), 2 bytes per entry cross PCIe, and the
+// device writes both forms it keeps: the uint16 stream of the solver kernels (d_pack) and the fp64 store (d_data).
+// 12 -> 6 bytes per entry over the bus for a CSR block (int32 columns + values).  *narrowed = 0: some value does not
+// fit; nothing on the device is valid and the caller copies the fp64 values as before.
+extern "C" int hb_host_pack_u16(const double* src, uint16_t* dst, size_t n);
+
+static bool hb_narrow_ingest_enabled() {
+    static const bool v = [] {
+        const char* e = getenv("HB_NARROW_INGEST");
+        return !(e && e[0] == '0');
+    }();
+    return v;
+}
+static int hb_ingest_workers() {
+    static const int v = [] {
+        const char* e = getenv("HB_INGEST_WORKERS");
+        if (e && atoi(e) > 0) return atoi(e) > 64 ? 64 : atoi(e);
+        int hw = (int)std::thread::hardware_concurrency();
+        if (hw <= 0) hw = 8;
+        const char* lw = getenv("LOCAL_WORLD_SIZE");          // torchrun: the ranks of this node share the cores
+        const int ranks = lw && atoi(lw) > 0 ? atoi(lw) : 1;
+        int w = hw / ranks;
+        return w < 2 ? 2 : (w > 16 ? 16 : w);
+    }();
+    return v;
+}
+static size_t hb_ingest_chunk_entries() {
+    static const size_t v = [] {
+        const char* e = getenv("HB_INGEST_CHUNK");             // entries per chunk (tests use a small one)
+        const long n = e ? atol(e) : 0;
+        return n >= 64 ? (size_t)n : ((size_t)1 << 20);   // 8 MB of fp64 read, 2 MB sent; pinning the staging costs ~0.8 ms/MB once
+    }();
+    return v;
+}
+
+__global__ void __launch_bounds__(256) hb_expand_u16_kernel(const uint16_t* __restrict__ src, double* __restrict__ dst, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] = (double)src[i];
+}
+
+struct HbIngestWorker {
+    int device = -1;
+    size_t chunk = 0;
+    cudaStream_t st = nullptr;
+    uint16_t* stage[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+};
+static std::mutex g_ingest_mutex;
+static HbIngestWorker g_ingest_worker[64];
+
+static void hb_ingest_teardown(HbIngestWorker& w) {
+    if (w.device >= 0) cudaSetDevice(w.device);
+    for (int b = 0; b < 2; ++b) {
+        if (w.done[b]) cudaEventDestroy(w.done[b]);
+        if (w.stage[b]) cudaFreeHost(w.stage[b]);
+        w.done[b] = nullptr;
+        w.stage[b] = nullptr;
+    }
+    if (w.st) cudaStreamDestroy(w.st);
+    w.st = nullptr;
+    w.device = -1;
+    w.chunk = 0;
+}
+
+static cudaError_t hb_ingest_prepare(HbIngestWorker& w, int device, size_t chunk) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return e;
+    if (w.device == device && w.chunk == chunk && w.st != nullptr) return cudaSuccess;
+    hb_ingest_teardown(w);
+    e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w.st, cudaStreamNonBlocking);
+    for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+        e = cudaHostAlloc((void**)&w.stage[b], chunk * sizeof(uint16_t), cudaHostAllocDefault);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w.done[b], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) {
+        w.device = device;
+        hb_ingest_teardown(w);
+        cudaGetLastError();
+        return e;
+    }
+    w.device = device;
+    w.chunk = chunk;
+    return cudaSuccess;
+}
+
+int hb_ingest_values(double* d_data, uint16_t* d_pack, const double* h_src, int64_t nnz, int device, int* narrowed) {
+    *narrowed = 0;
+    if (nnz <= 0 || !hb_narrow_ingest_enabled()) return HB_OK;
+    {
+        // a first look before any thread or staging buffer is set up: corrected / normalised matrices fail here
+        uint16_t probe[256];
+        const size_t np = (size_t)(nnz < 256 ? nnz : 256);
+        if (!hb_host_pack_u16(h_src, probe, np) || !hb_host_pack_u16(h_src + (nnz - (int64_t)np), probe, np)) return HB_OK;
+    }
+    std::lock_guard<std::mutex> guard(g_ingest_mutex);
+    const size_t chunk = hb_ingest_chunk_entries();
+    const size_t nchunks = ((size_t)nnz + chunk - 1) / chunk;
+    const int workers = (int)std::min<size_t>((size_t)hb_ingest_workers(), nchunks);
+    std::vector<cudaError_t> err((size_t)workers, cudaSuccess);
+    std::atomic<bool> refused(false);
+    std::atomic<uint64_t> launches(0);
+    static const bool timing = getenv("HB_INGEST_TIMING") != nullptr;
+    std::vector<double> t_prep((size_t)workers, 0.0), t_pack((size_t)workers, 0.0), t_wait((size_t)workers, 0.0),
+        t_issue((size_t)workers, 0.0), t_drain((size_t)workers, 0.0);
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+    auto work = [&](int t) {
+        HbIngestWorker& w = g_ingest_worker[t];
+        double t0 = now();
+        cudaError_t e = hb_ingest_prepare(w, device, chunk);
+        t_prep[(size_t)t] = now() - t0;
+        bool used[2] = {false, false};
+        int slot = 0;
+        for (size_t c = (size_t)t; c < nchunks && e == cudaSuccess && !refused.load(std::memory_order_relaxed);
+             c += (size_t)workers, slot ^= 1) {
+            const size_t off = c * chunk;
+            const size_t len = std::min(chunk, (size_t)nnz - off);
+            t0 = now();
+            if (used[slot]) e = cudaEventSynchronize(w.done[slot]);   // the staging buffer is reused
+            t_wait[(size_t)t] += now() - t0;
+            if (e != cudaSuccess) break;
+            t0 = now();
+            const bool ok = hb_host_pack_u16(h_src + off, w.stage[slot], len) != 0;
+            t_pack[(size_t)t] += now() - t0;
+            if (!ok) {
+                refused.store(true, std::memory_order_relaxed);
+                break;
+            }
+            t0 = now();
+            e = cudaMemcpyAsync(d_pack + off, w.stage[slot], len * sizeof(uint16_t), cudaMemcpyHostToDevice, w.st);
+            if (e != cudaSuccess) break;
+            hb_expand_u16_kernel<<<HB_NUM_SMS * 2, 256, 0, w.st>>>(d_pack + off, d_data + off, (int64_t)len);
+            launches.fetch_add(1, std::memory_order_relaxed);
+            e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaEventRecord(w.done[slot], w.st);
+            used[slot] = true;
+            t_issue[(size_t)t] += now() - t0;
+        }
+        t0 = now();
+        if (w.st) {   // always drain: the staging buffers outlive this call
+            const cudaError_t e2 = cudaStreamSynchronize(w.st);
+            if (e == cudaSuccess) e = e2;
+        }
+        t_drain[(size_t)t] = now() - t0;
+        err[(size_t)t] = e;
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < workers; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
+    g_hb_launches.fetch_add(launches.load());
+    if (timing) {
+        auto mx = [](const std::vector<double>& v) { return *std::max_element(v.begin(), v.end()); };
+        fprintf(stderr, "[hb ingest] %lld entries, %d workers, %zu chunks: total %.1f ms | per worker (max) prepare %.1f, "
+                        "convert %.1f, wait for staging %.1f, issue %.1f, drain %.1f ms\n",
+                (long long)nnz, workers, nchunks, 1e3 * (now() - t_begin), 1e3 * mx(t_prep), 1e3 * mx(t_pack), 1e3 * mx(t_wait),
+                1e3 * mx(t_issue), 1e3 * mx(t_drain));
+    }
+    for (int t = 0; t < workers; ++t)
+        if (err[(size_t)t] != cudaSuccess) return hb_cuda_fail(err[(size_t)t], "narrow ingest", __FILE__, __LINE__);
+    *narrowed = refused.load() ? 0 : 1;
+    return HB_OK;
+}
