@@ -543,3 +543,80 @@ HBIO_API int64_t hbio_encode_chunks(const uint8_t* src, int64_t nbytes, int64_t 
     }
     return pos;
 }
+
+
+/* ---- is a CSR canonical?  (rows sorted by column, no duplicates, columns inside [0, n_cols)) --------------------
+ * scipy's own check (csr_has_canonical_format) is one thread walking the whole index array: 0.43 s for the upper
+ * triangle of a genome-wide 10 kb matrix, on the critical path of every load.  Same test on all host cores.
+ * Returns 1 canonical, 0 not, -1 bad arguments.  indices: int32 (idx_bytes 4) or int64 (8); indptr: int32 or int64. */
+typedef struct {
+    const void* indptr;
+    const void* indices;
+    int ptr_bytes, idx_bytes;
+    int64_t n_rows, n_cols;
+    int nthreads, tid;
+    int ok;
+} hbio_canon_job;
+
+static void* hbio_canon_worker(void* arg) {
+    hbio_canon_job* j = (hbio_canon_job*)arg;
+    const int64_t r0 = j->n_rows * j->tid / j->nthreads, r1 = j->n_rows * (j->tid + 1) / j->nthreads;
+    int ok = 1;
+    for (int64_t r = r0; r < r1 && ok; ++r) {
+        const int64_t s = j->ptr_bytes == 8 ? ((const int64_t*)j->indptr)[r] : ((const int32_t*)j->indptr)[r];
+        const int64_t e = j->ptr_bytes == 8 ? ((const int64_t*)j->indptr)[r + 1] : ((const int32_t*)j->indptr)[r + 1];
+        if (e < s) {
+            ok = 0;
+            break;
+        }
+        if (e == s) continue;
+        if (j->idx_bytes == 4) {
+            const int32_t* x = (const int32_t*)j->indices;
+            int bad = x[s] < 0 || (int64_t)x[e - 1] >= j->n_cols;
+            for (int64_t k = s + 1; k < e; ++k) bad |= x[k - 1] >= x[k];
+            if (bad) ok = 0;
+        } else {
+            const int64_t* x = (const int64_t*)j->indices;
+            int bad = x[s] < 0 || x[e - 1] >= j->n_cols;
+            for (int64_t k = s + 1; k < e; ++k) bad |= x[k - 1] >= x[k];
+            if (bad) ok = 0;
+        }
+    }
+    j->ok = ok;
+    return NULL;
+}
+
+HBIO_API int hbio_csr_is_canonical(const void* indptr, int ptr_bytes, const void* indices, int idx_bytes, int64_t n_rows,
+                                   int64_t n_cols, int64_t nnz, int nthreads) {
+    if ((ptr_bytes != 4 && ptr_bytes != 8) || (idx_bytes != 4 && idx_bytes != 8) || n_rows < 0 || indptr == NULL) return -1;
+    if (n_rows == 0) return 1;
+    const int64_t first = ptr_bytes == 8 ? ((const int64_t*)indptr)[0] : ((const int32_t*)indptr)[0];
+    const int64_t last = ptr_bytes == 8 ? ((const int64_t*)indptr)[n_rows] : ((const int32_t*)indptr)[n_rows];
+    if (first != 0 || last != nnz) return 0;
+    if (nnz > 0 && indices == NULL) return -1;
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 64) nthreads = 64;
+    if ((int64_t)nthreads > n_rows) nthreads = (int)n_rows;
+    /* indptr must be monotone as a whole before the workers index through it */
+    for (int64_t r = 0; r < n_rows; ++r) {
+        const int64_t a = ptr_bytes == 8 ? ((const int64_t*)indptr)[r] : ((const int32_t*)indptr)[r];
+        const int64_t b = ptr_bytes == 8 ? ((const int64_t*)indptr)[r + 1] : ((const int32_t*)indptr)[r + 1];
+        if (b < a || a < 0 || b > nnz) return 0;
+    }
+    hbio_canon_job jobs[64];
+    pthread_t th[64];
+    int started[64] = {0};
+    for (int t = 0; t < nthreads; ++t) {
+        hbio_canon_job j = {indptr, indices, ptr_bytes, idx_bytes, n_rows, n_cols, nthreads, t, 1};
+        jobs[t] = j;
+    }
+    for (int t = 1; t < nthreads; ++t) started[t] = pthread_create(&th[t], NULL, hbio_canon_worker, &jobs[t]) == 0;
+    hbio_canon_worker(&jobs[0]);
+    int ok = jobs[0].ok;
+    for (int t = 1; t < nthreads; ++t) {
+        if (started[t]) pthread_join(th[t], NULL);
+        else hbio_canon_worker(&jobs[t]);
+        ok &= jobs[t].ok;
+    }
+    return ok;
+}

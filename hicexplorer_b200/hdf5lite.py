@@ -136,8 +136,29 @@ def _native_lib():
                 lib.hbio_encode_chunks.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
                                                    ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
                                                    ctypes.c_void_p, ctypes.c_void_p]
+            if hasattr(lib, "hbio_csr_is_canonical"):
+                lib.hbio_csr_is_canonical.restype = ctypes.c_int
+                lib.hbio_csr_is_canonical.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
+                                                      ctypes.c_int64, ctypes.c_int64, ctypes.c_int]
             _native = lib
     return _native or None
+
+
+def csr_is_canonical(m):
+    """scipy's ``has_canonical_format`` test (sorted rows, no duplicates) on all host cores; None when libhbio.so is not
+    there or the arrays are of a kind it does not take (the caller then asks scipy)"""
+    import os
+    lib = _native_lib()
+    if lib is None or not hasattr(lib, "hbio_csr_is_canonical"):
+        return None
+    ip, ix = m.indptr, m.indices
+    if ip.dtype.itemsize not in (4, 8) or ix.dtype.itemsize not in (4, 8) or ip.dtype.kind != "i" or ix.dtype.kind != "i":
+        return None
+    if not (ip.flags.c_contiguous and ix.flags.c_contiguous):
+        return None
+    rc = lib.hbio_csr_is_canonical(ip.ctypes.data, ip.dtype.itemsize, ix.ctypes.data, ix.dtype.itemsize, m.shape[0], m.shape[1],
+                                   len(ix), min(os.cpu_count() or 1, 16))
+    return None if rc < 0 else bool(rc)
 
 
 def _blosc_decompress(chunk):

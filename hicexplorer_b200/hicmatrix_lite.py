@@ -143,6 +143,8 @@ class hiCMatrix(object):
 
     def _set_upper(self, up):
         up = sparse.csr_matrix(up)
+        if hdf5lite.csr_is_canonical(up):    # scipy's one-thread test of the same property: 0.43 s on a 10 kb matrix
+            up.has_canonical_format = True
         try:
             up.sum_duplicates()              # also sorts the columns of every row (no-op for canonical input)
         except ValueError:                   # read-only views of a mapped file that is not canonical: work on a copy

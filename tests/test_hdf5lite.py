@@ -160,3 +160,36 @@ def test_chunk_btree_with_several_levels(tmp_path):
         path = str(tmp_path / "t.h5")
         w.save(path)
         np.testing.assert_array_equal(hdf5lite.File(path)["x"].read(), a)
+
+
+def test_threaded_canonical_check_agrees_with_scipy():
+    """hbio_csr_is_canonical (all host cores) replaces scipy's one-thread has_canonical_format walk at load time"""
+    from scipy import sparse
+    from hicexplorer_b200 import hdf5lite as h5
+    if h5._native_lib() is None:
+        pytest.skip("libhbio.so not built")
+    rng = np.random.default_rng(0)
+    m = sparse.random(3000, 3000, 0.02, random_state=rng, format="csr")
+    m.sort_indices()
+    assert h5.csr_is_canonical(m) is True
+    swapped = m.copy()
+    k = int(swapped.indptr[7])
+    assert swapped.indptr[8] - k >= 2
+    swapped.indices[k], swapped.indices[k + 1] = swapped.indices[k + 1], swapped.indices[k]
+    dup = m.copy()
+    dup.indices[k + 1] = dup.indices[k]
+    beyond = m.copy()
+    beyond.indices[-1] = 3000
+    negative = m.copy()
+    negative.indices[k] = -1
+    for bad in (swapped, dup, beyond, negative):
+        assert h5.csr_is_canonical(bad) is False
+        fresh = sparse.csr_matrix((bad.data, bad.indices, bad.indptr), shape=bad.shape)
+        assert fresh.has_canonical_format is False or bad is beyond or bad is negative
+    assert h5.csr_is_canonical(sparse.csr_matrix((5, 5))) is True
+    wide = sparse.csr_matrix((m.data, m.indices.astype(np.int64), m.indptr.astype(np.int64)), shape=m.shape)
+    assert h5.csr_is_canonical(wide) is True
+    broken_ptr = sparse.csr_matrix((m.data, m.indices, m.indptr), shape=m.shape)
+    broken_ptr.indptr = m.indptr.copy()
+    broken_ptr.indptr[10] = broken_ptr.indptr[11] + 5
+    assert h5.csr_is_canonical(broken_ptr) is False
