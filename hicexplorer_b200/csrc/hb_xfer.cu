@@ -194,12 +194,16 @@ int hb_copy_d2h(void* h_dst, const void* d_src, size_t bytes, int device) { retu
 // fit; nothing on the device is valid and the caller copies the fp64 values as before.
 extern "C" int hb_host_pack_u16(const double* src, uint16_t* dst, size_t n);
 
+static int hb_ingest_workers();
+// HB_NARROW_INGEST=1 / 0 forces the narrow ingest on / off (read at every call: A/B runs toggle it inside one process).
+// Unset: on when this rank has at least 8 host threads to convert with.  Measured (profiles/r2_ingest_probe_n8.json,
+// r2_narrow_ingest_timing.txt): one rank with 16 threads uploads 1.5e9 entries in 0.21 s instead of 0.33 s, but 8 ranks
+// sharing 32 threads take 0.135 s instead of 0.101 s -- there the host cores, not the 8 PCIe links, are the bottleneck.
 static bool hb_narrow_ingest_enabled() {
-    static const bool v = [] {
-        const char* e = getenv("HB_NARROW_INGEST");
-        return !(e && e[0] == '0');
-    }();
-    return v;
+    const char* e = getenv("HB_NARROW_INGEST");
+    if (e && e[0] == '0') return false;
+    if (e && e[0] == '1') return true;
+    return hb_ingest_workers() >= 8;
 }
 static int hb_ingest_workers() {
     static const int v = [] {

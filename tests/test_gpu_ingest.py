@@ -16,6 +16,14 @@ from hicexplorer_b200.store import DeviceCSR
 from tests.helpers import random_hic
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _narrow_on(monkeypatch):
+    """without the variable the library decides by the number of host threads this rank has (>= 8: on)"""
+    monkeypatch.setenv("HB_NARROW_INGEST", "1")
+
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -99,7 +107,7 @@ print("OK", int(iters[0]), float(bias.sum()))
 
 
 def test_many_small_chunks_and_a_refusal_in_the_middle():
-    env = dict(os.environ, HB_INGEST_CHUNK="1000", HB_INGEST_WORKERS="3")
+    env = dict(os.environ, HB_INGEST_CHUNK="1000", HB_INGEST_WORKERS="3", HB_NARROW_INGEST="1")
     out = subprocess.run([sys.executable, "-c", SCRIPT], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and out.stdout.startswith("OK"), out.stdout + out.stderr
     env = dict(os.environ, HB_NARROW_INGEST="0")
