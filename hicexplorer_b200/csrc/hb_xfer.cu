@@ -197,8 +197,9 @@ extern "C" int hb_host_pack_u16(const double* src, uint16_t* dst, size_t n);
 static int hb_ingest_workers();
 // HB_NARROW_INGEST=1 / 0 forces the narrow ingest on / off (read at every call: A/B runs toggle it inside one process).
 // Unset: on when this rank has at least 8 host threads to convert with.  Measured (profiles/r2_ingest_probe_n8.json,
-// r2_narrow_ingest_timing.txt): one rank with 16 threads uploads 1.5e9 entries in 0.21 s instead of 0.33 s, but 8 ranks
-// sharing 32 threads take 0.135 s instead of 0.101 s -- there the host cores, not the 8 PCIe links, are the bottleneck.
+// r2_narrow_ingest_timing.txt, r2_bench_n4*.json): one rank with 16 threads uploads 1.5e9 entries in 0.21 s instead of
+// 0.33 s; 4 ranks with 8 threads each finish the whole call in 0.159 s instead of 0.183 s; but 8 ranks with 4 threads each
+// take 0.135 s instead of 0.101 s -- there the host cores, not the PCIe links, are the bottleneck.
 static bool hb_narrow_ingest_enabled() {
     const char* e = getenv("HB_NARROW_INGEST");
     if (e && e[0] == '0') return false;
