@@ -12,6 +12,9 @@
 // ascending j] ++ [row i of U].  The lower parts are filled through per-row atomic cursors (arrival order is
 // arbitrary) and then each row's lower part is sorted by column in shared memory (bitonic network, keys are unique),
 // so the final layout -- and with it every later floating-point sum -- is deterministic.
+#include <climits>
+#include <cstdlib>
+
 #include "hb_internal.cuh"
 #include "hb_scan.cuh"
 
@@ -111,6 +114,120 @@ __global__ void hb_sym_sort_kernel(const int64_t* __restrict__ out_ptr, const un
             out_idx[base + i] = (int32_t)(sk[i] >> 32);
             out_val[base + i] = v[q];
         }
+    }
+}
+
+// [r2] The same job without a sorting network.  The keys of a row's lower part are distinct source-row numbers below the
+// row's own, so the sorted position of an entry is its RANK = number of smaller keys = number of set bits below its own
+// in a bitmap of the keys.  One CTA per row; every thread takes E entries (key and value) into registers, then the key
+// range is walked in windows of HB_SYM_WINDOW bits: clear, set one bit per key, popcount prefix over the words (block
+// scan), and every entry of the window is written straight to base + rank -- in place, since everything was read before
+// the first write.  Windows without keys (the gap between the band and a far contact) cost one barrier.  O(L + span/32)
+// per row instead of O(L log^2 L) compare-exchanges behind 78 barriers.
+#define HB_SYM_WINDOW 65536              // bits per window: 8 KB of bitmap + 8 KB of word prefixes
+#define HB_SYM_WWORDS (HB_SYM_WINDOW / 32)
+template <int E, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+hb_sym_rank_kernel(const int64_t* __restrict__ out_ptr, const unsigned int* __restrict__ low_cnt, int64_t n, int P,
+                   int32_t* __restrict__ out_idx, double* __restrict__ out_val) {
+    __shared__ unsigned int bm[HB_SYM_WWORDS];
+    __shared__ unsigned int pre[HB_SYM_WWORDS];
+    __shared__ unsigned int warp_tot[32];
+    __shared__ int s_min, s_max;
+    const int64_t row = blockIdx.x;
+    const int L = (int)low_cnt[row];
+    if (L < 2 || L > P || (P > 32 && L <= P / 2)) return;
+    const int64_t base = out_ptr[row];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = THREADS >> 5;
+    int key[E];
+    double val[E];
+    int kmin = INT_MAX, kmax = -1;
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+        const int i = tid + q * THREADS;
+        key[q] = -1;
+        val[q] = 0.0;
+        if (i < L) {
+            key[q] = out_idx[base + i];
+            val[q] = out_val[base + i];
+            kmin = min(kmin, key[q]);
+            kmax = max(kmax, key[q]);
+        }
+    }
+    if (tid == 0) {
+        s_min = INT_MAX;
+        s_max = -1;
+    }
+    __syncthreads();
+    kmin = __reduce_min_sync(0xffffffffu, kmin);
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
+    if (lane == 0) {
+        atomicMin(&s_min, kmin);
+        atomicMax(&s_max, kmax);
+    }
+    __syncthreads();       // also: every entry of the row is in registers from here on
+    kmin = s_min;
+    kmax = s_max;
+    unsigned int running = 0;
+    for (int w0 = kmin & ~(HB_SYM_WINDOW - 1); w0 <= kmax; w0 += HB_SYM_WINDOW) {
+        bool mine = false;
+#pragma unroll
+        for (int q = 0; q < E; ++q) mine |= key[q] >= w0 && key[q] - w0 < HB_SYM_WINDOW;
+        if (!__syncthreads_or(mine)) continue;
+        const int last = min(kmax - w0, HB_SYM_WINDOW - 1);
+        const int nwords = (last >> 5) + 1;
+        for (int w = tid; w < nwords; w += THREADS) bm[w] = 0u;
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            const int d = key[q] - w0;
+            if (key[q] >= w0 && d < HB_SYM_WINDOW) atomicOr(&bm[d >> 5], 1u << (d & 31));
+        }
+        __syncthreads();
+        // exclusive prefix of the word popcounts: a contiguous slice of words per thread, then a block scan of the slices
+        const int per = (nwords + THREADS - 1) / THREADS;
+        const int wb = tid * per, we = min(wb + per, nwords);
+        unsigned int mysum = 0;
+        for (int w = wb; w < we; ++w) mysum += __popc(bm[w]);
+        unsigned int incl = mysum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned int t = lane < nwarp ? warp_tot[lane] : 0u;
+            unsigned int ti = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int u = __shfl_up_sync(0xffffffffu, ti, o);
+                if (lane >= o) ti += u;
+            }
+            warp_tot[lane] = ti - t;                       // exclusive offsets of the warps
+            if (lane == 31) pre[HB_SYM_WWORDS - 1] = ti;    // parked: the window's total (read before it is overwritten)
+        }
+        __syncthreads();
+        const unsigned int window_total = pre[HB_SYM_WWORDS - 1];
+        unsigned int acc = warp_tot[warp] + incl - mysum;
+        __syncthreads();       // everyone holds window_total before the last word's prefix may replace it
+        for (int w = wb; w < we; ++w) {
+            pre[w] = acc;
+            acc += __popc(bm[w]);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            const int d = key[q] - w0;
+            if (key[q] >= w0 && d < HB_SYM_WINDOW) {
+                const unsigned int r = running + pre[d >> 5] + __popc(bm[d >> 5] & ((1u << (d & 31)) - 1u));
+                out_idx[base + r] = key[q];
+                out_val[base + r] = val[q];
+            }
+        }
+        running += window_total;
+        __syncthreads();       // bm / pre are cleared again by the next window
     }
 }
 
@@ -290,14 +407,33 @@ int hb_csr_symmetrize_upper(hb_csr* h) {
     if (n > 0 && full_nnz > 0) {
         hb_sym_fill_kernel<<<grid, 256, 0, s>>>(h->d_indptr + 0, h->d_indices, h->d_data, n, d_ptr, d_low, d_cursor, d_idx, d_val);
         g_hb_launches.fetch_add(1);
+        // HB_SYM_SORT=network selects the round-1 bitonic network (kept for A/B runs and as a cross-check in the tests)
+        const char* sort_env = getenv("HB_SYM_SORT");
+        const bool use_network = sort_env != nullptr && sort_env[0] == 'n';
         // size classes: P = 32 sorts lower parts of 2..32 entries, P > 32 those of (P/2, P] entries
         for (int P = 32; P <= 16384 && (P == 32 ? flags[1] >= 2u : flags[1] > (unsigned int)(P / 2)); P <<= 1) {
             const size_t smem = sizeof(unsigned long long) * (size_t)P;
-            if (smem > 48 * 1024)
+            if (use_network && smem > 48 * 1024)
                 SY(cudaFuncSetAttribute(hb_sym_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             // P / threads <= HB_SYM_MAX_PER_THREAD (16384 / 1024) for every class
             const int threads = P >= 2048 ? 1024 : (P >= 64 ? P / 2 : 32);
-            hb_sym_sort_kernel<<<(unsigned)n, threads, smem, s>>>(d_ptr, d_low, n, P, d_idx, d_val);
+            if (use_network) {
+                hb_sym_sort_kernel<<<(unsigned)n, threads, smem, s>>>(d_ptr, d_low, n, P, d_idx, d_val);
+            } else {
+                // rank by bitmap: E entries per thread in registers
+                switch (P) {
+                    case 32: hb_sym_rank_kernel<1, 32><<<(unsigned)n, 32, 0, s>>>(d_ptr, d_low, n, P, d_idx, d_val); break;
+                    case 64: hb_sym_rank_kernel<2, 32><<<(unsigned)n, 32, 0, s>>>(d_ptr, d_low, n, P, d_idx, d_val); break;
+                    case 128: hb_sym_rank_kernel<2, 64><<<(unsigned)n, 64, 0, s>>>(d_ptr, d_low, n, P, d_idx, d_val); break;
+                    case 256: hb_sym_rank_kernel<2, 128><<<(unsigned)n, 128, 0, s>>>(d_ptr, d_low, n, P, d_idx, d_val); break;
+                    case 512: hb_sym_rank_kernel<2, 256><<<(unsigned)n, 256, 0, s>>>(d_ptr, d_low, n, P, d_idx, d_val); break;
+                    case 1024: hb_sym_rank_kernel<4, 256><<<(unsigned)n, 256, 0, s>>>(d_ptr, d_low, n, P, d_idx, d_val); break;
+                    case 2048: hb_sym_rank_kernel<8, 256><<<(unsigned)n, 256, 0, s>>>(d_ptr, d_low, n, P, d_idx, d_val); break;
+                    case 4096: hb_sym_rank_kernel<8, 512><<<(unsigned)n, 512, 0, s>>>(d_ptr, d_low, n, P, d_idx, d_val); break;
+                    case 8192: hb_sym_rank_kernel<8, 1024><<<(unsigned)n, 1024, 0, s>>>(d_ptr, d_low, n, P, d_idx, d_val); break;
+                    default: hb_sym_rank_kernel<16, 1024><<<(unsigned)n, 1024, 0, s>>>(d_ptr, d_low, n, P, d_idx, d_val); break;
+                }
+            }
             g_hb_launches.fetch_add(1);
         }
         if (flags[1] > 16384u) {

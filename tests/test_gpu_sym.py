@@ -135,3 +135,37 @@ def test_keep_rows_equals_a_row_block_upload():
             rs_want, dg_want = ref.row_stats()
             np.testing.assert_array_equal(rs_got, rs_want)
             np.testing.assert_array_equal(dg_got, dg_want)
+
+
+def _sym_case(n, seed, band, per_row, far):
+    """upper triangle with a band of `per_row` entries per row within `band` columns plus `far` contacts anywhere"""
+    rng = np.random.default_rng(seed)
+    r = np.repeat(np.arange(n), per_row)
+    c = np.minimum(r + rng.integers(0, band, size=len(r)), n - 1)
+    fr = rng.integers(0, n, size=far)
+    fc = rng.integers(0, n, size=far)
+    r = np.concatenate([r, np.minimum(fr, fc)])
+    c = np.concatenate([c, np.maximum(fr, fc)])
+    v = rng.integers(1, 1000, size=len(r)).astype(np.float64)
+    up = sparse.coo_matrix((v, (r, c)), shape=(n, n)).tocsr()
+    up.sum_duplicates()
+    return up
+
+
+@pytest.mark.parametrize("n,band,per_row,far", [(150000, 3000, 6, 40000),       # keys of one row span several bitmap windows
+                                                 (70000, 66000, 3, 0),           # a band wider than one window
+                                                 (9000, 9000, 700, 0)])          # every size class up to 8192 entries
+def test_rank_ordering_of_the_mirror_image(monkeypatch, n, band, per_row, far):
+    """[r2] the lower parts are ordered by bitmap rank (hb_sym_rank_kernel) instead of a sorting network: same store as
+    scipy's transpose, and as the round-1 network (HB_SYM_SORT=network)"""
+    up = _sym_case(n, 5, band, per_row, far)
+    full = sparse.csr_matrix(up + sparse.triu(up, 1).T)
+    full.sort_indices()
+    with DeviceCSR.from_upper(up) as dev:
+        got = dev.download()
+    assert np.array_equal(got.indptr, full.indptr) and np.array_equal(got.indices, full.indices)
+    np.testing.assert_array_equal(got.data, full.data)
+    monkeypatch.setenv("HB_SYM_SORT", "network")
+    with DeviceCSR.from_upper(up) as dev:
+        ref = dev.download()
+    assert np.array_equal(ref.indices, got.indices) and np.array_equal(ref.data, got.data)
