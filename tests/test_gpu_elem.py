@@ -161,3 +161,38 @@ def test_edge_cases_empty_and_tiny_stores():
         assert dev.nnz == 0
         bias, iters, devn = dev.ice(3, 1e-5)                   # and the store is still usable
         assert np.all(bias == 0.0) or np.all(np.isnan(bias)) or bias.shape == (300,)
+
+
+@pytest.mark.parametrize("n,band,per_row,far", [(150000, 3000, 5, 30000), (70000, 66000, 3, 0), (3000, 3000, 400, 0)])
+def test_add_on_wide_rows(n, band, per_row, far):
+    """rows whose columns span many accumulation windows, partial overlap of the two patterns, cells that cancel,
+    explicit zeros -- against scipy"""
+    rng = np.random.default_rng(n)
+
+    def sym(seed):
+        g = np.random.default_rng(seed)
+        r = np.repeat(np.arange(n), per_row)
+        c = np.minimum(r + g.integers(0, band, size=len(r)), n - 1)
+        fr, fc = g.integers(0, n, size=far), g.integers(0, n, size=far)
+        r, c = np.concatenate([r, np.minimum(fr, fc)]), np.concatenate([c, np.maximum(fr, fc)])
+        v = g.integers(1, 50, size=len(r)).astype(np.float64)
+        up = sparse.coo_matrix((v, (r, c)), shape=(n, n)).tocsr()
+        up.sum_duplicates()
+        m = sparse.csr_matrix(up + sparse.triu(up, 1).T)
+        m.sort_indices()
+        return m
+    a, b = sym(1), sym(2)
+    common = a.multiply(b > 0).tocsr()                       # cells both matrices store (a's values there)
+    common.data[common.data > 10] = 0.0                      # (never compare a sparse matrix with <=: the result is dense)
+    common.eliminate_zeros()
+    bc = b.multiply(common > 0).tocsr()                      # b's values at the chosen cells
+    b = sparse.csr_matrix(b - bc - common)                   # there b = -a now: a + b cancels exactly; pattern of b kept
+    b.sort_indices()
+    a.data[rng.integers(0, a.nnz, size=50)] = 0.0            # explicit zeros that meet nothing, or something
+    want = sparse.csr_matrix(a + b)
+    want.sort_indices()
+    with DeviceCSR.from_scipy(a) as da, DeviceCSR.from_scipy(b) as db:
+        da.add(db)
+        got = da.download()
+    assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
+    np.testing.assert_array_equal(got.data, want.data)
