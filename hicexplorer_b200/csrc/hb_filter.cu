@@ -740,6 +740,12 @@ int hb_scrub(hb_csr* h, int64_t counts[2]) {
     int rc = hb_ensure_state(h);
     if (rc) return rc;
     cudaStream_t s = h->stream;
+    if (h->pack_kind == 1 && h->d_pack != nullptr) {
+        // a current uint16 copy exists (narrow ingest, or hb_csr_pack_values): every value is a finite count, there is
+        // nothing to scrub, and the copy stays valid
+        if (counts) counts[0] = counts[1] = 0;
+        return HB_OK;
+    }
     hb_drop_pack(h);  // the values may change
     HB_CUDA(cudaMemsetAsync(h->d_scalar_bits, 0, sizeof(unsigned long long) * 2, s));
     if (h->nnz > 0) {
