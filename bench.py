@@ -591,8 +591,9 @@ def main():
                          "hb_ice_run_s": max_over_ranks(t_run),
                          "host_bytes_read_per_gpu": 12.0 * nnz_local + 8.0 * (n_rows + 1),
                          "pcie_bytes_per_gpu": float(ingest_bytes.value),
-                         "value_layout_after_create": {0: "fp64 only", 1: "fp64 + uint16 (narrow ingest: counts converted on "
-                                                       "the host, 2 B per entry over PCIe)", 2: "fp64 + float"}[ingest_kind.value],
+                         "value_layout_after_create": {0: "fp64 only", 1: "fp64 + uint16 (narrow ingest: counts converted to uint16 on "
+                                                       "the host cores, 2 B per entry over PCIe; the chunks the cores did not get to "
+                                                       "went as fp64 and were narrowed on the device)", 2: "fp64 + float"}[ingest_kind.value],
                          "untimed_first_use_s": max_over_ranks(t_w),
                          "host_GBps_per_gpu_inside_create": 12.0 * nnz_local / max(t_create, 1e-9) / 1e9,
                          "note": "rank-wise maxima of host timestamps; the upload dominates hb_csr_create (pinned host memory, "

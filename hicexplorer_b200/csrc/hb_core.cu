@@ -235,19 +235,24 @@ int hb_csr_create_typed(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t ro
             h->d_pack = d_pack;
             HB_CREATE_CUDA(cudaMemsetAsync(d_pack, 0, sizeof(uint16_t) * 8, s));
             HB_CREATE_CUDA(cudaStreamSynchronize(s));
-            if (hb_ingest_values(h->d_data + phase, d_pack + phase, data + indptr[0], nnz, device, &narrowed) != HB_OK) {
+            int64_t direct_entries = -1;
+            if (hb_ingest_values(h->d_data + phase, d_pack + phase, data + indptr[0], nnz, device, &narrowed, &direct_entries) !=
+                HB_OK) {
                 return fail_create();
             }
-            if (narrowed) {
-                h->pack_kind = 1;
-                h->h2d_bytes += (int64_t)sizeof(uint16_t) * nnz;
-            } else {
+            if (narrowed) h->pack_kind = 1;
+            else {
                 hb_dfree(h->d_pack);
                 h->d_pack = nullptr;
+            }
+            if (direct_entries < 0) {
+                // not raw counts (or HB_NARROW_INGEST=0): the plain fp64 copy
                 if (hb_copy_h2d(h->d_data + phase, data + indptr[0], sizeof(double) * (size_t)nnz, device) != HB_OK) {
                     return fail_create();
                 }
                 h->h2d_bytes += (int64_t)sizeof(double) * nnz;
+            } else {
+                h->h2d_bytes += (int64_t)sizeof(double) * direct_entries + (int64_t)sizeof(uint16_t) * (nnz - direct_entries);
             }
         } else {
             h->h2d_bytes += (int64_t)(value_kind == HB_VALUES_I64 ? 8 : 4) * nnz;

@@ -206,9 +206,11 @@ void hb_drop_pack(hb_csr* h);
 // multi-threaded staged copies for pageable caller buffers (hb_xfer.cu); synchronous
 int hb_copy_h2d(void* d_dst, const void* h_src, size_t bytes, int device);
 int hb_copy_d2h(void* h_dst, const void* d_src, size_t bytes, int device);
-// fp64 counts -> uint16 on the host, 2 bytes per entry over the bus, both device forms written (hb_xfer.cu); *narrowed = 0
-// when some value does not fit and nothing was kept
-int hb_ingest_values(double* d_data, uint16_t* d_pack, const double* h_src, int64_t nnz, int device, int* narrowed);
+// value upload of hb_csr_create for raw counts (hb_xfer.cu): uint16 over the bus where the host cores keep up, fp64 where
+// they do not.  *direct_entries < 0: nothing was uploaded (the caller copies); otherwise d_data is complete, *direct_entries
+// of its entries crossed the bus as fp64, and *narrowed says whether d_pack holds the uint16 copy of all of them
+int hb_ingest_values(double* d_data, uint16_t* d_pack, const double* h_src, int64_t nnz, int device, int* narrowed,
+                     int64_t* direct_entries);
 // exchange buffer p (0/1) of this rank's symmetric region and its flag array
 static inline double* hb_sym_buf(const hb_csr* h, int p) { return (double*)((unsigned char*)h->pc->d_sym + (size_t)p * h->pc->buf_bytes); }
 static inline unsigned long long* hb_sym_flags(const hb_csr* h, int p) {

@@ -198,29 +198,35 @@ int hb_copy_d2h(void* h_dst, const void* d_src, size_t bytes, int device) { retu
 
 
 // ---- narrow ingest: fp64 counts leave the host as uint16 ------------------------------------------------------
-// hb_csr_create's value upload when every value is an integer in [0, 65535] (raw Hi-C counts): host threads convert
-// chunk after chunk into pinned staging (hb_hostpack.cpp; lossless or refused), 2 bytes per entry cross PCIe, and the
-// device writes both forms it keeps: the uint16 stream of the solver kernels (d_pack) and the fp64 store (d_data).
-// 12 -> 6 bytes per entry over the bus for a CSR block (int32 columns + values).  *narrowed = 0: some value does not
-// fit; nothing on the device is valid and the caller copies the fp64 values as before.
+// hb_csr_create's value upload when the values are raw Hi-C counts (integers in [0, 65535]).  Two ways lead from the
+// caller's fp64 array to the device, and they use different resources:
+//   narrow  host threads convert chunk after chunk to uint16 in pinned staging (hb_hostpack.cpp; lossless or refused),
+//           2 bytes per entry cross PCIe, the device writes the fp64 store (d_data) and keeps the uint16 stream (d_pack);
+//   direct  the chunk is copied as it is, 8 bytes per entry, no host core involved (pinned / registered sources only).
+// Which one is faster depends on how many cores this rank has against how fast its link is (one rank with 16 threads:
+// narrow, 0.19 s instead of 0.33 s for 1.5e9 entries; 8 ranks sharing 32 threads: direct, 0.10 s instead of 0.135 s),
+// so both run at once on the same array: the workers take chunks from the FRONT, a feeder thread takes chunks from the
+// BACK and sends them directly whenever no narrow copy is waiting for the link (= the cores are the bottleneck, not the
+// bus), and they meet wherever the machine puts the balance.  The directly copied tail is converted to uint16 on the
+// device afterwards (one pass over HBM), so the store ends up in the same two layouts either way.
+// A value that does not fit ends the narrow side only: what it has delivered is valid fp64 already, the feeder takes
+// the rest, and *narrowed = 0 tells the caller that no uint16 copy exists.  *direct_entries = entries sent as fp64.
 extern "C" int hb_host_pack_u16(const double* src, uint16_t* dst, size_t n);
 
-static int hb_ingest_workers();
-// HB_NARROW_INGEST=1 / 0 forces the narrow ingest on / off (read at every call: A/B runs toggle it inside one process).
-// Unset: on when this rank has at least 8 host threads to convert with.  Measured (profiles/r2_ingest_probe_n8.json,
-// r2_narrow_ingest_timing.txt, r2_bench_n4*.json): one rank with 16 threads uploads 1.5e9 entries in 0.21 s instead of
-// 0.33 s; 4 ranks with 8 threads each finish the whole call in 0.159 s instead of 0.183 s; but 8 ranks with 4 threads each
-// take 0.135 s instead of 0.101 s -- there the host cores, not the PCIe links, are the bottleneck.
+// HB_NARROW_INGEST=0 switches the narrow side off (everything goes the direct / staged way, as in round 1); read at
+// every call so that A/B runs can toggle it inside one process.  HB_INGEST_DIRECT=0 switches the feeder off.
 static bool hb_narrow_ingest_enabled() {
     const char* e = getenv("HB_NARROW_INGEST");
-    if (e && e[0] == '0') return false;
-    if (e && e[0] == '1') return true;
-    return hb_ingest_workers() >= 8;
+    return !(e && e[0] == '0');
+}
+static bool hb_ingest_feeder_enabled() {
+    const char* e = getenv("HB_INGEST_DIRECT");
+    return !(e && e[0] == '0');
 }
 static int hb_ingest_workers() {
+    const char* e = getenv("HB_INGEST_WORKERS");
+    if (e && atoi(e) > 0) return atoi(e) > 64 ? 64 : atoi(e);
     static const int v = [] {
-        const char* e = getenv("HB_INGEST_WORKERS");
-        if (e && atoi(e) > 0) return atoi(e) > 64 ? 64 : atoi(e);
         int hw = (int)std::thread::hardware_concurrency();
         if (hw <= 0) hw = 8;
         const char* lw = getenv("LOCAL_WORLD_SIZE");          // torchrun: the ranks of this node share the cores
@@ -243,6 +249,21 @@ __global__ void __launch_bounds__(256) hb_expand_u16_kernel(const uint16_t* __re
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) dst[i] = (double)src[i];
+}
+
+// the directly copied entries: fp64 -> uint16 on the device, *bad != 0 if one of them is not a count <= 65535
+__global__ void __launch_bounds__(256)
+hb_narrow_on_device_kernel(const double* __restrict__ src, uint16_t* __restrict__ dst, int64_t n, unsigned int* bad) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    bool b = false;
+    for (; i < n; i += stride) {
+        const double v = src[i];
+        const unsigned int u = (v >= 0.0 && v <= 65535.0) ? (unsigned int)v : 0u;
+        b |= __double_as_longlong((double)u) != __double_as_longlong(v);   // fractions, -0.0, NaN, out of range
+        dst[i] = (uint16_t)u;
+    }
+    if (__any_sync(0xffffffffu, b) && (threadIdx.x & 31) == 0) atomicOr(bad, 1u);
 }
 
 struct HbIngestWorker {
@@ -291,8 +312,14 @@ static cudaError_t hb_ingest_prepare(HbIngestWorker& w, int device, size_t chunk
     return cudaSuccess;
 }
 
-int hb_ingest_values(double* d_data, uint16_t* d_pack, const double* h_src, int64_t nnz, int device, int* narrowed) {
+static void CUDART_CB hb_ingest_copy_done(void* counter) {
+    static_cast<std::atomic<long long>*>(counter)->fetch_add(1, std::memory_order_release);
+}
+
+int hb_ingest_values(double* d_data, uint16_t* d_pack, const double* h_src, int64_t nnz, int device, int* narrowed,
+                     int64_t* direct_entries) {
     *narrowed = 0;
+    *direct_entries = -1;          // -1: nothing was uploaded here, the caller copies the values itself
     if (nnz <= 0 || !hb_narrow_ingest_enabled()) return HB_OK;
     {
         // a first look before any thread or staging buffer is set up: corrected / normalised matrices fail here
@@ -302,14 +329,32 @@ int hb_ingest_values(double* d_data, uint16_t* d_pack, const double* h_src, int6
     }
     std::lock_guard<std::mutex> guard(g_ingest_mutex);
     const size_t chunk = hb_ingest_chunk_entries();
-    const size_t nchunks = ((size_t)nnz + chunk - 1) / chunk;
-    const int workers = (int)std::min<size_t>((size_t)hb_ingest_workers(), nchunks);
-    std::vector<cudaError_t> err((size_t)workers, cudaSuccess);
+    const int64_t nchunks = (int64_t)(((size_t)nnz + chunk - 1) / chunk);
+    const int workers = (int)std::min<int64_t>((int64_t)hb_ingest_workers(), nchunks);
+    const bool feeder_on = hb_ingest_feeder_enabled() && hb_is_device_accessible_host(h_src) && nchunks >= 4;
+    std::vector<cudaError_t> err((size_t)workers + 1, cudaSuccess);
+    // chunks [lo, hi) are unclaimed: the workers take lo++, the feeder takes --hi
+    std::mutex range_mutex;
+    int64_t lo = 0, hi = nchunks;
+    auto take_front = [&]() -> int64_t {
+        std::lock_guard<std::mutex> g(range_mutex);
+        return lo < hi ? lo++ : -1;
+    };
+    auto take_back = [&]() -> int64_t {
+        std::lock_guard<std::mutex> g(range_mutex);
+        return lo < hi ? --hi : -1;
+    };
     std::atomic<bool> refused(false);
+    std::atomic<int> workers_running(workers);
+    std::atomic<long long> issued(0), completed(0);      // narrow copies handed to the copy engine / finished
+    std::vector<int64_t> redo;                           // chunks a worker had claimed when it met a value that does not fit
+    std::mutex redo_mutex;
     std::atomic<uint64_t> launches(0);
     static const bool timing = getenv("HB_INGEST_TIMING") != nullptr;
     std::vector<double> t_prep((size_t)workers, 0.0), t_pack((size_t)workers, 0.0), t_wait((size_t)workers, 0.0),
-        t_issue((size_t)workers, 0.0), t_drain((size_t)workers, 0.0);
+        t_issue((size_t)workers, 0.0);
+    std::vector<int64_t> n_chunks_w((size_t)workers, 0);
+    int64_t n_direct_chunks = 0;
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_begin = now();
     auto work = [&](int t) {
@@ -319,9 +364,10 @@ int hb_ingest_values(double* d_data, uint16_t* d_pack, const double* h_src, int6
         t_prep[(size_t)t] = now() - t0;
         bool used[2] = {false, false};
         int slot = 0;
-        for (size_t c = (size_t)t; c < nchunks && e == cudaSuccess && !refused.load(std::memory_order_relaxed);
-             c += (size_t)workers, slot ^= 1) {
-            const size_t off = c * chunk;
+        while (e == cudaSuccess && !refused.load(std::memory_order_relaxed)) {
+            const int64_t c = take_front();
+            if (c < 0) break;
+            const size_t off = (size_t)c * chunk;
             const size_t len = std::min(chunk, (size_t)nnz - off);
             t0 = now();
             if (used[slot]) e = cudaEventSynchronize(w.done[slot]);   // the staging buffer is reused
@@ -332,40 +378,134 @@ int hb_ingest_values(double* d_data, uint16_t* d_pack, const double* h_src, int6
             t_pack[(size_t)t] += now() - t0;
             if (!ok) {
                 refused.store(true, std::memory_order_relaxed);
+                std::lock_guard<std::mutex> g(redo_mutex);
+                redo.push_back(c);
                 break;
             }
             t0 = now();
+            issued.fetch_add(1, std::memory_order_relaxed);
             e = cudaMemcpyAsync(d_pack + off, w.stage[slot], len * sizeof(uint16_t), cudaMemcpyHostToDevice, w.st);
-            if (e != cudaSuccess) break;
+            if (e == cudaSuccess) e = cudaLaunchHostFunc(w.st, hb_ingest_copy_done, &completed);
+            if (e != cudaSuccess) {
+                completed.fetch_add(1);   // keep the two counters consistent for the feeder
+                break;
+            }
             hb_expand_u16_kernel<<<HB_NUM_SMS * 2, 256, 0, w.st>>>(d_pack + off, d_data + off, (int64_t)len);
             launches.fetch_add(1, std::memory_order_relaxed);
             e = cudaGetLastError();
             if (e == cudaSuccess) e = cudaEventRecord(w.done[slot], w.st);
             used[slot] = true;
+            slot ^= 1;
+            ++n_chunks_w[(size_t)t];
             t_issue[(size_t)t] += now() - t0;
         }
-        t0 = now();
         if (w.st) {   // always drain: the staging buffers outlive this call
             const cudaError_t e2 = cudaStreamSynchronize(w.st);
             if (e == cudaSuccess) e = e2;
         }
-        t_drain[(size_t)t] = now() - t0;
         err[(size_t)t] = e;
+        workers_running.fetch_sub(1, std::memory_order_release);
+    };
+    // the feeder: whole chunks straight from the caller's (pinned) array, at most two in flight, and -- while the narrow
+    // side is still producing -- only when none of its copies is waiting for the link
+    auto feed = [&]() {
+        cudaError_t e = cudaSetDevice(device);
+        cudaStream_t st = nullptr;
+        cudaEvent_t ev[2] = {nullptr, nullptr};   // blocking-sync events: the feeder must not spin on a core the workers need
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+        for (int b = 0; b < 2 && e == cudaSuccess; ++b)
+            e = cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming | cudaEventBlockingSync);
+        int64_t k = 0;
+        while (e == cudaSuccess) {
+            const bool narrow_active = workers_running.load(std::memory_order_acquire) > 0 && !refused.load(std::memory_order_relaxed);
+            if (narrow_active && issued.load(std::memory_order_relaxed) != completed.load(std::memory_order_acquire)) {
+                std::this_thread::sleep_for(std::chrono::microseconds(20));   // a narrow copy is waiting for the link
+                continue;
+            }
+            const int64_t c = take_back();
+            if (c < 0) {
+                if (workers_running.load(std::memory_order_acquire) == 0) break;   // every chunk is claimed and delivered
+                std::this_thread::sleep_for(std::chrono::microseconds(50));
+                continue;
+            }
+            const size_t off = (size_t)c * chunk;
+            const size_t len = std::min(chunk, (size_t)nnz - off);
+            if (k >= 2) e = cudaEventSynchronize(ev[k & 1]);       // two in flight keep the link busy, no more: it is shared
+            if (e == cudaSuccess) e = cudaMemcpyAsync(d_data + off, h_src + off, len * sizeof(double), cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaEventRecord(ev[k & 1], st);
+            ++k;
+            ++n_direct_chunks;
+        }
+        if (st) {
+            const cudaError_t e2 = cudaStreamSynchronize(st);
+            if (e == cudaSuccess) e = e2;
+        }
+        for (int b = 0; b < 2; ++b)
+            if (ev[b]) cudaEventDestroy(ev[b]);
+        if (st) cudaStreamDestroy(st);
+        err[(size_t)workers] = e;
     };
     std::vector<std::thread> pool;
     for (int t = 1; t < workers; ++t) pool.emplace_back(work, t);
+    std::thread feeder;
+    if (feeder_on) feeder = std::thread(feed);
     work(0);
     for (auto& th : pool) th.join();
+    if (feeder.joinable()) feeder.join();
     g_hb_launches.fetch_add(launches.load());
+    for (int t = 0; t <= workers; ++t)
+        if (err[(size_t)t] != cudaSuccess) return hb_cuda_fail(err[(size_t)t], "narrow ingest", __FILE__, __LINE__);
+    // what nobody delivered: the chunk(s) at which a worker met a value that does not fit, and -- without a feeder, or if
+    // the feeder stopped early -- everything still unclaimed
+    int64_t direct = n_direct_chunks;   // in chunks, converted to entries below
+    std::vector<int64_t> rest(redo);
+    for (int64_t c : redo) {
+        const size_t off = (size_t)c * chunk;
+        const size_t len = std::min(chunk, (size_t)nnz - off);
+        if (hb_copy_h2d(d_data + off, h_src + off, len * sizeof(double), device) != HB_OK) return HB_ERR_CUDA;
+        ++direct;
+    }
+    if (lo < hi) {   // one contiguous stretch
+        const size_t off = (size_t)lo * chunk;
+        const size_t end = std::min((size_t)hi * chunk, (size_t)nnz);
+        if (hb_copy_h2d(d_data + off, h_src + off, (end - off) * sizeof(double), device) != HB_OK) return HB_ERR_CUDA;
+        for (int64_t c = lo; c < hi; ++c) rest.push_back(c);
+        direct += hi - lo;
+    }
+    // entries that went over the bus as fp64: whole chunks, the last chunk of the array may be short
+    int64_t direct_n = direct * (int64_t)chunk;
+    {
+        const bool last_is_direct = hi < nchunks || std::find(rest.begin(), rest.end(), nchunks - 1) != rest.end();
+        if (last_is_direct && direct > 0) direct_n -= (int64_t)nchunks * (int64_t)chunk - nnz;
+    }
+    *direct_entries = direct_n;
+    bool ok = !refused.load();
+    if (ok && hi < nchunks) {
+        // the feeder's share is the tail [hi * chunk, nnz): make its uint16 copy on the device
+        const size_t off = (size_t)hi * chunk;
+        unsigned int* d_bad = nullptr;
+        unsigned int bad = 0;
+        HB_CUDA(hb_dmalloc(&d_bad, sizeof(unsigned int)));
+        cudaError_t e = cudaMemset(d_bad, 0, sizeof(unsigned int));
+        if (e == cudaSuccess) {
+            hb_narrow_on_device_kernel<<<HB_NUM_SMS * 8, 256>>>(d_data + off, d_pack + off, (int64_t)((size_t)nnz - off), d_bad);
+            g_hb_launches.fetch_add(1);
+            e = cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost);
+        }
+        hb_dfree(d_bad);
+        HB_CUDA(e);
+        ok = bad == 0;
+    }
+    *narrowed = ok ? 1 : 0;
     if (timing) {
         auto mx = [](const std::vector<double>& v) { return *std::max_element(v.begin(), v.end()); };
-        fprintf(stderr, "[hb ingest] %lld entries, %d workers, %zu chunks: total %.1f ms | per worker (max) prepare %.1f, "
-                        "convert %.1f, wait for staging %.1f, issue %.1f, drain %.1f ms\n",
-                (long long)nnz, workers, nchunks, 1e3 * (now() - t_begin), 1e3 * mx(t_prep), 1e3 * mx(t_pack), 1e3 * mx(t_wait),
-                1e3 * mx(t_issue), 1e3 * mx(t_drain));
+        int64_t narrow_chunks = 0;
+        for (int64_t c : n_chunks_w) narrow_chunks += c;
+        fprintf(stderr, "[hb ingest] %lld entries, %lld chunks: %lld narrow (%d workers), %lld direct%s: total %.1f ms | per worker "
+                        "(max) prepare %.1f, convert %.1f, wait for staging %.1f, issue %.1f ms\n",
+                (long long)nnz, (long long)nchunks, (long long)narrow_chunks, workers, (long long)direct,
+                ok ? "" : " (some value is not a small count: no uint16 copy)", 1e3 * (now() - t_begin), 1e3 * mx(t_prep),
+                1e3 * mx(t_pack), 1e3 * mx(t_wait), 1e3 * mx(t_issue));
     }
-    for (int t = 0; t < workers; ++t)
-        if (err[(size_t)t] != cudaSuccess) return hb_cuda_fail(err[(size_t)t], "narrow ingest", __FILE__, __LINE__);
-    *narrowed = refused.load() ? 0 : 1;
     return HB_OK;
 }

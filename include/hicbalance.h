@@ -190,10 +190,11 @@ HB_API int hb_row_stats_cis(hb_csr* h, double* row_sum, double* diag);
 HB_API int hb_csr_pack_values(hb_csr* h, int* kind_out);
 /* hb_csr_create does the same on the way in when it can: fp64 values that are all integer counts <= 65535 are
  * converted to uint16 by host threads while still in host memory (bit-exact round trip or refused), 2 bytes per entry
- * cross PCIe instead of 8, and the device writes both the uint16 copy (kind 1) and the fp64 store from them
- * (HB_NARROW_INGEST=1 / 0 forces it on / off; by default it is used when the calling rank has >= 8 host threads, i.e.
- * when converting is faster than sending: with 8 ranks sharing the cores of one node the plain copy wins).  hb_csr_ingest_info: the layout a store currently has and the bytes its
- * creation moved from host to device. */
+ * cross PCIe instead of 8, and the device writes both the uint16 copy (kind 1) and the fp64 store from them.  With a
+ * pinned source a feeder thread sends chunks from the other end of the array as they are whenever the link would
+ * otherwise wait for the converters (few cores per rank), and that part is narrowed on the device.
+ * HB_NARROW_INGEST=0 switches the whole mechanism off, HB_INGEST_DIRECT=0 the feeder.  hb_csr_ingest_info: the layout a
+ * store currently has and the bytes its creation moved from host to device. */
 HB_API int hb_csr_ingest_info(const hb_csr* h, int* pack_kind, int64_t* h2d_bytes);
 HB_API int hb_row_stats(hb_csr* h, double* row_sum, double* diag);
 HB_API int hb_mad_filter(hb_csr* h, double lo, double hi, uint8_t* mask_out, double* zscore_out,

@@ -114,3 +114,58 @@ def test_many_small_chunks_and_a_refusal_in_the_middle():
     ref = subprocess.run([sys.executable, "-c", SCRIPT.replace("assert info(dev) == 1", "assert info(dev) == 0")], env=env,
                          capture_output=True, text=True, timeout=600)
     assert ref.returncode == 0 and ref.stdout == out.stdout, ref.stdout + ref.stderr     # same iterations, same bias sum
+
+
+FEEDER_SCRIPT = r"""
+import ctypes, numpy as np, sys, torch
+sys.path.insert(0, %r)
+from scipy import sparse
+from hicexplorer_b200 import _lib
+from hicexplorer_b200.store import DeviceCSR
+from tests.helpers import random_hic
+m = random_hic(2500, 0.06, 2, integer=True)
+def pinned(a):
+    t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0].copy()).dtype, pin_memory=True)
+    t.numpy()[...] = a
+    return t
+keep = []
+def pinned_csr(m):
+    d, i, p = pinned(m.data), pinned(m.indices), pinned(m.indptr)
+    keep.extend([d, i, p])
+    return sparse.csr_matrix((d.numpy(), i.numpy(), p.numpy()), shape=m.shape)
+def info(dev):
+    k, b = ctypes.c_int(-1), ctypes.c_int64(-1)
+    _lib.check(_lib.lib().hb_csr_ingest_info(dev.handle, ctypes.byref(k), ctypes.byref(b)))
+    return k.value, b.value
+mp = pinned_csr(m)
+fixed = 8 * (m.shape[0] + 1) + 4 * m.nnz
+shares = []
+for rep in range(3):
+    with DeviceCSR.from_scipy(mp) as dev:
+        kind, nbytes = info(dev)
+        got = dev.download()
+        bias, iters, _ = dev.ice(30, 1e-6)
+    assert kind == 1
+    assert fixed + 2 * m.nnz <= nbytes <= fixed + 8 * m.nnz and (nbytes - fixed - 2 * m.nnz) %% 6 == 0
+    shares.append((nbytes - fixed - 2 * m.nnz) // 6)        # entries that went as fp64
+    assert np.array_equal(got.data.view(np.uint64), m.data.view(np.uint64)) and np.array_equal(got.indices, m.indices)
+for pos in (700, m.nnz // 3, m.nnz - 5000, m.nnz - 700):    # refused by a worker (front) or by the device pass (tail)
+    b = m.copy(); b.data[pos] = 0.25
+    with DeviceCSR.from_scipy(pinned_csr(b)) as dev:
+        kind, nbytes = info(dev)
+        got = dev.download()
+    assert kind == 0 and fixed + 2 * m.nnz <= nbytes <= fixed + 8 * m.nnz
+    assert np.array_equal(got.data.view(np.uint64), b.data.view(np.uint64))
+print("OK", int(iters[0]), float(bias.sum()), "direct entries per run:", shares)
+""" % ROOT
+
+
+def test_direct_feeder_shares_the_upload_with_the_narrow_side():
+    """pinned source, one slow converter thread, small chunks: the feeder takes a share of the chunks from the back and
+    sends them as fp64; the store and the uint16 copy must come out the same, refusals included"""
+    env = dict(os.environ, HB_INGEST_CHUNK="1000", HB_INGEST_WORKERS="1", HB_NARROW_INGEST="1")
+    out = subprocess.run([sys.executable, "-c", FEEDER_SCRIPT], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and out.stdout.startswith("OK"), out.stdout + out.stderr
+    ref = subprocess.run([sys.executable, "-c", SCRIPT], env=dict(os.environ, HB_NARROW_INGEST="1", HB_INGEST_CHUNK="1000"),
+                         capture_output=True, text=True, timeout=600)
+    assert ref.returncode == 0 and ref.stdout.split()[1:3] == out.stdout.split()[1:3], ref.stdout + ref.stderr + out.stdout

@@ -53,8 +53,10 @@ for kind in kinds:
     ixv[:] = cols[None, :]
     ixv += (torch.arange(n, dtype=torch.int32) % (n - per_row))[:, None]
     dav[:] = (cols % 1000).to(torch.float64)[None, :]
-    for narrow in ("1", "0", "1", "0"):
+    modes = [("1", "1"), ("1", "0"), ("0", "0")] * 2       # (narrow side, direct feeder): hybrid, narrow only, plain copy
+    for narrow, direct in modes:
         os.environ["HB_NARROW_INGEST"] = narrow
+        os.environ["HB_INGEST_DIRECT"] = direct
         times = []
         for rep in range(3):
             h = ctypes.c_void_p()
@@ -67,7 +69,9 @@ for kind in kinds:
             k, b = ctypes.c_int(), ctypes.c_int64()
             L.hb_csr_ingest_info(h, ctypes.byref(k), ctypes.byref(b))
             L.hb_csr_destroy(h)
-        res.setdefault(kind, []).append({"narrow": narrow == "1", "create_s": [round(t, 4) for t in times], "layout": k.value,
+        res.setdefault(kind, []).append({"mode": {"11": "hybrid", "10": "narrow only", "00": "plain copy"}[narrow + direct],
+                                         "workers": os.environ.get("HB_INGEST_WORKERS", "auto"),
+                                         "create_s": [round(t, 4) for t in times], "layout": k.value,
                                          "pcie_GB_per_gpu": round(b.value / 1e9, 2),
                                          "host_GBps_aggregate": round(12.0 * nnz * world / min(times) / 1e9, 1)})
     del ix, da, ixv, dav
