@@ -212,6 +212,7 @@ int hb_csr_create_typed(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t ro
     if (nnz > 0) {
         // int32 column ids go over the bus from a second host thread while this one deals with the values
         int idx_rc = HB_OK;
+        std::atomic<bool> idx_done(indices_i64 != 0);   // int64 ids are narrowed after the values, nothing runs beside them
         auto fail_create = [&]() {
             if (idx_thread.joinable()) idx_thread.join();
             hb_csr_destroy(h);
@@ -225,6 +226,7 @@ int hb_csr_create_typed(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t ro
                              ? hb_copy_h2d(h->d_indices + phase, (const int32_t*)indices + indptr[0], sizeof(int32_t) * (size_t)nnz, device)
                              : HB_ERR_CUDA;
                 t_idx = now() - t0;
+                idx_done.store(true, std::memory_order_release);
             });
         h->h2d_bytes = (int64_t)sizeof(int64_t) * (n_rows + 1) + (int64_t)(indices_i64 ? 8 : 4) * nnz;
         if (value_kind == HB_VALUES_F64) {
@@ -236,8 +238,8 @@ int hb_csr_create_typed(hb_csr** out, int64_t n_rows, int64_t n_cols, int64_t ro
             HB_CREATE_CUDA(cudaMemsetAsync(d_pack, 0, sizeof(uint16_t) * 8, s));
             HB_CREATE_CUDA(cudaStreamSynchronize(s));
             int64_t direct_entries = -1;
-            if (hb_ingest_values(h->d_data + phase, d_pack + phase, data + indptr[0], nnz, device, &narrowed, &direct_entries) !=
-                HB_OK) {
+            if (hb_ingest_values(h->d_data + phase, d_pack + phase, data + indptr[0], nnz, device, &narrowed, &direct_entries,
+                                 &idx_done) != HB_OK) {
                 return fail_create();
             }
             if (narrowed) h->pack_kind = 1;

@@ -210,7 +210,7 @@ int hb_copy_d2h(void* h_dst, const void* d_src, size_t bytes, int device);
 // they do not.  *direct_entries < 0: nothing was uploaded (the caller copies); otherwise d_data is complete, *direct_entries
 // of its entries crossed the bus as fp64, and *narrowed says whether d_pack holds the uint16 copy of all of them
 int hb_ingest_values(double* d_data, uint16_t* d_pack, const double* h_src, int64_t nnz, int device, int* narrowed,
-                     int64_t* direct_entries);
+                     int64_t* direct_entries, const std::atomic<bool>* other_upload_done);
 // exchange buffer p (0/1) of this rank's symmetric region and its flag array
 static inline double* hb_sym_buf(const hb_csr* h, int p) { return (double*)((unsigned char*)h->pc->d_sym + (size_t)p * h->pc->buf_bytes); }
 static inline unsigned long long* hb_sym_flags(const hb_csr* h, int p) {

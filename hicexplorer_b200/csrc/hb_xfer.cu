@@ -206,22 +206,28 @@ int hb_copy_d2h(void* h_dst, const void* d_src, size_t bytes, int device) { retu
 // Which one is faster depends on how many cores this rank has against how fast its link is (one rank with 16 threads:
 // narrow, 0.19 s instead of 0.33 s for 1.5e9 entries; 8 ranks sharing 32 threads: direct, 0.10 s instead of 0.135 s),
 // so both run at once on the same array: the workers take chunks from the FRONT, a feeder thread takes chunks from the
-// BACK and sends them directly whenever no narrow copy is waiting for the link (= the cores are the bottleneck, not the
-// bus), and they meet wherever the machine puts the balance.  The directly copied tail is converted to uint16 on the
+// BACK and sends them directly once the column ids are through and as long as no worker finds its staging buffer still
+// waiting for the link (= the cores are the bottleneck, not the bus), and they meet wherever the machine puts the balance.  The directly copied tail is converted to uint16 on the
 // device afterwards (one pass over HBM), so the store ends up in the same two layouts either way.
 // A value that does not fit ends the narrow side only: what it has delivered is valid fp64 already, the feeder takes
 // the rest, and *narrowed = 0 tells the caller that no uint16 copy exists.  *direct_entries = entries sent as fp64.
 extern "C" int hb_host_pack_u16(const double* src, uint16_t* dst, size_t n);
 
 // HB_NARROW_INGEST=0 switches the narrow side off (everything goes the direct / staged way, as in round 1); read at
-// every call so that A/B runs can toggle it inside one process.  HB_INGEST_DIRECT=0 switches the feeder off.
+// every call so that A/B runs can toggle it inside one process.
 static bool hb_narrow_ingest_enabled() {
     const char* e = getenv("HB_NARROW_INGEST");
     return !(e && e[0] == '0');
 }
-static bool hb_ingest_feeder_enabled() {
+// HB_INGEST_DIRECT=1 / 0 forces the feeder on / off.  Unset: on when this rank converts with at most 8 threads.  With 16
+// threads on one GPU the converters alone keep the link busy and the feeder's 8-byte entries only compete with them for
+// host memory bandwidth (measured: 0.175 s without, 0.175-0.21 s with); with 8 / 4 / 2 threads it is what makes the
+// upload 0.127 / 0.149 / 0.167 s instead of 0.152 / 0.235 / 0.40 s (9.6 GB of values, tools/ingest_probe.py).
+static bool hb_ingest_feeder_enabled(int workers) {
     const char* e = getenv("HB_INGEST_DIRECT");
-    return !(e && e[0] == '0');
+    if (e && e[0] == '0') return false;
+    if (e && e[0] == '1') return true;
+    return workers <= 8;
 }
 static int hb_ingest_workers() {
     const char* e = getenv("HB_INGEST_WORKERS");
@@ -312,12 +318,8 @@ static cudaError_t hb_ingest_prepare(HbIngestWorker& w, int device, size_t chunk
     return cudaSuccess;
 }
 
-static void CUDART_CB hb_ingest_copy_done(void* counter) {
-    static_cast<std::atomic<long long>*>(counter)->fetch_add(1, std::memory_order_release);
-}
-
 int hb_ingest_values(double* d_data, uint16_t* d_pack, const double* h_src, int64_t nnz, int device, int* narrowed,
-                     int64_t* direct_entries) {
+                     int64_t* direct_entries, const std::atomic<bool>* other_upload_done) {
     *narrowed = 0;
     *direct_entries = -1;          // -1: nothing was uploaded here, the caller copies the values itself
     if (nnz <= 0 || !hb_narrow_ingest_enabled()) return HB_OK;
@@ -331,7 +333,7 @@ int hb_ingest_values(double* d_data, uint16_t* d_pack, const double* h_src, int6
     const size_t chunk = hb_ingest_chunk_entries();
     const int64_t nchunks = (int64_t)(((size_t)nnz + chunk - 1) / chunk);
     const int workers = (int)std::min<int64_t>((int64_t)hb_ingest_workers(), nchunks);
-    const bool feeder_on = hb_ingest_feeder_enabled() && hb_is_device_accessible_host(h_src) && nchunks >= 4;
+    const bool feeder_on = hb_ingest_feeder_enabled(hb_ingest_workers()) && hb_is_device_accessible_host(h_src) && nchunks >= 4;
     std::vector<cudaError_t> err((size_t)workers + 1, cudaSuccess);
     // chunks [lo, hi) are unclaimed: the workers take lo++, the feeder takes --hi
     std::mutex range_mutex;
@@ -346,7 +348,8 @@ int hb_ingest_values(double* d_data, uint16_t* d_pack, const double* h_src, int6
     };
     std::atomic<bool> refused(false);
     std::atomic<int> workers_running(workers);
-    std::atomic<long long> issued(0), completed(0);      // narrow copies handed to the copy engine / finished
+    std::atomic<int> link_waiters(0);                    // workers whose staging buffer is still waiting for the link
+    std::atomic<long long> convert_us(0), blocked_us(0); // what the workers have spent converting / waiting for the link
     std::vector<int64_t> redo;                           // chunks a worker had claimed when it met a value that does not fit
     std::mutex redo_mutex;
     std::atomic<uint64_t> launches(0);
@@ -355,6 +358,7 @@ int hb_ingest_values(double* d_data, uint16_t* d_pack, const double* h_src, int6
         t_issue((size_t)workers, 0.0);
     std::vector<int64_t> n_chunks_w((size_t)workers, 0);
     int64_t n_direct_chunks = 0;
+    long long held[3] = {0, 0, 0};   // feeder polls that found: column ids still going / workers mostly waiting / a worker waiting
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_begin = now();
     auto work = [&](int t) {
@@ -370,12 +374,22 @@ int hb_ingest_values(double* d_data, uint16_t* d_pack, const double* h_src, int6
             const size_t off = (size_t)c * chunk;
             const size_t len = std::min(chunk, (size_t)nnz - off);
             t0 = now();
-            if (used[slot]) e = cudaEventSynchronize(w.done[slot]);   // the staging buffer is reused
-            t_wait[(size_t)t] += now() - t0;
+            if (used[slot] && cudaEventQuery(w.done[slot]) == cudaErrorNotReady) {
+                // the staging buffer is reused and its copy has not gone out yet: the link is the bottleneck right now --
+                // the feeder holds back while any worker is in this state
+                link_waiters.fetch_add(1, std::memory_order_relaxed);
+                e = cudaEventSynchronize(w.done[slot]);
+                link_waiters.fetch_sub(1, std::memory_order_relaxed);
+            }
+            const double dt_wait = now() - t0;
+            t_wait[(size_t)t] += dt_wait;
             if (e != cudaSuccess) break;
             t0 = now();
             const bool ok = hb_host_pack_u16(h_src + off, w.stage[slot], len) != 0;
-            t_pack[(size_t)t] += now() - t0;
+            const double dt_pack = now() - t0;
+            t_pack[(size_t)t] += dt_pack;
+            blocked_us.fetch_add((long long)(dt_wait * 1e6), std::memory_order_relaxed);
+            convert_us.fetch_add((long long)(dt_pack * 1e6), std::memory_order_relaxed);
             if (!ok) {
                 refused.store(true, std::memory_order_relaxed);
                 std::lock_guard<std::mutex> g(redo_mutex);
@@ -383,13 +397,8 @@ int hb_ingest_values(double* d_data, uint16_t* d_pack, const double* h_src, int6
                 break;
             }
             t0 = now();
-            issued.fetch_add(1, std::memory_order_relaxed);
             e = cudaMemcpyAsync(d_pack + off, w.stage[slot], len * sizeof(uint16_t), cudaMemcpyHostToDevice, w.st);
-            if (e == cudaSuccess) e = cudaLaunchHostFunc(w.st, hb_ingest_copy_done, &completed);
-            if (e != cudaSuccess) {
-                completed.fetch_add(1);   // keep the two counters consistent for the feeder
-                break;
-            }
+            if (e != cudaSuccess) break;
             hb_expand_u16_kernel<<<HB_NUM_SMS * 2, 256, 0, w.st>>>(d_pack + off, d_data + off, (int64_t)len);
             launches.fetch_add(1, std::memory_order_relaxed);
             e = cudaGetLastError();
@@ -416,10 +425,31 @@ int hb_ingest_values(double* d_data, uint16_t* d_pack, const double* h_src, int6
         for (int b = 0; b < 2 && e == cudaSuccess; ++b)
             e = cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming | cudaEventBlockingSync);
         int64_t k = 0;
+        double win_t0 = now();
+        long long win_conv = 0, win_blk = 0;
+        bool link_bound = false;
         while (e == cudaSuccess) {
             const bool narrow_active = workers_running.load(std::memory_order_acquire) > 0 && !refused.load(std::memory_order_relaxed);
-            if (narrow_active && issued.load(std::memory_order_relaxed) != completed.load(std::memory_order_acquire)) {
-                std::this_thread::sleep_for(std::chrono::microseconds(20));   // a narrow copy is waiting for the link
+            // the link has room for 8-byte entries only when nothing else is queueing for it: the column ids (their copy
+            // always has pieces in flight until it is done) and the narrow copies
+            const bool ids_pending = other_upload_done != nullptr && !other_upload_done->load(std::memory_order_acquire);
+            // ... and only while the workers spend their time converting, not waiting: when more than a tenth of the last
+            // few milliseconds went into waiting for staging buffers, the link is the bottleneck and every 8-byte entry
+            // makes it worse.  (Windows start once the column ids are through: behind them everybody waits.)
+            if (ids_pending) {
+                win_t0 = now();
+                win_conv = convert_us.load(std::memory_order_relaxed);
+                win_blk = blocked_us.load(std::memory_order_relaxed);
+            } else if (now() - win_t0 > 3e-3) {
+                const long long cv = convert_us.load(std::memory_order_relaxed), bl = blocked_us.load(std::memory_order_relaxed);
+                link_bound = 10 * (bl - win_blk) > (cv - win_conv);
+                win_t0 = now();
+                win_conv = cv;
+                win_blk = bl;
+            }
+            if (narrow_active && (ids_pending || link_bound || link_waiters.load(std::memory_order_relaxed) > 0)) {
+                ++held[ids_pending ? 0 : (link_bound ? 1 : 2)];
+                std::this_thread::sleep_for(std::chrono::microseconds(50));
                 continue;
             }
             const int64_t c = take_back();
@@ -502,10 +532,12 @@ int hb_ingest_values(double* d_data, uint16_t* d_pack, const double* h_src, int6
         int64_t narrow_chunks = 0;
         for (int64_t c : n_chunks_w) narrow_chunks += c;
         fprintf(stderr, "[hb ingest] %lld entries, %lld chunks: %lld narrow (%d workers), %lld direct%s: total %.1f ms | per worker "
-                        "(max) prepare %.1f, convert %.1f, wait for staging %.1f, issue %.1f ms\n",
+                        "(max) prepare %.1f, convert %.1f, wait for staging %.1f, issue %.1f ms | all workers: converting %.1f, "
+                        "waiting %.1f ms | feeder held back %lld / %lld / %lld times (ids / link-bound / waiter)\n",
                 (long long)nnz, (long long)nchunks, (long long)narrow_chunks, workers, (long long)direct,
                 ok ? "" : " (some value is not a small count: no uint16 copy)", 1e3 * (now() - t_begin), 1e3 * mx(t_prep),
-                1e3 * mx(t_pack), 1e3 * mx(t_wait), 1e3 * mx(t_issue));
+                1e3 * mx(t_pack), 1e3 * mx(t_wait), 1e3 * mx(t_issue), 1e-3 * (double)convert_us.load(), 1e-3 * (double)blocked_us.load(),
+                held[0], held[1], held[2]);
     }
     return HB_OK;
 }

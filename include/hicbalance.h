@@ -193,7 +193,8 @@ HB_API int hb_csr_pack_values(hb_csr* h, int* kind_out);
  * cross PCIe instead of 8, and the device writes both the uint16 copy (kind 1) and the fp64 store from them.  With a
  * pinned source a feeder thread sends chunks from the other end of the array as they are whenever the link would
  * otherwise wait for the converters (few cores per rank), and that part is narrowed on the device.
- * HB_NARROW_INGEST=0 switches the whole mechanism off, HB_INGEST_DIRECT=0 the feeder.  hb_csr_ingest_info: the layout a
+ * HB_NARROW_INGEST=0 switches the whole mechanism off; HB_INGEST_DIRECT=1 / 0 forces the feeder on / off (default: on
+ * when the rank converts with at most 8 host threads).  hb_csr_ingest_info: the layout a
  * store currently has and the bytes its creation moved from host to device. */
 HB_API int hb_csr_ingest_info(const hb_csr* h, int* pack_kind, int64_t* h2d_bytes);
 HB_API int hb_row_stats(hb_csr* h, double* row_sum, double* diag);

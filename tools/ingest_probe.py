@@ -53,7 +53,7 @@ for kind in kinds:
     ixv[:] = cols[None, :]
     ixv += (torch.arange(n, dtype=torch.int32) % (n - per_row))[:, None]
     dav[:] = (cols % 1000).to(torch.float64)[None, :]
-    modes = [("1", "1"), ("1", "0"), ("0", "0")] * 2       # (narrow side, direct feeder): hybrid, narrow only, plain copy
+    modes = [("1", "1"), ("1", "0"), ("0", "0")] * 2       # (narrow side, direct feeder forced on / off): hybrid, narrow only, plain copy
     for narrow, direct in modes:
         os.environ["HB_NARROW_INGEST"] = narrow
         os.environ["HB_INGEST_DIRECT"] = direct
