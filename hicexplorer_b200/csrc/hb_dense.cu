@@ -7,6 +7,8 @@
 // `X -= avg[:, None]; c = dot(X, X.T); c *= 1/fact`; np.corrcoef: `c /= stddev[:, None]; c /= stddev[None, :]`, clip).
 #include <dlfcn.h>
 
+#include <mutex>
+
 #include "hb_internal.cuh"
 
 namespace {
@@ -28,9 +30,8 @@ struct Cublas {
 
 Cublas* load_cublas() {
     static Cublas api;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    static std::once_flag once;
+    std::call_once(once, [] {
         const char* names[] = {"libcublas.so.12", "libcublas.so", "/usr/local/cuda/lib64/libcublas.so.12",
                                "/usr/local/cuda/lib64/libcublas.so"};
         for (const char* nm : names) {
@@ -43,7 +44,7 @@ Cublas* load_cublas() {
             api.set_stream = (cublasSetStream_t)dlsym(api.lib, "cublasSetStream_v2");
             api.dgemm = (cublasDgemm_t)dlsym(api.lib, "cublasDgemm_v2");
         }
-    }
+    });
     return (api.lib && api.create && api.destroy && api.set_stream && api.dgemm) ? &api : nullptr;
 }
 

@@ -57,8 +57,15 @@ def iterativeCorrection(matrix, v=None, M=50, tolerance=1e-5, verbose=False, dev
         if m is not matrix and m.dtype.kind == "f":
             m.data[np.isnan(m.data)] = 0
         dev, m = DeviceCSR.from_scipy_as_uploaded(m, device=device)
+    # the result is a matrix of its own, like the reference's (new index arrays): they are copied on a helper thread while the
+    # device checks the symmetry, iterates and emits
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(max_workers=1)
+    index_copy = pool.submit(lambda: (parallel_copy(m.indices), m.indptr.copy()))
+    pool.shutdown(wait=False)
     with dev:
         if dev.symmetry_ratio() > 1e-10:
+            index_copy.result()
             raise ValueError("Please provide symmetric matrix!")
         log.info("starting iterative correction")
         dev.pack_values()      # lossless narrow copy of integer counts for the streaming kernel; results unchanged
@@ -80,7 +87,8 @@ def iterativeCorrection(matrix, v=None, M=50, tolerance=1e-5, verbose=False, dev
         except _lib.OverflowFinal:
             log.error(_MSG_FINAL)
             raise SystemExit(1)
-    corrected = sparse.csr_matrix((values, parallel_copy(m.indices), m.indptr.copy()), shape=m.shape)
+    indices, indptr = index_copy.result()
+    corrected = sparse.csr_matrix((values, indices, indptr), shape=m.shape)
     return corrected, bias
 
 
